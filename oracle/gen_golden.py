@@ -1,0 +1,280 @@
+"""
+TEST INFRASTRUCTURE -- build-container only.
+
+Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/refshim.py) under np.random.seed(...)
+while recording every draw it takes from numpy's global stream.  Each fixture
+holds the injected stream (normals + uniforms) and the chain the reference
+produced from it; the numpy port (oracle/riemann_port.py) and the CUDA engine
+both replay the stream and must reproduce the chain.
+
+    python -m oracle.gen_golden            # rewrites every fixture
+
+The fixtures are committed; /root/reference does not exist on the GPU box.
+"""
+import os
+import sys
+
+import numpy as np
+
+from oracle import refshim
+from oracle import riemann_port as port
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                          "tests", "golden")
+LANES = 16
+
+
+def _run_recorded(R, sampler, T):
+    """Run T reference steps; return per-step draw logs + proposals."""
+    props, prop_lp = [], []
+    model = sampler.model
+    orig = model.log_posterior
+
+    def rec_lp(theta):
+        v = orig(theta)
+        props.append(theta)
+        prop_lp.append(v)
+        return v
+
+    model.log_posterior = rec_lp           # instance attribute; reference code untouched
+    steps = []
+    try:
+        with refshim.quiet(), refshim.RecordingRNG() as rec:
+            for _ in range(T):
+                a = rec.mark()
+                sampler.sample()
+                steps.append(rec.log[a:rec.mark()])
+    finally:
+        del model.log_posterior
+    return steps, props, np.array(prop_lp, dtype=np.float64)
+
+
+def _vector_fixture(R, name, model, proposal, theta0, T, seed, extra=None, track_scale=False):
+    np.random.seed(seed)
+    sampler = R.Sampler(model, proposal, theta0)
+    d = len(np.atleast_1d(theta0))
+    scales = [getattr(proposal, "scale", 1.0)]
+    if track_scale:
+        orig_adapt = proposal.adapt
+
+        def adapt(theta):
+            orig_adapt(theta)
+            scales.append(proposal.scale)
+        proposal.adapt = adapt
+    steps, props, prop_lp = _run_recorded(R, sampler, T)
+    xi = np.zeros((T, d))
+    u = np.zeros(T)
+    for t, log in enumerate(steps):
+        assert [k for k, _ in log] == ["normal", "uniform"], log
+        xi[t] = log[0][1]
+        u[t] = float(log[1][1])
+    out = dict(xi=xi, u=u,
+               thetas=np.array([np.atleast_1d(th) for th in sampler._chain_thetas], dtype=np.float64),
+               logpost=np.array(sampler._chain_logpost, dtype=np.float64),
+               prop_thetas=np.array([np.atleast_1d(p) for p in props], dtype=np.float64),
+               prop_logpost=prop_lp, seed=np.int64(seed))
+    if track_scale:
+        out["scales"] = np.array(scales, dtype=np.float64)
+        out["accept_rate"] = np.float64(proposal.accept_rate)
+    if extra:
+        out.update(extra)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    acc = np.mean(np.any(out["thetas"][1:] != out["thetas"][:-1], axis=1))
+    print("%-28s T=%d d=%d accept=%.3f" % (name, T, d, acc))
+
+
+def _cp_pack_state(theta, lanes=LANES):
+    k = len(theta.cpx)
+    cpx = np.zeros(lanes)
+    cpv = np.zeros(lanes)
+    cpx[:k] = theta.cpx
+    cpv[:k + 1] = theta.cpv
+    return k, cpx, cpv, float(np.squeeze(theta.sig))
+
+
+def _cp_tape_row(log, k, lanes=LANES):
+    """Map one step's recorded draws onto the fixed slots (control flow of
+    examples/test_changepoint.py:44-73 + sampler.py:84)."""
+    row = np.zeros(port.cp_nslot(lanes))
+    it = iter(log)
+
+    def nxt(kind):
+        kk, v = next(it)
+        assert kk == kind, (kk, kind, log)
+        return v
+
+    u1 = float(nxt("uniform"))
+    row[port.CP_SLOT_SEL1] = u1
+    nnorm = None
+    if u1 < 0.20:
+        nnorm = k
+    else:
+        u2 = float(nxt("uniform"))
+        row[port.CP_SLOT_SEL2] = u2
+        if u2 < 0.40:
+            nnorm = k + 1
+        else:
+            u3 = float(nxt("uniform"))
+            row[port.CP_SLOT_SEL3] = u3
+            if u3 < 0.60:
+                nnorm = 1
+            else:
+                birth = True
+                if k > 0:
+                    ub = float(nxt("uniform"))
+                    row[port.CP_SLOT_BD] = ub
+                    birth = ub > 0.5
+                if birth:
+                    row[port.CP_SLOT_S] = float(nxt("uniform"))
+                    row[port.CP_SLOT_DU] = float(nxt("uniform"))
+                else:
+                    row[port.CP_SLOT_N] = float(nxt("randint"))
+    if nnorm is not None:
+        v = np.atleast_1d(nxt("normal"))
+        assert len(v) == nnorm, (len(v), nnorm)
+        row[port.CP_SLOT_XI:port.CP_SLOT_XI + nnorm] = v
+    row[port.CP_SLOT_ACC] = float(nxt("uniform"))
+    assert next(it, None) is None
+    return row
+
+
+def _changepoint_fixture(R, name, nchains, T, seed0):
+    pm, pprop, ptheta0, ptrue = port.make_changepoint_problem()
+    tapes, ks, cpxs, cpvs, sigs, lps, plps = [], [], [], [], [], [], []
+    for c in range(nchains):
+        model = R.ChangepointRegression1D(pm.x, pm.y, pm.xmin, pm.xmax, pm.lamb,
+                                          pm.kmax, pm.alpha, pm.beta)
+        prop = R.ChangepointRegression1DProp(model, pprop.hscale)
+        theta0 = R.ChangepointParams(ptheta0.cpx, ptheta0.cpv, ptheta0.sig)
+        np.random.seed(seed0 + c)
+        sampler = R.Sampler(model, prop, theta0)
+        with np.errstate(all="ignore"):
+            steps, props, prop_lp = _run_recorded(R, sampler, T)
+        chain = sampler._chain_thetas
+        assert len(chain) == T + 1
+        tape = np.stack([_cp_tape_row(steps[t], len(chain[t].cpx)) for t in range(T)])
+        st = [_cp_pack_state(th) for th in chain]
+        assert max(s[0] for s in st) < LANES
+        tapes.append(tape)
+        ks.append([s[0] for s in st])
+        cpxs.append([s[1] for s in st])
+        cpvs.append([s[2] for s in st])
+        sigs.append([s[3] for s in st])
+        lps.append(sampler._chain_logpost)
+        plps.append(prop_lp)
+        k_arr = np.array(ks[-1])
+        print("%-28s chain %d T=%d k in [%d,%d] accept=%.3f" % (
+            name, c, T, k_arr.min(), k_arr.max(),
+            np.mean(np.array(lps[-1])[1:] != np.array(lps[-1])[:-1])))
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, name + ".npz"),
+        tape=np.array(tapes), k=np.array(ks, dtype=np.int32), cpx=np.array(cpxs),
+        cpv=np.array(cpvs), sig=np.array(sigs), logpost=np.array(lps, dtype=np.float64),
+        prop_logpost=np.array(plps), x=pm.x, y=pm.y,
+        hyper=np.array([pm.xmin, pm.xmax, pm.lamb, pm.kmax, pm.alpha, pm.beta, pprop.hscale]),
+        seed0=np.int64(seed0))
+
+
+def _portmodel_through_reference(R, name, kind, seed):
+    """Logistic / mMALA are not in the reference: run the PORT's model (and, for
+    mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
+    if kind == "mala":
+        N, d, T, eps = 500, 8, 400, 0.35
+    else:
+        N, d, T, eps = 400, 6, 300, 0.9
+    X, y, theta_star, pv = port.make_logistic_problem(N, d, seed=port.SEED_BASE + 40 + d)
+    pmodel = port.LogisticRegression(X, y, pv)
+
+    class RefLogistic(R.Model):                 # the reference's Model base (model.py)
+        def log_prior(self, theta):
+            return pmodel.log_prior(theta)
+
+        def log_likelihood(self, theta):
+            return pmodel.log_likelihood(theta)
+
+    model = RefLogistic()
+    if kind == "mala":
+        prop = R.VanillaHMC(eps, 1, pmodel.grad_log_posterior)     # reference proposal
+    else:
+        class RefMMALA(R.Proposal):
+            inner = port.SimplifiedMMALA(eps, pmodel)
+
+            def propose(self, theta):
+                return self.inner.propose(theta)
+        prop = RefMMALA()
+    theta0 = theta_star + 0.05 * np.ones(d)
+    _vector_fixture(R, name, model, prop, theta0, T, seed,
+                    extra=dict(X=X, y=y, prior_var=np.float64(pv), eps=np.float64(eps)))
+
+
+def main():
+    if not refshim.reference_available():
+        sys.exit("reference tree not available; fixtures can only be generated in "
+                 "the build container")
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    R = refshim.load_reference()
+    B = R.benchmarks
+
+    # --- config 1 family: RW on the Gaussian benchmarks (sampler.py:72-90,
+    #     randomwalk.py:21-26, gaussian.py:49-52)
+    C0 = np.array([[0.5, 0.2], [0.2, 0.3]])
+    _vector_fixture(R, "rw_gauss2d", B.benchmark_gauss2d_corr,
+                    R.MetropolisRandomWalk(C0), np.ones(2), 2000, 101, extra=dict(C0=C0))
+    _vector_fixture(R, "rw_gauss1d", B.benchmark_gauss1d,
+                    R.MetropolisRandomWalk(2.0), np.ones(1), 500, 102, extra=dict(C0=np.array([[2.0]])))
+    _vector_fixture(R, "adaptrw_gauss2d", B.benchmark_gauss2d_corr,
+                    R.AdaptScaleRandomWalk(1e-4 * np.eye(2)), np.ones(2), 3000, 103,
+                    extra=dict(C0=1e-4 * np.eye(2)), track_scale=True)
+    rng = np.random.Generator(np.random.Philox(7))
+    A = rng.standard_normal((5, 5))
+    C5 = A @ A.T / 5 + 0.2 * np.eye(5)
+    mu5 = rng.standard_normal(5)
+    g5 = R.MultiGaussianDist(mu5, C5)
+    _vector_fixture(R, "rw_gauss5d", g5, R.MetropolisRandomWalk(0.3 * C5), np.zeros(5), 1000, 104,
+                    extra=dict(C0=0.3 * C5, mu=mu5, C=C5))
+
+    # --- MALA == VanillaHMC(eps, 1, grad)  (hamiltonian.py:55-91)
+    g2 = B.benchmark_gauss2d_corr
+    _vector_fixture(R, "mala_gauss2d", g2, R.VanillaHMC(0.25, 1, g2.grad_log_likelihood),
+                    np.ones(2), 1000, 201, extra=dict(eps=np.float64(0.25)))
+    _vector_fixture(R, "mala_gauss5d", g5, R.VanillaHMC(0.3, 1, g5.grad_log_likelihood),
+                    np.zeros(5), 1000, 202, extra=dict(eps=np.float64(0.3), mu=mu5, C=C5))
+    g100 = B.benchmark_gauss100d_corr
+    _vector_fixture(R, "mala_gauss100d", g100, R.VanillaHMC(0.12, 1, g100.grad_log_likelihood),
+                    np.zeros(100), 300, 203, extra=dict(eps=np.float64(0.12)))
+    g1000 = R.MultiGaussianDist(np.zeros(1000), 0.1 * np.eye(1000) + 0.9 * np.ones((1000, 1000)))
+    th0 = np.random.Generator(np.random.Philox(11)).standard_normal(1000) * 0.3
+    _vector_fixture(R, "mala_gauss1000d", g1000, R.VanillaHMC(0.08, 1, g1000.grad_log_likelihood),
+                    th0, 8, 204, extra=dict(eps=np.float64(0.08)))
+    # RW at d=100 (benchmarks.py:25-26)
+    _vector_fixture(R, "rw_gauss100d", g100, R.MetropolisRandomWalk(0.002 * np.eye(100)),
+                    np.zeros(100), 300, 205, extra=dict(C0=0.002 * np.eye(100)))
+
+    # --- HMC proper ("next" row N1): Nsteps>1, mass matrix, adaptive scale
+    _vector_fixture(R, "hmc5_gauss2d", g2, R.VanillaHMC(0.1, 5, g2.grad_log_likelihood),
+                    np.ones(2), 1000, 301, extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)))
+    M2 = np.array([[2.0, 0.3], [0.3, 1.0]])
+    _vector_fixture(R, "hmc3_mass_gauss2d", g2, R.VanillaHMC(0.2, 3, g2.grad_log_likelihood, M=M2),
+                    np.ones(2), 1000, 302, extra=dict(eps=np.float64(0.2), nsteps=np.int64(3), M=M2))
+    _vector_fixture(R, "mala_mass_gauss5d", g5, R.VanillaHMC(0.3, 1, g5.grad_log_likelihood,
+                                                            M=np.linalg.inv(C5)),
+                    np.zeros(5), 500, 303,
+                    extra=dict(eps=np.float64(0.3), M=np.linalg.inv(C5), mu=mu5, C=C5))
+    _vector_fixture(R, "adapthmc5_gauss2d", g2, R.AdaptScaleHMC(0.1, 5, g2.grad_log_likelihood),
+                    np.ones(2), 1500, 304, extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)),
+                    track_scale=True)
+    # pCN ("next" row N2)
+    _vector_fixture(R, "pcn_gauss2d", g2, R.pCN(np.eye(2), 0.5), np.ones(2), 800, 305,
+                    extra=dict(C0=np.eye(2), rho=np.float64(0.5)))
+
+    # --- config 2: changepoint model + 4-way proposal
+    _changepoint_fixture(R, "changepoint", nchains=4, T=3000, seed0=400)
+
+    # --- models/proposals the reference lacks, driven through the reference Sampler
+    _portmodel_through_reference(R, "mala_logistic", "mala", 501)
+    _portmodel_through_reference(R, "mmala_logistic", "mmala", 502)
+
+
+if __name__ == "__main__":
+    main()
