@@ -1,0 +1,221 @@
+/*
+ * riemann_b200 -- C ABI of the B200-native many-chain Metropolis-Hastings engine.
+ *
+ * The reference (rscalzo/riemann) has no FFI layer: its boundary is the duck-typed
+ * Python protocol  Model.log_posterior / Proposal.propose+adapt / Sampler.run+sample
+ * (riemann/models/model.py:27-64, riemann/proposals/proposal.py:10-26,
+ * riemann/samplers/sampler.py:34-90).  The Python host classes in riemann_b200/
+ * keep those signatures and bind the entry points below through ctypes
+ * (riemann_b200/_lib.py); INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns int: RMN_OK or a negative RMN_ERR_*; nothing throws.
+ *     rmn_last_error() returns a thread-local message for the last failure.
+ *   - "d_" pointers are DEVICE pointers owned by the caller (e.g. tensor.data_ptr());
+ *     "h_" pointers are HOST pointers, copied during the call.
+ *   - all per-chain state of a sampler lives in ONE caller-provided device workspace
+ *     (size from rmn_sampler_workspace_bytes); the library never allocates chain
+ *     state.  Handles own only small hyper-parameter tables.
+ *   - every call that touches the device takes a cudaStream_t (as void*) and only
+ *     enqueues work on it; no hidden synchronisation.
+ *   - canonical external layouts: fixed-d states  theta[K][d] (row-major fp64);
+ *     changepoint states  k[K] (int32), cpx[K][RMN_CP_LANES], cpv[K][RMN_CP_LANES],
+ *     sig[K].  Internal layouts differ and are converted by
+ *     set_state/get_state.
+ *   - a handle is bound to the device current at creation and is not thread-safe.
+ */
+#ifndef RIEMANN_B200_H
+#define RIEMANN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMN_VERSION 100
+
+#define RMN_OK 0
+#define RMN_ERR_PARAM (-1)        /* bad argument      -> riemann ParameterError   */
+#define RMN_ERR_CUDA (-2)         /* CUDA failure      -> RuntimeError             */
+#define RMN_ERR_UNSUPPORTED (-3)  /* no device kernel for this model/proposal pair */
+
+typedef struct rmn_model rmn_model_t;
+typedef struct rmn_proposal rmn_proposal_t;
+typedef struct rmn_sampler rmn_sampler_t;
+
+int rmn_version(void);
+const char* rmn_last_error(void);
+
+/* ---------------------------------------------------------------- models ---- */
+
+/* MultiGaussianDist (riemann/models/gaussian.py:27-58).  h_prec = C^{-1} (d x d,
+ * row-major), h_linv = L^{-1} with C = L L^T (d x d row-major, lower; may be NULL
+ * for d > RMN_SMALL_D_MAX), logdetC = 2 sum log diag L (gaussian.py:43). */
+int rmn_model_gaussian_create(rmn_model_t** out, int d, const double* h_mu,
+                              const double* h_prec, const double* h_linv, double logdetC);
+
+/* ChangepointRegression1D (riemann/models/changepoint.py:81-181).  x must be sorted
+ * ascending (generate_synthetic_data, :170).  kmax is stored and, as in the
+ * reference (:100), never enforced. */
+int rmn_model_changepoint_create(rmn_model_t** out, int M, const double* h_x,
+                                 const double* h_y, double xmin, double xmax,
+                                 double lamb, int kmax, double alpha, double beta);
+
+/* Bayesian logistic regression, prior N(0, prior_var I) -- not in the reference;
+ * follows the Model protocol (model.py:27-55).  d_X is [N][d] row-major fp64,
+ * d_y is [N] fp64 in {0,1}; both stay owned by the caller and must outlive the
+ * model. */
+int rmn_model_logistic_create(rmn_model_t** out, int64_t N, int d, const double* d_X,
+                              const double* d_y, double prior_var);
+
+int rmn_model_destroy(rmn_model_t* m);
+int rmn_model_dim(const rmn_model_t* m);
+
+/* Pointwise evaluation for n arbitrary points (parity harness; also backs the
+ * scalar-theta Model.log_posterior / log_likelihood / log_prior of the host
+ * classes).  which: 0 = log_posterior (model.py:43-55 inf/nan rule applied),
+ * 1 = log_likelihood, 2 = log_prior. */
+int rmn_model_logpost(rmn_model_t* m, int which, int64_t n, const double* d_theta,
+                      double* d_out, void* stream);
+int rmn_model_grad(rmn_model_t* m, int64_t n, const double* d_theta, double* d_grad,
+                   void* stream);
+/* Fisher metric G[n][d][d] (logistic model only). */
+int rmn_model_metric(rmn_model_t* m, int64_t n, const double* d_theta, double* d_G,
+                     void* stream);
+int rmn_model_cp_logpost(rmn_model_t* m, int which, int64_t n, const int32_t* d_k,
+                         const double* d_cpx, const double* d_cpv, const double* d_sig,
+                         double* d_out, void* stream);
+
+/* -------------------------------------------------------------- proposals ---- */
+
+#define RMN_SMALL_D_MAX 8 /* fully fused register-resident kernels up to this d */
+
+/* MetropolisRandomWalk / AdaptScaleRandomWalk (riemann/proposals/randomwalk.py:12-37):
+ * theta' = theta + scale * L xi.  h_L = chol(C) (d x d row-major, lower).
+ * adapt != 0 enables AdaptScaleProposal (adaptive.py:11-35) PER CHAIN with the
+ * given target acceptance rate (0.25 in the reference). */
+int rmn_proposal_rw_create(rmn_proposal_t** out, int d, const double* h_L, int adapt,
+                           double target);
+
+/* VanillaHMC / AdaptScaleHMC (riemann/proposals/hamiltonian.py:13-103); nsteps = 1
+ * is MALA.  The gradient is the model's own grad log posterior.  Mass matrix
+ * optional: pass h_chM = chol(M), h_Minv = M^{-1}, h_chMinv = chol(M)^{-1}
+ * (each d x d row-major) or all NULL.  adapt != 0: eps = scale * eps0, per chain. */
+int rmn_proposal_hmc_create(rmn_proposal_t** out, int d, double eps, int nsteps,
+                            const double* h_chM, const double* h_Minv,
+                            const double* h_chMinv, int adapt, double target);
+
+/* pCN (riemann/proposals/randomwalk.py:78-100). h_L = chol(C); h_Linv its inverse. */
+int rmn_proposal_pcn_create(rmn_proposal_t** out, int d, const double* h_L,
+                            const double* h_Linv, double rho);
+
+/* Simplified manifold MALA with the model's Fisher metric (not in the reference;
+ * Proposal protocol proposal.py:10-17). */
+int rmn_proposal_mmala_create(rmn_proposal_t** out, int d, double eps);
+
+/* ChangepointRegression1DProp (examples/test_changepoint.py:18-73).  p_cum[3] are the
+ * sequential thresholds (.20, .40, .60 there). */
+int rmn_proposal_changepoint_create(rmn_proposal_t** out, double hscale,
+                                    const double* h_p_cum);
+
+int rmn_proposal_destroy(rmn_proposal_t* p);
+
+/* --------------------------------------------------------------- samplers ---- */
+
+#define RMN_CP_LANES 16                  /* lanes per chain; at most LANES-1 changepoints */
+#define RMN_CP_SLOT_SEL1 0               /* injected-tape slots, one row per MH step:   */
+#define RMN_CP_SLOT_SEL2 1               /*   block-selection uniforms (test_changepoint.py:48,51,54) */
+#define RMN_CP_SLOT_SEL3 2
+#define RMN_CP_SLOT_BD 3                 /*   birth/death coin (:59)                    */
+#define RMN_CP_SLOT_S 4                  /*   U(xmin,xmax) (:60), already scaled        */
+#define RMN_CP_SLOT_DU 5                 /*   U(-0.1,0.1) (:61), already scaled         */
+#define RMN_CP_SLOT_N 6                  /*   randint(k) (:67) as a double              */
+#define RMN_CP_SLOT_ACC 7                /*   accept uniform (sampler.py:84)            */
+#define RMN_CP_SLOT_XI 8                 /*   normals xi_0..xi_{LANES-1}                */
+#define RMN_CP_NSLOT (RMN_CP_SLOT_XI + RMN_CP_LANES)
+
+#define RMN_CP_NDIAG 8                   /* tracked functionals: sig, k, yhat(6 query points) */
+
+/* Injected randomness (the reference's own numpy stream, replayed):
+ *   fixed-d samplers: xi[(t*K + c)*d + j], u[t*K + c]
+ *   changepoint:      tape[(t*K + c)*RMN_CP_NSLOT + slot]  (xi unused) */
+typedef struct {
+    const double* d_xi;
+    const double* d_u;
+    const double* d_tape;
+} rmn_inject_t;
+
+/* Optional trace.  History index i = 0 is the state at entry, i = t+1 the state after
+ * step t of this call (sampler.py:49-54).  States with i >= first and
+ * (i - first) % thin == 0, i >= 1, are written to record r = (i - first) / thin.
+ *   fixed-d:      d_theta[r][K][d], d_logpost[r][K]
+ *   changepoint:  d_k[r][K], d_cpx[r][K][LANES], d_cpv[r][K][LANES], d_sig[r][K]
+ * d_prop_logpost[t][K] / d_accepted[t][K] (every step, unthinned) expose the
+ * proposed log-posterior and the decision for parity tests.  Any pointer may be NULL. */
+typedef struct {
+    int64_t first;
+    int64_t thin;
+    double* d_theta;
+    double* d_logpost;
+    int32_t* d_k;
+    double* d_cpx;
+    double* d_cpv;
+    double* d_sig;
+    double* d_prop_logpost;
+    uint8_t* d_accepted;
+} rmn_trace_t;
+
+size_t rmn_sampler_workspace_bytes(const rmn_model_t* m, const rmn_proposal_t* p, int64_t K);
+
+/* K chains on this device; chain c has global id chain_offset + c, which keys its
+ * Philox substream (results do not depend on how chains are sharded over GPUs). */
+int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
+                       int64_t chain_offset, uint64_t seed, void* d_workspace,
+                       size_t workspace_bytes);
+int rmn_sampler_destroy(rmn_sampler_t* s);
+
+/* = Sampler.__init__ (sampler.py:34-42): store the states and evaluate their
+ * log-posterior (and gradient / metric caches) on the device. */
+int rmn_sampler_set_state(rmn_sampler_t* s, const double* d_theta, void* stream);
+int rmn_sampler_get_state(rmn_sampler_t* s, double* d_theta, double* d_logpost, void* stream);
+int rmn_sampler_cp_set_state(rmn_sampler_t* s, const int32_t* d_k, const double* d_cpx,
+                             const double* d_cpv, const double* d_sig, void* stream);
+int rmn_sampler_cp_get_state(rmn_sampler_t* s, int32_t* d_k, double* d_cpx, double* d_cpv,
+                             double* d_sig, double* d_logpost, void* stream);
+
+/* T iterations of Sampler.sample (sampler.py:72-90) for every chain.
+ * inj == NULL: Philox4x32-10 randomness; else the injected stream is replayed. */
+int rmn_sampler_run(rmn_sampler_t* s, int64_t T, const rmn_inject_t* inj,
+                    const rmn_trace_t* trace, void* stream);
+
+/* AdaptScaleProposal state per chain (adaptive.py:19-24): scale, Nsamples, Naccepts. */
+int rmn_sampler_get_adapt(rmn_sampler_t* s, double* d_scale, int64_t* d_nsamples,
+                          int64_t* d_naccepts, void* stream);
+
+/* Diagnostics since the last reset.  nd = rmn_sampler_diag_dim().  The block is
+ *   [0] K  [1] steps per chain  [2] total accepts  [3] KCAP overflow events
+ *   [4..4+nd)       sum_c m_c[j]          (m_c = per-chain mean of functional j)
+ *   [4+nd..4+2nd)   sum_c m_c[j]^2
+ *   [4+2nd..4+3nd)  sum_c v_c[j]          (v_c = per-chain biased variance)
+ * every entry is a SUM over chains, so blocks from several GPUs combine with one
+ * all-reduce(sum); split-R-hat and ESS follow on the host. */
+int rmn_sampler_diag_dim(const rmn_sampler_t* s);
+int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream);
+int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stream);
+
+/* Number of kernel launches this handle has enqueued so far. */
+int64_t rmn_sampler_launch_count(const rmn_sampler_t* s);
+
+/* Raw device RNG, for known-answer tests: out[n][4] = Philox4x32-10(ctr[n][4], key[n][2]). */
+int rmn_philox_raw(int64_t n, const uint32_t* d_ctr, const uint32_t* d_key, uint32_t* d_out,
+                   void* stream);
+/* The engine's N(0,1)/U(0,1) for (seed, chain, step): normals[n][nn] and uniform[n]. */
+int rmn_rng_draws(uint64_t seed, int64_t chain0, int64_t step, int64_t n, int nn,
+                  double* d_normals, double* d_uniform, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIEMANN_B200_H */

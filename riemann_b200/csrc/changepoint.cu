@@ -1,0 +1,450 @@
+// riemann_b200 -- fused T-step MH kernel for the changepoint regression model.
+//
+// RMN_CP_LANES (=16) lanes cooperate on one chain: lane j holds cpx[j] and cpv[j] in
+// registers, so the variable-dimension state (k <= LANES-1 changepoints) needs no
+// dynamic indexing; insert/delete are warp shuffles.  Per iteration the kernel replaces
+//   Sampler.sample                                riemann/samplers/sampler.py:72-90
+//   ChangepointRegression1DProp.propose           examples/test_changepoint.py:44-73
+//   MetropolisRandomWalk.propose (3 block moves)  riemann/proposals/randomwalk.py:21-26
+//   add_changepoint / subtract_changepoint        riemann/models/changepoint.py:193-240
+//   ChangepointRegression1D.log_likelihood/log_prior/predict   changepoint.py:106-160,181
+//   Model.log_posterior                           riemann/models/model.py:43-55
+//
+// Likelihood: x is sorted, so the prediction is constant on runs of data points; with
+// prefix sums cy[i] = sum_{m<i} (y_m - c), cyy[i] = sum_{m<i} (y_m - c)^2 the residual
+// sum of squares of segment j is  n_j (v_j-c)^2 - 2 (v_j-c) S1_j + S2_j,  where the run
+// boundaries b_j = #{x_i <= cpx_j} come from a branch-free binary search (equivalent to
+// np.searchsorted(cpx, x), changepoint.py:181).  O(k log M) instead of O(M) per
+// evaluation; all arithmetic fp64 like the reference.  x/cy/cyy are staged in shared
+// memory once per block and reused by all chains and all T iterations.
+//
+// Reference behaviours reproduced: k = number of STEPS in
+// the three k-terms of the prior; constraints enforced only through nan/inf -> -inf;
+// a fresh uniform per block-selection elif; trans-dimensional moves use log|J| alone
+// as logqratio.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LANES = RMN_CP_LANES;
+constexpr int NQ = 6;   // prediction query points tracked by the diagnostics
+
+struct CPParams {
+    int M, P2, alpha_is_one, pad;
+    double xmin, xmax, alpha, beta, cv, logL, ycenter, Mlog2pi, sqrtM;
+    double tab1[LANES + 1];     // k log(lam) - gammaln(k) - lam        changepoint.py:134
+    double tab2[LANES + 1];     // gammaln(2k+1)                        changepoint.py:143
+    double sx[LANES + 1];       // sqrt(0.01 (xmax-xmin)/(k+1))         test_changepoint.py:36
+    double sv, ss;              // sqrt(0.01 hscale^2/M), sqrt(0.01 hscale)   :37-38
+    double p1, p2, p3;          // sequential selection thresholds      :28-30
+    double xq[NQ];
+};
+
+struct CPState {
+    int32_t* k;          // [K]
+    double* cpx;         // [K][LANES]
+    double* cpv;         // [K][LANES]
+    double* sig;         // [K]
+    double* lp;          // [K]
+    long long* dacc;     // [K]
+    long long* dovf;     // [K]
+    double* S1;          // [NDIAG][K]
+    double* S2;          // [NDIAG][K]
+};
+
+__device__ __forceinline__ unsigned group_ballot(bool pred) {
+    const unsigned full = __ballot_sync(0xffffffffu, pred);
+    return (full >> (threadIdx.x & 16)) & 0xffffu;
+}
+
+// #{i : x_i <= c}  (upper bound), branch-free, always in [0, M]
+__device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int M, int P2, double c) {
+    int pos = 0;
+    for (int step = P2; step > 0; step >>= 1) {
+        const int np = pos + step;
+        if (np <= M && xs[np - 1] <= c) pos = np;
+    }
+    return pos;
+}
+
+// Full log-posterior (which=0), log-likelihood (1) or log-prior (2) of one state held
+// across the 16 lanes of a group.  Plain IEEE arithmetic: log of a negative gap/height
+// gives nan, log(0) gives -inf, exactly like numpy; the reference's nan -> -inf and
+// inf/nan -> -inf rules are applied at the end.
+__device__ __forceinline__ double cp_logpost(const CPParams& P, const double* __restrict__ xs,
+                                             const double* __restrict__ cy,
+                                             const double* __restrict__ cyy, int lane, int k,
+                                             double cx, double cv_, double sig, int which) {
+    const bool active = lane <= k;
+    // boundaries of this lane's segment
+    const int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;
+    int bl = __shfl_up_sync(0xffffffffu, bu, 1, LANES);
+    if (lane == 0) bl = 0;
+    double prev = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
+    if (lane == 0) prev = P.xmin;
+    const double hi = (lane < k) ? cx : P.xmax;
+
+    double ss = 0.0, lg = 0.0, vt = 0.0;
+    if (active) {
+        const double n = (double)(bu - bl);
+        const double s1 = cy[bu] - cy[bl];
+        const double s2 = cyy[bu] - cyy[bl];
+        const double vc = cv_ - P.ycenter;
+        ss = n * vc * vc - 2.0 * vc * s1 + s2;
+        lg = log(hi - prev);                                   // changepoint.py:142-143
+        vt = -P.beta * cv_ + P.cv;                             // changepoint.py:18-19,136
+        if (!P.alpha_is_one) vt += (P.alpha - 1.0) * log(cv_);
+        else if (!(cv_ > 0.0)) vt = NAN;                       // 0 * log(v<=0) is nan in numpy
+    }
+    ss = group_sum<LANES>(ss);
+    lg = group_sum<LANES>(lg);
+    vt = group_sum<LANES>(vt);
+
+    const int ks = k + 1;                                      // number of steps
+    const double s2v = sig * sig;
+    double logl = -0.5 * ((ss / s2v + (double)P.M * log(s2v)) + P.Mlog2pi);   // :118-120
+    if (isnan(logl)) logl = -INFINITY;                         // :124-125
+    double lsig = log(1.0 / s2v);                              // :145
+    if (sig < 0.0) lsig = NAN;                                 // :146-147
+    const double lps = (P.tab2[ks] + lg) - (double)ks * P.logL;
+    double logp = ((P.tab1[ks] + vt) + lps) + lsig;            // :156
+    if (isnan(logp)) logp = -INFINITY;                         // :158-159
+    if (which == 1) return logl;
+    if (which == 2) return logp;
+    return combine_logpost(logp, logl);
+}
+
+template <bool INJ, bool SMEMDATA, bool DIAG>
+__global__ void __launch_bounds__(128)
+changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
+                   int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
+                   const double* __restrict__ tape, rmn_trace_t tr) {
+    extern __shared__ double smem[];
+    const double* xs = gdata;
+    if (SMEMDATA) {
+        const int n = 3 * P.M + 2;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = gdata[i];
+        __syncthreads();
+        xs = smem;
+    }
+    const double* cy = xs + P.M;
+    const double* cyy = cy + P.M + 1;
+
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    const bool live = c_raw < K;
+    const int64_t c = live ? c_raw : K - 1;       // dead groups shadow the last chain, never store
+
+    int k = st.k[c];
+    double cx = st.cpx[c * LANES + lane];
+    double cv = st.cpv[c * LANES + lane];
+    double sig = st.sig[c];
+    double lp = st.lp[c];
+    long long nacc = 0, novf = 0;
+    double s1 = 0.0, s2 = 0.0;                    // lane i < NDIAG accumulates functional i
+    const RngKey rk(seed, (uint64_t)(chain_offset + c));
+    const TraceSel ts{tr.first, tr.thin > 0 ? tr.thin : 1};
+
+    for (int64_t t = 0; t < T; ++t) {
+        const uint64_t step = (uint64_t)(step0 + t);
+        double u1, u2, u3, ubd, snew, du, uacc, xi;
+        int nrand;
+        if (INJ) {
+            const double* row = tape + (t * K + c) * RMN_CP_NSLOT;
+            u1 = row[RMN_CP_SLOT_SEL1]; u2 = row[RMN_CP_SLOT_SEL2]; u3 = row[RMN_CP_SLOT_SEL3];
+            ubd = row[RMN_CP_SLOT_BD]; snew = row[RMN_CP_SLOT_S]; du = row[RMN_CP_SLOT_DU];
+            nrand = (int)row[RMN_CP_SLOT_N]; uacc = row[RMN_CP_SLOT_ACC];
+            xi = row[RMN_CP_SLOT_XI + lane];
+        } else {
+            const uint4 a = rk.block(step, RMN_BLOCK_AUX);
+            const uint4 b = rk.block(step, RMN_BLOCK_AUX2);
+            u1 = u01(a.x); u2 = u01(a.y); u3 = u01(a.z); ubd = u01(a.w);
+            snew = P.xmin + (P.xmax - P.xmin) * u01(b.x);
+            du = -0.1 + 0.2 * u01(b.y);
+            nrand = (int)(u01(b.z) * (double)k);
+            uacc = u01(b.w);
+            const uint4 r = rk.block(step, (uint32_t)lane);
+            float n0, n1;
+            box_muller(r.x, r.y, n0, n1);
+            xi = (double)n0;
+        }
+        nrand = max(0, min(nrand, k - 1));
+
+        // ---- which block moves (fresh uniform per elif, test_changepoint.py:48-54)
+        const int mv = (u1 < P.p1) ? 0 : ((u2 < P.p2) ? 1 : ((u3 < P.p3) ? 2 : 3));
+        const bool birth = (k == 0) || (ubd > 0.5);                     // :59
+
+        // ---- shuffles every lane takes part in, whatever the move
+        const double xi0 = __shfl_sync(0xffffffffu, xi, 0, LANES);
+        const double px = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
+        const double pv = __shfl_up_sync(0xffffffffu, cv, 1, LANES);
+        const double qx = __shfl_down_sync(0xffffffffu, cx, 1, LANES);
+        const double qv = __shfl_down_sync(0xffffffffu, cv, 1, LANES);
+        const int nb = __popc(group_ballot(lane < k && cx < snew));     // searchsorted(cpx, s), :206
+        const double hb = __shfl_sync(0xffffffffu, cv, nb, LANES);
+        const double h1d = __shfl_sync(0xffffffffu, cv, nrand, LANES);
+        const double h2d = __shfl_sync(0xffffffffu, cv, nrand + 1, LANES);
+
+        // ---- build the proposal by selection (no divergence between the two chains of a warp)
+        int kk = k;
+        double nx = cx, nv = cv, nsig = sig, lqr = 0.0;
+        bool ovf = false;
+        if (mv == 0) {
+            if (lane < k) nx = __dadd_rn(cx, __dmul_rn(P.sx[k], xi));   // randomwalk.py:26, scale = 1
+        } else if (mv == 1) {
+            if (lane <= k) nv = __dadd_rn(cv, __dmul_rn(P.sv, xi));
+        } else if (mv == 2) {
+            nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
+        } else if (birth) {
+            const double u = 0.5 + du / P.sqrtM;                        // :61
+            const double f = sqrt((1.0 - u) / u);                       // changepoint.py:57
+            lqr = log(fabs(hb / (u * (1.0 - u))));                      // log|J|, :72-74
+            if (k + 1 > LANES - 1) {
+                ovf = true;
+            } else {
+                nx = (lane < nb) ? cx : ((lane == nb) ? snew : px);
+                nv = (lane < nb) ? cv : ((lane == nb) ? hb / f : ((lane == nb + 1) ? hb * f : pv));
+                kk = k + 1;
+            }
+        } else {
+            const double h = sqrt(h1d * h2d);                           // changepoint.py:67
+            const double u = 1.0 / (1.0 + h2d / h1d);                   // :68
+            lqr = -log(fabs(h / (u * (1.0 - u))));                      // log|J^-1|, :76-78
+            nx = (lane < nrand) ? cx : qx;
+            nv = (lane < nrand) ? cv : ((lane == nrand) ? h : qv);
+            kk = k - 1;
+        }
+        // lanes beyond the new extent hold zeros (canonical padding)
+        if (lane >= kk) nx = 0.0;
+        if (lane > kk) nv = 0.0;
+
+        const double lpn = cp_logpost(P, xs, cy, cyy, lane, kk, nx, nv, nsig, 0);
+        const bool acc = !ovf && mh_accept(lpn, lp, lqr, uacc);
+        if (acc) { k = kk; cx = nx; cv = nv; sig = nsig; lp = lpn; }
+        nacc += acc ? 1 : 0;
+        novf += ovf ? 1 : 0;
+
+        if (DIAG) {
+            double f = (lane == 0) ? sig : (double)k;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int cnt = __popc(group_ballot(lane < k && cx < P.xq[q]));
+                const double yq = __shfl_sync(0xffffffffu, cv, cnt, LANES);
+                if (lane == 2 + q) f = yq;
+            }
+            if (lane < RMN_CP_NDIAG) { s1 += f; s2 += f * f; }
+        }
+
+        if (live) {
+            if (lane == 0) {
+                if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpn;
+                if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
+            }
+            if (tr.d_k || tr.d_cpx || tr.d_cpv || tr.d_sig || tr.d_logpost) {
+                const long long r = ts.slot(t + 1);
+                if (r >= 0) {
+                    if (tr.d_cpx) tr.d_cpx[(r * K + c) * LANES + lane] = cx;
+                    if (tr.d_cpv) tr.d_cpv[(r * K + c) * LANES + lane] = cv;
+                    if (lane == 0) {
+                        if (tr.d_k) tr.d_k[r * K + c] = k;
+                        if (tr.d_sig) tr.d_sig[r * K + c] = sig;
+                        if (tr.d_logpost) tr.d_logpost[r * K + c] = lp;
+                    }
+                }
+            }
+        }
+    }
+
+    if (live) {
+        st.cpx[c * LANES + lane] = cx;
+        st.cpv[c * LANES + lane] = cv;
+        if (lane == 0) {
+            st.k[c] = k;
+            st.sig[c] = sig;
+            st.lp[c] = lp;
+            st.dacc[c] += nacc;
+            st.dovf[c] += novf;
+        }
+        if (DIAG && lane < RMN_CP_NDIAG) {
+            st.S1[(int64_t)lane * K + c] += s1;
+            st.S2[(int64_t)lane * K + c] += s2;
+        }
+    }
+}
+
+// evaluate n states given in the canonical layout (pointwise parity entry + set_state)
+__global__ void __launch_bounds__(128)
+cp_eval_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, int which,
+               int64_t n, const int32_t* __restrict__ kin, const double* __restrict__ cpx,
+               const double* __restrict__ cpv, const double* __restrict__ sig,
+               double* __restrict__ out) {
+    const int lane = threadIdx.x & (LANES - 1);
+    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    const bool live = c_raw < n;
+    const int64_t c = live ? c_raw : n - 1;
+    const double* xs = gdata;
+    const double* cy = xs + P.M;
+    const double* cyy = cy + P.M + 1;
+    const double v = cp_logpost(P, xs, cy, cyy, lane, kin[c], cpx[c * LANES + lane],
+                                cpv[c * LANES + lane], sig[c], which);
+    if (live && lane == 0) out[c] = v;
+}
+
+__global__ void cp_copy_state_kernel(int64_t K, const int32_t* k_in, const double* cpx_in,
+                                     const double* cpv_in, const double* sig_in, int32_t* k_out,
+                                     double* cpx_out, double* cpv_out, double* sig_out,
+                                     const double* lp_in, double* lp_out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= K * LANES) return;
+    const int64_t c = i / LANES;
+    const int lane = (int)(i % LANES);
+    const int k = k_in[c];
+    if (cpx_out) cpx_out[i] = (lane < k) ? cpx_in[i] : 0.0;
+    if (cpv_out) cpv_out[i] = (lane <= k) ? cpv_in[i] : 0.0;
+    if (lane == 0) {
+        if (k_out) k_out[c] = k;
+        if (sig_out) sig_out[c] = sig_in[c];
+        if (lp_out && lp_in) lp_out[c] = lp_in[c];
+    }
+}
+
+static CPParams make_params(const rmn_model* m, const rmn_proposal* p) {
+    CPParams P{};
+    P.M = m->M;
+    int p2 = 1;
+    while (p2 * 2 <= m->M) p2 *= 2;
+    P.P2 = (m->M >= 1) ? p2 : 0;
+    P.alpha_is_one = (m->alpha == 1.0);
+    P.xmin = m->xmin; P.xmax = m->xmax; P.alpha = m->alpha; P.beta = m->beta;
+    P.cv = m->cv;
+    P.logL = log(m->xmax - m->xmin);
+    P.ycenter = m->ycenter;
+    P.Mlog2pi = (double)m->M * log(2.0 * M_PI);
+    P.sqrtM = sqrt((double)m->M);
+    for (int ks = 0; ks <= LANES; ++ks) {
+        P.tab1[ks] = (ks >= 1) ? (double)ks * log(m->lamb) - lgamma((double)ks) - m->lamb : 0.0;
+        P.tab2[ks] = lgamma(2.0 * ks + 1.0);
+    }
+    const double hs = p ? p->hscale : 1.0;
+    for (int k = 0; k <= LANES; ++k) P.sx[k] = sqrt(0.01 * (m->xmax - m->xmin) / (double)(k + 1));
+    P.sv = sqrt(0.01 * (hs * hs) / (double)m->M);
+    P.ss = sqrt(0.01 * hs);
+    P.p1 = p ? p->p_cum[0] : 0.2; P.p2 = p ? p->p_cum[1] : 0.4; P.p3 = p ? p->p_cum[2] : 0.6;
+    for (int q = 0; q < NQ; ++q)
+        P.xq[q] = m->xmin + (m->xmax - m->xmin) * (q + 0.5) / (double)NQ;
+    return P;
+}
+
+struct ChangepointSampler : SamplerImpl {
+    rmn_sampler* s;
+    CPState st{};
+    CPParams P;
+    bool use_smem;
+    size_t smem_bytes;
+    explicit ChangepointSampler(rmn_sampler* s_) : s(s_) {
+        P = make_params(s->model, s->prop);
+        smem_bytes = (size_t)(3 * P.M + 2) * 8;
+        use_smem = smem_bytes <= 96 * 1024;
+    }
+    size_t workspace_bytes() const override {
+        const size_t K = (size_t)s->K;
+        return align256(K * 4) + 2 * align256(K * LANES * 8) + 4 * align256(K * 8) +
+               2 * align256(RMN_CP_NDIAG * K * 8) + 256;
+    }
+    int bind(void* ws) override {
+        const size_t K = (size_t)s->K;
+        char* p = (char*)ws;
+        st.k = (int32_t*)p; p += align256(K * 4);
+        st.cpx = (double*)p; p += align256(K * LANES * 8);
+        st.cpv = (double*)p; p += align256(K * LANES * 8);
+        st.sig = (double*)p; p += align256(K * 8);
+        st.lp = (double*)p; p += align256(K * 8);
+        st.dacc = (long long*)p; p += align256(K * 8);
+        st.dovf = (long long*)p; p += align256(K * 8);
+        st.S1 = (double*)p; p += align256(RMN_CP_NDIAG * K * 8);
+        st.S2 = (double*)p; p += align256(RMN_CP_NDIAG * K * 8);
+        RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        if (use_smem && smem_bytes > 48 * 1024) {
+            RMN_CUDA(cudaFuncSetAttribute(changepoint_kernel<false, true, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            RMN_CUDA(cudaFuncSetAttribute(changepoint_kernel<true, true, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        }
+        return RMN_OK;
+    }
+    unsigned grid() const { return (unsigned)((s->K * LANES + 127) / 128); }
+
+    int cp_set_state(const int32_t* d_k, const double* d_cpx, const double* d_cpv,
+                     const double* d_sig, cudaStream_t stream) override {
+        const int64_t n = s->K * LANES;
+        cp_copy_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+            s->K, d_k, d_cpx, d_cpv, d_sig, st.k, st.cpx, st.cpv, st.sig, nullptr, nullptr);
+        RMN_KERNEL_CHECK();
+        cp_eval_kernel<<<grid(), 128, 0, stream>>>(P, s->model->d_cpdata, 0, s->K, st.k, st.cpx,
+                                                   st.cpv, st.sig, st.lp);
+        RMN_KERNEL_CHECK();
+        launches += 2;
+        return RMN_OK;
+    }
+    int cp_get_state(int32_t* d_k, double* d_cpx, double* d_cpv, double* d_sig, double* d_lp,
+                     cudaStream_t stream) override {
+        const int64_t n = s->K * LANES;
+        cp_copy_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+            s->K, st.k, st.cpx, st.cpv, st.sig, d_k, d_cpx, d_cpv, d_sig, st.lp, d_lp);
+        RMN_KERNEL_CHECK();
+        launches++;
+        return RMN_OK;
+    }
+    template <bool INJ>
+    void launch(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
+        if (use_smem)
+            changepoint_kernel<INJ, true, true><<<grid(), 128, smem_bytes, stream>>>(
+                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
+        else
+            changepoint_kernel<INJ, false, true><<<grid(), 128, 0, stream>>>(
+                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
+    }
+    int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
+        rmn_trace_t t0{};
+        if (tr) t0 = *tr;
+        if (t0.thin <= 0) t0.thin = 1;
+        if (inj) {
+            RMN_REQUIRE(inj->d_tape, "injected changepoint run needs d_tape");
+            launch<true>(T, inj->d_tape, t0, stream);
+        } else {
+            launch<false>(T, nullptr, t0, stream);
+        }
+        RMN_KERNEL_CHECK();
+        launches++;
+        step0 += T; diag_steps += T;
+        return RMN_OK;
+    }
+    int diag_dim() const override { return RMN_CP_NDIAG; }
+    int reset_diag(cudaStream_t stream) override {
+        RMN_CUDA(cudaMemsetAsync(st.S1, 0, (size_t)RMN_CP_NDIAG * s->K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.S2, 0, (size_t)RMN_CP_NDIAG * s->K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)s->K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.dovf, 0, (size_t)s->K * 8, stream));
+        diag_steps = 0;
+        return RMN_OK;
+    }
+    int reduce_diag(double* d_block, cudaStream_t stream) override {
+        launches++;
+        return rmn_reduce_diag_block(s->K, RMN_CP_NDIAG, diag_steps, st.S1, st.S2, st.dacc, st.dovf,
+                                     d_block, stream);
+    }
+};
+
+}  // namespace
+
+SamplerImpl* make_changepoint_sampler(rmn_sampler* s) { return new ChangepointSampler(s); }
+
+int cp_pointwise(rmn_model* m, int which, int64_t n, const int32_t* d_k, const double* d_cpx,
+                 const double* d_cpv, const double* d_sig, double* d_out, cudaStream_t st) {
+    if (n <= 0) return RMN_OK;
+    const CPParams P = make_params(m, nullptr);
+    cp_eval_kernel<<<(unsigned)((n * LANES + 127) / 128), 128, 0, st>>>(P, m->d_cpdata, which, n, d_k,
+                                                                        d_cpx, d_cpv, d_sig, d_out);
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}

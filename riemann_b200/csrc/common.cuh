@@ -1,0 +1,247 @@
+// riemann_b200 -- shared device utilities and host-side handle definitions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/riemann_b200.h"
+
+// ----------------------------------------------------------------------------
+// error plumbing (host)
+// ----------------------------------------------------------------------------
+void rmn_set_error(const char* fmt, ...);
+
+#define RMN_CUDA(call)                                                             \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            rmn_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                          cudaGetErrorString(e__));                                \
+            return RMN_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+#define RMN_REQUIRE(cond, ...)                                                     \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            rmn_set_error(__VA_ARGS__);                                            \
+            return RMN_ERR_PARAM;                                                  \
+        }                                                                          \
+    } while (0)
+
+#define RMN_KERNEL_CHECK() RMN_CUDA(cudaGetLastError())
+
+// ----------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Replaces numpy's global MT19937 stream
+// (randomwalk.py:25, sampler.py:84).  key = (seed_lo, seed_hi),
+// counter = (block, step_lo, step_hi, global chain id).
+// ----------------------------------------------------------------------------
+#define RMN_PHILOX_M0 0xD2511F53u
+#define RMN_PHILOX_M1 0xCD9E8D57u
+#define RMN_PHILOX_W0 0x9E3779B9u
+#define RMN_PHILOX_W1 0xBB67AE85u
+#define RMN_BLOCK_ACCEPT 0xFFFFFFFFu /* block index reserved for the accept uniform */
+#define RMN_BLOCK_AUX 0xFFFFFFFEu    /* selection / auxiliary uniforms               */
+#define RMN_BLOCK_AUX2 0xFFFFFFFDu
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(RMN_PHILOX_M0, c.x), lo0 = RMN_PHILOX_M0 * c.x;
+        const uint32_t hi1 = __umulhi(RMN_PHILOX_M1, c.z), lo1 = RMN_PHILOX_M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += RMN_PHILOX_W0;
+        k.y += RMN_PHILOX_W1;
+    }
+    return c;
+}
+
+struct RngKey {
+    uint2 key;
+    uint32_t chain;
+    __device__ __forceinline__ RngKey(uint64_t seed, uint64_t chain_id)
+        : key(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), chain((uint32_t)chain_id) {}
+    __device__ __forceinline__ uint4 block(uint64_t step, uint32_t blk) const {
+        return philox4x32_10(make_uint4(blk, (uint32_t)step, (uint32_t)(step >> 32), chain), key);
+    }
+};
+
+// uniform on (0,1): (x + 0.5) * 2^-32, exact in fp64
+__device__ __forceinline__ double u01(uint32_t x) {
+    return ((double)x + 0.5) * (1.0 / 4294967296.0);
+}
+
+// Box-Muller in fp32 (cuRAND-style 32-bit uniforms), widened to fp64 afterwards.
+// The randomness is not parity-bound (parity runs inject the reference's stream).
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float ang = fmaf((float)b, 2.3283064365386963e-10f * 6.283185307179586f,
+                           1.1641532182693481e-10f * 6.283185307179586f - 3.14159265358979f);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(ang, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// four N(0,1) from one Philox block
+__device__ __forceinline__ void normal4(const uint4 r, double out[4]) {
+    float a, b, c, d;
+    box_muller(r.x, r.y, a, b);
+    box_muller(r.z, r.w, c, d);
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+}
+
+// ----------------------------------------------------------------------------
+// Metropolis-Hastings accept rule, sampler.py:83-84.
+//   mhratio = min(0, lp' - lp - logqratio)  with PYTHON's min: nan -> 0
+//   accept iff log(u) < mhratio (strict)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ bool mh_accept(double lp_new, double lp_old, double lqr, double u) {
+    const double delta = lp_new - lp_old - lqr;
+    const double mh = (delta < 0.0) ? delta : 0.0;   // false for nan -> 0
+    return log(u) < mh;
+}
+
+// model.py:50-54: any inf (either sign) or nan in prior or likelihood -> -inf
+__device__ __forceinline__ double combine_logpost(double logp, double logl) {
+    return (isfinite(logp) && isfinite(logl)) ? (logp + logl) : -INFINITY;
+}
+
+// AdaptScaleProposal.adapt (adaptive.py:26-35), one chain
+struct AdaptState {
+    double scale;
+    long long nsamples;
+    long long naccepts;
+    __device__ __forceinline__ void update(bool moved, double target) {
+        const bool first = (nsamples == 0);          // last_theta is None -> counts as accept
+        nsamples += 1;
+        naccepts += (moved || first) ? 1 : 0;
+        const double rate = (double)naccepts / (double)nsamples;
+        const double r = exp(1.0 / (double)nsamples);
+        if (rate > target) scale = __dmul_rn(scale, r);
+        else scale = __ddiv_rn(scale, r);
+    }
+};
+
+template <int W>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, W);
+    return v;
+}
+
+// trace bookkeeping: history index i (>=1) -> record slot or -1
+struct TraceSel {
+    long long first, thin;
+    __device__ __forceinline__ long long slot(long long i) const {
+        if (i < first) return -1;
+        const long long r = i - first;
+        return (r % thin == 0) ? r / thin : -1;
+    }
+};
+
+// ----------------------------------------------------------------------------
+// host-side handles
+// ----------------------------------------------------------------------------
+enum { RMN_MODEL_GAUSS = 1, RMN_MODEL_CP = 2, RMN_MODEL_LOGISTIC = 3 };
+enum { RMN_PROP_RW = 1, RMN_PROP_HMC = 2, RMN_PROP_PCN = 3, RMN_PROP_MMALA = 4, RMN_PROP_CP = 5 };
+
+struct rmn_model {
+    int kind = 0;
+    int d = 0;
+    int device = 0;
+    // gaussian
+    std::vector<double> h_mu, h_linv;    // linv: packed lower triangle, row-major
+    double logdetC = 0.0;
+    double* d_mu = nullptr;              // [d]
+    double* d_prec = nullptr;            // [d][d]
+    // changepoint
+    int M = 0, kmax = 0;
+    double xmin = 0, xmax = 0, lamb = 0, alpha = 0, beta = 0, ycenter = 0;
+    double* d_cpdata = nullptr;          // x[M] | cy[M+1] | cyy[M+1]
+    double tabA[RMN_CP_LANES + 1];       // k log lam - gammaln(k) - lam + gammaln(2k+1), k = #steps
+    double cv = 0.0;                     // alpha log beta - gammaln(alpha)
+    // logistic
+    int64_t N = 0;
+    const double* d_X = nullptr;
+    const double* d_y = nullptr;
+    double prior_var = 1.0;
+};
+
+struct rmn_proposal {
+    int kind = 0;
+    int d = 0;
+    int adapt = 0;
+    double target = 0.0;
+    // rw / pcn
+    std::vector<double> h_L, h_Linv;     // full d x d row-major
+    double rho = 0.0;
+    // hmc
+    double eps = 0.0;
+    int nsteps = 1;
+    bool has_mass = false;
+    std::vector<double> h_chM, h_Minv, h_chMinv;
+    // device copies for the large-d path
+    double* d_L = nullptr;
+    // changepoint mix
+    double hscale = 0.0;
+    double p_cum[3] = {0.20, 0.40, 0.60};
+};
+
+struct rmn_sampler;
+struct SamplerImpl {
+    virtual ~SamplerImpl() {}
+    virtual size_t workspace_bytes() const = 0;
+    virtual int bind(void* ws) = 0;
+    virtual int set_state(const double* d_theta, cudaStream_t st) { return unsupported("set_state"); }
+    virtual int get_state(double* d_theta, double* d_lp, cudaStream_t st) { return unsupported("get_state"); }
+    virtual int cp_set_state(const int32_t*, const double*, const double*, const double*, cudaStream_t) { return unsupported("cp_set_state"); }
+    virtual int cp_get_state(int32_t*, double*, double*, double*, double*, cudaStream_t) { return unsupported("cp_get_state"); }
+    virtual int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t st) = 0;
+    virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }
+    virtual int diag_dim() const = 0;
+    virtual int reset_diag(cudaStream_t st) = 0;
+    virtual int reduce_diag(double* d_block, cudaStream_t st) = 0;
+    int unsupported(const char* what) {
+        rmn_set_error("%s is not available for this sampler family", what);
+        return RMN_ERR_UNSUPPORTED;
+    }
+    int64_t launches = 0;
+    int64_t step0 = 0;        // global MH step index of the next iteration (Philox counter)
+    int64_t diag_steps = 0;   // steps since the last diagnostics reset
+};
+
+struct rmn_sampler {
+    rmn_model* model = nullptr;
+    rmn_proposal* prop = nullptr;
+    int64_t K = 0, chain_offset = 0;
+    uint64_t seed = 0;
+    SamplerImpl* impl = nullptr;
+};
+
+// factories implemented per family
+SamplerImpl* make_small_gauss_sampler(rmn_sampler* s);
+SamplerImpl* make_changepoint_sampler(rmn_sampler* s);
+SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s);
+SamplerImpl* make_logistic_sampler(rmn_sampler* s);
+
+// pointwise evaluators implemented per family
+int gauss_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta, double* d_out,
+                    double* d_grad, cudaStream_t st);
+int cp_pointwise(rmn_model* m, int which, int64_t n, const int32_t* d_k, const double* d_cpx,
+                 const double* d_cpv, const double* d_sig, double* d_out, cudaStream_t st);
+int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta, double* d_out,
+                       double* d_grad, double* d_metric, cudaStream_t st);
+
+// generic helper kernels (util.cu)
+int rmn_fill_f64(double* p, int64_t n, double v, cudaStream_t st);
+int rmn_fill_i64(long long* p, int64_t n, long long v, cudaStream_t st);
+// per-chain sums -> diagnostics block; S1/S2 are [nd][K] (chain fastest)
+int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsteps, const double* S1, const double* S2,
+                          const long long* acc, const long long* ovf, double* d_block,
+                          cudaStream_t st);
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }

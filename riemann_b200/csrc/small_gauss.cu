@@ -1,0 +1,404 @@
+// riemann_b200 -- fully fused T-step MH kernel for small-d Gaussian targets.
+//
+// One thread owns one chain; theta, log-posterior and the AdaptScale state stay in
+// registers for all T iterations of a launch.  Replaces, per iteration,
+//   Sampler.sample                       riemann/samplers/sampler.py:72-90
+//   MetropolisRandomWalk.propose         riemann/proposals/randomwalk.py:21-26
+//   VanillaHMC.propose + leapfrog        riemann/proposals/hamiltonian.py:13-52,76-91
+//   pCN.propose                          riemann/proposals/randomwalk.py:88-100
+//   AdaptScaleProposal.adapt             riemann/proposals/adaptive.py:26-35
+//   MultiGaussianDist.log_likelihood / grad_log_likelihood   riemann/models/gaussian.py:49-58
+//   Model.log_posterior                  riemann/models/model.py:43-55
+// Arithmetic is fp64 throughout (the reference is fp64 numpy).
+// Internal state layout: theta[D][K] (chain fastest => coalesced loads/stores).
+#include "common.cuh"
+
+namespace {
+
+template <int D>
+struct SGParams {
+    static constexpr int TRI = D * (D + 1) / 2;
+    double mu[D];
+    double linv[TRI];       // L^{-1}, C = L L^T, packed lower row-major
+    double c1, c2;          // d*log(2 pi), logdetC   (gaussian.py:52)
+    int kind, adapt, nsteps, has_mass;
+    double target;
+    double lprop[TRI];      // chol(C0) for RW / pCN
+    double lpinv[TRI];      // its inverse (pCN)
+    double rho, rho_c;
+    double eps0;
+    double chM[TRI];
+    double Minv[D * D];
+    double chMinv[TRI];
+};
+
+struct SGState {
+    double* theta;          // [D][K]
+    double* lp;             // [K]
+    double* scale;          // [K]
+    long long* nsamp;       // [K]
+    long long* nacc;        // [K]
+    long long* dacc;        // [K] accepts since diagnostics reset
+    double* S1;             // [D][K]
+    double* S2;             // [D][K]
+};
+
+template <int D>
+__device__ __forceinline__ void tri_mv(const double* __restrict__ L, const double* x, double* y) {
+    // y = L x, L packed lower
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) s += L[i * (i + 1) / 2 + j] * x[j];
+        y[i] = s;
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void tri_tmv(const double* __restrict__ L, const double* x, double* y) {
+    // y = L^T x
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = j; i < D; ++i) s += L[i * (i + 1) / 2 + j] * x[i];
+        y[j] = s;
+    }
+}
+
+template <int D>
+__device__ __forceinline__ double gauss_logpost(const SGParams<D>& P, const double* th) {
+    double y[D], u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = th[i] - P.mu[i];
+    tri_mv<D>(P.linv, y, u);
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) q += u[i] * u[i];
+    const double ll = -0.5 * ((q + P.c1) + P.c2);
+    return combine_logpost(0.0, ll);          // log_prior == 0.0 (gaussian.py:46-47)
+}
+
+template <int D>
+__device__ __forceinline__ void gauss_grad(const SGParams<D>& P, const double* th, double* g) {
+    double y[D], u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = th[i] - P.mu[i];
+    tri_mv<D>(P.linv, y, u);
+    tri_tmv<D>(P.linv, u, g);
+#pragma unroll
+    for (int i = 0; i < D; ++i) g[i] = -g[i];
+}
+
+template <int D>
+__device__ __forceinline__ void velocity(const SGParams<D>& P, const double* p, double* v) {
+    if (P.has_mass) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) s += P.Minv[i * D + j] * p[j];
+            v[i] = s;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[i] = p[i];
+    }
+}
+
+template <int D, bool INJ>
+__global__ void __launch_bounds__(128)
+small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t K, int64_t T,
+                   int64_t step0, uint64_t seed, int64_t chain_offset, const double* __restrict__ inj_xi,
+                   const double* __restrict__ inj_u, rmn_trace_t tr) {
+    __shared__ SGParams<D> P;
+    {
+        const int nw = sizeof(SGParams<D>) / 4;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gparams);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&P);
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= K) return;
+
+    double th[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) th[i] = st.theta[(int64_t)i * K + c];
+    double lp = st.lp[c];
+    AdaptState ad{st.scale[c], st.nsamp[c], st.nacc[c]};
+    long long dacc = st.dacc[c];
+    double s1[D], s2[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { s1[i] = 0.0; s2[i] = 0.0; }
+    const RngKey rk(seed, (uint64_t)(chain_offset + c));
+    const TraceSel ts{tr.first, tr.thin > 0 ? tr.thin : 1};
+
+    for (int64_t t = 0; t < T; ++t) {
+        const uint64_t step = (uint64_t)(step0 + t);
+        double xi[D], uacc;
+        if (INJ) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) xi[i] = inj_xi[(t * K + c) * D + i];
+            uacc = inj_u[t * K + c];
+        } else {
+#pragma unroll
+            for (int b = 0; 4 * b < D; ++b) {
+                double v[4];
+                normal4(rk.block(step, (uint32_t)b), v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (4 * b + q < D) xi[4 * b + q] = v[q];
+            }
+            uacc = u01(rk.block(step, RMN_BLOCK_ACCEPT).x);
+        }
+
+        double q[D], lqr = 0.0;
+        if (P.kind == RMN_PROP_RW) {
+            double lx[D];
+            tri_mv<D>(P.lprop, xi, lx);
+#pragma unroll
+            for (int i = 0; i < D; ++i) q[i] = th[i] + ad.scale * lx[i];
+        } else if (P.kind == RMN_PROP_PCN) {
+            double lx[D], df[D], dr[D], uf[D], ur[D];
+            tri_mv<D>(P.lprop, xi, lx);
+#pragma unroll
+            for (int i = 0; i < D; ++i) q[i] = P.rho * th[i] + P.rho_c * lx[i];
+#pragma unroll
+            for (int i = 0; i < D; ++i) { df[i] = q[i] - P.rho * th[i]; dr[i] = th[i] - P.rho * q[i]; }
+            tri_mv<D>(P.lpinv, df, uf);
+            tri_mv<D>(P.lpinv, dr, ur);
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { a += uf[i] * uf[i]; b += ur[i] * ur[i]; }
+            lqr = -0.5 * (a - b) / (P.rho_c * P.rho_c);
+        } else {   // HMC / MALA
+            const double eps = P.adapt ? ad.scale * P.eps0 : P.eps0;
+            double p0[D], p[D], g[D], v[D];
+            if (P.has_mass) tri_mv<D>(P.chM, xi, p0);
+            else {
+#pragma unroll
+                for (int i = 0; i < D; ++i) p0[i] = xi[i];
+            }
+            gauss_grad<D>(P, th, g);
+#pragma unroll
+            for (int i = 0; i < D; ++i) p[i] = p0[i] + 0.5 * eps * g[i];
+            velocity<D>(P, p, v);
+#pragma unroll
+            for (int i = 0; i < D; ++i) q[i] = th[i] + eps * v[i];
+            for (int s = 1; s < P.nsteps; ++s) {
+                gauss_grad<D>(P, q, g);
+#pragma unroll
+                for (int i = 0; i < D; ++i) p[i] = p[i] + eps * g[i];
+                velocity<D>(P, p, v);
+#pragma unroll
+                for (int i = 0; i < D; ++i) q[i] = q[i] + eps * v[i];
+            }
+            gauss_grad<D>(P, q, g);
+#pragma unroll
+            for (int i = 0; i < D; ++i) p[i] = p[i] + 0.5 * eps * g[i];
+            double k0 = 0.0, k1 = 0.0;
+            if (P.has_mass) {
+                double w0[D], w1[D];
+                tri_mv<D>(P.chMinv, p0, w0);
+                tri_mv<D>(P.chMinv, p, w1);
+#pragma unroll
+                for (int i = 0; i < D; ++i) { k0 += w0[i] * w0[i]; k1 += w1[i] * w1[i]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < D; ++i) { k0 += p0[i] * p0[i]; k1 += p[i] * p[i]; }
+            }
+            lqr = 0.5 * (k1 - k0);
+        }
+
+        const double lpq = gauss_logpost<D>(P, q);
+        const bool acc = mh_accept(lpq, lp, lqr, uacc);
+        bool moved = false;
+        if (acc) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) { moved |= (q[i] != th[i]); th[i] = q[i]; }
+            lp = lpq;
+        }
+        if (P.adapt) ad.update(moved, P.target);
+        dacc += acc ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { s1[i] += th[i]; s2[i] += th[i] * th[i]; }
+
+        if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpq;
+        if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
+        if (tr.d_theta || tr.d_logpost) {
+            const long long r = ts.slot(t + 1);
+            if (r >= 0) {
+                if (tr.d_theta) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) tr.d_theta[(r * K + c) * D + i] = th[i];
+                }
+                if (tr.d_logpost) tr.d_logpost[r * K + c] = lp;
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        st.theta[(int64_t)i * K + c] = th[i];
+        st.S1[(int64_t)i * K + c] += s1[i];
+        st.S2[(int64_t)i * K + c] += s2[i];
+    }
+    st.lp[c] = lp;
+    st.scale[c] = ad.scale;
+    st.nsamp[c] = ad.nsamples;
+    st.nacc[c] = ad.naccepts;
+    st.dacc[c] = dacc;
+}
+
+template <int D>
+__global__ void sg_set_state_kernel(const SGParams<D>* __restrict__ gp, SGState st, int64_t K,
+                                    const double* __restrict__ theta_in) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    double th[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        th[i] = theta_in[c * D + i];
+        st.theta[(int64_t)i * K + c] = th[i];
+    }
+    st.lp[c] = gauss_logpost<D>(*gp, th);
+}
+
+template <int D>
+__global__ void sg_get_state_kernel(SGState st, int64_t K, double* theta_out, double* lp_out) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    if (theta_out) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) theta_out[c * D + i] = st.theta[(int64_t)i * K + c];
+    }
+    if (lp_out) lp_out[c] = st.lp[c];
+}
+
+__global__ void sg_get_adapt_kernel(SGState st, int64_t K, double* scale, int64_t* ns, int64_t* na) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    if (scale) scale[c] = st.scale[c];
+    if (ns) ns[c] = st.nsamp[c];
+    if (na) na[c] = st.nacc[c];
+}
+
+static void pack_lower(const std::vector<double>& full, int d, double* out) {
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j <= i; ++j) out[i * (i + 1) / 2 + j] = full[(size_t)i * d + j];
+}
+
+template <int D>
+struct SmallGaussSampler : SamplerImpl {
+    rmn_sampler* s;
+    SGState st{};
+    SGParams<D>* d_params = nullptr;
+    explicit SmallGaussSampler(rmn_sampler* s_) : s(s_) {}
+    ~SmallGaussSampler() override { if (d_params) cudaFree(d_params); }
+
+    size_t workspace_bytes() const override {
+        const size_t K = (size_t)s->K;
+        return align256(D * K * 8) * 3 + align256(K * 8) * 5 + 256;
+    }
+    int bind(void* ws) override {
+        const size_t K = (size_t)s->K;
+        char* p = (char*)ws;
+        st.theta = (double*)p; p += align256(D * K * 8);
+        st.S1 = (double*)p; p += align256(D * K * 8);
+        st.S2 = (double*)p; p += align256(D * K * 8);
+        st.lp = (double*)p; p += align256(K * 8);
+        st.scale = (double*)p; p += align256(K * 8);
+        st.nsamp = (long long*)p; p += align256(K * 8);
+        st.nacc = (long long*)p; p += align256(K * 8);
+        st.dacc = (long long*)p; p += align256(K * 8);
+
+        SGParams<D> h{};
+        const rmn_model* m = s->model;
+        const rmn_proposal* pr = s->prop;
+        for (int i = 0; i < D; ++i) h.mu[i] = m->h_mu[i];
+        for (int i = 0; i < SGParams<D>::TRI; ++i) h.linv[i] = m->h_linv[i];
+        h.c1 = D * log(2.0 * M_PI);
+        h.c2 = m->logdetC;
+        h.kind = pr->kind; h.adapt = pr->adapt; h.target = pr->target;
+        h.nsteps = pr->nsteps; h.has_mass = pr->has_mass ? 1 : 0;
+        h.rho = pr->rho; h.rho_c = sqrt(1.0 - pr->rho * pr->rho);
+        h.eps0 = pr->eps;
+        if (!pr->h_L.empty()) pack_lower(pr->h_L, D, h.lprop);
+        if (!pr->h_Linv.empty()) pack_lower(pr->h_Linv, D, h.lpinv);
+        if (pr->has_mass) {
+            pack_lower(pr->h_chM, D, h.chM);
+            pack_lower(pr->h_chMinv, D, h.chMinv);
+            for (int i = 0; i < D * D; ++i) h.Minv[i] = pr->h_Minv[i];
+        }
+        RMN_CUDA(cudaMalloc(&d_params, sizeof(h)));
+        RMN_CUDA(cudaMemcpy(d_params, &h, sizeof(h), cudaMemcpyHostToDevice));
+        RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        int rc = rmn_fill_f64(st.scale, s->K, 1.0, 0);
+        if (rc) return rc;
+        RMN_CUDA(cudaDeviceSynchronize());
+        return RMN_OK;
+    }
+    unsigned grid() const { return (unsigned)((s->K + 127) / 128); }
+
+    int set_state(const double* d_theta, cudaStream_t stream) override {
+        sg_set_state_kernel<D><<<grid(), 128, 0, stream>>>(d_params, st, s->K, d_theta);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int get_state(double* d_theta, double* d_lp, cudaStream_t stream) override {
+        sg_get_state_kernel<D><<<grid(), 128, 0, stream>>>(st, s->K, d_theta, d_lp);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
+        rmn_trace_t t0{};
+        if (tr) t0 = *tr;
+        if (t0.thin <= 0) t0.thin = 1;
+        if (inj) {
+            RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+            small_gauss_kernel<D, true><<<grid(), 128, 0, stream>>>(
+                d_params, st, s->K, T, step0, s->seed, s->chain_offset, inj->d_xi, inj->d_u, t0);
+        } else {
+            small_gauss_kernel<D, false><<<grid(), 128, 0, stream>>>(
+                d_params, st, s->K, T, step0, s->seed, s->chain_offset, nullptr, nullptr, t0);
+        }
+        RMN_KERNEL_CHECK(); launches++;
+        step0 += T; diag_steps += T;
+        return RMN_OK;
+    }
+    int get_adapt(double* sc, int64_t* ns, int64_t* na, cudaStream_t stream) override {
+        sg_get_adapt_kernel<<<grid(), 128, 0, stream>>>(st, s->K, sc, ns, na);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int diag_dim() const override { return D; }
+    int reset_diag(cudaStream_t stream) override {
+        RMN_CUDA(cudaMemsetAsync(st.S1, 0, (size_t)D * s->K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.S2, 0, (size_t)D * s->K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)s->K * 8, stream));
+        diag_steps = 0;
+        return RMN_OK;
+    }
+    int reduce_diag(double* d_block, cudaStream_t stream) override {
+        launches++;
+        return rmn_reduce_diag_block(s->K, D, diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
+    }
+};
+
+}  // namespace
+
+SamplerImpl* make_small_gauss_sampler(rmn_sampler* s) {
+    switch (s->model->d) {
+        case 1: return new SmallGaussSampler<1>(s);
+        case 2: return new SmallGaussSampler<2>(s);
+        case 3: return new SmallGaussSampler<3>(s);
+        case 4: return new SmallGaussSampler<4>(s);
+        case 5: return new SmallGaussSampler<5>(s);
+        case 6: return new SmallGaussSampler<6>(s);
+        case 7: return new SmallGaussSampler<7>(s);
+        case 8: return new SmallGaussSampler<8>(s);
+        default: return nullptr;
+    }
+}

@@ -1,0 +1,60 @@
+"""
+Multi-GPU plumbing: chains shard across ranks (each rank owns K/G chains and the Philox
+substreams of its global chain ids); the only exchange is the per-batch diagnostics
+all-reduce of a (4 + 3 nd)-double block.  torch.distributed
+(NCCL on GPUs, gloo in the CPU tests) carries it.
+"""
+import numpy as np
+
+
+def rank_world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def shard_chains(K_total, rank=None, world=None):
+    """Contiguous split of K_total chains: returns (chain_offset, K_local) for this rank."""
+    if rank is None or world is None:
+        rank, world = rank_world()
+    base, rem = divmod(int(K_total), int(world))
+    k_local = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, k_local
+
+
+def reduce_block(blk):
+    """Sum a diagnostics block over ranks (no-op without an initialised process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        steps = blk[1].clone()
+        dist.all_reduce(blk, op=dist.ReduceOp.SUM)
+        blk[1] = steps            # steps-per-chain is identical on every rank, not additive
+    return blk
+
+
+def summarize_block(b):
+    """
+    b = [K, n, accepts, overflows, sum_c m_c (nd), sum_c m_c^2 (nd), sum_c v_c (nd)].
+    tau = n B / W with B the variance of the chain means and W the mean within-chain
+    variance; ESS = K n / tau; R-hat from (n-1)/n W + B.
+    """
+    b = np.asarray(b, dtype=np.float64)
+    nd = (len(b) - 4) // 3
+    K, n = b[0], b[1]
+    sm, sm2, sv = b[4:4 + nd], b[4 + nd:4 + 2 * nd], b[4 + 2 * nd:4 + 3 * nd]
+    mean = sm / K
+    with np.errstate(divide="ignore", invalid="ignore"):
+        B = (sm2 - sm * sm / K) / max(K - 1.0, 1.0)
+        W = sv / K * (n / max(n - 1.0, 1.0))
+        tau = np.where(W > 0, n * B / W, np.nan)
+        ess = np.where(tau > 0, K * n / tau, np.nan)
+        rhat = np.sqrt(((n - 1.0) / n * W + B) / W)
+    return {"chains": int(K), "steps": int(n), "accept_rate": b[2] / max(K * n, 1.0),
+            "overflows": int(b[3]), "mean": mean, "var": W + B, "within_var": W,
+            "between_var": B, "tau": tau, "ess": ess, "rhat": rhat,
+            "min_ess": float(np.nanmin(ess)) if nd else float("nan")}

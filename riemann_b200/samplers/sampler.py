@@ -1,0 +1,390 @@
+"""
+Sampler -- the many-chain, device-resident counterpart of riemann/samplers/sampler.py:28-90.
+
+Same constructor and methods as the reference (``Sampler(model, proposal, theta0)``,
+``run(Nsamples, Nburn=0, Nthin=1)``, ``sample()``, ``current_state()``, ``_add_state``)
+and the same directly-read attributes ``_chain_thetas`` / ``_chain_logpost``.  Extra
+keyword arguments select K chains, the Philox seed and the global chain offset (for
+sharding over GPUs).  One ``run`` is one (or a few) kernel launches; the host never
+sees an individual MH step.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from ..models.changepoint import (ChangepointParams, ChangepointRegression1D, pack_states,
+                                  unpack_state)
+from ..models.model import DeviceModel
+from ..proposals.proposal import DeviceProposal
+from ..sampling_errors import ParameterError
+
+LANES = _lib.CP_LANES
+TRACE_BYTES_LIMIT = 8 << 30
+
+
+class ChangepointTrace(object):
+    """History of K > 1 changepoint chains: arrays indexed [record, chain]."""
+
+    def __init__(self, k, cpx, cpv, sig):
+        self.k, self.cpx, self.cpv, self.sig = k, cpx, cpv, sig
+
+    def __len__(self):
+        return self.k.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            r, c = idx
+            return unpack_state(self.k[r, c], self.cpx[r, c], self.cpv[r, c], self.sig[r, c])
+        if isinstance(idx, slice):
+            return ChangepointTrace(self.k[idx], self.cpx[idx], self.cpv[idx], self.sig[idx])
+        return [self[idx, c] for c in range(self.k.shape[1])]
+
+
+class Sampler(object):
+    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0):
+        """
+        :param theta0: starting point.  Fixed-d models: shape (d,) (shared by all K
+            chains) or (K, d).  Changepoint model: a ChangepointParams or a list of K.
+        :param K: number of independent chains on this device (default 1, the reference's case)
+        :param seed, chain_offset: Philox key and the global id of chain 0 on this device
+        """
+        if not isinstance(model, DeviceModel):
+            raise ParameterError("model has no device kernel: riemann_b200 samples only device "
+                                 "models (there is no CPU fallback)")
+        if not isinstance(proposal, DeviceProposal):
+            raise ParameterError("proposal has no device kernel")
+        if proposal._model is not None and proposal._model is not model:
+            raise ParameterError("the proposal's gradient/metric belongs to a different model")
+        if getattr(model, "_handle", None) is None:
+            raise ParameterError("model has no data/device handle yet")
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self.model = model
+        self.proposal = proposal
+        self._is_cp = isinstance(model, ChangepointRegression1D)
+
+        if self._is_cp:
+            if isinstance(theta0, ChangepointParams):
+                states = [theta0] * (K or 1)
+            else:
+                states = list(theta0)
+                if K is not None and K != len(states):
+                    raise ParameterError("K does not match the number of start states")
+            self.K = len(states)
+            self.d = model.Ndim
+            self._squeeze = isinstance(theta0, ChangepointParams) and self.K == 1
+        else:
+            th = np.asarray(theta0, dtype=np.float64)
+            self._scalar_theta0 = (th.ndim == 0)
+            th = np.atleast_1d(th)
+            if th.ndim == 1:
+                th = np.tile(th[None, :], (K or 1, 1))
+            elif K is not None and K != th.shape[0]:
+                raise ParameterError("K does not match theta0.shape[0]")
+            if th.ndim != 2 or th.shape[1] != model.Ndim:
+                raise ParameterError("theta and model have incompatible shapes {} vs d={}"
+                                     .format(th.shape, model.Ndim))
+            self.K, self.d = th.shape
+            self._squeeze = (self.K == 1 and np.ndim(theta0) <= 1)
+
+        lib = _lib.load()
+        ph = proposal._get_handle(self.d)
+        nbytes = lib.rmn_sampler_workspace_bytes(model._handle, ph, self.K)
+        if nbytes == 0:
+            raise ParameterError(lib.rmn_last_error().decode() or
+                                 "no device kernel for this model/proposal pair")
+        self._ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        h = C.c_void_p()
+        _lib.check(lib.rmn_sampler_create(C.byref(h), model._handle, ph, self.K, int(chain_offset),
+                                          int(seed), _lib.ptr(self._ws), nbytes))
+        self._handle = h
+        self.seed, self.chain_offset = int(seed), int(chain_offset)
+        self.total_steps = 0
+
+        if self._is_cp:
+            self._cp_upload(states)
+        else:
+            t = torch.as_tensor(np.ascontiguousarray(th), device="cuda")
+            _lib.check(lib.rmn_sampler_set_state(h, _lib.ptr(t), _lib.stream_ptr()))
+        th_now, lp_now = self._download_state()
+        self._set_history([th_now], [lp_now])
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.load().rmn_sampler_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state i/o
+    def _cp_upload(self, states):
+        torch = self._torch
+        k, cpx, cpv, sig = pack_states(states)
+        bufs = [torch.as_tensor(a, device="cuda") for a in (k, cpx, cpv, sig)]
+        _lib.check(_lib.load().rmn_sampler_cp_set_state(
+            self._handle, *[_lib.ptr(b) for b in bufs], _lib.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def _download_state(self):
+        """Current state of all chains as host arrays (device -> host copy)."""
+        torch, lib, K = self._torch, _lib.load(), self.K
+        lp = torch.empty(K, dtype=torch.float64, device="cuda")
+        if self._is_cp:
+            k = torch.empty(K, dtype=torch.int32, device="cuda")
+            cpx = torch.empty((K, LANES), dtype=torch.float64, device="cuda")
+            cpv = torch.empty((K, LANES), dtype=torch.float64, device="cuda")
+            sig = torch.empty(K, dtype=torch.float64, device="cuda")
+            _lib.check(lib.rmn_sampler_cp_get_state(self._handle, _lib.ptr(k), _lib.ptr(cpx),
+                                                    _lib.ptr(cpv), _lib.ptr(sig), _lib.ptr(lp),
+                                                    _lib.stream_ptr()))
+            return (k.cpu().numpy(), cpx.cpu().numpy(), cpv.cpu().numpy(), sig.cpu().numpy()), \
+                lp.cpu().numpy()
+        th = torch.empty((K, self.d), dtype=torch.float64, device="cuda")
+        _lib.check(lib.rmn_sampler_get_state(self._handle, _lib.ptr(th), _lib.ptr(lp),
+                                             _lib.stream_ptr()))
+        return th.cpu().numpy(), lp.cpu().numpy()
+
+    def state_tensors(self):
+        """Current states as DEVICE tensors (theta[K,d], logpost[K]); fixed-d models only."""
+        torch = self._torch
+        th = torch.empty((self.K, self.d), dtype=torch.float64, device="cuda")
+        lp = torch.empty(self.K, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().rmn_sampler_get_state(self._handle, _lib.ptr(th), _lib.ptr(lp),
+                                                     _lib.stream_ptr()))
+        return th, lp
+
+    def set_state(self, theta):
+        """Replace the states of all chains (re-evaluates log-posteriors on the device)."""
+        if self._is_cp:
+            self._cp_upload(list(theta))
+        else:
+            torch = self._torch
+            t = torch.as_tensor(np.ascontiguousarray(np.asarray(theta, dtype=np.float64)
+                                                     .reshape(self.K, self.d)), device="cuda")
+            _lib.check(_lib.load().rmn_sampler_set_state(self._handle, _lib.ptr(t), _lib.stream_ptr()))
+        th, lp = self._download_state()
+        self._set_history([th], [lp])
+
+    # ------------------------------------------------------------------ history
+    def _set_history(self, thetas, logposts):
+        """thetas/logposts: lists of per-record host arrays over all K chains."""
+        if self._is_cp:
+            k = np.stack([t[0] for t in thetas]); cpx = np.stack([t[1] for t in thetas])
+            cpv = np.stack([t[2] for t in thetas]); sig = np.stack([t[3] for t in thetas])
+            lp = np.stack(logposts)
+            if self._squeeze:
+                self._chain_thetas = [unpack_state(k[r, 0], cpx[r, 0], cpv[r, 0], sig[r, 0])
+                                      for r in range(k.shape[0])]
+                self._chain_logpost = [float(v) for v in lp[:, 0]]
+            else:
+                self._chain_thetas = ChangepointTrace(k, cpx, cpv, sig)
+                self._chain_logpost = lp
+        else:
+            th = np.stack(thetas)
+            lp = np.stack(logposts)
+            if self._squeeze:
+                self._chain_thetas = [th[r, 0].copy() for r in range(th.shape[0])]
+                self._chain_logpost = [float(v) for v in lp[:, 0]]
+            else:
+                self._chain_thetas = th
+                self._chain_logpost = lp
+
+    def current_state(self):
+        """(theta, log_posterior) of the current state (sampler.py:56-60)."""
+        if self._squeeze:
+            return self._chain_thetas[-1], self._chain_logpost[-1]
+        if self._is_cp:
+            return self._chain_thetas[len(self._chain_thetas) - 1], self._chain_logpost[-1]
+        return self._chain_thetas[-1], self._chain_logpost[-1]
+
+    def _add_state(self, theta, logpost):
+        """sampler.py:62-70 hook: push an explicit state (it becomes the chain's state)."""
+        self.set_state([theta] * self.K if self._is_cp else
+                       np.tile(np.atleast_1d(theta)[None, :], (self.K, 1)) if np.ndim(theta) <= 1
+                       else theta)
+
+    # ------------------------------------------------------------------ running
+    def _run_device(self, T, first_dev, thin, nrec, inject=None, extras=False):
+        torch, K, d = self._torch, self.K, self.d
+        tr = _lib.Trace()
+        tr.first, tr.thin = int(first_dev), int(thin)
+        bufs = {}
+        if nrec > 0:
+            bufs["lp"] = torch.empty((nrec, K), dtype=torch.float64, device="cuda")
+            tr.d_logpost = bufs["lp"].data_ptr()
+            if self._is_cp:
+                bufs["k"] = torch.zeros((nrec, K), dtype=torch.int32, device="cuda")
+                bufs["cpx"] = torch.empty((nrec, K, LANES), dtype=torch.float64, device="cuda")
+                bufs["cpv"] = torch.empty((nrec, K, LANES), dtype=torch.float64, device="cuda")
+                bufs["sig"] = torch.empty((nrec, K), dtype=torch.float64, device="cuda")
+                tr.d_k, tr.d_cpx = bufs["k"].data_ptr(), bufs["cpx"].data_ptr()
+                tr.d_cpv, tr.d_sig = bufs["cpv"].data_ptr(), bufs["sig"].data_ptr()
+            else:
+                bufs["theta"] = torch.empty((nrec, K, d), dtype=torch.float64, device="cuda")
+                tr.d_theta = bufs["theta"].data_ptr()
+        if extras:
+            bufs["prop_lp"] = torch.empty((T, K), dtype=torch.float64, device="cuda")
+            bufs["acc"] = torch.empty((T, K), dtype=torch.uint8, device="cuda")
+            tr.d_prop_logpost, tr.d_accepted = bufs["prop_lp"].data_ptr(), bufs["acc"].data_ptr()
+        inj = None
+        if inject is not None:
+            inj = _lib.Inject()
+            keep = []
+            for name in ("xi", "u", "tape"):
+                if name in inject and inject[name] is not None:
+                    t = torch.as_tensor(np.ascontiguousarray(inject[name], dtype=np.float64),
+                                        device="cuda")
+                    keep.append(t)
+                    setattr(inj, "d_" + name, t.data_ptr())
+            bufs["_inj"] = keep
+        _lib.check(_lib.load().rmn_sampler_run(
+            self._handle, int(T), C.byref(inj) if inj is not None else None, C.byref(tr),
+            _lib.stream_ptr()))
+        self.total_steps += int(T)
+        return bufs
+
+    def run(self, Nsamples, Nburn=0, Nthin=1, trace=True, inject=None, extras=False):
+        """
+        Run every chain for Nsamples MH iterations (sampler.py:44-54).  The history
+        afterwards is ``[start state + Nsamples states][Nburn::Nthin]`` exactly as in the
+        reference; with ``trace=False`` only the final state is kept (no trace memory).
+        """
+        T = int(Nsamples)
+        if T < 0 or Nburn < 0 or Nthin < 1:
+            raise ParameterError("need Nsamples >= 0, Nburn >= 0, Nthin >= 1")
+        start_th, start_lp = self._last_record()
+        if not trace:
+            out = self._run_device(T, 0, 1, 0, inject, extras)
+            th, lp = self._download_state()
+            self._set_history([th], [lp])
+            self._refresh_adapt()
+            return out if extras else None
+        first_dev = Nburn if Nburn >= 1 else Nthin
+        nrec = 0 if first_dev > T else (T - first_dev) // Nthin + 1
+        per_rec = self.K * ((2 * LANES + 3) if self._is_cp else (self.d + 1)) * 8
+        if nrec * per_rec > TRACE_BYTES_LIMIT:
+            raise ParameterError("trace of {} records x {} chains needs {:.1f} GB; raise Nthin/Nburn "
+                                 "or pass trace=False".format(nrec, self.K, nrec * per_rec / 2**30))
+        bufs = self._run_device(T, first_dev, Nthin, nrec, inject, extras)
+        thetas, lps = [], []
+        if Nburn == 0:
+            thetas.append(start_th)
+            lps.append(start_lp)
+        if nrec > 0:
+            lp = bufs["lp"].cpu().numpy()
+            if self._is_cp:
+                k, cpx, cpv, sig = (bufs[n].cpu().numpy() for n in ("k", "cpx", "cpv", "sig"))
+                thetas += [(k[r], cpx[r], cpv[r], sig[r]) for r in range(nrec)]
+            else:
+                th = bufs["theta"].cpu().numpy()
+                thetas += [th[r] for r in range(nrec)]
+            lps += [lp[r] for r in range(nrec)]
+        if not thetas:          # Nburn > Nsamples: empty history, like the reference's slice
+            th, lp = self._download_state()
+            self._set_history([th], [lp])
+            if self._squeeze:
+                self._chain_thetas, self._chain_logpost = [], []
+        else:
+            self._set_history(thetas, lps)
+        self._final_state_cache = None
+        self._refresh_adapt()
+        if extras:
+            return {"prop_logpost": bufs["prop_lp"].cpu().numpy(),
+                    "accepted": bufs["acc"].cpu().numpy().astype(bool)}
+        return None
+
+    def run_injected(self, xi=None, u=None, tape=None, Nburn=0, Nthin=1):
+        """
+        Replay a given noise stream instead of Philox (parity mode):
+        fixed-d: xi[T, K, d] (or [T, d] for K = 1) and u[T, K]; changepoint: tape[T, K, NSLOT].
+        Returns {'prop_logpost': [T,K], 'accepted': [T,K]}.
+        """
+        if self._is_cp:
+            tape = np.asarray(tape, dtype=np.float64)
+            if tape.ndim == 2:
+                tape = tape[:, None, :]
+            if tape.shape[1:] != (self.K, _lib.CP_NSLOT):
+                raise ParameterError("tape must have shape [T, K, {}]".format(_lib.CP_NSLOT))
+            T, inj = tape.shape[0], {"tape": tape}
+        else:
+            xi = np.asarray(xi, dtype=np.float64)
+            u = np.asarray(u, dtype=np.float64)
+            if xi.ndim == 2:
+                xi = xi[:, None, :]
+            if u.ndim == 1:
+                u = u[:, None]
+            if xi.shape[1:] != (self.K, self.d) or u.shape != xi.shape[:2]:
+                raise ParameterError("xi must be [T, K, d] and u [T, K]")
+            T, inj = xi.shape[0], {"xi": xi, "u": u}
+        return self.run(T, Nburn, Nthin, trace=True, inject=inj, extras=True)
+
+    def _last_record(self):
+        th, lp = self._download_state()
+        return th, lp
+
+    def sample(self):
+        """One MH iteration for every chain (sampler.py:72-90); appends to the history."""
+        prev_t, prev_l = self._chain_thetas, self._chain_logpost
+        self.run(1, 1, 1)
+        new_t, new_l = self._chain_thetas, self._chain_logpost
+        if self._squeeze:
+            self._chain_thetas = list(prev_t) + list(new_t)
+            self._chain_logpost = list(prev_l) + list(new_l)
+        elif self._is_cp:
+            self._chain_thetas = ChangepointTrace(
+                *[np.concatenate([getattr(prev_t, n), getattr(new_t, n)]) for n in ("k", "cpx", "cpv", "sig")])
+            self._chain_logpost = np.concatenate([prev_l, new_l])
+        else:
+            self._chain_thetas = np.concatenate([prev_t, new_t])
+            self._chain_logpost = np.concatenate([prev_l, new_l])
+        return self.current_state()
+
+    # ------------------------------------------------------------------ adaptation / diagnostics
+    def _refresh_adapt(self):
+        p = self.proposal
+        if not getattr(p, "_adaptive", False):
+            return
+        torch, K = self._torch, self.K
+        sc = torch.empty(K, dtype=torch.float64, device="cuda")
+        ns = torch.empty(K, dtype=torch.int64, device="cuda")
+        na = torch.empty(K, dtype=torch.int64, device="cuda")
+        _lib.check(_lib.load().rmn_sampler_get_adapt(self._handle, _lib.ptr(sc), _lib.ptr(ns),
+                                                     _lib.ptr(na), _lib.stream_ptr()))
+        sc, ns, na = sc.cpu().numpy(), ns.cpu().numpy(), na.cpu().numpy()
+        rate = na / np.maximum(ns, 1)
+        if K == 1:
+            p.scale, p.Nsamples, p.Naccepts, p.accept_rate = float(sc[0]), int(ns[0]), int(na[0]), float(rate[0])
+        else:
+            p.scale, p.Nsamples, p.Naccepts, p.accept_rate = sc, ns, na, rate
+        if hasattr(p, "eps0"):
+            p.eps = p.scale * p.eps0                    # hamiltonian.py:102
+
+    def reset_diagnostics(self):
+        _lib.check(_lib.load().rmn_sampler_reset_diagnostics(self._handle, _lib.stream_ptr()))
+
+    def diagnostics_block(self):
+        """Device tensor with the per-device diagnostics block (see riemann_b200.h)."""
+        torch = self._torch
+        nd = _lib.load().rmn_sampler_diag_dim(self._handle)
+        blk = torch.zeros(4 + 3 * nd, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().rmn_sampler_reduce_diagnostics(self._handle, _lib.ptr(blk),
+                                                              _lib.stream_ptr()))
+        return blk
+
+    def diagnostics(self, allreduce=True):
+        """
+        Acceptance rate, per-functional posterior mean/variance, split-free R-hat, tau and
+        total ESS over ALL chains since the last reset.  With torch.distributed initialised
+        the block is summed over ranks first (one small NCCL all-reduce per batch).
+        """
+        from ..distributed import reduce_block, summarize_block
+        blk = self.diagnostics_block()
+        if allreduce:
+            blk = reduce_block(blk)
+        return summarize_block(blk.cpu().numpy())
+
+    @property
+    def launch_count(self):
+        return int(_lib.load().rmn_sampler_launch_count(self._handle))

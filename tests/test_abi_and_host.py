@@ -1,0 +1,145 @@
+"""
+CPU: the C-ABI library loads and exports every symbol include/riemann_b200.h declares
+(no compute calls), plus the host-side logic (sharding, diagnostics maths, error mapping,
+the 2-rank gloo all-reduce of the diagnostics block).
+"""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from riemann_b200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    hdr = open(os.path.join(ROOT, "include", "riemann_b200.h")).read()
+    declared = set(re.findall(r"\b(rmn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = lib.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), "library does not export %s" % name
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    assert L.rmn_version() == 100
+
+
+def test_header_constants_match_host_and_oracle(lib):
+    from oracle import riemann_port as port
+    hdr = open(os.path.join(ROOT, "include", "riemann_b200.h")).read()
+    val = lambda n: int(re.search(r"#define %s (\d+)" % n, hdr).group(1))
+    assert val("RMN_CP_LANES") == lib.CP_LANES
+    assert val("RMN_CP_SLOT_XI") == lib.CP_SLOT["xi"] == port.CP_SLOT_XI
+    assert val("RMN_CP_SLOT_ACC") == lib.CP_SLOT["acc"] == port.CP_SLOT_ACC
+    assert val("RMN_CP_SLOT_N") == port.CP_SLOT_N and val("RMN_CP_SLOT_S") == port.CP_SLOT_S
+    assert lib.CP_NSLOT == port.cp_nslot(lib.CP_LANES)
+    assert val("RMN_SMALL_D_MAX") == lib.SMALL_D_MAX
+
+
+def test_bad_arguments_return_param_error_without_a_gpu(lib):
+    import ctypes as C
+    from riemann_b200 import ParameterError
+    L = lib.load()
+    h = C.c_void_p()
+    # L with a non-positive diagonal -> RMN_ERR_PARAM -> ParameterError (host-only check)
+    bad = np.zeros((2, 2))
+    rc = L.rmn_proposal_rw_create(C.byref(h), 2, lib.ptr(bad), 0, 0.25)
+    assert rc == lib.RMN_ERR_PARAM
+    with pytest.raises(ParameterError):
+        lib.check(rc)
+    assert b"Cholesky" in L.rmn_last_error()
+    assert L.rmn_proposal_hmc_create(C.byref(h), 2, -1.0, 1, None, None, None, 0, 0.75) == lib.RMN_ERR_PARAM
+    assert L.rmn_proposal_mmala_create(C.byref(h), 0, 0.1) == lib.RMN_ERR_PARAM
+    assert L.rmn_proposal_changepoint_create(C.byref(h), 2.0, None) == lib.RMN_OK
+    assert L.rmn_proposal_destroy(h) == lib.RMN_OK
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from riemann_b200.models.gaussian import MultiGaussianDist
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MultiGaussianDist(np.zeros(2), np.eye(2))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "riemann_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_shard_chains():
+    from riemann_b200.distributed import shard_chains
+    for K, G in [(65536, 8), (10, 3), (7, 8), (16384, 4)]:
+        parts = [shard_chains(K, r, G) for r in range(G)]
+        assert sum(k for _, k in parts) == K
+        off = 0
+        for o, k in parts:
+            assert o == off
+            off += k
+
+
+def test_summarize_block_matches_oracle_estimator():
+    from oracle import ess
+    from riemann_b200.distributed import summarize_block
+    rng = np.random.default_rng(1)
+    K, n, d, phi = 300, 2000, 3, 0.7
+    x = np.zeros((n, K, d))
+    x[0] = rng.standard_normal((K, d))
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + np.sqrt(1 - phi ** 2) * rng.standard_normal((K, d))
+    m = x.mean(0)
+    v = x.var(0)
+    blk = np.concatenate([[K, n, 0.3 * K * n, 0], m.sum(0), (m * m).sum(0), v.sum(0)])
+    out = summarize_block(blk)
+    ess_o, tau_o, rhat_o = ess.ess_from_chain_moments(n, m, x.var(0, ddof=1))
+    assert np.allclose(out["tau"], tau_o, rtol=1e-9)
+    assert np.allclose(out["ess"], ess_o, rtol=1e-9)
+    assert np.allclose(out["rhat"], rhat_o, rtol=1e-9)
+    assert abs(out["accept_rate"] - 0.3) < 1e-12
+    assert np.all(np.abs(out["tau"] - (1 + phi) / (1 - phi)) < 1.5)
+
+
+_GLOO = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from riemann_b200.distributed import reduce_block, shard_chains, summarize_block
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+K_total, n, nd = 10, 50, 2
+off, k = shard_chains(K_total)
+rng = np.random.default_rng(0)
+m = rng.standard_normal((K_total, nd)); v = rng.uniform(0.5, 1.5, (K_total, nd))
+mine = slice(off, off + k)
+blk = np.concatenate([[k, n, 7.0 * k, 0], m[mine].sum(0), (m[mine]**2).sum(0), v[mine].sum(0)])
+out = reduce_block(torch.tensor(blk))
+full = np.concatenate([[K_total, n, 7.0 * K_total, 0], m.sum(0), (m**2).sum(0), v.sum(0)])
+assert np.allclose(out.numpy(), full), (out.numpy(), full)
+s = summarize_block(out.numpy())
+assert s["chains"] == K_total and s["steps"] == n
+dist.barrier(); dist.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_diagnostics_allreduce_two_ranks_gloo(tmp_path):
+    script = tmp_path / "gloo_worker.py"
+    script.write_text(_GLOO)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29617",
+                        str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,224 @@
+"""
+GPU parity for the changepoint kernel (riemann_b200/csrc/changepoint.cu): config 2.
+
+* the stream the REFERENCE drew (tests/golden/changepoint.npz: 4 chains x 3000 steps of
+  examples/test_changepoint.py's proposal on riemann/models/changepoint.py) is replayed on
+  the device; states, log-posteriors and decisions must match at every step;
+* pointwise log-posterior / likelihood / prior vs the numpy oracle, including the invalid
+  states the reference rejects through nan/inf -> -inf;
+* long Philox runs agree distributionally with oracle chains;
+* full-size (65,536 chains) self-consistency.
+
+Tolerance: 1e-9 relative-or-absolute (fp64 device vs fp64 numpy; the device sums residuals
+per segment from prefix sums, numpy sums them per datum); decisions identical.
+"""
+import numpy as np
+import pytest
+
+from gpu_helpers import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _setup(g=None):
+    from oracle import riemann_port as port
+    from riemann_b200.models.changepoint import ChangepointRegression1D
+    from riemann_b200.proposals.changepoint import ChangepointRegression1DProp
+    if g is not None:
+        x, y = g["x"], g["y"]
+        xmin, xmax, lamb, kmax, alpha, beta, hscale = g["hyper"]
+    else:
+        pm, pp, _, _ = port.make_changepoint_problem()
+        x, y, xmin, xmax, lamb, kmax, alpha, beta, hscale = (pm.x, pm.y, pm.xmin, pm.xmax, pm.lamb,
+                                                             pm.kmax, pm.alpha, pm.beta, pp.hscale)
+    dm = ChangepointRegression1D(x, y, xmin, xmax, lamb, int(kmax), alpha, beta)
+    dp = ChangepointRegression1DProp(dm, hscale)
+    om = port.ChangepointRegression1D(x, y, xmin, xmax, lamb, kmax, alpha, beta)
+    op = port.ChangepointRegression1DProp(om, hscale)
+    return dm, dp, om, op
+
+
+def test_injected_chains_match_reference(golden):
+    from riemann_b200 import Sampler
+    from riemann_b200.models.changepoint import ChangepointParams
+    g = golden("changepoint")
+    dm, dp, _, _ = _setup(g)
+    nch, T = g["tape"].shape[:2]
+    th0 = [ChangepointParams(g["cpx"][c, 0, :g["k"][c, 0]], g["cpv"][c, 0, :g["k"][c, 0] + 1],
+                             g["sig"][c, 0]) for c in range(nch)]
+    s = Sampler(dm, dp, th0)
+    ex = s.run_injected(tape=np.transpose(g["tape"], (1, 0, 2)))
+    tr = s._chain_thetas
+    assert tr.k.shape == (T + 1, nch)
+    assert np.array_equal(tr.k.T, g["k"])
+    assert relerr(np.transpose(tr.cpx, (1, 0, 2)), g["cpx"]) < TOL
+    assert relerr(np.transpose(tr.cpv, (1, 0, 2)), g["cpv"]) < TOL
+    assert relerr(tr.sig.T, g["sig"]) < TOL
+    assert relerr(s._chain_logpost.T, g["logpost"]) < TOL
+    assert relerr(ex["prop_logpost"].T, g["prop_logpost"]) < TOL
+    ref_acc = g["logpost"][:, 1:] != g["logpost"][:, :-1]
+    # a k=0 cpx move re-proposes the same state (accepted, unchanged): compare where it matters
+    moved = ex["accepted"].T & (ex["prop_logpost"].T != g["logpost"][:, :-1])
+    assert np.array_equal(moved, ref_acc)
+
+
+def test_single_chain_api_matches_reference_script(golden):
+    """K = 1 keeps the reference's list-of-ChangepointParams history (test_changepoint.py:87)."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models.changepoint import ChangepointParams
+    g = golden("changepoint")
+    dm, dp, _, _ = _setup(g)
+    th0 = ChangepointParams([2.0], [1.0, 3.0], 0.1)
+    s = Sampler(dm, dp, th0)
+    T = 500
+    s.run_injected(tape=g["tape"][1, :T])
+    assert isinstance(s._chain_thetas, list) and len(s._chain_thetas) == T + 1
+    for t in (0, 1, 77, T):
+        th = s._chain_thetas[t]
+        k = g["k"][1, t]
+        assert len(th.cpx) == k and len(th.cpv) == k + 1
+        assert relerr(th.cpx, g["cpx"][1, t, :k]) < TOL and relerr(th.cpv, g["cpv"][1, t, :k + 1]) < TOL
+    assert relerr(s._chain_logpost, g["logpost"][1, :T + 1]) < TOL
+
+
+def test_pointwise_including_invalid_states(golden):
+    from oracle import riemann_port as port
+    from riemann_b200.models.changepoint import ChangepointParams
+    g = golden("changepoint")
+    dm, _, om, _ = _setup(g)
+    rng = np.random.default_rng(0)
+    states = []
+    for _ in range(200):
+        k = int(rng.integers(0, 12))
+        states.append((np.sort(rng.uniform(1.0, 3.0, k)), rng.uniform(0.5, 3.5, k + 1), rng.uniform(0.03, 0.5)))
+    states += [
+        (np.array([2.5, 1.5]), np.array([1.0, 2.0, 3.0]), 0.1),      # unsorted -> -inf
+        (np.array([0.5]), np.array([1.0, 2.0]), 0.1),                # below xmin -> -inf
+        (np.array([3.5]), np.array([1.0, 2.0]), 0.1),                # above xmax -> -inf
+        (np.array([2.0, 2.0]), np.array([1.0, 2.0, 3.0]), 0.1),      # zero gap -> -inf
+        (np.array([2.0]), np.array([-1.0, 2.0]), 0.1),               # negative height -> -inf
+        (np.array([2.0]), np.array([0.0, 2.0]), 0.1),                # zero height -> -inf
+        (np.array([2.0]), np.array([1.0, 2.0]), -0.1),               # sigma < 0 -> -inf
+        (np.array([2.0]), np.array([1.0, 2.0]), 0.0),                # sigma = 0 -> -inf
+        (np.array([]), np.array([2.0]), 0.2),                        # k = 0
+    ]
+    dth = [ChangepointParams(*s) for s in states]
+    oth = [port.ChangepointParams(*s) for s in states]
+    with np.errstate(all="ignore"):
+        want = np.array([om.log_posterior(t) for t in oth])
+    got = dm.log_posterior_batch(dth)
+    assert relerr(got, want) < TOL
+    assert np.all(np.isneginf(got[200:208]))
+    for i in (0, 5, 208):
+        assert abs(dm.log_likelihood(dth[i]) - om.log_likelihood(oth[i])) < 1e-9 * abs(want[i])
+        assert abs(dm.log_prior(dth[i]) - om.log_prior(oth[i])) < 1e-9 * max(1, abs(want[i]))
+
+
+def test_alpha_beta_not_one():
+    """gamma(alpha, beta) height prior with alpha != 1 exercises the log(v) branch."""
+    from oracle import riemann_port as port
+    from riemann_b200.models.changepoint import ChangepointParams, ChangepointRegression1D
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0, 1, 37))
+    y = rng.normal(2.0, 0.3, 37)
+    dm = ChangepointRegression1D(x, y, 0.0, 1.0, 3.0, 10, 2.5, 1.7)
+    om = port.ChangepointRegression1D(x, y, 0.0, 1.0, 3.0, 10, 2.5, 1.7)
+    st = [(np.sort(rng.uniform(0, 1, k)), rng.uniform(0.5, 3, k + 1), 0.3) for k in range(0, 9)]
+    got = dm.log_posterior_batch([ChangepointParams(*s) for s in st])
+    want = [om.log_posterior(port.ChangepointParams(*s)) for s in st]
+    assert relerr(got, want) < TOL
+
+
+def test_infinite_start_is_always_left(golden):
+    """Appendix A.2: Python's min(0, nan) == 0, so a -inf -> anything move is accepted."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models.changepoint import ChangepointParams
+    from riemann_b200 import _lib
+    g = golden("changepoint")
+    dm, dp, _, _ = _setup(g)
+    s = Sampler(dm, dp, ChangepointParams([2.0], [1.0, 3.0], -0.1))     # sigma < 0: logpost = -inf
+    assert s._chain_logpost[0] == -np.inf
+    tape = np.zeros((1, _lib.CP_NSLOT))
+    tape[0, _lib.CP_SLOT["sel1"]] = 0.1                                  # cpx move
+    tape[0, _lib.CP_SLOT["acc"]] = 0.999999
+    ex = s.run_injected(tape=tape)
+    assert ex["accepted"][0, 0] and s._chain_logpost[-1] == -np.inf
+
+
+def test_kcap_overflow_is_counted_not_silent(golden):
+    from riemann_b200 import Sampler, _lib
+    from riemann_b200.models.changepoint import ChangepointParams
+    g = golden("changepoint")
+    dm, dp, _, _ = _setup(g)
+    k = _lib.CP_LANES - 1
+    th0 = ChangepointParams(np.linspace(1.1, 2.9, k), np.full(k + 1, 2.0), 0.1)
+    s = Sampler(dm, dp, th0)
+    tape = np.zeros((3, _lib.CP_NSLOT))
+    tape[:, :4] = 0.9                       # -> trans-dimensional, birth
+    tape[:, _lib.CP_SLOT["s"]] = 2.03
+    tape[:, _lib.CP_SLOT["acc"]] = 1e-12
+    s.run_injected(tape=tape)
+    dg = s.diagnostics(allreduce=False)
+    assert dg["overflows"] == 3 and dg["accept_rate"] == 0.0
+    assert len(s._chain_thetas[-1].cpx) == k
+
+
+def test_philox_run_agrees_with_oracle_chains():
+    """Distributional gate vs the CPU sampler (same model/proposal, its own numpy stream)."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.models.changepoint import ChangepointParams
+    dm, dp, om, op = _setup()
+    th0 = ChangepointParams([2.0], [1.0, 3.0], 0.1)
+    K = 4096
+    s = Sampler(dm, dp, th0, K=K, seed=2024)
+    s.run(6000, trace=False)
+    s.reset_diagnostics()
+    s.run(4000, trace=False)
+    dg = s.diagnostics(allreduce=False)
+    kdev = np.asarray(s._chain_thetas.k[-1])
+    # oracle: 6 chains x (6000 burn + 6000 kept)
+    ks, sigs, accs = [], [], []
+    for c in range(6):
+        np.random.seed(900 + c)
+        o = port.Sampler(om, op, port.ChangepointParams([2.0], [1.0, 3.0], 0.1))
+        with np.errstate(all="ignore"):
+            o.run(12000, 6000)
+        ks += [len(t.cpx) for t in o._chain_thetas]
+        sigs += [t.sig for t in o._chain_thetas]
+        lp = np.array(o._chain_logpost)
+        accs.append(np.mean(lp[1:] != lp[:-1]))
+    ks, sigs = np.array(ks), np.array(sigs)
+    assert dg["overflows"] == 0
+    assert abs(dg["mean"][0] - sigs.mean()) < 0.05 * sigs.mean()          # sigma
+    assert abs(dg["mean"][1] - ks.mean()) < 0.35                          # mean number of changepoints
+    assert abs(dg["accept_rate"] - np.mean(accs)) < 0.04
+    hist_dev = np.bincount(kdev, minlength=16)[:16] / K
+    hist_ora = np.bincount(ks, minlength=16)[:16] / len(ks)
+    assert np.max(np.abs(hist_dev - hist_ora)) < 0.08
+
+
+def test_full_size_self_consistency():
+    """BASELINE config 2 size: 65,536 chains.  The log-posterior carried through T
+    accept/reject steps must equal a fresh pointwise evaluation of the final states."""
+    import torch
+    from riemann_b200 import Sampler, _lib
+    from riemann_b200.models.changepoint import ChangepointParams
+    dm, dp, _, _ = _setup()
+    K = 65536
+    s = Sampler(dm, dp, ChangepointParams([2.0], [1.0, 3.0], 0.1), K=K, seed=7)
+    s.run(300, trace=False)
+    tr, lp = s._chain_thetas, np.asarray(s._chain_logpost[-1])
+    assert np.all(np.isfinite(lp))
+    dk, dx, dv, ds = (torch.as_tensor(a[-1], device="cuda") for a in (tr.k, tr.cpx, tr.cpv, tr.sig))
+    out = torch.empty(K, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().rmn_model_cp_logpost(dm._handle, 0, K, _lib.ptr(dk), _lib.ptr(dx),
+                                                _lib.ptr(dv), _lib.ptr(ds), _lib.ptr(out), _lib.stream_ptr()))
+    assert relerr(out.cpu().numpy(), lp) < 1e-12
+    k = tr.k[-1]
+    assert k.min() >= 0 and k.max() < _lib.CP_LANES
+    # sortedness / positivity invariants of every accepted state
+    for c in np.random.default_rng(0).integers(0, K, 200):
+        cx = tr.cpx[-1, c, :k[c]]
+        assert np.all(np.diff(cx) > 0) and np.all(tr.cpv[-1, c, :k[c] + 1] > 0) and tr.sig[-1, c] > 0
