@@ -251,6 +251,20 @@ def main():
     _vector_fixture(R, "rw_gauss100d", g100, R.MetropolisRandomWalk(0.002 * np.eye(100)),
                     np.zeros(100), 300, 205, extra=dict(C0=0.002 * np.eye(100)))
 
+    # d = 12: exercises the dense (d > 8) device path with a dense proposal covariance,
+    # a non-zero mean and per-chain step-size adaptation
+    A12 = rng.standard_normal((12, 12))
+    C12 = A12 @ A12.T / 12 + 0.2 * np.eye(12)
+    mu12 = rng.standard_normal(12)
+    g12 = R.MultiGaussianDist(mu12, C12)
+    _vector_fixture(R, "rw_dense_gauss12d", g12, R.MetropolisRandomWalk(0.15 * C12), mu12 + 0.5, 600, 206,
+                    extra=dict(C0=0.15 * C12, mu=mu12, C=C12))
+    _vector_fixture(R, "adaptrw_gauss12d", g12, R.AdaptScaleRandomWalk(0.01 * np.eye(12)), mu12 + 0.5, 800, 207,
+                    extra=dict(C0=0.01 * np.eye(12), mu=mu12, C=C12), track_scale=True)
+    _vector_fixture(R, "adaptmala_gauss12d", g12, R.AdaptScaleHMC(0.2, 1, g12.grad_log_likelihood),
+                    mu12 - 0.3, 800, 208, extra=dict(eps=np.float64(0.2), nsteps=np.int64(1), mu=mu12, C=C12),
+                    track_scale=True)
+
     # --- HMC proper ("next" row N1): Nsteps>1, mass matrix, adaptive scale
     _vector_fixture(R, "hmc5_gauss2d", g2, R.VanillaHMC(0.1, 5, g2.grad_log_likelihood),
                     np.ones(2), 1000, 301, extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)))

@@ -224,7 +224,7 @@ class ChangepointParams(object):
                              "number of changepoints")
         self.cpx = np.array(cpx, dtype=np.float64)
         self.cpv = np.array(cpv, dtype=np.float64)
-        self.sig = float(np.squeeze(sig))
+        self.sig = np.float64(np.squeeze(sig))      # numpy scalar: 1/0 -> inf like the reference
 
     def copy(self):
         return ChangepointParams(self.cpx, self.cpv, self.sig)
@@ -512,7 +512,7 @@ class ChangepointRegression1DProp(Proposal):
             new.cpv = theta.cpv + 1.0 * (sv * dr.normal("xi", k + 1))
             return new, 0.0
         if dr.uniform("sel3") < 0.60:
-            new.sig = float(theta.sig + 1.0 * (ss * dr.normal("xi", 1)[0]))
+            new.sig = np.float64(theta.sig + 1.0 * (ss * dr.normal("xi", 1)[0]))
             return new, 0.0
         if k == 0 or dr.uniform("bd") > 0.5:                            # :59
             s = dr.uniform("s", self.model.xmin, self.model.xmax)

@@ -1,7 +1,540 @@
+// riemann_b200 -- dense Gaussian target at any d (config 3: d = 1000, MALA, 16,384 chains).
+//
+// Per MH iteration and chain the reference does (fp64 numpy)
+//   VanillaHMC.propose, Nsteps = 1 (= MALA)     riemann/proposals/hamiltonian.py:76-91, 13-52
+//   MetropolisRandomWalk.propose               riemann/proposals/randomwalk.py:21-26
+//   MultiGaussianDist.log_likelihood / grad    riemann/models/gaussian.py:49-58  (O(d^3) LU per call)
+//   Sampler.sample accept/swap, adapt          riemann/samplers/sampler.py:72-90, adaptive.py:26-35
+// Here one product  V' = Y' P  (Y' = proposed states minus mu, K x d;  P = C^-1, d x d,
+// symmetric, L2-resident) gives both the gradient (-V') and the quadratic form
+// (rowsum(Y' * V')) of every chain; gradient and log-posterior of the current state are
+// cached, so a step costs ONE batched GEMM instead of the reference's three solves.
+//
+//   kernel 1  finish_propose : per row -- finish the previous step (sum the GEMM's row
+//             partials, log-posterior, log q ratio, accept, adapt), then draw xi (Philox or
+//             injected) and write the next proposal.  One warp per chain row, coalesced.
+//   kernel 2  gemm_abt       : C = A B^T in fp64 on the tensor cores (DMMA m8n8k4),
+//             128x128x16 tiles, 3-stage cp.async pipeline, 8 warps.  The epilogue is fused:
+//             it stores V', and reduces y'.v' and |p'|^2 over the tile's columns into
+//             deterministic per-(row, column-block) partials (no atomics).
+//
+// Accepting a proposal never copies a row: every chain has two state slots and a one-bit
+// "current slot" flag; the proposal is written to the other slot and accept flips the bit.
+// Internal state is centred (y = theta - mu), row-major [K][dp], dp = d rounded up to 16
+// (padding columns are exactly zero in Y, xi and P, so they contribute nothing).
 #include "common.cuh"
-SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s) { rmn_set_error("dense sampler not built yet"); return nullptr; }
 
 namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, LDT = 20;   // LDT: smem row stride (doubles)
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM = (size_t)STAGES * (BM + BN) * LDT * 8;
+constexpr int ND_MAX = 8;          // tracked functionals: first 7 coordinates + mean(theta)
+
+enum { EPI_LOGPOST_RW = 0, EPI_LOGPOST_MALA = 1, EPI_RWPROP = 2 };
+
+struct DenseState {
+    int64_t K; int d, dp, nblk;    // nblk = column blocks of 32 (partials per row)
+    double* Y;       // [2][K][dp]   centred states, two slots per chain
+    double* V;       // [2][K][dp]   V = Y P  (gradient = -V)
+    double* Xi;      // [K][dp]      noise of the pending proposal (MALA) / Xi L^T scratch (dense RW)
+    double* partq;   // [nblk][K]    row partials of y'.v'
+    double* partk;   // [nblk][K]    row partials of |p'|^2
+    double* lp;      // [K]
+    double* k0;      // [K]          |xi|^2 of the pending proposal
+    double* epsrow;  // [K]          step size used by the pending proposal
+    int* cur;        // [K]          current slot
+    double* scale; long long* nsamp; long long* nacc;   // AdaptScale state
+    long long* dacc;               // accepts since diagnostics reset
+    double* S1; double* S2;        // [ND_MAX][K]
+    const double* mu;              // [dp] (padded copy)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C[m][n] = sum_k A[m][k] B[n][k].  A rows are the PROPOSAL slots of the chains
+// (EPI_LOGPOST_*) or the noise scratch (EPI_RWPROP); B is P (symmetric) or L.
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;
+    double* Bs = sm + (size_t)STAGES * BM * LDT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;              // 2 x 4 warps, warp tile 64 x 32
+    const int64_t m0 = (int64_t)blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const int dp = st.dp;
+    const int64_t K = st.K;
+    const int KT = dp / BK;
+
+    // each thread copies 4 A-chunks and 4 B-chunks (16 B each) per k-tile
+    const double* a_src[4];
+    const double* b_src[4];
+    bool a_ok[4], b_ok[4];
+    int soff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = tid + GEMM_THREADS * i;
+        const int row = q >> 3, c2 = (q & 7) * 2;
+        soff[i] = row * LDT + c2;
+        const int64_t m = m0 + row;
+        a_ok[i] = m < K;
+        const int64_t mm = a_ok[i] ? m : 0;
+        if (EPI == EPI_RWPROP) a_src[i] = st.Xi + mm * dp + c2;
+        else a_src[i] = st.Y + ((int64_t)(st.cur[mm] ^ 1) * K + mm) * dp + c2;
+        const int n = n0 + row;
+        b_ok[i] = n < dp;
+        b_src[i] = B + (int64_t)(b_ok[i] ? n : 0) * dp + c2;
+    }
+    auto load_tile = [&](int kt, int stage) {
+        double* as = As + (size_t)stage * BM * LDT;
+        double* bs = Bs + (size_t)stage * BN * LDT;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cp_async16(as + soff[i], a_src[i] + kt * BK, a_ok[i]);
+            cp_async16(bs + soff[i], b_src[i] + kt * BK, b_ok[i]);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_tile(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nk = kt + STAGES - 1;
+        if (nk < KT) load_tile(nk, nk % STAGES);
+        cp_async_commit();
+        const double* as = As + (size_t)(kt % STAGES) * BM * LDT + (wm * 64 + g) * LDT + t;
+        const double* bs = Bs + (size_t)(kt % STAGES) * BN * LDT + (wn * 32 + g) * LDT + t;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = as[i * 8 * LDT + kk * 4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = bs[j * 8 * LDT + kk * 4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- fused epilogue.  Thread owns rows m0 + wm*64 + i*8 + g, cols n0 + wn*32 + j*8 + 2t (+1)
+    const int blk = blockIdx.x * 4 + wn;            // 32-column block index of this warp
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + wm * 64 + i * 8 + g;
+        const bool rok = m < K;
+        const int64_t mm = rok ? m : 0;
+        const int c = st.cur[mm];
+        double pq = 0.0, pk = 0.0;
+        if (EPI == EPI_RWPROP) {
+            const double sc = st.epsrow[mm];
+            const double* yc = st.Y + ((int64_t)c * K + mm) * dp;
+            double* yp = st.Y + ((int64_t)(c ^ 1) * K + mm) * dp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) {
+                    const double2 y = *reinterpret_cast<const double2*>(yc + n);
+                    double2 o;
+                    o.x = (n < st.d) ? y.x + sc * acc[i][j][0] : 0.0;
+                    o.y = (n + 1 < st.d) ? y.y + sc * acc[i][j][1] : 0.0;
+                    *reinterpret_cast<double2*>(yp + n) = o;
+                }
+            }
+        } else {
+            const double* yp = st.Y + ((int64_t)(c ^ 1) * K + mm) * dp;
+            double* vp = st.V + ((int64_t)(c ^ 1) * K + mm) * dp;
+            const double* vc = st.V + ((int64_t)c * K + mm) * dp;
+            const double* xi = st.Xi + mm * dp;
+            const double he = 0.5 * st.epsrow[mm];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) {
+                    const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                    *reinterpret_cast<double2*>(vp + n) = make_double2(v0, v1);
+                    const double2 y = *reinterpret_cast<const double2*>(yp + n);
+                    pq += y.x * v0 + y.y * v1;
+                    if (EPI == EPI_LOGPOST_MALA) {
+                        // p' = xi + eps/2 g + eps/2 g',  g = -V_cur, g' = -V'   (hamiltonian.py:27,40)
+                        const double2 x = *reinterpret_cast<const double2*>(xi + n);
+                        const double2 w = *reinterpret_cast<const double2*>(vc + n);
+                        const double p0 = (x.x - he * w.x) - he * v0;
+                        const double p1 = (x.y - he * w.y) - he * v1;
+                        pk += p0 * p0 + p1 * p1;
+                    }
+                }
+            }
+            pq += __shfl_xor_sync(0xffffffffu, pq, 1);
+            pq += __shfl_xor_sync(0xffffffffu, pq, 2);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+            if (rok && t == 0 && blk < st.nblk) {
+                st.partq[(int64_t)blk * K + m] = pq;
+                if (EPI == EPI_LOGPOST_MALA) st.partk[(int64_t)blk * K + m] = pk;
+            }
+        }
+    }
+}
+
+struct DenseStep {
+    int prop_kind;          // RMN_PROP_RW / RMN_PROP_HMC
+    int adapt, rw_diag, finish, propose, diag;
+    double target, eps0, c1, c2;
+    const double* Ldiag;    // [dp] diagonal of chol(C0) when the RW covariance is diagonal
+    uint64_t seed; int64_t chain_offset;
+    int64_t step_fin;       // global index of the step being finished
+    int64_t step_prop;      // global index of the step being proposed
+    const double* inj_xi; const double* inj_u;      // already offset to the respective step
+    int64_t trace_slot;     // record slot for the state after the finished step, or -1
+    double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc;   // offset to step
+};
+
+// One warp per chain row.
+__global__ void __launch_bounds__(256)
+finish_propose_kernel(DenseState st, DenseStep sp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int dp = st.dp, d = st.d;
+    const int64_t K = st.K;
+    int c = st.cur[r];
+    double lp = st.lp[r];
+    const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
+
+    if (sp.finish) {
+        double q = 0.0, k1 = 0.0;
+        for (int b = lane; b < st.nblk; b += 32) {
+            q += st.partq[(int64_t)b * K + r];
+            if (sp.prop_kind == RMN_PROP_HMC) k1 += st.partk[(int64_t)b * K + r];
+        }
+        // fixed-order reduction => bitwise reproducible log-posteriors
+        q = group_sum<32>(q);
+        k1 = group_sum<32>(k1);
+        const double ll = -0.5 * ((q + sp.c1) + sp.c2);            // gaussian.py:52
+        const double lpn = combine_logpost(0.0, ll);
+        const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r]) : 0.0;   // hamiltonian.py:89
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        const bool acc = mh_accept(lpn, lp, lqr, u);
+        if (acc) { c ^= 1; lp = lpn; }
+        if (lane == 0) {
+            if (acc) { st.cur[r] = c; st.lp[r] = lp; }
+            st.dacc[r] += acc ? 1 : 0;
+            if (sp.adapt) {
+                AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
+                ad.update(acc, sp.target);       // a.s. identical to any(theta != last_theta)
+                st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts;
+            }
+            if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
+            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
+            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+        }
+    }
+    __syncwarp();
+
+    const double* y = st.Y + ((int64_t)c * K + r) * dp;
+    const double* v = st.V + ((int64_t)c * K + r) * dp;
+    double* yp = st.Y + ((int64_t)(c ^ 1) * K + r) * dp;
+    double* xo = st.Xi + r * dp;
+    const double scale = sp.adapt ? st.scale[r] : 1.0;
+    const double eps = (sp.prop_kind == RMN_PROP_HMC) ? scale * sp.eps0 : scale;
+    double k0 = 0.0, rowsum = 0.0;
+    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+
+    for (int j4 = lane * 4; j4 < dp; j4 += 128) {
+        const double2 ya = *reinterpret_cast<const double2*>(y + j4);
+        const double2 yb = *reinterpret_cast<const double2*>(y + j4 + 2);
+        const double yv[4] = {ya.x, ya.y, yb.x, yb.y};
+        rowsum += (yv[0] + yv[1]) + (yv[2] + yv[3]);
+        if (want_trace) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j4 + q < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + q] = yv[q] + st.mu[j4 + q];
+        }
+        if (!sp.propose) continue;
+        double xi[4];
+        if (sp.inj_xi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xi[q] = (j4 + q < d) ? sp.inj_xi[r * d + j4 + q] : 0.0;
+        } else {
+            normal4(rk.block((uint64_t)sp.step_prop, (uint32_t)(j4 >> 2)), xi);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j4 + q >= d) xi[q] = 0.0;
+        }
+        double out[4];
+        if (sp.prop_kind == RMN_PROP_HMC) {
+            const double2 va = *reinterpret_cast<const double2*>(v + j4);
+            const double2 vb = *reinterpret_cast<const double2*>(v + j4 + 2);
+            const double vv[4] = {va.x, va.y, vb.x, vb.y};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double ph = xi[q] + 0.5 * eps * (-vv[q]);        // hamiltonian.py:27
+                out[q] = yv[q] + eps * ph;                             // :30
+                k0 += xi[q] * xi[q];
+            }
+            *reinterpret_cast<double2*>(xo + j4) = make_double2(xi[0], xi[1]);
+            *reinterpret_cast<double2*>(xo + j4 + 2) = make_double2(xi[2], xi[3]);
+        } else if (sp.rw_diag) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = yv[q] + scale * (sp.Ldiag[j4 + q] * xi[q]);   // randomwalk.py:26
+        } else {
+            // dense L: write xi; a GEMM (EPI_RWPROP) forms y + scale * xi L^T
+            *reinterpret_cast<double2*>(xo + j4) = make_double2(xi[0], xi[1]);
+            *reinterpret_cast<double2*>(xo + j4 + 2) = make_double2(xi[2], xi[3]);
+            continue;
+        }
+        *reinterpret_cast<double2*>(yp + j4) = make_double2(out[0], out[1]);
+        *reinterpret_cast<double2*>(yp + j4 + 2) = make_double2(out[2], out[3]);
+    }
+    if (sp.propose) {
+        k0 = group_sum<32>(k0);
+        if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
+    }
+    if (sp.diag) {
+        rowsum = group_sum<32>(rowsum);
+        const int nd = min(d, ND_MAX - 1) + 1;
+        if (lane < nd) {
+            const double f = (lane == nd - 1) ? rowsum / (double)d + 0.0 : y[lane];
+            st.S1[(int64_t)lane * K + r] += f;
+            st.S2[(int64_t)lane * K + r] += f * f;
+        }
+    }
+}
+
+// state i/o: theta[K][d] <-> centred slot-0/current rows; V recomputed by a GEMM on set
+__global__ void dense_set_kernel(DenseState st, const double* __restrict__ theta) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.dp) return;
+    const int64_t r = i / st.dp;
+    const int j = (int)(i % st.dp);
+    // the GEMM reads the PROPOSAL slot: stage the new state there, cur = 0 => slot 1
+    st.Y[((int64_t)1 * st.K + r) * st.dp + j] = (j < st.d) ? theta[r * st.d + j] - st.mu[j] : 0.0;
+    st.Xi[i] = 0.0;
+    if (j == 0) { st.cur[r] = 0; st.k0[r] = 0.0; st.epsrow[r] = 0.0; }
+}
+__global__ void dense_adopt_kernel(DenseState st, double c1, double c2) {
+    // after the GEMM on the staged rows: make slot 1 current and set lp from the partials
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    double q = 0.0;
+    for (int b = lane; b < st.nblk; b += 32) q += st.partq[(int64_t)b * st.K + r];
+    q = group_sum<32>(q);
+    if (lane == 0) {
+        st.cur[r] = 1;
+        st.lp[r] = combine_logpost(0.0, -0.5 * ((q + c1) + c2));
+    }
+}
+__global__ void dense_get_kernel(DenseState st, double* theta, double* lp) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.d) return;
+    const int64_t r = i / st.d;
+    const int j = (int)(i % st.d);
+    if (theta) theta[i] = st.Y[((int64_t)st.cur[r] * st.K + r) * st.dp + j] + st.mu[j];
+    if (lp && j == 0) lp[r] = st.lp[r];
+}
+__global__ void dense_get_adapt_kernel(DenseState st, double* scale, int64_t* ns, int64_t* na) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= st.K) return;
+    if (scale) scale[c] = st.scale[c];
+    if (ns) ns[c] = st.nsamp[c];
+    if (na) na[c] = st.nacc[c];
+}
+
+struct DenseGaussSampler : SamplerImpl {
+    rmn_sampler* s;
+    DenseState st{};
+    double* d_Ppad = nullptr;     // [dp][dp] zero-padded precision
+    double* d_Lpad = nullptr;     // [dp][dp] zero-padded chol(C0) (dense RW) or nullptr
+    double* d_Ldiag = nullptr;    // [dp]
+    double* d_mupad = nullptr;
+    bool rw_diag = true;
+    bool pending = false;         // a proposal is in flight (written, GEMM done, not finished)
+    explicit DenseGaussSampler(rmn_sampler* s_) : s(s_) {
+        st.K = s->K; st.d = s->model->d; st.dp = (st.d + 15) / 16 * 16; st.nblk = (st.dp + 31) / 32;
+    }
+    ~DenseGaussSampler() override {
+        cudaFree(d_Ppad); cudaFree(d_Lpad); cudaFree(d_Ldiag); cudaFree(d_mupad);
+    }
+    size_t row_bytes() const { return align256((size_t)st.K * st.dp * 8); }
+    size_t workspace_bytes() const override {
+        const size_t K = (size_t)st.K;
+        return 5 * row_bytes() + 2 * align256((size_t)st.nblk * K * 8) + 7 * align256(K * 8) +
+               align256(K * 4) + 2 * align256(ND_MAX * K * 8) + 256;
+    }
+    int bind(void* ws) override {
+        const size_t K = (size_t)st.K;
+        char* p = (char*)ws;
+        st.Y = (double*)p; p += 2 * row_bytes();
+        st.V = (double*)p; p += 2 * row_bytes();
+        st.Xi = (double*)p; p += row_bytes();
+        st.partq = (double*)p; p += align256((size_t)st.nblk * K * 8);
+        st.partk = (double*)p; p += align256((size_t)st.nblk * K * 8);
+        st.lp = (double*)p; p += align256(K * 8);
+        st.k0 = (double*)p; p += align256(K * 8);
+        st.epsrow = (double*)p; p += align256(K * 8);
+        st.scale = (double*)p; p += align256(K * 8);
+        st.nsamp = (long long*)p; p += align256(K * 8);
+        st.nacc = (long long*)p; p += align256(K * 8);
+        st.dacc = (long long*)p; p += align256(K * 8);
+        st.cur = (int*)p; p += align256(K * 4);
+        st.S1 = (double*)p; p += align256(ND_MAX * K * 8);
+        st.S2 = (double*)p; p += align256(ND_MAX * K * 8);
+        // Y and V slots are contiguous pairs: slot b of array X is X + b*K*dp (row_bytes may pad)
+        // -> keep the two slots exactly K*dp apart by laying them out inside one 2*row_bytes block
+        RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        const int d = st.d, dp = st.dp;
+        std::vector<double> hp((size_t)dp * dp, 0.0), hm(dp, 0.0);
+        std::vector<double> tmp((size_t)d * d);
+        RMN_CUDA(cudaMemcpy(tmp.data(), s->model->d_prec, (size_t)d * d * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) hp[(size_t)i * dp + j] = tmp[(size_t)i * d + j];
+        for (int i = 0; i < d; ++i) hm[i] = s->model->h_mu[i];
+        RMN_CUDA(cudaMalloc(&d_Ppad, hp.size() * 8));
+        RMN_CUDA(cudaMemcpy(d_Ppad, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice));
+        RMN_CUDA(cudaMalloc(&d_mupad, (size_t)dp * 8));
+        RMN_CUDA(cudaMemcpy(d_mupad, hm.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
+        st.mu = d_mupad;
+        const rmn_proposal* pr = s->prop;
+        if (pr->kind == RMN_PROP_RW) {
+            rw_diag = true;
+            for (int i = 0; i < d && rw_diag; ++i)
+                for (int j = 0; j < i; ++j)
+                    if (pr->h_L[(size_t)i * d + j] != 0.0) { rw_diag = false; break; }
+            std::vector<double> ld(dp, 0.0);
+            for (int i = 0; i < d; ++i) ld[i] = pr->h_L[(size_t)i * d + i];
+            RMN_CUDA(cudaMalloc(&d_Ldiag, (size_t)dp * 8));
+            RMN_CUDA(cudaMemcpy(d_Ldiag, ld.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
+            if (!rw_diag) {
+                std::vector<double> hl((size_t)dp * dp, 0.0);
+                for (int i = 0; i < d; ++i)
+                    for (int j = 0; j <= i; ++j) hl[(size_t)i * dp + j] = pr->h_L[(size_t)i * d + j];
+                RMN_CUDA(cudaMalloc(&d_Lpad, hl.size() * 8));
+                RMN_CUDA(cudaMemcpy(d_Lpad, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice));
+            }
+        }
+        RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_RW>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_MALA>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_RWPROP>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        int rc = rmn_fill_f64(st.scale, st.K, 1.0, 0);
+        if (rc) return rc;
+        RMN_CUDA(cudaDeviceSynchronize());
+        return RMN_OK;
+    }
+    dim3 gemm_grid() const { return dim3((st.dp + BN - 1) / BN, (unsigned)((st.K + BM - 1) / BM)); }
+    unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
+    double c1() const { return st.d * log(2.0 * M_PI); }
+
+    template <int EPI>
+    int gemm(const double* B, cudaStream_t stream) {
+        gemm_abt_kernel<EPI><<<gemm_grid(), GEMM_THREADS, GEMM_SMEM, stream>>>(st, B);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+
+    int set_state(const double* d_theta, cudaStream_t stream) override {
+        const int64_t n = st.K * st.dp;
+        dense_set_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta);
+        RMN_KERNEL_CHECK(); launches++;
+        if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc;
+        dense_adopt_kernel<<<row_grid(), 256, 0, stream>>>(st, c1(), s->model->logdetC);
+        RMN_KERNEL_CHECK(); launches++;
+        pending = false;
+        return RMN_OK;
+    }
+    int get_state(double* d_theta, double* d_lp, cudaStream_t stream) override {
+        const int64_t n = st.K * st.d;
+        dense_get_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta, d_lp);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
+        const rmn_proposal* pr = s->prop;
+        if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        rmn_trace_t t0{};
+        if (tr) t0 = *tr;
+        if (t0.thin <= 0) t0.thin = 1;
+        DenseStep sp{};
+        sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.rw_diag = rw_diag ? 1 : 0;
+        sp.target = pr->target; sp.eps0 = pr->eps; sp.c1 = c1(); sp.c2 = s->model->logdetC;
+        sp.Ldiag = d_Ldiag; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
+        const int64_t K = st.K;
+        const int d = st.d;
+        // iteration t: [finish step t-1 | propose step t] ; GEMM(s).  A last call finishes step T-1.
+        for (int64_t t = 0; t <= T; ++t) {
+            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
+            sp.step_fin = step0 + t - 1; sp.step_prop = step0 + t;
+            sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;
+            sp.inj_xi = (inj && t < T) ? inj->d_xi + t * K * d : nullptr;
+            sp.trace_slot = -1;
+            sp.tr_theta = t0.d_theta; sp.tr_logpost = t0.d_logpost;
+            sp.tr_prop_lp = (t0.d_prop_logpost && t > 0) ? t0.d_prop_logpost + (t - 1) * K : nullptr;
+            sp.tr_acc = (t0.d_accepted && t > 0) ? t0.d_accepted + (t - 1) * K : nullptr;
+            if (t > 0 && (t0.d_theta || t0.d_logpost)) {
+                const int64_t i = t;                      // history index of the state after step t-1
+                if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
+            }
+            finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
+            RMN_KERNEL_CHECK(); launches++;
+            if (t == T) break;
+            if (pr->kind == RMN_PROP_RW && !rw_diag)
+                if (int rc = gemm<EPI_RWPROP>(d_Lpad, stream)) return rc;
+            if (pr->kind == RMN_PROP_HMC) { if (int rc = gemm<EPI_LOGPOST_MALA>(d_Ppad, stream)) return rc; }
+            else { if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc; }
+        }
+        step0 += T; diag_steps += T;
+        return RMN_OK;
+    }
+    int get_adapt(double* sc, int64_t* ns, int64_t* na, cudaStream_t stream) override {
+        dense_get_adapt_kernel<<<(unsigned)((st.K + 127) / 128), 128, 0, stream>>>(st, sc, ns, na);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int diag_dim() const override { return (st.d < ND_MAX - 1 ? st.d : ND_MAX - 1) + 1; }
+    int reset_diag(cudaStream_t stream) override {
+        RMN_CUDA(cudaMemsetAsync(st.S1, 0, (size_t)ND_MAX * st.K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.S2, 0, (size_t)ND_MAX * st.K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)st.K * 8, stream));
+        diag_steps = 0;
+        return RMN_OK;
+    }
+    int reduce_diag(double* d_block, cudaStream_t stream) override {
+        launches++;
+        return rmn_reduce_diag_block(st.K, diag_dim(), diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
+    }
+};
+
 // one warp per point: v = P y, quad = y.v, grad = -v      (gaussian.py:49-58 via P = C^-1)
 __global__ void __launch_bounds__(128)
 gauss_point_kernel(int d, const double* __restrict__ mu, const double* __restrict__ prec, double c1,
@@ -24,7 +557,19 @@ gauss_point_kernel(int d, const double* __restrict__ mu, const double* __restric
         out[pt] = (which == 2) ? 0.0 : ((which == 1) ? ll : combine_logpost(0.0, ll));
     }
 }
+
 }  // namespace
+
+SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s) {
+    const rmn_proposal* p = s->prop;
+    if (p->kind == RMN_PROP_PCN || (p->kind == RMN_PROP_HMC && (p->nsteps != 1 || p->has_mass))) {
+        rmn_set_error("dense Gaussian path (d > %d) supports RW and MALA (VanillaHMC with Nsteps=1, no "
+                      "mass matrix); pCN / multi-step HMC / mass matrices run on the small-d path only",
+                      RMN_SMALL_D_MAX);
+        return nullptr;
+    }
+    return new DenseGaussSampler(s);
+}
 
 int gauss_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta, double* d_out,
                     double* d_grad, cudaStream_t st) {

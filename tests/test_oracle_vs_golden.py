@@ -46,7 +46,7 @@ def _replay(g, model, proposal, theta0):
 
 
 @pytest.mark.parametrize("name,d", [("rw_gauss1d", 1), ("rw_gauss2d", 2), ("rw_gauss5d", 5),
-                                    ("rw_gauss100d", 100)])
+                                    ("rw_gauss100d", 100), ("rw_dense_gauss12d", 12)])
 def test_rw(golden, name, d):
     g = golden(name)
     _replay(g, _gauss(g, d), port.MetropolisRandomWalk(g["C0"]), g["thetas"][0])
@@ -91,6 +91,16 @@ def test_adapt_scale_hmc(golden):
     g = golden("adapthmc5_gauss2d")
     m = _gauss(g, 2)
     prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood)
+    _replay(g, m, prop, g["thetas"][0])
+    assert abs(prop.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
+
+
+@pytest.mark.parametrize("name", ["adaptrw_gauss12d", "adaptmala_gauss12d"])
+def test_adaptive_d12(golden, name):
+    g = golden(name)
+    m = _gauss(g, 12)
+    prop = (port.AdaptScaleRandomWalk(g["C0"]) if name.startswith("adaptrw")
+            else port.AdaptScaleHMC(float(g["eps"]), 1, m.grad_log_likelihood))
     _replay(g, m, prop, g["thetas"][0])
     assert abs(prop.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
 
