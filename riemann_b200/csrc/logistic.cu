@@ -1,4 +1,856 @@
+// riemann_b200 -- Bayesian logistic regression: MALA (config 4) and simplified manifold
+// MALA with the Fisher metric (config 5).  Neither model nor metric proposal exists in the
+// reference; they follow its protocols -- Model.log_posterior (riemann/models/model.py:43-55),
+// Proposal.propose -> (theta', log q(theta'|theta)/q(theta|theta')) (riemann/proposals/
+// proposal.py:10-17), MALA == VanillaHMC(eps, 1, grad) (riemann/proposals/hamiltonian.py:76-91),
+// Sampler.sample (riemann/samplers/sampler.py:72-90) -- and are checked against the fp64 numpy
+// restatement in oracle/riemann_port.py.
+//
+//   log L(theta) = sum_i y_i z_i - softplus(z_i),  z = X theta       prior N(0, pv I)
+//   grad         = X^T (y - sigmoid(z)) - theta / pv
+//   metric G     = X^T diag(p (1-p)) X + I / pv
+//
+// lg_eval_kernel  ("flash-attention shaped"): a CTA owns 64 chains and a range of data rows.
+//   Per 64-row tile of X (cp.async double-buffered in shared memory, read ONCE for all 64
+//   chains):  Z^T = Theta X^T  on the fp64 tensor cores (DMMA m8n8k4)  ->  pointwise
+//   sigmoid / softplus in registers  ->  G += R^T X  on the tensor cores again.  The C
+//   fragment of the first product is fed straight into the A fragment of the second (the
+//   contraction index is permuted instead of transposing through shared memory).  Z never
+//   touches memory; the log-likelihood is accumulated in fp64.
+// lg_metric_kernel: per chain  G = X^T diag(w) X  as a 64x64xN DMMA product, two warps per
+//   chain, w recomputed in-kernel from z.
+// mm_geometry (inside the finish/propose kernel): per-chain Cholesky, log-determinant and
+//   triangular solves in shared memory, one warp per chain.
 #include "common.cuh"
-SamplerImpl* make_logistic_sampler(rmn_sampler* s) { rmn_set_error("logistic sampler not built yet"); return nullptr; }
+
+namespace {
+
+constexpr int BC = 64;        // chains per CTA (eval)
+constexpr int BI = 64;        // data rows per tile
+constexpr int EVAL_THREADS = 256;
+constexpr int ND_MAX = 8;
+constexpr int MM_DMAX = 64;   // mMALA: d <= 64 (shared-memory Cholesky, 64x64 accumulators)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// row permutation inside an 8-row group that makes BOTH products' shared-memory fragment
+// loads bank-conflict free with a row stride = 4 (mod 16) doubles
+__device__ __forceinline__ int perm8(int g) { return (g < 4) ? g : (g ^ 1); }   // 0 1 2 3 5 4 7 6
+
+struct LogisticState {
+    int64_t K, N; int d, dp, ldt, nsplit; int64_t rows_per_split;
+    double pv;
+    const double* X; const double* y;
+    double* Th;      // [2][K][dp]  two state slots per chain
+    double* Gr;      // [2][K][dp]  grad log posterior
+    double* Xi;      // [K][dp]
+    double* llpart;  // [nsplit][K]
+    double* gpart;   // [nsplit][K][dp]
+    double* lp; double* k0; double* epsrow; int* cur;
+    double* scale; long long* nsamp; long long* nacc; long long* dacc;
+    double* S1; double* S2;
+    // mMALA
+    double* Gm;      // [K][d][d]   metric of the pending proposal (likelihood part)
+    double* Lc;      // [2][K][d][d] Cholesky factors (current / proposal slot follows cur)
+    double* logdet;  // [2][K]
+    double* nat;     // [2][K][dp]   G^-1 grad
+};
+
+// ---------------------------------------------------------------------------------------
+// eval: llpart[split][c], gpart[split][c][:] for the chains' PROPOSAL slots (slot = cur^1),
+// or for slot `fixed_slot` when >= 0 (set_state / pointwise).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EVAL_THREADS, 1)
+lg_eval_kernel(LogisticState st, int fixed_slot) {
+    extern __shared__ __align__(16) double sm[];
+    const int ldt = st.ldt, dp = st.dp, d = st.d;
+    double* Ts = sm;                              // [BC][ldt]
+    double* Xs = Ts + BC * ldt;                   // [2][BI][ldt]
+    double* ys = Xs + 2 * BI * ldt;               // [2][BI]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t K = st.K;
+    const int64_t c0 = (int64_t)blockIdx.x * BC;
+    const int split = blockIdx.y;
+    const int64_t r_begin = (int64_t)split * st.rows_per_split;
+    const int64_t r_end = min(st.N, r_begin + st.rows_per_split);
+    const int ntiles = (r_end > r_begin) ? (int)((r_end - r_begin + BI - 1) / BI) : 0;
+
+    // stage Theta (zero padded) and clear the pad columns of the X buffers
+    for (int q = tid; q < BC * ldt; q += EVAL_THREADS) {
+        const int c = q / ldt, k = q % ldt;
+        const int64_t cc = c0 + c;
+        double v = 0.0;
+        if (cc < K && k < d) {
+            const int slot = (fixed_slot >= 0) ? fixed_slot : (st.cur[cc] ^ 1);
+            v = st.Th[((int64_t)slot * K + cc) * dp + k];
+        }
+        Ts[q] = v;
+    }
+    for (int q = tid; q < 2 * BI * ldt; q += EVAL_THREADS)
+        if (q % ldt >= d) Xs[q] = 0.0;
+
+    const bool even = (d & 1) == 0;
+    const int cpr = even ? d / 2 : d;             // chunks per row
+    auto load_tile = [&](int tile, int buf) {
+        const int64_t r0 = r_begin + (int64_t)tile * BI;
+        double* xs = Xs + buf * BI * ldt;
+        for (int q = tid; q < BI * cpr; q += EVAL_THREADS) {
+            const int row = q / cpr, ch = q % cpr;
+            const int64_t r = r0 + row;
+            const bool ok = r < r_end;
+            const double* src = st.X + (ok ? r : 0) * d + (even ? 2 * ch : ch);
+            if (even) cp_async16(xs + row * ldt + 2 * ch, src, ok);
+            else cp_async8(xs + row * ldt + ch, src, ok);
+        }
+        if (tid < BI) {
+            const int64_t r = r0 + tid;
+            cp_async8(ys + buf * BI + tid, st.y + (r < r_end ? r : 0), r < r_end);
+        }
+    };
+
+    double accg[16][2];                           // G[c = 8*warp + g][k = 8*jn + 2t (+1)], jn < dp/8 <= 16
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { accg[j][0] = 0.0; accg[j][1] = 0.0; }
+    double ll = 0.0;
+    const int nkn = dp / 8;
+
+    if (ntiles > 0) load_tile(0, 0);
+    cp_async_commit();
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) load_tile(tile + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* xs = Xs + buf * BI * ldt;
+        const double* yb = ys + buf * BI;
+        const int64_t r0 = r_begin + (int64_t)tile * BI;
+
+        // ---- product 1: Z^T[c][i] = sum_k Theta[c][k] X[i][k]
+        double z[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { z[j][0] = 0.0; z[j][1] = 0.0; }
+        const double* ta = Ts + (warp * 8 + g) * ldt + t;
+        const double* xb = xs + perm8(g) * ldt + t;
+        for (int k4 = 0; k4 < dp; k4 += 4) {
+            const double a = ta[k4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma884(z[j][0], z[j][1], a, xb[j * 8 * ldt + k4]);
+        }
+        // ---- pointwise: p = sigmoid(z), r = y - p, ll += y z - softplus(z)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = j * 8 + perm8(2 * t + e);
+                const bool ok = (r0 + i) < r_end;
+                const double yv = yb[i];
+                const double zz = z[j][e];
+                const double ex = exp(-fabs(zz));
+                const double inv = 1.0 / (1.0 + ex);
+                const double p = (zz >= 0.0) ? inv : ex * inv;
+                const double sp = fmax(zz, 0.0) + log1p(ex);
+                ll += ok ? (yv * zz - sp) : 0.0;
+                z[j][e] = ok ? (yv - p) : 0.0;
+            }
+        }
+        // ---- product 2: G[c][k] += sum_i R[c][i] X[i][k]   (contraction rows permuted, see perm8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double* xr = xs + (j * 8 + perm8(2 * t + e)) * ldt + g;
+                const double a = z[j][e];
+#pragma unroll
+                for (int jn = 0; jn < 16; ++jn)
+                    if (jn < nkn) dmma884(accg[jn][0], accg[jn][1], a, xr[jn * 8]);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+    ll += __shfl_xor_sync(0xffffffffu, ll, 1);
+    ll += __shfl_xor_sync(0xffffffffu, ll, 2);
+    const int64_t c = c0 + warp * 8 + g;
+    if (c < K) {
+        if (t == 0) st.llpart[(int64_t)split * K + c] = ll;
+        double* gp = st.gpart + ((int64_t)split * K + c) * dp;
+#pragma unroll
+        for (int jn = 0; jn < 16; ++jn)
+            if (jn < nkn) *reinterpret_cast<double2*>(gp + jn * 8 + 2 * t) = make_double2(accg[jn][0], accg[jn][1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// metric: Gm[c] += sum_i w_ic x_i x_i^T (likelihood part) for the PROPOSAL slot (or fixed).
+// CTA = 8 warps = 4 chains x 2 warps; warp h of a chain owns rows a in [32h, 32h+32).
+// Accumulated over splits with a deterministic two-pass (gm_part -> summed by the caller)
+// when nsplit > 1; here each CTA loops over ALL rows (nsplit = 1 for the metric).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+lg_metric_kernel(LogisticState st, int fixed_slot) {
+    extern __shared__ __align__(16) double sm[];
+    const int ldt = st.ldt, dp = st.dp, d = st.d;
+    double* Ts = sm;                              // [4][ldt]
+    double* Xs = Ts + 4 * ldt;                    // [2][BI][ldt]
+    double* ws = Xs + 2 * BI * ldt;               // [4][BI]  weights of the current tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ch = warp >> 1, half = warp & 1;
+    const int64_t K = st.K;
+    const int64_t c = (int64_t)blockIdx.x * 4 + ch;
+    const int ntiles = (int)((st.N + BI - 1) / BI);
+
+    for (int q = tid; q < 4 * ldt; q += 256) {
+        const int cc = q / ldt, k = q % ldt;
+        const int64_t cg = (int64_t)blockIdx.x * 4 + cc;
+        double v = 0.0;
+        if (cg < K && k < d) {
+            const int slot = (fixed_slot >= 0) ? fixed_slot : (st.cur[cg] ^ 1);
+            v = st.Th[((int64_t)slot * K + cg) * dp + k];
+        }
+        Ts[q] = v;
+    }
+    for (int q = tid; q < 2 * BI * ldt; q += 256)
+        if (q % ldt >= d) Xs[q] = 0.0;
+    const bool even = (d & 1) == 0;
+    const int cpr = even ? d / 2 : d;
+    auto load_tile = [&](int tile, int buf) {
+        const int64_t r0 = (int64_t)tile * BI;
+        double* xs = Xs + buf * BI * ldt;
+        for (int q = tid; q < BI * cpr; q += 256) {
+            const int row = q / cpr, chk = q % cpr;
+            const int64_t r = r0 + row;
+            const bool ok = r < st.N;
+            const double* src = st.X + (ok ? r : 0) * d + (even ? 2 * chk : chk);
+            if (even) cp_async16(xs + row * ldt + 2 * chk, src, ok);
+            else cp_async8(xs + row * ldt + chk, src, ok);
+        }
+    };
+
+    double acc[4][8][2];                          // rows a = 32*half + 8*ia + g, cols b = 8*jb + 2t (+1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    load_tile(0, 0);
+    cp_async_commit();
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) load_tile(tile + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* xs = Xs + buf * BI * ldt;
+        // weights: thread q handles (chain q/64, row q%64): z = x_i . theta, w = p (1 - p)
+        {
+            const int cc = tid >> 6, i = tid & 63;
+            const double* xr = xs + i * ldt;
+            const double* th = Ts + cc * ldt;
+            double zz = 0.0;
+            for (int k = 0; k < d; ++k) zz += xr[k] * th[k];
+            const double ex = exp(-fabs(zz));
+            const double inv = 1.0 / (1.0 + ex);
+            const bool ok = ((int64_t)tile * BI + i) < st.N;
+            ws[cc * BI + i] = ok ? (ex * inv) * inv : 0.0;       // p(1-p) = e/(1+e)^2
+        }
+        __syncthreads();
+        const double* wc = ws + ch * BI;
+#pragma unroll 2
+        for (int i4 = 0; i4 < BI; i4 += 4) {
+            // A[a][i] = x_ia w_i  (thread: a = base + g, i = i4 + t);  B[i][b] = x_ib (i = i4 + t, b = .. + g)
+            const double* xr = xs + (i4 + t) * ldt;
+            const double w = wc[i4 + t];
+            double a[4], b[8];
+#pragma unroll
+            for (int ia = 0; ia < 4; ++ia) a[ia] = xr[half * 32 + ia * 8 + g] * w;
+#pragma unroll
+            for (int jb = 0; jb < 8; ++jb) b[jb] = xr[jb * 8 + g];
+#pragma unroll
+            for (int ia = 0; ia < 4; ++ia)
+#pragma unroll
+                for (int jb = 0; jb < 8; ++jb) dmma884(acc[ia][jb][0], acc[ia][jb][1], a[ia], b[jb]);
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    if (c < K) {
+        double* G = st.Gm + c * (int64_t)d * d;
+#pragma unroll
+        for (int ia = 0; ia < 4; ++ia) {
+            const int a = half * 32 + ia * 8 + g;
+#pragma unroll
+            for (int jb = 0; jb < 8; ++jb) {
+                const int b = jb * 8 + 2 * t;
+                if (a < d && b < d) G[a * d + b] = acc[ia][jb][0];
+                if (a < d && b + 1 < d) G[a * d + b + 1] = acc[ia][jb][1];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finish / propose, one warp per chain.
+// ---------------------------------------------------------------------------------------
+struct LgStep {
+    int mmala, adapt, finish, propose, diag;
+    double target, eps0;
+    uint64_t seed; int64_t chain_offset, step_fin, step_prop;
+    const double* inj_xi; const double* inj_u;
+    int64_t trace_slot;
+    double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc;
+};
+
+// In-place Cholesky of the d x d matrix A (row-major, leading dim d) held in shared memory,
+// executed by one warp.  Returns log det = 2 sum log L_jj; NaN if not positive definite.
+__device__ double warp_cholesky(double* A, int d, int lane) {
+    double logdet = 0.0;
+    for (int j = 0; j < d; ++j) {
+        double s = 0.0;
+        for (int k = lane; k < j; k += 32) s += A[j * d + k] * A[j * d + k];
+        s = group_sum<32>(s);
+        const double djj = A[j * d + j] - s;
+        const double ljj = sqrt(djj);
+        logdet += 2.0 * log(ljj);
+        __syncwarp();
+        if (lane == 0) A[j * d + j] = ljj;
+        for (int i = j + 1 + lane; i < d; i += 32) {
+            double v = A[i * d + j];
+            for (int k = 0; k < j; ++k) v -= A[i * d + k] * A[j * d + k];
+            A[i * d + j] = v / ljj;
+        }
+        __syncwarp();
+    }
+    return logdet;
+}
+// x <- L^-1 x (forward) ; x in shared memory
+__device__ void warp_trsv_lower(const double* L, double* x, int d, int lane) {
+    for (int j = 0; j < d; ++j) {
+        __syncwarp();
+        const double xj = x[j] / L[j * d + j];
+        __syncwarp();
+        if (lane == 0) x[j] = xj;
+        for (int i = j + 1 + lane; i < d; i += 32) x[i] -= L[i * d + j] * xj;
+    }
+    __syncwarp();
+}
+// x <- L^-T x (backward)
+__device__ void warp_trsv_lower_t(const double* L, double* x, int d, int lane) {
+    for (int j = d - 1; j >= 0; --j) {
+        __syncwarp();
+        const double xj = x[j] / L[j * d + j];
+        __syncwarp();
+        if (lane == 0) x[j] = xj;
+        for (int i = lane; i < j; i += 32) x[i] -= L[j * d + i] * xj;
+    }
+    __syncwarp();
+}
+
+template <bool MMALA>
+__global__ void __launch_bounds__(128)
+lg_finish_propose_kernel(LogisticState st, LgStep sp) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int dp = st.dp, d = st.d;
+    const int64_t K = st.K;
+    double* Lw = sm + (size_t)wib * (MMALA ? (d * d + 2 * dp) : 0);    // [d][d] + two vectors
+    double* v1 = Lw + d * d;
+    double* v2 = v1 + dp;
+    int c = st.cur[r];
+    double lp = st.lp[r];
+    const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
+    const double pvinv = 1.0 / st.pv;
+
+    if (sp.finish) {
+        const int pslot = c ^ 1;
+        const double* thp = st.Th + ((int64_t)pslot * K + r) * dp;
+        const double* thc = st.Th + ((int64_t)c * K + r) * dp;
+        double* grp = st.Gr + ((int64_t)pslot * K + r) * dp;
+        const double* grc = st.Gr + ((int64_t)c * K + r) * dp;
+        const double* xi = st.Xi + r * dp;
+        const double eps = st.epsrow[r];
+        double ll = 0.0;
+        for (int s = 0; s < st.nsplit; ++s) ll += st.llpart[(int64_t)s * K + r];   // fixed order
+        double tt = 0.0, k1 = 0.0;
+        for (int j = lane; j < dp; j += 32) {
+            double gsum = 0.0;
+            for (int s = 0; s < st.nsplit; ++s) gsum += st.gpart[((int64_t)s * K + r) * dp + j];
+            const double th = thp[j];
+            const double gp = (j < d) ? gsum - th * pvinv : 0.0;
+            grp[j] = gp;
+            tt += th * th;
+            if (!MMALA) {
+                const double p1 = xi[j] + 0.5 * eps * (grc[j] + gp);     // hamiltonian.py:27,40
+                k1 += p1 * p1;
+            }
+        }
+        tt = group_sum<32>(tt);
+        k1 = group_sum<32>(k1);
+        const double lprior = -0.5 * tt * pvinv - 0.5 * (double)d * log(2.0 * M_PI * st.pv);
+        const double lpn = combine_logpost(lprior, ll);
+        double lqr;
+        if (!MMALA) {
+            lqr = 0.5 * (k1 - st.k0[r]);                                  // hamiltonian.py:89
+        } else {
+            // geometry of the proposal: L' = chol(G'), logdet', nat' = G'^-1 grad'
+            const double* Gm = st.Gm + r * (int64_t)d * d;
+            for (int q = lane; q < d * d; q += 32) {
+                const int a = q / d, b = q % d;
+                Lw[q] = Gm[q] + ((a == b) ? pvinv : 0.0);
+            }
+            __syncwarp();
+            const double ld = warp_cholesky(Lw, d, lane);
+            for (int j = lane; j < d; j += 32) v1[j] = grp[j];
+            __syncwarp();
+            warp_trsv_lower(Lw, v1, d, lane);
+            warp_trsv_lower_t(Lw, v1, d, lane);                           // v1 = nat'
+            // reverse residual  r = L'^T (theta - mean'),  mean' = theta' + eps^2/2 nat'
+            for (int j = lane; j < d; j += 32) v2[j] = thc[j] - (thp[j] + 0.5 * eps * eps * v1[j]);
+            __syncwarp();
+            double rr = 0.0;
+            for (int j = lane; j < d; j += 32) {
+                double s = 0.0;
+                for (int i = j; i < d; ++i) s += Lw[i * d + j] * v2[i];  // (L^T v)_j
+                rr += s * s;
+            }
+            rr = group_sum<32>(rr);
+            const double ldc = st.logdet[(int64_t)c * K + r];
+            const double cst = 0.5 * (double)d * log(2.0 * M_PI * eps * eps);
+            const double lq_fwd = 0.5 * ldc - cst - 0.5 * st.k0[r];      // |L^T(theta'-mean)|^2 = eps^2 |xi|^2
+            const double lq_rev = 0.5 * ld - cst - 0.5 * rr / (eps * eps);
+            lqr = lq_fwd - lq_rev;
+            // stash the proposal's geometry in its slot
+            double* Lp = st.Lc + ((int64_t)pslot * K + r) * d * d;
+            for (int q = lane; q < d * d; q += 32) Lp[q] = Lw[q];
+            double* np_ = st.nat + ((int64_t)pslot * K + r) * dp;
+            for (int j = lane; j < d; j += 32) np_[j] = v1[j];
+            if (lane == 0) st.logdet[(int64_t)pslot * K + r] = ld;
+        }
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        const bool acc = mh_accept(lpn, lp, lqr, u);
+        if (acc) { c ^= 1; lp = lpn; }
+        if (lane == 0) {
+            if (acc) { st.cur[r] = c; st.lp[r] = lp; }
+            st.dacc[r] += acc ? 1 : 0;
+            if (sp.adapt) {
+                AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
+                ad.update(acc, sp.target);
+                st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts;
+            }
+            if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
+            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
+            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+        }
+        __syncwarp();
+    }
+
+    const double* th = st.Th + ((int64_t)c * K + r) * dp;
+    const double* gr = st.Gr + ((int64_t)c * K + r) * dp;
+    double* thn = st.Th + ((int64_t)(c ^ 1) * K + r) * dp;
+    double* xo = st.Xi + r * dp;
+    const double scale = sp.adapt ? st.scale[r] : 1.0;
+    const double eps = scale * sp.eps0;
+    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+    double k0 = 0.0, rowsum = 0.0;
+
+    if (MMALA && sp.propose) {
+        const double* Lcur = st.Lc + ((int64_t)c * K + r) * d * d;
+        for (int q = lane; q < d * d; q += 32) Lw[q] = Lcur[q];
+    }
+    for (int j4 = lane * 4; j4 < dp; j4 += 128) {
+        double xi[4];
+        if (sp.propose) {
+            if (sp.inj_xi) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xi[q] = (j4 + q < d) ? sp.inj_xi[r * d + j4 + q] : 0.0;
+            } else {
+                normal4(rk.block((uint64_t)sp.step_prop, (uint32_t)(j4 >> 2)), xi);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (j4 + q >= d) xi[q] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j4 + q;
+            const double tv = th[j];
+            rowsum += tv;
+            if (want_trace && j < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j] = tv;
+            if (!sp.propose) continue;
+            k0 += xi[q] * xi[q];
+            xo[j] = xi[q];
+            if (!MMALA) {
+                const double ph = xi[q] + 0.5 * eps * gr[j];             // hamiltonian.py:27
+                thn[j] = tv + eps * ph;                                  // :30
+            } else {
+                v1[j] = xi[q];
+            }
+        }
+    }
+    if (MMALA && sp.propose) {
+        __syncwarp();
+        warp_trsv_lower_t(Lw, v1, d, lane);                              // v1 = L^-T xi
+        const double* nc = st.nat + ((int64_t)c * K + r) * dp;
+        for (int j = lane; j < dp; j += 32)
+            thn[j] = (j < d) ? (th[j] + 0.5 * eps * eps * nc[j]) + eps * v1[j] : 0.0;
+    }
+    if (sp.propose) {
+        k0 = group_sum<32>(k0);
+        if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
+    }
+    if (sp.diag) {
+        rowsum = group_sum<32>(rowsum);
+        const int nd = min(d, ND_MAX - 1) + 1;
+        if (lane < nd) {
+            const double f = (lane == nd - 1) ? rowsum / (double)d : th[lane];
+            st.S1[(int64_t)lane * K + r] += f;
+            st.S2[(int64_t)lane * K + r] += f * f;
+        }
+    }
+}
+
+// set_state helpers: stage into slot 1, evaluate with fixed_slot = 1, then adopt
+__global__ void lg_set_kernel(LogisticState st, const double* __restrict__ theta) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.dp) return;
+    const int64_t r = i / st.dp;
+    const int j = (int)(i % st.dp);
+    st.Th[((int64_t)1 * st.K + r) * st.dp + j] = (j < st.d) ? theta[r * st.d + j] : 0.0;
+    st.Xi[i] = 0.0;
+    if (j == 0) { st.cur[r] = 0; st.k0[r] = 0.0; st.epsrow[r] = 0.0; }
+}
+template <bool MMALA>
+__global__ void __launch_bounds__(128)
+lg_adopt_kernel(LogisticState st) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int dp = st.dp, d = st.d;
+    const int64_t K = st.K;
+    const double pvinv = 1.0 / st.pv;
+    const double* th = st.Th + ((int64_t)1 * K + r) * dp;
+    double* gr = st.Gr + ((int64_t)1 * K + r) * dp;
+    double ll = 0.0;
+    for (int s = 0; s < st.nsplit; ++s) ll += st.llpart[(int64_t)s * K + r];
+    double tt = 0.0;
+    for (int j = lane; j < dp; j += 32) {
+        double gsum = 0.0;
+        for (int s = 0; s < st.nsplit; ++s) gsum += st.gpart[((int64_t)s * K + r) * dp + j];
+        gr[j] = (j < d) ? gsum - th[j] * pvinv : 0.0;
+        tt += th[j] * th[j];
+    }
+    tt = group_sum<32>(tt);
+    if (MMALA) {
+        double* Lw = sm + (size_t)wib * (d * d + dp);
+        double* v1 = Lw + d * d;
+        const double* Gm = st.Gm + r * (int64_t)d * d;
+        for (int q = lane; q < d * d; q += 32) Lw[q] = Gm[q] + ((q / d == q % d) ? pvinv : 0.0);
+        __syncwarp();
+        const double ld = warp_cholesky(Lw, d, lane);
+        for (int j = lane; j < d; j += 32) v1[j] = gr[j];
+        __syncwarp();
+        warp_trsv_lower(Lw, v1, d, lane);
+        warp_trsv_lower_t(Lw, v1, d, lane);
+        double* Lp = st.Lc + ((int64_t)1 * K + r) * d * d;
+        for (int q = lane; q < d * d; q += 32) Lp[q] = Lw[q];
+        double* np_ = st.nat + ((int64_t)1 * K + r) * dp;
+        for (int j = lane; j < d; j += 32) np_[j] = v1[j];
+        if (lane == 0) st.logdet[(int64_t)1 * K + r] = ld;
+    }
+    if (lane == 0) {
+        const double lprior = -0.5 * tt * pvinv - 0.5 * (double)d * log(2.0 * M_PI * st.pv);
+        st.lp[r] = combine_logpost(lprior, ll);
+        st.cur[r] = 1;
+    }
+}
+__global__ void lg_get_kernel(LogisticState st, double* theta, double* lp) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.d) return;
+    const int64_t r = i / st.d;
+    const int j = (int)(i % st.d);
+    if (theta) theta[i] = st.Th[((int64_t)st.cur[r] * st.K + r) * st.dp + j];
+    if (lp && j == 0) lp[r] = st.lp[r];
+}
+__global__ void lg_get_adapt_kernel(LogisticState st, double* scale, int64_t* ns, int64_t* na) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= st.K) return;
+    if (scale) scale[c] = st.scale[c];
+    if (ns) ns[c] = st.nsamp[c];
+    if (na) na[c] = st.nacc[c];
+}
+// pointwise outputs from a staged evaluation (slot 1)
+__global__ void lg_point_out_kernel(LogisticState st, int which, double* out, double* grad, double* metric) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int dp = st.dp, d = st.d;
+    const double pvinv = 1.0 / st.pv;
+    const double* th = st.Th + ((int64_t)1 * st.K + r) * dp;
+    double ll = 0.0;
+    for (int s = 0; s < st.nsplit; ++s) ll += st.llpart[(int64_t)s * st.K + r];
+    double tt = 0.0;
+    for (int j = lane; j < d; j += 32) {
+        double gsum = 0.0;
+        for (int s = 0; s < st.nsplit; ++s) gsum += st.gpart[((int64_t)s * st.K + r) * dp + j];
+        if (grad) grad[r * d + j] = gsum - th[j] * pvinv;
+        tt += th[j] * th[j];
+    }
+    tt = group_sum<32>(tt);
+    const double lprior = -0.5 * tt * pvinv - 0.5 * (double)d * log(2.0 * M_PI * st.pv);
+    if (out && lane == 0) out[r] = (which == 1) ? ll : ((which == 2) ? lprior : combine_logpost(lprior, ll));
+    if (metric) {
+        const double* Gm = st.Gm + r * (int64_t)d * d;
+        for (int q = lane; q < d * d; q += 32) metric[r * (int64_t)d * d + q] = Gm[q] + ((q / d == q % d) ? pvinv : 0.0);
+    }
+}
+
+static int choose_nsplit(int64_t K, int64_t N) {
+    const int64_t nblocks = (K + BC - 1) / BC;
+    int ns = (int)(148 / nblocks);
+    if (ns < 1) ns = 1;
+    const int64_t max_by_rows = (N + 4 * BI - 1) / (4 * BI);
+    if (ns > max_by_rows) ns = (int)max_by_rows;
+    if (ns > 64) ns = 64;
+    return ns;
+}
+
+static void fill_geometry(LogisticState& st, const rmn_model* m, int64_t K) {
+    st.K = K; st.N = m->N; st.d = m->d;
+    st.dp = (m->d + 15) / 16 * 16;
+    st.ldt = st.dp + 4;
+    st.nsplit = choose_nsplit(K, m->N);
+    const int64_t per = (m->N + st.nsplit - 1) / st.nsplit;
+    st.rows_per_split = (per + BI - 1) / BI * BI;
+    st.pv = m->prior_var;
+    st.X = m->d_X; st.y = m->d_y;
+}
+
+struct LogisticSampler : SamplerImpl {
+    rmn_sampler* s;
+    LogisticState st{};
+    bool mmala;
+    explicit LogisticSampler(rmn_sampler* s_) : s(s_) {
+        fill_geometry(st, s->model, s->K);
+        mmala = (s->prop->kind == RMN_PROP_MMALA);
+    }
+    size_t rowb() const { return align256((size_t)st.K * st.dp * 8); }
+    size_t eval_smem() const { return ((size_t)BC * st.ldt + 2 * BI * st.ldt + 2 * BI) * 8; }
+    size_t metric_smem() const { return ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8; }
+    size_t fp_smem() const { return mmala ? (size_t)4 * (st.d * st.d + 2 * st.dp) * 8 : 0; }
+    size_t workspace_bytes() const override {
+        const size_t K = (size_t)st.K;
+        size_t n = 5 * rowb() + align256((size_t)st.nsplit * K * 8) +
+                   align256((size_t)st.nsplit * K * st.dp * 8) + 7 * align256(K * 8) + align256(K * 4) +
+                   2 * align256(ND_MAX * K * 8) + 256;
+        if (mmala) n += 3 * align256(K * st.d * st.d * 8) + 2 * align256(K * 8) + 2 * rowb();
+        return n;
+    }
+    int bind(void* ws) override {
+        const size_t K = (size_t)st.K;
+        char* p = (char*)ws;
+        st.Th = (double*)p; p += 2 * rowb();
+        st.Gr = (double*)p; p += 2 * rowb();
+        st.Xi = (double*)p; p += rowb();
+        st.llpart = (double*)p; p += align256((size_t)st.nsplit * K * 8);
+        st.gpart = (double*)p; p += align256((size_t)st.nsplit * K * st.dp * 8);
+        st.lp = (double*)p; p += align256(K * 8);
+        st.k0 = (double*)p; p += align256(K * 8);
+        st.epsrow = (double*)p; p += align256(K * 8);
+        st.scale = (double*)p; p += align256(K * 8);
+        st.nsamp = (long long*)p; p += align256(K * 8);
+        st.nacc = (long long*)p; p += align256(K * 8);
+        st.dacc = (long long*)p; p += align256(K * 8);
+        st.cur = (int*)p; p += align256(K * 4);
+        st.S1 = (double*)p; p += align256(ND_MAX * K * 8);
+        st.S2 = (double*)p; p += align256(ND_MAX * K * 8);
+        if (mmala) {
+            st.Gm = (double*)p; p += align256(K * st.d * st.d * 8);
+            st.Lc = (double*)p; p += 2 * align256(K * st.d * st.d * 8);
+            st.logdet = (double*)p; p += 2 * align256(K * 8);
+            st.nat = (double*)p; p += 2 * rowb();
+        }
+        RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem()));
+        if (mmala) {
+            RMN_CUDA(cudaFuncSetAttribute(lg_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)metric_smem()));
+            RMN_CUDA(cudaFuncSetAttribute(lg_finish_propose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem()));
+            RMN_CUDA(cudaFuncSetAttribute(lg_adopt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem()));
+        }
+        int rc = rmn_fill_f64(st.scale, st.K, 1.0, 0);
+        if (rc) return rc;
+        RMN_CUDA(cudaDeviceSynchronize());
+        return RMN_OK;
+    }
+    // Lc / logdet slots must be exactly K*d*d / K apart
+    unsigned row_grid() const { return (unsigned)((st.K * 32 + 127) / 128); }
+
+    int eval(int fixed_slot, cudaStream_t stream) {
+        dim3 grid((unsigned)((st.K + BC - 1) / BC), st.nsplit);
+        lg_eval_kernel<<<grid, EVAL_THREADS, eval_smem(), stream>>>(st, fixed_slot);
+        RMN_KERNEL_CHECK(); launches++;
+        if (mmala) {
+            lg_metric_kernel<<<(unsigned)((st.K + 3) / 4), 256, metric_smem(), stream>>>(st, fixed_slot);
+            RMN_KERNEL_CHECK(); launches++;
+        }
+        return RMN_OK;
+    }
+    int set_state(const double* d_theta, cudaStream_t stream) override {
+        const int64_t n = st.K * st.dp;
+        lg_set_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta);
+        RMN_KERNEL_CHECK(); launches++;
+        if (int rc = eval(1, stream)) return rc;
+        if (mmala) lg_adopt_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(st);
+        else lg_adopt_kernel<false><<<row_grid(), 128, 0, stream>>>(st);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int get_state(double* d_theta, double* d_lp, cudaStream_t stream) override {
+        const int64_t n = st.K * st.d;
+        lg_get_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta, d_lp);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
+        const rmn_proposal* pr = s->prop;
+        if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        rmn_trace_t t0{};
+        if (tr) t0 = *tr;
+        if (t0.thin <= 0) t0.thin = 1;
+        LgStep sp{};
+        sp.mmala = mmala; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
+        sp.seed = s->seed; sp.chain_offset = s->chain_offset;
+        const int64_t K = st.K;
+        const int d = st.d;
+        for (int64_t t = 0; t <= T; ++t) {
+            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
+            sp.step_fin = step0 + t - 1; sp.step_prop = step0 + t;
+            sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;
+            sp.inj_xi = (inj && t < T) ? inj->d_xi + t * K * d : nullptr;
+            sp.trace_slot = -1;
+            sp.tr_theta = t0.d_theta; sp.tr_logpost = t0.d_logpost;
+            sp.tr_prop_lp = (t0.d_prop_logpost && t > 0) ? t0.d_prop_logpost + (t - 1) * K : nullptr;
+            sp.tr_acc = (t0.d_accepted && t > 0) ? t0.d_accepted + (t - 1) * K : nullptr;
+            if (t > 0 && (t0.d_theta || t0.d_logpost)) {
+                const int64_t i = t;
+                if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
+            }
+            if (mmala) lg_finish_propose_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(st, sp);
+            else lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(st, sp);
+            RMN_KERNEL_CHECK(); launches++;
+            if (t == T) break;
+            if (int rc = eval(-1, stream)) return rc;
+        }
+        step0 += T; diag_steps += T;
+        return RMN_OK;
+    }
+    int get_adapt(double* sc, int64_t* ns, int64_t* na, cudaStream_t stream) override {
+        lg_get_adapt_kernel<<<(unsigned)((st.K + 127) / 128), 128, 0, stream>>>(st, sc, ns, na);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int diag_dim() const override { return (st.d < ND_MAX - 1 ? st.d : ND_MAX - 1) + 1; }
+    int reset_diag(cudaStream_t stream) override {
+        RMN_CUDA(cudaMemsetAsync(st.S1, 0, (size_t)ND_MAX * st.K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.S2, 0, (size_t)ND_MAX * st.K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)st.K * 8, stream));
+        diag_steps = 0;
+        return RMN_OK;
+    }
+    int reduce_diag(double* d_block, cudaStream_t stream) override {
+        launches++;
+        return rmn_reduce_diag_block(st.K, diag_dim(), diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
+    }
+};
+
+}  // namespace
+
+SamplerImpl* make_logistic_sampler(rmn_sampler* s) {
+    const rmn_proposal* p = s->prop;
+    const int d = s->model->d;
+    if (d > 128) {
+        rmn_set_error("logistic kernels support d <= 128 (got %d)", d);
+        return nullptr;
+    }
+    if (p->kind == RMN_PROP_MMALA) {
+        if (d > MM_DMAX) {
+            rmn_set_error("mMALA supports d <= %d (shared-memory Cholesky); got %d", MM_DMAX, d);
+            return nullptr;
+        }
+        return new LogisticSampler(s);
+    }
+    if (p->kind == RMN_PROP_HMC && p->nsteps == 1 && !p->has_mass) return new LogisticSampler(s);
+    rmn_set_error("logistic model: device kernels exist for MALA (VanillaHMC Nsteps=1, no mass matrix) "
+                  "and SimplifiedMMALA");
+    return nullptr;
+}
+
+// Pointwise evaluation of n arbitrary points: stage them as a temporary chain block and run
+// the same kernels the sampler uses (parity harness entry; allocates scratch, synchronous).
 int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta, double* d_out,
-                       double* d_grad, double* d_metric, cudaStream_t st) { rmn_set_error("logistic not built yet"); return RMN_ERR_UNSUPPORTED; }
+                       double* d_grad, double* d_metric, cudaStream_t stream) {
+    if (n <= 0) return RMN_OK;
+    if (m->d > 128) { rmn_set_error("logistic kernels support d <= 128"); return RMN_ERR_UNSUPPORTED; }
+    if (d_metric && m->d > MM_DMAX) { rmn_set_error("metric supports d <= %d", MM_DMAX); return RMN_ERR_UNSUPPORTED; }
+    LogisticState st{};
+    fill_geometry(st, m, n);
+    const size_t rowb = (size_t)n * st.dp * 8;
+    char* buf = nullptr;
+    const size_t total = 2 * rowb + rowb + (size_t)st.nsplit * n * 8 + (size_t)st.nsplit * n * st.dp * 8 +
+                         (size_t)n * 4 + (d_metric ? (size_t)n * st.d * st.d * 8 : 0) + 4096;
+    RMN_CUDA(cudaMalloc(&buf, total));
+    RMN_CUDA(cudaMemsetAsync(buf, 0, total, stream));
+    char* p = buf;
+    st.Th = (double*)p; p += 2 * rowb;
+    st.Xi = (double*)p; p += rowb;
+    st.llpart = (double*)p; p += (size_t)st.nsplit * n * 8;
+    st.gpart = (double*)p; p += (size_t)st.nsplit * n * st.dp * 8;
+    if (d_metric) { st.Gm = (double*)p; p += (size_t)n * st.d * st.d * 8; }
+    st.cur = (int*)p;
+    // k0/epsrow are touched by lg_set_kernel: point them at scratch inside Xi's tail is unsafe -> own words
+    double* scratch = nullptr;
+    RMN_CUDA(cudaMalloc(&scratch, (size_t)n * 16));
+    st.k0 = scratch; st.epsrow = scratch + n;
+    const size_t esm = ((size_t)BC * st.ldt + 2 * BI * st.ldt + 2 * BI) * 8;
+    const size_t msm = ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8;
+    RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+    const int64_t ne = n * st.dp;
+    lg_set_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(st, d_theta);
+    dim3 grid((unsigned)((n + BC - 1) / BC), st.nsplit);
+    lg_eval_kernel<<<grid, EVAL_THREADS, esm, stream>>>(st, 1);
+    if (d_metric) {
+        RMN_CUDA(cudaFuncSetAttribute(lg_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+        lg_metric_kernel<<<(unsigned)((n + 3) / 4), 256, msm, stream>>>(st, 1);
+    }
+    lg_point_out_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(st, which, d_out, d_grad, d_metric);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(stream);
+    cudaFree(buf);
+    cudaFree(scratch);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        rmn_set_error("logistic_pointwise: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return RMN_ERR_CUDA;
+    }
+    return RMN_OK;
+}

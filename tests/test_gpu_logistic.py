@@ -1,0 +1,147 @@
+"""
+GPU parity for the logistic-regression family (riemann_b200/csrc/logistic.cu): MALA
+(config 4 shape) and simplified manifold MALA (config 5 shape).
+
+The reference has neither the model nor the metric proposal ("parity unpinned"):
+the fixtures were produced by driving the numpy restatement of the model through the
+REFERENCE's own Sampler.sample and VanillaHMC (oracle/gen_golden.py), and the device
+replays that stream.
+
+Tolerance: fp64 kernels vs fp64 numpy.  Log-posteriors 1e-9 relative-or-absolute, gradients
+and metric 1e-9, mMALA log q ratio through the decisions (identical) and the chains (1e-8:
+the Cholesky / triangular solves amplify round-off by the metric's condition number).
+"""
+import numpy as np
+import pytest
+
+from gpu_helpers import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _models(X, y, pv):
+    from oracle import riemann_port as port
+    from riemann_b200.models.logistic import LogisticRegression
+    return LogisticRegression(X, y, pv), port.LogisticRegression(X, y, pv)
+
+
+@pytest.mark.parametrize("N,d", [(500, 8), (1000, 100), (333, 7), (400, 6), (5000, 64), (130, 1)])
+def test_pointwise_logpost_grad_metric(N, d):
+    from oracle import riemann_port as port
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=100 + d)
+    dm, om = _models(X, y, pv)
+    rng = np.random.default_rng(d)
+    Th = ts[None, :] * rng.uniform(0, 1.5, (13, 1)) + 0.3 * rng.standard_normal((13, d))
+    assert relerr(dm.log_posterior_batch(Th).cpu().numpy(), [om.log_posterior(t) for t in Th]) < TOL
+    assert relerr(dm.log_likelihood_batch(Th).cpu().numpy(), [om.log_likelihood(t) for t in Th]) < TOL
+    assert relerr(dm.log_prior_batch(Th).cpu().numpy(), [om.log_prior(t) for t in Th]) < TOL
+    assert relerr(dm.grad_log_posterior_batch(Th).cpu().numpy(), [om.grad_log_posterior(t) for t in Th]) < TOL
+    if d <= 64:
+        assert relerr(dm.metric_batch(Th).cpu().numpy(), [om.metric(t) for t in Th]) < TOL
+    assert abs(dm.log_posterior(Th[0]) - om.log_posterior(Th[0])) < TOL * abs(om.log_posterior(Th[0]))
+
+
+def test_extreme_logits_are_stable():
+    from oracle import riemann_port as port
+    X, y, ts, pv = port.make_logistic_problem(300, 5, seed=3)
+    dm, om = _models(X, y, pv)
+    Th = np.stack([ts * 400.0, -ts * 400.0, np.zeros(5)])            # |z| up to several hundred
+    assert relerr(dm.log_posterior_batch(Th).cpu().numpy(), [om.log_posterior(t) for t in Th]) < TOL
+    assert relerr(dm.grad_log_posterior_batch(Th).cpu().numpy(), [om.grad_log_posterior(t) for t in Th]) < 1e-8
+
+
+@pytest.mark.parametrize("name,tol", [("mala_logistic", 1e-9), ("mmala_logistic", 1e-8)])
+def test_injected_chain_matches_fixture(golden, name, tol):
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
+    g = golden(name)
+    dm, _ = _models(g["X"], g["y"], float(g["prior_var"]))
+    p = (MALA(float(g["eps"]), dm.grad_log_posterior) if name == "mala_logistic"
+         else SimplifiedMMALA(float(g["eps"]), dm))
+    s = Sampler(dm, p, g["thetas"][0])
+    ex = s.run_injected(xi=g["xi"], u=g["u"])
+    assert relerr(np.array(s._chain_thetas), g["thetas"]) < tol
+    assert relerr(s._chain_logpost, g["logpost"]) < tol
+    assert relerr(ex["prop_logpost"][:, 0], g["prop_logpost"]) < tol
+    assert np.array_equal(ex["accepted"][:, 0], np.any(g["thetas"][1:] != g["thetas"][:-1], axis=1))
+
+
+@pytest.mark.parametrize("kind", ["mala", "mmala"])
+def test_ragged_chains_vs_oracle(kind):
+    """K = 70 chains (not a multiple of the 64-chain CTA tile), several row splits."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
+    N, d, K, T = 1500, 10, 70, 25
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=77)
+    dm, om = _models(X, y, pv)
+    rng = np.random.default_rng(1)
+    th0 = ts[None, :] + 0.1 * rng.standard_normal((K, d))
+    xi = rng.standard_normal((T, K, d))
+    u = rng.uniform(size=(T, K))
+    eps = 0.15 if kind == "mala" else 0.7
+    p = MALA(eps, dm.grad_log_posterior) if kind == "mala" else SimplifiedMMALA(eps, dm)
+    s = Sampler(dm, p, th0)
+    s.run_injected(xi=xi, u=u)
+    for c in (0, 63, 64, 69):
+        op = port.MALA(eps, om.grad_log_posterior) if kind == "mala" else port.SimplifiedMMALA(eps, om)
+        o = port.Sampler(om, op, th0[c], draws=port.VectorTapeDraws(xi[:, c], u[:, c]))
+        o.run(T)
+        assert relerr(s._chain_thetas[:, c], np.array(o._chain_thetas)) < 1e-8
+        assert relerr(s._chain_logpost[:, c], np.array(o._chain_logpost)) < 1e-8
+    acc = np.mean(np.any(s._chain_thetas[1:] != s._chain_thetas[:-1], axis=2))
+    assert 0.2 < acc < 0.99
+
+
+@pytest.mark.parametrize("kind", ["mala", "mmala"])
+def test_philox_run_agrees_with_oracle_posterior(kind):
+    """Distributional gate vs a long CPU chain of the oracle (same model, own numpy stream)."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
+    N, d = 400, 5
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=21)
+    dm, om = _models(X, y, pv)
+    eps = 0.3 if kind == "mala" else 0.9
+    np.random.seed(5)
+    op = port.MALA(eps, om.grad_log_posterior) if kind == "mala" else port.SimplifiedMMALA(eps, om)
+    o = port.Sampler(om, op, ts.copy())
+    o.run(6000, 1000)
+    och = np.array(o._chain_thetas)
+    p = MALA(eps, dm.grad_log_posterior) if kind == "mala" else SimplifiedMMALA(eps, dm)
+    s = Sampler(dm, p, ts.copy(), K=2048, seed=17)
+    s.run(300, trace=False)
+    s.reset_diagnostics()
+    s.run(300, trace=False)
+    dg = s.diagnostics(allreduce=False)
+    th = np.asarray(s._chain_thetas[-1])
+    sd = och.std(0)
+    assert np.all(np.abs(th.mean(0) - och.mean(0)) < 0.25 * sd)
+    assert np.all(np.abs(th.std(0) / sd - 1.0) < 0.2)
+    oacc = np.mean(np.any(och[1:] != och[:-1], axis=1))
+    assert abs(dg["accept_rate"] - oacc) < 0.06
+    lp = np.asarray(s._chain_logpost[-1])
+    assert relerr(lp, dm.log_posterior_batch(th).cpu().numpy()) < 1e-10
+
+
+def test_config5_shape_self_consistency():
+    """N = 1e5, d = 64 (config 5 data shape), 128 chains of mMALA: carried log-posterior equals
+    a fresh evaluation; the metric is symmetric positive definite."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import SimplifiedMMALA
+    X, y, ts, pv = port.make_logistic_problem(100000, 64)
+    dm, om = _models(X, y, pv)
+    rng = np.random.default_rng(0)
+    th0 = ts[None, :] + 0.01 * rng.standard_normal((128, 64))
+    s = Sampler(dm, SimplifiedMMALA(0.5, dm), th0, seed=1)
+    s.run(4, trace=False)
+    th, lp = s.state_tensors()
+    assert relerr(lp.cpu().numpy(), dm.log_posterior_batch(th).cpu().numpy()) < 1e-10
+    G = dm.metric_batch(th[:3]).cpu().numpy()
+    assert relerr(G[0], om.metric(th[0].cpu().numpy())) < TOL
+    assert np.allclose(G, np.transpose(G, (0, 2, 1)), rtol=1e-12, atol=1e-12)
+    assert np.all(np.linalg.eigvalsh(G[1]) > 0)
+    dg = s.diagnostics(allreduce=False)
+    assert dg["accept_rate"] > 0.3
