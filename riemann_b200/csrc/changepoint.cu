@@ -67,44 +67,54 @@ __device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int M,
     return pos;
 }
 
-// Full log-posterior (which=0), log-likelihood (1) or log-prior (2) of one state held
-// across the 16 lanes of a group.  Plain IEEE arithmetic: log of a negative gap/height
-// gives nan, log(0) gives -inf, exactly like numpy; the reference's nan -> -inf and
-// inf/nan -> -inf rules are applied at the end.
-__device__ __forceinline__ double cp_logpost(const CPParams& P, const double* __restrict__ xs,
+// ---------------------------------------------------------------------------------------
+// Log-posterior of one state held across the 16 lanes of a group, in two stages so that the
+// kernel can batch ALL of a step's fp64 logarithms into one (rarely two) `log` calls:
+//   stage 1 (cp_segments): binary search, per-lane segment residual, gap and height term;
+//   the caller takes log(gap) per lane together with the step's scalar logs
+//   (log sigma^2, log 1/sigma^2, log u, log|J|) computed on otherwise idle lanes;
+//   stage 2 (cp_combine): 16-lane reductions and the reference's term-by-term sums.
+// Plain IEEE arithmetic: log of a negative gap/height gives nan, log(0) gives -inf, exactly
+// like numpy; the reference's nan -> -inf and inf/nan -> -inf rules are applied at the end.
+// ---------------------------------------------------------------------------------------
+struct CPSeg { double ss, gap, vt; };
+
+__device__ __forceinline__ CPSeg cp_segments(const CPParams& P, const double* __restrict__ xs,
                                              const double* __restrict__ cy,
                                              const double* __restrict__ cyy, int lane, int k,
-                                             double cx, double cv_, double sig, int which) {
-    const bool active = lane <= k;
-    // boundaries of this lane's segment
+                                             double cx, double cv_) {
     const int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;
     int bl = __shfl_up_sync(0xffffffffu, bu, 1, LANES);
     if (lane == 0) bl = 0;
     double prev = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
     if (lane == 0) prev = P.xmin;
     const double hi = (lane < k) ? cx : P.xmax;
-
-    double ss = 0.0, lg = 0.0, vt = 0.0;
-    if (active) {
+    CPSeg o;
+    o.ss = 0.0; o.vt = 0.0; o.gap = 1.0;                       // log(1) = 0 on inactive lanes
+    if (lane <= k) {
         const double n = (double)(bu - bl);
         const double s1 = cy[bu] - cy[bl];
         const double s2 = cyy[bu] - cyy[bl];
         const double vc = cv_ - P.ycenter;
-        ss = n * vc * vc - 2.0 * vc * s1 + s2;
-        lg = log(hi - prev);                                   // changepoint.py:142-143
-        vt = -P.beta * cv_ + P.cv;                             // changepoint.py:18-19,136
-        if (!P.alpha_is_one) vt += (P.alpha - 1.0) * log(cv_);
-        else if (!(cv_ > 0.0)) vt = NAN;                       // 0 * log(v<=0) is nan in numpy
+        o.ss = n * vc * vc - 2.0 * vc * s1 + s2;
+        o.gap = hi - prev;                                     // changepoint.py:142-143
+        o.vt = -P.beta * cv_ + P.cv;                           // changepoint.py:18-19,136
+        if (!P.alpha_is_one) o.vt += (P.alpha - 1.0) * log(cv_);
+        else if (!(cv_ > 0.0)) o.vt = NAN;                     // 0 * log(v<=0) is nan in numpy
     }
-    ss = group_sum<LANES>(ss);
-    lg = group_sum<LANES>(lg);
-    vt = group_sum<LANES>(vt);
+    return o;
+}
 
+// lg = per-lane log(gap) (0 on inactive lanes); log_s2 = log(sigma^2); lsig = log(1/sigma^2)
+__device__ __forceinline__ double cp_combine(const CPParams& P, int k, double sig, CPSeg sg, double lg,
+                                             double log_s2, double lsig, int which) {
+    const double ss = group_sum<LANES>(sg.ss);
+    lg = group_sum<LANES>(lg);
+    const double vt = group_sum<LANES>(sg.vt);
     const int ks = k + 1;                                      // number of steps
     const double s2v = sig * sig;
-    double logl = -0.5 * ((ss / s2v + (double)P.M * log(s2v)) + P.Mlog2pi);   // :118-120
+    double logl = -0.5 * ((ss / s2v + (double)P.M * log_s2) + P.Mlog2pi);   // :118-120
     if (isnan(logl)) logl = -INFINITY;                         // :124-125
-    double lsig = log(1.0 / s2v);                              // :145
     if (sig < 0.0) lsig = NAN;                                 // :146-147
     const double lps = (P.tab2[ks] + lg) - (double)ks * P.logL;
     double logp = ((P.tab1[ks] + vt) + lps) + lsig;            // :156
@@ -114,8 +124,27 @@ __device__ __forceinline__ double cp_logpost(const CPParams& P, const double* __
     return combine_logpost(logp, logl);
 }
 
+// stand-alone evaluation (set_state / pointwise): scalar logs ride on lanes 14, 15 when free
+__device__ __forceinline__ double cp_logpost(const CPParams& P, const double* __restrict__ xs,
+                                             const double* __restrict__ cy,
+                                             const double* __restrict__ cyy, int lane, int k,
+                                             double cx, double cv_, double sig, int which) {
+    const CPSeg sg = cp_segments(P, xs, cy, cyy, lane, k, cx, cv_);
+    const double s2v = sig * sig;
+    const double lg = log(sg.gap);
+    const double sl = log((lane & 1) ? 1.0 / s2v : s2v);
+    const double log_s2 = __shfl_sync(0xffffffffu, sl, 0, LANES);
+    const double lsig = __shfl_sync(0xffffffffu, sl, 1, LANES);
+    return cp_combine(P, k, sig, sg, (lane <= k) ? lg : 0.0, log_s2, lsig, which);
+}
+
+// uniform on (0,1) from 32 random bits with 2 fp64 instructions: [1,2) mantissa trick + 2^-33
+__device__ __forceinline__ double u01_fast(uint32_t x) {
+    return __hiloint2double(0x3ff00000 | (x >> 12), x << 20) - (1.0 - 1.1641532182693481e-10);
+}
+
 template <bool INJ, bool SMEMDATA, bool DIAG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
                    int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
                    const double* __restrict__ tape, rmn_trace_t tr) {
@@ -144,6 +173,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     double s1 = 0.0, s2 = 0.0;                    // lane i < NDIAG accumulates functional i
     const RngKey rk(seed, (uint64_t)(chain_offset + c));
     const TraceSel ts{tr.first, tr.thin > 0 ? tr.thin : 1};
+    const bool tracing = tr.d_k || tr.d_cpx || tr.d_cpv || tr.d_sig || tr.d_logpost;
 
     for (int64_t t = 0; t < T; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
@@ -156,17 +186,21 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             nrand = (int)row[RMN_CP_SLOT_N]; uacc = row[RMN_CP_SLOT_ACC];
             xi = row[RMN_CP_SLOT_XI + lane];
         } else {
-            const uint4 a = rk.block(step, RMN_BLOCK_AUX);
-            const uint4 b = rk.block(step, RMN_BLOCK_AUX2);
-            u1 = u01(a.x); u2 = u01(a.y); u3 = u01(a.z); ubd = u01(a.w);
-            snew = P.xmin + (P.xmax - P.xmin) * u01(b.x);
-            du = -0.1 + 0.2 * u01(b.y);
-            nrand = (int)(u01(b.z) * (double)k);
-            uacc = u01(b.w);
+            // ONE Philox block per lane and step: words x,y -> this lane's normal; the spare
+            // words z,w of lanes 0..3 carry the chain-level uniforms
             const uint4 r = rk.block(step, (uint32_t)lane);
             float n0, n1;
             box_muller(r.x, r.y, n0, n1);
             xi = (double)n0;
+            const uint32_t z0 = __shfl_sync(0xffffffffu, r.z, 0, LANES), w0 = __shfl_sync(0xffffffffu, r.w, 0, LANES);
+            const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, LANES), w1 = __shfl_sync(0xffffffffu, r.w, 1, LANES);
+            const uint32_t z2 = __shfl_sync(0xffffffffu, r.z, 2, LANES), w2 = __shfl_sync(0xffffffffu, r.w, 2, LANES);
+            const uint32_t z3 = __shfl_sync(0xffffffffu, r.z, 3, LANES), w3 = __shfl_sync(0xffffffffu, r.w, 3, LANES);
+            u1 = u01_fast(z0); u2 = u01_fast(w0); u3 = u01_fast(z1); ubd = u01_fast(w1);
+            snew = P.xmin + (P.xmax - P.xmin) * u01_fast(z2);
+            du = -0.1 + 0.2 * u01_fast(w2);
+            nrand = (int)(u01_fast(z3) * (double)k);
+            uacc = u01_fast(w3);
         }
         nrand = max(0, min(nrand, k - 1));
 
@@ -174,52 +208,76 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         const int mv = (u1 < P.p1) ? 0 : ((u2 < P.p2) ? 1 : ((u3 < P.p3) ? 2 : 3));
         const bool birth = (k == 0) || (ubd > 0.5);                     // :59
 
-        // ---- shuffles every lane takes part in, whatever the move
-        const double xi0 = __shfl_sync(0xffffffffu, xi, 0, LANES);
-        const double px = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
-        const double pv = __shfl_up_sync(0xffffffffu, cv, 1, LANES);
-        const double qx = __shfl_down_sync(0xffffffffu, cx, 1, LANES);
-        const double qv = __shfl_down_sync(0xffffffffu, cv, 1, LANES);
-        const int nb = __popc(group_ballot(lane < k && cx < snew));     // searchsorted(cpx, s), :206
-        const double hb = __shfl_sync(0xffffffffu, cv, nb, LANES);
-        const double h1d = __shfl_sync(0xffffffffu, cv, nrand, LANES);
-        const double h2d = __shfl_sync(0xffffffffu, cv, nrand + 1, LANES);
-
-        // ---- build the proposal by selection (no divergence between the two chains of a warp)
+        // ---- build the proposal by selection (the two chains of a warp never diverge on mv)
         int kk = k;
-        double nx = cx, nv = cv, nsig = sig, lqr = 0.0;
+        double nx = cx, nv = cv, nsig = sig, jarg = 1.0;
         bool ovf = false;
         if (mv == 0) {
             if (lane < k) nx = __dadd_rn(cx, __dmul_rn(P.sx[k], xi));   // randomwalk.py:26, scale = 1
         } else if (mv == 1) {
             if (lane <= k) nv = __dadd_rn(cv, __dmul_rn(P.sv, xi));
-        } else if (mv == 2) {
-            nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
-        } else if (birth) {
-            const double u = 0.5 + du / P.sqrtM;                        // :61
-            const double f = sqrt((1.0 - u) / u);                       // changepoint.py:57
-            lqr = log(fabs(hb / (u * (1.0 - u))));                      // log|J|, :72-74
-            if (k + 1 > LANES - 1) {
-                ovf = true;
-            } else {
-                nx = (lane < nb) ? cx : ((lane == nb) ? snew : px);
-                nv = (lane < nb) ? cv : ((lane == nb) ? hb / f : ((lane == nb + 1) ? hb * f : pv));
-                kk = k + 1;
+        }
+        const double xi0 = __shfl_sync(0xffffffffu, xi, 0, LANES);
+        if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
+        if (__any_sync(0xffffffffu, mv == 3)) {                         // warp-uniform (35 % of steps)
+            const double px = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
+            const double pv = __shfl_up_sync(0xffffffffu, cv, 1, LANES);
+            const double qx = __shfl_down_sync(0xffffffffu, cx, 1, LANES);
+            const double qv = __shfl_down_sync(0xffffffffu, cv, 1, LANES);
+            const int nb = __popc(group_ballot(lane < k && cx < snew)); // searchsorted(cpx, s), :206
+            const double hb = __shfl_sync(0xffffffffu, cv, nb, LANES);
+            const double h1d = __shfl_sync(0xffffffffu, cv, nrand, LANES);
+            const double h2d = __shfl_sync(0xffffffffu, cv, nrand + 1, LANES);
+            if (mv == 3) {
+                if (birth) {
+                    const double u = 0.5 + du / P.sqrtM;                // :61
+                    const double f = sqrt((1.0 - u) / u);               // changepoint.py:57
+                    jarg = fabs(hb / (u * (1.0 - u)));                  // |J|, :72-74
+                    if (k + 1 > LANES - 1) {
+                        ovf = true;
+                    } else {
+                        nx = (lane < nb) ? cx : ((lane == nb) ? snew : px);
+                        nv = (lane < nb) ? cv : ((lane == nb) ? hb / f : ((lane == nb + 1) ? hb * f : pv));
+                        kk = k + 1;
+                    }
+                } else {
+                    const double h = sqrt(h1d * h2d);                   // changepoint.py:67
+                    const double u = 1.0 / (1.0 + h2d / h1d);           // :68
+                    jarg = fabs(h / (u * (1.0 - u)));                   // 1/|J^-1|, :76-78
+                    nx = (lane < nrand) ? cx : qx;
+                    nv = (lane < nrand) ? cv : ((lane == nrand) ? h : qv);
+                    kk = k - 1;
+                }
             }
-        } else {
-            const double h = sqrt(h1d * h2d);                           // changepoint.py:67
-            const double u = 1.0 / (1.0 + h2d / h1d);                   // :68
-            lqr = -log(fabs(h / (u * (1.0 - u))));                      // log|J^-1|, :76-78
-            nx = (lane < nrand) ? cx : qx;
-            nv = (lane < nrand) ? cv : ((lane == nrand) ? h : qv);
-            kk = k - 1;
         }
         // lanes beyond the new extent hold zeros (canonical padding)
         if (lane >= kk) nx = 0.0;
         if (lane > kk) nv = 0.0;
 
-        const double lpn = cp_logpost(P, xs, cy, cyy, lane, kk, nx, nv, nsig, 0);
-        const bool acc = !ovf && mh_accept(lpn, lp, lqr, uacc);
+        // ---- log-posterior of the proposal; every fp64 log of the step in one call:
+        //      lanes 0..kk take log(gap); lanes 12..15 take log sigma^2, log 1/sigma^2, log u, log|J|
+        //      (if a chain has more than 11 changepoints those four go through a second call)
+        const CPSeg sg = cp_segments(P, xs, cy, cyy, lane, kk, nx, nv);
+        const double s2n = nsig * nsig;
+        const int sl = lane & 3;
+        const double sarg = (sl == 0) ? s2n : ((sl == 1) ? 1.0 / s2n : ((sl == 2) ? uacc : jarg));
+        const bool crowded = kk > 11;
+        const double l1 = log((lane >= 12 && !crowded) ? sarg : sg.gap);
+        double l2 = 0.0;
+        if (__any_sync(0xffffffffu, crowded)) l2 = log(sarg);
+        const double lsrc = crowded ? l2 : l1;
+        const int sbase = crowded ? 0 : 12;
+        const double log_s2 = __shfl_sync(0xffffffffu, lsrc, sbase + 0, LANES);
+        const double lsig = __shfl_sync(0xffffffffu, lsrc, sbase + 1, LANES);
+        const double logu = __shfl_sync(0xffffffffu, lsrc, sbase + 2, LANES);
+        const double ljac = __shfl_sync(0xffffffffu, lsrc, sbase + 3, LANES);
+        const double lpn = cp_combine(P, kk, nsig, sg, (lane <= kk) ? l1 : 0.0, log_s2, lsig, 0);
+        const double lqr = (mv == 3) ? (birth ? ljac : -ljac) : 0.0;
+
+        // sampler.py:83-84 with Python's min(0, nan) == 0
+        const double delta = lpn - lp - lqr;
+        const double mh = (delta < 0.0) ? delta : 0.0;
+        const bool acc = !ovf && (logu < mh);
         if (acc) { k = kk; cx = nx; cv = nv; sig = nsig; lp = lpn; }
         nacc += acc ? 1 : 0;
         novf += ovf ? 1 : 0;
@@ -240,7 +298,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                 if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpn;
                 if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
             }
-            if (tr.d_k || tr.d_cpx || tr.d_cpv || tr.d_sig || tr.d_logpost) {
+            if (tracing) {
                 const long long r = ts.slot(t + 1);
                 if (r >= 0) {
                     if (tr.d_cpx) tr.d_cpx[(r * K + c) * LANES + lane] = cx;

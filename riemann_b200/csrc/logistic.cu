@@ -815,23 +815,26 @@ int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta
     if (d_metric && m->d > MM_DMAX) { rmn_set_error("metric supports d <= %d", MM_DMAX); return RMN_ERR_UNSUPPORTED; }
     LogisticState st{};
     fill_geometry(st, m, n);
-    const size_t rowb = (size_t)n * st.dp * 8;
+    const size_t rowb = align256((size_t)n * st.dp * 8);
+    const size_t sz_ll = align256((size_t)st.nsplit * n * 8);
+    const size_t sz_g = align256((size_t)st.nsplit * n * st.dp * 8);
+    const size_t sz_m = d_metric ? align256((size_t)n * st.d * st.d * 8) : 0;
+    const size_t sz_s = align256((size_t)n * 8);
+    const size_t total = 3 * rowb + sz_ll + sz_g + sz_m + 3 * sz_s;
     char* buf = nullptr;
-    const size_t total = 2 * rowb + rowb + (size_t)st.nsplit * n * 8 + (size_t)st.nsplit * n * st.dp * 8 +
-                         (size_t)n * 4 + (d_metric ? (size_t)n * st.d * st.d * 8 : 0) + 4096;
     RMN_CUDA(cudaMalloc(&buf, total));
     RMN_CUDA(cudaMemsetAsync(buf, 0, total, stream));
     char* p = buf;
+    // the two Th slots must be exactly n*dp doubles apart: carve them from one 2*rowb block
     st.Th = (double*)p; p += 2 * rowb;
     st.Xi = (double*)p; p += rowb;
-    st.llpart = (double*)p; p += (size_t)st.nsplit * n * 8;
-    st.gpart = (double*)p; p += (size_t)st.nsplit * n * st.dp * 8;
-    if (d_metric) { st.Gm = (double*)p; p += (size_t)n * st.d * st.d * 8; }
-    st.cur = (int*)p;
-    // k0/epsrow are touched by lg_set_kernel: point them at scratch inside Xi's tail is unsafe -> own words
+    st.llpart = (double*)p; p += sz_ll;
+    st.gpart = (double*)p; p += sz_g;
+    if (d_metric) { st.Gm = (double*)p; p += sz_m; }
+    st.cur = (int*)p; p += sz_s;
+    st.k0 = (double*)p; p += sz_s;
+    st.epsrow = (double*)p; p += sz_s;
     double* scratch = nullptr;
-    RMN_CUDA(cudaMalloc(&scratch, (size_t)n * 16));
-    st.k0 = scratch; st.epsrow = scratch + n;
     const size_t esm = ((size_t)BC * st.ldt + 2 * BI * st.ldt + 2 * BI) * 8;
     const size_t msm = ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8;
     RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));

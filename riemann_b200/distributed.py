@@ -57,4 +57,4 @@ def summarize_block(b):
     return {"chains": int(K), "steps": int(n), "accept_rate": b[2] / max(K * n, 1.0),
             "overflows": int(b[3]), "mean": mean, "var": W + B, "within_var": W,
             "between_var": B, "tau": tau, "ess": ess, "rhat": rhat,
-            "min_ess": float(np.nanmin(ess)) if nd else float("nan")}
+            "min_ess": float(np.nanmin(ess)) if nd and np.any(np.isfinite(ess)) else float("nan")}
