@@ -176,6 +176,37 @@ def _changepoint_fixture(R, name, nchains, T, seed0):
         seed0=np.int64(seed0))
 
 
+def _cp_summary_worker(seed):
+    """One long chain of the UNMODIFIED reference on the bench problem; window statistics."""
+    R = refshim.load_reference()
+    pm, pprop, ptheta0, _ = port.make_changepoint_problem()
+    model = R.ChangepointRegression1D(pm.x, pm.y, pm.xmin, pm.xmax, pm.lamb, pm.kmax, pm.alpha, pm.beta)
+    prop = R.ChangepointRegression1DProp(model, pprop.hscale)
+    np.random.seed(seed)
+    s = R.Sampler(model, prop, R.ChangepointParams(ptheta0.cpx, ptheta0.cpv, ptheta0.sig))
+    with refshim.quiet(), np.errstate(all="ignore"):
+        s.run(10000, 6000)
+    ks = np.array([len(t.cpx) for t in s._chain_thetas])
+    sig = np.array([float(np.squeeze(t.sig)) for t in s._chain_thetas])
+    lp = np.array(s._chain_logpost)
+    return (ks.mean(), sig.mean(), np.mean(lp[1:] != lp[:-1]), np.bincount(ks, minlength=LANES)[:LANES] / len(ks))
+
+
+def _changepoint_posterior_summary(name, nchains=48, seed0=7000):
+    """Distributional fixture: per-chain window means (steps 6000..10000 from the example's
+    start state) of 48 independent reference chains, each on numpy's own stream."""
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(_cp_summary_worker, [seed0 + i for i in range(nchains)])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),
+                        mean_k=np.array([r[0] for r in res]), mean_sig=np.array([r[1] for r in res]),
+                        accept=np.array([r[2] for r in res]), khist=np.array([r[3] for r in res]),
+                        burn=np.int64(6000), T=np.int64(10000), seed0=np.int64(seed0))
+    mk = np.array([r[0] for r in res])
+    print("%-28s %d chains: mean k = %.3f +- %.3f, accept = %.3f" % (
+        name, nchains, mk.mean(), mk.std() / np.sqrt(nchains), np.mean([r[2] for r in res])))
+
+
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
@@ -284,6 +315,7 @@ def main():
 
     # --- config 2: changepoint model + 4-way proposal
     _changepoint_fixture(R, "changepoint", nchains=4, T=3000, seed0=400)
+    _changepoint_posterior_summary("changepoint_posterior")
 
     # --- models/proposals the reference lacks, driven through the reference Sampler
     _portmodel_through_reference(R, "mala_logistic", "mala", 501)
