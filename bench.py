@@ -344,7 +344,7 @@ def run_e2e(args, s, T, Kg, world, sync_all):
         dev_out = [torch.empty_like(host_in[0], device="cuda"), torch.empty(Kg, dtype=torch.float64, device="cuda")]
     host_out = [torch.empty_like(d, device="cpu").pin_memory() for d in dev_out]
     nd = lib.rmn_sampler_diag_dim(s._handle)
-    host_blk = torch.empty(4 + 3 * nd, dtype=torch.float64).pin_memory()
+    host_blk = torch.empty(_lib.DIAG_HDR + 3 * nd, dtype=torch.float64).pin_memory()
     h2d = sum(h.numel() * h.element_size() for h in host_in)
     d2h = sum(h.numel() * h.element_size() for h in host_out) + host_blk.numel() * 8
 

@@ -194,13 +194,16 @@ int rmn_sampler_run(rmn_sampler_t* s, int64_t T, const rmn_inject_t* inj,
 int rmn_sampler_get_adapt(rmn_sampler_t* s, double* d_scale, int64_t* d_nsamples,
                           int64_t* d_naccepts, void* stream);
 
-/* Diagnostics since the last reset.  nd = rmn_sampler_diag_dim().  The block is
- *   [0] K  [1] steps per chain  [2] total accepts  [3] KCAP overflow events
- *   [4..4+nd)       sum_c m_c[j]          (m_c = per-chain mean of functional j)
- *   [4+nd..4+2nd)   sum_c m_c[j]^2
- *   [4+2nd..4+3nd)  sum_c v_c[j]          (v_c = per-chain biased variance)
- * every entry is a SUM over chains, so blocks from several GPUs combine with one
- * all-reduce(sum); split-R-hat and ESS follow on the host. */
+/* Diagnostics since the last reset.  nd = rmn_sampler_diag_dim(), H = RMN_DIAG_HDR.  The block is
+ *   [0] K   [1] functional samples per chain (the changepoint kernel accumulates every
+ *   RMN_CP_DIAG_EVERY-th step, the others every step)   [2] total accepts
+ *   [3] KCAP overflow events   [4] MH steps per chain   [5] reserved
+ *   [H..H+nd)        sum_c m_c[j]          (m_c = per-chain mean of functional j)
+ *   [H+nd..H+2nd)    sum_c m_c[j]^2
+ *   [H+2nd..H+3nd)   sum_c v_c[j]          (v_c = per-chain biased variance)
+ * entries [0],[2],[3] and the sums are additive over chains, so blocks from several GPUs
+ * combine with one all-reduce(sum); split-R-hat and ESS follow on the host. */
+#define RMN_DIAG_HDR 6
 int rmn_sampler_diag_dim(const rmn_sampler_t* s);
 int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream);
 int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stream);

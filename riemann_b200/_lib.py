@@ -18,6 +18,7 @@ CP_LANES = 16
 CP_SLOT = dict(sel1=0, sel2=1, sel3=2, bd=3, s=4, du=5, n=6, acc=7, xi=8)
 CP_NSLOT = 8 + CP_LANES
 CP_NDIAG = 8
+DIAG_HDR = 6
 SMALL_D_MAX = 8
 
 

@@ -28,6 +28,7 @@ namespace {
 
 constexpr int LANES = RMN_CP_LANES;
 constexpr int NQ = 6;   // prediction query points tracked by the diagnostics
+#define RMN_CP_DIAG_EVERY 4   // diagnostics functionals are accumulated every 4th MH step
 
 struct CPParams {
     int M, P2, alpha_is_one, pad;
@@ -37,6 +38,7 @@ struct CPParams {
     double sx[LANES + 1];       // sqrt(0.01 (xmax-xmin)/(k+1))         test_changepoint.py:36
     double sv, ss;              // sqrt(0.01 hscale^2/M), sqrt(0.01 hscale)   :37-38
     double p1, p2, p3;          // sequential selection thresholds      :28-30
+    uint32_t t1, t2, t3, tpad;  // the same thresholds on the raw 32-bit Philox words
     double xq[NQ];
 };
 
@@ -79,11 +81,10 @@ __device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int M,
 // ---------------------------------------------------------------------------------------
 struct CPSeg { double ss, gap, vt; };
 
-__device__ __forceinline__ CPSeg cp_segments(const CPParams& P, const double* __restrict__ xs,
-                                             const double* __restrict__ cy,
+__device__ __forceinline__ CPSeg cp_segments(const CPParams& P, const double* __restrict__ cy,
                                              const double* __restrict__ cyy, int lane, int k,
-                                             double cx, double cv_) {
-    const int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;
+                                             double cx, double cv_, int bu) {
+    // bu = #{x_i <= cpx[lane]} for lane < k, M otherwise (upper end of this lane's run of data)
     int bl = __shfl_up_sync(0xffffffffu, bu, 1, LANES);
     if (lane == 0) bl = 0;
     double prev = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
@@ -129,7 +130,8 @@ __device__ __forceinline__ double cp_logpost(const CPParams& P, const double* __
                                              const double* __restrict__ cy,
                                              const double* __restrict__ cyy, int lane, int k,
                                              double cx, double cv_, double sig, int which) {
-    const CPSeg sg = cp_segments(P, xs, cy, cyy, lane, k, cx, cv_);
+    const int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;
+    const CPSeg sg = cp_segments(P, cy, cyy, lane, k, cx, cv_, bu);
     const double s2v = sig * sig;
     const double lg = log(sg.gap);
     const double sl = log((lane & 1) ? 1.0 / s2v : s2v);
@@ -169,6 +171,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     double cv = st.cpv[c * LANES + lane];
     double sig = st.sig[c];
     double lp = st.lp[c];
+    int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;   // cached run boundaries of the state
     long long nacc = 0, novf = 0;
     double s1 = 0.0, s2 = 0.0;                    // lane i < NDIAG accumulates functional i
     const RngKey rk(seed, (uint64_t)(chain_offset + c));
@@ -177,14 +180,19 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
 
     for (int64_t t = 0; t < T; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
-        double u1, u2, u3, ubd, snew, du, uacc, xi;
-        int nrand;
+        double snew, du, uacc, xi;
+        int nrand, mv;
+        bool birth;
         if (INJ) {
             const double* row = tape + (t * K + c) * RMN_CP_NSLOT;
-            u1 = row[RMN_CP_SLOT_SEL1]; u2 = row[RMN_CP_SLOT_SEL2]; u3 = row[RMN_CP_SLOT_SEL3];
-            ubd = row[RMN_CP_SLOT_BD]; snew = row[RMN_CP_SLOT_S]; du = row[RMN_CP_SLOT_DU];
+            const double u1 = row[RMN_CP_SLOT_SEL1], u2 = row[RMN_CP_SLOT_SEL2], u3 = row[RMN_CP_SLOT_SEL3];
+            const double ubd = row[RMN_CP_SLOT_BD];
+            snew = row[RMN_CP_SLOT_S]; du = row[RMN_CP_SLOT_DU];
             nrand = (int)row[RMN_CP_SLOT_N]; uacc = row[RMN_CP_SLOT_ACC];
             xi = row[RMN_CP_SLOT_XI + lane];
+            // which block moves (fresh uniform per elif, test_changepoint.py:48-54); birth/death :59
+            mv = (u1 < P.p1) ? 0 : ((u2 < P.p2) ? 1 : ((u3 < P.p3) ? 2 : 3));
+            birth = (k == 0) || (ubd > 0.5);
         } else {
             // ONE Philox block per lane and step: words x,y -> this lane's normal; the spare
             // words z,w of lanes 0..3 carry the chain-level uniforms
@@ -196,7 +204,8 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, LANES), w1 = __shfl_sync(0xffffffffu, r.w, 1, LANES);
             const uint32_t z2 = __shfl_sync(0xffffffffu, r.z, 2, LANES), w2 = __shfl_sync(0xffffffffu, r.w, 2, LANES);
             const uint32_t z3 = __shfl_sync(0xffffffffu, r.z, 3, LANES), w3 = __shfl_sync(0xffffffffu, r.w, 3, LANES);
-            u1 = u01_fast(z0); u2 = u01_fast(w0); u3 = u01_fast(z1); ubd = u01_fast(w1);
+            mv = (z0 < P.t1) ? 0 : ((w0 < P.t2) ? 1 : ((z1 < P.t3) ? 2 : 3));   // same tests on raw words
+            birth = (k == 0) || (w1 >= 0x80000000u);                            // u > 0.5
             snew = P.xmin + (P.xmax - P.xmin) * u01_fast(z2);
             du = -0.1 + 0.2 * u01_fast(w2);
             nrand = (int)(u01_fast(z3) * (double)k);
@@ -204,12 +213,8 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         }
         nrand = max(0, min(nrand, k - 1));
 
-        // ---- which block moves (fresh uniform per elif, test_changepoint.py:48-54)
-        const int mv = (u1 < P.p1) ? 0 : ((u2 < P.p2) ? 1 : ((u3 < P.p3) ? 2 : 3));
-        const bool birth = (k == 0) || (ubd > 0.5);                     // :59
-
         // ---- build the proposal by selection (the two chains of a warp never diverge on mv)
-        int kk = k;
+        int kk = k, nbu = bu;
         double nx = cx, nv = cv, nsig = sig, jarg = 1.0;
         bool ovf = false;
         if (mv == 0) {
@@ -228,6 +233,8 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             const double hb = __shfl_sync(0xffffffffu, cv, nb, LANES);
             const double h1d = __shfl_sync(0xffffffffu, cv, nrand, LANES);
             const double h2d = __shfl_sync(0xffffffffu, cv, nrand + 1, LANES);
+            const int pbu = __shfl_up_sync(0xffffffffu, bu, 1, LANES);
+            const int qbu = __shfl_down_sync(0xffffffffu, bu, 1, LANES);
             if (mv == 3) {
                 if (birth) {
                     const double u = 0.5 + du / P.sqrtM;                // :61
@@ -238,6 +245,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                     } else {
                         nx = (lane < nb) ? cx : ((lane == nb) ? snew : px);
                         nv = (lane < nb) ? cv : ((lane == nb) ? hb / f : ((lane == nb + 1) ? hb * f : pv));
+                        nbu = (lane <= nb) ? bu : pbu;          // lane nb is searched below
                         kk = k + 1;
                     }
                 } else {
@@ -246,18 +254,26 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                     jarg = fabs(h / (u * (1.0 - u)));                   // 1/|J^-1|, :76-78
                     nx = (lane < nrand) ? cx : qx;
                     nv = (lane < nrand) ? cv : ((lane == nrand) ? h : qv);
+                    nbu = (lane < nrand) ? bu : qbu;
                     kk = k - 1;
                 }
             }
         }
         // lanes beyond the new extent hold zeros (canonical padding)
-        if (lane >= kk) nx = 0.0;
+        if (lane >= kk) { nx = 0.0; nbu = P.M; }
         if (lane > kk) nv = 0.0;
+        // run boundaries only move when a location moves: a cpx block move (every lane) or a
+        // birth (the new lane).  Warp-uniform, taken on about half of the steps.
+        const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
+        if (__any_sync(0xffffffffu, moved_x)) {
+            const int sb = upper_bound(xs, P.M, P.P2, nx);
+            if (moved_x && lane < kk) nbu = sb;
+        }
 
         // ---- log-posterior of the proposal; every fp64 log of the step in one call:
         //      lanes 0..kk take log(gap); lanes 12..15 take log sigma^2, log 1/sigma^2, log u, log|J|
         //      (if a chain has more than 11 changepoints those four go through a second call)
-        const CPSeg sg = cp_segments(P, xs, cy, cyy, lane, kk, nx, nv);
+        const CPSeg sg = cp_segments(P, cy, cyy, lane, kk, nx, nv, nbu);
         const double s2n = nsig * nsig;
         const int sl = lane & 3;
         const double sarg = (sl == 0) ? s2n : ((sl == 1) ? 1.0 / s2n : ((sl == 2) ? uacc : jarg));
@@ -278,11 +294,11 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         const double delta = lpn - lp - lqr;
         const double mh = (delta < 0.0) ? delta : 0.0;
         const bool acc = !ovf && (logu < mh);
-        if (acc) { k = kk; cx = nx; cv = nv; sig = nsig; lp = lpn; }
+        if (acc) { k = kk; cx = nx; cv = nv; sig = nsig; lp = lpn; bu = nbu; }
         nacc += acc ? 1 : 0;
         novf += ovf ? 1 : 0;
 
-        if (DIAG) {
+        if (DIAG && (step % RMN_CP_DIAG_EVERY) == 0) {      // thinned accumulation (warp-uniform)
             double f = (lane == 0) ? sig : (double)k;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -388,6 +404,12 @@ static CPParams make_params(const rmn_model* m, const rmn_proposal* p) {
     P.sv = sqrt(0.01 * (hs * hs) / (double)m->M);
     P.ss = sqrt(0.01 * hs);
     P.p1 = p ? p->p_cum[0] : 0.2; P.p2 = p ? p->p_cum[1] : 0.4; P.p3 = p ? p->p_cum[2] : 0.6;
+    // (x + 0.5) 2^-32 < p  <=>  x < ceil(p 2^32 - 0.5)
+    auto thr = [](double pc) {
+        const double v = ceil(pc * 4294967296.0 - 0.5);
+        return (uint32_t)(v <= 0.0 ? 0.0 : (v >= 4294967295.0 ? 4294967295.0 : v));
+    };
+    P.t1 = thr(P.p1); P.t2 = thr(P.p2); P.t3 = thr(P.p3); P.tpad = 0;
     for (int q = 0; q < NQ; ++q)
         P.xq[q] = m->xmin + (m->xmax - m->xmin) * (q + 0.5) / (double)NQ;
     return P;
@@ -474,6 +496,9 @@ struct ChangepointSampler : SamplerImpl {
         }
         RMN_KERNEL_CHECK();
         launches++;
+        // samples = #{ s in [step0, step0+T) : s % EVERY == 0 }
+        const int64_t E = RMN_CP_DIAG_EVERY;
+        diag_samples += (step0 + T + E - 1) / E - (step0 + E - 1) / E;
         step0 += T; diag_steps += T;
         return RMN_OK;
     }
@@ -483,12 +508,12 @@ struct ChangepointSampler : SamplerImpl {
         RMN_CUDA(cudaMemsetAsync(st.S2, 0, (size_t)RMN_CP_NDIAG * s->K * 8, stream));
         RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)s->K * 8, stream));
         RMN_CUDA(cudaMemsetAsync(st.dovf, 0, (size_t)s->K * 8, stream));
-        diag_steps = 0;
+        diag_steps = 0; diag_samples = 0;
         return RMN_OK;
     }
     int reduce_diag(double* d_block, cudaStream_t stream) override {
         launches++;
-        return rmn_reduce_diag_block(s->K, RMN_CP_NDIAG, diag_steps, st.S1, st.S2, st.dacc, st.dovf,
+        return rmn_reduce_diag_block(s->K, RMN_CP_NDIAG, diag_samples, diag_steps, st.S1, st.S2, st.dacc, st.dovf,
                                      d_block, stream);
     }
 };

@@ -212,6 +212,7 @@ struct SamplerImpl {
     int64_t launches = 0;
     int64_t step0 = 0;        // global MH step index of the next iteration (Philox counter)
     int64_t diag_steps = 0;   // steps since the last diagnostics reset
+    int64_t diag_samples = 0; // functional samples accumulated since the reset (families that thin)
 };
 
 struct rmn_sampler {
@@ -240,7 +241,7 @@ int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta
 int rmn_fill_f64(double* p, int64_t n, double v, cudaStream_t st);
 int rmn_fill_i64(long long* p, int64_t n, long long v, cudaStream_t st);
 // per-chain sums -> diagnostics block; S1/S2 are [nd][K] (chain fastest)
-int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsteps, const double* S1, const double* S2,
+int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsamples, int64_t nsteps, const double* S1, const double* S2,
                           const long long* acc, const long long* ovf, double* d_block,
                           cudaStream_t st);
 

@@ -780,7 +780,7 @@ struct LogisticSampler : SamplerImpl {
     }
     int reduce_diag(double* d_block, cudaStream_t stream) override {
         launches++;
-        return rmn_reduce_diag_block(st.K, diag_dim(), diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
+        return rmn_reduce_diag_block(st.K, diag_dim(), diag_steps, diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
     }
 };
 

@@ -383,7 +383,7 @@ struct SmallGaussSampler : SamplerImpl {
     }
     int reduce_diag(double* d_block, cudaStream_t stream) override {
         launches++;
-        return rmn_reduce_diag_block(s->K, D, diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
+        return rmn_reduce_diag_block(s->K, D, diag_steps, diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
     }
 };
 

@@ -28,14 +28,14 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
 // S1/S2 laid out [nd][K] (chain fastest).  Block j < nd reduces functional j over
 // chains; block nd reduces the counters.  Plain stores, no atomics.
 __global__ void __launch_bounds__(256)
-reduce_diag_kernel(int64_t K, int nd, int64_t nsteps, const double* __restrict__ S1,
+reduce_diag_kernel(int64_t K, int nd, int64_t nsamples, int64_t nsteps, const double* __restrict__ S1,
                    const double* __restrict__ S2, const long long* __restrict__ acc,
                    const long long* __restrict__ ovf, double* __restrict__ block) {
     __shared__ double sh[8];
     const int j = blockIdx.x;
     if (j < nd) {
         double sm = 0, sm2 = 0, sv = 0;
-        const double inv = nsteps > 0 ? 1.0 / (double)nsteps : 0.0;
+        const double inv = nsamples > 0 ? 1.0 / (double)nsamples : 0.0;
         for (int64_t c = threadIdx.x; c < K; c += blockDim.x) {
             const double m = S1[(int64_t)j * K + c] * inv;
             const double v = S2[(int64_t)j * K + c] * inv - m * m;
@@ -45,9 +45,9 @@ reduce_diag_kernel(int64_t K, int nd, int64_t nsteps, const double* __restrict__
         sm2 = block_sum_256(sm2, sh);
         sv = block_sum_256(sv, sh);
         if (threadIdx.x == 0) {
-            block[4 + j] = sm;
-            block[4 + nd + j] = sm2;
-            block[4 + 2 * nd + j] = sv;
+            block[RMN_DIAG_HDR + j] = sm;
+            block[RMN_DIAG_HDR + nd + j] = sm2;
+            block[RMN_DIAG_HDR + 2 * nd + j] = sv;
         }
     } else {
         double a = 0, o = 0;
@@ -59,9 +59,11 @@ reduce_diag_kernel(int64_t K, int nd, int64_t nsteps, const double* __restrict__
         o = block_sum_256(o, sh);
         if (threadIdx.x == 0) {
             block[0] = (double)K;
-            block[1] = (double)nsteps;
+            block[1] = (double)nsamples;
             block[2] = a;
             block[3] = o;
+            block[4] = (double)nsteps;
+            block[5] = 0.0;
         }
     }
 }
@@ -104,10 +106,10 @@ int rmn_fill_i64(long long* p, int64_t n, long long v, cudaStream_t st) {
     return RMN_OK;
 }
 
-int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsteps, const double* S1, const double* S2,
+int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsamples, int64_t nsteps, const double* S1, const double* S2,
                           const long long* acc, const long long* ovf, double* d_block,
                           cudaStream_t st) {
-    reduce_diag_kernel<<<nd + 1, 256, 0, st>>>(K, nd, nsteps, S1, S2, acc, ovf, d_block);
+    reduce_diag_kernel<<<nd + 1, 256, 0, st>>>(K, nd, nsamples, nsteps, S1, S2, acc, ovf, d_block);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }

@@ -1,7 +1,7 @@
 """
 Multi-GPU plumbing: chains shard across ranks (each rank owns K/G chains and the Philox
 substreams of its global chain ids); the only exchange is the per-batch diagnostics
-all-reduce of a (4 + 3 nd)-double block.  torch.distributed
+all-reduce of a (6 + 3 nd)-double block.  torch.distributed
 (NCCL on GPUs, gloo in the CPU tests) carries it.
 """
 import numpy as np
@@ -31,30 +31,33 @@ def reduce_block(blk):
     """Sum a diagnostics block over ranks (no-op without an initialised process group)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        steps = blk[1].clone()
+        same = blk[[1, 4]].clone()
         dist.all_reduce(blk, op=dist.ReduceOp.SUM)
-        blk[1] = steps            # steps-per-chain is identical on every rank, not additive
+        blk[[1, 4]] = same        # samples / steps per chain are identical on every rank, not additive
     return blk
 
 
 def summarize_block(b):
     """
-    b = [K, n, accepts, overflows, sum_c m_c (nd), sum_c m_c^2 (nd), sum_c v_c (nd)].
+    b = [K, n_samples, accepts, overflows, steps, -, sum_c m_c (nd), sum_c m_c^2 (nd), sum_c v_c (nd)].
     tau = n B / W with B the variance of the chain means and W the mean within-chain
     variance; ESS = K n / tau; R-hat from (n-1)/n W + B.
     """
     b = np.asarray(b, dtype=np.float64)
-    nd = (len(b) - 4) // 3
-    K, n = b[0], b[1]
-    sm, sm2, sv = b[4:4 + nd], b[4 + nd:4 + 2 * nd], b[4 + 2 * nd:4 + 3 * nd]
+    H = 6
+    nd = (len(b) - H) // 3
+    K, n, steps = b[0], b[1], b[4]
+    sm, sm2, sv = b[H:H + nd], b[H + nd:H + 2 * nd], b[H + 2 * nd:H + 3 * nd]
     mean = sm / K
     with np.errstate(divide="ignore", invalid="ignore"):
         B = (sm2 - sm * sm / K) / max(K - 1.0, 1.0)
         W = sv / K * (n / max(n - 1.0, 1.0))
-        tau = np.where(W > 0, n * B / W, np.nan)
-        ess = np.where(tau > 0, K * n / tau, np.nan)
+        tau_s = np.where(W > 0, n * B / W, np.nan)          # in units of accumulated samples
+        ess = np.where(tau_s > 0, K * n / tau_s, np.nan)     # = K W / B, independent of the thinning
+        tau = tau_s * (steps / max(n, 1.0))                  # in MH steps
         rhat = np.sqrt(((n - 1.0) / n * W + B) / W)
-    return {"chains": int(K), "steps": int(n), "accept_rate": b[2] / max(K * n, 1.0),
+    return {"chains": int(K), "steps": int(steps), "samples": int(n),
+            "accept_rate": b[2] / max(K * steps, 1.0),
             "overflows": int(b[3]), "mean": mean, "var": W + B, "within_var": W,
             "between_var": B, "tau": tau, "ess": ess, "rhat": rhat,
             "min_ess": float(np.nanmin(ess)) if nd and np.any(np.isfinite(ess)) else float("nan")}

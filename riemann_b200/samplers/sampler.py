@@ -368,7 +368,7 @@ class Sampler(object):
         """Device tensor with the per-device diagnostics block (see riemann_b200.h)."""
         torch = self._torch
         nd = _lib.load().rmn_sampler_diag_dim(self._handle)
-        blk = torch.zeros(4 + 3 * nd, dtype=torch.float64, device="cuda")
+        blk = torch.zeros(_lib.DIAG_HDR + 3 * nd, dtype=torch.float64, device="cuda")
         _lib.check(_lib.load().rmn_sampler_reduce_diagnostics(self._handle, _lib.ptr(blk),
                                                               _lib.stream_ptr()))
         return blk

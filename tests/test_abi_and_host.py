@@ -102,7 +102,7 @@ def test_summarize_block_matches_oracle_estimator():
         x[t] = phi * x[t - 1] + np.sqrt(1 - phi ** 2) * rng.standard_normal((K, d))
     m = x.mean(0)
     v = x.var(0)
-    blk = np.concatenate([[K, n, 0.3 * K * n, 0], m.sum(0), (m * m).sum(0), v.sum(0)])
+    blk = np.concatenate([[K, n, 0.3 * K * n, 0, n, 0], m.sum(0), (m * m).sum(0), v.sum(0)])
     out = summarize_block(blk)
     ess_o, tau_o, rhat_o = ess.ess_from_chain_moments(n, m, x.var(0, ddof=1))
     assert np.allclose(out["tau"], tau_o, rtol=1e-9)
@@ -123,9 +123,9 @@ off, k = shard_chains(K_total)
 rng = np.random.default_rng(0)
 m = rng.standard_normal((K_total, nd)); v = rng.uniform(0.5, 1.5, (K_total, nd))
 mine = slice(off, off + k)
-blk = np.concatenate([[k, n, 7.0 * k, 0], m[mine].sum(0), (m[mine]**2).sum(0), v[mine].sum(0)])
+blk = np.concatenate([[k, n, 7.0 * k, 0, n, 0], m[mine].sum(0), (m[mine]**2).sum(0), v[mine].sum(0)])
 out = reduce_block(torch.tensor(blk))
-full = np.concatenate([[K_total, n, 7.0 * K_total, 0], m.sum(0), (m**2).sum(0), v.sum(0)])
+full = np.concatenate([[K_total, n, 7.0 * K_total, 0, n, 0], m.sum(0), (m**2).sum(0), v.sum(0)])
 assert np.allclose(out.numpy(), full), (out.numpy(), full)
 s = summarize_block(out.numpy())
 assert s["chains"] == K_total and s["steps"] == n
