@@ -115,24 +115,35 @@ def cpu_baseline(workload, budget_s=12.0, cores=None):
 # clocks
 # ----------------------------------------------------------------------------
 class ClockSampler(object):
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 50 ms in the background; started BEFORE warm-up (the tool needs
+    a few hundred ms to come up) and filtered to the wall-clock window of the timed region."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f,
+                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.12)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -140,25 +151,29 @@ class ClockSampler(object):
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             [nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), samples=len(sm))
-        out["reasons"] = sorted(reasons)
+        inwin = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+        use = inwin
+        if not use and rows and self.t0 is not None:          # window shorter than the sampling period
+            mid = 0.5 * (self.t0 + self.t1)
+            use = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
+            out["note"] = "timed window shorter than the 50 ms sampling period: nearest samples used"
+        if use:
+            out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=float(max(r[2] for r in use)),
+                       samples=len(use), reasons=sorted({x for r in use for x in r[3]}))
         return out
 
 
@@ -241,6 +256,7 @@ def run_engine(args):
             torch.cuda.synchronize()
 
     # burn-in (untimed setup), then warm-up steps
+    clocks = ClockSampler(local) if rank == 0 else None
     burn = args.burn if args.burn is not None else {"changepoint": 10000}.get(wl, 2 * T)
     s.run(burn, trace=False)
     for _ in range(max(args.warmup, 3)):
@@ -251,10 +267,11 @@ def run_engine(args):
 
     lib = _lib.load()
     launches0 = s.launch_count
-    clocks = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     sync_all()
+    if clocks:
+        clocks.begin()
     for i in range(args.steps):
         flush.fill_(i & 0xff)                      # L2 flush, outside the event pair
         ev[i][0].record(stream)
@@ -263,6 +280,8 @@ def run_engine(args):
         blk = reduce_block(s.diagnostics_block())  # per-batch diagnostics all-reduce (NCCL)
         ev[i][1].record(stream)
     sync_all()
+    if clocks:
+        clocks.end()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     clk = clocks.stop() if clocks else None
     launches = s.launch_count - launches0

@@ -152,8 +152,11 @@ typedef struct {
  * (i - first) % thin == 0, i >= 1, are written to record r = (i - first) / thin.
  *   fixed-d:      d_theta[r][K][d], d_logpost[r][K]
  *   changepoint:  d_k[r][K], d_cpx[r][K][LANES], d_cpv[r][K][LANES], d_sig[r][K]
- * d_prop_logpost[t][K] / d_accepted[t][K] (every step, unthinned) expose the
- * proposed log-posterior and the decision for parity tests.  Any pointer may be NULL. */
+ * d_prop_logpost[t][K] / d_accepted[t][K] / d_logqratio[t][K] (every step, unthinned)
+ * expose the proposed log-posterior, the decision and log q(theta'|theta)/q(theta|theta')
+ * (proposal.py:15); d_prop_theta[t][K][d] (fixed-d) or d_prop_k/cpx/cpv/sig (changepoint,
+ * canonical layout per step) expose the proposed state itself = what Proposal.propose
+ * returns.  Any pointer may be NULL. */
 typedef struct {
     int64_t first;
     int64_t thin;
@@ -165,6 +168,12 @@ typedef struct {
     double* d_sig;
     double* d_prop_logpost;
     uint8_t* d_accepted;
+    double* d_logqratio;
+    double* d_prop_theta;
+    int32_t* d_prop_k;
+    double* d_prop_cpx;
+    double* d_prop_cpv;
+    double* d_prop_sig;
 } rmn_trace_t;
 
 size_t rmn_sampler_workspace_bytes(const rmn_model_t* m, const rmn_proposal_t* p, int64_t K);
@@ -193,6 +202,12 @@ int rmn_sampler_run(rmn_sampler_t* s, int64_t T, const rmn_inject_t* inj,
 /* AdaptScaleProposal state per chain (adaptive.py:19-24): scale, Nsamples, Naccepts. */
 int rmn_sampler_get_adapt(rmn_sampler_t* s, double* d_scale, int64_t* d_nsamples,
                           int64_t* d_naccepts, void* stream);
+int rmn_sampler_set_adapt(rmn_sampler_t* s, const double* d_scale, const int64_t* d_nsamples,
+                          const int64_t* d_naccepts, void* stream);
+/* Global index of the next MH step = the Philox counter; with get/set_state and get/set_adapt
+ * this is the complete resumable state of a sampler (checkpoint / resume). */
+int64_t rmn_sampler_get_step(const rmn_sampler_t* s);
+int rmn_sampler_set_step(rmn_sampler_t* s, int64_t step);
 
 /* Diagnostics since the last reset.  nd = rmn_sampler_diag_dim(), H = RMN_DIAG_HDR.  The block is
  *   [0] K   [1] functional samples per chain (the changepoint kernel accumulates every

@@ -11,7 +11,7 @@ import os
 from .sampling_errors import ParameterError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libriemann_b200.so")
+LIB_PATH = os.environ.get("RIEMANN_B200_LIB") or os.path.join(_HERE, "libriemann_b200.so")   # env: kernel experiments
 
 RMN_OK, RMN_ERR_PARAM, RMN_ERR_CUDA, RMN_ERR_UNSUPPORTED = 0, -1, -2, -3
 CP_LANES = 16
@@ -30,7 +30,9 @@ class Trace(C.Structure):
     _fields_ = [("first", C.c_int64), ("thin", C.c_int64), ("d_theta", C.c_void_p),
                 ("d_logpost", C.c_void_p), ("d_k", C.c_void_p), ("d_cpx", C.c_void_p),
                 ("d_cpv", C.c_void_p), ("d_sig", C.c_void_p), ("d_prop_logpost", C.c_void_p),
-                ("d_accepted", C.c_void_p)]
+                ("d_accepted", C.c_void_p), ("d_logqratio", C.c_void_p), ("d_prop_theta", C.c_void_p),
+                ("d_prop_k", C.c_void_p), ("d_prop_cpx", C.c_void_p), ("d_prop_cpv", C.c_void_p),
+                ("d_prop_sig", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -67,6 +69,9 @@ SIGNATURES = {
     "rmn_sampler_cp_get_state": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "rmn_sampler_run": (_I, [_P, _L, C.POINTER(Inject), C.POINTER(Trace), _P]),
     "rmn_sampler_get_adapt": (_I, [_P, _P, _P, _P, _P]),
+    "rmn_sampler_set_adapt": (_I, [_P, _P, _P, _P, _P]),
+    "rmn_sampler_get_step": (_L, [_P]),
+    "rmn_sampler_set_step": (_I, [_P, _L]),
     "rmn_sampler_diag_dim": (_I, [_P]),
     "rmn_sampler_reset_diagnostics": (_I, [_P, _P]),
     "rmn_sampler_reduce_diagnostics": (_I, [_P, _P, _P]),

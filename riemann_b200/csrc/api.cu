@@ -354,6 +354,17 @@ extern "C" int rmn_sampler_get_adapt(rmn_sampler_t* s, double* d_scale, int64_t*
     RMN_S(s);
     return s->impl->get_adapt(d_scale, d_nsamples, d_naccepts, (cudaStream_t)stream);
 }
+extern "C" int rmn_sampler_set_adapt(rmn_sampler_t* s, const double* d_scale, const int64_t* d_nsamples,
+                                     const int64_t* d_naccepts, void* stream) {
+    RMN_S(s);
+    return s->impl->set_adapt(d_scale, d_nsamples, d_naccepts, (cudaStream_t)stream);
+}
+extern "C" int64_t rmn_sampler_get_step(const rmn_sampler_t* s) { return (s && s->impl) ? s->impl->step0 : -1; }
+extern "C" int rmn_sampler_set_step(rmn_sampler_t* s, int64_t step) {
+    RMN_S(s); RMN_REQUIRE(step >= 0, "rmn_sampler_set_step: step must be >= 0");
+    s->impl->step0 = step;
+    return RMN_OK;
+}
 extern "C" int rmn_sampler_diag_dim(const rmn_sampler_t* s) { return (s && s->impl) ? s->impl->diag_dim() : 0; }
 extern "C" int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream) {
     RMN_S(s);

@@ -202,6 +202,7 @@ struct SamplerImpl {
     virtual int cp_get_state(int32_t*, double*, double*, double*, double*, cudaStream_t) { return unsupported("cp_get_state"); }
     virtual int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t st) = 0;
     virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }
+    virtual int set_adapt(const double*, const int64_t*, const int64_t*, cudaStream_t) { return unsupported("set_adapt"); }
     virtual int diag_dim() const = 0;
     virtual int reset_diag(cudaStream_t st) = 0;
     virtual int reduce_diag(double* d_block, cudaStream_t st) = 0;
@@ -240,6 +241,8 @@ int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta
 // generic helper kernels (util.cu)
 int rmn_fill_f64(double* p, int64_t n, double v, cudaStream_t st);
 int rmn_fill_i64(long long* p, int64_t n, long long v, cudaStream_t st);
+int rmn_copy_adapt(int64_t K, const double* sc_in, const int64_t* ns_in, const int64_t* na_in, double* sc,
+                   long long* ns, long long* na, cudaStream_t st);
 // per-chain sums -> diagnostics block; S1/S2 are [nd][K] (chain fastest)
 int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsamples, int64_t nsteps, const double* S1, const double* S2,
                           const long long* acc, const long long* ovf, double* d_block,

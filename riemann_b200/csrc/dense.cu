@@ -215,6 +215,7 @@ struct DenseStep {
     const double* inj_xi; const double* inj_u;      // already offset to the respective step
     int64_t trace_slot;     // record slot for the state after the finished step, or -1
     double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc;   // offset to step
+    double* tr_lqr; double* tr_prop_theta;                                       // offset to step
 };
 
 // One warp per chain row.
@@ -243,6 +244,11 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
         const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r]) : 0.0;   // hamiltonian.py:89
         const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
         const bool acc = mh_accept(lpn, lp, lqr, u);
+        if (sp.tr_prop_theta) {                  // the proposal = what Proposal.propose returned
+            const double* ypr = st.Y + ((int64_t)(c ^ 1) * K + r) * dp;
+            for (int j = lane; j < d; j += 32) sp.tr_prop_theta[r * d + j] = ypr[j] + st.mu[j];
+        }
+        if (sp.tr_lqr && lane == 0) sp.tr_lqr[r] = lqr;
         if (acc) { c ^= 1; lp = lpn; }
         if (lane == 0) {
             if (acc) { st.cur[r] = c; st.lp[r] = lp; }
@@ -501,6 +507,8 @@ struct DenseGaussSampler : SamplerImpl {
             sp.tr_theta = t0.d_theta; sp.tr_logpost = t0.d_logpost;
             sp.tr_prop_lp = (t0.d_prop_logpost && t > 0) ? t0.d_prop_logpost + (t - 1) * K : nullptr;
             sp.tr_acc = (t0.d_accepted && t > 0) ? t0.d_accepted + (t - 1) * K : nullptr;
+            sp.tr_lqr = (t0.d_logqratio && t > 0) ? t0.d_logqratio + (t - 1) * K : nullptr;
+            sp.tr_prop_theta = (t0.d_prop_theta && t > 0) ? t0.d_prop_theta + (t - 1) * K * d : nullptr;
             if (t > 0 && (t0.d_theta || t0.d_logpost)) {
                 const int64_t i = t;                      // history index of the state after step t-1
                 if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
@@ -520,6 +528,10 @@ struct DenseGaussSampler : SamplerImpl {
         dense_get_adapt_kernel<<<(unsigned)((st.K + 127) / 128), 128, 0, stream>>>(st, sc, ns, na);
         RMN_KERNEL_CHECK(); launches++;
         return RMN_OK;
+    }
+    int set_adapt(const double* sc, const int64_t* ns, const int64_t* na, cudaStream_t stream) override {
+        launches++;
+        return rmn_copy_adapt(st.K, sc, ns, na, st.scale, st.nsamp, st.nacc, stream);
     }
     int diag_dim() const override { return (st.d < ND_MAX - 1 ? st.d : ND_MAX - 1) + 1; }
     int reset_diag(cudaStream_t stream) override {

@@ -213,6 +213,10 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         }
 
         const double lpq = gauss_logpost<D>(P, q);
+        if (tr.d_prop_theta) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) tr.d_prop_theta[(t * K + c) * D + i] = q[i];
+        }
         const bool acc = mh_accept(lpq, lp, lqr, uacc);
         bool moved = false;
         if (acc) {
@@ -227,6 +231,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
 
         if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpq;
         if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
+        if (tr.d_logqratio) tr.d_logqratio[t * K + c] = lqr;
         if (tr.d_theta || tr.d_logpost) {
             const long long r = ts.slot(t + 1);
             if (r >= 0) {
@@ -372,6 +377,10 @@ struct SmallGaussSampler : SamplerImpl {
         sg_get_adapt_kernel<<<grid(), 128, 0, stream>>>(st, s->K, sc, ns, na);
         RMN_KERNEL_CHECK(); launches++;
         return RMN_OK;
+    }
+    int set_adapt(const double* sc, const int64_t* ns, const int64_t* na, cudaStream_t stream) override {
+        launches++;
+        return rmn_copy_adapt(s->K, sc, ns, na, st.scale, st.nsamp, st.nacc, stream);
     }
     int diag_dim() const override { return D; }
     int reset_diag(cudaStream_t stream) override {

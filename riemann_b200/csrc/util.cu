@@ -68,6 +68,15 @@ reduce_diag_kernel(int64_t K, int nd, int64_t nsamples, int64_t nsteps, const do
     }
 }
 
+__global__ void copy_adapt_kernel(int64_t K, const double* sc_in, const int64_t* ns_in, const int64_t* na_in,
+                                  double* sc, long long* ns, long long* na) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    if (sc_in) sc[c] = sc_in[c];
+    if (ns_in) ns[c] = ns_in[c];
+    if (na_in) na[c] = na_in[c];
+}
+
 __global__ void philox_raw_kernel(int64_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -102,6 +111,13 @@ int rmn_fill_i64(long long* p, int64_t n, long long v, cudaStream_t st) {
     if (n <= 0) return RMN_OK;
     int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
     fill_i64_kernel<<<grid, 256, 0, st>>>(p, n, v);
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}
+
+int rmn_copy_adapt(int64_t K, const double* sc_in, const int64_t* ns_in, const int64_t* na_in, double* sc,
+                   long long* ns, long long* na, cudaStream_t st) {
+    copy_adapt_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(K, sc_in, ns_in, na_in, sc, ns, na);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }

@@ -32,6 +32,49 @@ class ChangepointRegression1DProp(DeviceProposal):
         self.P_cumprop_dim = 1.00
         self.k = None
 
+    def propose(self, theta):
+        """
+        examples/test_changepoint.py:44-73 for ONE state, evaluated by the device kernel.  The
+        draws come from numpy's global stream in the reference's order (the host only routes
+        them into the kernel's tape slots; no proposal arithmetic happens here).
+        """
+        from .. import _lib
+        from ..models.changepoint import unpack_state
+        from ..samplers.sampler import Sampler
+        S = _lib.CP_SLOT
+        k = len(theta.cpx)
+        row = np.zeros(_lib.CP_NSLOT)
+        row[S["acc"]] = 1.0                                  # log(1) = 0 is never < mhratio
+        nnorm = None
+        row[S["sel1"]] = np.random.uniform()
+        if row[S["sel1"]] < self.P_cumprop_cpx:
+            nnorm = k
+        else:
+            row[S["sel2"]] = np.random.uniform()
+            if row[S["sel2"]] < self.P_cumprop_cpv:
+                nnorm = k + 1
+            else:
+                row[S["sel3"]] = np.random.uniform()
+                if row[S["sel3"]] < self.P_cumprop_sig:
+                    nnorm = 1
+                else:
+                    birth = True
+                    if k > 0:
+                        row[S["bd"]] = np.random.uniform()
+                        birth = row[S["bd"]] > 0.5
+                    if birth:
+                        row[S["s"]] = np.random.uniform(self.model.xmin, self.model.xmax)
+                        row[S["du"]] = np.random.uniform(-0.1, 0.1)
+                    else:
+                        row[S["n"]] = np.random.randint(k)
+        if nnorm:
+            row[S["xi"]:S["xi"] + nnorm] = np.random.normal(size=(nnorm,))
+        s = Sampler(self.model, self, theta)
+        out = s.run(1, trace=False, inject={"tape": row[None, None, :]}, extras=True)
+        th = unpack_state(out["prop_k"][0, 0], out["prop_cpx"][0, 0], out["prop_cpv"][0, 0],
+                          out["prop_sig"][0, 0])
+        return th, float(out["logqratio"][0, 0])
+
     def _create_handle(self, d):
         h = C.c_void_p()
         p = np.array([self.P_cumprop_cpx, self.P_cumprop_cpv, self.P_cumprop_sig], dtype=np.float64)

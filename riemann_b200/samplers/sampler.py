@@ -227,7 +227,19 @@ class Sampler(object):
         if extras:
             bufs["prop_lp"] = torch.empty((T, K), dtype=torch.float64, device="cuda")
             bufs["acc"] = torch.empty((T, K), dtype=torch.uint8, device="cuda")
+            bufs["lqr"] = torch.empty((T, K), dtype=torch.float64, device="cuda")
             tr.d_prop_logpost, tr.d_accepted = bufs["prop_lp"].data_ptr(), bufs["acc"].data_ptr()
+            tr.d_logqratio = bufs["lqr"].data_ptr()
+            if self._is_cp:
+                bufs["pk"] = torch.empty((T, K), dtype=torch.int32, device="cuda")
+                bufs["pcpx"] = torch.empty((T, K, LANES), dtype=torch.float64, device="cuda")
+                bufs["pcpv"] = torch.empty((T, K, LANES), dtype=torch.float64, device="cuda")
+                bufs["psig"] = torch.empty((T, K), dtype=torch.float64, device="cuda")
+                tr.d_prop_k, tr.d_prop_cpx = bufs["pk"].data_ptr(), bufs["pcpx"].data_ptr()
+                tr.d_prop_cpv, tr.d_prop_sig = bufs["pcpv"].data_ptr(), bufs["psig"].data_ptr()
+            else:
+                bufs["pth"] = torch.empty((T, K, d), dtype=torch.float64, device="cuda")
+                tr.d_prop_theta = bufs["pth"].data_ptr()
         inj = None
         if inject is not None:
             inj = _lib.Inject()
@@ -260,7 +272,7 @@ class Sampler(object):
             th, lp = self._download_state()
             self._set_history([th], [lp])
             self._refresh_adapt()
-            return out if extras else None
+            return self._extras(out) if extras else None
         first_dev = Nburn if Nburn >= 1 else Nthin
         nrec = 0 if first_dev > T else (T - first_dev) // Nthin + 1
         per_rec = self.K * ((2 * LANES + 3) if self._is_cp else (self.d + 1)) * 8
@@ -291,15 +303,27 @@ class Sampler(object):
         self._final_state_cache = None
         self._refresh_adapt()
         if extras:
-            return {"prop_logpost": bufs["prop_lp"].cpu().numpy(),
-                    "accepted": bufs["acc"].cpu().numpy().astype(bool)}
+            return self._extras(bufs)
         return None
+
+    def _extras(self, bufs):
+        """Per-step proposal record: what Proposal.propose returned and what the sampler decided."""
+        out = {"prop_logpost": bufs["prop_lp"].cpu().numpy(),
+               "accepted": bufs["acc"].cpu().numpy().astype(bool),
+               "logqratio": bufs["lqr"].cpu().numpy()}
+        if self._is_cp:
+            out.update(prop_k=bufs["pk"].cpu().numpy(), prop_cpx=bufs["pcpx"].cpu().numpy(),
+                       prop_cpv=bufs["pcpv"].cpu().numpy(), prop_sig=bufs["psig"].cpu().numpy())
+        else:
+            out["prop_theta"] = bufs["pth"].cpu().numpy()
+        return out
 
     def run_injected(self, xi=None, u=None, tape=None, Nburn=0, Nthin=1):
         """
         Replay a given noise stream instead of Philox (parity mode):
         fixed-d: xi[T, K, d] (or [T, d] for K = 1) and u[T, K]; changepoint: tape[T, K, NSLOT].
-        Returns {'prop_logpost': [T,K], 'accepted': [T,K]}.
+        Returns the per-step proposal record: 'prop_theta' [T,K,d] (or prop_k/cpx/cpv/sig),
+        'logqratio', 'prop_logpost', 'accepted' [T,K].
         """
         if self._is_cp:
             tape = np.asarray(tape, dtype=np.float64)
@@ -360,6 +384,41 @@ class Sampler(object):
             p.scale, p.Nsamples, p.Naccepts, p.accept_rate = sc, ns, na, rate
         if hasattr(p, "eps0"):
             p.eps = p.scale * p.eps0                    # hamiltonian.py:102
+
+    def set_adapt(self, scale=None, nsamples=None, naccepts=None):
+        """Set the per-chain AdaptScale state (scalars broadcast over chains)."""
+        torch, K = self._torch, self.K
+        def dev(v, dt):
+            if v is None:
+                return None
+            return torch.as_tensor(np.broadcast_to(np.asarray(v), (K,)).copy(), device="cuda").to(dt)
+        sc, ns, na = dev(scale, torch.float64), dev(nsamples, torch.int64), dev(naccepts, torch.int64)
+        _lib.check(_lib.load().rmn_sampler_set_adapt(self._handle, _lib.ptr(sc), _lib.ptr(ns),
+                                                     _lib.ptr(na), _lib.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def get_checkpoint(self):
+        """Everything needed to resume bit-for-bit: states, Philox step counter, adapt state."""
+        th, lp = self._download_state()
+        ck = {"state": th, "step": int(_lib.load().rmn_sampler_get_step(self._handle)),
+              "seed": self.seed, "chain_offset": self.chain_offset}
+        if getattr(self.proposal, "_adaptive", False):
+            self._refresh_adapt()
+            p = self.proposal
+            ck["adapt"] = (np.atleast_1d(p.scale).copy(), np.atleast_1d(p.Nsamples).copy(),
+                           np.atleast_1d(p.Naccepts).copy())
+        return ck
+
+    def set_checkpoint(self, ck):
+        if self._is_cp:
+            k, cpx, cpv, sig = ck["state"]
+            self.set_state([unpack_state(k[i], cpx[i], cpv[i], sig[i]) for i in range(self.K)])
+        else:
+            self.set_state(ck["state"])
+        _lib.check(_lib.load().rmn_sampler_set_step(self._handle, int(ck["step"])))
+        if "adapt" in ck:
+            self.set_adapt(*ck["adapt"])
+            self._refresh_adapt()
 
     def reset_diagnostics(self):
         _lib.check(_lib.load().rmn_sampler_reset_diagnostics(self._handle, _lib.stream_ptr()))
