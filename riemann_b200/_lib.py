@@ -78,6 +78,7 @@ SIGNATURES = {
     "rmn_sampler_launch_count": (_L, [_P]),
     "rmn_philox_raw": (_I, [_L, _P, _P, _P, _P]),
     "rmn_rng_draws": (_I, [C.c_uint64, _L, _L, _L, _I, _P, _P, _P]),
+    "rmn_tf32x3_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,219 @@
+// riemann_b200 -- tcgen05 3xTF32 GEMM kernel (see tc_gemm.cuh) with two epilogues:
+//   EPI_PLAIN : C[m][n] (fp32) stored                        -- validation entry point
+//   EPI_MALA  : the dense-Gaussian MALA epilogue of dense.cu -- V' stored, rowsum(y'.v') and
+//               rowsum(p'^2) reduced per (row, 256-column block) in fp64, no atomics
+// This is the fp32-accurate tensor-core counterpart of gemm_abt_kernel (fp64 DMMA) for
+// SURVEY.md row D4 / BASELINE config 3.
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace tc {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                 uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { rmn_set_error("cuTensorMapEncodeTiled not available from the driver"); return RMN_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { rmn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RMN_ERR_CUDA; }
+    return RMN_OK;
+}
+
+struct MalaEpi {
+    const float* yph; const float* ypl;   // proposal (split), [K][dp]
+    const float* xi;                      // noise, [K][dp]
+    const float* vcur;                    // V of the current state, [K][dp]
+    float* vp;                            // V of the proposal (output), [K][dp]
+    const double* epsrow;                 // [K]
+    double* partq; double* partk;         // [nblk][K]
+    int mala;                             // 0: RW (no p' partials)
+};
+
+enum { EPI_PLAIN = 0, EPI_MALA = 1 };
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
+                   int ldc, MalaEpi ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.y * TM;
+    const int n0 = blockIdx.x * TN;
+    const int KB = Kdim / TK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.al);
+        tma_prefetch_desc(&maps.bh); tma_prefetch_desc(&maps.bl);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + s * STAGE_BYTES;
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            tma_load_2d(st, &maps.ah, &full[s], kb * TK, (int)m0);
+            tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, (int)m0);
+            tma_load_2d(st + 2 * A_BYTES, &maps.bh, &full[s], kb * TK, n0);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.bl, &full[s], kb * TK, n0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer (one thread) =====
+        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+            const uint64_t dah = umma_desc_kmajor_sw128(sa);
+            const uint64_t dal = umma_desc_kmajor_sw128(sa + A_BYTES);
+            const uint64_t dbh = umma_desc_kmajor_sw128(sa + 2 * A_BYTES);
+            const uint64_t dbl = umma_desc_kmajor_sw128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int k = 0; k < TK / UK; ++k) {
+                const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);       // +32 bytes per K step, 16-byte units
+                umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+                umma_tf32(tmem_base, dah + adv, dbl + adv, idesc, 1);
+                umma_tf32(tmem_base, dal + adv, dbh + adv, idesc, 1);
+            }
+            umma_commit(&empty[s]);                 // frees the stage when these MMAs retire
+        }
+        umma_commit(tmem_full);                     // accumulator complete
+    } else if (warp >= 4) {
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31, one row per thread =====
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int64_t m = m0 + q * 32 + lane;
+        const bool rok = m < M;
+        double pq = 0.0, pk = 0.0;
+        const double he = (EPI == EPI_MALA && rok) ? 0.5 * ep.epsrow[m] : 0.0;
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int n = n0 + c0;
+            if (!rok || n >= N) continue;
+            if (EPI == EPI_PLAIN) {
+                float4* dst = reinterpret_cast<float4*>(C + m * ldc + n);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+                const size_t off = (size_t)m * ldc + n;
+                float4* dst = reinterpret_cast<float4*>(ep.vp + off);
+                const float4* yh = reinterpret_cast<const float4*>(ep.yph + off);
+                const float4* yl = reinterpret_cast<const float4*>(ep.ypl + off);
+                const float4* xi = reinterpret_cast<const float4*>(ep.xi + off);
+                const float4* vc = reinterpret_cast<const float4*>(ep.vcur + off);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    const float4 a = yh[i], b = yl[i];
+                    const double y0 = (double)a.x + (double)b.x, y1 = (double)a.y + (double)b.y;
+                    const double y2 = (double)a.z + (double)b.z, y3 = (double)a.w + (double)b.w;
+                    pq += y0 * (double)v[4 * i] + y1 * (double)v[4 * i + 1] + y2 * (double)v[4 * i + 2] +
+                          y3 * (double)v[4 * i + 3];
+                    if (ep.mala) {
+                        const float4 x = xi[i], w = vc[i];
+                        const double p0 = ((double)x.x - he * (double)w.x) - he * (double)v[4 * i];
+                        const double p1 = ((double)x.y - he * (double)w.y) - he * (double)v[4 * i + 1];
+                        const double p2 = ((double)x.z - he * (double)w.z) - he * (double)v[4 * i + 2];
+                        const double p3 = ((double)x.w - he * (double)w.w) - he * (double)v[4 * i + 3];
+                        pk += p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3;
+                    }
+                }
+            }
+        }
+        if (EPI == EPI_MALA && rok) {
+            ep.partq[(size_t)blockIdx.x * M + m] = pq;
+            if (ep.mala) ep.partk[(size_t)blockIdx.x * M + m] = pk;
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
+                         cudaStream_t st) {
+    if (Kdim % TK != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
+    dim3 grid((N + TN - 1) / TN, (unsigned)((M + TM - 1) / TM));
+    static bool attr = false;
+    if (!attr) {
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    if (ep) tf32x3_gemm_kernel<EPI_MALA><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep);
+    else tf32x3_gemm_kernel<EPI_PLAIN><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{});
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}
+
+int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st);
+}
+int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
+                const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
+                int mala, cudaStream_t st) {
+    MalaEpi ep{yph, ypl, xi, vcur, vp, epsrow, partq, partk, mala};
+    return launch_common(maps, M, N, Kdim, nullptr, ld, &ep, st);
+}
+
+}  // namespace tc
+
+// Validation entry: C[M][N] (fp32, ld = N) ~= (Ah + Al)(Bh + Bl)^T; A* are [M][K], B* are [N][K], fp32, K % 32 == 0.
+extern "C" int rmn_tf32x3_gemm(int64_t M, int N, int Kdim, const float* d_Ah, const float* d_Al, const float* d_Bh,
+                               const float* d_Bl, float* d_C, void* stream) {
+    RMN_REQUIRE(M >= 1 && N >= 1 && Kdim >= 32 && Kdim % 32 == 0 && N % 4 == 0, "rmn_tf32x3_gemm: bad shape");
+    RMN_REQUIRE(d_Ah && d_Al && d_Bh && d_Bl && d_C, "rmn_tf32x3_gemm: null pointer");
+    tc::GemmMaps maps;
+    int rc;
+    if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN))) return rc;
+    return tc::launch_plain(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
+}
