@@ -180,7 +180,7 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------
-def build_workload(name, K, seed, chain_offset):
+def build_workload(name, K, seed, chain_offset, precision="f64"):
     """Returns (sampler, host_inputs dict for the e2e leg, description)."""
     from oracle import riemann_port as port        # synthetic-input recipes only (SURVEY 8d)
     from riemann_b200 import Sampler
@@ -205,8 +205,9 @@ def build_workload(name, K, seed, chain_offset):
         m = benchmarks.gauss_corr(1000)
         rng = np.random.Generator(np.random.Philox(port.SEED_BASE + 3))
         th0 = rng.standard_normal((K, 1000))
-        s = Sampler(m, MALA(0.08, m.grad_log_likelihood), th0, seed=seed, chain_offset=chain_offset)
-        return s, "dense Gaussian d=1000 (0.1 I + 0.9 11^T), MALA eps=0.08"
+        s = Sampler(m, MALA(0.08, m.grad_log_likelihood), th0, seed=seed, chain_offset=chain_offset,
+                    precision=precision)
+        return s, "dense Gaussian d=1000 (0.1 I + 0.9 11^T), MALA eps=0.08, precision " + precision
     if name in ("logistic_mala", "logistic_mmala"):
         from riemann_b200.models.logistic import LogisticRegression
         from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
@@ -245,7 +246,7 @@ def run_engine(args):
     T = args.iters or {"changepoint": 1000, "gauss2d_rw": 2000, "gauss1000_mala": 20,
                        "logistic_mala": 2, "logistic_mmala": 2}[wl]
     seed = 20261018
-    s, desc = build_workload(wl, Kg, seed, rank * Kg)
+    s, desc = build_workload(wl, Kg, seed, rank * Kg, args.precision)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -440,6 +441,8 @@ def main():
     ap.add_argument("--burn", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "tf32x3"],
+                    help="tf32x3: tcgen05 tensor-core mode of the dense Gaussian workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

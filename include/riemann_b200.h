@@ -183,6 +183,16 @@ size_t rmn_sampler_workspace_bytes(const rmn_model_t* m, const rmn_proposal_t* p
 int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
                        int64_t chain_offset, uint64_t seed, void* d_workspace,
                        size_t workspace_bytes);
+/* Precision modes.  RMN_PREC_F64 (default): fp64 state and arithmetic like the reference's numpy
+ * (DMMA / DFMA).  RMN_PREC_TF32X3: dense Gaussian model only -- fp32 chain state, the K x d by
+ * d x d product on tcgen05 tensor cores with a 3xTF32 split (fp32-accurate), everything that
+ * enters the accept test reduced in fp64; |log-posterior error| <~ 5e-3 at d = 1000. */
+#define RMN_PREC_F64 0
+#define RMN_PREC_TF32X3 1
+size_t rmn_sampler_workspace_bytes_ex(const rmn_model_t* m, const rmn_proposal_t* p, int64_t K, int precision);
+int rmn_sampler_create_ex(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
+                          int64_t chain_offset, uint64_t seed, void* d_workspace,
+                          size_t workspace_bytes, int precision);
 int rmn_sampler_destroy(rmn_sampler_t* s);
 
 /* = Sampler.__init__ (sampler.py:34-42): store the states and evaluate their

@@ -20,6 +20,7 @@ CP_NSLOT = 8 + CP_LANES
 CP_NDIAG = 8
 DIAG_HDR = 6
 SMALL_D_MAX = 8
+PRECISIONS = {"f64": 0, "tf32x3": 1}
 
 
 class Inject(C.Structure):
@@ -62,6 +63,8 @@ SIGNATURES = {
     "rmn_proposal_destroy": (_I, [_P]),
     "rmn_sampler_workspace_bytes": (C.c_size_t, [_P, _P, _L]),
     "rmn_sampler_create": (_I, [_PP, _P, _P, _L, _L, C.c_uint64, _P, C.c_size_t]),
+    "rmn_sampler_workspace_bytes_ex": (C.c_size_t, [_P, _P, _L, _I]),
+    "rmn_sampler_create_ex": (_I, [_PP, _P, _P, _L, _L, C.c_uint64, _P, C.c_size_t, _I]),
     "rmn_sampler_destroy": (_I, [_P]),
     "rmn_sampler_set_state": (_I, [_P, _P, _P]),
     "rmn_sampler_get_state": (_I, [_P, _P, _P, _P]),

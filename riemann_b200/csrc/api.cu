@@ -265,6 +265,12 @@ static SamplerImpl* make_impl(rmn_sampler* s, int* rc) {
         *rc = RMN_ERR_PARAM;
         return nullptr;
     }
+    if (s->precision == RMN_PREC_TF32X3) return make_dense_tf32_sampler(s);
+    if (s->precision != RMN_PREC_F64) {
+        rmn_set_error("unknown precision mode %d", s->precision);
+        *rc = RMN_ERR_PARAM;
+        return nullptr;
+    }
     if (m->kind == RMN_MODEL_GAUSS) {
         if (p->kind == RMN_PROP_MMALA) {
             rmn_set_error("mMALA needs a model with a Fisher metric (logistic)");
@@ -279,11 +285,17 @@ static SamplerImpl* make_impl(rmn_sampler* s, int* rc) {
 }
 
 extern "C" size_t rmn_sampler_workspace_bytes(const rmn_model_t* m, const rmn_proposal_t* p, int64_t K) {
+    return rmn_sampler_workspace_bytes_ex(m, p, K, RMN_PREC_F64);
+}
+
+extern "C" size_t rmn_sampler_workspace_bytes_ex(const rmn_model_t* m, const rmn_proposal_t* p, int64_t K,
+                                                 int precision) {
     if (!m || !p || K < 1) return 0;
     rmn_sampler tmp;
     tmp.model = const_cast<rmn_model*>(m);
     tmp.prop = const_cast<rmn_proposal*>(p);
     tmp.K = K;
+    tmp.precision = precision;
     int rc;
     SamplerImpl* impl = make_impl(&tmp, &rc);
     if (!impl) return 0;
@@ -295,11 +307,18 @@ extern "C" size_t rmn_sampler_workspace_bytes(const rmn_model_t* m, const rmn_pr
 extern "C" int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
                                   int64_t chain_offset, uint64_t seed, void* d_workspace,
                                   size_t workspace_bytes) {
+    return rmn_sampler_create_ex(out, m, p, K, chain_offset, seed, d_workspace, workspace_bytes, RMN_PREC_F64);
+}
+
+extern "C" int rmn_sampler_create_ex(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
+                                     int64_t chain_offset, uint64_t seed, void* d_workspace,
+                                     size_t workspace_bytes, int precision) {
     RMN_REQUIRE(out && m && p && d_workspace, "rmn_sampler_create: null argument");
     RMN_REQUIRE(K >= 1, "rmn_sampler_create: need K >= 1 chains");
     RMN_REQUIRE(chain_offset >= 0, "rmn_sampler_create: chain_offset must be >= 0");
     rmn_sampler* s = new rmn_sampler();
     s->model = m; s->prop = p; s->K = K; s->chain_offset = chain_offset; s->seed = seed;
+    s->precision = precision;
     int rc;
     s->impl = make_impl(s, &rc);
     if (!s->impl) { delete s; return rc; }

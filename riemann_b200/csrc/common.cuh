@@ -221,6 +221,7 @@ struct rmn_sampler {
     rmn_proposal* prop = nullptr;
     int64_t K = 0, chain_offset = 0;
     uint64_t seed = 0;
+    int precision = 0;
     SamplerImpl* impl = nullptr;
 };
 
@@ -229,6 +230,7 @@ SamplerImpl* make_small_gauss_sampler(rmn_sampler* s);
 SamplerImpl* make_changepoint_sampler(rmn_sampler* s);
 SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s);
 SamplerImpl* make_logistic_sampler(rmn_sampler* s);
+SamplerImpl* make_dense_tf32_sampler(rmn_sampler* s);
 
 // pointwise evaluators implemented per family
 int gauss_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta, double* d_out,

@@ -1,0 +1,377 @@
+// riemann_b200 -- dense Gaussian target, fp32-accurate tensor-core mode ("tf32x3").
+//
+// Same MH step as dense.cu (MALA = VanillaHMC(eps, 1, grad), hamiltonian.py:76-91; random walk,
+// randomwalk.py:21-26; MultiGaussianDist log-density and gradient, gaussian.py:49-58; accept and
+// adapt, sampler.py:72-90 / adaptive.py:26-35) but the product V' = Y' P runs on the 5th-gen
+// tensor cores: tcgen05.mma.kind::tf32 fed by TMA, accumulators in TMEM, three TF32 MMAs per
+// operand pair (tc_gemm.cu).  Chain state is fp32; everything that enters the accept test
+// (quadratic form, |p'|^2, log-posterior) is reduced and kept in fp64.
+//
+// Accuracy budget (stated, and checked in tests/test_gpu_dense_tf32.py): the log-posterior is a
+// deterministic function of the fp32 state that differs from the fp64 value by <~ 5e-3 absolute
+// at d = 1000 (fp32 rounding of P and of the accumulation; condition number 9e3), so the chain
+// targets exp(logpost + O(1e-3)); decisions agree with the fp64 reference except when
+// log u is within that distance of the threshold.
+//
+// TMA boxes cannot follow a per-row "current slot" bit, so this mode keeps ONE proposal buffer
+// and fuses the accept-copy into the finish/propose pass (which has to touch both rows anyway).
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace tc {
+int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
+                const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
+                int mala, cudaStream_t st);
+}
+
+namespace {
+
+constexpr int ND_MAX = 8;
+
+struct TState {
+    int64_t K; int d, dp, nblk;
+    float* Y; float* V;            // current state (centred) and V = Y P           [K][dp]
+    float* Yph; float* Ypl;        // proposal, split into TF32-exact hi + remainder [K][dp]
+    float* Vp;                     // V of the proposal (GEMM output)                [K][dp]
+    float* Xi;                     // noise of the pending proposal                  [K][dp]
+    double* partq; double* partk;  // [nblk][K]
+    double* lp; double* k0; double* epsrow;
+    double* scale; long long* nsamp; long long* nacc; long long* dacc;
+    double* S1; double* S2;
+    const double* mu;              // [dp]
+    const float* Ldiag;            // [dp]
+};
+
+struct TStep {
+    int prop_kind, adapt, finish, propose, diag;
+    double target, eps0, c1, c2;
+    uint64_t seed; int64_t chain_offset, step_fin, step_prop;
+    const double* inj_xi; const double* inj_u;
+    int64_t trace_slot;
+    double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc; double* tr_lqr; double* tr_prop_theta;
+};
+
+// one warp per chain row
+__global__ void __launch_bounds__(256)
+finish_propose_f32_kernel(TState st, TStep sp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int dp = st.dp, d = st.d;
+    const int64_t K = st.K;
+    double lp = st.lp[r];
+    bool acc = false;
+    const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
+
+    if (sp.finish) {
+        double q = 0.0, k1 = 0.0;
+        for (int b = lane; b < st.nblk; b += 32) {
+            q += st.partq[(int64_t)b * K + r];
+            if (sp.prop_kind == RMN_PROP_HMC) k1 += st.partk[(int64_t)b * K + r];
+        }
+        q = group_sum<32>(q);
+        k1 = group_sum<32>(k1);
+        const double lpn = combine_logpost(0.0, -0.5 * ((q + sp.c1) + sp.c2));           // gaussian.py:52
+        const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r]) : 0.0; // hamiltonian.py:89
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        acc = mh_accept(lpn, lp, lqr, u);
+        if (acc) lp = lpn;
+        if (lane == 0) {
+            if (acc) st.lp[r] = lp;
+            st.dacc[r] += acc ? 1 : 0;
+            if (sp.adapt) {
+                AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
+                ad.update(acc, sp.target);
+                st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts;
+            }
+            if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
+            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
+            if (sp.tr_lqr) sp.tr_lqr[r] = lqr;
+            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+        }
+    }
+    __syncwarp();
+
+    const size_t ro = (size_t)r * dp;
+    const double scale = sp.adapt ? st.scale[r] : 1.0;
+    const double eps = (sp.prop_kind == RMN_PROP_HMC) ? scale * sp.eps0 : scale;
+    double k0 = 0.0, rowsum = 0.0;
+    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+
+    for (int j4 = lane * 4; j4 < dp; j4 += 128) {
+        // the row's (new) current state: the accepted proposal or the old state
+        float4 yc, vc;
+        if (acc || sp.tr_prop_theta) {
+            const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro + j4);
+            const float4 b = *reinterpret_cast<const float4*>(st.Ypl + ro + j4);
+            const float4 yp = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);   // exact: hi + lo
+            if (sp.tr_prop_theta && sp.finish) {
+                const float pv[4] = {yp.x, yp.y, yp.z, yp.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (j4 + q < d) sp.tr_prop_theta[r * d + j4 + q] = (double)pv[q] + st.mu[j4 + q];
+            }
+            if (acc) {
+                yc = yp;
+                vc = *reinterpret_cast<const float4*>(st.Vp + ro + j4);
+                *reinterpret_cast<float4*>(st.Y + ro + j4) = yc;       // accept = copy, fused into this pass
+                *reinterpret_cast<float4*>(st.V + ro + j4) = vc;
+            }
+        }
+        if (!acc) {
+            yc = *reinterpret_cast<const float4*>(st.Y + ro + j4);
+            vc = *reinterpret_cast<const float4*>(st.V + ro + j4);
+        }
+        const float yv[4] = {yc.x, yc.y, yc.z, yc.w};
+        const float vv[4] = {vc.x, vc.y, vc.z, vc.w};
+        rowsum += ((double)yv[0] + (double)yv[1]) + ((double)yv[2] + (double)yv[3]);
+        if (want_trace) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j4 + q < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + q] = (double)yv[q] + st.mu[j4 + q];
+        }
+        if (!sp.propose) continue;
+        double xi[4];
+        if (sp.inj_xi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xi[q] = (j4 + q < d) ? sp.inj_xi[r * d + j4 + q] : 0.0;
+        } else {
+            normal4(rk.block((uint64_t)sp.step_prop, (uint32_t)(j4 >> 2)), xi);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j4 + q >= d) xi[q] = 0.0;
+        }
+        float oh[4], ol[4], xf[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            xf[q] = (float)xi[q];                                        // the noise as the kernels see it
+            double out;
+            if (sp.prop_kind == RMN_PROP_HMC) {
+                const double ph = (double)xf[q] + 0.5 * eps * (-(double)vv[q]);      // hamiltonian.py:27
+                out = (double)yv[q] + eps * ph;                                      // :30
+            } else {
+                out = (double)yv[q] + scale * ((double)st.Ldiag[j4 + q] * (double)xf[q]);   // randomwalk.py:26
+            }
+            k0 += (double)xf[q] * (double)xf[q];
+            tc::split_tf32((float)out, oh[q], ol[q]);
+        }
+        *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+        *reinterpret_cast<float4*>(st.Xi + ro + j4) = make_float4(xf[0], xf[1], xf[2], xf[3]);
+    }
+    if (sp.propose) {
+        k0 = group_sum<32>(k0);
+        if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
+    }
+    if (sp.diag) {
+        rowsum = group_sum<32>(rowsum);
+        const int nd = min(d, ND_MAX - 1) + 1;
+        if (lane < nd) {
+            const double f = (lane == nd - 1) ? rowsum / (double)d : (double)st.Y[ro + lane];
+            st.S1[(int64_t)lane * K + r] += f;
+            st.S2[(int64_t)lane * K + r] += f * f;
+        }
+    }
+}
+
+__global__ void tset_kernel(TState st, const double* __restrict__ theta) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.dp) return;
+    const int64_t r = i / st.dp;
+    const int j = (int)(i % st.dp);
+    const float y = (j < st.d) ? (float)(theta[r * st.d + j] - st.mu[j]) : 0.0f;
+    float hi, lo;
+    tc::split_tf32(y, hi, lo);
+    st.Y[i] = y; st.Yph[i] = hi; st.Ypl[i] = lo; st.Xi[i] = 0.0f; st.V[i] = 0.0f;
+    if (j == 0) { st.k0[r] = 0.0; st.epsrow[r] = 0.0; }
+}
+__global__ void __launch_bounds__(256) tadopt_kernel(TState st, double c1, double c2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    double q = 0.0;
+    for (int b = lane; b < st.nblk; b += 32) q += st.partq[(int64_t)b * st.K + r];
+    q = group_sum<32>(q);
+    for (int j = lane; j < st.dp; j += 32) st.V[(size_t)r * st.dp + j] = st.Vp[(size_t)r * st.dp + j];
+    if (lane == 0) st.lp[r] = combine_logpost(0.0, -0.5 * ((q + c1) + c2));
+}
+__global__ void tget_kernel(TState st, double* theta, double* lp) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.d) return;
+    const int64_t r = i / st.d;
+    const int j = (int)(i % st.d);
+    if (theta) theta[i] = (double)st.Y[(size_t)r * st.dp + j] + st.mu[j];
+    if (lp && j == 0) lp[r] = st.lp[r];
+}
+__global__ void tget_adapt_kernel(TState st, double* scale, int64_t* ns, int64_t* na) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= st.K) return;
+    if (scale) scale[c] = st.scale[c];
+    if (ns) ns[c] = st.nsamp[c];
+    if (na) na[c] = st.nacc[c];
+}
+
+struct DenseTF32Sampler : SamplerImpl {
+    rmn_sampler* s;
+    TState st{};
+    tc::GemmMaps maps;
+    float* d_Ph = nullptr; float* d_Pl = nullptr; float* d_Ldiag = nullptr; double* d_mupad = nullptr;
+    explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
+        st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = (st.dp + tc::TN - 1) / tc::TN;
+    }
+    ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
+    size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
+    size_t workspace_bytes() const override {
+        const size_t K = (size_t)st.K;
+        return 6 * rowb() + 2 * align256((size_t)st.nblk * K * 8) + 7 * align256(K * 8) +
+               2 * align256(ND_MAX * K * 8) + 256;
+    }
+    int bind(void* ws) override {
+        const size_t K = (size_t)st.K;
+        char* p = (char*)ws;
+        st.Y = (float*)p; p += rowb();   st.V = (float*)p; p += rowb();
+        st.Yph = (float*)p; p += rowb(); st.Ypl = (float*)p; p += rowb();
+        st.Vp = (float*)p; p += rowb();  st.Xi = (float*)p; p += rowb();
+        st.partq = (double*)p; p += align256((size_t)st.nblk * K * 8);
+        st.partk = (double*)p; p += align256((size_t)st.nblk * K * 8);
+        st.lp = (double*)p; p += align256(K * 8);
+        st.k0 = (double*)p; p += align256(K * 8);
+        st.epsrow = (double*)p; p += align256(K * 8);
+        st.scale = (double*)p; p += align256(K * 8);
+        st.nsamp = (long long*)p; p += align256(K * 8);
+        st.nacc = (long long*)p; p += align256(K * 8);
+        st.dacc = (long long*)p; p += align256(K * 8);
+        st.S1 = (double*)p; p += align256(ND_MAX * K * 8);
+        st.S2 = (double*)p; p += align256(ND_MAX * K * 8);
+        RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        const int d = st.d, dp = st.dp;
+        std::vector<double> tmp((size_t)d * d), hm(dp, 0.0);
+        RMN_CUDA(cudaMemcpy(tmp.data(), s->model->d_prec, (size_t)d * d * 8, cudaMemcpyDeviceToHost));
+        std::vector<float> ph((size_t)dp * dp, 0.0f), pl((size_t)dp * dp, 0.0f), ld(dp, 0.0f);
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                float hi, lo;
+                tc::split_tf32((float)tmp[(size_t)i * d + j], hi, lo);
+                ph[(size_t)i * dp + j] = hi; pl[(size_t)i * dp + j] = lo;
+            }
+        for (int i = 0; i < d; ++i) hm[i] = s->model->h_mu[i];
+        const rmn_proposal* pr = s->prop;
+        if (pr->kind == RMN_PROP_RW)
+            for (int i = 0; i < d; ++i) ld[i] = (float)pr->h_L[(size_t)i * d + i];
+        RMN_CUDA(cudaMalloc(&d_Ph, ph.size() * 4)); RMN_CUDA(cudaMalloc(&d_Pl, pl.size() * 4));
+        RMN_CUDA(cudaMalloc(&d_Ldiag, (size_t)dp * 4)); RMN_CUDA(cudaMalloc(&d_mupad, (size_t)dp * 8));
+        RMN_CUDA(cudaMemcpy(d_Ph, ph.data(), ph.size() * 4, cudaMemcpyHostToDevice));
+        RMN_CUDA(cudaMemcpy(d_Pl, pl.data(), pl.size() * 4, cudaMemcpyHostToDevice));
+        RMN_CUDA(cudaMemcpy(d_Ldiag, ld.data(), (size_t)dp * 4, cudaMemcpyHostToDevice));
+        RMN_CUDA(cudaMemcpy(d_mupad, hm.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
+        st.mu = d_mupad; st.Ldiag = d_Ldiag;
+        int rc;
+        if ((rc = tc::make_tmap_2d(&maps.ah, st.Yph, st.K, dp, dp, tc::TM))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.al, st.Ypl, st.K, dp, dp, tc::TM))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.bh, d_Ph, dp, dp, dp, tc::TN))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.bl, d_Pl, dp, dp, dp, tc::TN))) return rc;
+        if ((rc = rmn_fill_f64(st.scale, st.K, 1.0, 0))) return rc;
+        RMN_CUDA(cudaDeviceSynchronize());
+        return RMN_OK;
+    }
+    unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
+    double c1() const { return st.d * log(2.0 * M_PI); }
+    int gemm(int mala, cudaStream_t stream) {
+        launches++;
+        return tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
+                               st.partq, st.partk, mala, stream);
+    }
+    int set_state(const double* d_theta, cudaStream_t stream) override {
+        const int64_t n = st.K * st.dp;
+        tset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta);
+        RMN_KERNEL_CHECK(); launches++;
+        if (int rc = gemm(0, stream)) return rc;
+        tadopt_kernel<<<row_grid(), 256, 0, stream>>>(st, c1(), s->model->logdetC);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int get_state(double* d_theta, double* d_lp, cudaStream_t stream) override {
+        const int64_t n = st.K * st.d;
+        tget_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta, d_lp);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
+        const rmn_proposal* pr = s->prop;
+        if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        rmn_trace_t t0{};
+        if (tr) t0 = *tr;
+        if (t0.thin <= 0) t0.thin = 1;
+        TStep sp{};
+        sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
+        sp.c1 = c1(); sp.c2 = s->model->logdetC; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
+        const int64_t K = st.K;
+        const int d = st.d;
+        for (int64_t t = 0; t <= T; ++t) {
+            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
+            sp.step_fin = step0 + t - 1; sp.step_prop = step0 + t;
+            sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;
+            sp.inj_xi = (inj && t < T) ? inj->d_xi + t * K * d : nullptr;
+            sp.trace_slot = -1;
+            sp.tr_theta = t0.d_theta; sp.tr_logpost = t0.d_logpost;
+            sp.tr_prop_lp = (t0.d_prop_logpost && t > 0) ? t0.d_prop_logpost + (t - 1) * K : nullptr;
+            sp.tr_acc = (t0.d_accepted && t > 0) ? t0.d_accepted + (t - 1) * K : nullptr;
+            sp.tr_lqr = (t0.d_logqratio && t > 0) ? t0.d_logqratio + (t - 1) * K : nullptr;
+            sp.tr_prop_theta = (t0.d_prop_theta && t > 0) ? t0.d_prop_theta + (t - 1) * K * d : nullptr;
+            if (t > 0 && (t0.d_theta || t0.d_logpost)) {
+                const int64_t i = t;
+                if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
+            }
+            finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
+            RMN_KERNEL_CHECK(); launches++;
+            if (t == T) break;
+            if (int rc = gemm(pr->kind == RMN_PROP_HMC ? 1 : 0, stream)) return rc;
+        }
+        step0 += T; diag_steps += T;
+        return RMN_OK;
+    }
+    int get_adapt(double* sc, int64_t* ns, int64_t* na, cudaStream_t stream) override {
+        tget_adapt_kernel<<<(unsigned)((st.K + 127) / 128), 128, 0, stream>>>(st, sc, ns, na);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
+    }
+    int set_adapt(const double* sc, const int64_t* ns, const int64_t* na, cudaStream_t stream) override {
+        launches++;
+        return rmn_copy_adapt(st.K, sc, ns, na, st.scale, st.nsamp, st.nacc, stream);
+    }
+    int diag_dim() const override { return (st.d < ND_MAX - 1 ? st.d : ND_MAX - 1) + 1; }
+    int reset_diag(cudaStream_t stream) override {
+        RMN_CUDA(cudaMemsetAsync(st.S1, 0, (size_t)ND_MAX * st.K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.S2, 0, (size_t)ND_MAX * st.K * 8, stream));
+        RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)st.K * 8, stream));
+        diag_steps = 0;
+        return RMN_OK;
+    }
+    int reduce_diag(double* d_block, cudaStream_t stream) override {
+        launches++;
+        return rmn_reduce_diag_block(st.K, diag_dim(), diag_steps, diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);
+    }
+};
+
+}  // namespace
+
+SamplerImpl* make_dense_tf32_sampler(rmn_sampler* s) {
+    const rmn_proposal* p = s->prop;
+    if (s->model->kind != RMN_MODEL_GAUSS) {
+        rmn_set_error("tf32x3 precision is implemented for the dense Gaussian model");
+        return nullptr;
+    }
+    if (p->kind == RMN_PROP_HMC && p->nsteps == 1 && !p->has_mass) return new DenseTF32Sampler(s);
+    if (p->kind == RMN_PROP_RW) {
+        const int d = s->model->d;
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < i; ++j)
+                if (p->h_L[(size_t)i * d + j] != 0.0) {
+                    rmn_set_error("tf32x3 random walk supports diagonal proposal covariances");
+                    return nullptr;
+                }
+        return new DenseTF32Sampler(s);
+    }
+    rmn_set_error("tf32x3 precision supports RW (diagonal covariance) and MALA (VanillaHMC Nsteps=1, no mass matrix)");
+    return nullptr;
+}

