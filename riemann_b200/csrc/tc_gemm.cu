@@ -1,7 +1,10 @@
 // riemann_b200 -- tcgen05 3xTF32 GEMM kernel (see tc_gemm.cuh) with two epilogues:
 //   EPI_PLAIN : C[m][n] (fp32) stored                        -- validation entry point
-//   EPI_MALA  : the dense-Gaussian MALA epilogue of dense.cu -- V' stored, rowsum(y'.v') and
-//               rowsum(p'^2) reduced per (row, 256-column block) in fp64, no atomics
+//   EPI_MALA  : dense-Gaussian MH epilogue in DELTA form.  A = delta = theta' - theta (split), so the
+//               accumulator holds P delta; stored, and rowsum(delta.(2 v + P delta)) = quad' - quad
+//               and rowsum(p'^2) are reduced per (row, 256-column block) in fp64, no atomics.
+//               (Forming P y' directly would cancel 30 - 29.97 in fp32 for the 0.1 I + 0.9 11^T
+//               target; the increment has no common mode, so the MH ratio keeps ~1e-5 accuracy.)
 // This is the fp32-accurate tensor-core counterpart of gemm_abt_kernel (fp64 DMMA) for
 // SURVEY.md row D4 / BASELINE config 3.
 #include "common.cuh"
@@ -41,10 +44,10 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t co
 }
 
 struct MalaEpi {
-    const float* yph; const float* ypl;   // proposal (split), [K][dp]
+    const float* yph; const float* ypl;   // increment delta (split), [K][dp]
     const float* xi;                      // noise, [K][dp]
-    const float* vcur;                    // V of the current state, [K][dp]
-    float* vp;                            // V of the proposal (output), [K][dp]
+    const float* vcur;                    // V = P y of the current state, [K][dp]
+    float* vp;                            // P delta (output), [K][dp]
     const double* epsrow;                 // [K]
     double* partq; double* partk;         // [nblk][K]
     int mala;                             // 0: RW (no p' partials)
@@ -147,18 +150,21 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    const float4 a = yh[i], b = yl[i];
-                    const double y0 = (double)a.x + (double)b.x, y1 = (double)a.y + (double)b.y;
-                    const double y2 = (double)a.z + (double)b.z, y3 = (double)a.w + (double)b.w;
-                    pq += y0 * (double)v[4 * i] + y1 * (double)v[4 * i + 1] + y2 * (double)v[4 * i + 2] +
-                          y3 * (double)v[4 * i + 3];
+                    const float4 a = yh[i], b = yl[i], w = vc[i];
+                    const double dl[4] = {(double)a.x + (double)b.x, (double)a.y + (double)b.y,
+                                          (double)a.z + (double)b.z, (double)a.w + (double)b.w};
+                    const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pq += dl[e] * (2.0 * wv[e] + (double)v[4 * i + e]);   // quad' - quad
                     if (ep.mala) {
-                        const float4 x = xi[i], w = vc[i];
-                        const double p0 = ((double)x.x - he * (double)w.x) - he * (double)v[4 * i];
-                        const double p1 = ((double)x.y - he * (double)w.y) - he * (double)v[4 * i + 1];
-                        const double p2 = ((double)x.z - he * (double)w.z) - he * (double)v[4 * i + 2];
-                        const double p3 = ((double)x.w - he * (double)w.w) - he * (double)v[4 * i + 3];
-                        pk += p0 * p0 + p1 * p1 + p2 * p2 + p3 * p3;
+                        // p' = xi + eps/2 g + eps/2 g',  g = -V, g' = -(V + P delta)   (hamiltonian.py:27,40)
+                        const float4 x = xi[i];
+                        const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + (double)v[4 * i + e]);
+                            pk += p1 * p1;
+                        }
                     }
                 }
             }
