@@ -313,6 +313,14 @@ def run_engine(args):
                         "%.0f algorithmic op/chain-step x rate; peak = 148 SM x 64 fp64 FMA lanes x 2 x "
                         "clocks.max.sm (computed, MEASURED_PEAKS.json has no ALU figure); see "
                         "profiles/ for issue-slot utilisation" % ALGO_FLOP[wl]}
+    elif args.precision == "tf32x3":
+        peak = 0.5 * peaks["bf16_tflops_sustained" if ms > 2000 else "bf16_tflops"]
+        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach_tflops / peak, "traffic": None,
+                "note": "tcgen05 kind::tf32, 3 MMAs per product (fp32-accurate): achieved counts the ALGORITHMIC "
+                        "2 d^2 flop per chain-step once, so 1/3 is the ceiling of this scheme; peak = half the %s "
+                        "bf16 figure of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate; not measured "
+                        "separately)" % peak_src}
     else:
         peak = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
         roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
@@ -324,7 +332,8 @@ def run_engine(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_launch, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == "f64" else "tf32x3/f32 state, f64 accept test",
+        "data": "synthetic",
         "config": {"workload": "%s: %s; %d chains/GPU x %d MH iterations per step; Philox4x32-10 RNG; "
                                "L2 flushed (256 MiB write) between steps, per-step CUDA events summed"
                                % (wl, desc, Kg, T),
