@@ -1,0 +1,62 @@
+// riemann_b200 -- definitions shared by the two changepoint kernels (changepoint.cu, changepoint_tpc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cp {
+
+constexpr int LANES = RMN_CP_LANES;
+constexpr int NQ = 6;   // prediction query points tracked by the diagnostics
+#define RMN_CP_DIAG_EVERY 4   // diagnostics functionals are accumulated every 4th MH step
+
+struct CPParams {
+    int M, P2, alpha_is_one, pad;
+    double xmin, xmax, alpha, beta, cv, logL, ycenter, Mlog2pi, sqrtM;
+    double tab1[LANES + 1];     // k log(lam) - gammaln(k) - lam        changepoint.py:134
+    double tab2[LANES + 1];     // gammaln(2k+1)                        changepoint.py:143
+    double sx[LANES + 1];       // sqrt(0.01 (xmax-xmin)/(k+1))         test_changepoint.py:36
+    double sv, ss;              // sqrt(0.01 hscale^2/M), sqrt(0.01 hscale)   :37-38
+    double p1, p2, p3;          // sequential selection thresholds      :28-30
+    uint32_t t1, t2, t3, tpad;  // the same thresholds on the raw 32-bit Philox words
+    double xq[NQ];
+};
+
+struct CPState {
+    int32_t* k;          // [K]
+    double* cpx;         // [K][LANES]
+    double* cpv;         // [K][LANES]
+    double* sig;         // [K]
+    double* lp;          // [K]
+    long long* dacc;     // [K]
+    long long* dovf;     // [K]
+    double* S1;          // [NDIAG][K]
+    double* S2;          // [NDIAG][K]
+};
+
+__device__ __forceinline__ unsigned group_ballot(bool pred) {
+    const unsigned full = __ballot_sync(0xffffffffu, pred);
+    return (full >> (threadIdx.x & 16)) & 0xffffu;
+}
+
+// #{i : x_i <= c}  (upper bound), branch-free, always in [0, M]
+__device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int M, int P2, double c) {
+    int pos = 0;
+    for (int step = P2; step > 0; step >>= 1) {
+        const int np = pos + step;
+        if (np <= M && xs[np - 1] <= c) pos = np;
+    }
+    return pos;
+}
+
+// uniform on (0,1) from 32 random bits with 2 fp64 instructions: [1,2) mantissa trick + 2^-33
+__device__ __forceinline__ double u01_fast(uint32_t x) {
+    return __hiloint2double(0x3ff00000 | (x >> 12), x << 20) - (1.0 - 1.1641532182693481e-10);
+}
+
+
+// thread-per-chain kernel (changepoint_tpc.cu)
+size_t tpc_smem_bytes(int M);
+void tpc_launch(bool inj, const CPParams& P, const double* gdata, const CPState& st, int64_t K, int64_t T,
+                int64_t step0, uint64_t seed, int64_t chain_offset, const double* tape, const rmn_trace_t& tr,
+                cudaStream_t stream);
+
+}  // namespace cp
