@@ -22,9 +22,6 @@
 // the three k-terms of the prior; constraints enforced only through nan/inf -> -inf;
 // a fresh uniform per block-selection elif; trans-dimensional moves use log|J| alone
 // as logqratio.
-#include <stdlib.h>
-#include <string.h>
-
 #include "changepoint.cuh"
 
 namespace {
@@ -439,17 +436,8 @@ struct ChangepointSampler : SamplerImpl {
         launches++;
         return RMN_OK;
     }
-    bool use_tpc() const {
-        const char* e = getenv("RMN_CP_KERNEL");          // "lanes" | "tpc"; default: tpc when the data fit
-        if (e && !strcmp(e, "lanes")) return false;
-        return tpc_smem_bytes(P.M) <= 160 * 1024;
-    }
     template <bool INJ>
     void launch(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
-        if (use_tpc()) {
-            tpc_launch(INJ, P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, stream);
-            return;
-        }
         if (use_smem)
             changepoint_kernel<INJ, true, true><<<grid(), 128, smem_bytes, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);

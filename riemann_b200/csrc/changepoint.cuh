@@ -1,4 +1,4 @@
-// riemann_b200 -- definitions shared by the two changepoint kernels (changepoint.cu, changepoint_tpc.cu).
+// riemann_b200 -- definitions of the changepoint kernels (changepoint.cu; also used by experiments/changepoint_tpc.cu).
 #pragma once
 #include "common.cuh"
 
@@ -52,11 +52,5 @@ __device__ __forceinline__ double u01_fast(uint32_t x) {
     return __hiloint2double(0x3ff00000 | (x >> 12), x << 20) - (1.0 - 1.1641532182693481e-10);
 }
 
-
-// thread-per-chain kernel (changepoint_tpc.cu)
-size_t tpc_smem_bytes(int M);
-void tpc_launch(bool inj, const CPParams& P, const double* gdata, const CPState& st, int64_t K, int64_t T,
-                int64_t step0, uint64_t seed, int64_t chain_offset, const double* tape, const rmn_trace_t& tr,
-                cudaStream_t stream);
 
 }  // namespace cp
