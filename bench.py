@@ -43,6 +43,21 @@ ALGO_FLOP = {"changepoint": 650.0, "gauss2d_rw": 40.0, "gauss1000_mala": 2.0e6,
              "logistic_mala": 4.0e8, "logistic_mmala": 4.4e8}
 
 
+# From the committed ncu captures (profiles/r1_*.md; `ncu --set full`, one launch of the dominant
+# kernel on this code): DRAM bytes per launch and the pipe/issue utilisation.  Static evidence,
+# NOT re-measured by this script -- the live numbers of a run are `value`, `ms_per_step`, `roofline.achieved`.
+PROFILED = {
+    ("changepoint", "f64"): {"kernel": "changepoint_kernel", "traffic": 27.56e6 + 0.31e6, "issue_slot_util": 0.832,
+                             "fp64_pipe_active": 0.279, "warp_inst_per_chain_step": 347, "source": "profiles/r1_changepoint.md"},
+    ("gauss1000_mala", "f64"): {"kernel": "gemm_abt_kernel<1>", "traffic": 455.6e6 + 125.1e6, "tensor_pipe_active": 0.770,
+                                "source": "profiles/r1_gauss1000.md"},
+    ("gauss1000_mala", "tf32x3"): {"kernel": "tf32x3_gemm_kernel<1>", "traffic": 320.0e6 + 57.5e6, "tensor_pipe_active": 0.310,
+                                   "source": "profiles/r1_gauss1000_tf32x3_gemm.md"},
+    ("logistic_mala", "f64"): {"kernel": "lg_eval_kernel", "traffic": 811.2e6 + 4.7e6, "tensor_pipe_active": 0.636,
+                               "source": "profiles/r1_logistic.md"},
+}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -328,6 +343,10 @@ def run_engine(args):
                 "note": "fp64 path (DMMA/DFMA); peak = 148 SM x 64 fp64 FMA lanes x 2 x clocks.max.sm "
                         "(computed; bf16 %s peak %.0f TF/s shown for context only)"
                         % (peak_src, peaks["bf16_tflops"])}
+    prof = PROFILED.get((wl, args.precision))
+    if prof:
+        roof["traffic"] = prof["traffic"]
+        roof["profiled"] = prof
     cpu = None if args.no_cpu else cpu_baseline(wl, args.cpu_seconds)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
