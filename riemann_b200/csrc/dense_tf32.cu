@@ -244,7 +244,7 @@ struct DenseTF32Sampler : SamplerImpl {
     int64_t refresh = 512;        // exact fp64 recomputation of V / log-posterior every this many steps
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
-        st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = (st.dp + tc::TN - 1) / tc::TN;
+        st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = 2 * ((st.dp + tc::TN - 1) / tc::TN);   // one partial per 128-column half tile
     }
     ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }

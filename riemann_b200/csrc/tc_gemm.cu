@@ -55,6 +55,12 @@ struct MalaEpi {
 
 enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 
+// Persistent kernel: gridDim.x CTAs (one per SM) walk the tile list  tile = blockIdx.x + i * gridDim.x,
+// tile -> (m_tile, n_tile) with n fastest, so concurrently running CTAs share the same rows of A in L2.
+// Three independent pipelines (Blackwell canonical form):
+//   TMA warp   --full/empty[STAGES]-->   MMA thread   --tmem_full/tmem_empty[ACC_STAGES]-->   8 epilogue warps
+// The accumulator is double buffered in TMEM (2 x 256 columns), so the epilogue of tile i runs while the
+// tensor cores work on tile i+1.
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
@@ -64,12 +70,14 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.y * TM;
-    const int n0 = blockIdx.x * TN;
     const int KB = Kdim / TK;
+    const int n_tiles = (N + TN - 1) / TN;
+    const int64_t m_tiles = (M + TM - 1) / TM;
+    const int64_t num_tiles = m_tiles * n_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.al);
@@ -77,7 +85,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -87,94 +95,115 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* st = smem + s * STAGE_BYTES;
-            mbar_expect_tx(&full[s], STAGE_BYTES);
-            tma_load_2d(st, &maps.ah, &full[s], kb * TK, (int)m0);
-            tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, (int)m0);
-            tma_load_2d(st + 2 * A_BYTES, &maps.bh, &full[s], kb * TK, n0);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.bl, &full[s], kb * TK, n0);
+        // ===== TMA producer: runs ahead across tiles, bounded by the stage ring =====
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (int)(tile / n_tiles) * TM, n0 = (int)(tile % n_tiles) * TN;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_2d(st, &maps.ah, &full[s], kb * TK, m0);
+                tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, m0);
+                tma_load_2d(st + 2 * A_BYTES, &maps.bh, &full[s], kb * TK, n0);
+                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.bl, &full[s], kb * TK, n0);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer (one thread) =====
         constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&full[s], ph);
+        uint32_t it = 0, ti = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int a = ti % ACC_STAGES;
+            mbar_wait(&tmem_empty[a], ((ti / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-            const uint64_t dah = umma_desc_kmajor_sw128(sa);
-            const uint64_t dal = umma_desc_kmajor_sw128(sa + A_BYTES);
-            const uint64_t dbh = umma_desc_kmajor_sw128(sa + 2 * A_BYTES);
-            const uint64_t dbl = umma_desc_kmajor_sw128(sa + 2 * A_BYTES + B_BYTES);
+            const uint32_t tacc = tmem_base + (uint32_t)(a * TN);
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t dah = umma_desc_kmajor_sw128(sa);
+                const uint64_t dal = umma_desc_kmajor_sw128(sa + A_BYTES);
+                const uint64_t dbh = umma_desc_kmajor_sw128(sa + 2 * A_BYTES);
+                const uint64_t dbl = umma_desc_kmajor_sw128(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-            for (int k = 0; k < TK / UK; ++k) {
-                const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);       // +32 bytes per K step, 16-byte units
-                umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, (kb | k) != 0);
-                umma_tf32(tmem_base, dah + adv, dbl + adv, idesc, 1);
-                umma_tf32(tmem_base, dal + adv, dbh + adv, idesc, 1);
+                for (int k = 0; k < TK / UK; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);   // +32 bytes per K step, 16-byte units
+                    umma_tf32(tacc, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+                    umma_tf32(tacc, dah + adv, dbl + adv, idesc, 1);
+                    umma_tf32(tacc, dal + adv, dbh + adv, idesc, 1);
+                }
+                umma_commit(&empty[s]);                 // frees the stage when these MMAs retire
             }
-            umma_commit(&empty[s]);                 // frees the stage when these MMAs retire
+            umma_commit(&tmem_full[a]);                 // accumulator complete
         }
-        umma_commit(tmem_full);                     // accumulator complete
     } else if (warp >= 4) {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31, one row per thread =====
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;
-        const int64_t m = m0 + q * 32 + lane;
-        const bool rok = m < M;
-        double pq = 0.0, pk = 0.0;
-        const double he = (EPI == EPI_MALA && rok) ? 0.5 * ep.epsrow[m] : 0.0;
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-            float v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const int n = n0 + c0;
-            if (!rok || n >= N) continue;
-            if (EPI == EPI_PLAIN) {
-                float4* dst = reinterpret_cast<float4*>(C + m * ldc + n);
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4).. (one row per thread), columns half (w-4)/4 =====
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        uint32_t ti = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int a = ti % ACC_STAGES;
+            const int64_t m0 = (tile / n_tiles) * TM;
+            const int n0 = (int)(tile % n_tiles) * TN;
+            mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
+            tc_fence_after();
+            const int64_t m = m0 + q * 32 + lane;
+            const bool rok = m < M;
+            double pq = 0.0, pk = 0.0;
+            const double he = (EPI == EPI_MALA && rok) ? 0.5 * ep.epsrow[m] : 0.0;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (TN / 2));
+            for (int c0 = 0; c0 < TN / 2; c0 += 16) {
+                float v[16];
+                tmem_ld_32x16(trow + (uint32_t)c0, v);
+                const int n = n0 + half * (TN / 2) + c0;
+                if (!rok || n >= N) continue;
+                if (EPI == EPI_PLAIN) {
+                    float4* dst = reinterpret_cast<float4*>(C + m * ldc + n);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
-                const size_t off = (size_t)m * ldc + n;
-                float4* dst = reinterpret_cast<float4*>(ep.vp + off);
-                const float4* yh = reinterpret_cast<const float4*>(ep.yph + off);
-                const float4* yl = reinterpret_cast<const float4*>(ep.ypl + off);
-                const float4* xi = reinterpret_cast<const float4*>(ep.xi + off);
-                const float4* vc = reinterpret_cast<const float4*>(ep.vcur + off);
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                } else {
+                    const size_t off = (size_t)m * ldc + n;
+                    float4* dst = reinterpret_cast<float4*>(ep.vp + off);
+                    const float4* yh = reinterpret_cast<const float4*>(ep.yph + off);
+                    const float4* yl = reinterpret_cast<const float4*>(ep.ypl + off);
+                    const float4* xi = reinterpret_cast<const float4*>(ep.xi + off);
+                    const float4* vc = reinterpret_cast<const float4*>(ep.vcur + off);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    const float4 a = yh[i], b = yl[i], w = vc[i];
-                    const double dl[4] = {(double)a.x + (double)b.x, (double)a.y + (double)b.y,
-                                          (double)a.z + (double)b.z, (double)a.w + (double)b.w};
-                    const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
+                    for (int i = 0; i < 4; ++i) {
+                        dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        const float4 a4 = yh[i], b4 = yl[i], w = vc[i];
+                        const double dl[4] = {(double)a4.x + (double)b4.x, (double)a4.y + (double)b4.y,
+                                              (double)a4.z + (double)b4.z, (double)a4.w + (double)b4.w};
+                        const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) pq += dl[e] * (2.0 * wv[e] + (double)v[4 * i + e]);   // quad' - quad
-                    if (ep.mala) {
-                        // p' = xi + eps/2 g + eps/2 g',  g = -V, g' = -(V + P delta)   (hamiltonian.py:27,40)
-                        const float4 x = xi[i];
-                        const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
+                        for (int e = 0; e < 4; ++e) pq += dl[e] * (2.0 * wv[e] + (double)v[4 * i + e]);   // quad' - quad
+                        if (ep.mala) {
+                            // p' = xi + eps/2 g + eps/2 g',  g = -V, g' = -(V + P delta)   (hamiltonian.py:27,40)
+                            const float4 x = xi[i];
+                            const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + (double)v[4 * i + e]);
-                            pk += p1 * p1;
+                            for (int e = 0; e < 4; ++e) {
+                                const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + (double)v[4 * i + e]);
+                                pk += p1 * p1;
+                            }
                         }
                     }
                 }
             }
+            // this warp is done with accumulator a: hand it back to the MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[a]);
+            if (EPI == EPI_MALA && rok) {
+                const size_t blk = (size_t)(tile % n_tiles) * 2 + half;            // 128-column block index
+                ep.partq[blk * M + m] = pq;
+                if (ep.mala) ep.partk[blk * M + m] = pk;
+            }
         }
-        if (EPI == EPI_MALA && rok) {
-            ep.partq[(size_t)blockIdx.x * M + m] = pq;
-            if (ep.mala) ep.partk[(size_t)blockIdx.x * M + m] = pk;
-        }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -185,7 +214,10 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
                          cudaStream_t st) {
     if (Kdim % TK != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
-    dim3 grid((N + TN - 1) / TN, (unsigned)((M + TM - 1) / TM));
+    const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM);
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    dim3 grid((unsigned)(tiles < sms ? tiles : sms));          // persistent: one CTA per SM
     static bool attr = false;
     if (!attr) {
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
