@@ -17,6 +17,10 @@ namespace cp {
 // once per warp for 32 chains (the 16-lane kernel above serves 2).  The sum of log-gaps becomes
 // one log of their product (fp64 has the range: at most 16 factors in (0, xmax-xmin]).
 // =======================================================================================
+// Every loop of the step runs to a WARP-UNIFORM trip count (warp maximum of the per-thread bound)
+// with a predicated body, so no loop has a divergent exit and no loop sits inside a divergent branch.
+__device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
 template <bool INJ, int NT>
 __global__ void __launch_bounds__(NT)
 changepoint_tpc_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
@@ -85,14 +89,14 @@ changepoint_tpc_kernel(const __grid_constant__ CPParams P, const double* __restr
         const int ocur = bsel * GEN, onew = (bsel ^ 1) * GEN;     // offsets of the two boundary generations
         int kk = k;
         double nsig = sig, jarg = 1.0;
-        bool ovf = false, newb = false;
-
-        // ---- block moves: theta + scale * L xi with diagonal L (randomwalk.py:26), in place
+        bool ovf = false;
         const int nnorm = (mv == 0) ? k : ((mv == 1) ? k + 1 : ((mv == 2) ? 1 : 0));
         const int aoff = (mv == 0) ? 0 : GEN;                   // moved block: CX or CV
         const double mscale = (mv == 0) ? P.sx[k] : P.sv;
-        // noise for the step: generated for the widest lane of the warp, before any divergent code
-        const int maxn = __reduce_max_sync(0xffffffffu, nnorm);
+        const int kw = wmax(k);                                 // warp-uniform loop bounds
+        const int maxn = wmax(nnorm);
+
+        // ---- noise of the step (uniform loop)
         for (int b4 = 0; b4 < maxn; b4 += 4) {
             double xi[4];
             if (INJ) {
@@ -104,90 +108,97 @@ changepoint_tpc_kernel(const __grid_constant__ CPParams P, const double* __restr
 #pragma unroll
             for (int q = 0; q < 4; ++q) XI[(b4 + q) * NT] = xi[q];
         }
-        if (mv == 2) {
-            nsig = __dadd_rn(sig, __dmul_rn(P.ss, XI[0]));
-        } else {
-            for (int j = 0; j < nnorm; ++j) {
+        // ---- block moves: theta + scale * L xi with diagonal L (randomwalk.py:26), in place
+        for (int j = 0; j < maxn; ++j) {
+            if (mv < 2 && j < nnorm) {
                 const double old = CX[aoff + j * NT];
                 BK[j * NT] = old;
                 CX[aoff + j * NT] = __dadd_rn(old, __dmul_rn(mscale, XI[j * NT]));
             }
         }
-        if (mv == 0) {
-            // run boundaries follow the moved locations; proposals are local, so walk from the old one
-            newb = true;
-            for (int j = 0; j < k; ++j) {
-                const double cc = CX[j * NT];
-                const int b = upper_bound(xs, P.M, P.P2, cc);      // fixed-trip, branch-free
-                BU[onew + j * NT] = b;
-            }
+        if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, XI[0]));
+        // run boundaries of moved locations (cpx block move): fixed-trip search, predicated store
+        for (int j = 0; j < kw; ++j) {
+            const int b = upper_bound(xs, P.M, P.P2, CX[j * NT]);
+            if (mv == 0 && j < k) BU[onew + j * NT] = b;
         }
-        // ---- trans-dimensional moves (changepoint.py:193-240), in place with an undo record
-        int dpos = 0;
-        double sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-        if (mv == 3) {
-            if (birth) {
-                const double u = 0.5 + du / P.sqrtM;                                  // test_changepoint.py:61
-                const double f = sqrt((1.0 - u) / u);                                 // changepoint.py:57
-                int nb = 0;
-                for (int j = 0; j < k; ++j) nb += (CX[j * NT] < snew) ? 1 : 0;        // searchsorted(cpx, s)
-                const double h = CV[nb * NT];
-                jarg = fabs(h / (u * (1.0 - u)));                                     // |J|
-                if (k + 1 > LANES - 1) {
-                    ovf = true;
-                } else {
-                    for (int j = k; j > nb; --j) {
-                        CX[j * NT] = CX[(j - 1) * NT];
-                        CV[(j + 1) * NT] = CV[j * NT];
-                    }
-                    CX[nb * NT] = snew; CV[nb * NT] = h / f; CV[(nb + 1) * NT] = h * f;
-                    for (int j = 0; j < nb; ++j) BU[onew + j * NT] = BU[ocur + j * NT];
-                    BU[onew + nb * NT] = upper_bound(xs, P.M, P.P2, snew);
-                    for (int j = nb; j < k; ++j) BU[onew + (j + 1) * NT] = BU[ocur + j * NT];
-                    kk = k + 1; newb = true; dpos = nb; sv0 = h;
-                }
-            } else {
-                const int n = nrand;
-                const double h1 = CV[n * NT], h2 = CV[(n + 1) * NT];
-                const double h = sqrt(h1 * h2);                                       // changepoint.py:67
-                const double u = 1.0 / (1.0 + h2 / h1);                               // :68
-                jarg = fabs(h / (u * (1.0 - u)));                                     // 1/|J^-1|
-                dpos = n; sv0 = CX[n * NT]; sv1 = h1; sv2 = h2;
-                for (int j = n; j < k - 1; ++j) CX[j * NT] = CX[(j + 1) * NT];
-                CV[n * NT] = h;
-                for (int j = n + 1; j < k; ++j) CV[j * NT] = CV[(j + 1) * NT];
-                for (int j = 0; j < n; ++j) BU[onew + j * NT] = BU[ocur + j * NT];
-                for (int j = n; j < k - 1; ++j) BU[onew + j * NT] = BU[ocur + (j + 1) * NT];
-                kk = k - 1; newb = true;
-            }
-        }
+        bool newb = (mv == 0);
 
-        // ---- log-posterior of the (in-place) proposal
+        // ---- trans-dimensional moves (changepoint.py:193-240), in place with an undo record
+        const bool dimv = (mv == 3);
+        const bool want_b = dimv && birth;
+        const bool is_d = dimv && !birth;
+        int nb = 0;
+        for (int j = 0; j < kw; ++j) nb += (want_b && j < k && CX[j * NT] < snew) ? 1 : 0;   // searchsorted(cpx, s)
+        const int dn = is_d ? nrand : 0;
+        const double hb = CV[nb * NT];
+        const double h1 = CV[dn * NT], h2 = CV[min(dn + 1, LANES - 1) * NT];
+        const double ub = 0.5 + du / P.sqrtM;                                          // test_changepoint.py:61
+        const double fb = sqrt((1.0 - ub) / ub);                                       // changepoint.py:57
+        const double hd = sqrt(h1 * h2);                                               // :67
+        const double ud = 1.0 / (1.0 + h2 / h1);                                       // :68
+        if (want_b) jarg = fabs(hb / (ub * (1.0 - ub)));                               // |J|
+        if (is_d) jarg = fabs(hd / (ud * (1.0 - ud)));                                 // 1/|J^-1|
+        ovf = want_b && (k + 1 > LANES - 1);
+        const bool is_b = want_b && !ovf;
+        const int ubs = upper_bound(xs, P.M, P.P2, snew);
+        const double sv0 = is_b ? hb : CX[dn * NT];                                    // undo record
+        const int dpos = is_b ? nb : dn;
+        // birth: shift up (descending, predicated)
+        for (int j = kw; j >= 1; --j) {
+            if (is_b && j > nb && j <= k) {
+                CX[j * NT] = CX[(j - 1) * NT];
+                CV[(j + 1) * NT] = CV[j * NT];
+            }
+        }
+        if (is_b) { CX[nb * NT] = snew; CV[nb * NT] = hb / fb; CV[(nb + 1) * NT] = hb * fb; }
+        // death: shift down (ascending, predicated)
+        for (int j = 0; j < kw; ++j) {
+            if (is_d && j >= dn && j < k - 1) CX[j * NT] = CX[(j + 1) * NT];
+            if (is_d && j >= dn + 1 && j < k) CV[j * NT] = CV[(j + 1) * NT];
+        }
+        if (is_d) CV[dn * NT] = hd;
+        // boundaries of the new generation
+        for (int j = 0; j <= kw; ++j) {
+            if (is_b && j <= k) {
+                const int src = (j < nb) ? BU[ocur + j * NT] : ((j == nb) ? ubs : BU[ocur + (j - 1) * NT]);
+                BU[onew + j * NT] = src;
+            }
+            if (is_d && j < k - 1) BU[onew + j * NT] = (j < dn) ? BU[ocur + j * NT] : BU[ocur + (j + 1) * NT];
+        }
+        if (is_b) kk = k + 1;
+        if (is_d) kk = k - 1;
+        newb = newb || is_b || is_d;
+
+        // ---- log-posterior of the (in-place) proposal (uniform loop, predicated body)
         const int eoff = newb ? onew : ocur;
+        const int kkw = wmax(kk);
         double SS = 0.0, prod = 1.0, vsum = 0.0, vprod = 1.0, prevx = P.xmin;
         int bl = 0;
         bool bad = false;
-        for (int j = 0; j <= kk; ++j) {
-            const double hi = (j < kk) ? CX[j * NT] : P.xmax;
-            int bj = (j < kk) ? BU[eoff + j * NT] : P.M;
-            bj = max(0, min(bj, P.M));
-            const double v = CV[j * NT];
-            const double gap = hi - prevx;
-            bad |= !(gap > 0.0) || !(v > 0.0);
-            prod *= gap;
-            const double n = (double)(bj - bl);
-            const double a1 = cy[bj] - cy[bl], a2 = cyy[bj] - cyy[bl];
-            const double vc = v - P.ycenter;
-            SS += n * vc * vc - 2.0 * vc * a1 + a2;
-            vsum += v;
-            if (!P.alpha_is_one) vprod *= v;
-            prevx = hi; bl = bj;
+        for (int j = 0; j <= kkw; ++j) {
+            if (j <= kk) {
+                const double hi = (j < kk) ? CX[j * NT] : P.xmax;
+                const int bj = (j < kk) ? BU[eoff + j * NT] : P.M;
+                const double v = CV[j * NT];
+                const double gap = hi - prevx;
+                bad |= !(gap > 0.0) || !(v > 0.0);
+                prod *= gap;
+                const double n = (double)(bj - bl);
+                const double a1 = cy[bj] - cy[bl], a2 = cyy[bj] - cyy[bl];
+                const double vc = v - P.ycenter;
+                SS += n * vc * vc - 2.0 * vc * a1 + a2;
+                vsum += v;
+                if (!P.alpha_is_one) vprod *= v;
+                prevx = hi; bl = bj;
+            }
         }
         const int ks = kk + 1;
         const double s2n = nsig * nsig;
         const double log_s2 = log(s2n);
         const double lg = log(prod);
         const double logu = log(uacc);
+        const double ljac = log(jarg);
         double vt = -P.beta * vsum + (double)ks * P.cv;
         if (!P.alpha_is_one) vt += (P.alpha - 1.0) * log(vprod);
         double logl = -0.5 * ((SS / s2n + (double)P.M * log_s2) + P.Mlog2pi);
@@ -198,8 +209,7 @@ changepoint_tpc_kernel(const __grid_constant__ CPParams P, const double* __restr
         double logp = ((P.tab1[ks] + vt) + lps) + lsig;
         if (isnan(logp) || bad) logp = -INFINITY;
         const double lpn = combine_logpost(logp, logl);
-        double lqr = 0.0;
-        if (mv == 3) { const double lj = log(jarg); lqr = birth ? lj : -lj; }
+        const double lqr = dimv ? (birth ? ljac : -ljac) : 0.0;
 
         const double delta = lpn - lp - lqr;
         const double mh = (delta < 0.0) ? delta : 0.0;               // Python min(0, nan) == 0
@@ -217,37 +227,39 @@ changepoint_tpc_kernel(const __grid_constant__ CPParams P, const double* __restr
                 for (int j = 0; j < LANES; ++j) tr.d_prop_cpv[(t * K + c) * LANES + j] = (j <= kk) ? CV[j * NT] : 0.0;
         }
 
+        // ---- accept, or undo the in-place move (uniform loops, predicated bodies)
+        const bool undo_blk = !acc && mv < 2;
+        const bool undo_b = !acc && is_b, undo_d = !acc && is_d;
+        for (int j = 0; j < maxn; ++j)
+            if (undo_blk && j < nnorm) CX[aoff + j * NT] = BK[j * NT];
+        for (int j = 0; j < kw; ++j) {                       // undo insert at dpos (old k)
+            if (undo_b && j >= dpos && j < k) {
+                CX[j * NT] = CX[(j + 1) * NT];
+                CV[(j + 1) * NT] = CV[(j + 2) * NT];
+            }
+        }
+        if (undo_b) CV[dpos * NT] = sv0;
+        for (int j = kw; j >= 1; --j) {                      // undo delete at dpos (old k)
+            if (undo_d && j > dpos && j <= k - 1) CX[j * NT] = CX[(j - 1) * NT];
+            if (undo_d && j > dpos + 1 && j <= k) CV[j * NT] = CV[(j - 1) * NT];
+        }
+        if (undo_d) { CX[dpos * NT] = sv0; CV[dpos * NT] = h1; CV[(dpos + 1) * NT] = h2; }
+        novf += ovf ? 1 : 0;
         if (acc) {
             k = kk; sig = nsig; lp = lpn;
             if (newb) bsel ^= 1;
             nacc += 1;
-        } else {
-            novf += ovf ? 1 : 0;
-            if (mv < 2) {
-                for (int j = 0; j < nnorm; ++j) CX[aoff + j * NT] = BK[j * NT];
-            } else if (mv == 3 && !ovf) {
-                if (birth) {           // undo the insert at dpos
-                    for (int j = dpos; j < k; ++j) {
-                        CX[j * NT] = CX[(j + 1) * NT];
-                        CV[(j + 1) * NT] = CV[(j + 2) * NT];
-                    }
-                    CV[dpos * NT] = sv0;
-                } else {               // undo the delete at dpos
-                    for (int j = k - 1; j > dpos; --j) CX[j * NT] = CX[(j - 1) * NT];
-                    for (int j = k; j > dpos + 1; --j) CV[j * NT] = CV[(j - 1) * NT];
-                    CX[dpos * NT] = sv0; CV[dpos * NT] = sv1; CV[(dpos + 1) * NT] = sv2;
-                }
-            }
         }
 
         if ((step % RMN_CP_DIAG_EVERY) == 0) {
             int cnt[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) cnt[q] = 0;
-            for (int j = 0; j < k; ++j) {
+            const int kw2 = wmax(k);
+            for (int j = 0; j < kw2; ++j) {
                 const double cc = CX[j * NT];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) cnt[q] += (cc < P.xq[q]) ? 1 : 0;
+                for (int q = 0; q < NQ; ++q) cnt[q] += (j < k && cc < P.xq[q]) ? 1 : 0;
             }
             s1[0] += sig; s2[0] += sig * sig;
             s1[1] += (double)k; s2[1] += (double)k * (double)k;

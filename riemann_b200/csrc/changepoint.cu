@@ -24,6 +24,17 @@
 // as logqratio.
 #include "changepoint.cuh"
 
+#ifdef RMN_WITH_TPC   /* experiments/changepoint_tpc.cu linked in (not part of the product build) */
+#include <stdlib.h>
+#include <string.h>
+namespace cp {
+size_t tpc_smem_bytes(int M);
+void tpc_launch(bool inj, const CPParams& P, const double* gdata, const CPState& st, int64_t K, int64_t T,
+                int64_t step0, uint64_t seed, int64_t chain_offset, const double* tape, const rmn_trace_t& tr,
+                cudaStream_t stream);
+}
+#endif
+
 namespace {
 using namespace cp;
 
@@ -438,6 +449,15 @@ struct ChangepointSampler : SamplerImpl {
     }
     template <bool INJ>
     void launch(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
+#ifdef RMN_WITH_TPC
+        {
+            const char* e = getenv("RMN_CP_KERNEL");
+            if (!(e && !strcmp(e, "lanes")) && cp::tpc_smem_bytes(P.M) <= 160 * 1024) {
+                cp::tpc_launch(INJ, P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, stream);
+                return;
+            }
+        }
+#endif
         if (use_smem)
             changepoint_kernel<INJ, true, true><<<grid(), 128, smem_bytes, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
