@@ -77,9 +77,12 @@ extern "C" int rmn_model_changepoint_create(rmn_model_t** out, int M, const doub
     for (int i = 0; i < M; ++i) mean += h_y[i];
     mean /= (double)M;
     m->ycenter = mean;
-    std::vector<double> buf((size_t)3 * M + 2);
+    int p2 = 1;
+    while (p2 * 2 <= M) p2 *= 2;
+    const int XP = 2 * p2;                         // x table padded with NaN (changepoint.cuh: upper_bound)
+    std::vector<double> buf((size_t)XP + 2 * (size_t)M + 2, NAN);
     double* x = buf.data();
-    double* cy = x + M;
+    double* cy = x + XP;
     double* cyy = cy + M + 1;
     cy[0] = 0.0; cyy[0] = 0.0;
     for (int i = 0; i < M; ++i) {

@@ -23,69 +23,197 @@
 // a fresh uniform per block-selection elif; trans-dimensional moves use log|J| alone
 // as logqratio.
 #include "changepoint.cuh"
-
-#ifdef RMN_WITH_TPC   /* experiments/changepoint_tpc.cu linked in (not part of the product build) */
 #include <stdlib.h>
-#include <string.h>
-namespace cp {
-size_t tpc_smem_bytes(int M);
-void tpc_launch(bool inj, const CPParams& P, const double* gdata, const CPState& st, int64_t K, int64_t T,
-                int64_t step0, uint64_t seed, int64_t chain_offset, const double* tape, const rmn_trace_t& tr,
-                cudaStream_t stream);
-}
+
+#ifndef RMN_CP_DEFAULT_GL
+#define RMN_CP_DEFAULT_GL 4
 #endif
+
 
 namespace {
 using namespace cp;
 
 // ---------------------------------------------------------------------------------------
-// Log-posterior of one state held across the 16 lanes of a group, in two stages so that the
-// kernel can batch ALL of a step's fp64 logarithms into one (rarely two) `log` calls:
-//   stage 1 (cp_segments): binary search, per-lane segment residual, gap and height term;
-//   the caller takes log(gap) per lane together with the step's scalar logs
-//   (log sigma^2, log 1/sigma^2, log u, log|J|) computed on otherwise idle lanes;
-//   stage 2 (cp_combine): 16-lane reductions and the reference's term-by-term sums.
-// Plain IEEE arithmetic: log of a negative gap/height gives nan, log(0) gives -inf, exactly
-// like numpy; the reference's nan -> -inf and inf/nan -> -inf rules are applied at the end.
+// Group geometry.  GL lanes cooperate on one chain (32/GL chains per warp); lane l holds the
+// EPL = LANES/GL elements e = l + GL*j, j = 0..EPL-1 ("row" j) of cpx, cpv and of the cached
+// run boundaries in registers, statically indexed.  Rows beyond the warp's largest extent hold
+// the canonical padding (cpx = 0, cpv = 0, boundary = M) and are skipped by a warp-uniform
+// guard, so with the typical 3..8 changepoints a GL = 4 warp spends its instructions on 8
+// chains and two rows instead of on 2 chains and ten idle lanes.
 // ---------------------------------------------------------------------------------------
-struct CPSeg { double ss, gap, vt; };
+template <int GL> struct Geo {
+    static_assert(GL == 4 || GL == 8 || GL == 16, "GL must be 4, 8 or 16");
+    static constexpr int EPL = LANES / GL;
+    static constexpr int LOG = (GL == 4) ? 2 : ((GL == 8) ? 3 : 4);
+    static constexpr int NS = (RMN_CP_NDIAG + GL - 1) / GL;     // diagnostics slots per lane
+    // rows below ALWAYS are processed unconditionally (straight-line code, the rows' dependent chains
+    // interleave); only the rows above carry the warp-uniform guard.  12 elements cover k <= 10.
+    static constexpr int ALWAYS = (GL == 4) ? 3 : EPL;
+};
 
-__device__ __forceinline__ CPSeg cp_segments(const CPParams& P, const double* __restrict__ cy,
-                                             const double* __restrict__ cyy, int lane, int k,
-                                             double cx, double cv_, int bu) {
-    // bu = #{x_i <= cpx[lane]} for lane < k, M otherwise (upper end of this lane's run of data)
-    int bl = __shfl_up_sync(0xffffffffu, bu, 1, LANES);
-    if (lane == 0) bl = 0;
-    double prev = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
-    if (lane == 0) prev = P.xmin;
-    const double hi = (lane < k) ? cx : P.xmax;
-    CPSeg o;
-    o.ss = 0.0; o.vt = 0.0; o.gap = 1.0;                       // log(1) = 0 on inactive lanes
-    if (lane <= k) {
-        const double n = (double)(bu - bl);
-        const double s1 = cy[bu] - cy[bl];
-        const double s2 = cyy[bu] - cyy[bl];
-        const double vc = cv_ - P.ycenter;
-        o.ss = n * vc * vc - 2.0 * vc * s1 + s2;
-        o.gap = hi - prev;                                     // changepoint.py:142-143
-        o.vt = -P.beta * cv_ + P.cv;                           // changepoint.py:18-19,136
-        if (!P.alpha_is_one) o.vt += (P.alpha - 1.0) * log(cv_);
-        else if (!(cv_ > 0.0)) o.vt = NAN;                     // 0 * log(v<=0) is nan in numpy
-    }
-    return o;
+template <int GL>
+__device__ __forceinline__ unsigned gballot(bool pred) {
+    const unsigned full = __ballot_sync(0xffffffffu, pred);
+    return (full >> (threadIdx.x & 31 & ~(GL - 1))) & ((1u << GL) - 1u);
 }
 
-// lg = per-lane log(gap) (0 on inactive lanes); log_s2 = log(sigma^2); lsig = log(1/sigma^2)
-__device__ __forceinline__ double cp_combine(const CPParams& P, int k, double sig, CPSeg sg, double lg,
-                                             double log_s2, double lsig, int which) {
-    const double ss = group_sum<LANES>(sg.ss);
-    lg = group_sum<LANES>(lg);
-    const double vt = group_sum<LANES>(sg.vt);
-    const int ks = k + 1;                                      // number of steps
-    const double s2v = sig * sig;
+template <int GL>
+__device__ __forceinline__ double gsum(double v) {
+#pragma unroll
+    for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, GL);
+    return v;
+}
+
+template <int GL>
+__device__ __forceinline__ double gprod(double v) {
+#pragma unroll
+    for (int o = GL / 2; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o, GL);
+    return v;
+}
+
+// row j is live for this warp-step iff it can hold an element of any chain of the warp:
+// elements 0..k+1 (k+1 after a birth), kw = warp maximum of k
+#define ROW_ON(j) ((j) < Geo<GL>::ALWAYS || (j) * GL <= kw + 1)
+
+// value of element e-1 for every row (element -1 = `first`)
+template <int GL, typename T>
+__device__ __forceinline__ void shift_prev(const T (&a)[Geo<GL>::EPL], T (&out)[Geo<GL>::EPL], T first,
+                                           int lane, int kw) {
+#pragma unroll
+    for (int j = 0; j < Geo<GL>::EPL; ++j) {
+        out[j] = a[j];
+        if (ROW_ON(j)) {
+            const T up = __shfl_up_sync(0xffffffffu, a[j], 1, GL);
+            T w = first;
+            if (j > 0) w = __shfl_sync(0xffffffffu, a[j > 0 ? j - 1 : 0], GL - 1, GL);
+            out[j] = (lane == 0) ? w : up;
+        }
+    }
+}
+
+// value of element e+1 for every row (element LANES = `pad`)
+template <int GL, typename T>
+__device__ __forceinline__ void shift_next(const T (&a)[Geo<GL>::EPL], T (&out)[Geo<GL>::EPL], T pad,
+                                           int lane, int kw) {
+    constexpr int EPL = Geo<GL>::EPL;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        out[j] = a[j];
+        if (ROW_ON(j)) {
+            const T dn = __shfl_down_sync(0xffffffffu, a[j], 1, GL);
+            T w = pad;
+            if (j + 1 < EPL) w = __shfl_sync(0xffffffffu, a[j + 1 < EPL ? j + 1 : j], 0, GL);
+            out[j] = (lane == GL - 1) ? w : dn;
+        }
+    }
+}
+
+// value of element e + off, off in {-1, 0, +1} chosen per chain (birth: -1 above the insertion point,
+// death: +1 from the removed element on, everything else 0); elements -1 and LANES read `pad`.
+// Two shuffles per row: the row itself and the neighbouring row the wrap-around lane reads from.
+template <int GL, typename T>
+__device__ __forceinline__ void shift_by(const T (&a)[Geo<GL>::EPL], T (&out)[Geo<GL>::EPL], T pad, int lane,
+                                         int dir, const int (&off)[Geo<GL>::EPL], int kw) {
+    constexpr int EPL = Geo<GL>::EPL;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        out[j] = a[j];
+        if (ROW_ON(j)) {
+            const int src = (lane + off[j]) & (GL - 1);
+            const T lo = (j > 0) ? a[j > 0 ? j - 1 : 0] : pad;            // row below (read by lane 0 when off = -1)
+            const T hi = (j + 1 < EPL) ? a[j + 1 < EPL ? j + 1 : j] : pad; // row above (read by lane GL-1 when off = +1)
+            const T m = __shfl_sync(0xffffffffu, a[j], src, GL);
+            const T w = __shfl_sync(0xffffffffu, (dir < 0) ? lo : hi, src, GL);
+            const bool wrap = (off[j] < 0 && lane == 0) || (off[j] > 0 && lane == GL - 1);
+            out[j] = wrap ? w : m;
+        }
+    }
+}
+
+// a[idx] for a per-chain element index idx in [0, LANES)
+template <int GL>
+__device__ __forceinline__ double elem_at(const double (&a)[Geo<GL>::EPL], int idx, int kw) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < Geo<GL>::EPL; ++j) {
+        if (ROW_ON(j)) {
+            const double t = __shfl_sync(0xffffffffu, a[j], idx & (GL - 1), GL);
+            if ((idx >> Geo<GL>::LOG) == j) r = t;
+        }
+    }
+    return r;
+}
+
+// #{e < k : cpx[e] < s}   (np.searchsorted(cpx, s), changepoint.py:206)
+template <int GL>
+__device__ __forceinline__ int count_below(const double (&cx)[Geo<GL>::EPL], int lane, int k, double s, int kw) {
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < Geo<GL>::EPL; ++j)
+        if (ROW_ON(j)) n += __popc(gballot<GL>(lane + GL * j < k && cx[j] < s));
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// Log-posterior of one state held across the GL lanes of a group.  Per element: residual sum
+// of squares of its run of data (prefix sums), gap to the previous changepoint, height-prior
+// term.  The sum over changepoints of log(gap) (changepoint.py:142-143) is taken as ONE log of
+// the product of the gaps (a negative gap poisons the product with nan, exactly what a sum
+// containing log(negative) gives numpy; a zero gap gives -inf either way), and that log is
+// batched with the step's other fp64 logarithms -- log sigma^2, log u (accept test), log|J| --
+// on lanes 0..3 of the group: ONE `log` call per warp-step.  log(1/sigma^2) (:148) is
+// -log(sigma^2) (+inf where 1/sigma^2 overflows, as in numpy).  The reference's nan -> -inf and
+// inf/nan -> -inf rules are applied at the end.  Differences from numpy's term-by-term sums are
+// O(1e-15) relative (tests: 1e-9).
+// ---------------------------------------------------------------------------------------
+template <int GL>
+__device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const double* __restrict__ cy,
+                                                  const double* __restrict__ cyy, int lane, int kw, int kk,
+                                                  const double (&nx)[Geo<GL>::EPL], const double (&nv)[Geo<GL>::EPL],
+                                                  const int (&nbu)[Geo<GL>::EPL], double nsig, double uacc,
+                                                  double jarg, double& logu, double& ljac, int which) {
+    constexpr int EPL = Geo<GL>::EPL;
+    double px[EPL];
+    int pb[EPL];
+    shift_prev<GL, double>(nx, px, P.xmin, lane, kw);
+    shift_prev<GL, int>(nbu, pb, 0, lane, kw);
+    double ss = 0.0, vt = 0.0, gp = 1.0;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        if (ROW_ON(j)) {
+            const int e = lane + GL * j;
+            if (e <= kk) {
+                const int bu = nbu[j], bl = pb[j];
+                const double n = (double)(bu - bl);
+                const double s1 = cy[bu] - cy[bl];
+                const double s2 = cyy[bu] - cyy[bl];
+                const double vc = nv[j] - P.ycenter;
+                ss += n * vc * vc - 2.0 * vc * s1 + s2;
+                const double gap = ((e < kk) ? nx[j] : P.xmax) - px[j];            // changepoint.py:142-143
+                gp *= (gap < 0.0) ? NAN : gap;
+                double t = -P.beta * nv[j] + P.cv;                                 // changepoint.py:18-19,136
+                if (!P.alpha_is_one) t += (P.alpha - 1.0) * log(nv[j]);
+                else if (!(nv[j] > 0.0)) t = NAN;                                  // 0 * log(v<=0) is nan in numpy
+                vt += t;
+            }
+        }
+    }
+    ss = gsum<GL>(ss);
+    vt = gsum<GL>(vt);
+    gp = gprod<GL>(gp);
+    const double s2v = nsig * nsig;
+    const int sl = lane & 3;
+    const double larg = (sl == 0) ? gp : ((sl == 1) ? s2v : ((sl == 2) ? uacc : jarg));
+    const double lres = log(larg);
+    const double lg = __shfl_sync(0xffffffffu, lres, 0, GL);
+    const double log_s2 = __shfl_sync(0xffffffffu, lres, 1, GL);
+    logu = __shfl_sync(0xffffffffu, lres, 2, GL);
+    ljac = __shfl_sync(0xffffffffu, lres, 3, GL);
+    const int ks = kk + 1;                                     // number of steps
     double logl = -0.5 * ((ss / s2v + (double)P.M * log_s2) + P.Mlog2pi);   // :118-120
     if (isnan(logl)) logl = -INFINITY;                         // :124-125
-    if (sig < 0.0) lsig = NAN;                                 // :146-147
+    double lsig = (s2v < 5.562684646268003e-309) ? INFINITY : -log_s2;      // log(1/sigma^2), :148
+    if (nsig < 0.0) lsig = NAN;                                // :146-147
     const double lps = (P.tab2[ks] + lg) - (double)ks * P.logL;
     double logp = ((P.tab1[ks] + vt) + lps) + lsig;            // :156
     if (isnan(logp)) logp = -INFINITY;                         // :158-159
@@ -94,60 +222,62 @@ __device__ __forceinline__ double cp_combine(const CPParams& P, int k, double si
     return combine_logpost(logp, logl);
 }
 
-// stand-alone evaluation (set_state / pointwise): scalar logs ride on lanes 14, 15 when free
-__device__ __forceinline__ double cp_logpost(const CPParams& P, const double* __restrict__ xs,
-                                             const double* __restrict__ cy,
-                                             const double* __restrict__ cyy, int lane, int k,
-                                             double cx, double cv_, double sig, int which) {
-    const int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;
-    const CPSeg sg = cp_segments(P, cy, cyy, lane, k, cx, cv_, bu);
-    const double s2v = sig * sig;
-    const double lg = log(sg.gap);
-    const double sl = log((lane & 1) ? 1.0 / s2v : s2v);
-    const double log_s2 = __shfl_sync(0xffffffffu, sl, 0, LANES);
-    const double lsig = __shfl_sync(0xffffffffu, sl, 1, LANES);
-    return cp_combine(P, k, sig, sg, (lane <= k) ? lg : 0.0, log_s2, lsig, which);
-}
-
-template <bool INJ, bool SMEMDATA, bool DIAG>
 #ifndef RMN_CP_MINBLOCKS
-#define RMN_CP_MINBLOCKS 8   /* 64 regs/thread, 32 warps/SM: measured +3.5 % over 6 */
+#define RMN_CP_MINBLOCKS 5   /* 96 regs, 20 warps/SM: best of 4..8 measured (gpurun r17) */
 #endif
-__global__ void __launch_bounds__(128, RMN_CP_MINBLOCKS)
+
+// DATA: 0 = data tables read from global memory (too large for shared memory), 1 = staged in shared
+// memory, 2 = staged and 64 <= M < 128 (P2 = 64: fully unrolled 7-level search; the bench shape)
+template <bool INJ, int DATA, int GL>
+__global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
 changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
                    int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
                    const double* __restrict__ tape, rmn_trace_t tr) {
+    constexpr int EPL = Geo<GL>::EPL;
+    constexpr int NS = Geo<GL>::NS;
     extern __shared__ double smem[];
     const double* xs = gdata;
-    if (SMEMDATA) {
-        const int n = 3 * P.M + 2;
+    constexpr int LOGP2 = (DATA == 2) ? 6 : -1;
+    if (DATA != 0) {
+        const int n = P.XP + 2 * P.M + 2;
         for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = gdata[i];
         __syncthreads();
         xs = smem;
     }
-    const double* cy = xs + P.M;
+    const double* cy = xs + P.XP;
     const double* cyy = cy + P.M + 1;
 
-    const int lane = threadIdx.x & (LANES - 1);
-    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    const int lane = threadIdx.x & (GL - 1);
+    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GL;
     const bool live = c_raw < K;
     const int64_t c = live ? c_raw : K - 1;       // dead groups shadow the last chain, never store
 
     int k = st.k[c];
-    double cx = st.cpx[c * LANES + lane];
-    double cv = st.cpv[c * LANES + lane];
+    double cx[EPL], cv[EPL];
+    int bu[EPL];                                  // cached run boundaries of the state
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+        const int e = lane + GL * j;
+        cx[j] = st.cpx[c * LANES + e];
+        cv[j] = st.cpv[c * LANES + e];
+        bu[j] = (e < k) ? upper_bound<LOGP2>(xs, P.P2, cx[j]) : P.M;
+    }
     double sig = st.sig[c];
     double lp = st.lp[c];
-    int bu = (lane < k) ? upper_bound(xs, P.M, P.P2, cx) : P.M;   // cached run boundaries of the state
-    long long nacc = 0, novf = 0;
-    double s1 = 0.0, s2 = 0.0;                    // lane i < NDIAG accumulates functional i
+    int nacc = 0, novf = 0;
+    double s1[NS], s2[NS];                        // lane l, slot s accumulates functional l + GL*s
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { s1[s] = 0.0; s2[s] = 0.0; }
     const RngKey rk(seed, (uint64_t)(chain_offset + c));
     const TraceSel ts{tr.first, tr.thin > 0 ? tr.thin : 1};
     const bool tracing = tr.d_k || tr.d_cpx || tr.d_cpv || tr.d_sig || tr.d_logpost;
+    const bool tracing_prop = tr.d_prop_logpost || tr.d_accepted || tr.d_logqratio || tr.d_prop_k ||
+                              tr.d_prop_sig || tr.d_prop_cpx || tr.d_prop_cpv;
 
     for (int64_t t = 0; t < T; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
-        double snew, du, uacc, xi;
+        const int kw = __reduce_max_sync(0xffffffffu, k);
+        double snew, du, uacc, xi[EPL];
         int nrand, mv;
         bool birth;
         if (INJ) {
@@ -156,21 +286,32 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             const double ubd = row[RMN_CP_SLOT_BD];
             snew = row[RMN_CP_SLOT_S]; du = row[RMN_CP_SLOT_DU];
             nrand = (int)row[RMN_CP_SLOT_N]; uacc = row[RMN_CP_SLOT_ACC];
-            xi = row[RMN_CP_SLOT_XI + lane];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) xi[j] = row[RMN_CP_SLOT_XI + lane + GL * j];
             // which block moves (fresh uniform per elif, test_changepoint.py:48-54); birth/death :59
             mv = (u1 < P.p1) ? 0 : ((u2 < P.p2) ? 1 : ((u3 < P.p3) ? 2 : 3));
             birth = (k == 0) || (ubd > 0.5);
         } else {
-            // ONE Philox block per lane and step: words x,y -> this lane's normal; the spare
-            // words z,w of lanes 0..3 carry the chain-level uniforms
+            // ONE Philox block per lane and step: words x,y -> Box-Muller pair = the normals of this
+            // lane's rows 0 and 1; the spare words z,w of lanes 0..3 carry the chain-level uniforms.
+            // Rows 2,3 (GL = 4, only when some chain of the warp has >= 7 changepoints) take a second block.
             const uint4 r = rk.block(step, (uint32_t)lane);
             float n0, n1;
             box_muller(r.x, r.y, n0, n1);
-            xi = (double)n0;
-            const uint32_t z0 = __shfl_sync(0xffffffffu, r.z, 0, LANES), w0 = __shfl_sync(0xffffffffu, r.w, 0, LANES);
-            const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, LANES), w1 = __shfl_sync(0xffffffffu, r.w, 1, LANES);
-            const uint32_t z2 = __shfl_sync(0xffffffffu, r.z, 2, LANES), w2 = __shfl_sync(0xffffffffu, r.w, 2, LANES);
-            const uint32_t z3 = __shfl_sync(0xffffffffu, r.z, 3, LANES), w3 = __shfl_sync(0xffffffffu, r.w, 3, LANES);
+            xi[0] = (double)n0;
+            if (EPL > 1) xi[1 % EPL] = (double)n1;
+            if (EPL > 2) {
+                xi[2 % EPL] = 0.0; xi[3 % EPL] = 0.0;
+                if (ROW_ON(2)) {
+                    const uint4 q = rk.block(step, (uint32_t)(GL + lane));
+                    box_muller(q.x, q.y, n0, n1);
+                    xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
+                }
+            }
+            const uint32_t z0 = __shfl_sync(0xffffffffu, r.z, 0, GL), w0 = __shfl_sync(0xffffffffu, r.w, 0, GL);
+            const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, GL), w1 = __shfl_sync(0xffffffffu, r.w, 1, GL);
+            const uint32_t z2 = __shfl_sync(0xffffffffu, r.z, 2, GL), w2 = __shfl_sync(0xffffffffu, r.w, 2, GL);
+            const uint32_t z3 = __shfl_sync(0xffffffffu, r.z, 3, GL), w3 = __shfl_sync(0xffffffffu, r.w, 3, GL);
             mv = (z0 < P.t1) ? 0 : ((w0 < P.t2) ? 1 : ((z1 < P.t3) ? 2 : 3));   // same tests on raw words
             birth = (k == 0) || (w1 >= 0x80000000u);                            // u > 0.5
             snew = P.xmin + (P.xmax - P.xmin) * u01_fast(z2);
@@ -180,103 +321,124 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         }
         nrand = max(0, min(nrand, k - 1));
 
-        // ---- build the proposal by selection (the two chains of a warp never diverge on mv)
-        int kk = k, nbu = bu;
-        double nx = cx, nv = cv, nsig = sig, jarg = 1.0;
+        // ---- build the proposal by selection (the chains of a warp never diverge on mv)
+        int kk = k, nbu[EPL];
+        double nx[EPL], nv[EPL], nsig = sig, jarg = 1.0;
         bool ovf = false;
-        if (mv == 0) {
-            if (lane < k) nx = __dadd_rn(cx, __dmul_rn(P.sx[k], xi));   // randomwalk.py:26, scale = 1
-        } else if (mv == 1) {
-            if (lane <= k) nv = __dadd_rn(cv, __dmul_rn(P.sv, xi));
+        const double sxk = P.sx[k];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int e = lane + GL * j;
+            nx[j] = cx[j]; nv[j] = cv[j]; nbu[j] = bu[j];
+            if (ROW_ON(j)) {
+                if (mv == 0 && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));   // randomwalk.py:26, scale = 1
+                if (mv == 1 && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));
+            }
         }
-        const double xi0 = __shfl_sync(0xffffffffu, xi, 0, LANES);
+        const double xi0 = __shfl_sync(0xffffffffu, xi[0], 0, GL);
         if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
-        if (__any_sync(0xffffffffu, mv == 3)) {                         // warp-uniform (35 % of steps)
-            const double px = __shfl_up_sync(0xffffffffu, cx, 1, LANES);
-            const double pv = __shfl_up_sync(0xffffffffu, cv, 1, LANES);
-            const double qx = __shfl_down_sync(0xffffffffu, cx, 1, LANES);
-            const double qv = __shfl_down_sync(0xffffffffu, cv, 1, LANES);
-            const int nb = __popc(group_ballot(lane < k && cx < snew)); // searchsorted(cpx, s), :206
-            const double hb = __shfl_sync(0xffffffffu, cv, nb, LANES);
-            const double h1d = __shfl_sync(0xffffffffu, cv, nrand, LANES);
-            const double h2d = __shfl_sync(0xffffffffu, cv, nrand + 1, LANES);
-            const int pbu = __shfl_up_sync(0xffffffffu, bu, 1, LANES);
-            const int qbu = __shfl_down_sync(0xffffffffu, bu, 1, LANES);
-            if (mv == 3) {
-                if (birth) {
-                    const double u = 0.5 + du / P.sqrtM;                // :61
-                    const double f = sqrt((1.0 - u) / u);               // changepoint.py:57
-                    jarg = fabs(hb / (u * (1.0 - u)));                  // |J|, :72-74
-                    if (k + 1 > LANES - 1) {
-                        ovf = true;
-                    } else {
-                        nx = (lane < nb) ? cx : ((lane == nb) ? snew : px);
-                        nv = (lane < nb) ? cv : ((lane == nb) ? hb / f : ((lane == nb + 1) ? hb * f : pv));
-                        nbu = (lane <= nb) ? bu : pbu;          // lane nb is searched below
-                        kk = k + 1;
+        int nb = 0;
+        if (__any_sync(0xffffffffu, mv == 3)) {                         // warp-uniform
+            nb = count_below<GL>(cx, lane, k, snew, kw);                // searchsorted(cpx, s), :206
+            const double hb = elem_at<GL>(cv, nb, kw);
+            const double h1d = elem_at<GL>(cv, nrand, kw);
+            const double h2d = elem_at<GL>(cv, nrand + 1, kw);
+            // birth (changepoint.py:57,61,72-74) and death (:67-68,76-78) share one instruction
+            // stream: the operands of each division / square root are selected per chain
+            const double q1 = birth ? du / P.sqrtM : h2d / h1d;
+            const double ub = 0.5 + q1;                                 // birth: u, :61
+            const double q2 = birth ? (1.0 - ub) / ub : 1.0 / (1.0 + q1);       // birth: f^2; death: u, :68
+            const double u = birth ? ub : q2;
+            const double r = sqrt(birth ? q2 : h1d * h2d);              // birth: f, :57; death: h, :67
+            jarg = fabs((birth ? hb : r) / (u * (1.0 - u)));            // |J| resp. 1/|J^-1|
+            const double hbf = hb / r;
+            ovf = (mv == 3) && birth && (k + 1 > LANES - 1);
+            const bool td = (mv == 3) && !ovf;
+            if (!(mv == 3)) jarg = 1.0;
+            // insert / delete = every element reads its neighbour below (birth, above the insertion
+            // point) or above (death, from the removed element on); other chains read themselves
+            const int dir = birth ? -1 : 1;
+            const int pivot = birth ? nb : nrand - 1;                   // elements <= pivot stay
+            int off[EPL];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) off[j] = (td && lane + GL * j > pivot) ? dir : 0;
+            double sx_[EPL], sv_[EPL];
+            int sb_[EPL];
+            shift_by<GL, double>(cx, sx_, 0.0, lane, dir, off, kw);
+            shift_by<GL, double>(cv, sv_, 0.0, lane, dir, off, kw);
+            shift_by<GL, int>(bu, sb_, P.M, lane, dir, off, kw);
+            if (td) {
+                kk = birth ? k + 1 : k - 1;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const int e = lane + GL * j;
+                    nx[j] = sx_[j]; nv[j] = sv_[j]; nbu[j] = sb_[j];
+                    if (birth) {
+                        if (e == nb) { nx[j] = snew; nv[j] = hbf; nbu[j] = bu[j]; }   // boundary searched below
+                        if (e == nb + 1) nv[j] = hb * r;
+                    } else if (e == nrand) {
+                        nv[j] = r;
                     }
-                } else {
-                    const double h = sqrt(h1d * h2d);                   // changepoint.py:67
-                    const double u = 1.0 / (1.0 + h2d / h1d);           // :68
-                    jarg = fabs(h / (u * (1.0 - u)));                   // 1/|J^-1|, :76-78
-                    nx = (lane < nrand) ? cx : qx;
-                    nv = (lane < nrand) ? cv : ((lane == nrand) ? h : qv);
-                    nbu = (lane < nrand) ? bu : qbu;
-                    kk = k - 1;
                 }
             }
         }
-        // lanes beyond the new extent hold zeros (canonical padding)
-        if (lane >= kk) { nx = 0.0; nbu = P.M; }
-        if (lane > kk) nv = 0.0;
-        // run boundaries only move when a location moves: a cpx block move (every lane) or a
-        // birth (the new lane).  Warp-uniform, taken on about half of the steps.
+        // elements beyond the new extent hold zeros (canonical padding)
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int e = lane + GL * j;
+            if (e >= kk) { nx[j] = 0.0; nbu[j] = P.M; }
+            if (e > kk) nv[j] = 0.0;
+        }
+        // run boundaries only move when a location moves: a cpx block move (every element) or a
+        // birth (the new element).
         const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
         if (__any_sync(0xffffffffu, moved_x)) {
-            const int sb = upper_bound(xs, P.M, P.P2, nx);
-            if (moved_x && lane < kk) nbu = sb;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                if (ROW_ON(j)) {
+                    const int e = lane + GL * j;
+                    const int sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
+                    if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
+                }
+            }
         }
 
-        // ---- log-posterior of the proposal; every fp64 log of the step in one call:
-        //      lanes 0..kk take log(gap); lanes 12..15 take log sigma^2, log 1/sigma^2, log u, log|J|
-        //      (if a chain has more than 11 changepoints those four go through a second call)
-        const CPSeg sg = cp_segments(P, cy, cyy, lane, kk, nx, nv, nbu);
-        const double s2n = nsig * nsig;
-        const int sl = lane & 3;
-        const double sarg = (sl == 0) ? s2n : ((sl == 1) ? 1.0 / s2n : ((sl == 2) ? uacc : jarg));
-        const bool crowded = kk > 11;
-        const double l1 = log((lane >= 12 && !crowded) ? sarg : sg.gap);
-        double l2 = 0.0;
-        if (__any_sync(0xffffffffu, crowded)) l2 = log(sarg);
-        const double lsrc = crowded ? l2 : l1;
-        const int sbase = crowded ? 0 : 12;
-        const double log_s2 = __shfl_sync(0xffffffffu, lsrc, sbase + 0, LANES);
-        const double lsig = __shfl_sync(0xffffffffu, lsrc, sbase + 1, LANES);
-        const double logu = __shfl_sync(0xffffffffu, lsrc, sbase + 2, LANES);
-        const double ljac = __shfl_sync(0xffffffffu, lsrc, sbase + 3, LANES);
-        const double lpn = cp_combine(P, kk, nsig, sg, (lane <= kk) ? l1 : 0.0, log_s2, lsig, 0);
+        // ---- log-posterior of the proposal; every fp64 log of the step in one call
+        double logu, ljac;
+        const double lpn = cp_logpost_rows<GL>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, nsig, uacc, jarg, logu, ljac, 0);
         const double lqr = (mv == 3) ? (birth ? ljac : -ljac) : 0.0;
 
         // sampler.py:83-84 with Python's min(0, nan) == 0
         const double delta = lpn - lp - lqr;
         const double mh = (delta < 0.0) ? delta : 0.0;
         const bool acc = !ovf && (logu < mh);
-        if (acc) { k = kk; cx = nx; cv = nv; sig = nsig; lp = lpn; bu = nbu; }
+        if (acc) {
+            k = kk; sig = nsig; lp = lpn;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; cv[j] = nv[j]; bu[j] = nbu[j]; }
+        }
         nacc += acc ? 1 : 0;
         novf += ovf ? 1 : 0;
 
-        if (DIAG && (step % RMN_CP_DIAG_EVERY) == 0) {      // thinned accumulation (warp-uniform)
-            double f = (lane == 0) ? sig : (double)k;
+        if ((step % RMN_CP_DIAG_EVERY) == 0) {              // thinned accumulation (warp-uniform)
+            // (k <= kw + 1 after an accepted birth, so the step's row guard still covers the state)
+            double f[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) f[s] = 0.0;
+            if (lane == 0) f[0] = sig;
+            if (lane == 1 % GL) f[1 / GL] = (double)k;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const int cnt = __popc(group_ballot(lane < k && cx < P.xq[q]));
-                const double yq = __shfl_sync(0xffffffffu, cv, cnt, LANES);
-                if (lane == 2 + q) f = yq;
+                const int cnt = count_below<GL>(cx, lane, k, P.xq[q], kw);
+                const double yq = elem_at<GL>(cv, cnt, kw);
+                if (lane == (2 + q) % GL) f[(2 + q) / GL] = yq;
             }
-            if (lane < RMN_CP_NDIAG) { s1 += f; s2 += f * f; }
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (lane + GL * s < RMN_CP_NDIAG) { s1[s] += f[s]; s2[s] += f[s] * f[s]; }
         }
 
-        if (live) {
+        if (live && (tracing || tracing_prop)) {
             if (lane == 0) {
                 if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpn;
                 if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
@@ -284,13 +446,21 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                 if (tr.d_prop_k) tr.d_prop_k[t * K + c] = kk;
                 if (tr.d_prop_sig) tr.d_prop_sig[t * K + c] = nsig;
             }
-            if (tr.d_prop_cpx) tr.d_prop_cpx[(t * K + c) * LANES + lane] = nx;
-            if (tr.d_prop_cpv) tr.d_prop_cpv[(t * K + c) * LANES + lane] = nv;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + GL * j;
+                if (tr.d_prop_cpx) tr.d_prop_cpx[(t * K + c) * LANES + e] = nx[j];
+                if (tr.d_prop_cpv) tr.d_prop_cpv[(t * K + c) * LANES + e] = nv[j];
+            }
             if (tracing) {
                 const long long r = ts.slot(t + 1);
                 if (r >= 0) {
-                    if (tr.d_cpx) tr.d_cpx[(r * K + c) * LANES + lane] = cx;
-                    if (tr.d_cpv) tr.d_cpv[(r * K + c) * LANES + lane] = cv;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) {
+                        const int e = lane + GL * j;
+                        if (tr.d_cpx) tr.d_cpx[(r * K + c) * LANES + e] = cx[j];
+                        if (tr.d_cpv) tr.d_cpv[(r * K + c) * LANES + e] = cv[j];
+                    }
                     if (lane == 0) {
                         if (tr.d_k) tr.d_k[r * K + c] = k;
                         if (tr.d_sig) tr.d_sig[r * K + c] = sig;
@@ -302,8 +472,12 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     }
 
     if (live) {
-        st.cpx[c * LANES + lane] = cx;
-        st.cpv[c * LANES + lane] = cv;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int e = lane + GL * j;
+            st.cpx[c * LANES + e] = cx[j];
+            st.cpv[c * LANES + e] = cv[j];
+        }
         if (lane == 0) {
             st.k[c] = k;
             st.sig[c] = sig;
@@ -311,9 +485,13 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             st.dacc[c] += nacc;
             st.dovf[c] += novf;
         }
-        if (DIAG && lane < RMN_CP_NDIAG) {
-            st.S1[(int64_t)lane * K + c] += s1;
-            st.S2[(int64_t)lane * K + c] += s2;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = lane + GL * s;
+            if (i < RMN_CP_NDIAG) {
+                st.S1[(int64_t)i * K + c] += s1[s];
+                st.S2[(int64_t)i * K + c] += s2[s];
+            }
         }
     }
 }
@@ -324,15 +502,22 @@ cp_eval_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gd
                int64_t n, const int32_t* __restrict__ kin, const double* __restrict__ cpx,
                const double* __restrict__ cpv, const double* __restrict__ sig,
                double* __restrict__ out) {
-    const int lane = threadIdx.x & (LANES - 1);
-    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    constexpr int GL = 16;
+    const int lane = threadIdx.x & (GL - 1);
+    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GL;
     const bool live = c_raw < n;
     const int64_t c = live ? c_raw : n - 1;
     const double* xs = gdata;
-    const double* cy = xs + P.M;
+    const double* cy = xs + P.XP;
     const double* cyy = cy + P.M + 1;
-    const double v = cp_logpost(P, xs, cy, cyy, lane, kin[c], cpx[c * LANES + lane],
-                                cpv[c * LANES + lane], sig[c], which);
+    const int k = kin[c];
+    const int kw = LANES;                                        // every row on
+    double x1[1] = {cpx[c * LANES + lane]}, v1[1] = {cpv[c * LANES + lane]};
+    int b1[1] = {(lane < k) ? upper_bound<-1>(xs, P.P2, x1[0]) : P.M};
+    if (lane >= k) x1[0] = 0.0;
+    if (lane > k) v1[0] = 0.0;
+    double logu, ljac;
+    const double v = cp_logpost_rows<GL>(P, cy, cyy, lane, kw, k, x1, v1, b1, sig[c], 1.0, 1.0, logu, ljac, which);
     if (live && lane == 0) out[c] = v;
 }
 
@@ -360,6 +545,7 @@ static CPParams make_params(const rmn_model* m, const rmn_proposal* p) {
     int p2 = 1;
     while (p2 * 2 <= m->M) p2 *= 2;
     P.P2 = (m->M >= 1) ? p2 : 0;
+    P.XP = 2 * P.P2;
     P.alpha_is_one = (m->alpha == 1.0);
     P.xmin = m->xmin; P.xmax = m->xmax; P.alpha = m->alpha; P.beta = m->beta;
     P.cv = m->cv;
@@ -393,9 +579,14 @@ struct ChangepointSampler : SamplerImpl {
     CPParams P;
     bool use_smem;
     size_t smem_bytes;
+    int gl = RMN_CP_DEFAULT_GL;     // lanes per chain (4, 8 or 16); RMN_CP_GL overrides (A/B measurements)
     explicit ChangepointSampler(rmn_sampler* s_) : s(s_) {
         P = make_params(s->model, s->prop);
-        smem_bytes = (size_t)(3 * P.M + 2) * 8;
+        if (const char* e = getenv("RMN_CP_GL")) {
+            const int v = atoi(e);
+            if (v == 4 || v == 8 || v == 16) gl = v;
+        }
+        smem_bytes = (size_t)(P.XP + 2 * P.M + 2) * 8;
         use_smem = smem_bytes <= 96 * 1024;
     }
     size_t workspace_bytes() const override {
@@ -417,14 +608,20 @@ struct ChangepointSampler : SamplerImpl {
         st.S2 = (double*)p; p += align256(RMN_CP_NDIAG * K * 8);
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
         if (use_smem && smem_bytes > 48 * 1024) {
-            RMN_CUDA(cudaFuncSetAttribute(changepoint_kernel<false, true, true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-            RMN_CUDA(cudaFuncSetAttribute(changepoint_kernel<true, true, true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            RMN_CUDA(set_smem_attr<4>());
+            RMN_CUDA(set_smem_attr<8>());
+            RMN_CUDA(set_smem_attr<16>());
         }
         return RMN_OK;
     }
-    unsigned grid() const { return (unsigned)((s->K * LANES + 127) / 128); }
+    template <int GL> cudaError_t set_smem_attr() {
+        cudaError_t e = cudaFuncSetAttribute(changepoint_kernel<false, 1, GL>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(changepoint_kernel<true, 1, GL>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
+    unsigned grid(int gl = LANES) const { return (unsigned)((s->K * gl + 127) / 128); }
 
     int cp_set_state(const int32_t* d_k, const double* d_cpx, const double* d_cpv,
                      const double* d_sig, cudaStream_t stream) override {
@@ -449,20 +646,22 @@ struct ChangepointSampler : SamplerImpl {
     }
     template <bool INJ>
     void launch(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
-#ifdef RMN_WITH_TPC
-        {
-            const char* e = getenv("RMN_CP_KERNEL");
-            if (!(e && !strcmp(e, "lanes")) && cp::tpc_smem_bytes(P.M) <= 160 * 1024) {
-                cp::tpc_launch(INJ, P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, stream);
-                return;
-            }
+        switch (gl) {
+            case 16: launch_gl<INJ, 16>(T, tape, t0, stream); break;
+            case 8: launch_gl<INJ, 8>(T, tape, t0, stream); break;
+            default: launch_gl<INJ, 4>(T, tape, t0, stream); break;
         }
-#endif
-        if (use_smem)
-            changepoint_kernel<INJ, true, true><<<grid(), 128, smem_bytes, stream>>>(
+    }
+    template <bool INJ, int GL>
+    void launch_gl(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
+        if (use_smem && P.P2 == 64)
+            changepoint_kernel<INJ, 2, GL><<<grid(GL), 128, smem_bytes, stream>>>(
+                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
+        else if (use_smem)
+            changepoint_kernel<INJ, 1, GL><<<grid(GL), 128, smem_bytes, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
         else
-            changepoint_kernel<INJ, false, true><<<grid(), 128, 0, stream>>>(
+            changepoint_kernel<INJ, 0, GL><<<grid(GL), 128, 0, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
     }
     int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {

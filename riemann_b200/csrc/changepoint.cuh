@@ -9,7 +9,7 @@ constexpr int NQ = 6;   // prediction query points tracked by the diagnostics
 #define RMN_CP_DIAG_EVERY 4   // diagnostics functionals are accumulated every 4th MH step
 
 struct CPParams {
-    int M, P2, alpha_is_one, pad;
+    int M, P2, alpha_is_one, XP;  // XP = 2*P2: padded length of the x table (device data = xpad[XP] | cy[M+1] | cyy[M+1])
     double xmin, xmax, alpha, beta, cv, logL, ycenter, Mlog2pi, sqrtM;
     double tab1[LANES + 1];     // k log(lam) - gammaln(k) - lam        changepoint.py:134
     double tab2[LANES + 1];     // gammaln(2k+1)                        changepoint.py:143
@@ -37,12 +37,21 @@ __device__ __forceinline__ unsigned group_ballot(bool pred) {
     return (full >> (threadIdx.x & 16)) & 0xffffu;
 }
 
-// #{i : x_i <= c}  (upper bound), branch-free, always in [0, M]
-__device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int M, int P2, double c) {
+// #{i : x_i <= c}  (upper bound, np.searchsorted(x, c, 'right')), branch-free, always in [0, M].
+// The x table is padded with NaN up to XP = 2*P2 entries (P2 = largest power of two <= M): a NaN
+// never compares <= c, so the search needs no bound check and stops at M by itself; a NaN / +inf
+// query gives 0 / M like the unpadded search.  LOGP2 >= 0: P2 known at compile time, fully unrolled
+// (one LDS + one compare + one predicated add per level); LOGP2 < 0: run-time P2.
+template <int LOGP2>
+__device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int P2, double c) {
     int pos = 0;
-    for (int step = P2; step > 0; step >>= 1) {
-        const int np = pos + step;
-        if (np <= M && xs[np - 1] <= c) pos = np;
+    if (LOGP2 >= 0) {
+#pragma unroll
+        for (int b = LOGP2; b >= 0; --b)
+            if (xs[pos + (1 << b) - 1] <= c) pos += (1 << b);
+    } else {
+        for (int step = P2; step > 0; step >>= 1)
+            if (xs[pos + step - 1] <= c) pos += step;
     }
     return pos;
 }
