@@ -25,6 +25,15 @@
 #include "changepoint.cuh"
 #include <stdlib.h>
 
+#ifndef RMN_CP_PREFETCH
+#define RMN_CP_PREFETCH 1
+#endif
+#ifndef RMN_CP_UNCOND_TD
+#define RMN_CP_UNCOND_TD 0
+#endif
+#ifndef RMN_CP_UNCOND_SEARCH
+#define RMN_CP_UNCOND_SEARCH 1   /* the search joins the evaluation's basic block: +7 % (gpurun r20) */
+#endif
 #ifndef RMN_CP_DEFAULT_GL
 #define RMN_CP_DEFAULT_GL 4
 #endif
@@ -274,6 +283,15 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     const bool tracing_prop = tr.d_prop_logpost || tr.d_accepted || tr.d_logqratio || tr.d_prop_k ||
                               tr.d_prop_sig || tr.d_prop_cpx || tr.d_prop_cpv;
 
+#if RMN_CP_PREFETCH
+    // software pipelining: the Philox blocks of step t+1 are issued in the middle of step t (they depend
+    // on nothing but the counter), so their integer multiplies fill the fp64 / LDS latency of the evaluation
+    uint4 rA = make_uint4(0, 0, 0, 0), rB = make_uint4(0, 0, 0, 0);
+    if (!INJ) {
+        rA = rk.block((uint64_t)step0, (uint32_t)lane);
+        if (EPL > 2) rB = rk.block((uint64_t)step0, (uint32_t)(GL + lane));
+    }
+#endif
     for (int64_t t = 0; t < T; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
         const int kw = __reduce_max_sync(0xffffffffu, k);
@@ -295,7 +313,11 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             // ONE Philox block per lane and step: words x,y -> Box-Muller pair = the normals of this
             // lane's rows 0 and 1; the spare words z,w of lanes 0..3 carry the chain-level uniforms.
             // Rows 2,3 (GL = 4, only when some chain of the warp has >= 7 changepoints) take a second block.
+#if RMN_CP_PREFETCH
+            const uint4 r = rA;
+#else
             const uint4 r = rk.block(step, (uint32_t)lane);
+#endif
             float n0, n1;
             box_muller(r.x, r.y, n0, n1);
             xi[0] = (double)n0;
@@ -303,7 +325,11 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             if (EPL > 2) {
                 xi[2 % EPL] = 0.0; xi[3 % EPL] = 0.0;
                 if (ROW_ON(2)) {
+#if RMN_CP_PREFETCH
+                    const uint4 q = rB;
+#else
                     const uint4 q = rk.block(step, (uint32_t)(GL + lane));
+#endif
                     box_muller(q.x, q.y, n0, n1);
                     xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
                 }
@@ -338,7 +364,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         const double xi0 = __shfl_sync(0xffffffffu, xi[0], 0, GL);
         if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
         int nb = 0;
-        if (__any_sync(0xffffffffu, mv == 3)) {                         // warp-uniform
+        if (RMN_CP_UNCOND_TD || __any_sync(0xffffffffu, mv == 3)) {     // warp-uniform
             nb = count_below<GL>(cx, lane, k, snew, kw);                // searchsorted(cpx, s), :206
             const double hb = elem_at<GL>(cv, nb, kw);
             const double h1d = elem_at<GL>(cv, nrand, kw);
@@ -392,17 +418,29 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         // run boundaries only move when a location moves: a cpx block move (every element) or a
         // birth (the new element).
         const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
-        if (__any_sync(0xffffffffu, moved_x)) {
+        if (RMN_CP_UNCOND_SEARCH || __any_sync(0xffffffffu, moved_x)) {
+            constexpr int NA = Geo<GL>::ALWAYS;
+            double qa[NA];
+            int sa[NA];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) qa[j] = nx[j];
+            upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
 #pragma unroll
             for (int j = 0; j < EPL; ++j) {
-                if (ROW_ON(j)) {
-                    const int e = lane + GL * j;
-                    const int sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
-                    if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
-                }
+                const int e = lane + GL * j;
+                int sb = 0;
+                if (j < NA) sb = sa[j < NA ? j : 0];
+                else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
+                if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
             }
         }
 
+#if RMN_CP_PREFETCH
+        if (!INJ) {
+            rA = rk.block(step + 1, (uint32_t)lane);
+            if (EPL > 2) rB = rk.block(step + 1, (uint32_t)(GL + lane));
+        }
+#endif
         // ---- log-posterior of the proposal; every fp64 log of the step in one call
         double logu, ljac;
         const double lpn = cp_logpost_rows<GL>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, nsig, uacc, jarg, logu, ljac, 0);

@@ -44,16 +44,47 @@ __device__ __forceinline__ unsigned group_ballot(bool pred) {
 // (one LDS + one compare + one predicated add per level); LOGP2 < 0: run-time P2.
 template <int LOGP2>
 __device__ __forceinline__ int upper_bound(const double* __restrict__ xs, int P2, double c) {
-    int pos = 0;
+    const char* base = (const char*)xs;
+    unsigned off = 0;                               // byte offset of the running position
     if (LOGP2 >= 0) {
 #pragma unroll
         for (int b = LOGP2; b >= 0; --b)
-            if (xs[pos + (1 << b) - 1] <= c) pos += (1 << b);
+            if (*(const double*)(base + off + ((1 << b) - 1) * 8) <= c) off += 8u << b;
     } else {
         for (int step = P2; step > 0; step >>= 1)
-            if (xs[pos + step - 1] <= c) pos += step;
+            if (*(const double*)(base + off + (step - 1) * 8) <= c) off += 8u * step;
     }
-    return pos;
+    return (int)(off >> 3);
+}
+
+// R independent searches, levels interleaved (the R dependent LDS chains overlap)
+template <int LOGP2, int R>
+__device__ __forceinline__ void upper_bound_rows(const double* __restrict__ xs, int P2, const double (&c)[R],
+                                                 int (&pos)[R]) {
+    const char* base = (const char*)xs;
+    unsigned off[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) off[r] = 0;
+    if (LOGP2 >= 0) {
+#pragma unroll
+        for (int b = LOGP2; b >= 0; --b) {
+            double v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = *(const double*)(base + off[r] + ((1 << b) - 1) * 8);
+#pragma unroll
+            for (int r = 0; r < R; ++r) if (v[r] <= c[r]) off[r] += 8u << b;
+        }
+    } else {
+        for (int step = P2; step > 0; step >>= 1) {
+            double v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = *(const double*)(base + off[r] + (step - 1) * 8);
+#pragma unroll
+            for (int r = 0; r < R; ++r) if (v[r] <= c[r]) off[r] += 8u * step;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) pos[r] = (int)(off[r] >> 3);
 }
 
 // uniform on (0,1) from 32 random bits with 2 fp64 instructions: [1,2) mantissa trick + 2^-33

@@ -6,8 +6,11 @@ set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
-for mb in "$@"; do
-  nvcc $FLAGS -DRMN_CP_MINBLOCKS=$mb -c riemann_b200/csrc/changepoint.cu -o build/changepoint_mb$mb.o
+# each argument: <name>[:<extra -D flags, comma separated>], e.g. 5  6:-DRMN_CP_PREFETCH=1
+for spec in "$@"; do
+  mb=${spec%%:*}; extra=""; [ "$spec" != "$mb" ] && extra=$(echo "${spec#*:}" | tr ',' ' ')
+  tagx=$(echo "$extra" | tr -cd 'A-Z0-9=' | sed 's/DRMNCP//g'); mbn=${mb}; mb=${mb}${tagx:+_$tagx}
+  nvcc $FLAGS -DRMN_CP_MINBLOCKS=$mbn $extra -c riemann_b200/csrc/changepoint.cu -o build/changepoint_mb$mb.o
   objs="build/api.o build/util.o build/small_gauss.o build/dense.o build/logistic.o build/tc_gemm.o build/dense_tf32.o"
   nvcc -shared -o build/lib_cp_mb$mb.so $objs build/changepoint_mb$mb.o -lcudart
   echo "built build/lib_cp_mb$mb.so"

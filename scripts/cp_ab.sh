@@ -2,7 +2,7 @@
 # A/B of the changepoint kernel geometry on one B200: parity tests per lanes-per-chain setting,
 # then the headline bench per (occupancy variant, lanes per chain).
 OUT=gpurun_out; TAG=${1:-ab}; mkdir -p $OUT
-for gl in 4 8 16; do
+for gl in ${GLS:-4 8 16}; do
   RMN_CP_GL=$gl timeout 900 python -m pytest tests/test_gpu_changepoint.py tests/test_gpu_proposals.py -x -q -m gpu > $OUT/${TAG}_pytest_gl$gl.log 2>&1
   echo "GL=$gl pytest rc=$? $(tail -1 $OUT/${TAG}_pytest_gl$gl.log)"
 done
@@ -18,10 +18,9 @@ except Exception as e:
 PY
 }
 D=$PWD/riemann_b200/libriemann_b200.so
-bench $D 16 gl16
-bench $D 8 gl8_mb4
-bench $D 4 gl4_mb4
-for mb in 5 6 8; do
+bench $D 4 gl4_default
+bench $D 8 gl8_default
+for mb in $MBS; do
   bench $PWD/build/lib_cp_mb$mb.so 4 gl4_mb$mb
   bench $PWD/build/lib_cp_mb$mb.so 8 gl8_mb$mb
 done
