@@ -47,11 +47,11 @@ ALGO_FLOP = {"changepoint": 650.0, "gauss2d_rw": 40.0, "gauss1000_mala": 2.0e6,
 # kernel on this code): DRAM bytes per launch and the pipe/issue utilisation.  Static evidence,
 # NOT re-measured by this script -- the live numbers of a run are `value`, `ms_per_step`, `roofline.achieved`.
 PROFILED = {
-    ("changepoint", "f64"): {"kernel": "changepoint_kernel", "traffic": 27.56e6 + 0.31e6, "issue_slot_util": 0.832,
-                             "fp64_pipe_active": 0.279, "warp_inst_per_chain_step": 347, "source": "profiles/r1_changepoint.md"},
+    ("changepoint", "f64"): {"kernel": "changepoint_kernel<0,2,4>", "traffic": 27.58e6 + 0.07e6, "issue_slot_util": 0.673,
+                             "fp64_pipe_active": 0.219, "warp_inst_per_chain_step": 159, "source": "profiles/r1_changepoint_gl4.md"},
     ("gauss1000_mala", "f64"): {"kernel": "gemm_abt_kernel<1>", "traffic": 455.6e6 + 125.1e6, "tensor_pipe_active": 0.770,
                                 "source": "profiles/r1_gauss1000.md"},
-    ("gauss1000_mala", "tf32x3"): {"kernel": "tf32x3_gemm_kernel<1>", "traffic": 320.0e6 + 57.5e6, "tensor_pipe_active": 0.310,
+    ("gauss1000_mala", "tf32x3"): {"kernel": "tf32x3_gemm_kernel<1>", "traffic": 404.2e6 + 54.1e6, "tensor_pipe_active": 0.429,
                                    "source": "profiles/r1_gauss1000_tf32x3_gemm.md"},
     ("logistic_mala", "f64"): {"kernel": "lg_eval_kernel", "traffic": 811.2e6 + 4.7e6, "tensor_pipe_active": 0.636,
                                "source": "profiles/r1_logistic.md"},
@@ -59,13 +59,20 @@ PROFILED = {
 
 
 def load_peaks():
+    """MEASURED_PEAKS.json (driver-written: HBM copy GB/s, bf16 cuBLAS TF/s) plus the figures it does
+    not carry, measured here with the same method by scripts/peaks/measure_peaks.py and committed as
+    profiles/measured_peaks_extra.json (fp64 DFMA / DMMA, TF32 cuBLAS).  Fallbacks are B200_PROFILING.md's."""
+    d, src = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d, "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
-            "sm_max_mhz": 1965.0}, "fallback"
+        src = "measured"
+    x = os.path.join(ROOT, "profiles", "measured_peaks_extra.json")
+    if os.path.exists(x):
+        with open(x) as f:
+            d["extra"] = json.load(f)
+    return d, src
 
 
 # ----------------------------------------------------------------------------
@@ -320,29 +327,33 @@ def run_engine(args):
     ms_launch = ms / args.steps
     algo_flop = ALGO_FLOP[wl] * Kg * T                   # per launch, per GPU
     ach_tflops = algo_flop / (ms_launch * 1e-3) / 1e12
+    extra = peaks.get("extra", {})
+    computed_fp64 = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12      # fp64 FMA lanes x clock
     if wl in ("changepoint", "gauss2d_rw"):
-        peak = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12     # fp64 FMA lanes x clock
+        peak = extra.get("fp64_dfma_tflops", computed_fp64)
         roof = {"bound": "alu", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / peak, "traffic": None,
                 "note": "issue-bound fp64/integer kernel (SURVEY 8d: not HBM, not tensor); achieved = "
-                        "%.0f algorithmic op/chain-step x rate; peak = 148 SM x 64 fp64 FMA lanes x 2 x "
-                        "clocks.max.sm (computed, MEASURED_PEAKS.json has no ALU figure); see "
-                        "profiles/ for issue-slot utilisation" % ALGO_FLOP[wl]}
+                        "%.0f algorithmic op/chain-step x rate; peak = fp64 DFMA rate %s; the binding resource "
+                        "is the warp-instruction issue rate, see `profiled` (issue-slot utilisation from ncu)"
+                        % (ALGO_FLOP[wl], "measured by scripts/peaks (profiles/measured_peaks_extra.json)"
+                           if "fp64_dfma_tflops" in extra else "computed as 148 SM x 64 lanes x 2 x clocks.max.sm")}
     elif args.precision == "tf32x3":
-        peak = 0.5 * peaks["bf16_tflops_sustained" if ms > 2000 else "bf16_tflops"]
+        peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
         roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / peak, "traffic": None,
                 "note": "tcgen05 kind::tf32, 3 MMAs per product (fp32-accurate): achieved counts the ALGORITHMIC "
-                        "2 d^2 flop per chain-step once, so 1/3 is the ceiling of this scheme; peak = half the %s "
-                        "bf16 figure of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate; not measured "
-                        "separately)" % peak_src}
+                        "2 d^2 flop per chain-step once, so 1/3 is the ceiling of this scheme; peak = %s"
+                        % ("cuBLAS TF32 8192^3 measured by scripts/peaks (profiles/measured_peaks_extra.json)"
+                           if "tf32_cublas_tflops" in extra else "half the %s bf16 figure of MEASURED_PEAKS.json" % peak_src)}
     else:
-        peak = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        peak = extra.get("fp64_dmma_tflops", computed_fp64)
         roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / peak, "traffic": None,
-                "note": "fp64 path (DMMA/DFMA); peak = 148 SM x 64 fp64 FMA lanes x 2 x clocks.max.sm "
-                        "(computed; bf16 %s peak %.0f TF/s shown for context only)"
-                        % (peak_src, peaks["bf16_tflops"])}
+                "note": "fp64 tensor path (DMMA m8n8k4); peak = %s (bf16 %s peak %.0f TF/s for context only)"
+                        % ("mma.sync.m8n8k4.f64 rate measured by scripts/peaks (profiles/measured_peaks_extra.json)"
+                           if "fp64_dmma_tflops" in extra else "computed 148 SM x 64 lanes x 2 x clocks.max.sm",
+                           peak_src, peaks["bf16_tflops"])}
     prof = PROFILED.get((wl, args.precision))
     if prof:
         roof["traffic"] = prof["traffic"]
