@@ -207,6 +207,35 @@ def _changepoint_posterior_summary(name, nchains=48, seed0=7000):
         name, nchains, mk.mean(), mk.std() / np.sqrt(nchains), np.mean([r[2] for r in res])))
 
 
+def _cp_marginal_worker(seed):
+    """Thinned samples (every 400th state of steps 6000..10000) of one reference chain: sigma, k and the
+    predicted step height at two query points -- the raw material of the two-sample KS gate."""
+    R = refshim.load_reference()
+    pm, pprop, ptheta0, _ = port.make_changepoint_problem()
+    model = R.ChangepointRegression1D(pm.x, pm.y, pm.xmin, pm.xmax, pm.lamb, pm.kmax, pm.alpha, pm.beta)
+    prop = R.ChangepointRegression1DProp(model, pprop.hscale)
+    np.random.seed(seed)
+    s = R.Sampler(model, prop, R.ChangepointParams(ptheta0.cpx, ptheta0.cpv, ptheta0.sig))
+    with refshim.quiet(), np.errstate(all="ignore"):
+        s.run(10000, 6000, 400)
+    xq = np.array([pm.xmin + (pm.xmax - pm.xmin) * (q + 0.5) / 6.0 for q in (1, 4)])
+    sig = np.array([float(np.squeeze(t.sig)) for t in s._chain_thetas])
+    ks = np.array([len(t.cpx) for t in s._chain_thetas])
+    yq = np.array([np.asarray(t.cpv)[np.searchsorted(np.asarray(t.cpx), xq)] for t in s._chain_thetas])
+    return sig, ks, yq
+
+
+def _changepoint_marginal_samples(name, nchains=96, seed0=7000):
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(_cp_marginal_worker, [seed0 + i for i in range(nchains)])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"),
+                        sig=np.array([r[0] for r in res]), k=np.array([r[1] for r in res]),
+                        yq=np.array([r[2] for r in res]), query=np.array([1, 4]),
+                        burn=np.int64(6000), T=np.int64(10000), thin=np.int64(400), seed0=np.int64(seed0))
+    print("%-28s %d chains x %d thinned samples" % (name, nchains, len(res[0][0])))
+
+
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
@@ -244,6 +273,9 @@ def main():
         sys.exit("reference tree not available; fixtures can only be generated in "
                  "the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--only-cp-marginals" in sys.argv:          # (slow fixtures can be regenerated on their own)
+        _changepoint_marginal_samples("changepoint_marginals")
+        return
     R = refshim.load_reference()
     B = R.benchmarks
 
@@ -316,6 +348,7 @@ def main():
     # --- config 2: changepoint model + 4-way proposal
     _changepoint_fixture(R, "changepoint", nchains=4, T=3000, seed0=400)
     _changepoint_posterior_summary("changepoint_posterior")
+    _changepoint_marginal_samples("changepoint_marginals")
 
     # --- models/proposals the reference lacks, driven through the reference Sampler
     _portmodel_through_reference(R, "mala_logistic", "mala", 501)

@@ -222,12 +222,54 @@ lg_eval_kernel(LogisticState st, int fixed_slot) {
 }
 
 // ---------------------------------------------------------------------------------------
-// metric: Gm[c] += sum_i w_ic x_i x_i^T (likelihood part) for the PROPOSAL slot (or fixed).
-// CTA = 8 warps = 4 chains x 2 warps; warp h of a chain owns rows a in [32h, 32h+32).
-// Accumulated over splits with a deterministic two-pass (gm_part -> summed by the caller)
-// when nsplit > 1; here each CTA loops over ALL rows (nsplit = 1 for the metric).
+// metric: Gm[c] = sum_i w_ic x_i x_i^T (likelihood part) for the PROPOSAL slot (or fixed).
+// CTA = 8 warps = 4 chains x 2 warps.  G is symmetric: only the 36 8x8 tiles on or below the block
+// diagonal are accumulated (18 per warp: warp 0 owns row-blocks {0,3,4,7}, warp 1 {1,2,5,6}, so both
+// issue the same number of DMMAs) and the strict upper triangle is mirrored at the store.
+// Each CTA loops over ALL rows (X is L2-resident at config 5: 51 MB).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+template <int H> struct MetricTiles {
+    // row-blocks of warp H and the offset of each row-block's tiles in the accumulator array
+    static constexpr int rb(int q) { return H == 0 ? (q == 0 ? 0 : q == 1 ? 3 : q == 2 ? 4 : 7)
+                                                   : (q == 0 ? 1 : q == 1 ? 2 : q == 2 ? 5 : 6); }
+    static constexpr int off(int q) { return H == 0 ? (q == 0 ? 0 : q == 1 ? 1 : q == 2 ? 5 : 10)
+                                                    : (q == 0 ? 0 : q == 1 ? 2 : q == 2 ? 5 : 11); }
+};
+
+template <int H>
+__device__ __forceinline__ void metric_slab(double (&acc)[18][2], const double* __restrict__ xr, double w, int g) {
+    double b[8];
+#pragma unroll
+    for (int jb = 0; jb < 8; ++jb) b[jb] = xr[jb * 8 + g];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rb = MetricTiles<H>::rb(q);
+        const double a = xr[rb * 8 + g] * w;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb)
+            if (cb <= rb) dmma884(acc[MetricTiles<H>::off(q) + cb][0], acc[MetricTiles<H>::off(q) + cb][1], a, b[cb]);
+    }
+}
+
+template <int H>
+__device__ __forceinline__ void metric_store(const double (&acc)[18][2], double* __restrict__ G, int d, int g, int t) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rb = MetricTiles<H>::rb(q);
+        const int a = rb * 8 + g;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+            if (cb <= rb) {
+                const int b = cb * 8 + 2 * t;
+                const double v0 = acc[MetricTiles<H>::off(q) + cb][0], v1 = acc[MetricTiles<H>::off(q) + cb][1];
+                if (a < d && b < d) { G[a * d + b] = v0; if (cb < rb) G[b * d + a] = v0; }
+                if (a < d && b + 1 < d) { G[a * d + b + 1] = v1; if (cb < rb) G[(b + 1) * d + a] = v1; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
 lg_metric_kernel(LogisticState st, int fixed_slot) {
     extern __shared__ __align__(16) double sm[];
     const int ldt = st.ldt, dp = st.dp, d = st.d;
@@ -268,11 +310,9 @@ lg_metric_kernel(LogisticState st, int fixed_slot) {
         }
     };
 
-    double acc[4][8][2];                          // rows a = 32*half + 8*ia + g, cols b = 8*jb + 2t (+1)
+    double acc[18][2];                            // this warp's 18 lower-triangle tiles (MetricTiles)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int i = 0; i < 18; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 
     load_tile(0, 0);
     cp_async_commit();
@@ -299,34 +339,19 @@ lg_metric_kernel(LogisticState st, int fixed_slot) {
         const double* wc = ws + ch * BI;
 #pragma unroll 2
         for (int i4 = 0; i4 < BI; i4 += 4) {
-            // A[a][i] = x_ia w_i  (thread: a = base + g, i = i4 + t);  B[i][b] = x_ib (i = i4 + t, b = .. + g)
+            // A[a][i] = x_ia w_i  (thread: a = 8*rb + g, i = i4 + t);  B[i][b] = x_ib (i = i4 + t, b = 8*cb + g)
             const double* xr = xs + (i4 + t) * ldt;
             const double w = wc[i4 + t];
-            double a[4], b[8];
-#pragma unroll
-            for (int ia = 0; ia < 4; ++ia) a[ia] = xr[half * 32 + ia * 8 + g] * w;
-#pragma unroll
-            for (int jb = 0; jb < 8; ++jb) b[jb] = xr[jb * 8 + g];
-#pragma unroll
-            for (int ia = 0; ia < 4; ++ia)
-#pragma unroll
-                for (int jb = 0; jb < 8; ++jb) dmma884(acc[ia][jb][0], acc[ia][jb][1], a[ia], b[jb]);
+            if (half == 0) metric_slab<0>(acc, xr, w, g);
+            else metric_slab<1>(acc, xr, w, g);
         }
         __syncthreads();
     }
     cp_async_wait<0>();
     if (c < K) {
         double* G = st.Gm + c * (int64_t)d * d;
-#pragma unroll
-        for (int ia = 0; ia < 4; ++ia) {
-            const int a = half * 32 + ia * 8 + g;
-#pragma unroll
-            for (int jb = 0; jb < 8; ++jb) {
-                const int b = jb * 8 + 2 * t;
-                if (a < d && b < d) G[a * d + b] = acc[ia][jb][0];
-                if (a < d && b + 1 < d) G[a * d + b + 1] = acc[ia][jb][1];
-            }
-        }
+        if (half == 0) metric_store<0>(acc, G, d, g, t);
+        else metric_store<1>(acc, G, d, g, t);
     }
 }
 
