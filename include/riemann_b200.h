@@ -189,6 +189,11 @@ int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, i
  * enters the accept test reduced in fp64; |log-posterior error| <~ 5e-3 at d = 1000. */
 #define RMN_PREC_F64 0
 #define RMN_PREC_TF32X3 1
+/* RMN_PREC_TF32_METRIC: logistic model + simplified mMALA only -- the Fisher metric of the proposal,
+ * X^T diag(p(1-p)) X per chain, as ONE single-pass TF32 GEMM on tcgen05 (weights x Khatri-Rao table);
+ * log-posterior, gradient, Cholesky and the accept test stay fp64.  The metric only shapes the proposal
+ * and the same function theta -> G(theta) enters both proposal densities, so the sampler stays exact. */
+#define RMN_PREC_TF32_METRIC 2
 size_t rmn_sampler_workspace_bytes_ex(const rmn_model_t* m, const rmn_proposal_t* p, int64_t K, int precision);
 int rmn_sampler_create_ex(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
                           int64_t chain_offset, uint64_t seed, void* d_workspace,
@@ -249,6 +254,10 @@ int rmn_rng_draws(uint64_t seed, int64_t chain0, int64_t step, int64_t n, int nn
  * It is the GEMM behind the tf32x3 precision mode of the dense Gaussian sampler. */
 int rmn_tf32x3_gemm(int64_t M, int N, int K, const float* d_Ah, const float* d_Al, const float* d_Bh,
                     const float* d_Bl, float* d_C, void* stream);
+/* Single-pass TF32 product on the same kernel, validation entry: C[M][N] (fp32) ~= A B^T, A [M][K],
+ * B [N][K] fp32 (the tensor core drops the low 13 mantissa bits of each operand); K % 32 == 0, N % 4 == 0.
+ * It is the GEMM behind RMN_PREC_TF32_METRIC. */
+int rmn_tf32_gemm(int64_t M, int N, int K, const float* d_A, const float* d_B, float* d_C, void* stream);
 
 #ifdef __cplusplus
 }

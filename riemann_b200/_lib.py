@@ -20,7 +20,7 @@ CP_NSLOT = 8 + CP_LANES
 CP_NDIAG = 8
 DIAG_HDR = 6
 SMALL_D_MAX = 8
-PRECISIONS = {"f64": 0, "tf32x3": 1}
+PRECISIONS = {"f64": 0, "tf32x3": 1, "tf32-metric": 2}
 
 
 class Inject(C.Structure):
@@ -82,6 +82,7 @@ SIGNATURES = {
     "rmn_philox_raw": (_I, [_L, _P, _P, _P, _P]),
     "rmn_rng_draws": (_I, [C.c_uint64, _L, _L, _L, _I, _P, _P, _P]),
     "rmn_tf32x3_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "rmn_tf32_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -269,6 +269,13 @@ static SamplerImpl* make_impl(rmn_sampler* s, int* rc) {
         return nullptr;
     }
     if (s->precision == RMN_PREC_TF32X3) return make_dense_tf32_sampler(s);
+    if (s->precision == RMN_PREC_TF32_METRIC) {
+        if (m->kind != RMN_MODEL_LOGISTIC || p->kind != RMN_PROP_MMALA) {
+            rmn_set_error("precision tf32-metric needs the logistic model with the simplified mMALA proposal");
+            return nullptr;
+        }
+        return make_logistic_sampler(s);
+    }
     if (s->precision != RMN_PREC_F64) {
         rmn_set_error("unknown precision mode %d", s->precision);
         *rc = RMN_ERR_PARAM;

@@ -21,7 +21,20 @@
 //   chain, w recomputed in-kernel from z.
 // mm_geometry (inside the finish/propose kernel): per-chain Cholesky, log-determinant and
 //   triangular solves in shared memory, one warp per chain.
+//
+// Precision mode RMN_PREC_TF32_METRIC (mMALA only): the Fisher metric is a dense contraction over the
+// data rows, G_c[a][b] = sum_i w_ic x_ia x_ib, i.e. ONE GEMM  Gp[K][d(d+1)/2] = W[K][N] . KR[d(d+1)/2][N]^T
+// with the Khatri-Rao table KR[(a,b)][i] = x_ia x_ib built once per sampler and the weights
+// W[c][i] = p(1-p) written by lg_eval_kernel (which has z in registers anyway).  It runs on the tcgen05
+// tensor cores in single-pass TF32 (tc_gemm.cu, PASSES = 1).  The metric only shapes the proposal: the
+// SAME deterministic function theta -> G~(theta) enters the forward and the reverse proposal density,
+// and the log-posterior / gradient stay fp64, so the chain still targets the exact posterior.
 #include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace tc {
+int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+}
 
 namespace {
 
@@ -70,7 +83,21 @@ struct LogisticState {
     double* Lc;      // [2][K][d][d] Cholesky factors (current / proposal slot follows cur)
     double* logdet;  // [2][K]
     double* nat;     // [2][K][dp]   G^-1 grad
+    // mMALA, RMN_PREC_TF32_METRIC (all null / 0 otherwise)
+    float* W;        // [K][Npad]    p(1-p) of the pending proposal, written by lg_eval_kernel
+    float* KR;       // [NP][Npad]   x_ia x_ib for a >= b, pair index a(a+1)/2 + b
+    float* Gp;       // [K][NP]      packed lower triangle of the metric (likelihood part)
+    int64_t Npad; int NP;
 };
+
+// likelihood part of the metric entry (a, b) of chain r, from whichever representation is live
+__device__ __forceinline__ double metric_entry(const LogisticState& st, int64_t r, int a, int b) {
+    if (st.Gp) {
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        return (double)st.Gp[r * st.NP + hi * (hi + 1) / 2 + lo];
+    }
+    return st.Gm[r * (int64_t)st.d * st.d + a * st.d + b];
+}
 
 // ---------------------------------------------------------------------------------------
 // eval: llpart[split][c], gpart[split][c][:] for the chains' PROPOSAL slots (slot = cur^1),
@@ -176,6 +203,8 @@ lg_eval_kernel(LogisticState st, int fixed_slot) {
                 const double sp = fmax(zz, 0.0) + log(opx);
                 ll += ok ? (yv * zz - sp) : 0.0;
                 z[j][e] = ok ? (yv - p) : 0.0;
+                if (st.W && ok && c0 + cw * 8 + g < K)
+                    st.W[(c0 + cw * 8 + g) * st.Npad + (r0 + i)] = (float)((ex * inv) * inv);   // p(1-p)
             }
         }
         // ---- product 2: G[c][k] += sum_i R[c][i] X[i][k]   (contraction rows permuted, see perm8)
@@ -355,6 +384,30 @@ lg_metric_kernel(LogisticState st, int fixed_slot) {
     }
 }
 
+// Khatri-Rao table for the tensor-core metric: KR[a(a+1)/2 + b][i] = x_ia x_ib (fp32), a >= b.
+// A block stages 32 data rows in shared memory; each warp then writes one 128-byte line per pair.
+__global__ void __launch_bounds__(256)
+lg_build_kr_kernel(LogisticState st) {
+    extern __shared__ __align__(16) double sm[];                  // [32][d + 1]
+    const int d = st.d, ld = d + 1;
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    for (int q = threadIdx.x; q < 32 * d; q += blockDim.x) {
+        const int r = q / d, k = q % d;
+        sm[r * ld + k] = (i0 + r < st.N) ? st.X[(i0 + r) * d + k] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int npair = d * (d + 1) / 2;
+    if (i0 + lane >= st.Npad) return;
+    const double* xr = sm + lane * ld;
+    int a = 0, base = 0;                                           // base = a(a+1)/2
+    for (int pr = warp; pr < npair; pr += nw) {
+        while (pr >= base + a + 1) { base += a + 1; ++a; }
+        const int b = pr - base;
+        st.KR[(int64_t)pr * st.Npad + i0 + lane] = (float)(xr[a] * xr[b]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // finish / propose, one warp per chain.
 // ---------------------------------------------------------------------------------------
@@ -462,10 +515,9 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             lqr = 0.5 * (k1 - st.k0[r]);                                  // hamiltonian.py:89
         } else {
             // geometry of the proposal: L' = chol(G'), logdet', nat' = G'^-1 grad'
-            const double* Gm = st.Gm + r * (int64_t)d * d;
             for (int q = lane; q < d * d; q += 32) {
                 const int a = q / d, b = q % d;
-                Lw[q] = Gm[q] + ((a == b) ? pvinv : 0.0);
+                Lw[q] = metric_entry(st, r, a, b) + ((a == b) ? pvinv : 0.0);
             }
             __syncwarp();
             const double ld = warp_cholesky(Lw, d, lane);
@@ -616,8 +668,7 @@ lg_adopt_kernel(LogisticState st) {
     if (MMALA) {
         double* Lw = sm + (size_t)wib * (d * d + dp);
         double* v1 = Lw + d * d;
-        const double* Gm = st.Gm + r * (int64_t)d * d;
-        for (int q = lane; q < d * d; q += 32) Lw[q] = Gm[q] + ((q / d == q % d) ? pvinv : 0.0);
+        for (int q = lane; q < d * d; q += 32) Lw[q] = metric_entry(st, r, q / d, q % d) + ((q / d == q % d) ? pvinv : 0.0);
         __syncwarp();
         const double ld = warp_cholesky(Lw, d, lane);
         for (int j = lane; j < d; j += 32) v1[j] = gr[j];
@@ -710,10 +761,20 @@ struct LogisticSampler : SamplerImpl {
     rmn_sampler* s;
     LogisticState st{};
     bool mmala;
+    bool tf32m;                 // RMN_PREC_TF32_METRIC: tcgen05 metric GEMM instead of lg_metric_kernel
+    tc::GemmMaps maps;
     explicit LogisticSampler(rmn_sampler* s_) : s(s_) {
         fill_geometry(st, s->model, s->K);
         mmala = (s->prop->kind == RMN_PROP_MMALA);
+        tf32m = mmala && s->precision == RMN_PREC_TF32_METRIC;
+        if (tf32m) {
+            st.Npad = (st.N + 31) / 32 * 32;
+            st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
+        }
     }
+    size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * 4); }
+    size_t w_bytes() const { return align256((size_t)st.K * st.Npad * 4); }
+    size_t gp_bytes() const { return align256((size_t)st.K * st.NP * 4); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 8); }
     size_t eval_smem() const { return eval_smem_bytes(st.ldt); }
     size_t metric_smem() const { return ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8; }
@@ -724,6 +785,7 @@ struct LogisticSampler : SamplerImpl {
                    align256((size_t)st.nsplit * K * st.dp * 8) + 7 * align256(K * 8) + align256(K * 4) +
                    2 * align256(ND_MAX * K * 8) + 256;
         if (mmala) n += 3 * align256(K * st.d * st.d * 8) + 2 * align256(K * 8) + 2 * rowb();
+        if (tf32m) n += kr_bytes() + w_bytes() + gp_bytes();
         return n;
     }
     int bind(void* ws) override {
@@ -750,7 +812,20 @@ struct LogisticSampler : SamplerImpl {
             st.logdet = (double*)p; p += 2 * align256(K * 8);
             st.nat = (double*)p; p += 2 * rowb();
         }
+        if (tf32m) {
+            st.KR = (float*)p; p += kr_bytes();
+            st.W = (float*)p; p += w_bytes();
+            st.Gp = (float*)p; p += gp_bytes();
+        }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        if (tf32m) {
+            const size_t ksm = (size_t)32 * (st.d + 1) * 8;
+            lg_build_kr_kernel<<<(unsigned)(st.Npad / 32), 256, ksm>>>(st);
+            RMN_KERNEL_CHECK();
+            if (int rc = tc::make_tmap_2d(&maps.ah, st.W, (uint64_t)st.K, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TM)) return rc;
+            if (int rc = tc::make_tmap_2d(&maps.bh, st.KR, (uint64_t)st.NP, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TN)) return rc;
+            maps.al = maps.ah; maps.bl = maps.bh;
+        }
         RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem()));
         if (mmala) {
             RMN_CUDA(cudaFuncSetAttribute(lg_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)metric_smem()));
@@ -769,7 +844,10 @@ struct LogisticSampler : SamplerImpl {
         dim3 grid((unsigned)((st.K + BC - 1) / BC), st.nsplit);
         lg_eval_kernel<<<grid, EVAL_THREADS, eval_smem(), stream>>>(st, fixed_slot);
         RMN_KERNEL_CHECK(); launches++;
-        if (mmala) {
+        if (tf32m) {
+            if (int rc = tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
+            launches++;
+        } else if (mmala) {
             lg_metric_kernel<<<(unsigned)((st.K + 3) / 4), 256, metric_smem(), stream>>>(st, fixed_slot);
             RMN_KERNEL_CHECK(); launches++;
         }

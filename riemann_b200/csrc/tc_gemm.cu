@@ -61,10 +61,18 @@ enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 //   TMA warp   --full/empty[STAGES]-->   MMA thread   --tmem_full/tmem_empty[ACC_STAGES]-->   8 epilogue warps
 // The accumulator is double buffered in TMEM (2 x 256 columns), so the epilogue of tile i runs while the
 // tensor cores work on tile i+1.
-template <int EPI>
+// PASSES = 3: fp32-accurate split product (Ah Bh + Ah Bl + Al Bh), 2 stages of 96 KB.
+// PASSES = 1: plain TF32 product of the "hi" maps only (the Fisher-metric GEMM of the logistic sampler,
+//             where the product only shapes a proposal), 4 stages of 48 KB so the TMA latency stays hidden
+//             behind one third of the tensor work per stage.
+template <int EPI, int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
                    int ldc, MalaEpi ep) {
+    constexpr int STAGES = (PASSES == 1) ? 4 : tc::STAGES;
+    constexpr int STAGE_BYTES = (PASSES == 1) ? (A_BYTES + B_BYTES) : tc::STAGE_BYTES;
+    constexpr int OFF_BH = (PASSES == 1) ? A_BYTES : 2 * A_BYTES;
+    static_assert(STAGES * STAGE_BYTES <= tc::STAGES * tc::STAGE_BYTES, "stage ring must fit SMEM_BYTES");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -80,8 +88,8 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     const int64_t num_tiles = m_tiles * n_tiles;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.al);
-        tma_prefetch_desc(&maps.bh); tma_prefetch_desc(&maps.bl);
+        tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.bh);
+        if (PASSES == 3) { tma_prefetch_desc(&maps.al); tma_prefetch_desc(&maps.bl); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -105,9 +113,11 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
                 tma_load_2d(st, &maps.ah, &full[s], kb * TK, m0);
-                tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, m0);
-                tma_load_2d(st + 2 * A_BYTES, &maps.bh, &full[s], kb * TK, n0);
-                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.bl, &full[s], kb * TK, n0);
+                tma_load_2d(st + OFF_BH, &maps.bh, &full[s], kb * TK, n0);
+                if (PASSES == 3) {
+                    tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, m0);
+                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.bl, &full[s], kb * TK, n0);
+                }
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -126,14 +136,16 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t dah = umma_desc_kmajor_sw128(sa);
                 const uint64_t dal = umma_desc_kmajor_sw128(sa + A_BYTES);
-                const uint64_t dbh = umma_desc_kmajor_sw128(sa + 2 * A_BYTES);
+                const uint64_t dbh = umma_desc_kmajor_sw128(sa + OFF_BH);
                 const uint64_t dbl = umma_desc_kmajor_sw128(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int k = 0; k < TK / UK; ++k) {
                     const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);   // +32 bytes per K step, 16-byte units
                     umma_tf32(tacc, dah + adv, dbh + adv, idesc, (kb | k) != 0);
-                    umma_tf32(tacc, dah + adv, dbl + adv, idesc, 1);
-                    umma_tf32(tacc, dal + adv, dbh + adv, idesc, 1);
+                    if (PASSES == 3) {
+                        umma_tf32(tacc, dah + adv, dbl + adv, idesc, 1);
+                        umma_tf32(tacc, dal + adv, dbh + adv, idesc, 1);
+                    }
                 }
                 umma_commit(&empty[s]);                 // frees the stage when these MMAs retire
             }
@@ -162,7 +174,8 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 if (EPI == EPI_PLAIN) {
                     float4* dst = reinterpret_cast<float4*>(C + m * ldc + n);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 4; ++i)
+                        if (n + 4 * i < N) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 } else {
                     const size_t off = (size_t)m * ldc + n;
                     float4* dst = reinterpret_cast<float4*>(ep.vp + off);
@@ -212,7 +225,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 }
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
-                         cudaStream_t st) {
+                         cudaStream_t st, int passes = 3) {
     if (Kdim % TK != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
     const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM);
     static int sms = 0;
@@ -220,18 +233,23 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));          // persistent: one CTA per SM
     static bool attr = false;
     if (!attr) {
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    if (ep) tf32x3_gemm_kernel<EPI_MALA><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep);
-    else tf32x3_gemm_kernel<EPI_PLAIN><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{});
+    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep);
+    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{});
+    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{});
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
 
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st);
+}
+int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 1);
 }
 int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
                 const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
@@ -241,6 +259,19 @@ int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const 
 }
 
 }  // namespace tc
+
+// Validation entry of the single-pass mode: C[M][N] (fp32, ld = N) ~= A B^T with TF32 operands
+// (tcgen05.mma.kind::tf32 reads fp32 and drops the low 13 mantissa bits); A is [M][K], B is [N][K].
+extern "C" int rmn_tf32_gemm(int64_t M, int N, int Kdim, const float* d_A, const float* d_B, float* d_C, void* stream) {
+    RMN_REQUIRE(M >= 1 && N >= 1 && Kdim >= 32 && Kdim % 32 == 0 && N % 4 == 0, "rmn_tf32_gemm: bad shape");
+    RMN_REQUIRE(d_A && d_B && d_C, "rmn_tf32_gemm: null pointer");
+    tc::GemmMaps maps;
+    int rc;
+    if ((rc = tc::make_tmap_2d(&maps.ah, d_A, M, Kdim, Kdim, tc::TM))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bh, d_B, N, Kdim, Kdim, tc::TN))) return rc;
+    maps.al = maps.ah; maps.bl = maps.bh;
+    return tc::launch_plain_tf32(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
+}
 
 // Validation entry: C[M][N] (fp32, ld = N) ~= (Ah + Al)(Bh + Bl)^T; A* are [M][K], B* are [N][K], fp32, K % 32 == 0.
 extern "C" int rmn_tf32x3_gemm(int64_t M, int N, int Kdim, const float* d_Ah, const float* d_Al, const float* d_Bh,

@@ -145,3 +145,97 @@ def test_config5_shape_self_consistency():
     assert np.all(np.linalg.eigvalsh(G[1]) > 0)
     dg = s.diagnostics(allreduce=False)
     assert dg["accept_rate"] > 0.3
+
+
+# ---------------------------------------------------------------------------------------
+# precision="tf32-metric": the Fisher metric of the mMALA proposal as one tcgen05 TF32 GEMM
+# ---------------------------------------------------------------------------------------
+def test_tf32_metric_is_a_deterministic_function_of_theta():
+    """Detailed balance needs G~(theta) to be ONE function of theta: chains holding the same state and
+    fed the same noise must produce bit-identical proposals wherever they sit in the GEMM's tiling
+    (K = 300 spans three 128-row tiles), and repeated launches must agree bit for bit."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import SimplifiedMMALA
+    N, d = 3000, 20
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=4)
+    dm, _ = _models(X, y, pv)
+    K, T = 300, 4
+    rng = np.random.default_rng(1)
+    xi = np.repeat(rng.standard_normal((T, 1, d)), K, axis=1)
+    u = np.repeat(rng.uniform(size=(T, 1)), K, axis=1)
+    runs = []
+    for _ in range(2):
+        s = Sampler(dm, SimplifiedMMALA(0.7, dm), np.repeat(ts[None], K, 0), precision="tf32-metric")
+        ex = s.run_injected(xi=xi, u=u)
+        th = np.asarray(s._chain_thetas)                       # [T+1][K][d]
+        assert np.all(th == th[:, :1]) and np.all(ex["prop_logpost"] == ex["prop_logpost"][:, :1])
+        runs.append((th.copy(), np.asarray(s._chain_logpost).copy(), ex["accepted"].copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert runs[0][2].any()                                   # the chain moves
+
+
+def test_tf32_metric_proposals_track_the_fp64_metric():
+    """Same states, same noise: the proposal built with the TF32 metric differs from the fp64 one by the
+    metric's rounding only (<~ 1e-3 relative in G, so ~1e-3 of the step), and its log-posterior -- still
+    evaluated in fp64 -- equals a fresh fp64 evaluation at the device's own proposed point."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import SimplifiedMMALA
+    N, d = 5000, 16
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=9)
+    dm, om = _models(X, y, pv)
+    K = 70
+    rng = np.random.default_rng(2)
+    th0 = ts[None] + 0.05 * rng.standard_normal((K, d))
+    xi, u = rng.standard_normal((1, K, d)), np.ones((1, K))          # u = 1: nothing is accepted
+    out = {}
+    for prec in ("f64", "tf32-metric"):
+        s = Sampler(dm, SimplifiedMMALA(0.8, dm), th0, precision=prec)
+        out[prec] = s.run_injected(xi=xi, u=u)
+    pa, pb = out["f64"]["prop_theta"][0], out["tf32-metric"]["prop_theta"][0]
+    step = np.linalg.norm(pa - th0, axis=1)
+    assert np.all(np.linalg.norm(pa - pb, axis=1) < 5e-3 * step)
+    assert np.any(pa != pb)
+    want = np.array([om.log_posterior(t) for t in pb])
+    assert relerr(out["tf32-metric"]["prop_logpost"][0], want) < 1e-9
+    assert np.max(np.abs(out["tf32-metric"]["logqratio"][0] - out["f64"]["logqratio"][0])) < 0.05
+
+
+def test_tf32_metric_chain_targets_the_same_posterior():
+    """Distributional gate: KS of every marginal against a long thinned oracle chain (fp64 metric)."""
+    from scipy import stats
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import SimplifiedMMALA
+    N, d = 400, 5
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=21)
+    dm, om = _models(X, y, pv)
+    np.random.seed(5)
+    o = port.Sampler(om, port.SimplifiedMMALA(0.9, om), ts.copy())
+    o.run(13000, 1000, 20)
+    och = np.array(o._chain_thetas)
+    acc = {}
+    for prec in ("tf32-metric", "f64"):
+        s = Sampler(dm, SimplifiedMMALA(0.9, dm), ts.copy(), K=2048, seed=23, precision=prec)
+        s.run(300, trace=False)
+        s.reset_diagnostics()
+        s.run(300, trace=False)
+        acc[prec] = s.diagnostics(allreduce=False)["accept_rate"]
+        th = np.asarray(s._chain_thetas[-1])
+        for j in range(d):
+            assert stats.ks_2samp(th[:, j], och[:, j]).pvalue > 1e-3
+        if prec == "tf32-metric":
+            th_t, lp_t = th, np.asarray(s._chain_logpost[-1])
+    assert abs(acc["tf32-metric"] - acc["f64"]) < 0.01           # the rounded metric costs no acceptance
+    th, lp = th_t, lp_t
+    assert relerr(lp, dm.log_posterior_batch(th).cpu().numpy()) < 1e-10
+
+
+def test_tf32_metric_rejects_other_models():
+    from riemann_b200 import Sampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    from riemann_b200.sampling_errors import ParameterError
+    with pytest.raises((ParameterError, RuntimeError)):
+        Sampler(benchmarks.benchmark_gauss2d_corr, MetropolisRandomWalk(np.eye(2)), np.ones(2), precision="tf32-metric")

@@ -35,3 +35,23 @@ def test_tf32x3_gemm_matches_fp64(M, N, K):
     assert np.all(np.isfinite(got))
     assert err3 < 3e-6, err3
     assert err1 > 20 * err3                      # one TF32 pass is far worse: the split matters
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 2080, 4096), (70, 12, 1024)])
+def test_single_pass_tf32_gemm(M, N, K):
+    """rmn_tf32_gemm (PASSES = 1, 4-stage ring): TF32-level accuracy -- each operand loses its low
+    13 mantissa bits (2^-11 relative), the accumulation is fp32."""
+    import torch
+    from riemann_b200 import _lib
+    rng = np.random.default_rng(M * 7 + N + K)
+    A = rng.uniform(0.0, 0.25, (M, K)).astype(np.float32)            # like the p(1-p) weights
+    B = (rng.standard_normal((N, K)) * 0.1).astype(np.float32)
+    dA, dB = torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda")
+    C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().rmn_tf32_gemm(M, N, K, _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(C), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = C.cpu().numpy().astype(np.float64)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - ref) / scale) < 1.5e-3
