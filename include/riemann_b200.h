@@ -259,6 +259,10 @@ int rmn_tf32x3_gemm(int64_t M, int N, int K, const float* d_Ah, const float* d_A
  * It is the GEMM behind RMN_PREC_TF32_METRIC. */
 int rmn_tf32_gemm(int64_t M, int N, int K, const float* d_A, const float* d_B, float* d_C, void* stream);
 
+/* The logistic likelihood's pointwise stage (riemann_b200/csrc/logistic_math.cuh), validation entry:
+ * p[i] = sigmoid(z[i]), sp[i] = softplus(z[i]), pq[i] = p (1 - p), fp64, |error| <~ 2e-16 absolute. */
+int rmn_logistic_math(int64_t n, const double* d_z, double* d_p, double* d_sp, double* d_pq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

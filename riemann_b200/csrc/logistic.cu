@@ -31,12 +31,26 @@
 // and the log-posterior / gradient stay fp64, so the chain still targets the exact posterior.
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "logistic_math.cuh"
 
 namespace tc {
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 }
 
 namespace {
+
+__device__ double g_lg_tab[lgmath::TAB_DOUBLES];     // sigmoid/softplus tables (logistic_math.cuh)
+static int lg_tables_ready() {
+    static int done[64] = {0};                        // per device
+    int dev = 0;
+    RMN_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return RMN_OK;
+    double h[lgmath::TAB_DOUBLES];
+    lgmath::fill_tables(h);
+    RMN_CUDA(cudaMemcpyToSymbol(g_lg_tab, h, sizeof(h)));
+    if (dev < 64) done[dev] = 1;
+    return RMN_OK;
+}
 
 constexpr int BC = 64;        // chains per CTA (eval)
 constexpr int BI = 64;        // data rows per tile
@@ -68,6 +82,7 @@ __device__ __forceinline__ int perm8(int g) { return (g < 4) ? g : (g ^ 1); }   
 
 struct LogisticState {
     int64_t K, N; int d, dp, ldt, nsplit; int64_t rows_per_split;
+    int eval_tab_off;   // offset (doubles) of the sigmoid/softplus tables in lg_eval_kernel's shared memory
     double pv;
     const double* X; const double* y;
     double* Th;      // [2][K][dp]  two state slots per chain
@@ -113,9 +128,11 @@ lg_eval_kernel(LogisticState st, int fixed_slot) {
     double* Ts = sm;                              // [BC][ldt]
     double* Xs = Ts + BC * ldt;                   // [2][BI][ldt]
     double* ys = Xs + 2 * BI * ldt;               // [2][BI]
+    double* tab = sm + st.eval_tab_off;           // sigmoid/softplus tables, behind everything else
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int cw = warp & 7, rh = warp >> 3;
+    for (int q = tid; q < lgmath::TAB_DOUBLES; q += EVAL_THREADS) tab[q] = g_lg_tab[q];
     const int64_t K = st.K;
     const int64_t c0 = (int64_t)blockIdx.x * BC;
     const int split = blockIdx.y;
@@ -186,8 +203,7 @@ lg_eval_kernel(LogisticState st, int fixed_slot) {
             for (int j = 0; j < 4; ++j) dmma884(z[j][0], z[j][1], a, xb[j * 8 * ldt + k4]);
         }
         // ---- pointwise: p = sigmoid(z), r = y - p, ll += y z - softplus(z)
-        //      softplus = max(z,0) + log(1 + e), e = exp(-|z|) in (0,1]: log(1+e) instead of
-        //      log1p(e) costs 1e-16 ABSOLUTE error on an O(1) term and ~30 fewer instructions
+        //      table-driven fp64 exp / log / reciprocal sharing their range reduction (logistic_math.cuh)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -196,15 +212,12 @@ lg_eval_kernel(LogisticState st, int fixed_slot) {
                 const bool ok = (r0 + i) < r_end;
                 const double yv = yb[i];
                 const double zz = z[j][e];
-                const double ex = exp(-fabs(zz));
-                const double opx = 1.0 + ex;
-                const double inv = 1.0 / opx;
-                const double p = (zz >= 0.0) ? inv : ex * inv;
-                const double sp = fmax(zz, 0.0) + log(opx);
+                double p, sp, pq;
+                lgmath::sigmoid_softplus(zz, tab, p, sp, pq);
                 ll += ok ? (yv * zz - sp) : 0.0;
                 z[j][e] = ok ? (yv - p) : 0.0;
                 if (st.W && ok && c0 + cw * 8 + g < K)
-                    st.W[(c0 + cw * 8 + g) * st.Npad + (r0 + i)] = (float)((ex * inv) * inv);   // p(1-p)
+                    st.W[(c0 + cw * 8 + g) * st.Npad + (r0 + i)] = (float)pq;                    // p(1-p)
             }
         }
         // ---- product 2: G[c][k] += sum_i R[c][i] X[i][k]   (contraction rows permuted, see perm8)
@@ -730,11 +743,12 @@ __global__ void lg_point_out_kernel(LogisticState st, int which, double* out, do
 
 // dynamic shared memory of lg_eval_kernel: Theta + two X tiles + y, and at least the
 // [8][32][33] combine buffer that overlays the X tiles at the end
-static size_t eval_smem_bytes(int ldt) {
+static size_t eval_tab_offset(int ldt) {
     const size_t tiles = (size_t)2 * BI * ldt + 2 * BI;
     const size_t red = (size_t)8 * 32 * 33;
-    return ((size_t)BC * ldt + (tiles > red ? tiles : red)) * 8;
+    return ((size_t)BC * ldt + (tiles > red ? tiles : red) + 1) & ~(size_t)1;     // 16-byte aligned
 }
+static size_t eval_smem_bytes(int ldt) { return (eval_tab_offset(ldt) + lgmath::TAB_DOUBLES) * 8; }
 
 static int choose_nsplit(int64_t K, int64_t N) {
     const int64_t nblocks = (K + BC - 1) / BC;
@@ -755,6 +769,7 @@ static void fill_geometry(LogisticState& st, const rmn_model* m, int64_t K) {
     st.rows_per_split = (per + BI - 1) / BI * BI;
     st.pv = m->prior_var;
     st.X = m->d_X; st.y = m->d_y;
+    st.eval_tab_off = (int)eval_tab_offset(st.ldt);
 }
 
 struct LogisticSampler : SamplerImpl {
@@ -818,6 +833,7 @@ struct LogisticSampler : SamplerImpl {
             st.Gp = (float*)p; p += gp_bytes();
         }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        if (int rc = lg_tables_ready()) return rc;
         if (tf32m) {
             const size_t ksm = (size_t)32 * (st.d + 1) * 8;
             lg_build_kr_kernel<<<(unsigned)(st.Npad / 32), 256, ksm>>>(st);
@@ -978,6 +994,7 @@ int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta
     st.k0 = (double*)p; p += sz_s;
     st.epsrow = (double*)p; p += sz_s;
     double* scratch = nullptr;
+    if (int rc = lg_tables_ready()) return rc;
     const size_t esm = eval_smem_bytes(st.ldt);
     const size_t msm = ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8;
     RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
@@ -998,5 +1015,30 @@ int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta
         rmn_set_error("logistic_pointwise: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
         return RMN_ERR_CUDA;
     }
+    return RMN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// validation entry for logistic_math.cuh: p = sigmoid(z), sp = softplus(z), pq = p(1-p)
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void lg_math_kernel(int64_t n, const double* __restrict__ z, double* p, double* sp, double* pq) {
+    __shared__ double tab[lgmath::TAB_DOUBLES];
+    for (int q = threadIdx.x; q < lgmath::TAB_DOUBLES; q += blockDim.x) tab[q] = g_lg_tab[q];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a, b, c;
+    lgmath::sigmoid_softplus(z[i], tab, a, b, c);
+    p[i] = a; sp[i] = b; pq[i] = c;
+}
+}  // namespace
+
+extern "C" int rmn_logistic_math(int64_t n, const double* d_z, double* d_p, double* d_sp, double* d_pq, void* stream) {
+    RMN_REQUIRE(n >= 0 && d_z && d_p && d_sp && d_pq, "rmn_logistic_math: bad argument");
+    if (n == 0) return RMN_OK;
+    if (int rc = lg_tables_ready()) return rc;
+    lg_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, d_z, d_p, d_sp, d_pq);
+    RMN_KERNEL_CHECK();
     return RMN_OK;
 }

@@ -239,3 +239,33 @@ def test_tf32_metric_rejects_other_models():
     from riemann_b200.sampling_errors import ParameterError
     with pytest.raises((ParameterError, RuntimeError)):
         Sampler(benchmarks.benchmark_gauss2d_corr, MetropolisRandomWalk(np.eye(2)), np.ones(2), precision="tf32-metric")
+
+
+def test_fast_sigmoid_softplus_accuracy():
+    """logistic_math.cuh (table-driven fp64 exp / log / reciprocal) against 80-bit long double."""
+    import torch
+    from riemann_b200 import _lib
+    rng = np.random.default_rng(0)
+    z = np.concatenate([rng.standard_normal(200000) * 3, rng.uniform(-70, 70, 100000), np.linspace(-1e-3, 1e-3, 2001),
+                        [0.0, -0.0, 1e-300, -1e-300, 36.0, -36.0, 64.0, -64.0, 700.0, -700.0, 1e6, -1e6, np.inf, -np.inf]])
+    dz = torch.as_tensor(z, device="cuda")
+    out = [torch.empty_like(dz) for _ in range(3)]
+    _lib.check(_lib.load().rmn_logistic_math(len(z), _lib.ptr(dz), *[_lib.ptr(o) for o in out], _lib.stream_ptr()))
+    p, sp, pq = (o.cpu().numpy() for o in out)
+    zl = z.astype(np.longdouble)
+    with np.errstate(all="ignore"):
+        el = np.exp(-np.abs(zl))
+        p_ref = np.where(zl >= 0, 1 / (1 + el), el / (1 + el))
+        sp_ref = np.maximum(zl, 0) + np.log1p(el)
+        pq_ref = el / (1 + el) ** 2
+    fin = np.isfinite(z)
+    assert np.max(np.abs(p[fin] - p_ref[fin])) < 3e-16
+    assert np.max(np.abs(sp[fin] - sp_ref[fin]) / np.maximum(1.0, np.abs(sp_ref[fin]).astype(np.float64))) < 4e-16
+    assert np.max(np.abs(pq[fin] - pq_ref[fin])) < 2e-16
+    small = fin & (np.abs(z) < 30)
+    assert np.max(np.abs(p[small] / p_ref[small].astype(np.float64) - 1)) < 1e-15        # relative, both tails
+    assert p[-2] == 1.0 and sp[-2] == np.inf and 0.0 <= p[-1] < 1e-27 and 0.0 <= sp[-1] < 1e-27   # +-inf (|z| clamped at 64)
+    dn = torch.as_tensor(np.array([np.nan]), device="cuda")
+    o1 = [torch.empty_like(dn) for _ in range(3)]
+    _lib.check(_lib.load().rmn_logistic_math(1, _lib.ptr(dn), *[_lib.ptr(o) for o in o1], _lib.stream_ptr()))
+    assert all(np.isnan(o.cpu().numpy()[0]) for o in o1)
