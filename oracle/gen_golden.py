@@ -236,6 +236,24 @@ def _changepoint_marginal_samples(name, nchains=96, seed0=7000):
     print("%-28s %d chains x %d thinned samples" % (name, nchains, len(res[0][0])))
 
 
+def _n1_dense_fixtures(R):
+    """"next" row N1 on the dense (d > 8) device path: leapfrog with Nsteps > 1 (hamiltonian.py:13-52),
+    fixed and adaptive step size, on a d = 12 Gaussian with a dense covariance and on benchmarks.py:25-26."""
+    rng = np.random.Generator(np.random.Philox(7))
+    rng.standard_normal((5, 5)); rng.standard_normal(5)              # same stream position as main()
+    A12 = rng.standard_normal((12, 12))
+    C12 = A12 @ A12.T / 12 + 0.2 * np.eye(12)
+    mu12 = rng.standard_normal(12)
+    g12 = R.MultiGaussianDist(mu12, C12)
+    _vector_fixture(R, "hmc4_gauss12d", g12, R.VanillaHMC(0.15, 4, g12.grad_log_likelihood), mu12 + 0.4, 500, 401,
+                    extra=dict(eps=np.float64(0.15), nsteps=np.int64(4), mu=mu12, C=C12))
+    _vector_fixture(R, "adapthmc3_gauss12d", g12, R.AdaptScaleHMC(0.1, 3, g12.grad_log_likelihood), mu12 - 0.3, 800, 402,
+                    extra=dict(eps=np.float64(0.1), nsteps=np.int64(3), mu=mu12, C=C12), track_scale=True)
+    g100 = R.benchmarks.benchmark_gauss100d_corr
+    _vector_fixture(R, "hmc5_gauss100d", g100, R.VanillaHMC(0.1, 5, g100.grad_log_likelihood), np.zeros(100), 200, 403,
+                    extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)))
+
+
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
@@ -277,6 +295,9 @@ def main():
         _changepoint_marginal_samples("changepoint_marginals")
         return
     R = refshim.load_reference()
+    if "--only-n1-dense" in sys.argv:
+        _n1_dense_fixtures(R)
+        return
     B = R.benchmarks
 
     # --- config 1 family: RW on the Gaussian benchmarks (sampler.py:72-90,
@@ -341,6 +362,7 @@ def main():
     _vector_fixture(R, "adapthmc5_gauss2d", g2, R.AdaptScaleHMC(0.1, 5, g2.grad_log_likelihood),
                     np.ones(2), 1500, 304, extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)),
                     track_scale=True)
+    _n1_dense_fixtures(R)
     # pCN ("next" row N2)
     _vector_fixture(R, "pcn_gauss2d", g2, R.pCN(np.eye(2), 0.5), np.ones(2), 800, 305,
                     extra=dict(C0=np.eye(2), rho=np.float64(0.5)))

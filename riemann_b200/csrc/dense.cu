@@ -13,6 +13,8 @@
 //   kernel 1  finish_propose : per row -- finish the previous step (sum the GEMM's row
 //             partials, log-posterior, log q ratio, accept, adapt), then draw xi (Philox or
 //             injected) and write the next proposal.  One warp per chain row, coalesced.
+//             Nsteps > 1 (leapfrog, hamiltonian.py:13-52): Nsteps - 1 extra [gradient GEMM,
+//             leapfrog_mid_kernel] pairs advance the trajectory in place on the proposal slot.
 //   kernel 2  gemm_abt       : C = A B^T in fp64 on the tensor cores (DMMA m8n8k4),
 //             128x128x16 tiles, 3-stage cp.async pipeline, 8 warps.  The epilogue is fused:
 //             it stores V', and reduces y'.v' and |p'|^2 over the tile's columns into
@@ -171,7 +173,6 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
         } else {
             const double* yp = st.Y + ((int64_t)(c ^ 1) * K + mm) * dp;
             double* vp = st.V + ((int64_t)(c ^ 1) * K + mm) * dp;
-            const double* vc = st.V + ((int64_t)c * K + mm) * dp;
             const double* xi = st.Xi + mm * dp;
             const double he = 0.5 * st.epsrow[mm];
 #pragma unroll
@@ -183,11 +184,10 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
                     const double2 y = *reinterpret_cast<const double2*>(yp + n);
                     pq += y.x * v0 + y.y * v1;
                     if (EPI == EPI_LOGPOST_MALA) {
-                        // p' = xi + eps/2 g + eps/2 g',  g = -V_cur, g' = -V'   (hamiltonian.py:27,40)
+                        // final half step  p' = p + eps/2 g',  g' = -V'   (hamiltonian.py:40); Xi holds p
                         const double2 x = *reinterpret_cast<const double2*>(xi + n);
-                        const double2 w = *reinterpret_cast<const double2*>(vc + n);
-                        const double p0 = (x.x - he * w.x) - he * v0;
-                        const double p1 = (x.y - he * w.y) - he * v1;
+                        const double p0 = x.x - he * v0;
+                        const double p1 = x.y - he * v1;
                         pk += p0 * p0 + p1 * p1;
                     }
                 }
@@ -305,7 +305,9 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
                 const double ph = xi[q] + 0.5 * eps * (-vv[q]);        // hamiltonian.py:27
                 out[q] = yv[q] + eps * ph;                             // :30
                 k0 += xi[q] * xi[q];
+                xi[q] = ph;
             }
+            // the momentum after the initial half step rides in the Xi buffer through the trajectory
             *reinterpret_cast<double2*>(xo + j4) = make_double2(xi[0], xi[1]);
             *reinterpret_cast<double2*>(xo + j4 + 2) = make_double2(xi[2], xi[3]);
         } else if (sp.rw_diag) {
@@ -333,6 +335,25 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
             st.S2[(int64_t)lane * K + r] += f * f;
         }
     }
+}
+
+// Interior leapfrog step (hamiltonian.py:33-37, Nsteps > 1): with V' = Y' P of the trajectory point just
+// evaluated,  p <- p + eps (-V'),  y' <- y' + eps p,  in place on the chain's proposal slot.
+__global__ void __launch_bounds__(256)
+leapfrog_mid_kernel(DenseState st) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 2;
+    if (i >= st.K * st.dp) return;
+    const int64_t r = i / st.dp;
+    const int j = (int)(i % st.dp);
+    const double eps = st.epsrow[r];
+    const int64_t o = ((int64_t)(st.cur[r] ^ 1) * st.K + r) * st.dp + j;
+    const double2 v = *reinterpret_cast<const double2*>(st.V + o);
+    double2 p = *reinterpret_cast<const double2*>(st.Xi + i);
+    double2 y = *reinterpret_cast<const double2*>(st.Y + o);
+    p.x = p.x + eps * (-v.x); p.y = p.y + eps * (-v.y);
+    y.x = y.x + eps * p.x;    y.y = y.y + eps * p.y;
+    *reinterpret_cast<double2*>(st.Xi + i) = p;
+    *reinterpret_cast<double2*>(st.Y + o) = y;
 }
 
 // state i/o: theta[K][d] <-> centred slot-0/current rows; V recomputed by a GEMM on set
@@ -518,8 +539,18 @@ struct DenseGaussSampler : SamplerImpl {
             if (t == T) break;
             if (pr->kind == RMN_PROP_RW && !rw_diag)
                 if (int rc = gemm<EPI_RWPROP>(d_Lpad, stream)) return rc;
-            if (pr->kind == RMN_PROP_HMC) { if (int rc = gemm<EPI_LOGPOST_MALA>(d_Ppad, stream)) return rc; }
-            else { if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc; }
+            if (pr->kind == RMN_PROP_HMC) {
+                // Nsteps - 1 interior leapfrog steps, each one gradient GEMM + an in-place update
+                for (int l = 1; l < pr->nsteps; ++l) {
+                    if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc;
+                    const int64_t n2 = st.K * st.dp / 2;
+                    leapfrog_mid_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, stream>>>(st);
+                    RMN_KERNEL_CHECK(); launches++;
+                }
+                if (int rc = gemm<EPI_LOGPOST_MALA>(d_Ppad, stream)) return rc;
+            } else {
+                if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc;
+            }
         }
         step0 += T; diag_steps += T;
         return RMN_OK;
@@ -574,10 +605,10 @@ gauss_point_kernel(int d, const double* __restrict__ mu, const double* __restric
 
 SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s) {
     const rmn_proposal* p = s->prop;
-    if (p->kind == RMN_PROP_PCN || (p->kind == RMN_PROP_HMC && (p->nsteps != 1 || p->has_mass))) {
-        rmn_set_error("dense Gaussian path (d > %d) supports RW and MALA (VanillaHMC with Nsteps=1, no "
-                      "mass matrix); pCN / multi-step HMC / mass matrices run on the small-d path only",
-                      RMN_SMALL_D_MAX);
+    if (p->kind == RMN_PROP_PCN || (p->kind == RMN_PROP_HMC && p->has_mass)) {
+        rmn_set_error("dense Gaussian path (d > %d) supports RW and VanillaHMC / AdaptScaleHMC (any Nsteps, "
+                      "Nsteps = 1 is MALA) without a mass matrix; pCN and mass matrices run on the small-d "
+                      "path only", RMN_SMALL_D_MAX);
         return nullptr;
     }
     return new DenseGaussSampler(s);

@@ -25,12 +25,18 @@ def _prop(name, g, m):
         return rw.AdaptScaleRandomWalk(g["C0"])
     if name.startswith("adaptmala"):
         return hm.AdaptScaleHMC(float(g["eps"]), 1, m.grad_log_likelihood)
+    if name.startswith("adapthmc"):
+        return hm.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood)
+    if name.startswith("hmc"):
+        return hm.VanillaHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood)
     return hm.MALA(float(g["eps"]), m.grad_log_likelihood)
 
 
 @pytest.mark.parametrize("name,d", [("rw_gauss100d", 100), ("rw_dense_gauss12d", 12),
                                     ("adaptrw_gauss12d", 12), ("adaptmala_gauss12d", 12),
-                                    ("mala_gauss100d", 100), ("mala_gauss1000d", 1000)])
+                                    ("mala_gauss100d", 100), ("mala_gauss1000d", 1000),
+                                    # "next" row N1: leapfrog with Nsteps > 1 on the dense path
+                                    ("hmc4_gauss12d", 12), ("adapthmc3_gauss12d", 12), ("hmc5_gauss100d", 100)])
 def test_injected_chain_matches_reference(golden, name, d):
     from riemann_b200 import Sampler
     g = golden(name)
@@ -130,3 +136,25 @@ def test_full_size_config3_self_consistency():
     th, lp = s.state_tensors()
     want = m.log_posterior_batch(th[:512])
     assert relerr(lp[:512].cpu().numpy(), want.cpu().numpy()) < 1e-10
+
+
+def test_philox_hmc5_d100_matches_target():
+    """N1 distributional gate: 5 leapfrog steps per proposal on benchmark_gauss100d_corr."""
+    from scipy import stats
+    from riemann_b200 import Sampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.hamiltonian import VanillaHMC
+    m = benchmarks.benchmark_gauss100d_corr
+    K = 4096
+    rng = np.random.default_rng(0)
+    th0 = rng.standard_normal((K, 100)) * np.sqrt(0.1) + rng.standard_normal((K, 1)) * np.sqrt(0.9)
+    s = Sampler(m, VanillaHMC(0.1, 5, m.grad_log_likelihood), th0, seed=4)
+    s.run(300, trace=False)
+    dg = s.diagnostics(allreduce=False)
+    th = np.asarray(s._chain_thetas[-1])
+    assert 0.8 < dg["accept_rate"] <= 1.0
+    assert stats.kstest(th[:, 3], "norm").pvalue > 1e-3
+    assert stats.kstest(th.mean(1) / np.sqrt(0.9 + 0.1 / 100), "norm").pvalue > 1e-3
+    assert stats.kstest((th[:, 0] - th[:, 1]) / np.sqrt(0.2), "norm").pvalue > 1e-3
+    lp = np.asarray(s._chain_logpost[-1])
+    assert relerr(lp, m.log_posterior_batch(th).cpu().numpy()) < 1e-10

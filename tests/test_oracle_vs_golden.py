@@ -71,10 +71,11 @@ def test_mala_is_hmc1(golden, name, d):
     _replay(g, m, port.MALA(float(g["eps"]), m.grad_log_likelihood), g["thetas"][0])
 
 
-@pytest.mark.parametrize("name", ["hmc5_gauss2d", "hmc3_mass_gauss2d"])
-def test_hmc(golden, name):
+@pytest.mark.parametrize("name,d", [("hmc5_gauss2d", 2), ("hmc3_mass_gauss2d", 2), ("hmc4_gauss12d", 12),
+                                    ("hmc5_gauss100d", 100)])
+def test_hmc(golden, name, d):
     g = golden(name)
-    m = _gauss(g, 2)
+    m = _gauss(g, d)
     M = g["M"] if "M" in g else None
     _replay(g, m, port.VanillaHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood, M=M),
             g["thetas"][0])
@@ -87,9 +88,10 @@ def test_mala_mass(golden):
             g["thetas"][0])
 
 
-def test_adapt_scale_hmc(golden):
-    g = golden("adapthmc5_gauss2d")
-    m = _gauss(g, 2)
+@pytest.mark.parametrize("name,d", [("adapthmc5_gauss2d", 2), ("adapthmc3_gauss12d", 12)])
+def test_adapt_scale_hmc(golden, name, d):
+    g = golden(name)
+    m = _gauss(g, d)
     prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood)
     _replay(g, m, prop, g["thetas"][0])
     assert abs(prop.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
