@@ -241,6 +241,15 @@ int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stre
 /* Number of kernel launches this handle has enqueued so far. */
 int64_t rmn_sampler_launch_count(const rmn_sampler_t* s);
 
+/* Measurement aid: CUDA-event timing of the sampler's DOMINANT kernel (changepoint_kernel,
+ * small_gauss_kernel, gemm_abt_kernel, tf32x3_gemm_kernel, lg_eval_kernel / lg_metric_kernel), one event
+ * pair per launch on the launching stream.  rmn_sampler_kernel_timing waits for the last recorded
+ * event, returns the summed duration and the number of timed launches since the previous call (at most
+ * 8192 per window; `untimed` counts the rest) and the kernel's name, and starts a new window. */
+int rmn_sampler_enable_kernel_timing(rmn_sampler_t* s, int enable);
+int rmn_sampler_kernel_timing(rmn_sampler_t* s, double* total_ms, int64_t* launches, int64_t* untimed,
+                              const char** kernel_name);
+
 /* Raw device RNG, for known-answer tests: out[n][4] = Philox4x32-10(ctr[n][4], key[n][2]). */
 int rmn_philox_raw(int64_t n, const uint32_t* d_ctr, const uint32_t* d_key, uint32_t* d_out,
                    void* stream);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "rmn_sampler_reset_diagnostics": (_I, [_P, _P]),
     "rmn_sampler_reduce_diagnostics": (_I, [_P, _P, _P]),
     "rmn_sampler_launch_count": (_L, [_P]),
+    "rmn_sampler_enable_kernel_timing": (_I, [_P, _I]),
+    "rmn_sampler_kernel_timing": (_I, [_P, _P, _P, _P, _P]),
     "rmn_philox_raw": (_I, [_L, _P, _P, _P, _P]),
     "rmn_rng_draws": (_I, [C.c_uint64, _L, _L, _L, _I, _P, _P, _P]),
     "rmn_tf32x3_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P]),

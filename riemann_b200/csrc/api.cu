@@ -404,3 +404,18 @@ extern "C" int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block,
     return s->impl->reduce_diag(d_block, (cudaStream_t)stream);
 }
 extern "C" int64_t rmn_sampler_launch_count(const rmn_sampler_t* s) { return (s && s->impl) ? s->impl->launches : 0; }
+
+extern "C" int rmn_sampler_enable_kernel_timing(rmn_sampler_t* s, int enable) {
+    RMN_REQUIRE(s && s->impl, "rmn_sampler_enable_kernel_timing: null sampler");
+    s->impl->ktimer.on = enable != 0;
+    s->impl->ktimer.used = 0; s->impl->ktimer.untimed = 0;
+    return RMN_OK;
+}
+extern "C" int rmn_sampler_kernel_timing(rmn_sampler_t* s, double* total_ms, int64_t* launches, int64_t* untimed,
+                                         const char** kernel_name) {
+    RMN_REQUIRE(s && s->impl, "rmn_sampler_kernel_timing: null sampler");
+    if (untimed) *untimed = s->impl->ktimer.untimed;
+    if (kernel_name) *kernel_name = s->impl->ktimer.name;
+    s->impl->ktimer.collect(total_ms, launches);
+    return RMN_OK;
+}

@@ -706,12 +706,14 @@ struct ChangepointSampler : SamplerImpl {
         rmn_trace_t t0{};
         if (tr) t0 = *tr;
         if (t0.thin <= 0) t0.thin = 1;
+        ktimer.begin("changepoint_kernel", stream);
         if (inj) {
             RMN_REQUIRE(inj->d_tape, "injected changepoint run needs d_tape");
             launch<true>(T, inj->d_tape, t0, stream);
         } else {
             launch<false>(T, nullptr, t0, stream);
         }
+        ktimer.end(stream);
         RMN_KERNEL_CHECK();
         launches++;
         // samples = #{ s in [step0, step0+T) : s % EVERY == 0 }

@@ -191,9 +191,56 @@ struct rmn_proposal {
     double p_cum[3] = {0.20, 0.40, 0.60};
 };
 
+// Optional CUDA-event timing of a sampler's dominant kernel (rmn_sampler_enable_kernel_timing): one event
+// pair around each launch on the launching stream, resolved by rmn_sampler_kernel_timing.  bench.py uses
+// it for `roofline.achieved` (algorithmic work / the kernel's own average launch duration).
+struct KernelTimer {
+    bool on = false;
+    const char* name = "";
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    static constexpr size_t CAP = 16384;       // events; later launches of a window are not timed
+    int64_t untimed = 0;
+    bool armed = false;
+    void begin(const char* kname, cudaStream_t st) {
+        armed = false;
+        if (!on) return;
+        name = kname;
+        if (used + 2 > CAP) { ++untimed; return; }
+        while (ev.size() < used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) { ++untimed; return; }
+            ev.push_back(e);
+        }
+        cudaEventRecord(ev[used], st);
+        armed = true;
+    }
+    void end(cudaStream_t st) {
+        if (!armed) return;
+        cudaEventRecord(ev[used + 1], st);
+        used += 2;
+        armed = false;
+    }
+    // total ms and number of timed launches since the last collect; synchronizes on the last event
+    int collect(double* ms, int64_t* n) {
+        double tot = 0.0;
+        if (used) cudaEventSynchronize(ev[used - 1]);
+        for (size_t i = 0; i + 1 < used; i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) tot += t;
+        }
+        if (ms) *ms = tot;
+        if (n) *n = (int64_t)(used / 2);
+        used = 0; untimed = 0;
+        return 0;
+    }
+    ~KernelTimer() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
 struct rmn_sampler;
 struct SamplerImpl {
     virtual ~SamplerImpl() {}
+    KernelTimer ktimer;
     virtual size_t workspace_bytes() const = 0;
     virtual int bind(void* ws) = 0;
     virtual int set_state(const double* d_theta, cudaStream_t st) { return unsupported("set_state"); }

@@ -485,7 +485,9 @@ struct DenseGaussSampler : SamplerImpl {
 
     template <int EPI>
     int gemm(const double* B, cudaStream_t stream) {
+        ktimer.begin("gemm_abt_kernel", stream);
         gemm_abt_kernel<EPI><<<gemm_grid(), GEMM_THREADS, GEMM_SMEM, stream>>>(st, B);
+        ktimer.end(stream);
         RMN_KERNEL_CHECK(); launches++;
         return RMN_OK;
     }

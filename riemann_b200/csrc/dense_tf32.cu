@@ -305,8 +305,11 @@ struct DenseTF32Sampler : SamplerImpl {
     double c1() const { return st.d * log(2.0 * M_PI); }
     int gemm(int mala, cudaStream_t stream) {
         launches++;
-        return tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
-                               st.partq, st.partk, mala, stream);
+        ktimer.begin("tf32x3_gemm_kernel", stream);
+        const int rc = tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
+                                       st.partq, st.partk, mala, stream);
+        ktimer.end(stream);
+        return rc;
     }
     int set_state(const double* d_theta, cudaStream_t stream) override {
         const int64_t n = st.K * st.dp;

@@ -858,13 +858,18 @@ struct LogisticSampler : SamplerImpl {
 
     int eval(int fixed_slot, cudaStream_t stream) {
         dim3 grid((unsigned)((st.K + BC - 1) / BC), st.nsplit);
+        const bool time_eval = !mmala || tf32m;          // the dominant kernel of this configuration
+        if (time_eval) ktimer.begin("lg_eval_kernel", stream);
         lg_eval_kernel<<<grid, EVAL_THREADS, eval_smem(), stream>>>(st, fixed_slot);
+        if (time_eval) ktimer.end(stream);
         RMN_KERNEL_CHECK(); launches++;
         if (tf32m) {
             if (int rc = tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
             launches++;
         } else if (mmala) {
+            ktimer.begin("lg_metric_kernel", stream);
             lg_metric_kernel<<<(unsigned)((st.K + 3) / 4), 256, metric_smem(), stream>>>(st, fixed_slot);
+            ktimer.end(stream);
             RMN_KERNEL_CHECK(); launches++;
         }
         return RMN_OK;

@@ -361,14 +361,16 @@ struct SmallGaussSampler : SamplerImpl {
         rmn_trace_t t0{};
         if (tr) t0 = *tr;
         if (t0.thin <= 0) t0.thin = 1;
+        if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        ktimer.begin("small_gauss_kernel", stream);
         if (inj) {
-            RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
             small_gauss_kernel<D, true><<<grid(), 128, 0, stream>>>(
                 d_params, st, s->K, T, step0, s->seed, s->chain_offset, inj->d_xi, inj->d_u, t0);
         } else {
             small_gauss_kernel<D, false><<<grid(), 128, 0, stream>>>(
                 d_params, st, s->K, T, step0, s->seed, s->chain_offset, nullptr, nullptr, t0);
         }
+        ktimer.end(stream);
         RMN_KERNEL_CHECK(); launches++;
         step0 += T; diag_steps += T;
         return RMN_OK;

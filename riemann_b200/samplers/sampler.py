@@ -450,6 +450,18 @@ class Sampler(object):
             blk = reduce_block(blk)
         return summarize_block(blk.cpu().numpy())
 
+    def enable_kernel_timing(self, enable=True):
+        """CUDA-event timing of the dominant kernel's launches (measurement aid, see bench.py)."""
+        _lib.check(_lib.load().rmn_sampler_enable_kernel_timing(self._handle, 1 if enable else 0))
+
+    def kernel_timing(self):
+        """-> dict(kernel, total_ms, launches, untimed) since the previous call; synchronizes."""
+        ms, n, un, name = C.c_double(), C.c_int64(), C.c_int64(), C.c_char_p()
+        _lib.check(_lib.load().rmn_sampler_kernel_timing(self._handle, C.byref(ms), C.byref(n), C.byref(un),
+                                                         C.byref(name)))
+        return {"kernel": (name.value or b"").decode(), "total_ms": ms.value, "launches": n.value,
+                "untimed": un.value}
+
     @property
     def launch_count(self):
         return int(_lib.load().rmn_sampler_launch_count(self._handle))

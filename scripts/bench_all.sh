@@ -9,3 +9,4 @@ run cfg3_gauss1000_tf32x3 --workload gauss1000_mala --precision tf32x3 --steps 3
 run cfg4_logistic_mala --workload logistic_mala --steps 2 --warmup 3 --iters 2 --cpu-seconds 10
 run cfg4_logistic_mala_k8192 --workload logistic_mala --chains 8192 --steps 2 --warmup 3 --iters 1 --no-cpu
 run cfg5_logistic_mmala --workload logistic_mmala --chains 4096 --steps 2 --warmup 3 --iters 1 --cpu-seconds 10
+run cfg5_logistic_mmala_tf32metric --workload logistic_mmala --chains 4096 --steps 2 --warmup 3 --iters 1 --precision tf32-metric --no-cpu
