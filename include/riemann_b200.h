@@ -263,6 +263,10 @@ int rmn_rng_draws(uint64_t seed, int64_t chain0, int64_t step, int64_t n, int nn
  * It is the GEMM behind the tf32x3 precision mode of the dense Gaussian sampler. */
 int rmn_tf32x3_gemm(int64_t M, int N, int K, const float* d_Ah, const float* d_Al, const float* d_Bh,
                     const float* d_Bl, float* d_C, void* stream);
+/* Split-K mode of the same kernel (few output tiles, long contraction): C[s][M][N], s < *used_splits <= ksplit,
+ * are partial products over contiguous ranges of K; their sum is the product. */
+int rmn_tf32x3_gemm_splitk(int64_t M, int N, int K, int ksplit, const float* d_Ah, const float* d_Al,
+                           const float* d_Bh, const float* d_Bl, float* d_C, int* used_splits, void* stream);
 /* Single-pass TF32 product on the same kernel, validation entry: C[M][N] (fp32) ~= A B^T, A [M][K],
  * B [N][K] fp32 (the tensor core drops the low 13 mantissa bits of each operand); K % 32 == 0, N % 4 == 0.
  * It is the GEMM behind RMN_PREC_TF32_METRIC. */

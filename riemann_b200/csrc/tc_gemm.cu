@@ -68,7 +68,11 @@ enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 template <int EPI, int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
-                   int ldc, MalaEpi ep) {
+                   int ldc, MalaEpi ep, int ksplit, int kb_per, int64_t split_stride) {
+    // ksplit > 1 (EPI_PLAIN only): the k-blocks are divided into ksplit contiguous ranges; a tile is
+    // (m_tile, n_tile, split) and split s stores its partial product at C + s * split_stride (summed by
+    // the caller) -- this is how a product with few output tiles but a long contraction (the logistic
+    // gradient R X: K x d output, N data rows deep) still fills all SMs.
     constexpr int STAGES = (PASSES == 1) ? 4 : tc::STAGES;
     constexpr int STAGE_BYTES = (PASSES == 1) ? (A_BYTES + B_BYTES) : tc::STAGE_BYTES;
     constexpr int OFF_BH = (PASSES == 1) ? A_BYTES : 2 * A_BYTES;
@@ -82,10 +86,12 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KB = Kdim / TK;
+    const int KB_all = Kdim / TK;
+    // kb_per = k-blocks per split (the last one may be short, none is empty: launch_common)
     const int n_tiles = (N + TN - 1) / TN;
     const int64_t m_tiles = (M + TM - 1) / TM;
-    const int64_t num_tiles = m_tiles * n_tiles;
+    const int64_t mn_tiles = m_tiles * n_tiles;
+    const int64_t num_tiles = mn_tiles * ksplit;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.bh);
@@ -106,8 +112,11 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         // ===== TMA producer: runs ahead across tiles, bounded by the stage ring =====
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (int)(tile / n_tiles) * TM, n0 = (int)(tile % n_tiles) * TN;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int64_t mn = tile % mn_tiles;
+            const int kb0 = (int)(tile / mn_tiles) * kb_per;
+            const int kb1 = min(KB_all, kb0 + kb_per);
+            const int m0 = (int)(mn / n_tiles) * TM, n0 = (int)(mn % n_tiles) * TN;
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
@@ -129,7 +138,9 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             mbar_wait(&tmem_empty[a], ((ti / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(a * TN);
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int kb0 = (int)(tile / mn_tiles) * kb_per;
+            const int kb1 = min(KB_all, kb0 + kb_per);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&full[s], (it / STAGES) & 1);
                 tc_fence_after();
@@ -141,7 +152,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 #pragma unroll
                 for (int k = 0; k < TK / UK; ++k) {
                     const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);   // +32 bytes per K step, 16-byte units
-                    umma_tf32(tacc, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+                    umma_tf32(tacc, dah + adv, dbh + adv, idesc, ((kb - kb0) | k) != 0);
                     if (PASSES == 3) {
                         umma_tf32(tacc, dah + adv, dbl + adv, idesc, 1);
                         umma_tf32(tacc, dal + adv, dbh + adv, idesc, 1);
@@ -157,8 +168,10 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         uint32_t ti = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int a = ti % ACC_STAGES;
-            const int64_t m0 = (tile / n_tiles) * TM;
-            const int n0 = (int)(tile % n_tiles) * TN;
+            const int64_t mn = tile % mn_tiles;
+            const int64_t m0 = (mn / n_tiles) * TM;
+            const int n0 = (int)(mn % n_tiles) * TN;
+            float* Cs = (EPI == EPI_PLAIN) ? C + (tile / mn_tiles) * split_stride : C;
             mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
             tc_fence_after();
             const int64_t m = m0 + q * 32 + lane;
@@ -172,7 +185,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 const int n = n0 + half * (TN / 2) + c0;
                 if (!rok || n >= N) continue;
                 if (EPI == EPI_PLAIN) {
-                    float4* dst = reinterpret_cast<float4*>(C + m * ldc + n);
+                    float4* dst = reinterpret_cast<float4*>(Cs + m * ldc + n);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (n + 4 * i < N) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -210,7 +223,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
             if (EPI == EPI_MALA && rok) {
-                const size_t blk = (size_t)(tile % n_tiles) * 2 + half;            // 128-column block index
+                const size_t blk = (size_t)(mn % n_tiles) * 2 + half;              // 128-column block index
                 ep.partq[blk * M + m] = pq;
                 if (ep.mala) ep.partk[blk * M + m] = pk;
             }
@@ -225,9 +238,13 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 }
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
-                         cudaStream_t st, int passes = 3) {
+                         cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0) {
     if (Kdim % TK != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
-    const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM);
+    if (ksplit < 1 || ksplit > Kdim / TK || (ep && ksplit != 1)) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
+    // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
+    const int kbp = (Kdim / TK + ksplit - 1) / ksplit;
+    ksplit = (Kdim / TK + kbp - 1) / kbp;
+    const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM) * ksplit;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));          // persistent: one CTA per SM
@@ -238,9 +255,9 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep);
-    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{});
-    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{});
+    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep, 1, kbp, 0);
+    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride);
+    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
@@ -250,6 +267,14 @@ int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int
 }
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 1);
+}
+// 3-pass product with the contraction split into `ksplit` ranges; returns the number of splits actually
+// used through *used (<= ksplit); partial s is at C + s * split_stride
+int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
+                        int64_t split_stride, int* used, cudaStream_t st) {
+    const int kbp = (Kdim / TK + ksplit - 1) / ksplit;
+    if (used) *used = (Kdim / TK + kbp - 1) / kbp;
+    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 3, ksplit, split_stride);
 }
 int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
                 const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
@@ -271,6 +296,21 @@ extern "C" int rmn_tf32_gemm(int64_t M, int N, int Kdim, const float* d_A, const
     if ((rc = tc::make_tmap_2d(&maps.bh, d_B, N, Kdim, Kdim, tc::TN))) return rc;
     maps.al = maps.ah; maps.bl = maps.bh;
     return tc::launch_plain_tf32(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
+}
+
+// Validation entry of the split-K mode: C[ksplit][M][N] partial products (the caller sums them).
+extern "C" int rmn_tf32x3_gemm_splitk(int64_t M, int N, int Kdim, int ksplit, const float* d_Ah, const float* d_Al,
+                                      const float* d_Bh, const float* d_Bl, float* d_C, int* used_splits, void* stream) {
+    RMN_REQUIRE(M >= 1 && N >= 1 && Kdim >= 32 && Kdim % 32 == 0 && N % 4 == 0 && ksplit >= 1, "rmn_tf32x3_gemm_splitk: bad shape");
+    RMN_REQUIRE(d_Ah && d_Al && d_Bh && d_Bl && d_C, "rmn_tf32x3_gemm_splitk: null pointer");
+    tc::GemmMaps maps;
+    int rc;
+    if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN))) return rc;
+    if (ksplit > Kdim / 32) ksplit = Kdim / 32;
+    return tc::launch_plain_splitk(maps, M, N, Kdim, d_C, N, ksplit, (int64_t)M * N, used_splits, (cudaStream_t)stream);
 }
 
 // Validation entry: C[M][N] (fp32, ld = N) ~= (Ah + Al)(Bh + Bl)^T; A* are [M][K], B* are [N][K], fp32, K % 32 == 0.

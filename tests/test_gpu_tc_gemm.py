@@ -55,3 +55,28 @@ def test_single_pass_tf32_gemm(M, N, K):
     scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
     assert np.all(np.isfinite(got))
     assert np.max(np.abs(got - ref) / scale) < 1.5e-3
+
+
+@pytest.mark.parametrize("M,N,K,ks", [(256, 128, 4096, 7), (1024, 100, 32 * 37, 18), (70, 64, 64, 5)])
+def test_split_k_partials_sum_to_the_product(M, N, K, ks):
+    """rmn_tf32x3_gemm_splitk: the contraction is cut into <= ks ranges, one partial product per range."""
+    import ctypes as C
+    import torch
+    from riemann_b200 import _lib
+    rng = np.random.default_rng(M + N + K + ks)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    Ah, Al = _split(A)
+    Bh, Bl = _split(B)
+    d = [torch.as_tensor(x, device="cuda") for x in (Ah, Al, Bh, Bl)]
+    Cp = torch.full((ks, M, N), float("nan"), dtype=torch.float32, device="cuda")
+    used = C.c_int(0)
+    _lib.check(_lib.load().rmn_tf32x3_gemm_splitk(M, N, K, ks, *[_lib.ptr(t) for t in d], _lib.ptr(Cp),
+                                                  C.byref(used), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert 1 <= used.value <= ks
+    got = Cp[:used.value].cpu().numpy().astype(np.float64).sum(0)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - ref) / scale) < 3e-6
