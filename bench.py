@@ -244,11 +244,13 @@ def build_workload(name, K, seed, chain_offset, precision="f64"):
         rng = np.random.Generator(np.random.Philox(port.SEED_BASE + 5))
         th0 = ts[None, :] + 0.01 * rng.standard_normal((K, d))
         prop = SimplifiedMMALA(0.5, m) if name == "logistic_mmala" else MALA(0.02, m.grad_log_posterior)
-        s = Sampler(m, prop, th0, seed=seed, chain_offset=chain_offset,
-                    precision=precision if name == "logistic_mmala" else "f64")
+        if precision == "tf32-metric" and name != "logistic_mmala":
+            raise SystemExit("--precision tf32-metric applies to logistic_mmala only")
+        s = Sampler(m, prop, th0, seed=seed, chain_offset=chain_offset, precision=precision)
         return s, "logistic regression N=%d d=%d, %s%s" % (
             N, d, "simplified mMALA" if "mm" in name else "MALA",
-            ", Fisher metric on tcgen05 (TF32 GEMM)" if (name == "logistic_mmala" and precision == "tf32-metric") else "")
+            {"f64": "", "tf32-metric": ", Fisher metric on tcgen05 (TF32 GEMM)",
+             "tf32x3": ", likelihood sweep on tcgen05 (3xTF32 GEMMs, fp64 pointwise stage)"}[precision])
     raise SystemExit("unknown workload %r" % name)
 
 
@@ -362,6 +364,17 @@ def run_engine(args):
                 "note": "dominant kernel = lg_eval_kernel (fp64 DMMA, 4 N d = 2.6e7 flop per chain-step) against the "
                         "measured DMMA peak; the metric GEMM (4.2e8 flop per chain-step) runs on tcgen05 in TF32 at 95 % "
                         "tensor-pipe utilisation (profiles/r1_mmala_metric_tf32_gemm.md) and is the smaller share of the step"}
+    elif args.precision == "tf32x3" and wl.startswith("logistic"):
+        peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
+        n_, d_ = (100000, 64) if wl == "logistic_mmala" else (1000000, 100)
+        ach_tflops = 4.0 * n_ * d_ * Kg * T * args.steps / (kernel_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach_tflops / peak, "traffic": None,
+                "note": "likelihood sweep = logits GEMM + fp64 pointwise kernel + split-K gradient GEMM, timed together "
+                        "(CUDA events around the three launches); achieved counts the ALGORITHMIC 4 N d flop per chain-step "
+                        "once (3 TF32 MMAs are issued per product, and the d-wide gradient tile fills 100/256 resp. 64/256 "
+                        "of the MMA's N), so the fraction of the cuBLAS TF32 peak is small by construction; the sweep is "
+                        "bounded by the fp64 pointwise stage and the 12 B/(chain,row) of Z/R traffic"}
     elif args.precision == "tf32x3":
         peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
         roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
@@ -390,7 +403,8 @@ def run_engine(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_launch, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": {"f64": "f64", "tf32x3": "tf32x3/f32 state, f64 accept test",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"f64": "f64", "tf32x3": ("tf32x3 likelihood GEMMs, f64 pointwise + accept test" if wl.startswith("logistic")
+                                                                       else "tf32x3/f32 state, f64 accept test"),
                                                             "tf32-metric": "f64 (proposal metric: tf32 tensor cores)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "%s: %s; %d chains/GPU x %d MH iterations per step; Philox4x32-10 RNG; "

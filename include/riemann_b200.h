@@ -187,6 +187,9 @@ int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, i
  * (DMMA / DFMA).  RMN_PREC_TF32X3: dense Gaussian model only -- fp32 chain state, the K x d by
  * d x d product on tcgen05 tensor cores with a 3xTF32 split (fp32-accurate), everything that
  * enters the accept test reduced in fp64; |log-posterior error| <~ 5e-3 at d = 1000. */
+/* RMN_PREC_TF32X3 on the logistic model (MALA or mMALA): logits Z = Theta X^T and gradient R X as 3xTF32
+ * tcgen05 GEMMs over materialised fp32 matrices, sigmoid/softplus and the log-likelihood sum in fp64 from the
+ * fp32 logits (|log-likelihood error| <~ 1e-3 at N = 1e6), mMALA metric as in RMN_PREC_TF32_METRIC. */
 #define RMN_PREC_F64 0
 #define RMN_PREC_TF32X3 1
 /* RMN_PREC_TF32_METRIC: logistic model + simplified mMALA only -- the Fisher metric of the proposal,

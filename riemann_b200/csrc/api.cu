@@ -268,7 +268,8 @@ static SamplerImpl* make_impl(rmn_sampler* s, int* rc) {
         *rc = RMN_ERR_PARAM;
         return nullptr;
     }
-    if (s->precision == RMN_PREC_TF32X3) return make_dense_tf32_sampler(s);
+    if (s->precision == RMN_PREC_TF32X3)
+        return (m->kind == RMN_MODEL_LOGISTIC) ? make_logistic_sampler(s) : make_dense_tf32_sampler(s);
     if (s->precision == RMN_PREC_TF32_METRIC) {
         if (m->kind != RMN_MODEL_LOGISTIC || p->kind != RMN_PROP_MMALA) {
             rmn_set_error("precision tf32-metric needs the logistic model with the simplified mMALA proposal");

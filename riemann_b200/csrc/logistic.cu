@@ -29,12 +29,28 @@
 // tensor cores in single-pass TF32 (tc_gemm.cu, PASSES = 1).  The metric only shapes the proposal: the
 // SAME deterministic function theta -> G~(theta) enters the forward and the reverse proposal density,
 // and the log-posterior / gradient stay fp64, so the chain still targets the exact posterior.
+//
+// Precision mode RMN_PREC_TF32X3 (MALA and mMALA): the likelihood sweep itself on the tcgen05 tensor
+// cores, fp32-accurate (3xTF32), as three passes over materialised fp32 matrices instead of the fused
+// fp64 DMMA kernel:
+//   Z[K][N]  = Theta' X^T          GEMM (M = chains, N = data rows, contraction d)      tc_gemm.cu
+//   pointwise: p, softplus in fp64 from z; log-likelihood partial sums in fp64; R = y - p split hi/lo
+//              (and W = p(1-p) for the mMALA metric)                                    lg_tc_pointwise_kernel
+//   G[K][d]  = R X                 split-K GEMM (M = chains, N = d, contraction over data rows)
+// Chains are processed in blocks of at most 2,048 so Z and R stay at 12 bytes x N x 2,048.  The log-
+// likelihood carries the fp32 rounding of z (~1e-6 per row, |error| <~ 1e-3 at N = 1e6, measured in
+// tests/test_gpu_logistic.py) as a deterministic function of theta; the accept test, prior, proposal
+// arithmetic and Cholesky stay fp64.
+#include <algorithm>
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "logistic_math.cuh"
 
 namespace tc {
+int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
+                        int64_t split_stride, int* used, cudaStream_t st);
 }
 
 namespace {
@@ -422,6 +438,135 @@ lg_build_kr_kernel(LogisticState st) {
 }
 
 // ---------------------------------------------------------------------------------------
+// RMN_PREC_TF32X3: buffers and kernels of the tensor-core likelihood sweep
+// ---------------------------------------------------------------------------------------
+struct LgTC {
+    float* Xh; float* Xl;      // [N][dp32]      X split, the B operand of Z = Theta X^T
+    float* XTh; float* XTl;    // [dp32][Npad]   X^T split, the B operand of G = R X
+    float* Th; float* Tl;      // [K][dp32]      Theta' split
+    float* Z;                  // [Kb][Npad]     logits of the chain block in flight
+    float* Rh; float* Rl;      // [Kb][Npad]     y - p, split
+    float* Gp32;               // [ksplit][Kb][dp32]  split-K partial gradients
+    double* llp;               // [nchunk][Kb]   log-likelihood partial sums
+    int dp32, Kb, nchunk, ksplit; int64_t Npad;
+};
+
+__device__ __forceinline__ void split_f64(double x, float& hi, float& lo) {
+    const float xf = (float)x;
+    hi = __uint_as_float(__float_as_uint(xf) & 0xFFFFE000u);         // TF32-exact
+    lo = (float)(x - (double)hi);
+}
+
+// X[N][d] (fp64) -> Xh/Xl[N][dp32] and the transposed XTh/XTl[dp32][Npad]; one block per 32 data rows
+__global__ void __launch_bounds__(256)
+lg_tc_prep_x_kernel(LogisticState st, LgTC tc) {
+    extern __shared__ __align__(16) double sm[];                  // [32][dp32 + 1]
+    const int d = st.d, dp32 = tc.dp32, ld = dp32 + 1;
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    for (int q = threadIdx.x; q < 32 * dp32; q += blockDim.x) {
+        const int r = q / dp32, k = q % dp32;
+        const double v = (i0 + r < st.N && k < d) ? st.X[(i0 + r) * d + k] : 0.0;
+        sm[r * ld + k] = v;
+        if (i0 + r < st.N) {
+            float hi, lo;
+            split_f64(v, hi, lo);
+            tc.Xh[(i0 + r) * dp32 + k] = hi;
+            tc.Xl[(i0 + r) * dp32 + k] = lo;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (i0 + lane >= tc.Npad) return;
+    for (int k = warp; k < dp32; k += nw) {
+        float hi, lo;
+        split_f64(sm[lane * ld + k], hi, lo);
+        tc.XTh[(int64_t)k * tc.Npad + i0 + lane] = hi;
+        tc.XTl[(int64_t)k * tc.Npad + i0 + lane] = lo;
+    }
+}
+
+// Theta' (proposal slot, or `fixed_slot`) -> Th/Tl[K][dp32]
+__global__ void lg_tc_split_theta_kernel(LogisticState st, LgTC tc, int fixed_slot) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= st.K * tc.dp32) return;
+    const int64_t c = idx / tc.dp32;
+    const int k = (int)(idx % tc.dp32);
+    double v = 0.0;
+    if (k < st.d) {
+        const int slot = (fixed_slot >= 0) ? fixed_slot : (st.cur[c] ^ 1);
+        v = st.Th[((int64_t)slot * st.K + c) * st.dp + k];
+    }
+    float hi, lo;
+    split_f64(v, hi, lo);
+    tc.Th[idx] = hi; tc.Tl[idx] = lo;
+}
+
+// pointwise stage for the chain block [c0, c0 + kb): block = (row chunk, chain)
+constexpr int PW_THREADS = 256;
+__global__ void __launch_bounds__(PW_THREADS)
+lg_tc_pointwise_kernel(LogisticState st, LgTC tc, int64_t c0, int kb) {
+    __shared__ double tab[lgmath::TAB_DOUBLES];
+    __shared__ double red[PW_THREADS / 32];
+    for (int q = threadIdx.x; q < lgmath::TAB_DOUBLES; q += PW_THREADS) tab[q] = g_lg_tab[q];
+    __syncthreads();
+    const int cl = blockIdx.y;                                      // chain within the block
+    const int64_t rows_per = ((tc.Npad / 4 + tc.nchunk - 1) / tc.nchunk) * 4;
+    const int64_t i_begin = (int64_t)blockIdx.x * rows_per;
+    const int64_t i_end = min(tc.Npad, i_begin + rows_per);
+    const float* zrow = tc.Z + (int64_t)cl * tc.Npad;
+    float* rh = tc.Rh + (int64_t)cl * tc.Npad;
+    float* rl = tc.Rl + (int64_t)cl * tc.Npad;
+    float* wrow = st.W ? st.W + (c0 + cl) * st.Npad : nullptr;      // st.Npad == tc.Npad
+    double ll = 0.0;
+    for (int64_t i4 = i_begin + 4 * (int64_t)threadIdx.x; i4 < i_end; i4 += 4 * PW_THREADS) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zrow + i4);
+        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+        float h[4], l[4], w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i4 + e;
+            const bool ok = i < st.N;
+            const double zz = (double)zv[e];
+            const double yv = ok ? st.y[i] : 0.0;
+            double p, sp, pq;
+            lgmath::sigmoid_softplus(zz, tab, p, sp, pq);
+            ll += ok ? (yv * zz - sp) : 0.0;
+            split_f64(ok ? (yv - p) : 0.0, h[e], l[e]);
+            w[e] = ok ? (float)pq : 0.f;
+        }
+        *reinterpret_cast<float4*>(rh + i4) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(rl + i4) = make_float4(l[0], l[1], l[2], l[3]);
+        if (wrow) *reinterpret_cast<float4*>(wrow + i4) = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    ll = group_sum<32>(ll);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < PW_THREADS / 32; ++q) t += red[q];       // fixed order
+        tc.llp[(int64_t)blockIdx.x * tc.Kb + cl] = t;
+    }
+}
+
+// sum the partials of the chain block into slot 0 of llpart / gpart (the layout the finish kernels read)
+__global__ void __launch_bounds__(128)
+lg_tc_reduce_kernel(LogisticState st, LgTC tc, int64_t c0, int kb, int nsplit_used) {
+    const int lane = threadIdx.x & 31;
+    const int64_t cl = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (cl >= kb) return;
+    const int64_t c = c0 + cl;
+    double ll = 0.0;
+    for (int q = lane; q < tc.nchunk; q += 32) ll += tc.llp[(int64_t)q * tc.Kb + cl];
+    ll = group_sum<32>(ll);
+    if (lane == 0) st.llpart[c] = ll;
+    for (int j = lane; j < st.dp; j += 32) {
+        double g = 0.0;
+        for (int s2 = 0; s2 < nsplit_used; ++s2) g += (double)tc.Gp32[((int64_t)s2 * tc.Kb + cl) * tc.dp32 + j];
+        st.gpart[c * st.dp + j] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // finish / propose, one warp per chain.
 // ---------------------------------------------------------------------------------------
 struct LgStep {
@@ -776,15 +921,43 @@ struct LogisticSampler : SamplerImpl {
     rmn_sampler* s;
     LogisticState st{};
     bool mmala;
-    bool tf32m;                 // RMN_PREC_TF32_METRIC: tcgen05 metric GEMM instead of lg_metric_kernel
-    tc::GemmMaps maps;
+    bool tf32m;                 // tcgen05 metric GEMM instead of lg_metric_kernel (TF32_METRIC and TF32X3)
+    bool tcx3;                  // RMN_PREC_TF32X3: the likelihood sweep on tcgen05 (LgTC pipeline)
+    tc::GemmMaps maps;          // metric GEMM
+    LgTC tcb{};
+    tc::GemmMaps maps_z, maps_g;               // Z = Theta X^T (A map rebuilt per chain block) ; G = R X
+    std::vector<tc::GemmMaps> maps_z_blk;
     explicit LogisticSampler(rmn_sampler* s_) : s(s_) {
         fill_geometry(st, s->model, s->K);
         mmala = (s->prop->kind == RMN_PROP_MMALA);
-        tf32m = mmala && s->precision == RMN_PREC_TF32_METRIC;
-        if (tf32m) {
-            st.Npad = (st.N + 31) / 32 * 32;
-            st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
+        tcx3 = s->precision == RMN_PREC_TF32X3;
+        tf32m = mmala && (s->precision == RMN_PREC_TF32_METRIC || tcx3);
+        if (tf32m || tcx3) st.Npad = (st.N + 31) / 32 * 32;
+        if (tf32m) st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
+        if (tcx3) {
+            tcb.Npad = st.Npad;
+            tcb.dp32 = (st.d + 31) / 32 * 32;
+            tcb.Kb = (int)(st.K < 2048 ? st.K : 2048);
+            tcb.nchunk = 64;
+            while (tcb.nchunk > 1 && st.Npad / tcb.nchunk < 4096) tcb.nchunk /= 2;
+            const int m_tiles = (tcb.Kb + tc::TM - 1) / tc::TM;
+            int ks = (2 * 148 + m_tiles - 1) / m_tiles;                  // ~2 tiles per SM
+            const int kball = (int)(st.Npad / tc::TK);
+            if (ks > kball) ks = kball;
+            if (ks < 1) ks = 1;
+            tcb.ksplit = ks;
+        }
+    }
+    size_t tc_bytes(int which) const {     // 0 X split, 1 XT split, 2 Theta split, 3 Z, 4 R split, 5 Gp32, 6 llp
+        const size_t N = (size_t)st.N, Np = (size_t)tcb.Npad, dp32 = (size_t)tcb.dp32, Kb = (size_t)tcb.Kb;
+        switch (which) {
+            case 0: return 2 * align256(N * dp32 * 4);
+            case 1: return 2 * align256(dp32 * Np * 4);
+            case 2: return 2 * align256((size_t)st.K * dp32 * 4);
+            case 3: return align256(Kb * Np * 4);
+            case 4: return 2 * align256(Kb * Np * 4);
+            case 5: return align256((size_t)tcb.ksplit * Kb * dp32 * 4);
+            default: return align256((size_t)tcb.nchunk * Kb * 8);
         }
     }
     size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * 4); }
@@ -801,6 +974,7 @@ struct LogisticSampler : SamplerImpl {
                    2 * align256(ND_MAX * K * 8) + 256;
         if (mmala) n += 3 * align256(K * st.d * st.d * 8) + 2 * align256(K * 8) + 2 * rowb();
         if (tf32m) n += kr_bytes() + w_bytes() + gp_bytes();
+        if (tcx3) for (int w = 0; w < 7; ++w) n += tc_bytes(w);
         return n;
     }
     int bind(void* ws) override {
@@ -832,8 +1006,38 @@ struct LogisticSampler : SamplerImpl {
             st.W = (float*)p; p += w_bytes();
             st.Gp = (float*)p; p += gp_bytes();
         }
+        if (tcx3) {
+            const size_t N = (size_t)st.N, Np = (size_t)tcb.Npad, dp32 = (size_t)tcb.dp32, Kb = (size_t)tcb.Kb;
+            tcb.Xh = (float*)p; p += align256(N * dp32 * 4);  tcb.Xl = (float*)p; p += align256(N * dp32 * 4);
+            tcb.XTh = (float*)p; p += align256(dp32 * Np * 4); tcb.XTl = (float*)p; p += align256(dp32 * Np * 4);
+            tcb.Th = (float*)p; p += align256((size_t)st.K * dp32 * 4); tcb.Tl = (float*)p; p += align256((size_t)st.K * dp32 * 4);
+            tcb.Z = (float*)p; p += tc_bytes(3);
+            tcb.Rh = (float*)p; p += align256(Kb * Np * 4); tcb.Rl = (float*)p; p += align256(Kb * Np * 4);
+            tcb.Gp32 = (float*)p; p += tc_bytes(5);
+            tcb.llp = (double*)p; p += tc_bytes(6);
+        }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
         if (int rc = lg_tables_ready()) return rc;
+        if (tcx3) {
+            const size_t psm = (size_t)32 * (tcb.dp32 + 1) * 8;
+            lg_tc_prep_x_kernel<<<(unsigned)(tcb.Npad / 32), 256, psm>>>(st, tcb);
+            RMN_KERNEL_CHECK();
+            const uint64_t Np = (uint64_t)tcb.Npad, dp32 = (uint64_t)tcb.dp32;
+            const int nblk = (int)((st.K + tcb.Kb - 1) / tcb.Kb);
+            maps_z_blk.resize(nblk);
+            for (int b = 0; b < nblk; ++b) {
+                const uint64_t rows = (uint64_t)std::min<int64_t>(tcb.Kb, st.K - (int64_t)b * tcb.Kb);
+                tc::GemmMaps& m = maps_z_blk[b];
+                if (int rc = tc::make_tmap_2d(&m.ah, tcb.Th + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.al, tcb.Tl + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.bh, tcb.Xh, (uint64_t)st.N, dp32, dp32, tc::TN)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.bl, tcb.Xl, (uint64_t)st.N, dp32, dp32, tc::TN)) return rc;
+            }
+            if (int rc = tc::make_tmap_2d(&maps_g.ah, tcb.Rh, (uint64_t)tcb.Kb, Np, Np, tc::TM)) return rc;
+            if (int rc = tc::make_tmap_2d(&maps_g.al, tcb.Rl, (uint64_t)tcb.Kb, Np, Np, tc::TM)) return rc;
+            if (int rc = tc::make_tmap_2d(&maps_g.bh, tcb.XTh, dp32, Np, Np, tc::TN)) return rc;
+            if (int rc = tc::make_tmap_2d(&maps_g.bl, tcb.XTl, dp32, Np, Np, tc::TN)) return rc;
+        }
         if (tf32m) {
             const size_t ksm = (size_t)32 * (st.d + 1) * 8;
             lg_build_kr_kernel<<<(unsigned)(st.Npad / 32), 256, ksm>>>(st);
@@ -856,7 +1060,38 @@ struct LogisticSampler : SamplerImpl {
     // Lc / logdet slots must be exactly K*d*d / K apart
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 127) / 128); }
 
+    // RMN_PREC_TF32X3: logits GEMM -> pointwise -> split-K gradient GEMM -> partial sums, per chain block
+    int eval_tc(int fixed_slot, cudaStream_t stream) {
+        const int64_t nth = st.K * tcb.dp32;
+        lg_tc_split_theta_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, stream>>>(st, tcb, fixed_slot);
+        RMN_KERNEL_CHECK(); launches++;
+        const int nblk = (int)maps_z_blk.size();
+        for (int b = 0; b < nblk; ++b) {
+            const int64_t c0 = (int64_t)b * tcb.Kb;
+            const int kb = (int)std::min<int64_t>(tcb.Kb, st.K - c0);
+            ktimer.begin("tf32x3_gemm_kernel+lg_tc_pointwise_kernel", stream);
+            if (int rc = tc::launch_plain(maps_z_blk[b], kb, (int)tcb.Npad, tcb.dp32, tcb.Z, (int)tcb.Npad, stream)) return rc;
+            lg_tc_pointwise_kernel<<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
+            RMN_KERNEL_CHECK();
+            int used = 1;
+            if (int rc = tc::launch_plain_splitk(maps_g, kb, tcb.dp32, (int)tcb.Npad, tcb.Gp32, tcb.dp32, tcb.ksplit,
+                                                 (int64_t)tcb.Kb * tcb.dp32, &used, stream)) return rc;
+            ktimer.end(stream);
+            lg_tc_reduce_kernel<<<(unsigned)(((int64_t)kb * 32 + 127) / 128), 128, 0, stream>>>(st, tcb, c0, kb, used);
+            RMN_KERNEL_CHECK();
+            launches += 4;
+        }
+        return RMN_OK;
+    }
     int eval(int fixed_slot, cudaStream_t stream) {
+        if (tcx3) {
+            if (int rc = eval_tc(fixed_slot, stream)) return rc;
+            if (tf32m) {
+                if (int rc = tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
+                launches++;
+            }
+            return RMN_OK;
+        }
         dim3 grid((unsigned)((st.K + BC - 1) / BC), st.nsplit);
         const bool time_eval = !mmala || tf32m;          // the dominant kernel of this configuration
         if (time_eval) ktimer.begin("lg_eval_kernel", stream);

@@ -269,3 +269,91 @@ def test_fast_sigmoid_softplus_accuracy():
     o1 = [torch.empty_like(dn) for _ in range(3)]
     _lib.check(_lib.load().rmn_logistic_math(1, _lib.ptr(dn), *[_lib.ptr(o) for o in o1], _lib.stream_ptr()))
     assert all(np.isnan(o.cpu().numpy()[0]) for o in o1)
+
+
+# ---------------------------------------------------------------------------------------
+# precision="tf32x3" on the logistic model: the likelihood sweep on the tcgen05 tensor cores
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,N,d,K", [("mala", 20000, 20, 300), ("mmala", 9000, 12, 70), ("mala", 4099, 100, 130)])
+def test_tf32x3_logpost_and_proposal_budget(kind, N, d, K):
+    """Carried log-posterior of the tensor-core sweep vs an fp64 evaluation of the same states
+    (budget: 5e-7 per data row, i.e. 1e-2 at N = 20,000 is generous; measured ~1e-4), proposals vs the
+    fp64 sampler on the same noise, and determinism across tile positions."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=31)
+    dm, _ = _models(X, y, pv)
+    rng = np.random.default_rng(3)
+    th0 = ts[None] + 0.05 * rng.standard_normal((K, d))
+    th0[K // 2:] = th0[0]                                             # second half: identical states
+    xi = rng.standard_normal((3, K, d)); xi[:, K // 2:] = xi[:, :1]
+    u = np.ones((3, K)); u[2] = 0.3
+    mk = (lambda: MALA(0.05, dm.grad_log_posterior)) if kind == "mala" else (lambda: SimplifiedMMALA(0.7, dm))
+    out, lp0 = {}, {}
+    for prec in ("f64", "tf32x3"):
+        s = Sampler(dm, mk(), th0, precision=prec)
+        lp0[prec] = np.asarray(s._chain_logpost[0]).copy()
+        out[prec] = s.run_injected(xi=xi, u=u)
+    budget = 5e-7 * N
+    assert np.max(np.abs(lp0["tf32x3"] - lp0["f64"])) < budget
+    assert np.max(np.abs(lp0["tf32x3"] - lp0["f64"])) > 0             # it IS the fp32-accurate path
+    # first step (nothing accepted yet: u = 1): same states in both modes
+    pa, pb = out["f64"]["prop_theta"][0], out["tf32x3"]["prop_theta"][0]
+    step = np.linalg.norm(pa - th0, axis=1)
+    assert np.all(np.linalg.norm(pa - pb, axis=1) < 5e-3 * step)
+    want = dm.log_posterior_batch(pb).cpu().numpy()
+    assert np.max(np.abs(out["tf32x3"]["prop_logpost"][0] - want)) < budget
+    # determinism: chains K/2.. hold the same state and noise as chain K/2
+    h = K // 2
+    for key in ("prop_theta", "prop_logpost", "logqratio"):
+        a = out["tf32x3"][key]
+        assert np.array_equal(a[:, h:], np.repeat(a[:, h:h + 1], K - h, axis=1)), key
+
+
+def test_tf32x3_logistic_chain_targets_the_same_posterior():
+    from scipy import stats
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA
+    N, d = 400, 5
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=21)
+    dm, om = _models(X, y, pv)
+    np.random.seed(5)
+    o = port.Sampler(om, port.MALA(0.3, om.grad_log_posterior), ts.copy())
+    o.run(13000, 1000, 20)
+    och = np.array(o._chain_thetas)
+    acc = {}
+    for prec in ("tf32x3", "f64"):
+        s = Sampler(dm, MALA(0.3, dm.grad_log_posterior), ts.copy(), K=2048, seed=29, precision=prec)
+        s.run(300, trace=False)
+        s.reset_diagnostics()
+        s.run(300, trace=False)
+        acc[prec] = s.diagnostics(allreduce=False)["accept_rate"]
+        th = np.asarray(s._chain_thetas[-1])
+        for j in range(d):
+            assert stats.ks_2samp(th[:, j], och[:, j]).pvalue > 1e-3
+    assert abs(acc["tf32x3"] - acc["f64"]) < 0.01
+
+
+def test_tf32x3_logistic_config4_budget():
+    """BASELINE config 4 shape (N = 1e6, d = 100): the log-likelihood of the tensor-core sweep against
+    the fp64 kernels at the same points, and chain blocks (K = 2,100 > the 2,048-chain block)."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import MALA
+    N, d, K = 1000000, 100, 2100
+    X, y, ts, pv = port.make_logistic_problem(N, d)
+    dm, _ = _models(X, y, pv)
+    rng = np.random.default_rng(8)
+    th0 = ts[None] + 0.01 * rng.standard_normal((K, d))
+    s = Sampler(dm, MALA(0.02, dm.grad_log_posterior), th0, precision="tf32x3", seed=1)
+    lp = np.asarray(s._chain_logpost[0])
+    want = dm.log_posterior_batch(th0[:64]).cpu().numpy()
+    want_tail = dm.log_posterior_batch(th0[-16:]).cpu().numpy()
+    assert np.max(np.abs(lp[:64] - want)) < 5e-3 and np.max(np.abs(lp[-16:] - want_tail)) < 5e-3
+    s.run(3, trace=False)
+    th = np.asarray(s._chain_thetas[-1])
+    lp = np.asarray(s._chain_logpost[-1])
+    assert np.max(np.abs(lp[:32] - dm.log_posterior_batch(th[:32]).cpu().numpy())) < 5e-3
+    assert 0.3 < s.diagnostics(allreduce=False)["accept_rate"] <= 1.0
