@@ -34,10 +34,12 @@
 // cores, fp32-accurate (3xTF32), as three passes over materialised fp32 matrices instead of the fused
 // fp64 DMMA kernel:
 //   Z[K][N]  = Theta' X^T          GEMM (M = chains, N = data rows, contraction d)      tc_gemm.cu
-//   pointwise: p, softplus in fp64 from z; log-likelihood partial sums in fp64; R = y - p split hi/lo
+//   pointwise: p, softplus in fp64 from z; log-likelihood partial sums in fp64; R = y - p as fp32
 //              (and W = p(1-p) for the mMALA metric)                                    lg_tc_pointwise_kernel
-//   G[K][d]  = R X                 split-K GEMM (M = chains, N = d, contraction over data rows)
-// Chains are processed in blocks of at most 2,048 so Z and R stay at 12 bytes x N x 2,048.  The log-
+//   G[K][d]  = R X                 split-K GEMM (M = chains, N = d, contraction over data rows), SINGLE-pass
+//                                  TF32: like the metric, the gradient only shapes the proposal (the same
+//                                  function theta -> g~(theta) enters both proposal densities)
+// Chains are processed in blocks of at most 2,048 so Z and R stay at 8 bytes x N x 2,048.  The log-
 // likelihood carries the fp32 rounding of z (~1e-6 per row, |error| <~ 1e-3 at N = 1e6, measured in
 // tests/test_gpu_logistic.py) as a deterministic function of theta; the accept test, prior, proposal
 // arithmetic and Cholesky stay fp64.
@@ -50,7 +52,8 @@ namespace tc {
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
-                        int64_t split_stride, int* used, cudaStream_t st);
+                        int64_t split_stride, int* used, cudaStream_t st, int passes);
+int launch_plain_mfast(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 }
 
 namespace {
@@ -445,7 +448,7 @@ struct LgTC {
     float* XTh; float* XTl;    // [dp32][Npad]   X^T split, the B operand of G = R X
     float* Th; float* Tl;      // [K][dp32]      Theta' split
     float* Z;                  // [Kb][Npad]     logits of the chain block in flight
-    float* Rh; float* Rl;      // [Kb][Npad]     y - p, split
+    float* Rh;                 // [Kb][Npad]     y - p (fp32; the gradient GEMM is single-pass TF32)
     float* Gp32;               // [ksplit][Kb][dp32]  split-K partial gradients
     double* llp;               // [nchunk][Kb]   log-likelihood partial sums
     int dp32, Kb, nchunk, ksplit; int64_t Npad;
@@ -515,13 +518,12 @@ lg_tc_pointwise_kernel(LogisticState st, LgTC tc, int64_t c0, int kb) {
     const int64_t i_end = min(tc.Npad, i_begin + rows_per);
     const float* zrow = tc.Z + (int64_t)cl * tc.Npad;
     float* rh = tc.Rh + (int64_t)cl * tc.Npad;
-    float* rl = tc.Rl + (int64_t)cl * tc.Npad;
     float* wrow = st.W ? st.W + (c0 + cl) * st.Npad : nullptr;      // st.Npad == tc.Npad
     double ll = 0.0;
     for (int64_t i4 = i_begin + 4 * (int64_t)threadIdx.x; i4 < i_end; i4 += 4 * PW_THREADS) {
         const float4 z4 = *reinterpret_cast<const float4*>(zrow + i4);
         const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
-        float h[4], l[4], w[4];
+        float h[4], w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int64_t i = i4 + e;
@@ -531,11 +533,10 @@ lg_tc_pointwise_kernel(LogisticState st, LgTC tc, int64_t c0, int kb) {
             double p, sp, pq;
             lgmath::sigmoid_softplus(zz, tab, p, sp, pq);
             ll += ok ? (yv * zz - sp) : 0.0;
-            split_f64(ok ? (yv - p) : 0.0, h[e], l[e]);
+            h[e] = ok ? (float)(yv - p) : 0.f;
             w[e] = ok ? (float)pq : 0.f;
         }
         *reinterpret_cast<float4*>(rh + i4) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(rl + i4) = make_float4(l[0], l[1], l[2], l[3]);
         if (wrow) *reinterpret_cast<float4*>(wrow + i4) = make_float4(w[0], w[1], w[2], w[3]);
     }
     ll = group_sum<32>(ll);
@@ -955,7 +956,7 @@ struct LogisticSampler : SamplerImpl {
             case 1: return 2 * align256(dp32 * Np * 4);
             case 2: return 2 * align256((size_t)st.K * dp32 * 4);
             case 3: return align256(Kb * Np * 4);
-            case 4: return 2 * align256(Kb * Np * 4);
+            case 4: return align256(Kb * Np * 4);
             case 5: return align256((size_t)tcb.ksplit * Kb * dp32 * 4);
             default: return align256((size_t)tcb.nchunk * Kb * 8);
         }
@@ -1012,7 +1013,7 @@ struct LogisticSampler : SamplerImpl {
             tcb.XTh = (float*)p; p += align256(dp32 * Np * 4); tcb.XTl = (float*)p; p += align256(dp32 * Np * 4);
             tcb.Th = (float*)p; p += align256((size_t)st.K * dp32 * 4); tcb.Tl = (float*)p; p += align256((size_t)st.K * dp32 * 4);
             tcb.Z = (float*)p; p += tc_bytes(3);
-            tcb.Rh = (float*)p; p += align256(Kb * Np * 4); tcb.Rl = (float*)p; p += align256(Kb * Np * 4);
+            tcb.Rh = (float*)p; p += align256(Kb * Np * 4);
             tcb.Gp32 = (float*)p; p += tc_bytes(5);
             tcb.llp = (double*)p; p += tc_bytes(6);
         }
@@ -1034,9 +1035,8 @@ struct LogisticSampler : SamplerImpl {
                 if (int rc = tc::make_tmap_2d(&m.bl, tcb.Xl, (uint64_t)st.N, dp32, dp32, tc::TN)) return rc;
             }
             if (int rc = tc::make_tmap_2d(&maps_g.ah, tcb.Rh, (uint64_t)tcb.Kb, Np, Np, tc::TM)) return rc;
-            if (int rc = tc::make_tmap_2d(&maps_g.al, tcb.Rl, (uint64_t)tcb.Kb, Np, Np, tc::TM)) return rc;
             if (int rc = tc::make_tmap_2d(&maps_g.bh, tcb.XTh, dp32, Np, Np, tc::TN)) return rc;
-            if (int rc = tc::make_tmap_2d(&maps_g.bl, tcb.XTl, dp32, Np, Np, tc::TN)) return rc;
+            maps_g.al = maps_g.ah; maps_g.bl = maps_g.bh;
         }
         if (tf32m) {
             const size_t ksm = (size_t)32 * (st.d + 1) * 8;
@@ -1070,12 +1070,12 @@ struct LogisticSampler : SamplerImpl {
             const int64_t c0 = (int64_t)b * tcb.Kb;
             const int kb = (int)std::min<int64_t>(tcb.Kb, st.K - c0);
             ktimer.begin("tf32x3_gemm_kernel+lg_tc_pointwise_kernel", stream);
-            if (int rc = tc::launch_plain(maps_z_blk[b], kb, (int)tcb.Npad, tcb.dp32, tcb.Z, (int)tcb.Npad, stream)) return rc;
+            if (int rc = tc::launch_plain_mfast(maps_z_blk[b], kb, (int)tcb.Npad, tcb.dp32, tcb.Z, (int)tcb.Npad, stream)) return rc;
             lg_tc_pointwise_kernel<<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
             RMN_KERNEL_CHECK();
             int used = 1;
             if (int rc = tc::launch_plain_splitk(maps_g, kb, tcb.dp32, (int)tcb.Npad, tcb.Gp32, tcb.dp32, tcb.ksplit,
-                                                 (int64_t)tcb.Kb * tcb.dp32, &used, stream)) return rc;
+                                                 (int64_t)tcb.Kb * tcb.dp32, &used, stream, 1)) return rc;
             ktimer.end(stream);
             lg_tc_reduce_kernel<<<(unsigned)(((int64_t)kb * 32 + 127) / 128), 128, 0, stream>>>(st, tcb, c0, kb, used);
             RMN_KERNEL_CHECK();

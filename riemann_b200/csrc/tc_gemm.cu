@@ -68,7 +68,10 @@ enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 template <int EPI, int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
-                   int ldc, MalaEpi ep, int ksplit, int kb_per, int64_t split_stride) {
+                   int ldc, MalaEpi ep, int ksplit, int kb_per, int64_t split_stride, int m_fastest) {
+    // m_fastest: tile order.  0 = n fastest (CTAs running together share rows of A in L2), 1 = m fastest
+    // (they share rows of B: the logits GEMM, whose A -- the chains' Theta -- is tiny and whose B -- the data
+    // matrix -- should cross HBM once).
     // ksplit > 1 (EPI_PLAIN only): the k-blocks are divided into ksplit contiguous ranges; a tile is
     // (m_tile, n_tile, split) and split s stores its partial product at C + s * split_stride (summed by
     // the caller) -- this is how a product with few output tiles but a long contraction (the logistic
@@ -84,6 +87,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+    float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [EPI_WARPS][32][20]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB_all = Kdim / TK;
@@ -115,7 +119,8 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             const int64_t mn = tile % mn_tiles;
             const int kb0 = (int)(tile / mn_tiles) * kb_per;
             const int kb1 = min(KB_all, kb0 + kb_per);
-            const int m0 = (int)(mn / n_tiles) * TM, n0 = (int)(mn % n_tiles) * TN;
+            const int m0 = (int)(m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
+            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * TN;
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -131,7 +136,9 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer (one thread) =====
-        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+        // UMMA N = the valid width of B rounded up to 16 (a d-wide gradient tile does not pay for 256 columns)
+        const int n_eff = (N >= TN) ? TN : ((N + 15) / 16 * 16);
+        const uint32_t idesc = umma_idesc_tf32(TM, n_eff);
         uint32_t it = 0, ti = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int a = ti % ACC_STAGES;
@@ -169,8 +176,8 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int a = ti % ACC_STAGES;
             const int64_t mn = tile % mn_tiles;
-            const int64_t m0 = (mn / n_tiles) * TM;
-            const int n0 = (int)(mn % n_tiles) * TN;
+            const int64_t m0 = (m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
+            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * TN;
             float* Cs = (EPI == EPI_PLAIN) ? C + (tile / mn_tiles) * split_stride : C;
             mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
             tc_fence_after();
@@ -183,13 +190,27 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 float v[16];
                 tmem_ld_32x16(trow + (uint32_t)c0, v);
                 const int n = n0 + half * (TN / 2) + c0;
-                if (!rok || n >= N) continue;
                 if (EPI == EPI_PLAIN) {
-                    float4* dst = reinterpret_cast<float4*>(Cs + m * ldc + n);
+                    // One TMEM lane (= output row) per thread would store 32 rows x 16 B per instruction;
+                    // transposing the 32 x 16 chunk through shared memory makes it 8 rows x 64 B.
+                    if (n >= N) continue;                               // warp-uniform
+                    float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
+                    float4* w4 = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (n + 4 * i < N) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                } else {
+                    for (int i = 0; i < 4; ++i) w4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int rr = it * 8 + (lane >> 2), cg = (lane & 3) * 4;
+                        const int64_t mr = m0 + q * 32 + rr;
+                        const float4 val = *reinterpret_cast<const float4*>(stg + rr * 20 + cg);
+                        if (mr < M && n + cg < N) *reinterpret_cast<float4*>(Cs + mr * ldc + n + cg) = val;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                if (!rok || n >= N) continue;
+                {
                     const size_t off = (size_t)m * ldc + n;
                     float4* dst = reinterpret_cast<float4*>(ep.vp + off);
                     const float4* yh = reinterpret_cast<const float4*>(ep.yph + off);
@@ -223,7 +244,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
             if (EPI == EPI_MALA && rok) {
-                const size_t blk = (size_t)(mn % n_tiles) * 2 + half;              // 128-column block index
+                const size_t blk = (size_t)(n0 / TN) * 2 + half;                   // 128-column block index
                 ep.partq[blk * M + m] = pq;
                 if (ep.mala) ep.partk[blk * M + m] = pk;
             }
@@ -238,7 +259,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 }
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
-                         cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0) {
+                         cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0) {
     if (Kdim % TK != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
     if (ksplit < 1 || ksplit > Kdim / TK || (ep && ksplit != 1)) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
     // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
@@ -255,9 +276,9 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep, 1, kbp, 0);
-    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride);
-    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride);
+    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep, 1, kbp, 0, 0);
+    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest);
+    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
@@ -271,10 +292,14 @@ int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C
 // 3-pass product with the contraction split into `ksplit` ranges; returns the number of splits actually
 // used through *used (<= ksplit); partial s is at C + s * split_stride
 int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
-                        int64_t split_stride, int* used, cudaStream_t st) {
+                        int64_t split_stride, int* used, cudaStream_t st, int passes) {
     const int kbp = (Kdim / TK + ksplit - 1) / ksplit;
     if (used) *used = (Kdim / TK + kbp - 1) / kbp;
-    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 3, ksplit, split_stride);
+    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, passes, ksplit, split_stride);
+}
+// 3-pass product, m-fastest tile order (A small and L2-resident, B streamed once)
+int launch_plain_mfast(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 3, 1, 0, 1);
 }
 int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
                 const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
@@ -310,7 +335,7 @@ extern "C" int rmn_tf32x3_gemm_splitk(int64_t M, int N, int Kdim, int ksplit, co
     if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN))) return rc;
     if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN))) return rc;
     if (ksplit > Kdim / 32) ksplit = Kdim / 32;
-    return tc::launch_plain_splitk(maps, M, N, Kdim, d_C, N, ksplit, (int64_t)M * N, used_splits, (cudaStream_t)stream);
+    return tc::launch_plain_splitk(maps, M, N, Kdim, d_C, N, ksplit, (int64_t)M * N, used_splits, (cudaStream_t)stream, 3);
 }
 
 // Validation entry: C[M][N] (fp32, ld = N) ~= (Ah + Al)(Bh + Bl)^T; A* are [M][K], B* are [N][K], fp32, K % 32 == 0.

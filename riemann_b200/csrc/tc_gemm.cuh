@@ -26,7 +26,8 @@ constexpr int STAGES = 2;
 constexpr int A_BYTES = TM * TK * 4;                 // 16 KB
 constexpr int B_BYTES = TN * TK * 4;                 // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // Ah Al Bh Bl = 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_FLOATS = 32 * 20;      // per epilogue warp: 32 rows x 16 columns (+4 pad) for the coalescing transpose
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * EPI_STAGE_FLOATS * 4;
 constexpr int THREADS = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (2 per TMEM lane quarter)
 constexpr int EPI_WARPS = 8;
 constexpr int ACC_STAGES = 2;    // accumulator double buffering: epilogue(i) overlaps mainloop(i+1)
