@@ -332,6 +332,24 @@ def run_engine(args):
     # ---- end-to-end leg: host buffers in, host results out, copies inside the timed region
     e2e = run_e2e(args, s, T, Kg, world, sync_all)
 
+    # ---- estimator cross-check (outside every timed region): Sokal-window integrated autocorrelation time
+    #      (emcee's estimator, examples/test_randomwalk.py:42) of a traced subset of chains next to the
+    #      moment-based tau = n B / W of the diagnostics block that min_ess_per_sec is computed from
+    tau_check = None
+    if rank == 0 and wl == "changepoint":
+        from riemann_b200 import diagnostics as dgn
+        s2, _ = build_workload(wl, 128, seed + 1, 0, args.precision)
+        s2.run(burn, trace=False)
+        s2.run(8000, 0, 1)
+        tr = s2._chain_thetas
+        x = np.stack([tr.sig[1:], tr.k[1:].astype(np.float64)], axis=2)          # [N, K, 2]: sigma, k
+        tau_s = dgn.integrated_time_chains(x)
+        tau_m = diag["tau"][:2]
+        tau_check = {"functionals": ["sigma", "k"], "sokal_tau_steps": [float(t) for t in tau_s],
+                     "moment_tau_steps": [float(t) for t in tau_m],
+                     "note": "Sokal tau (c = 5) of 128 traced chains x 8000 steps vs tau = n B / W of the "
+                             "%d bench chains (MH steps per independent sample)" % K_total}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -416,6 +434,7 @@ def run_engine(args):
         "diagnostics": {"accept_rate": diag["accept_rate"], "max_rhat": float(np.nanmax(diag["rhat"])),
                         "min_ess": diag["min_ess"], "overflows": diag["overflows"],
                         "chains": diag["chains"], "steps_per_chain": diag["steps"]},
+        "tau_check": tau_check,
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "clocks": clk, "peaks_source": peak_src,
     }

@@ -451,6 +451,7 @@ struct LgTC {
     float* Rh;                 // [Kb][Npad]     y - p (fp32; the gradient GEMM is single-pass TF32)
     float* Gp32;               // [ksplit][Kb][dp32]  split-K partial gradients
     double* llp;               // [nchunk][Kb]   log-likelihood partial sums
+    uint8_t* yb;               // [Npad]         labels as bytes (y is 0/1)
     int dp32, Kb, nchunk, ksplit; int64_t Npad;
 };
 
@@ -480,6 +481,7 @@ lg_tc_prep_x_kernel(LogisticState st, LgTC tc) {
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (i0 + lane >= tc.Npad) return;
+    if (warp == 0) tc.yb[i0 + lane] = (i0 + lane < st.N && st.y[i0 + lane] != 0.0) ? 1 : 0;
     for (int k = warp; k < dp32; k += nw) {
         float hi, lo;
         split_f64(sm[lane * ld + k], hi, lo);
@@ -504,8 +506,12 @@ __global__ void lg_tc_split_theta_kernel(LogisticState st, LgTC tc, int fixed_sl
     tc.Th[idx] = hi; tc.Tl[idx] = lo;
 }
 
-// pointwise stage for the chain block [c0, c0 + kb): block = (row chunk, chain)
+// pointwise stage for the chain block [c0, c0 + kb): block = (row chunk, chain).  Rows i >= N (padding up
+// to Npad) are computed like the others -- their R and W values multiply zero columns of X^T / KR in the
+// GEMMs that follow -- and only the log-likelihood sum masks them.  NaN logits (a NaN state) need no
+// handling here: the prior term of such a state is already NaN -> log-posterior -inf (model.py:50-54).
 constexpr int PW_THREADS = 256;
+template <bool HASW>
 __global__ void __launch_bounds__(PW_THREADS)
 lg_tc_pointwise_kernel(LogisticState st, LgTC tc, int64_t c0, int kb) {
     __shared__ double tab[lgmath::TAB_DOUBLES];
@@ -518,26 +524,27 @@ lg_tc_pointwise_kernel(LogisticState st, LgTC tc, int64_t c0, int kb) {
     const int64_t i_end = min(tc.Npad, i_begin + rows_per);
     const float* zrow = tc.Z + (int64_t)cl * tc.Npad;
     float* rh = tc.Rh + (int64_t)cl * tc.Npad;
-    float* wrow = st.W ? st.W + (c0 + cl) * st.Npad : nullptr;      // st.Npad == tc.Npad
+    float* wrow = HASW ? st.W + (c0 + cl) * st.Npad : nullptr;      // st.Npad == tc.Npad
+    const int64_t N = st.N;
     double ll = 0.0;
     for (int64_t i4 = i_begin + 4 * (int64_t)threadIdx.x; i4 < i_end; i4 += 4 * PW_THREADS) {
         const float4 z4 = *reinterpret_cast<const float4*>(zrow + i4);
+        const uint32_t y4 = *reinterpret_cast<const uint32_t*>(tc.yb + i4);     // four 0/1 bytes
         const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
         float h[4], w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int64_t i = i4 + e;
-            const bool ok = i < st.N;
             const double zz = (double)zv[e];
-            const double yv = ok ? st.y[i] : 0.0;
+            const bool y1 = (y4 >> (8 * e)) & 1u;
             double p, sp, pq;
-            lgmath::sigmoid_softplus(zz, tab, p, sp, pq);
-            ll += ok ? (yv * zz - sp) : 0.0;
-            h[e] = ok ? (float)(yv - p) : 0.f;
-            w[e] = ok ? (float)pq : 0.f;
+            lgmath::sigmoid_softplus<false>(zz, tab, p, sp, pq);
+            const double t = (y1 ? zz : 0.0) - sp;                  // y z - softplus(z)
+            ll += (i4 + e < N) ? t : 0.0;
+            h[e] = (float)((y1 ? 1.0 : 0.0) - p);
+            if (HASW) w[e] = (float)pq;
         }
         *reinterpret_cast<float4*>(rh + i4) = make_float4(h[0], h[1], h[2], h[3]);
-        if (wrow) *reinterpret_cast<float4*>(wrow + i4) = make_float4(w[0], w[1], w[2], w[3]);
+        if (HASW) *reinterpret_cast<float4*>(wrow + i4) = make_float4(w[0], w[1], w[2], w[3]);
     }
     ll = group_sum<32>(ll);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
@@ -949,7 +956,7 @@ struct LogisticSampler : SamplerImpl {
             tcb.ksplit = ks;
         }
     }
-    size_t tc_bytes(int which) const {     // 0 X split, 1 XT split, 2 Theta split, 3 Z, 4 R split, 5 Gp32, 6 llp
+    size_t tc_bytes(int which) const {     // 0 X split, 1 XT split, 2 Theta split, 3 Z, 4 R, 5 Gp32, 6 llp, 7 y bytes
         const size_t N = (size_t)st.N, Np = (size_t)tcb.Npad, dp32 = (size_t)tcb.dp32, Kb = (size_t)tcb.Kb;
         switch (which) {
             case 0: return 2 * align256(N * dp32 * 4);
@@ -958,7 +965,8 @@ struct LogisticSampler : SamplerImpl {
             case 3: return align256(Kb * Np * 4);
             case 4: return align256(Kb * Np * 4);
             case 5: return align256((size_t)tcb.ksplit * Kb * dp32 * 4);
-            default: return align256((size_t)tcb.nchunk * Kb * 8);
+            case 6: return align256((size_t)tcb.nchunk * Kb * 8);
+            default: return align256(Np);
         }
     }
     size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * 4); }
@@ -975,7 +983,7 @@ struct LogisticSampler : SamplerImpl {
                    2 * align256(ND_MAX * K * 8) + 256;
         if (mmala) n += 3 * align256(K * st.d * st.d * 8) + 2 * align256(K * 8) + 2 * rowb();
         if (tf32m) n += kr_bytes() + w_bytes() + gp_bytes();
-        if (tcx3) for (int w = 0; w < 7; ++w) n += tc_bytes(w);
+        if (tcx3) for (int w = 0; w < 8; ++w) n += tc_bytes(w);
         return n;
     }
     int bind(void* ws) override {
@@ -1016,6 +1024,7 @@ struct LogisticSampler : SamplerImpl {
             tcb.Rh = (float*)p; p += align256(Kb * Np * 4);
             tcb.Gp32 = (float*)p; p += tc_bytes(5);
             tcb.llp = (double*)p; p += tc_bytes(6);
+            tcb.yb = (uint8_t*)p; p += tc_bytes(7);
         }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
         if (int rc = lg_tables_ready()) return rc;
@@ -1071,7 +1080,8 @@ struct LogisticSampler : SamplerImpl {
             const int kb = (int)std::min<int64_t>(tcb.Kb, st.K - c0);
             ktimer.begin("tf32x3_gemm_kernel+lg_tc_pointwise_kernel", stream);
             if (int rc = tc::launch_plain_mfast(maps_z_blk[b], kb, (int)tcb.Npad, tcb.dp32, tcb.Z, (int)tcb.Npad, stream)) return rc;
-            lg_tc_pointwise_kernel<<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
+            if (st.W) lg_tc_pointwise_kernel<true><<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
+            else lg_tc_pointwise_kernel<false><<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
             RMN_KERNEL_CHECK();
             int used = 1;
             if (int rc = tc::launch_plain_splitk(maps_g, kb, tcb.dp32, (int)tcb.Npad, tcb.Gp32, tcb.dp32, tcb.ksplit,

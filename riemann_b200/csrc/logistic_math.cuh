@@ -31,7 +31,9 @@ inline void fill_tables(double* tab) {
     }
 }
 
-// p = sigmoid(z), sp = softplus(z) = log(1 + e^z), pq = p (1 - p)
+// p = sigmoid(z), sp = softplus(z) = log(1 + e^z), pq = p (1 - p).
+// NANPROP = false skips the NaN propagation (callers whose prior term already maps a NaN state to -inf).
+template <bool NANPROP = true>
 __device__ __forceinline__ void sigmoid_softplus(double zz, const double* __restrict__ tab, double& p, double& sp,
                                                  double& pq) {
     const double* T2 = tab;
@@ -74,7 +76,7 @@ __device__ __forceinline__ void sigmoid_softplus(double zz, const double* __rest
     p = (zz >= 0.0) ? inv : ei;
     sp = fmax(zz, 0.0) + lm;
     pq = ei * inv;
-    if (zz != zz) { p = zz; sp = zz; pq = zz; }
+    if (NANPROP && zz != zz) { p = zz; sp = zz; pq = zz; }
 }
 
 }  // namespace lgmath

@@ -10,3 +10,6 @@ run cfg4_logistic_mala --workload logistic_mala --steps 2 --warmup 3 --iters 2 -
 run cfg4_logistic_mala_k8192 --workload logistic_mala --chains 8192 --steps 2 --warmup 3 --iters 1 --no-cpu
 run cfg5_logistic_mmala --workload logistic_mmala --chains 4096 --steps 2 --warmup 3 --iters 1 --cpu-seconds 10
 run cfg5_logistic_mmala_tf32metric --workload logistic_mmala --chains 4096 --steps 2 --warmup 3 --iters 1 --precision tf32-metric --no-cpu
+run cfg4_logistic_mala_tf32x3 --workload logistic_mala --steps 2 --warmup 3 --iters 2 --precision tf32x3 --no-cpu
+run cfg4_logistic_mala_k8192_tf32x3 --workload logistic_mala --chains 8192 --steps 2 --warmup 3 --iters 1 --precision tf32x3 --no-cpu
+run cfg5_logistic_mmala_tf32x3 --workload logistic_mmala --chains 4096 --steps 2 --warmup 3 --iters 1 --precision tf32x3 --no-cpu

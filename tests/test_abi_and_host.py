@@ -143,3 +143,31 @@ def test_diagnostics_allreduce_two_ranks_gloo(tmp_path):
                         str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_sokal_tau_matches_ar1_and_oracle():
+    """riemann_b200.diagnostics (emcee-style integrated autocorrelation time) on AR(1) chains with the
+    analytic tau = (1 + phi) / (1 - phi), against oracle/ess.py, and against the engine's moment-based
+    many-chain estimator (summarize_block)."""
+    from oracle import ess as oess
+    from riemann_b200 import diagnostics as dg
+    from riemann_b200.distributed import summarize_block
+    rng = np.random.default_rng(0)
+    N, K = 4000, 256
+    for phi in (0.5, 0.9):
+        e = rng.standard_normal((N + 500, K)) * np.sqrt(1 - phi * phi)
+        x = np.zeros_like(e)
+        for t in range(1, len(e)):
+            x[t] = phi * x[t - 1] + e[t]
+        x = x[500:]
+        want = (1 + phi) / (1 - phi)
+        tau_multi = dg.integrated_time_chains(x)[0]
+        assert abs(tau_multi / want - 1) < 0.05
+        one = dg.integrated_time(x[:, 0])[0]
+        assert abs(one - oess.integrated_time(x[:, 0])[0]) < 1e-9             # same algorithm as the oracle
+        assert abs(tau_multi - oess.integrated_time_multi(x[:, :, None])[0]) < 1e-9
+        # the moment-based estimator of the diagnostics block on the same chains
+        m, v = x.mean(0), x.var(0)
+        blk = np.array([K, N, 0, 0, N, 0, m.sum(), (m * m).sum(), v.sum()])
+        assert abs(summarize_block(blk)["tau"][0] / want - 1) < 0.25
+        assert abs(dg.effective_sample_size(x)[0] / (N * K / want) - 1) < 0.05
