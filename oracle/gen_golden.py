@@ -249,6 +249,10 @@ def _n1_dense_fixtures(R):
                     extra=dict(eps=np.float64(0.15), nsteps=np.int64(4), mu=mu12, C=C12))
     _vector_fixture(R, "adapthmc3_gauss12d", g12, R.AdaptScaleHMC(0.1, 3, g12.grad_log_likelihood), mu12 - 0.3, 800, 402,
                     extra=dict(eps=np.float64(0.1), nsteps=np.int64(3), mu=mu12, C=C12), track_scale=True)
+    # "next" row N2 on the dense path: pCN (randomwalk.py:78-100) with a dense covariance
+    g12z = R.MultiGaussianDist(np.zeros(12), C12)                  # pCN shrinks towards 0: zero-mean target
+    _vector_fixture(R, "pcn_gauss12d", g12z, R.pCN(0.6 * C12, 0.85), np.full(12, 0.3), 600, 404,
+                    extra=dict(C0=0.6 * C12, rho=np.float64(0.85), mu=np.zeros(12), C=C12))
     g100 = R.benchmarks.benchmark_gauss100d_corr
     _vector_fixture(R, "hmc5_gauss100d", g100, R.VanillaHMC(0.1, 5, g100.grad_log_likelihood), np.zeros(100), 200, 403,
                     extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)))

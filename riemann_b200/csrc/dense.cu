@@ -13,6 +13,8 @@
 //   kernel 1  finish_propose : per row -- finish the previous step (sum the GEMM's row
 //             partials, log-posterior, log q ratio, accept, adapt), then draw xi (Philox or
 //             injected) and write the next proposal.  One warp per chain row, coalesced.
+//             pCN (randomwalk.py:78-100): two extra GEMMs per step, theta' = rho theta + rho_c xi L^T and
+//             the reverse residual (rho_c L)^-1 (theta - rho theta'), whose squared norm is the log q ratio.
 //             Nsteps > 1 (leapfrog, hamiltonian.py:13-52): Nsteps - 1 extra [gradient GEMM,
 //             leapfrog_mid_kernel] pairs advance the trajectory in place on the proposal slot.
 //   kernel 2  gemm_abt       : C = A B^T in fp64 on the tensor cores (DMMA m8n8k4),
@@ -33,7 +35,7 @@ constexpr int GEMM_THREADS = 256;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (BM + BN) * LDT * 8;
 constexpr int ND_MAX = 8;          // tracked functionals: first 7 coordinates + mean(theta)
 
-enum { EPI_LOGPOST_RW = 0, EPI_LOGPOST_MALA = 1, EPI_RWPROP = 2 };
+enum { EPI_LOGPOST_RW = 0, EPI_LOGPOST_MALA = 1, EPI_RWPROP = 2, EPI_PCNPROP = 3, EPI_PCNREV = 4 };
 
 struct DenseState {
     int64_t K; int d, dp, nblk;    // nblk = column blocks of 32 (partials per row)
@@ -50,6 +52,7 @@ struct DenseState {
     long long* dacc;               // accepts since diagnostics reset
     double* S1; double* S2;        // [ND_MAX][K]
     const double* mu;              // [dp] (padded copy)
+    double rho, rho_c;             // pCN (randomwalk.py:83-86)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -96,7 +99,8 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
         const int64_t m = m0 + row;
         a_ok[i] = m < K;
         const int64_t mm = a_ok[i] ? m : 0;
-        if (EPI == EPI_RWPROP) a_src[i] = st.Xi + mm * dp + c2;
+        if (EPI == EPI_RWPROP || EPI == EPI_PCNPROP) a_src[i] = st.Xi + mm * dp + c2;
+        else if (EPI == EPI_PCNREV) a_src[i] = st.V + ((int64_t)(st.cur[mm] ^ 1) * K + mm) * dp + c2;   // D, see below
         else a_src[i] = st.Y + ((int64_t)(st.cur[mm] ^ 1) * K + mm) * dp + c2;
         const int n = n0 + row;
         b_ok[i] = n < dp;
@@ -155,7 +159,42 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
         const int64_t mm = rok ? m : 0;
         const int c = st.cur[mm];
         double pq = 0.0, pk = 0.0;
-        if (EPI == EPI_RWPROP) {
+        if (EPI == EPI_PCNPROP) {
+            // pCN (randomwalk.py:88-94): theta' = rho theta + rho_c L xi; the residual of the REVERSE move,
+            // D = theta - rho theta', is parked in the proposal slot of V (free until the log-posterior GEMM)
+            const double* yc = st.Y + ((int64_t)c * K + mm) * dp;
+            double* yp = st.Y + ((int64_t)(c ^ 1) * K + mm) * dp;
+            double* dv = st.V + ((int64_t)(c ^ 1) * K + mm) * dp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) {
+                    const double2 y = *reinterpret_cast<const double2*>(yc + n);
+                    const double2 mu = *reinterpret_cast<const double2*>(st.mu + n);
+                    const double th0 = y.x + mu.x, th1 = y.y + mu.y;
+                    const double tp0 = st.rho * th0 + st.rho_c * acc[i][j][0];
+                    const double tp1 = st.rho * th1 + st.rho_c * acc[i][j][1];
+                    const bool in0 = n < st.d, in1 = n + 1 < st.d;
+                    *reinterpret_cast<double2*>(yp + n) = make_double2(in0 ? tp0 - mu.x : 0.0, in1 ? tp1 - mu.y : 0.0);
+                    *reinterpret_cast<double2*>(dv + n) = make_double2(in0 ? th0 - st.rho * tp0 : 0.0,
+                                                                       in1 ? th1 - st.rho * tp1 : 0.0);
+                }
+            }
+        } else if (EPI == EPI_PCNREV) {
+            // u_rev = (rho_c L)^-1 D  (randomwalk.py:98): acc = D Linv^T; only |u_rev|^2 is needed
+            const double irc = 1.0 / st.rho_c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) {
+                    const double u0 = acc[i][j][0] * irc, u1 = acc[i][j][1] * irc;
+                    pk += u0 * u0 + u1 * u1;
+                }
+            }
+            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+            if (rok && t == 0 && blk < st.nblk) st.partk[(int64_t)blk * K + m] = pk;
+        } else if (EPI == EPI_RWPROP) {
             const double sc = st.epsrow[mm];
             const double* yc = st.Y + ((int64_t)c * K + mm) * dp;
             double* yp = st.Y + ((int64_t)(c ^ 1) * K + mm) * dp;
@@ -234,14 +273,17 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
         double q = 0.0, k1 = 0.0;
         for (int b = lane; b < st.nblk; b += 32) {
             q += st.partq[(int64_t)b * K + r];
-            if (sp.prop_kind == RMN_PROP_HMC) k1 += st.partk[(int64_t)b * K + r];
+            if (sp.prop_kind != RMN_PROP_RW) k1 += st.partk[(int64_t)b * K + r];
         }
         // fixed-order reduction => bitwise reproducible log-posteriors
         q = group_sum<32>(q);
         k1 = group_sum<32>(k1);
         const double ll = -0.5 * ((q + sp.c1) + sp.c2);            // gaussian.py:52
         const double lpn = combine_logpost(0.0, ll);
-        const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r]) : 0.0;   // hamiltonian.py:89
+        // HMC: kinetic-energy difference (hamiltonian.py:89); pCN: -(|u_fwd|^2 - |u_rev|^2)/2 with
+        // u_fwd = (rho_c L)^-1 (theta' - rho theta) = xi (randomwalk.py:95-100)
+        const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r])
+                         : ((sp.prop_kind == RMN_PROP_PCN) ? -0.5 * (st.k0[r] - k1) : 0.0);
         const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
         const bool acc = mh_accept(lpn, lp, lqr, u);
         if (sp.tr_prop_theta) {                  // the proposal = what Proposal.propose returned
@@ -310,13 +352,14 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
             // the momentum after the initial half step rides in the Xi buffer through the trajectory
             *reinterpret_cast<double2*>(xo + j4) = make_double2(xi[0], xi[1]);
             *reinterpret_cast<double2*>(xo + j4 + 2) = make_double2(xi[2], xi[3]);
-        } else if (sp.rw_diag) {
+        } else if (sp.prop_kind == RMN_PROP_RW && sp.rw_diag) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) out[q] = yv[q] + scale * (sp.Ldiag[j4 + q] * xi[q]);   // randomwalk.py:26
         } else {
-            // dense L: write xi; a GEMM (EPI_RWPROP) forms y + scale * xi L^T
+            // dense L: write xi; a GEMM (EPI_RWPROP / EPI_PCNPROP) forms y + scale * xi L^T resp. the pCN move
             *reinterpret_cast<double2*>(xo + j4) = make_double2(xi[0], xi[1]);
             *reinterpret_cast<double2*>(xo + j4 + 2) = make_double2(xi[2], xi[3]);
+            k0 += (xi[0] * xi[0] + xi[1] * xi[1]) + (xi[2] * xi[2] + xi[3] * xi[3]);
             continue;
         }
         *reinterpret_cast<double2*>(yp + j4) = make_double2(out[0], out[1]);
@@ -400,7 +443,8 @@ struct DenseGaussSampler : SamplerImpl {
     rmn_sampler* s;
     DenseState st{};
     double* d_Ppad = nullptr;     // [dp][dp] zero-padded precision
-    double* d_Lpad = nullptr;     // [dp][dp] zero-padded chol(C0) (dense RW) or nullptr
+    double* d_Lpad = nullptr;     // [dp][dp] zero-padded chol(C0) (dense RW, pCN) or nullptr
+    double* d_Linvpad = nullptr;  // [dp][dp] zero-padded chol(C0)^-1 (pCN)
     double* d_Ldiag = nullptr;    // [dp]
     double* d_mupad = nullptr;
     bool rw_diag = true;
@@ -409,7 +453,7 @@ struct DenseGaussSampler : SamplerImpl {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 15) / 16 * 16; st.nblk = (st.dp + 31) / 32;
     }
     ~DenseGaussSampler() override {
-        cudaFree(d_Ppad); cudaFree(d_Lpad); cudaFree(d_Ldiag); cudaFree(d_mupad);
+        cudaFree(d_Ppad); cudaFree(d_Lpad); cudaFree(d_Linvpad); cudaFree(d_Ldiag); cudaFree(d_mupad);
     }
     size_t row_bytes() const { return align256((size_t)st.K * st.dp * 8); }
     size_t workspace_bytes() const override {
@@ -467,6 +511,24 @@ struct DenseGaussSampler : SamplerImpl {
                 RMN_CUDA(cudaMalloc(&d_Lpad, hl.size() * 8));
                 RMN_CUDA(cudaMemcpy(d_Lpad, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice));
             }
+        }
+        if (pr->kind == RMN_PROP_PCN) {
+            rw_diag = false;
+            st.rho = pr->rho; st.rho_c = sqrt(1.0 - pr->rho * pr->rho);
+            std::vector<double> hl((size_t)dp * dp, 0.0), hi((size_t)dp * dp, 0.0);
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    hl[(size_t)i * dp + j] = pr->h_L[(size_t)i * d + j];
+                    hi[(size_t)i * dp + j] = pr->h_Linv[(size_t)i * d + j];
+                }
+            RMN_CUDA(cudaMalloc(&d_Lpad, hl.size() * 8));
+            RMN_CUDA(cudaMemcpy(d_Lpad, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice));
+            RMN_CUDA(cudaMalloc(&d_Linvpad, hi.size() * 8));
+            RMN_CUDA(cudaMemcpy(d_Linvpad, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice));
+            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_PCNPROP>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_PCNREV>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         }
         RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_RW>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
@@ -541,6 +603,11 @@ struct DenseGaussSampler : SamplerImpl {
             if (t == T) break;
             if (pr->kind == RMN_PROP_RW && !rw_diag)
                 if (int rc = gemm<EPI_RWPROP>(d_Lpad, stream)) return rc;
+            if (pr->kind == RMN_PROP_PCN) {
+                // theta' = rho theta + rho_c xi L^T (and D = theta - rho theta'), then |(rho_c L)^-1 D|^2
+                if (int rc = gemm<EPI_PCNPROP>(d_Lpad, stream)) return rc;
+                if (int rc = gemm<EPI_PCNREV>(d_Linvpad, stream)) return rc;
+            }
             if (pr->kind == RMN_PROP_HMC) {
                 // Nsteps - 1 interior leapfrog steps, each one gradient GEMM + an in-place update
                 for (int l = 1; l < pr->nsteps; ++l) {
@@ -607,10 +674,10 @@ gauss_point_kernel(int d, const double* __restrict__ mu, const double* __restric
 
 SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s) {
     const rmn_proposal* p = s->prop;
-    if (p->kind == RMN_PROP_PCN || (p->kind == RMN_PROP_HMC && p->has_mass)) {
-        rmn_set_error("dense Gaussian path (d > %d) supports RW and VanillaHMC / AdaptScaleHMC (any Nsteps, "
-                      "Nsteps = 1 is MALA) without a mass matrix; pCN and mass matrices run on the small-d "
-                      "path only", RMN_SMALL_D_MAX);
+    if (p->kind == RMN_PROP_HMC && p->has_mass) {
+        rmn_set_error("dense Gaussian path (d > %d) supports RW, pCN and VanillaHMC / AdaptScaleHMC (any Nsteps, "
+                      "Nsteps = 1 is MALA) without a mass matrix; mass matrices run on the small-d path only",
+                      RMN_SMALL_D_MAX);
         return nullptr;
     }
     return new DenseGaussSampler(s);

@@ -23,6 +23,8 @@ def _prop(name, g, m):
         return rw.MetropolisRandomWalk(g["C0"])
     if name.startswith("adaptrw_"):
         return rw.AdaptScaleRandomWalk(g["C0"])
+    if name.startswith("pcn"):
+        return rw.pCN(g["C0"], float(g["rho"]))
     if name.startswith("adaptmala"):
         return hm.AdaptScaleHMC(float(g["eps"]), 1, m.grad_log_likelihood)
     if name.startswith("adapthmc"):
@@ -36,7 +38,9 @@ def _prop(name, g, m):
                                     ("adaptrw_gauss12d", 12), ("adaptmala_gauss12d", 12),
                                     ("mala_gauss100d", 100), ("mala_gauss1000d", 1000),
                                     # "next" row N1: leapfrog with Nsteps > 1 on the dense path
-                                    ("hmc4_gauss12d", 12), ("adapthmc3_gauss12d", 12), ("hmc5_gauss100d", 100)])
+                                    ("hmc4_gauss12d", 12), ("adapthmc3_gauss12d", 12), ("hmc5_gauss100d", 100),
+                                    # "next" row N2: pCN on the dense path
+                                    ("pcn_gauss12d", 12)])
 def test_injected_chain_matches_reference(golden, name, d):
     from riemann_b200 import Sampler
     g = golden(name)

@@ -37,7 +37,8 @@ def _pair(name, g, d):
 CASES = [("rw_gauss2d", 2), ("rw_gauss5d", 5), ("adaptrw_gauss2d", 2), ("pcn_gauss2d", 2),
          ("mala_gauss5d", 5), ("hmc5_gauss2d", 2), ("hmc3_mass_gauss2d", 2), ("mala_mass_gauss5d", 5),
          ("adapthmc5_gauss2d", 2), ("rw_dense_gauss12d", 12), ("adaptmala_gauss12d", 12),
-         ("rw_gauss100d", 100), ("mala_gauss100d", 100), ("mala_gauss1000d", 1000)]
+         ("rw_gauss100d", 100), ("mala_gauss100d", 100), ("mala_gauss1000d", 1000),
+         ("hmc4_gauss12d", 12), ("adapthmc3_gauss12d", 12), ("hmc5_gauss100d", 100), ("pcn_gauss12d", 12)]
 
 
 @pytest.mark.parametrize("name,d", CASES)

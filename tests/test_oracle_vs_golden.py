@@ -107,9 +107,10 @@ def test_adaptive_d12(golden, name):
     assert abs(prop.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
 
 
-def test_pcn(golden):
-    g = golden("pcn_gauss2d")
-    _replay(g, _gauss(g, 2), port.pCN(g["C0"], float(g["rho"])), g["thetas"][0])
+@pytest.mark.parametrize("name,d", [("pcn_gauss2d", 2), ("pcn_gauss12d", 12)])
+def test_pcn(golden, name, d):
+    g = golden(name)
+    _replay(g, _gauss(g, d), port.pCN(g["C0"], float(g["rho"])), g["thetas"][0])
 
 
 @pytest.mark.parametrize("name", ["mala_logistic", "mmala_logistic"])
