@@ -181,72 +181,82 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             float* Cs = (EPI == EPI_PLAIN) ? C + (tile / mn_tiles) * split_stride : C;
             mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
             tc_fence_after();
-            const int64_t m = m0 + q * 32 + lane;
-            const bool rok = m < M;
-            double pq = 0.0, pk = 0.0;
-            const double he = (EPI == EPI_MALA && rok) ? 0.5 * ep.epsrow[m] : 0.0;
+            // Epilogue data mapping: tcgen05.ld hands each thread one TMEM lane (= output row) x 16 columns;
+            // every 32 x 16 chunk is transposed through shared memory so that a warp instruction touches
+            // 8 rows x 64 contiguous bytes of C and of the epilogue's input arrays instead of 32 rows x 16 B.
+            // Lane L then works on rows it*8 + L/4 (it = 0..3), columns 4 (L%4) .. +3 of the chunk.
+            float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
+            const int rsub = lane >> 2, cg = (lane & 3) * 4;
+            double pq4[4] = {0.0, 0.0, 0.0, 0.0}, pk4[4] = {0.0, 0.0, 0.0, 0.0}, hev[4] = {0.0, 0.0, 0.0, 0.0};
+            if (EPI == EPI_MALA) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int64_t mr = m0 + q * 32 + it * 8 + rsub;
+                    if (mr < M) hev[it] = 0.5 * ep.epsrow[mr];
+                }
+            }
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (TN / 2));
             for (int c0 = 0; c0 < TN / 2; c0 += 16) {
                 float v[16];
                 tmem_ld_32x16(trow + (uint32_t)c0, v);
                 const int n = n0 + half * (TN / 2) + c0;
-                if (EPI == EPI_PLAIN) {
-                    // One TMEM lane (= output row) per thread would store 32 rows x 16 B per instruction;
-                    // transposing the 32 x 16 chunk through shared memory makes it 8 rows x 64 B.
-                    if (n >= N) continue;                               // warp-uniform
-                    float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
-                    float4* w4 = reinterpret_cast<float4*>(stg + lane * 20);
+                if (n >= N) continue;                                   // warp-uniform
+                float4* w4 = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) w4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    __syncwarp();
+                for (int i = 0; i < 4; ++i) w4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                __syncwarp();
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {
-                        const int rr = it * 8 + (lane >> 2), cg = (lane & 3) * 4;
-                        const int64_t mr = m0 + q * 32 + rr;
-                        const float4 val = *reinterpret_cast<const float4*>(stg + rr * 20 + cg);
-                        if (mr < M && n + cg < N) *reinterpret_cast<float4*>(Cs + mr * ldc + n + cg) = val;
-                    }
-                    __syncwarp();
-                    continue;
-                }
-                if (!rok || n >= N) continue;
-                {
-                    const size_t off = (size_t)m * ldc + n;
-                    float4* dst = reinterpret_cast<float4*>(ep.vp + off);
-                    const float4* yh = reinterpret_cast<const float4*>(ep.yph + off);
-                    const float4* yl = reinterpret_cast<const float4*>(ep.ypl + off);
-                    const float4* xi = reinterpret_cast<const float4*>(ep.xi + off);
-                    const float4* vc = reinterpret_cast<const float4*>(ep.vcur + off);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        const float4 a4 = yh[i], b4 = yl[i], w = vc[i];
+                for (int it = 0; it < 4; ++it) {
+                    const int rr = it * 8 + rsub;
+                    const int64_t mr = m0 + q * 32 + rr;
+                    if (!(mr < M && n + cg < N)) continue;
+                    const float4 val = *reinterpret_cast<const float4*>(stg + rr * 20 + cg);
+                    if (EPI == EPI_PLAIN) {
+                        *reinterpret_cast<float4*>(Cs + mr * ldc + n + cg) = val;
+                    } else {
+                        const size_t off = (size_t)mr * ldc + n + cg;
+                        *reinterpret_cast<float4*>(ep.vp + off) = val;
+                        const float4 a4 = *reinterpret_cast<const float4*>(ep.yph + off);
+                        const float4 b4 = *reinterpret_cast<const float4*>(ep.ypl + off);
+                        const float4 w = *reinterpret_cast<const float4*>(ep.vcur + off);
                         const double dl[4] = {(double)a4.x + (double)b4.x, (double)a4.y + (double)b4.y,
                                               (double)a4.z + (double)b4.z, (double)a4.w + (double)b4.w};
                         const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
+                        const double pv[4] = {(double)val.x, (double)val.y, (double)val.z, (double)val.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) pq += dl[e] * (2.0 * wv[e] + (double)v[4 * i + e]);   // quad' - quad
+                        for (int e = 0; e < 4; ++e) pq4[it] += dl[e] * (2.0 * wv[e] + pv[e]);          // quad' - quad
                         if (ep.mala) {
                             // p' = xi + eps/2 g + eps/2 g',  g = -V, g' = -(V + P delta)   (hamiltonian.py:27,40)
-                            const float4 x = xi[i];
+                            const float4 x = *reinterpret_cast<const float4*>(ep.xi + off);
                             const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
+                            const double he = hev[it];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + (double)v[4 * i + e]);
-                                pk += p1 * p1;
+                                const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + pv[e]);
+                                pk4[it] += p1 * p1;
                             }
                         }
                     }
                 }
+                __syncwarp();
             }
             // this warp is done with accumulator a: hand it back to the MMA thread
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
-            if (EPI == EPI_MALA && rok) {
+            if (EPI == EPI_MALA) {
                 const size_t blk = (size_t)(n0 / TN) * 2 + half;                   // 128-column block index
-                ep.partq[blk * M + m] = pq;
-                if (ep.mala) ep.partk[blk * M + m] = pk;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    double sq = pq4[it], sk = pk4[it];
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+                    sk += __shfl_xor_sync(0xffffffffu, sk, 1); sk += __shfl_xor_sync(0xffffffffu, sk, 2);
+                    const int64_t mr = m0 + q * 32 + it * 8 + rsub;
+                    if ((lane & 3) == 0 && mr < M) {
+                        ep.partq[blk * M + mr] = sq;
+                        if (ep.mala) ep.partk[blk * M + mr] = sk;
+                    }
+                }
             }
         }
     }
