@@ -293,10 +293,10 @@ struct DenseTF32Sampler : SamplerImpl {
         RMN_CUDA(cudaMemcpy(d_mupad, hm.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
         st.mu = d_mupad; st.Ldiag = d_Ldiag; st.prec = s->model->d_prec;
         int rc;
-        if ((rc = tc::make_tmap_2d(&maps.ah, st.Yph, st.K, dp, dp, tc::TM))) return rc;
-        if ((rc = tc::make_tmap_2d(&maps.al, st.Ypl, st.K, dp, dp, tc::TM))) return rc;
-        if ((rc = tc::make_tmap_2d(&maps.bh, d_Ph, dp, dp, dp, tc::TN))) return rc;
-        if ((rc = tc::make_tmap_2d(&maps.bl, d_Pl, dp, dp, dp, tc::TN))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.ah, st.Yph, st.K, dp, dp, tc::TM, tc::TK3))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.al, st.Ypl, st.K, dp, dp, tc::TM, tc::TK3))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.bh, d_Ph, dp, dp, dp, tc::TN, tc::TK3))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps.bl, d_Pl, dp, dp, dp, tc::TN, tc::TK3))) return rc;
         if ((rc = rmn_fill_f64(st.scale, st.K, 1.0, 0))) return rc;
         RMN_CUDA(cudaDeviceSynchronize());
         return RMN_OK;

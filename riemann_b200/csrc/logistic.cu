@@ -1038,10 +1038,10 @@ struct LogisticSampler : SamplerImpl {
             for (int b = 0; b < nblk; ++b) {
                 const uint64_t rows = (uint64_t)std::min<int64_t>(tcb.Kb, st.K - (int64_t)b * tcb.Kb);
                 tc::GemmMaps& m = maps_z_blk[b];
-                if (int rc = tc::make_tmap_2d(&m.ah, tcb.Th + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM)) return rc;
-                if (int rc = tc::make_tmap_2d(&m.al, tcb.Tl + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM)) return rc;
-                if (int rc = tc::make_tmap_2d(&m.bh, tcb.Xh, (uint64_t)st.N, dp32, dp32, tc::TN)) return rc;
-                if (int rc = tc::make_tmap_2d(&m.bl, tcb.Xl, (uint64_t)st.N, dp32, dp32, tc::TN)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.ah, tcb.Th + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM, tc::TK3)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.al, tcb.Tl + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM, tc::TK3)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.bh, tcb.Xh, (uint64_t)st.N, dp32, dp32, tc::TN, tc::TK3)) return rc;
+                if (int rc = tc::make_tmap_2d(&m.bl, tcb.Xl, (uint64_t)st.N, dp32, dp32, tc::TN, tc::TK3)) return rc;
             }
             if (int rc = tc::make_tmap_2d(&maps_g.ah, tcb.Rh, (uint64_t)tcb.Kb, Np, Np, tc::TM)) return rc;
             if (int rc = tc::make_tmap_2d(&maps_g.bh, tcb.XTh, dp32, Np, Np, tc::TN)) return rc;

@@ -29,15 +29,17 @@ static PFN_encodeTiled get_encode() {
 }
 
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                 uint32_t box_rows) {
+                 uint32_t box_rows, int tk) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { rmn_set_error("cuTensorMapEncodeTiled not available from the driver"); return RMN_ERR_CUDA; }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {ld_elems * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
+    if (tk != 32 && tk != 16) { rmn_set_error("make_tmap_2d: k-block must be 16 or 32"); return RMN_ERR_PARAM; }
+    cuuint32_t box[2] = {(cuuint32_t)tk, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, tk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rmn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RMN_ERR_CUDA; }
     return RMN_OK;
@@ -76,8 +78,11 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     // (m_tile, n_tile, split) and split s stores its partial product at C + s * split_stride (summed by
     // the caller) -- this is how a product with few output tiles but a long contraction (the logistic
     // gradient R X: K x d output, N data rows deep) still fills all SMs.
-    constexpr int STAGES = (PASSES == 1) ? 4 : tc::STAGES;
-    constexpr int STAGE_BYTES = (PASSES == 1) ? (A_BYTES + B_BYTES) : tc::STAGE_BYTES;
+    constexpr int TK = (PASSES == 1) ? tc::TK : tc::TK3;               // fp32 per k-block
+    constexpr int ROWB = TK * 4;                                       // bytes per tile row = swizzle span
+    constexpr int A_BYTES = TM * ROWB, B_BYTES = TN * ROWB;
+    constexpr int STAGE_BYTES = (PASSES == 1) ? (A_BYTES + B_BYTES) : 2 * (A_BYTES + B_BYTES);
+    constexpr int STAGES = (tc::STAGES * tc::STAGE_BYTES) / STAGE_BYTES;   // 4 x 48 KB (or 2 x 96 KB with TK3 = 32)
     constexpr int OFF_BH = (PASSES == 1) ? A_BYTES : 2 * A_BYTES;
     static_assert(STAGES * STAGE_BYTES <= tc::STAGES * tc::STAGE_BYTES, "stage ring must fit SMEM_BYTES");
     extern __shared__ uint8_t smem_raw[];
@@ -152,10 +157,10 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 mbar_wait(&full[s], (it / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t dah = umma_desc_kmajor_sw128(sa);
-                const uint64_t dal = umma_desc_kmajor_sw128(sa + A_BYTES);
-                const uint64_t dbh = umma_desc_kmajor_sw128(sa + OFF_BH);
-                const uint64_t dbl = umma_desc_kmajor_sw128(sa + 2 * A_BYTES + B_BYTES);
+                const uint64_t dah = umma_desc_kmajor<ROWB>(sa);
+                const uint64_t dal = umma_desc_kmajor<ROWB>(sa + A_BYTES);
+                const uint64_t dbh = umma_desc_kmajor<ROWB>(sa + OFF_BH);
+                const uint64_t dbl = umma_desc_kmajor<ROWB>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int k = 0; k < TK / UK; ++k) {
                     const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);   // +32 bytes per K step, 16-byte units
@@ -179,6 +184,23 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             const int64_t m0 = (m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
             const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * TN;
             float* Cs = (EPI == EPI_PLAIN) ? C + (tile / mn_tiles) * split_stride : C;
+            if (EPI == EPI_MALA) {
+                // The epilogue's inputs do not depend on the accumulator: pull this warp's 32 rows x 128 columns of
+                // delta (hi, lo), V and xi towards L2 now, so the chunk loop below waits on L2, not on HBM
+                // (the MALA epilogue, not the mainloop, bounds this kernel: 272 us vs 140 us with the plain one).
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int64_t mr = m0 + q * 32 + it * 8 + (lane >> 2);
+                    const int nn = n0 + half * (TN / 2) + (lane & 3) * 32;
+                    if (mr < M && nn < N) {
+                        const size_t off = (size_t)mr * ldc + nn;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.yph + off));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.ypl + off));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.vcur + off));
+                        if (ep.mala) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.xi + off));
+                    }
+                }
+            }
             mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
             tc_fence_after();
             // Epilogue data mapping: tcgen05.ld hands each thread one TMEM lane (= output row) x 16 columns;
@@ -197,10 +219,26 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             }
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (TN / 2));
             for (int c0 = 0; c0 < TN / 2; c0 += 16) {
-                float v[16];
-                tmem_ld_32x16(trow + (uint32_t)c0, v);
                 const int n = n0 + half * (TN / 2) + c0;
                 if (n >= N) continue;                                   // warp-uniform
+                // (MALA) issue the chunk's 16 independent global loads FIRST: their L2 latency (well over
+                // 1,000 cycles under the TMA traffic) then overlaps the TMEM read and the staging below
+                float4 A4[4], B4[4], W4[4], X4[4];
+                bool okr[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int64_t mr = m0 + q * 32 + it * 8 + rsub;
+                    okr[it] = (mr < M) && (n + cg < N);
+                    if (EPI == EPI_MALA) {
+                        const size_t off = (size_t)(okr[it] ? mr : m0) * ldc + (okr[it] ? n + cg : n0);
+                        A4[it] = *reinterpret_cast<const float4*>(ep.yph + off);
+                        B4[it] = *reinterpret_cast<const float4*>(ep.ypl + off);
+                        W4[it] = *reinterpret_cast<const float4*>(ep.vcur + off);
+                        if (ep.mala) X4[it] = *reinterpret_cast<const float4*>(ep.xi + off);
+                    }
+                }
+                float v[16];
+                tmem_ld_32x16(trow + (uint32_t)c0, v);
                 float4* w4 = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) w4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -209,16 +247,14 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 for (int it = 0; it < 4; ++it) {
                     const int rr = it * 8 + rsub;
                     const int64_t mr = m0 + q * 32 + rr;
-                    if (!(mr < M && n + cg < N)) continue;
+                    if (!okr[it]) continue;
                     const float4 val = *reinterpret_cast<const float4*>(stg + rr * 20 + cg);
                     if (EPI == EPI_PLAIN) {
                         *reinterpret_cast<float4*>(Cs + mr * ldc + n + cg) = val;
                     } else {
                         const size_t off = (size_t)mr * ldc + n + cg;
                         *reinterpret_cast<float4*>(ep.vp + off) = val;
-                        const float4 a4 = *reinterpret_cast<const float4*>(ep.yph + off);
-                        const float4 b4 = *reinterpret_cast<const float4*>(ep.ypl + off);
-                        const float4 w = *reinterpret_cast<const float4*>(ep.vcur + off);
+                        const float4 a4 = A4[it], b4 = B4[it], w = W4[it];
                         const double dl[4] = {(double)a4.x + (double)b4.x, (double)a4.y + (double)b4.y,
                                               (double)a4.z + (double)b4.z, (double)a4.w + (double)b4.w};
                         const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
@@ -227,7 +263,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                         for (int e = 0; e < 4; ++e) pq4[it] += dl[e] * (2.0 * wv[e] + pv[e]);          // quad' - quad
                         if (ep.mala) {
                             // p' = xi + eps/2 g + eps/2 g',  g = -V, g' = -(V + P delta)   (hamiltonian.py:27,40)
-                            const float4 x = *reinterpret_cast<const float4*>(ep.xi + off);
+                            const float4 x = X4[it];
                             const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
                             const double he = hev[it];
 #pragma unroll
@@ -270,11 +306,12 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
                          cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0) {
-    if (Kdim % TK != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
-    if (ksplit < 1 || ksplit > Kdim / TK || (ep && ksplit != 1)) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
+    const int tk = (passes == 1) ? TK : TK3;                           // k-block of the kernel variant
+    if (Kdim % 32 != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
+    if (ksplit < 1 || ksplit > Kdim / tk || (ep && ksplit != 1)) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
     // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
-    const int kbp = (Kdim / TK + ksplit - 1) / ksplit;
-    ksplit = (Kdim / TK + kbp - 1) / kbp;
+    const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
+    ksplit = (Kdim / tk + kbp - 1) / kbp;
     const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM) * ksplit;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -303,8 +340,9 @@ int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C
 // used through *used (<= ksplit); partial s is at C + s * split_stride
 int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
                         int64_t split_stride, int* used, cudaStream_t st, int passes) {
-    const int kbp = (Kdim / TK + ksplit - 1) / ksplit;
-    if (used) *used = (Kdim / TK + kbp - 1) / kbp;
+    const int tk = (passes == 1) ? TK : TK3;
+    const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
+    if (used) *used = (Kdim / tk + kbp - 1) / kbp;
     return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, passes, ksplit, split_stride);
 }
 // 3-pass product, m-fastest tile order (A small and L2-resident, B streamed once)
@@ -340,10 +378,10 @@ extern "C" int rmn_tf32x3_gemm_splitk(int64_t M, int N, int Kdim, int ksplit, co
     RMN_REQUIRE(d_Ah && d_Al && d_Bh && d_Bl && d_C, "rmn_tf32x3_gemm_splitk: null pointer");
     tc::GemmMaps maps;
     int rc;
-    if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN, tc::TK3))) return rc;
     if (ksplit > Kdim / 32) ksplit = Kdim / 32;
     return tc::launch_plain_splitk(maps, M, N, Kdim, d_C, N, ksplit, (int64_t)M * N, used_splits, (cudaStream_t)stream, 3);
 }
@@ -355,9 +393,9 @@ extern "C" int rmn_tf32x3_gemm(int64_t M, int N, int Kdim, const float* d_Ah, co
     RMN_REQUIRE(d_Ah && d_Al && d_Bh && d_Bl && d_C, "rmn_tf32x3_gemm: null pointer");
     tc::GemmMaps maps;
     int rc;
-    if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN, tc::TK3))) return rc;
     return tc::launch_plain(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
 }

@@ -20,7 +20,14 @@ namespace tc {
 
 constexpr int TM = 128;          // rows of A per CTA  (UMMA M)
 constexpr int TN = 256;          // rows of B per CTA  (UMMA N)
-constexpr int TK = 32;           // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int TK = 32;           // fp32 per k-block = 128 bytes = one swizzle row (single-pass kernels)
+#ifndef RMN_TC_TK3
+#define RMN_TC_TK3 16
+#endif
+// k-block of the 3-pass kernels: 16 fp32 = 64-byte rows (SWIZZLE_64B), so a stage (Ah Al Bh Bl) is 48 KB and
+// FOUR stages fit -- with 96-KB stages only two did, and the TMA latency of a stage (~2,500 cycles) was longer
+// than the 1,600 cycles of tensor work it fed
+constexpr int TK3 = RMN_TC_TK3;
 constexpr int UK = 8;            // K per tcgen05.mma.kind::tf32
 constexpr int STAGES = 2;
 constexpr int A_BYTES = TM * TK * 4;                 // 16 KB
@@ -68,16 +75,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) {
+// shared-memory matrix descriptor: K-major, rows of ROWB = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B) bytes,
+// 8-row groups 8 * ROWB bytes apart
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
+    static_assert(ROWB == 128 || ROWB == 64, "row bytes = swizzle span");
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, 16-byte units   [0,14)
-    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for SW128 K-major) [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset = 8 rows * 128 B           [32,46)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;             // stride byte offset = 8 rows * ROWB            [32,46)
     d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)                   [46,48)
-    d |= (uint64_t)2 << 61;                             // layout type: SWIZZLE_128B                     [61,64)
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;         // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4 [61,64)
     return d;
 }
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr) { return umma_desc_kmajor<128>(saddr); }
 // instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) /*c = f32*/ | (2u << 7) /*a = tf32*/ | (2u << 10) /*b = tf32*/ |
@@ -141,8 +152,9 @@ struct GemmMaps {
     CUtensorMap ah, al, bh, bl;
 };
 
-// host: 2-D fp32 row-major [rows][cols] tensor map, box = [box_rows][32], SWIZZLE_128B, OOB -> 0
+// host: 2-D fp32 row-major [rows][cols] tensor map, box = [box_rows][tk], tk = 32 (SWIZZLE_128B, single-pass
+// kernels) or TK3 (3-pass kernels; SWIZZLE_64B when 16), OOB -> 0
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                 uint32_t box_rows);
+                 uint32_t box_rows, int tk = TK);
 
 }  // namespace tc
