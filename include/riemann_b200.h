@@ -145,6 +145,8 @@ typedef struct {
     const double* d_xi;
     const double* d_u;
     const double* d_tape;
+    const double* d_usel;   /* tempered samplers: swap-selection uniforms usel[t*K + c] (ptsampler.py:104);
+                             * d_u then holds the accept uniform of a within-chain step or the swap uniform (:121) */
 } rmn_inject_t;
 
 /* Optional trace.  History index i = 0 is the state at entry, i = t+1 the state after
@@ -202,6 +204,13 @@ int rmn_sampler_create_ex(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p
                           int64_t chain_offset, uint64_t seed, void* d_workspace,
                           size_t workspace_bytes, int precision);
 int rmn_sampler_destroy(rmn_sampler_t* s);
+
+/* PTSampler (riemann/samplers/ptsampler.py:41-127) on the small-d Gaussian family: chains c = l*nt + i form ladder l,
+ * chain i of a ladder samples TemperedModel(model, h_betas[i]) (likelihood * beta, :33-34); every step each chain either
+ * takes a within-chain MH step or, with probability pswap and sequentially along the ladder exactly as :102-125,
+ * proposes a swap with its lower neighbour.  K must be a multiple of nt (2..32); non-adaptive RW / pCN proposals.
+ * Call before rmn_sampler_set_state. */
+int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double* h_betas, double pswap);
 
 /* = Sampler.__init__ (sampler.py:34-42): store the states and evaluate their
  * log-posterior (and gradient / metric caches) on the device. */

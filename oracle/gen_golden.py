@@ -258,6 +258,61 @@ def _n1_dense_fixtures(R):
                     extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)))
 
 
+def _pt_fixture(R, name, model, proposal, theta0, T, seed, extra=None):
+    """"next" row N3: the reference's PTSampler (default ladder 0.5**arange(5), Pswap = 0.1) with every draw
+    recorded.  Per PT step and chain i the stream is: one selection uniform; then, unless the chain was swapped
+    by its upper neighbour, either a within-chain step (normal(d), accept uniform) or one swap uniform."""
+    np.random.seed(seed)
+    with refshim.quiet():
+        pt = R.PTSampler(model, proposal, theta0)
+    nt, d = len(pt.betas), len(np.atleast_1d(theta0))
+    usel, xi, u = np.zeros((T, nt)), np.zeros((T, nt, d)), np.zeros((T, nt))
+    kind = np.zeros((T, nt), dtype=np.int8)            # 0 within-chain step, 1 swap initiator, 2 swapped partner
+    with refshim.quiet(), refshim.RecordingRNG() as rec:
+        for t in range(T):
+            a = rec.mark()
+            pt.sample()
+            log = rec.log[a:rec.mark()]
+            k, i = 0, 0
+            while i < nt:
+                assert log[k][0] == "uniform"
+                usel[t, i] = float(log[k][1]); k += 1
+                if i > 0 and kind[t, i - 1] == 1:
+                    kind[t, i] = 2
+                elif usel[t, i] > pt.Pswap or i == nt - 1:
+                    assert log[k][0] == "normal" and log[k + 1][0] == "uniform", log[k:k + 2]
+                    xi[t, i] = log[k][1]; u[t, i] = float(log[k + 1][1]); k += 2
+                else:
+                    assert log[k][0] == "uniform"
+                    kind[t, i] = 1; u[t, i] = float(log[k][1]); k += 1
+                i += 1
+            assert k == len(log), (k, len(log))
+    out = dict(usel=usel, xi=xi, u=u, kind=kind, betas=np.asarray(pt.betas, dtype=np.float64),
+               pswap=np.float64(pt.Pswap),
+               thetas=np.array([[np.atleast_1d(th) for th in s._chain_thetas] for s in pt.samplers]),   # [nt][T+1][d]
+               logpost=np.array([s._chain_logpost for s in pt.samplers], dtype=np.float64), seed=np.int64(seed))
+    if extra:
+        out.update(extra)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print("%-28s T=%d nt=%d swaps proposed=%d accepted=%d" % (
+        name, T, nt, int((kind == 1).sum()),
+        int(sum(np.any(out["thetas"][i, 1:] != out["thetas"][i, :-1], axis=1)[kind[:, i] == 1].sum() for i in range(nt)))))
+
+
+def _n3_pt_fixtures(R):
+    B = R.benchmarks
+    C0 = np.array([[0.5, 0.2], [0.2, 0.3]])
+    _pt_fixture(R, "pt_rw_gauss2d", B.benchmark_gauss2d_corr, R.MetropolisRandomWalk(C0), np.ones(2), 1500, 601,
+                extra=dict(C0=C0))
+    rng = np.random.Generator(np.random.Philox(7))
+    A = rng.standard_normal((5, 5))
+    C5 = A @ A.T / 5 + 0.2 * np.eye(5)
+    mu5 = rng.standard_normal(5)
+    g5 = R.MultiGaussianDist(mu5, C5)
+    _pt_fixture(R, "pt_rw_gauss5d", g5, R.MetropolisRandomWalk(0.3 * C5), np.zeros(5), 800, 602,
+                extra=dict(C0=0.3 * C5, mu=mu5, C=C5))
+
+
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
@@ -301,6 +356,9 @@ def main():
     R = refshim.load_reference()
     if "--only-n1-dense" in sys.argv:
         _n1_dense_fixtures(R)
+        return
+    if "--only-n3-pt" in sys.argv:
+        _n3_pt_fixtures(R)
         return
     B = R.benchmarks
 
@@ -367,6 +425,7 @@ def main():
                     np.ones(2), 1500, 304, extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)),
                     track_scale=True)
     _n1_dense_fixtures(R)
+    _n3_pt_fixtures(R)
     # pCN ("next" row N2)
     _vector_fixture(R, "pcn_gauss2d", g2, R.pCN(np.eye(2), 0.5), np.ones(2), 800, 305,
                     extra=dict(C0=np.eye(2), rho=np.float64(0.5)))

@@ -112,6 +112,7 @@ def load_reference():
     import riemann.proposals as rprops
     rprops.MetropolisRandomWalk = randomwalk.MetropolisRandomWalk  # shim 4
     from riemann.models import gaussian, benchmarks, changepoint, model
+    from riemann.samplers import ptsampler
 
     # examples/test_changepoint.py holds the proposal config 2 uses; load by path
     spec = importlib.util.spec_from_file_location(
@@ -144,7 +145,8 @@ def load_reference():
         ChangepointParams=changepoint.ChangepointParams,
         ChangepointRegression1D=ChangepointRegression1DSqueezed,
         ChangepointRegression1DProp=ex_cp.ChangepointRegression1DProp,
-        changepoint=changepoint)
+        changepoint=changepoint,
+        PTSampler=ptsampler.PTSampler, TemperedModel=ptsampler.TemperedModel)
     _cached = ns
     return ns
 

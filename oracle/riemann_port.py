@@ -566,6 +566,96 @@ class Sampler(object):
 
 
 # --------------------------------------------------------------------------
+# Parallel tempering ("next" row N3)               riemann/samplers/ptsampler.py:11-127
+# --------------------------------------------------------------------------
+class PTTapeDraws(object):
+    """Replay for PTSampler: usel[T, Nt] selection uniforms, xi[T, Nt, d] normals and u[T, Nt] accept /
+    swap uniforms, addressed by the chain the draw is made for."""
+
+    def __init__(self, usel, xi, u):
+        self.usel, self.xi, self.u = (np.asarray(a, dtype=np.float64) for a in (usel, xi, u))
+        self.t, self.i = 0, 0
+
+    def normal(self, role, n):
+        return self.xi[self.t, self.i, :n].copy()
+
+    def uniform(self, role, low=0.0, high=1.0):
+        return self.usel[self.t, self.i] if role == "ptsel" else self.u[self.t, self.i]
+
+    def randint(self, role, n):
+        raise NotImplementedError
+
+    def next_step(self):
+        pass                                    # PTSampler advances t itself (one PT step = Nt chains)
+
+
+class TemperedModel(Model):
+    """ptsampler.py:11-38: likelihood scaled by beta, prior untouched."""
+
+    def __init__(self, base_model, beta):
+        if not (beta >= 0 and beta <= 1):
+            raise ParameterError("beta = {} must be a number between 0 and 1".format(beta))
+        self.base_model, self.beta = base_model, beta
+
+    def log_likelihood(self, theta):
+        return self.base_model.log_likelihood(theta) * self.beta
+
+    def log_prior(self, theta):
+        return self.base_model.log_prior(theta)
+
+
+class PTSampler(object):
+    """ptsampler.py:41-127 with the default ladder betas = 0.5**arange(5) (the `betas=` branch of the
+    reference raises: `isinstance(betas, np.array)`, :62); an explicit ladder is accepted here and used
+    as given, which is what that branch intends (:66-68 computes a sorted copy and then ignores it)."""
+
+    def __init__(self, model, proposal, theta0, betas=None, Pswap=0.1, draws=None):
+        self.betas = 0.5 ** np.arange(5) if betas is None else np.asarray(betas, dtype=np.float64)
+        if not (Pswap > 0 and Pswap < 1):
+            raise ParameterError("Pswap must be a number between 0 and 1")
+        self.Pswap = Pswap
+        self.draws = draws if draws is not None else LiveDraws()
+        self.samplers = [Sampler(TemperedModel(model, b), proposal, theta0, draws=self.draws) for b in self.betas]
+
+    def run(self, Nsamples, Nburn=0, Nthin=1):
+        for _ in range(Nsamples):                               # :83-90: Nburn / Nthin are ignored
+            self.sample()
+        self._chain_thetas = self.samplers[0]._chain_thetas
+        self._chain_logpost = self.samplers[0]._chain_logpost
+
+    def sample(self):
+        swapped = []
+        n = len(self.samplers)
+        tape = isinstance(self.draws, PTTapeDraws)
+        for i in range(n):
+            if tape:
+                self.draws.i = i
+            u = self.draws.uniform("ptsel")                     # :104 drawn for EVERY chain, swapped or not
+            if i in swapped:
+                continue
+            elif u > self.Pswap or i == n - 1:
+                self.samplers[i].sample()                       # :110
+            else:
+                j = i + 1
+                th_i, lp_ii = self.samplers[i].current_state()
+                th_j, lp_jj = self.samplers[j].current_state()
+                lp_ij = self.samplers[i].model.log_posterior(th_j)
+                lp_ji = self.samplers[j].model.log_posterior(th_i)
+                with np.errstate(all="ignore"):
+                    x = np.exp((lp_ji + lp_ij) - (lp_ii + lp_jj))
+                mh = x if x < 1 else 1                          # Python min(1, x): nan -> 1  (:119-120)
+                if self.draws.uniform("acc") < mh:              # :121
+                    self.samplers[i]._add_state(th_j, lp_ij)
+                    self.samplers[j]._add_state(th_i, lp_ji)
+                else:
+                    self.samplers[i]._add_state(th_i, lp_ii)
+                    self.samplers[j]._add_state(th_j, lp_jj)
+                swapped.extend([i, j])
+        if tape:
+            self.draws.t += 1
+
+
+# --------------------------------------------------------------------------
 # synthetic inputs of SURVEY.md section 8d (numpy Philox generator => reproducible)
 # --------------------------------------------------------------------------
 SEED_BASE = 20261018

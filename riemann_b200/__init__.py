@@ -10,6 +10,7 @@ from .sampling_errors import ParameterError, RiemannBaseError
 from .models.model import Model, DeviceModel
 from .proposals.proposal import Proposal, DeviceProposal
 from .samplers.sampler import Sampler
+from .samplers.ptsampler import PTSampler, TemperedModel
 
 __all__ = ["Model", "Sampler", "Proposal", "ParameterError", "RiemannBaseError",
            "DeviceModel", "DeviceProposal"]

@@ -24,7 +24,7 @@ PRECISIONS = {"f64": 0, "tf32x3": 1, "tf32-metric": 2}
 
 
 class Inject(C.Structure):
-    _fields_ = [("d_xi", C.c_void_p), ("d_u", C.c_void_p), ("d_tape", C.c_void_p)]
+    _fields_ = [("d_xi", C.c_void_p), ("d_u", C.c_void_p), ("d_tape", C.c_void_p), ("d_usel", C.c_void_p)]
 
 
 class Trace(C.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     "rmn_sampler_reset_diagnostics": (_I, [_P, _P]),
     "rmn_sampler_reduce_diagnostics": (_I, [_P, _P, _P]),
     "rmn_sampler_launch_count": (_L, [_P]),
+    "rmn_sampler_set_tempering": (_I, [_P, _I, _P, _D]),
     "rmn_sampler_enable_kernel_timing": (_I, [_P, _I]),
     "rmn_sampler_kernel_timing": (_I, [_P, _P, _P, _P, _P]),
     "rmn_philox_raw": (_I, [_L, _P, _P, _P, _P]),

@@ -404,6 +404,11 @@ extern "C" int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block,
     RMN_S(s); RMN_REQUIRE(d_block, "rmn_sampler_reduce_diagnostics: null block");
     return s->impl->reduce_diag(d_block, (cudaStream_t)stream);
 }
+extern "C" int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double* h_betas, double pswap) {
+    RMN_REQUIRE(s && s->impl, "rmn_sampler_set_tempering: null sampler");
+    return s->impl->set_tempering(nt, h_betas, pswap);
+}
+
 extern "C" int64_t rmn_sampler_launch_count(const rmn_sampler_t* s) { return (s && s->impl) ? s->impl->launches : 0; }
 
 extern "C" int rmn_sampler_enable_kernel_timing(rmn_sampler_t* s, int enable) {

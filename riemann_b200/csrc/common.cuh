@@ -248,6 +248,7 @@ struct SamplerImpl {
     virtual int cp_set_state(const int32_t*, const double*, const double*, const double*, cudaStream_t) { return unsupported("cp_set_state"); }
     virtual int cp_get_state(int32_t*, double*, double*, double*, double*, cudaStream_t) { return unsupported("cp_get_state"); }
     virtual int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t st) = 0;
+    virtual int set_tempering(int, const double*, double) { return unsupported("parallel tempering (small-d Gaussian samplers only)"); }
     virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }
     virtual int set_adapt(const double*, const int64_t*, const int64_t*, cudaStream_t) { return unsupported("set_adapt"); }
     virtual int diag_dim() const = 0;

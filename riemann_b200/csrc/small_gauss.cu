@@ -9,6 +9,8 @@
 //   AdaptScaleProposal.adapt             riemann/proposals/adaptive.py:26-35
 //   MultiGaussianDist.log_likelihood / grad_log_likelihood   riemann/models/gaussian.py:49-58
 //   Model.log_posterior                  riemann/models/model.py:43-55
+//   PTSampler.sample / TemperedModel     riemann/samplers/ptsampler.py:11-38, 92-127  (set_tempering:
+//                                        ladders of nt chains on consecutive threads, swaps by shuffle)
 // Arithmetic is fp64 throughout (the reference is fp64 numpy).
 // Internal state layout: theta[D][K] (chain fastest => coalesced loads/stores).
 #include "common.cuh"
@@ -30,11 +32,16 @@ struct SGParams {
     double chM[TRI];
     double Minv[D * D];
     double chMinv[TRI];
+    // parallel tempering (ptsampler.py): nt = 0 off; a ladder occupies `stride` (power of two >= nt) threads
+    int nt, stride;
+    double pswap;
+    double betas[32];
 };
 
 struct SGState {
     double* theta;          // [D][K]
-    double* lp;             // [K]
+    double* lp;             // [K]   (tempered log-posterior when a ladder is set)
+    double* ll;             // [K]   untempered log-likelihood (parallel tempering)
     double* scale;          // [K]
     long long* nsamp;       // [K]
     long long* nacc;        // [K]
@@ -68,7 +75,7 @@ __device__ __forceinline__ void tri_tmv(const double* __restrict__ L, const doub
 }
 
 template <int D>
-__device__ __forceinline__ double gauss_logpost(const SGParams<D>& P, const double* th) {
+__device__ __forceinline__ double gauss_loglik(const SGParams<D>& P, const double* th) {
     double y[D], u[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) y[i] = th[i] - P.mu[i];
@@ -76,8 +83,21 @@ __device__ __forceinline__ double gauss_logpost(const SGParams<D>& P, const doub
     double q = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) q += u[i] * u[i];
-    const double ll = -0.5 * ((q + P.c1) + P.c2);
-    return combine_logpost(0.0, ll);          // log_prior == 0.0 (gaussian.py:46-47)
+    return -0.5 * ((q + P.c1) + P.c2);        // gaussian.py:52
+}
+template <int D>
+__device__ __forceinline__ double gauss_logpost(const SGParams<D>& P, const double* th) {
+    return combine_logpost(0.0, gauss_loglik<D>(P, th));          // log_prior == 0.0 (gaussian.py:46-47)
+}
+// thread -> chain mapping: plain = one chain per thread; tempered = ladder l on threads l*stride .. l*stride+nt-1
+template <int D>
+__device__ __forceinline__ int64_t chain_of_thread(const SGParams<D>& P, int64_t g, int64_t K, int& ti, bool& active) {
+    if (P.nt == 0) { ti = 0; active = g < K; return active ? g : 0; }
+    const int64_t ladder = g / P.stride;
+    ti = (int)(g % P.stride);
+    active = ti < P.nt && (ladder + 1) * P.nt <= K;
+    if (ti >= P.nt) ti = P.nt - 1;
+    return active ? ladder * P.nt + ti : 0;
 }
 
 template <int D>
@@ -111,7 +131,7 @@ template <int D, bool INJ>
 __global__ void __launch_bounds__(128)
 small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t K, int64_t T,
                    int64_t step0, uint64_t seed, int64_t chain_offset, const double* __restrict__ inj_xi,
-                   const double* __restrict__ inj_u, rmn_trace_t tr) {
+                   const double* __restrict__ inj_u, const double* __restrict__ inj_usel, rmn_trace_t tr) {
     __shared__ SGParams<D> P;
     {
         const int nw = sizeof(SGParams<D>) / 4;
@@ -120,13 +140,18 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= K) return;
+    int ti;
+    bool active;
+    const int64_t c = chain_of_thread<D>(P, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, K, ti, active);
+    const bool pt = P.nt > 0;
+    if (!pt && !active) return;                 // tempered warps keep their idle threads for the shuffles
+    const double beta = pt ? P.betas[ti] : 1.0;
 
     double th[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) th[i] = st.theta[(int64_t)i * K + c];
     double lp = st.lp[c];
+    double ll = pt ? st.ll[c] : 0.0;
     AdaptState ad{st.scale[c], st.nsamp[c], st.nacc[c]};
     long long dacc = st.dacc[c];
     double s1[D], s2[D];
@@ -137,12 +162,14 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
 
     for (int64_t t = 0; t < T; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
-        double xi[D], uacc;
+        double xi[D], uacc, usel = 1.0;
         if (INJ) {
 #pragma unroll
             for (int i = 0; i < D; ++i) xi[i] = inj_xi[(t * K + c) * D + i];
             uacc = inj_u[t * K + c];
+            if (pt) usel = inj_usel[t * K + c];
         } else {
+            if (pt) usel = u01(rk.block(step, RMN_BLOCK_AUX).x);
 #pragma unroll
             for (int b = 0; 4 * b < D; ++b) {
                 double v[4];
@@ -153,6 +180,21 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
             }
             uacc = u01(rk.block(step, RMN_BLOCK_ACCEPT).x);
         }
+
+        // ---- parallel tempering roles (ptsampler.py:102-112): chain i initiates a swap with i+1 iff it was not
+        //      itself swapped by i-1, u <= Pswap and it is not the last rung; sequential along the ladder
+        bool is_init = false, is_part = false;
+        if (pt) {
+            const bool want = active && ti < P.nt - 1 && !(usel > P.pswap);
+            const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(P.stride - 1);
+            const unsigned wmask = (__ballot_sync(0xffffffffu, want) >> base) & (P.stride == 32 ? 0xffffffffu : ((1u << P.stride) - 1u));
+            unsigned init = 0;
+            for (int b = 0; b < P.nt - 1; ++b)
+                if (((wmask >> b) & 1u) && !(b > 0 && ((init >> (b - 1)) & 1u))) init |= 1u << b;
+            is_init = active && ((init >> ti) & 1u);
+            is_part = active && ti > 0 && ((init >> (ti - 1)) & 1u);
+        }
+        const bool regular = active && !is_init && !is_part;
 
         double q[D], lqr = 0.0;
         if (P.kind == RMN_PROP_RW) {
@@ -212,20 +254,60 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
             lqr = 0.5 * (k1 - k0);
         }
 
-        const double lpq = gauss_logpost<D>(P, q);
-        if (tr.d_prop_theta) {
-#pragma unroll
-            for (int i = 0; i < D; ++i) tr.d_prop_theta[(t * K + c) * D + i] = q[i];
-        }
-        const bool acc = mh_accept(lpq, lp, lqr, uacc);
+        const double llq = gauss_loglik<D>(P, q);
+        double lpq = combine_logpost(0.0, pt ? llq * beta : llq);       // TemperedModel: logL * beta (ptsampler.py:33-34)
+        bool acc = regular && mh_accept(lpq, lp, lqr, uacc);
         bool moved = false;
         if (acc) {
 #pragma unroll
             for (int i = 0; i < D; ++i) { moved |= (q[i] != th[i]); th[i] = q[i]; }
-            lp = lpq;
+            lp = lpq; ll = llq;
+        }
+        if (pt) {
+            // ---- swap proposals (ptsampler.py:113-125): the initiator i sees its lower neighbour j = i+1
+            const int W = P.stride;
+            double thn[D], thp[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                thn[i] = __shfl_down_sync(0xffffffffu, th[i], 1, W);
+                thp[i] = __shfl_up_sync(0xffffffffu, th[i], 1, W);
+            }
+            const double lln = __shfl_down_sync(0xffffffffu, ll, 1, W), lpn = __shfl_down_sync(0xffffffffu, lp, 1, W);
+            const double llpv = __shfl_up_sync(0xffffffffu, ll, 1, W);
+            const double beta_n = P.betas[min(ti + 1, P.nt - 1)];
+            const double lp_ij = combine_logpost(0.0, lln * beta);      // model_i at theta_j
+            const double lp_ji = combine_logpost(0.0, ll * beta_n);     // model_j at theta_i
+            const double x = exp((lp_ji + lp_ij) - (lp + lpn));
+            const double mhr = (x < 1.0) ? x : 1.0;                     // Python min(1, x): nan -> 1
+            const bool sw = is_init && (uacc < mhr);                    // :121
+            const bool sw_prev = __shfl_up_sync(0xffffffffu, (int)sw, 1, W) != 0;
+            if (is_init) {
+                lpq = lp_ij; acc = sw;
+#pragma unroll
+                for (int i = 0; i < D; ++i) q[i] = thn[i];
+                if (sw) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) th[i] = thn[i];
+                    ll = lln; lp = lp_ij;
+                }
+            } else if (is_part) {
+                lpq = combine_logpost(0.0, llpv * beta); acc = sw_prev;
+#pragma unroll
+                for (int i = 0; i < D; ++i) q[i] = thp[i];
+                if (sw_prev) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) th[i] = thp[i];
+                    ll = llpv; lp = lpq;
+                }
+            }
+        }
+        if (!active) continue;
+        if (tr.d_prop_theta) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) tr.d_prop_theta[(t * K + c) * D + i] = q[i];
         }
         if (P.adapt) ad.update(moved, P.target);
-        dacc += acc ? 1 : 0;
+        dacc += (acc && regular) ? 1 : 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { s1[i] += th[i]; s2[i] += th[i] * th[i]; }
 
@@ -244,6 +326,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         }
     }
 
+    if (!active) return;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         st.theta[(int64_t)i * K + c] = th[i];
@@ -251,6 +334,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         st.S2[(int64_t)i * K + c] += s2[i];
     }
     st.lp[c] = lp;
+    if (pt) st.ll[c] = ll;
     st.scale[c] = ad.scale;
     st.nsamp[c] = ad.nsamples;
     st.nacc[c] = ad.naccepts;
@@ -268,7 +352,9 @@ __global__ void sg_set_state_kernel(const SGParams<D>* __restrict__ gp, SGState 
         th[i] = theta_in[c * D + i];
         st.theta[(int64_t)i * K + c] = th[i];
     }
-    st.lp[c] = gauss_logpost<D>(*gp, th);
+    const double ll = gauss_loglik<D>(*gp, th);
+    st.ll[c] = ll;
+    st.lp[c] = combine_logpost(0.0, gp->nt > 0 ? ll * gp->betas[c % gp->nt] : ll);
 }
 
 template <int D>
@@ -300,12 +386,13 @@ struct SmallGaussSampler : SamplerImpl {
     rmn_sampler* s;
     SGState st{};
     SGParams<D>* d_params = nullptr;
+    SGParams<D> hparams{};
     explicit SmallGaussSampler(rmn_sampler* s_) : s(s_) {}
     ~SmallGaussSampler() override { if (d_params) cudaFree(d_params); }
 
     size_t workspace_bytes() const override {
         const size_t K = (size_t)s->K;
-        return align256(D * K * 8) * 3 + align256(K * 8) * 5 + 256;
+        return align256(D * K * 8) * 3 + align256(K * 8) * 6 + 256;
     }
     int bind(void* ws) override {
         const size_t K = (size_t)s->K;
@@ -314,6 +401,7 @@ struct SmallGaussSampler : SamplerImpl {
         st.S1 = (double*)p; p += align256(D * K * 8);
         st.S2 = (double*)p; p += align256(D * K * 8);
         st.lp = (double*)p; p += align256(K * 8);
+        st.ll = (double*)p; p += align256(K * 8);
         st.scale = (double*)p; p += align256(K * 8);
         st.nsamp = (long long*)p; p += align256(K * 8);
         st.nacc = (long long*)p; p += align256(K * 8);
@@ -337,6 +425,7 @@ struct SmallGaussSampler : SamplerImpl {
             pack_lower(pr->h_chMinv, D, h.chMinv);
             for (int i = 0; i < D * D; ++i) h.Minv[i] = pr->h_Minv[i];
         }
+        hparams = h;
         RMN_CUDA(cudaMalloc(&d_params, sizeof(h)));
         RMN_CUDA(cudaMemcpy(d_params, &h, sizeof(h), cudaMemcpyHostToDevice));
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
@@ -346,6 +435,31 @@ struct SmallGaussSampler : SamplerImpl {
         return RMN_OK;
     }
     unsigned grid() const { return (unsigned)((s->K + 127) / 128); }
+    // tempered runs: one ladder per `stride` threads
+    unsigned run_grid() const {
+        if (hparams.nt == 0) return grid();
+        const int64_t threads = (s->K / hparams.nt) * hparams.stride;
+        return (unsigned)((threads + 127) / 128);
+    }
+    // PTSampler (ptsampler.py:41-81): chains c = l*nt + i form ladder l with beta_i; call before set_state
+    int set_tempering(int nt, const double* betas, double pswap) override {
+        RMN_REQUIRE(nt >= 2 && nt <= 32 && betas, "set_tempering: need 2 <= nt <= 32 temperatures");
+        RMN_REQUIRE(pswap > 0.0 && pswap < 1.0, "Pswap must be a number between 0 and 1");
+        RMN_REQUIRE(s->K % nt == 0, "set_tempering: the number of chains (%lld) must be a multiple of nt = %d", (long long)s->K, nt);
+        RMN_REQUIRE(s->chain_offset % nt == 0, "set_tempering: chain_offset must be a multiple of nt");
+        RMN_REQUIRE(hparams.adapt == 0, "parallel tempering supports non-adaptive proposals only (the reference shares ONE "
+                                        "proposal object between all temperatures, ptsampler.py:81)");
+        RMN_REQUIRE(hparams.kind != RMN_PROP_HMC, "parallel tempering: the HMC gradient is not tempered in the reference; use RW or pCN");
+        for (int i = 0; i < nt; ++i) {
+            RMN_REQUIRE(betas[i] >= 0.0 && betas[i] <= 1.0, "beta = %g must be a number between 0 and 1", betas[i]);
+            hparams.betas[i] = betas[i];
+        }
+        int stride = 1;
+        while (stride < nt) stride *= 2;
+        hparams.nt = nt; hparams.stride = stride; hparams.pswap = pswap;
+        RMN_CUDA(cudaMemcpy(d_params, &hparams, sizeof(hparams), cudaMemcpyHostToDevice));
+        return RMN_OK;
+    }
 
     int set_state(const double* d_theta, cudaStream_t stream) override {
         sg_set_state_kernel<D><<<grid(), 128, 0, stream>>>(d_params, st, s->K, d_theta);
@@ -362,13 +476,14 @@ struct SmallGaussSampler : SamplerImpl {
         if (tr) t0 = *tr;
         if (t0.thin <= 0) t0.thin = 1;
         if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        if (inj && hparams.nt > 0) RMN_REQUIRE(inj->d_usel, "injected tempered run needs d_usel (selection uniforms)");
         ktimer.begin("small_gauss_kernel", stream);
         if (inj) {
-            small_gauss_kernel<D, true><<<grid(), 128, 0, stream>>>(
-                d_params, st, s->K, T, step0, s->seed, s->chain_offset, inj->d_xi, inj->d_u, t0);
+            small_gauss_kernel<D, true><<<run_grid(), 128, 0, stream>>>(
+                d_params, st, s->K, T, step0, s->seed, s->chain_offset, inj->d_xi, inj->d_u, inj->d_usel, t0);
         } else {
-            small_gauss_kernel<D, false><<<grid(), 128, 0, stream>>>(
-                d_params, st, s->K, T, step0, s->seed, s->chain_offset, nullptr, nullptr, t0);
+            small_gauss_kernel<D, false><<<run_grid(), 128, 0, stream>>>(
+                d_params, st, s->K, T, step0, s->seed, s->chain_offset, nullptr, nullptr, nullptr, t0);
         }
         ktimer.end(stream);
         RMN_KERNEL_CHECK(); launches++;

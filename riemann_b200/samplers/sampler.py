@@ -42,7 +42,7 @@ class ChangepointTrace(object):
 
 
 class Sampler(object):
-    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64"):
+    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64", _tempering=None):
         """
         :param theta0: starting point.  Fixed-d models: shape (d,) (shared by all K
             chains) or (K, d).  Changepoint model: a ChangepointParams or a list of K.
@@ -108,6 +108,10 @@ class Sampler(object):
         self.seed, self.chain_offset = int(seed), int(chain_offset)
         self.total_steps = 0
 
+        if _tempering is not None:            # PTSampler: ladders along the chain axis, before the first evaluation
+            betas, pswap = _tempering
+            b = np.ascontiguousarray(betas, dtype=np.float64)
+            _lib.check(lib.rmn_sampler_set_tempering(h, len(b), b.ctypes.data_as(C.c_void_p), float(pswap)))
         if self._is_cp:
             self._cp_upload(states)
         else:
@@ -250,7 +254,7 @@ class Sampler(object):
         if inject is not None:
             inj = _lib.Inject()
             keep = []
-            for name in ("xi", "u", "tape"):
+            for name in ("xi", "u", "tape", "usel"):
                 if name in inject and inject[name] is not None:
                     t = torch.as_tensor(np.ascontiguousarray(inject[name], dtype=np.float64),
                                         device="cuda")
@@ -324,7 +328,7 @@ class Sampler(object):
             out["prop_theta"] = bufs["pth"].cpu().numpy()
         return out
 
-    def run_injected(self, xi=None, u=None, tape=None, Nburn=0, Nthin=1):
+    def run_injected(self, xi=None, u=None, tape=None, Nburn=0, Nthin=1, usel=None):
         """
         Replay a given noise stream instead of Philox (parity mode):
         fixed-d: xi[T, K, d] (or [T, d] for K = 1) and u[T, K]; changepoint: tape[T, K, NSLOT].
@@ -348,6 +352,11 @@ class Sampler(object):
             if xi.shape[1:] != (self.K, self.d) or u.shape != xi.shape[:2]:
                 raise ParameterError("xi must be [T, K, d] and u [T, K]")
             T, inj = xi.shape[0], {"xi": xi, "u": u}
+            if usel is not None:                       # tempered samplers: swap-selection uniforms
+                usel = np.asarray(usel, dtype=np.float64)
+                if usel.shape != u.shape:
+                    raise ParameterError("usel must be [T, K] like u")
+                inj["usel"] = usel
         return self.run(T, Nburn, Nthin, trace=True, inject=inj, extras=True)
 
     def _last_record(self):

@@ -1,0 +1,84 @@
+"""
+GPU parity for parallel tempering ("next" row N3): riemann_b200.PTSampler / rmn_sampler_set_tempering against
+the recorded stream of the reference's PTSampler (riemann/samplers/ptsampler.py:41-127, fixtures
+tests/golden/pt_rw_gauss{2,5}d.npz written by oracle/gen_golden.py): every temperature's chain, tempered
+log-posterior and swap decision at every step; several ladders side by side; distributional checks in Philox mode.
+Tolerance 1e-9 (fp64 device vs fp64 numpy).
+"""
+import numpy as np
+import pytest
+
+from gpu_helpers import device_gauss, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _pt(g, d, K=1, **kw):
+    from riemann_b200 import PTSampler
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    return PTSampler(device_gauss(g, d), MetropolisRandomWalk(g["C0"]), g["thetas"][0, 0], K=K, **kw)
+
+
+@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5)])
+def test_injected_ladder_matches_reference(golden, name, d):
+    g = golden(name)
+    pt = _pt(g, d)
+    assert np.array_equal(pt.betas, g["betas"]) and pt.Pswap == float(g["pswap"])
+    ex = pt.run_injected(g["usel"], g["xi"], g["u"])
+    T, nt = g["usel"].shape
+    for i in range(nt):
+        assert relerr(np.array(pt.samplers[i]._chain_thetas), g["thetas"][i]) < TOL
+        assert relerr(np.array(pt.samplers[i]._chain_logpost), g["logpost"][i]) < TOL
+    assert relerr(np.array(pt._chain_thetas), g["thetas"][0]) < TOL          # ptsampler.py:89-90
+    # swap decisions: an accepted swap shows as both partners changing state at a swap step
+    kind = g["kind"]
+    moved_ref = np.any(g["thetas"][:, 1:] != g["thetas"][:, :-1], axis=2).T   # [T][nt]
+    acc = ex["accepted"].astype(bool)                                         # [T][nt]
+    assert np.array_equal(acc[kind == 1], moved_ref[kind == 1])
+    assert np.array_equal(acc[kind == 2], moved_ref[kind == 2])
+
+
+def test_many_ladders_each_replay_the_stream(golden):
+    """K = 13 ladders x 5 temperatures = 65 chains (ladders straddle warp boundaries in chain space, not in
+    thread space): every ladder fed the same stream reproduces the reference."""
+    g = golden("pt_rw_gauss2d")
+    K, T = 13, 400
+    pt = _pt(g, 2, K=K)
+    rep = lambda a: np.concatenate([a[:T]] * K, axis=1)
+    pt.run_injected(rep(g["usel"]), rep(g["xi"]), rep(g["u"]))
+    th, lp = pt.samplers[3]._chain_thetas, pt.samplers[3]._chain_logpost      # [rec, K, d]
+    for l in (0, 6, 12):
+        assert relerr(th[:, l], g["thetas"][3, :T + 1]) < TOL
+        assert relerr(lp[:, l], g["logpost"][3, :T + 1]) < TOL
+
+
+def test_philox_ladder_samples_every_tempered_target(golden):
+    """Philox mode, 512 ladders: temperature i must sample N(mu, C / beta_i); swap moves keep that invariant."""
+    from scipy import stats
+    g = golden("pt_rw_gauss2d")
+    pt = _pt(g, 2, K=512, seed=5)
+    pt.run(3000, trace=False)
+    th = pt._thetas[-1]                                                       # [K, nt, d]
+    for i, beta in enumerate(pt.betas):
+        x = th[:, i]
+        assert stats.kstest(x[:, 0] * np.sqrt(beta), "norm").pvalue > 1e-3
+        assert stats.kstest((x[:, 0] - x[:, 1]) * np.sqrt(beta / 0.2), "norm").pvalue > 1e-3
+    lp = pt._logpost[-1]
+    from riemann_b200.models import benchmarks
+    ll = benchmarks.benchmark_gauss2d_corr.log_posterior_batch(th.reshape(-1, 2)).cpu().numpy().reshape(512, -1)
+    assert relerr(lp, ll * pt.betas[None, :]) < 1e-10                         # carried tempered log-posterior
+
+
+def test_tempering_rejects_what_the_reference_cannot_mean(golden):
+    from riemann_b200 import PTSampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import AdaptScaleRandomWalk, MetropolisRandomWalk
+    from riemann_b200.sampling_errors import ParameterError
+    m = benchmarks.benchmark_gauss2d_corr
+    with pytest.raises(ParameterError):
+        PTSampler(m, MetropolisRandomWalk(np.eye(2)), np.ones(2), Pswap=1.5)          # ptsampler.py:71-72
+    with pytest.raises(ParameterError):
+        PTSampler(m, AdaptScaleRandomWalk(np.eye(2)), np.ones(2))                    # shared adaptive proposal
+    with pytest.raises(ParameterError):
+        PTSampler(m, MetropolisRandomWalk(np.eye(2)), np.ones(2), betas=[1.0, 1.5])   # :26-27

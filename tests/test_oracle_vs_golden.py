@@ -167,3 +167,21 @@ def test_live_stream_matches_tape(golden):
     with np.errstate(all="ignore"):
         s.run(1500)
     assert np.max(np.abs(np.array(s._chain_logpost) - g["logpost"][0, :1501])) < TOL
+
+
+@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5)])
+def test_parallel_tempering(golden, name, d):
+    """N3: port.PTSampler replays the recorded stream of the reference's PTSampler (ptsampler.py:41-127):
+    every temperature's chain, log-posterior and swap decision."""
+    g = golden(name)
+    m = _gauss(g, d)
+    pt = port.PTSampler(m, port.MetropolisRandomWalk(g["C0"]), g["thetas"][0, 0],
+                        draws=port.PTTapeDraws(g["usel"], g["xi"], g["u"]))
+    assert np.array_equal(pt.betas, g["betas"]) and pt.Pswap == float(g["pswap"])
+    T = g["usel"].shape[0]
+    with np.errstate(all="ignore"):
+        pt.run(T)
+    for i, s in enumerate(pt.samplers):
+        assert np.max(np.abs(np.array(s._chain_thetas) - g["thetas"][i])) < 1e-12
+        assert np.max(np.abs(np.array(s._chain_logpost) - g["logpost"][i])) < 1e-9
+    assert pt._chain_thetas is pt.samplers[0]._chain_thetas
