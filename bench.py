@@ -37,10 +37,10 @@ if ROOT not in sys.path:
 METRIC = "mh_chain_steps_per_sec"
 UNIT = "chain-steps/s"
 CHAINS_PER_GPU = {"changepoint": 65536, "gauss2d_rw": 1 << 20, "gauss1000_mala": 16384,
-                  "logistic_mala": 1024, "logistic_mmala": 512}
+                  "logistic_mala": 1024, "logistic_mmala": 512, "gauss2d_pt": 5 * (1 << 17)}
 # SURVEY.md section 8d / BASELINE.md section 4: algorithmic work per chain-step
 ALGO_FLOP = {"changepoint": 650.0, "gauss2d_rw": 40.0, "gauss1000_mala": 2.0e6,
-             "logistic_mala": 4.0e8, "logistic_mmala": 4.4e8}
+             "logistic_mala": 4.0e8, "logistic_mmala": 4.4e8, "gauss2d_pt": 40.0}
 
 
 # From the committed ncu captures (profiles/r1_*.md; `ncu --set full`, one launch of the dominant
@@ -226,6 +226,18 @@ def build_workload(name, K, seed, chain_offset, precision="f64"):
         s = Sampler(benchmarks.benchmark_gauss2d_corr, MetropolisRandomWalk(0.5 * np.eye(2)), np.ones(2),
                     K=K, seed=seed, chain_offset=chain_offset)
         return s, "benchmark_gauss2d_corr, MetropolisRandomWalk(0.5 I)"
+    if name == "gauss2d_pt":
+        # "next" row N3: parallel tempering, ladders of 5 temperatures (ptsampler.py default) along the chain axis
+        from riemann_b200 import PTSampler
+        from riemann_b200.models import benchmarks
+        from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+        if K % 5:
+            raise SystemExit("gauss2d_pt: chains per GPU must be a multiple of 5 (one ladder = 5 temperatures)")
+        pt = PTSampler(benchmarks.benchmark_gauss2d_corr, MetropolisRandomWalk(0.5 * np.eye(2)), np.ones(2),
+                       K=K // 5, seed=seed, chain_offset=chain_offset // 5)
+        pt._sampler._pt_owner = pt                      # keep the wrapper alive
+        return pt._sampler, ("benchmark_gauss2d_corr, PTSampler: %d ladders x 5 temperatures (0.5**arange(5)), "
+                             "Pswap = 0.1, MetropolisRandomWalk(0.5 I)" % (K // 5))
     if name == "gauss1000_mala":
         from riemann_b200.models import benchmarks
         from riemann_b200.proposals.hamiltonian import MALA
@@ -276,7 +288,7 @@ def run_engine(args):
     wl = args.workload
     Kg = args.chains or CHAINS_PER_GPU[wl]
     T = args.iters or {"changepoint": 1000, "gauss2d_rw": 2000, "gauss1000_mala": 20,
-                       "logistic_mala": 2, "logistic_mmala": 2}[wl]
+                       "logistic_mala": 2, "logistic_mmala": 2, "gauss2d_pt": 2000}[wl]
     seed = 20261018
     s, desc = build_workload(wl, Kg, seed, rank * Kg, args.precision)
     stream = torch.cuda.current_stream()
@@ -366,7 +378,7 @@ def run_engine(args):
     ach_tflops = algo_flop_step * args.steps / (kernel_ms * 1e-3) / 1e12
     extra = peaks.get("extra", {})
     computed_fp64 = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12      # fp64 FMA lanes x clock
-    if wl in ("changepoint", "gauss2d_rw"):
+    if wl in ("changepoint", "gauss2d_rw", "gauss2d_pt"):
         peak = extra.get("fp64_dfma_tflops", computed_fp64)
         roof = {"bound": "alu", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach_tflops / peak, "traffic": None,

@@ -459,6 +459,35 @@ class Sampler(object):
             blk = reduce_block(blk)
         return summarize_block(blk.cpu().numpy())
 
+    # ------------------------------------------------------------------ trace wire format
+    def save_trace(self, path):
+        """Write the current history (`_chain_thetas` / `_chain_logpost`, i.e. the thinned device trace
+        of the last run) to a compressed .npz: `theta[rec, K, d]` (or k / cpx / cpv / sig for the
+        changepoint model), `logpost[rec, K]`, plus seed, chain offset, step counter and precision --
+        enough to resume with `Sampler(..., theta0=last record)` + `rmn_sampler_set_step`."""
+        meta = dict(seed=np.int64(self.seed), chain_offset=np.int64(self.chain_offset),
+                    step=np.int64(_lib.load().rmn_sampler_get_step(self._handle)), K=np.int64(self.K),
+                    precision=np.array(self.precision))
+        lp = np.asarray(self._chain_logpost, dtype=np.float64)
+        if self._is_cp:
+            tr = self._chain_thetas
+            if isinstance(tr, list):
+                k, cpx, cpv, sig = pack_states(tr)
+                k, cpx, cpv, sig = k[:, None], cpx[:, None], cpv[:, None], sig[:, None]
+            else:
+                k, cpx, cpv, sig = tr.k, tr.cpx, tr.cpv, tr.sig
+            np.savez_compressed(path, k=k, cpx=cpx, cpv=cpv, sig=sig, logpost=lp.reshape(k.shape[0], -1), **meta)
+        else:
+            th = np.asarray(self._chain_thetas, dtype=np.float64)
+            th = th.reshape(th.shape[0], self.K, self.d)
+            np.savez_compressed(path, theta=th, logpost=lp.reshape(th.shape[0], self.K), **meta)
+
+    @staticmethod
+    def load_trace(path):
+        """-> dict of the arrays `save_trace` wrote."""
+        with np.load(path, allow_pickle=False) as z:
+            return {k: z[k] for k in z.files}
+
     def enable_kernel_timing(self, enable=True):
         """CUDA-event timing of the dominant kernel's launches (measurement aid, see bench.py)."""
         _lib.check(_lib.load().rmn_sampler_enable_kernel_timing(self._handle, 1 if enable else 0))

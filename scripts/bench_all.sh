@@ -13,3 +13,4 @@ run cfg5_logistic_mmala_tf32metric --workload logistic_mmala --chains 4096 --ste
 run cfg4_logistic_mala_tf32x3 --workload logistic_mala --steps 2 --warmup 3 --iters 2 --precision tf32x3 --no-cpu
 run cfg4_logistic_mala_k8192_tf32x3 --workload logistic_mala --chains 8192 --steps 2 --warmup 3 --iters 1 --precision tf32x3 --no-cpu
 run cfg5_logistic_mmala_tf32x3 --workload logistic_mmala --chains 4096 --steps 2 --warmup 3 --iters 1 --precision tf32x3 --no-cpu
+run n3_gauss2d_pt --workload gauss2d_pt --steps 5 --warmup 3 --no-cpu
