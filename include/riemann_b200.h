@@ -99,6 +99,14 @@ int rmn_model_cp_logpost(rmn_model_t* m, int which, int64_t n, const int32_t* d_
 int rmn_proposal_rw_create(rmn_proposal_t** out, int d, const double* h_L, int adapt,
                            double target);
 
+/* AdaptCovRandomWalk = AdaptiveMetropolisRandomWalk = HaarioRandomWalk (riemann/proposals/randomwalk.py:40-59,
+ * adaptive.py:38-103): per chain, the proposal covariance follows the sample covariance of the chain's history,
+ * recomputed (and refactored in-kernel) whenever the number of states is a perfect square > 2; options t_adapt,
+ * marginalize, smooth_adapt as in the reference.  h_C0 is the initial covariance, h_L0 = chol(C0), both d x d
+ * row-major.  Small-d path only (d <= 8). */
+int rmn_proposal_adaptcov_create(rmn_proposal_t** out, int d, const double* h_C0, const double* h_L0,
+                                 double t_adapt, int marginalize, int smooth_adapt);
+
 /* VanillaHMC / AdaptScaleHMC (riemann/proposals/hamiltonian.py:13-103); nsteps = 1
  * is MALA.  The gradient is the model's own grad log posterior.  Mass matrix
  * optional: pass h_chM = chol(M), h_Minv = M^{-1}, h_chMinv = chol(M)^{-1}
@@ -204,6 +212,9 @@ int rmn_sampler_create_ex(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p
                           int64_t chain_offset, uint64_t seed, void* d_workspace,
                           size_t workspace_bytes, int precision);
 int rmn_sampler_destroy(rmn_sampler_t* s);
+
+/* AdaptCovProposal.L of every chain: d_L[K][d][d] (lower triangular). */
+int rmn_sampler_get_adaptcov(rmn_sampler_t* s, double* d_L, void* stream);
 
 /* PTSampler (riemann/samplers/ptsampler.py:41-127) on the small-d Gaussian family: chains c = l*nt + i form ladder l,
  * chain i of a ladder samples TemperedModel(model, h_betas[i]) (likelihood * beta, :33-34); every step each chain either

@@ -313,6 +313,37 @@ def _n3_pt_fixtures(R):
                 extra=dict(C0=0.3 * C5, mu=mu5, C=C5))
 
 
+def _n5_adaptcov_fixtures(R):
+    """"next" row N5: AdaptCovRandomWalk (randomwalk.py:40-56, adaptive.py:38-103) -- needs shim 6 (np.float)."""
+    B = R.benchmarks
+    def run(name, model, d, theta0, T, seed, **kw):
+        C0 = 0.1 * np.eye(d)
+        prop = R.AdaptCovRandomWalk(C0.copy(), **kw)
+        _vector_fixture(R, name, model, prop, theta0, T, seed,
+                        extra=dict(C0=C0, L_final=np.array(prop.L), t_adapt=np.float64(kw.get("t_adapt", 1)),
+                                   marginalize=np.int64(kw.get("marginalize", False)),
+                                   smooth_adapt=np.int64(kw.get("smooth_adapt", False))))
+        g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        out = {k: g[k] for k in g.files}
+        out["L_final"] = np.array(prop.L)                       # after the run
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    run("adaptcov_gauss2d", B.benchmark_gauss2d_corr, 2, np.ones(2), 1200, 701)
+    run("adaptcov_smooth_gauss2d", B.benchmark_gauss2d_corr, 2, np.ones(2), 800, 702, t_adapt=50, smooth_adapt=True)
+    rng = np.random.Generator(np.random.Philox(7))
+    A = rng.standard_normal((5, 5))
+    C5 = A @ A.T / 5 + 0.2 * np.eye(5)
+    mu5 = rng.standard_normal(5)
+    g5 = R.MultiGaussianDist(mu5, C5)
+    for nm, kw in (("adaptcov_gauss5d", {}), ("adaptcov_marg_gauss5d", dict(marginalize=True)),
+                   ("adaptcov_smooth_gauss5d", dict(t_adapt=30, smooth_adapt=True)),
+                   ("adaptcov_smooth_marg_gauss5d", dict(t_adapt=30, smooth_adapt=True, marginalize=True))):
+        run(nm, g5, 5, np.zeros(5), 1000, 703, **kw)
+        g = np.load(os.path.join(GOLDEN_DIR, nm + ".npz"))
+        out = {k: g[k] for k in g.files}
+        out.update(mu=mu5, C=C5)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, nm + ".npz"), **out)
+
+
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
@@ -356,6 +387,9 @@ def main():
     R = refshim.load_reference()
     if "--only-n1-dense" in sys.argv:
         _n1_dense_fixtures(R)
+        return
+    if "--only-n5-adaptcov" in sys.argv:
+        _n5_adaptcov_fixtures(R)
         return
     if "--only-n3-pt" in sys.argv:
         _n3_pt_fixtures(R)
@@ -426,6 +460,7 @@ def main():
                     track_scale=True)
     _n1_dense_fixtures(R)
     _n3_pt_fixtures(R)
+    _n5_adaptcov_fixtures(R)
     # pCN ("next" row N2)
     _vector_fixture(R, "pcn_gauss2d", g2, R.pCN(np.eye(2), 0.5), np.ones(2), 800, 305,
                     extra=dict(C0=np.eye(2), rho=np.float64(0.5)))

@@ -16,6 +16,8 @@ Shims
                                     reference's own ``log|det J|`` lines (:72-78) run
 3. ``sys.modules['riemann.riemann'] = riemann``   (changepoint.py:15 bad import)
 4. ``riemann.proposals.MetropolisRandomWalk``     (examples/test_changepoint.py:15)
+6. numpy >= 1.24 removed ``np.float`` (riemann/proposals/adaptive.py:82): ``np.float = float`` while
+   the AdaptCov proposals run (value-preserving: it was an alias of the builtin).
 5. numpy >= 1.24: a ``sig`` move turns ``theta.sig`` into a shape-(1,) array and
    ``model.py:50`` then builds a ragged list -> subclass that squeezes the two
    terms to floats (value-preserving).
@@ -103,6 +105,8 @@ def load_reference():
     if not reference_available():
         raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
     _install_stubs()
+    if not hasattr(np, "float"):
+        np.float = float                                           # shim 6 (adaptive.py:82)
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import riemann
@@ -138,6 +142,7 @@ def load_reference():
         MetropolisRandomWalk=randomwalk.MetropolisRandomWalk,
         AdaptScaleRandomWalk=randomwalk.AdaptScaleRandomWalk,
         pCN=randomwalk.pCN,
+        AdaptCovRandomWalk=randomwalk.AdaptCovRandomWalk,
         AdaptScaleProposal=adaptive.AdaptScaleProposal,
         VanillaHMC=hamiltonian.VanillaHMC, AdaptScaleHMC=hamiltonian.AdaptScaleHMC,
         leapfrog=hamiltonian.leapfrog,

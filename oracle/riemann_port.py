@@ -369,6 +369,44 @@ class AdaptScaleRandomWalk(AdaptScaleProposal, MetropolisRandomWalk):
         MetropolisRandomWalk.__init__(self, C)
 
 
+class AdaptCovRandomWalk(MetropolisRandomWalk):
+    """randomwalk.py:40-56 + adaptive.py:38-103 (Haario et al. 2001): the proposal covariance follows the sample
+    covariance of the chain history, recomputed when the number of states n is a perfect square > 2.
+    The strict (non-smooth) mode with n < t_adapt is not restated: there the reference divides its current C in
+    place (adaptive.py:89-91 stores to a dead attribute, :101 then rescales the old C, which on the first occasion
+    is the caller's C0 array itself); t_adapt <= 4 never gets there."""
+
+    def __init__(self, C0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        MetropolisRandomWalk.__init__(self, C0)
+        if not smooth_adapt and t_adapt > 4:
+            raise ParameterError("strict Haario mode with t_adapt > 4 is an in-place aliasing bug in the reference")
+        self.C0 = np.array(np.atleast_2d(C0), dtype=np.float64)
+        self.C = self.C0
+        self.t_adapt, self.marginalize, self.smooth_adapt = t_adapt, marginalize, smooth_adapt
+        self._S, self._SX, self._SX2 = 0.0, 0.0, 0.0
+
+    def adapt(self, theta):
+        X = np.atleast_1d(theta)
+        self._S += 1
+        self._SX = self._SX + X
+        self._SX2 = self._SX2 + X[:, None] * X[None, :]
+        n = float(self._S)
+        # adaptive.py:82-83.  NB: on numpy scalars `x ** 2` is libm pow(x, 2.0); the test is true for all perfect squares
+        # and, through rounding, for about half of the other n (and not for the same n as `x * x == n`: 238, 952, ...)
+        if np.sqrt(n) ** 2 == n and n > 2:
+            Cs = (self._SX2 - self._SX[:, None] * self._SX[None, :] / n) / (n - 1)
+            if self.smooth_adapt:
+                C = (n * Cs + self.t_adapt * self.C0) / (n + self.t_adapt)        # :86-87
+            else:
+                Creg = np.mean(np.diag(self.C0)) * np.eye(Cs.shape[0])
+                C = Cs + 1e-12 * Creg                                             # :92-93
+            if self.marginalize:
+                C = np.diag(np.diag(C))                                           # :96-97
+            d = C.shape[0]
+            self.C = C / d ** 0.4                                                 # :101
+            self.L = np.linalg.cholesky(self.C) / d ** 0.2                        # :102
+
+
 class pCN(Proposal):
     """Preconditioned Crank-Nicolson.        riemann/proposals/randomwalk.py:78-100"""
 

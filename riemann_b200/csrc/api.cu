@@ -186,6 +186,24 @@ extern "C" int rmn_proposal_rw_create(rmn_proposal_t** out, int d, const double*
     return RMN_OK;
 }
 
+extern "C" int rmn_proposal_adaptcov_create(rmn_proposal_t** out, int d, const double* h_C0, const double* h_L0,
+                                            double t_adapt, int marginalize, int smooth_adapt) {
+    RMN_REQUIRE(out && h_C0 && h_L0 && d >= 1, "rmn_proposal_adaptcov_create: bad argument");
+    RMN_REQUIRE(d <= RMN_SMALL_D_MAX, "AdaptCovRandomWalk runs on the small-d path only (d <= %d, got %d)", RMN_SMALL_D_MAX, d);
+    if (int rc = lower_ok(h_L0, d, "rmn_proposal_adaptcov_create")) return rc;
+    RMN_REQUIRE(t_adapt >= 0 && isfinite(t_adapt), "rmn_proposal_adaptcov_create: t_adapt must be >= 0");
+    RMN_REQUIRE(smooth_adapt || t_adapt <= 4.0,
+                "AdaptCovRandomWalk: strict Haario mode with t_adapt > 4 is not reproduced (the reference rescales its "
+                "current C in place there, adaptive.py:89-101); use smooth_adapt or t_adapt <= 4");
+    rmn_proposal* p = new rmn_proposal();
+    p->kind = RMN_PROP_RW; p->d = d; p->adapt = 0; p->target = 0.25;
+    p->h_L.assign(h_L0, h_L0 + (size_t)d * d);
+    p->h_C0.assign(h_C0, h_C0 + (size_t)d * d);
+    p->acov = 1; p->ac_marginalize = marginalize ? 1 : 0; p->ac_smooth = smooth_adapt ? 1 : 0; p->ac_t_adapt = t_adapt;
+    *out = p;
+    return RMN_OK;
+}
+
 extern "C" int rmn_proposal_hmc_create(rmn_proposal_t** out, int d, double eps, int nsteps,
                                        const double* h_chM, const double* h_Minv,
                                        const double* h_chMinv, int adapt, double target) {
@@ -404,6 +422,11 @@ extern "C" int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block,
     RMN_S(s); RMN_REQUIRE(d_block, "rmn_sampler_reduce_diagnostics: null block");
     return s->impl->reduce_diag(d_block, (cudaStream_t)stream);
 }
+extern "C" int rmn_sampler_get_adaptcov(rmn_sampler_t* s, double* d_L, void* stream) {
+    RMN_REQUIRE(s && s->impl && d_L, "rmn_sampler_get_adaptcov: bad argument");
+    return s->impl->get_adaptcov(d_L, (cudaStream_t)stream);
+}
+
 extern "C" int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double* h_betas, double pswap) {
     RMN_REQUIRE(s && s->impl, "rmn_sampler_set_tempering: null sampler");
     return s->impl->set_tempering(nt, h_betas, pswap);

@@ -186,6 +186,10 @@ struct rmn_proposal {
     std::vector<double> h_chM, h_Minv, h_chMinv;
     // device copies for the large-d path
     double* d_L = nullptr;
+    // covariance adaptation (AdaptCovRandomWalk, adaptive.py:38-103)
+    int acov = 0, ac_marginalize = 0, ac_smooth = 0;
+    double ac_t_adapt = 1.0;
+    std::vector<double> h_C0;            // full d x d
     // changepoint mix
     double hscale = 0.0;
     double p_cum[3] = {0.20, 0.40, 0.60};
@@ -248,6 +252,7 @@ struct SamplerImpl {
     virtual int cp_set_state(const int32_t*, const double*, const double*, const double*, cudaStream_t) { return unsupported("cp_set_state"); }
     virtual int cp_get_state(int32_t*, double*, double*, double*, double*, cudaStream_t) { return unsupported("cp_get_state"); }
     virtual int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t st) = 0;
+    virtual int get_adaptcov(double*, cudaStream_t) { return unsupported("get_adaptcov (small-d AdaptCovRandomWalk samplers only)"); }
     virtual int set_tempering(int, const double*, double) { return unsupported("parallel tempering (small-d Gaussian samplers only)"); }
     virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }
     virtual int set_adapt(const double*, const int64_t*, const int64_t*, cudaStream_t) { return unsupported("set_adapt"); }

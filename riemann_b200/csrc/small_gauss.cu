@@ -9,6 +9,7 @@
 //   AdaptScaleProposal.adapt             riemann/proposals/adaptive.py:26-35
 //   MultiGaussianDist.log_likelihood / grad_log_likelihood   riemann/models/gaussian.py:49-58
 //   Model.log_posterior                  riemann/models/model.py:43-55
+//   AdaptCovProposal.adapt (Haario)      riemann/proposals/adaptive.py:38-103 (per chain; ACOV instantiation)
 //   PTSampler.sample / TemperedModel     riemann/samplers/ptsampler.py:11-38, 92-127  (set_tempering:
 //                                        ladders of nt chains on consecutive threads, swaps by shuffle)
 // Arithmetic is fp64 throughout (the reference is fp64 numpy).
@@ -36,6 +37,12 @@ struct SGParams {
     int nt, stride;
     double pswap;
     double betas[32];
+    // covariance adaptation (adaptive.py:38-103): acov = 0 off
+    int acov, marginalize, smooth;
+    double t_adapt, creg, dpow04, dpow02;   // creg = mean(diag(C0)); d**0.4, d**0.2 (:101-102)
+    double c0[D * D];
+    const uint32_t* acmask;                 // bit n: does the reference adapt at state count n (see haario_schedule)
+    long long acmask_n;
 };
 
 struct SGState {
@@ -48,6 +55,11 @@ struct SGState {
     long long* dacc;        // [K] accepts since diagnostics reset
     double* S1;             // [D][K]
     double* S2;             // [D][K]
+    // Haario state per chain (ACOV): n, sum x, sum x x^T (full), current proposal Cholesky factor (packed lower)
+    double* acS;            // [K]
+    double* acSX;           // [D][K]
+    double* acSX2;          // [D*D][K]
+    double* acL;            // [TRI][K]
 };
 
 template <int D>
@@ -127,8 +139,64 @@ __device__ __forceinline__ void velocity(const SGParams<D>& P, const double* p, 
     }
 }
 
-template <int D, bool INJ>
-__global__ void __launch_bounds__(128)
+// AdaptCovProposal.adapt for one chain: accumulate the state, and when n is a perfect square > 2 rebuild
+// C from the sample covariance and refactor it (adaptive.py:70-102).  Arithmetic in the reference's order
+// with explicit roundings (no FMA contraction), so the proposal matrix tracks numpy's to the last bits.
+template <int D>
+__device__ __forceinline__ void haario_adapt(const SGParams<D>& P, const double* x, double& n, double* sx, double* sx2,
+                                             double* L) {
+    n += 1.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) sx[i] = __dadd_rn(sx[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) sx2[i * D + j] = __dadd_rn(sx2[i * D + j], __dmul_rn(x[i], x[j]));
+    // :82-83  `np.sqrt(n)**2 == n and n > 2`: true for the perfect squares the comment there intends and, through
+    // rounding, for about half of all other n; the host tabulates it with the reference's own expression
+    bool hit;
+    if (n < (double)P.acmask_n) {
+        const unsigned ni = (unsigned)n;
+        hit = (P.acmask[ni >> 5] >> (ni & 31u)) & 1u;
+    } else {
+        const double r = sqrt(n);
+        hit = __dmul_rn(r, r) == n;
+    }
+    if (!(hit && n > 2.0)) return;
+    double Cm[D * D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double cs = __ddiv_rn(__dsub_rn(sx2[i * D + j], __ddiv_rn(__dmul_rn(sx[i], sx[j]), n)), n - 1.0);   // :84
+            double c;
+            if (P.smooth) c = __ddiv_rn(__dadd_rn(__dmul_rn(n, cs), __dmul_rn(P.t_adapt, P.c0[i * D + j])), __dadd_rn(n, P.t_adapt));   // :87
+            else c = __dadd_rn(cs, (i == j) ? __dmul_rn(1e-12, P.creg) : 0.0);   // :92-93 (n >= t_adapt guaranteed by the host)
+            if (P.marginalize && i != j) c = 0.0;                                // :96-97
+            Cm[i * D + j] = __ddiv_rn(c, P.dpow04);                              // :101
+        }
+    // L = chol(C) / d**0.2   (:102); lower, packed
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double s = Cm[j * D + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+        const double ljj = sqrt(s);
+        L[j * (j + 1) / 2 + j] = ljj;
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) {
+            double v = Cm[i * D + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+            L[i * (i + 1) / 2 + j] = v / ljj;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SGParams<D>::TRI; ++q) L[q] = L[q] / P.dpow02;
+}
+
+template <int D, bool INJ, bool ACOV, bool PT>
+__global__ void __launch_bounds__(128, (D <= 2 && !ACOV) ? 4 : 1)   // d <= 2: 128 registers = 16 warps/SM (config 1)
 small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t K, int64_t T,
                    int64_t step0, uint64_t seed, int64_t chain_offset, const double* __restrict__ inj_xi,
                    const double* __restrict__ inj_u, const double* __restrict__ inj_usel, rmn_trace_t tr) {
@@ -143,7 +211,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
     int ti;
     bool active;
     const int64_t c = chain_of_thread<D>(P, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, K, ti, active);
-    const bool pt = P.nt > 0;
+    constexpr bool pt = PT;                       // compile-time: the plain kernel carries no ladder logic
     if (!pt && !active) return;                 // tempered warps keep their idle threads for the shuffles
     const double beta = pt ? P.betas[ti] : 1.0;
 
@@ -153,6 +221,16 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
     double lp = st.lp[c];
     double ll = pt ? st.ll[c] : 0.0;
     AdaptState ad{st.scale[c], st.nsamp[c], st.nacc[c]};
+    double acn = 0.0, acsx[ACOV ? D : 1], acsx2[ACOV ? D * D : 1], acl[ACOV ? SGParams<D>::TRI : 1];
+    if (ACOV) {
+        acn = st.acS[c];
+#pragma unroll
+        for (int i = 0; i < D; ++i) acsx[ACOV ? i : 0] = st.acSX[(int64_t)i * K + c];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) acsx2[ACOV ? i : 0] = st.acSX2[(int64_t)i * K + c];
+#pragma unroll
+        for (int i = 0; i < SGParams<D>::TRI; ++i) acl[ACOV ? i : 0] = st.acL[(int64_t)i * K + c];
+    }
     long long dacc = st.dacc[c];
     double s1[D], s2[D];
 #pragma unroll
@@ -199,7 +277,8 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         double q[D], lqr = 0.0;
         if (P.kind == RMN_PROP_RW) {
             double lx[D];
-            tri_mv<D>(P.lprop, xi, lx);
+            if (ACOV) tri_mv<D>(acl, xi, lx);            // this chain's adapted factor
+            else tri_mv<D>(P.lprop, xi, lx);
 #pragma unroll
             for (int i = 0; i < D; ++i) q[i] = th[i] + ad.scale * lx[i];
         } else if (P.kind == RMN_PROP_PCN) {
@@ -307,6 +386,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
             for (int i = 0; i < D; ++i) tr.d_prop_theta[(t * K + c) * D + i] = q[i];
         }
         if (P.adapt) ad.update(moved, P.target);
+        if (ACOV) haario_adapt<D>(P, th, acn, acsx, acsx2, acl);          // adapt(theta) after every step (sampler.py:88)
         dacc += (acc && regular) ? 1 : 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { s1[i] += th[i]; s2[i] += th[i] * th[i]; }
@@ -334,6 +414,15 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         st.S2[(int64_t)i * K + c] += s2[i];
     }
     st.lp[c] = lp;
+    if (ACOV) {
+        st.acS[c] = acn;
+#pragma unroll
+        for (int i = 0; i < D; ++i) st.acSX[(int64_t)i * K + c] = acsx[ACOV ? i : 0];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) st.acSX2[(int64_t)i * K + c] = acsx2[ACOV ? i : 0];
+#pragma unroll
+        for (int i = 0; i < SGParams<D>::TRI; ++i) st.acL[(int64_t)i * K + c] = acl[ACOV ? i : 0];
+    }
     if (pt) st.ll[c] = ll;
     st.scale[c] = ad.scale;
     st.nsamp[c] = ad.nsamples;
@@ -368,12 +457,34 @@ __global__ void sg_get_state_kernel(SGState st, int64_t K, double* theta_out, do
     if (lp_out) lp_out[c] = st.lp[c];
 }
 
+template <int D>
+__global__ void sg_get_acl_kernel(SGState st, int64_t K, double* L_out) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j)
+            L_out[(c * D + i) * D + j] = (j <= i) ? st.acL[(int64_t)(i * (i + 1) / 2 + j) * K + c] : 0.0;
+}
+
 __global__ void sg_get_adapt_kernel(SGState st, int64_t K, double* scale, int64_t* ns, int64_t* na) {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= K) return;
     if (scale) scale[c] = st.scale[c];
     if (ns) ns[c] = st.nsamp[c];
     if (na) na[c] = st.nacc[c];
+}
+
+// The reference recomputes the covariance when `np.sqrt(n)**2 == n` (adaptive.py:82-83).  For numpy scalars
+// `x**2` is libm's pow(x, 2.0), which is not always the correctly rounded product (n = 238, 952, ... differ), so the
+// schedule is tabulated here on the host with the same libm call instead of being re-derived on the device.
+static std::vector<uint32_t> haario_schedule(long long nmax) {
+    std::vector<uint32_t> m((size_t)((nmax + 31) / 32), 0u);
+    double (*volatile pw)(double, double) = pow;           // volatile: keep the compiler from folding pow(x, 2) to x*x
+    for (long long n = 0; n < nmax; ++n) {
+        const double x = (double)n;
+        if (pw(sqrt(x), 2.0) == x) m[(size_t)(n >> 5)] |= 1u << (n & 31);
+    }
+    return m;
 }
 
 static void pack_lower(const std::vector<double>& full, int d, double* out) {
@@ -387,12 +498,15 @@ struct SmallGaussSampler : SamplerImpl {
     SGState st{};
     SGParams<D>* d_params = nullptr;
     SGParams<D> hparams{};
+    uint32_t* d_acmask = nullptr;
     explicit SmallGaussSampler(rmn_sampler* s_) : s(s_) {}
-    ~SmallGaussSampler() override { if (d_params) cudaFree(d_params); }
+    ~SmallGaussSampler() override { if (d_params) cudaFree(d_params); if (d_acmask) cudaFree(d_acmask); }
 
     size_t workspace_bytes() const override {
         const size_t K = (size_t)s->K;
-        return align256(D * K * 8) * 3 + align256(K * 8) * 6 + 256;
+        size_t n = align256(D * K * 8) * 3 + align256(K * 8) * 6 + 256;
+        if (s->prop->acov) n += align256(K * 8) + align256(D * K * 8) + align256(D * D * K * 8) + align256(SGParams<D>::TRI * K * 8);
+        return n;
     }
     int bind(void* ws) override {
         const size_t K = (size_t)s->K;
@@ -406,6 +520,12 @@ struct SmallGaussSampler : SamplerImpl {
         st.nsamp = (long long*)p; p += align256(K * 8);
         st.nacc = (long long*)p; p += align256(K * 8);
         st.dacc = (long long*)p; p += align256(K * 8);
+        if (s->prop->acov) {
+            st.acS = (double*)p; p += align256(K * 8);
+            st.acSX = (double*)p; p += align256(D * K * 8);
+            st.acSX2 = (double*)p; p += align256(D * D * K * 8);
+            st.acL = (double*)p; p += align256(SGParams<D>::TRI * K * 8);
+        }
 
         SGParams<D> h{};
         const rmn_model* m = s->model;
@@ -425,10 +545,29 @@ struct SmallGaussSampler : SamplerImpl {
             pack_lower(pr->h_chMinv, D, h.chMinv);
             for (int i = 0; i < D * D; ++i) h.Minv[i] = pr->h_Minv[i];
         }
+        if (pr->acov) {
+            h.acov = 1; h.marginalize = pr->ac_marginalize; h.smooth = pr->ac_smooth; h.t_adapt = pr->ac_t_adapt;
+            double tr = 0.0;
+            for (int i = 0; i < D; ++i) tr += pr->h_C0[(size_t)i * D + i];
+            h.creg = tr / D;
+            h.dpow04 = pow((double)D, 0.4); h.dpow02 = pow((double)D, 0.2);
+            for (int i = 0; i < D * D; ++i) h.c0[i] = pr->h_C0[i];
+            const long long nmax = 1ll << 22;                  // 4M states tabulated; beyond: correctly rounded r*r
+            const std::vector<uint32_t> mask = haario_schedule(nmax);
+            RMN_CUDA(cudaMalloc(&d_acmask, mask.size() * 4));
+            RMN_CUDA(cudaMemcpy(d_acmask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice));
+            h.acmask = d_acmask; h.acmask_n = nmax;
+        }
         hparams = h;
         RMN_CUDA(cudaMalloc(&d_params, sizeof(h)));
         RMN_CUDA(cudaMemcpy(d_params, &h, sizeof(h), cudaMemcpyHostToDevice));
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        if (pr->acov) {                                   // every chain starts from chol(C0) (adaptive.py:61)
+            for (int q = 0; q < SGParams<D>::TRI; ++q) {
+                int rc2 = rmn_fill_f64(st.acL + (size_t)q * K, s->K, h.lprop[q], 0);
+                if (rc2) return rc2;
+            }
+        }
         int rc = rmn_fill_f64(st.scale, s->K, 1.0, 0);
         if (rc) return rc;
         RMN_CUDA(cudaDeviceSynchronize());
@@ -447,6 +586,7 @@ struct SmallGaussSampler : SamplerImpl {
         RMN_REQUIRE(pswap > 0.0 && pswap < 1.0, "Pswap must be a number between 0 and 1");
         RMN_REQUIRE(s->K % nt == 0, "set_tempering: the number of chains (%lld) must be a multiple of nt = %d", (long long)s->K, nt);
         RMN_REQUIRE(s->chain_offset % nt == 0, "set_tempering: chain_offset must be a multiple of nt");
+        RMN_REQUIRE(hparams.acov == 0, "parallel tempering supports non-adaptive proposals only");
         RMN_REQUIRE(hparams.adapt == 0, "parallel tempering supports non-adaptive proposals only (the reference shares ONE "
                                         "proposal object between all temperatures, ptsampler.py:81)");
         RMN_REQUIRE(hparams.kind != RMN_PROP_HMC, "parallel tempering: the HMC gradient is not tempered in the reference; use RW or pCN");
@@ -478,13 +618,20 @@ struct SmallGaussSampler : SamplerImpl {
         if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
         if (inj && hparams.nt > 0) RMN_REQUIRE(inj->d_usel, "injected tempered run needs d_usel (selection uniforms)");
         ktimer.begin("small_gauss_kernel", stream);
+        const bool ac = hparams.acov != 0, ptm = hparams.nt > 0;
+#define RMN_SG_LAUNCH(INJ_, AC_, PT_, XI_, U_, US_)                                                      \
+        small_gauss_kernel<D, INJ_, AC_, PT_><<<run_grid(), 128, 0, stream>>>(                             \
+            d_params, st, s->K, T, step0, s->seed, s->chain_offset, XI_, U_, US_, t0)
         if (inj) {
-            small_gauss_kernel<D, true><<<run_grid(), 128, 0, stream>>>(
-                d_params, st, s->K, T, step0, s->seed, s->chain_offset, inj->d_xi, inj->d_u, inj->d_usel, t0);
+            if (ptm) RMN_SG_LAUNCH(true, false, true, inj->d_xi, inj->d_u, inj->d_usel);
+            else if (ac) RMN_SG_LAUNCH(true, true, false, inj->d_xi, inj->d_u, nullptr);
+            else RMN_SG_LAUNCH(true, false, false, inj->d_xi, inj->d_u, nullptr);
         } else {
-            small_gauss_kernel<D, false><<<run_grid(), 128, 0, stream>>>(
-                d_params, st, s->K, T, step0, s->seed, s->chain_offset, nullptr, nullptr, nullptr, t0);
+            if (ptm) RMN_SG_LAUNCH(false, false, true, nullptr, nullptr, nullptr);
+            else if (ac) RMN_SG_LAUNCH(false, true, false, nullptr, nullptr, nullptr);
+            else RMN_SG_LAUNCH(false, false, false, nullptr, nullptr, nullptr);
         }
+#undef RMN_SG_LAUNCH
         ktimer.end(stream);
         RMN_KERNEL_CHECK(); launches++;
         step0 += T; diag_steps += T;
@@ -498,6 +645,13 @@ struct SmallGaussSampler : SamplerImpl {
     int set_adapt(const double* sc, const int64_t* ns, const int64_t* na, cudaStream_t stream) override {
         launches++;
         return rmn_copy_adapt(s->K, sc, ns, na, st.scale, st.nsamp, st.nacc, stream);
+    }
+    // the adapted proposal factor of every chain, full lower-triangular [K][D][D] (AdaptCovProposal.L)
+    int get_adaptcov(double* d_L, cudaStream_t stream) override {
+        RMN_REQUIRE(hparams.acov, "this proposal does not adapt its covariance");
+        sg_get_acl_kernel<D><<<grid(), 128, 0, stream>>>(st, s->K, d_L);
+        RMN_KERNEL_CHECK(); launches++;
+        return RMN_OK;
     }
     int diag_dim() const override { return D; }
     int reset_diag(cudaStream_t stream) override {

@@ -313,10 +313,16 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
     const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
     ksplit = (Kdim / tk + kbp - 1) / kbp;
     const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM) * ksplit;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    static int sms_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& sms = sms_of[dev & 63];
+    if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));          // persistent: one CTA per SM
-    static bool attr = false;
+    static bool attr_done[64] = {false};          // function attributes are per device
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool& attr = attr_done[dev_id & 63];
     if (!attr) {
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

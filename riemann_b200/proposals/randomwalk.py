@@ -44,6 +44,36 @@ class AdaptScaleRandomWalk(AdaptScaleProposal, MetropolisRandomWalk):
         MetropolisRandomWalk.__init__(self, C_)
 
 
+class AdaptCovRandomWalk(MetropolisRandomWalk):
+    """randomwalk.py:40-56 + adaptive.py:38-103 (Haario et al. 2001): the proposal covariance follows the sample
+    covariance of the chain history; per chain, adapted and refactored inside the device kernel.  `.C` / `.L` are
+    refreshed from the device after every batch (arrays [K, d, d] for K > 1 chains).  Small-d path (d <= 8)."""
+
+    _adaptive = False
+    _adapt_cov = True
+
+    def __init__(self, C0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        MetropolisRandomWalk.__init__(self, C0)
+        self.C0 = np.array(np.atleast_2d(C0), dtype=np.float64)
+        self.C = self.C0
+        self.t_adapt, self.marginalize, self.smooth_adapt = t_adapt, marginalize, smooth_adapt
+
+    def _create_handle(self, d):
+        if self.L.shape[1] != d:
+            raise ParameterError("theta and L have incompatible shapes")
+        h = C.c_void_p()
+        C0 = np.ascontiguousarray(self.C0)
+        L0 = np.ascontiguousarray(np.linalg.cholesky(self.C0))
+        _lib.check(_lib.load().rmn_proposal_adaptcov_create(C.byref(h), d, _lib.ptr(C0), _lib.ptr(L0),
+                                                            float(self.t_adapt), int(bool(self.marginalize)),
+                                                            int(bool(self.smooth_adapt))))
+        return h
+
+
+# aliases of the reference (randomwalk.py:59)
+AdaptiveMetropolisRandomWalk = HaarioRandomWalk = AdaptCovRandomWalk
+
+
 class pCN(DeviceProposal):
     """Preconditioned Crank-Nicolson (randomwalk.py:78-100)."""
 

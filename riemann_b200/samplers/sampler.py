@@ -383,6 +383,14 @@ class Sampler(object):
     # ------------------------------------------------------------------ adaptation / diagnostics
     def _refresh_adapt(self):
         p = self.proposal
+        if getattr(p, "_adapt_cov", False):            # AdaptCovProposal.L / .C (adaptive.py:61-63, 101-102)
+            torch = self._torch
+            L = torch.empty((self.K, self.d, self.d), dtype=torch.float64, device="cuda")
+            _lib.check(_lib.load().rmn_sampler_get_adaptcov(self._handle, _lib.ptr(L), _lib.stream_ptr()))
+            L = L.cpu().numpy()
+            dd = float(self.d) ** 0.2
+            Cm = np.einsum("kij,klj->kil", L * dd, L * dd)          # L = chol(C) / d**0.2
+            p.L, p.C = (L[0], Cm[0]) if self.K == 1 else (L, Cm)
         if not getattr(p, "_adaptive", False):
             return
         torch, K = self._torch, self.K

@@ -185,3 +185,15 @@ def test_parallel_tempering(golden, name, d):
         assert np.max(np.abs(np.array(s._chain_thetas) - g["thetas"][i])) < 1e-12
         assert np.max(np.abs(np.array(s._chain_logpost) - g["logpost"][i])) < 1e-9
     assert pt._chain_thetas is pt.samplers[0]._chain_thetas
+
+
+@pytest.mark.parametrize("name,d", [("adaptcov_gauss2d", 2), ("adaptcov_smooth_gauss2d", 2),
+                                    ("adaptcov_gauss5d", 5), ("adaptcov_marg_gauss5d", 5),
+                                    ("adaptcov_smooth_gauss5d", 5), ("adaptcov_smooth_marg_gauss5d", 5)])
+def test_adapt_cov_random_walk(golden, name, d):
+    """N5: Haario-style covariance adaptation (adaptive.py:38-103 through randomwalk.py:40-56)."""
+    g = golden(name)
+    prop = port.AdaptCovRandomWalk(g["C0"], t_adapt=float(g["t_adapt"]), marginalize=bool(g["marginalize"]),
+                                   smooth_adapt=bool(g["smooth_adapt"]))
+    _replay(g, _gauss(g, d), prop, g["thetas"][0])
+    assert np.max(np.abs(prop.L - g["L_final"])) < 1e-12 * np.max(np.abs(g["L_final"]))
