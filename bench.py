@@ -13,8 +13,14 @@ collective (weak scaling: 65,536 chains per GPU); the only exchange is the per-b
 diagnostics all-reduce (NCCL), which is inside the timed region.
 
 Other workloads (`--workload gauss1000_mala | logistic_mala | logistic_mmala | gauss2d_rw`)
-print the same JSON line for BASELINE configs 3, 4, 5 and 1; they are for profiling and
-DESIGN.md, the driver's line is the default one.
+print the same JSON line for BASELINE configs 3, 4, 5 and 1, `gauss2d_pt` for the parallel-tempering
+"next" row; `--precision tf32x3 | tf32-metric` selects the tcgen05 tensor-core modes of the dense
+Gaussian and logistic workloads (default f64 = the parity mode).  They are for profiling and DESIGN.md;
+the driver's line is the default one.
+
+`roofline.achieved` is the algorithmic work of the timed region divided by the DOMINANT kernel's own time
+in it (CUDA events around each of its launches, rmn_sampler_kernel_timing); `tau_check` (changepoint) puts
+the Sokal-window autocorrelation time of a traced subset next to the moment-based one behind min_ess_per_sec.
 
 Timing: W untimed warm-up steps, then K steps each bracketed by CUDA events on the
 launching stream, L2 flushed (256 MiB write) between steps outside the event pairs,
