@@ -25,8 +25,10 @@
 // and fuses the accept-update (y += delta, V += P delta) into the finish/propose pass.
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include <stdlib.h>
 
 namespace tc {
+int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
                 const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
                 int mala, cudaStream_t st);
@@ -53,6 +55,7 @@ struct TState {
 
 struct TStep {
     int prop_kind, adapt, finish, propose, diag;
+    int row_reduce;      // 1: the GEMM used the plain epilogue (V' only); this pass forms quad' - quad and |p'|^2 itself
     double target, eps0, c1, c2;
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
     const double* inj_xi; const double* inj_u;
@@ -74,9 +77,39 @@ finish_propose_f32_kernel(TState st, TStep sp) {
 
     if (sp.finish) {
         double q = 0.0, k1 = 0.0;
-        for (int b = lane; b < st.nblk; b += 32) {
-            q += st.partq[(int64_t)b * K + r];
-            if (sp.prop_kind == RMN_PROP_HMC) k1 += st.partk[(int64_t)b * K + r];
+        if (sp.row_reduce) {
+            // quad' - quad = delta . (2 V + P delta) and |p'|^2 from the row itself: the same arithmetic the fused
+            // GEMM epilogue did, in a fixed lane-strided order (deterministic).  The row is re-read from L2 by the
+            // update loop below; the GEMM keeps its plain, store-only epilogue (140 us instead of 235 at config 3).
+            const size_t ro0 = (size_t)r * dp;
+            const double he = 0.5 * st.epsrow[r];
+            const bool mala = sp.prop_kind == RMN_PROP_HMC;
+            for (int j4 = lane * 4; j4 < dp; j4 += 128) {
+                const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro0 + j4);
+                const float4 b = *reinterpret_cast<const float4*>(st.Ypl + ro0 + j4);
+                const float4 w = *reinterpret_cast<const float4*>(st.V + ro0 + j4);
+                const float4 pd = *reinterpret_cast<const float4*>(st.Vp + ro0 + j4);
+                const double dl[4] = {(double)a.x + (double)b.x, (double)a.y + (double)b.y,
+                                      (double)a.z + (double)b.z, (double)a.w + (double)b.w};
+                const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
+                const double pv[4] = {(double)pd.x, (double)pd.y, (double)pd.z, (double)pd.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) q += dl[e] * (2.0 * wv[e] + pv[e]);
+                if (mala) {
+                    const float4 x = *reinterpret_cast<const float4*>(st.Xi + ro0 + j4);
+                    const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + pv[e]);   // hamiltonian.py:27,40
+                        k1 += p1 * p1;
+                    }
+                }
+            }
+        } else {
+            for (int b = lane; b < st.nblk; b += 32) {
+                q += st.partq[(int64_t)b * K + r];
+                if (sp.prop_kind == RMN_PROP_HMC) k1 += st.partk[(int64_t)b * K + r];
+            }
         }
         q = group_sum<32>(q);
         k1 = group_sum<32>(k1);
@@ -245,6 +278,7 @@ struct DenseTF32Sampler : SamplerImpl {
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = 2 * ((st.dp + tc::TN - 1) / tc::TN);   // one partial per 128-column half tile
+        if (const char* e = getenv("RMN_TF32_FUSED_EPI")) row_reduce = !(e[0] == '1');
     }
     ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
@@ -303,11 +337,16 @@ struct DenseTF32Sampler : SamplerImpl {
     }
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
     double c1() const { return st.d * log(2.0 * M_PI); }
+    // row_reduce (default): plain store-only GEMM epilogue, the MH reductions run in the finish/propose pass;
+    // RMN_TF32_FUSED_EPI=1 selects the fused epilogue (kept for A/B measurements, same results to rounding)
+    bool row_reduce = true;
     int gemm(int mala, cudaStream_t stream) {
         launches++;
         ktimer.begin("tf32x3_gemm_kernel", stream);
-        const int rc = tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
-                                       st.partq, st.partk, mala, stream);
+        int rc;
+        if (row_reduce) rc = tc::launch_plain(maps, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
+        else rc = tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
+                                  st.partq, st.partk, mala, stream);
         ktimer.end(stream);
         return rc;
     }
@@ -338,6 +377,7 @@ struct DenseTF32Sampler : SamplerImpl {
         TStep sp{};
         sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
         sp.c1 = c1(); sp.c2 = s->model->logdetC; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
+        sp.row_reduce = row_reduce ? 1 : 0;
         const int64_t K = st.K;
         const int d = st.d;
         for (int64_t t = 0; t <= T; ++t) {
