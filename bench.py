@@ -53,11 +53,13 @@ ALGO_FLOP = {"changepoint": 650.0, "gauss2d_rw": 40.0, "gauss1000_mala": 2.0e6,
 # kernel on this code): DRAM bytes per launch and the pipe/issue utilisation.  Static evidence,
 # NOT re-measured by this script -- the live numbers of a run are `value`, `ms_per_step`, `roofline.achieved`.
 PROFILED = {
+    ("gauss2d_rw", "f64"): {"kernel": "small_gauss_kernel<2,0,0,0>", "traffic": 92.7e6 + 36.6e6, "issue_slot_util": 0.652,
+                            "fp64_pipe_active": 0.281, "source": "profiles/r1_gauss2d_small_gauss.md"},
     ("changepoint", "f64"): {"kernel": "changepoint_kernel<0,2,4>", "traffic": 27.58e6 + 0.07e6, "issue_slot_util": 0.673,
                              "fp64_pipe_active": 0.219, "warp_inst_per_chain_step": 159, "source": "profiles/r1_changepoint_gl4.md"},
     ("gauss1000_mala", "f64"): {"kernel": "gemm_abt_kernel<1>", "traffic": 455.6e6 + 125.1e6, "tensor_pipe_active": 0.770,
                                 "source": "profiles/r1_gauss1000.md"},
-    ("gauss1000_mala", "tf32x3"): {"kernel": "tf32x3_gemm_kernel<1>", "traffic": 404.2e6 + 54.1e6, "tensor_pipe_active": 0.429,
+    ("gauss1000_mala", "tf32x3"): {"kernel": "tf32x3_gemm_kernel<0,3>", "traffic": 144.8e6 + 42.0e6, "tensor_pipe_active": 0.855,
                                    "source": "profiles/r1_gauss1000_tf32x3_gemm.md"},
     ("logistic_mala", "f64"): {"kernel": "lg_eval_kernel", "traffic": 812.9e6 + 7.9e6, "tensor_pipe_active": 0.683,
                                "source": "profiles/r1_logistic.md"},
