@@ -227,30 +227,50 @@ __global__ void tset_kernel(TState st, const double* __restrict__ theta) {
     if (j == 0) { st.k0[r] = 0.0; st.epsrow[r] = 0.0; }
 }
 // Exact (fp64) V = P y and log-posterior of the CURRENT fp32 states: start of a run and the
-// periodic refresh.  One block per chain row, y staged in shared memory, P rows read coalesced.
+// periodic refresh.  One block per RB = 8 chain rows (their y staged in shared memory), so every row of P a
+// warp reads serves 8 chains: one row per block streamed all of P (8 MB at d = 1000) from L2 per chain,
+// 131 GB per pass and 11.5 ms at config 3; this blocking brings it to the 2 ms range.
+constexpr int TEX_RB = 8;
 __global__ void __launch_bounds__(256) texact_kernel(TState st, double c1, double c2) {
-    extern __shared__ double ysh[];
-    __shared__ double red[8];
-    const int64_t r = blockIdx.x;
+    extern __shared__ double ysh[];                      // [TEX_RB][d]
+    __shared__ double red[8][TEX_RB];
+    const int64_t r0 = (int64_t)blockIdx.x * TEX_RB;
     const int d = st.d, dp = st.dp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = threadIdx.x; j < d; j += blockDim.x) ysh[j] = (double)st.Y[(size_t)r * dp + j];
+    for (int q = threadIdx.x; q < TEX_RB * d; q += blockDim.x) {
+        const int rr = q / d, j = q % d;
+        ysh[q] = (r0 + rr < st.K) ? (double)st.Y[(size_t)(r0 + rr) * dp + j] : 0.0;
+    }
     __syncthreads();
-    double quad = 0.0;
+    double quad[TEX_RB];
+#pragma unroll
+    for (int rr = 0; rr < TEX_RB; ++rr) quad[rr] = 0.0;
     for (int j = warp; j < d; j += 8) {
         const double* pr = st.prec + (size_t)j * d;
-        double s = 0.0;
-        for (int k = lane; k < d; k += 32) s += pr[k] * ysh[k];
-        s = group_sum<32>(s);
-        if (lane == 0) st.V[(size_t)r * dp + j] = (float)s;
-        quad += s * ysh[j];
+        double s[TEX_RB];
+#pragma unroll
+        for (int rr = 0; rr < TEX_RB; ++rr) s[rr] = 0.0;
+        for (int k = lane; k < d; k += 32) {
+            const double pk = pr[k];
+#pragma unroll
+            for (int rr = 0; rr < TEX_RB; ++rr) s[rr] += pk * ysh[rr * d + k];
+        }
+#pragma unroll
+        for (int rr = 0; rr < TEX_RB; ++rr) {
+            const double t = group_sum<32>(s[rr]);
+            if (lane == 0 && r0 + rr < st.K) st.V[(size_t)(r0 + rr) * dp + j] = (float)t;
+            quad[rr] += t * ysh[rr * d + j];
+        }
     }
-    if (lane == 0) red[warp] = quad;
+    if (lane == 0) {
+#pragma unroll
+        for (int rr = 0; rr < TEX_RB; ++rr) red[warp][rr] = quad[rr];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < TEX_RB && r0 + threadIdx.x < st.K) {
         double q = 0.0;
-        for (int w = 0; w < 8; ++w) q += red[w];
-        st.lp[r] = combine_logpost(0.0, -0.5 * ((q + c1) + c2));
+        for (int w = 0; w < 8; ++w) q += red[w][threadIdx.x];
+        st.lp[r0 + threadIdx.x] = combine_logpost(0.0, -0.5 * ((q + c1) + c2));
     }
 }
 __global__ void tget_kernel(TState st, double* theta, double* lp) {
@@ -357,7 +377,14 @@ struct DenseTF32Sampler : SamplerImpl {
         return exact(stream);
     }
     int exact(cudaStream_t stream) {
-        texact_kernel<<<(unsigned)st.K, 256, (size_t)st.d * 8, stream>>>(st, c1(), s->model->logdetC);
+        const size_t sm = (size_t)TEX_RB * st.d * 8;
+        static bool attr_set = false;
+        if (!attr_set && sm > 48 * 1024) {
+            RMN_CUDA(cudaFuncSetAttribute(texact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        RMN_REQUIRE(sm <= 200 * 1024, "tf32x3 dense path: d = %d exceeds the exact-refresh kernel's shared memory", st.d);
+        texact_kernel<<<(unsigned)((st.K + TEX_RB - 1) / TEX_RB), 256, sm, stream>>>(st, c1(), s->model->logdetC);
         RMN_KERNEL_CHECK(); launches++;
         since_refresh = 0;
         return RMN_OK;
