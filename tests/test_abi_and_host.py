@@ -171,3 +171,39 @@ def test_sokal_tau_matches_ar1_and_oracle():
         blk = np.array([K, N, 0, 0, N, 0, m.sum(), (m * m).sum(), v.sum()])
         assert abs(summarize_block(blk)["tau"][0] / want - 1) < 0.25
         assert abs(dg.effective_sample_size(x)[0] / (N * K / want) - 1) < 0.05
+
+
+def test_bench_line_contract():
+    """The JSON line bench.py printed on a B200 in round 1 (tests/golden/bench_line_changepoint_r1.json,
+    gpurun r60) against the measurement contract: every required key, its type and the internal consistency
+    of the numbers.  bench.py's static tables must cover every workload it offers."""
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "bench_line_changepoint_r1.json")) as f:
+        d = json.load(f)
+    for k, t in (("metric", str), ("value", float), ("unit", str), ("n_gpus", int), ("steps", int), ("warmup", int),
+                 ("ms_per_step", float), ("higher_is_better", bool), ("scaling", str), ("dtype", str), ("data", str),
+                 ("config", dict), ("e2e", dict), ("gpu_launches", int), ("roofline", dict), ("cpu_baseline", dict),
+                 ("clocks", dict)):
+        assert isinstance(d[k], t), k
+    assert d["vs_baseline"] is None and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_share_of_step"):
+        assert k in r
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    K, T = d["config"]["chains_total"], d["config"]["iters_per_step"]
+    assert abs(d["value"] - K * T / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert set(b.CHAINS_PER_GPU) == set(b.ALGO_FLOP)
+    assert b.METRIC == d["metric"] and b.UNIT == d["unit"]
