@@ -82,3 +82,43 @@ def test_tempering_rejects_what_the_reference_cannot_mean(golden):
         PTSampler(m, AdaptScaleRandomWalk(np.eye(2)), np.ones(2))                    # shared adaptive proposal
     with pytest.raises(ParameterError):
         PTSampler(m, MetropolisRandomWalk(np.eye(2)), np.ones(2), betas=[1.0, 1.5])   # :26-27
+
+
+def test_explicit_ladder_matches_oracle_port():
+    """A 3-temperature ladder with Pswap = 0.3 (the reference's `betas=` branch raises, ptsampler.py:62; the port
+    implements what it intends): device vs oracle on a random tape, every chain and decision."""
+    from oracle import riemann_port as port
+    from riemann_b200 import PTSampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    betas, T, d = np.array([1.0, 0.4, 0.1]), 600, 2
+    rng = np.random.default_rng(12)
+    usel, xi, u = rng.uniform(size=(T, 3)), rng.standard_normal((T, 3, d)), rng.uniform(size=(T, 3))
+    C0 = np.array([[0.5, 0.2], [0.2, 0.3]])
+    om = port.benchmark_gauss(2)
+    opt = port.PTSampler(om, port.MetropolisRandomWalk(C0), np.ones(2), betas=betas, Pswap=0.3,
+                         draws=port.PTTapeDraws(usel, xi, u))
+    with np.errstate(all="ignore"):
+        opt.run(T)
+    pt = PTSampler(benchmarks.benchmark_gauss2d_corr, MetropolisRandomWalk(C0), np.ones(2), betas=betas, Pswap=0.3)
+    pt.run_injected(usel, xi, u)
+    for i in range(3):
+        assert relerr(np.array(pt.samplers[i]._chain_thetas), np.array(opt.samplers[i]._chain_thetas)) < TOL
+        assert relerr(np.array(pt.samplers[i]._chain_logpost), np.array(opt.samplers[i]._chain_logpost)) < TOL
+    swaps = sum(np.any(np.array(opt.samplers[0]._chain_thetas)[1:] != np.array(opt.samplers[0]._chain_thetas)[:-1], axis=1))
+    assert swaps > 50
+
+
+def test_philox_ladder_with_pcn():
+    """Tempering with the other supported proposal: pCN (randomwalk.py:78-100) inside the ladder."""
+    from scipy import stats
+    from riemann_b200 import PTSampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import pCN
+    pt = PTSampler(benchmarks.benchmark_gauss2d_corr, pCN(np.array([[1.0, 0.9], [0.9, 1.0]]), 0.8), np.ones(2),
+                   betas=[1.0, 0.5, 0.25, 0.125], Pswap=0.2, K=512, seed=8)
+    pt.run(2000, trace=False)
+    th = pt._thetas[-1]
+    for i, beta in enumerate(pt.betas):
+        assert stats.kstest(th[:, i, 0] * np.sqrt(beta), "norm").pvalue > 1e-3
+        assert stats.kstest((th[:, i, 0] + th[:, i, 1]) * np.sqrt(beta / 3.8), "norm").pvalue > 1e-3
