@@ -291,7 +291,7 @@ def run_engine(args):
     if world > 1:
         dist.barrier()
     from riemann_b200 import _lib
-    from riemann_b200.distributed import reduce_block, summarize_block
+    from riemann_b200.distributed import reduce_block, summarize_block, summarize_split
 
     wl = args.workload
     Kg = args.chains or CHAINS_PER_GPU[wl]
@@ -326,8 +326,13 @@ def run_engine(args):
     sync_all()
     if clocks:
         clocks.begin()
+    half = args.steps // 2 if args.steps >= 2 and args.steps % 2 == 0 else 0
+    blk_first = None
     for i in range(args.steps):
         flush.fill_(i & 0xff)                      # L2 flush, outside the event pair
+        if half and i == half:                     # second half-window of the split-chain diagnostics
+            blk_first = blk.clone()
+            s.reset_diagnostics()
         ev[i][0].record(stream)
         _lib.check(lib.rmn_sampler_run(s._handle, T, None, None, _lib.stream_ptr()))
         s.total_steps += T
@@ -345,7 +350,17 @@ def run_engine(args):
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms = float(t_all.item())
-    diag = summarize_block(blk.cpu().numpy())
+    diag = None
+    if blk_first is not None:
+        # split-chain diagnostics over the two halves of the timed region (split-R-hat, ESS of 2K half-chains)
+        try:
+            diag = summarize_split(blk_first.cpu().numpy(), blk.cpu().numpy())
+            diag_kind = "split: %d half-chains of %d MH steps" % (diag["chains"], diag["steps"])
+        except ValueError:
+            diag = None
+    if diag is None:
+        diag = summarize_block(blk.cpu().numpy())
+        diag_kind = "whole window"
     K_total = Kg * world
     value = K_total * T * args.steps / (ms * 1e-3)
 
@@ -451,7 +466,7 @@ def run_engine(args):
                    "chains_per_gpu": Kg, "chains_total": K_total, "iters_per_step": T,
                    "burn_in_iters": burn, "parallelism": "chains sharded, dp%d" % world},
         "min_ess_per_sec": (diag["min_ess"] * 1.0) / (ms * 1e-3) if np.isfinite(diag["min_ess"]) else None,
-        "diagnostics": {"accept_rate": diag["accept_rate"], "max_rhat": float(np.nanmax(diag["rhat"])),
+        "diagnostics": {"estimator": diag_kind, "accept_rate": diag["accept_rate"], "max_rhat": float(np.nanmax(diag["rhat"])),
                         "min_ess": diag["min_ess"], "overflows": diag["overflows"],
                         "chains": diag["chains"], "steps_per_chain": diag["steps"]},
         "tau_check": tau_check,

@@ -61,3 +61,26 @@ def summarize_block(b):
             "overflows": int(b[3]), "mean": mean, "var": W + B, "within_var": W,
             "between_var": B, "tau": tau, "ess": ess, "rhat": rhat,
             "min_ess": float(np.nanmin(ess)) if nd and np.any(np.isfinite(ess)) else float("nan")}
+
+
+def summarize_split(block_a, block_b):
+    """
+    Split-chain diagnostics (Gelman et al., BDA3 / Stan's split-R-hat) from the diagnostics blocks of two
+    consecutive windows of equal length: every chain's two halves are treated as separate chains, so a chain
+    whose mean drifts between the halves raises R-hat even when all chains drift alike.  The blocks' chain sums
+    are additive, so the 2K half-chains' between-variance B and within-variance W follow from the two blocks:
+        tau = n_half B / W (in samples), ESS = 2K n_half / tau, R-hat = sqrt(((n-1)/n W + B) / W).
+    Returns the same keys as summarize_block (`chains` = 2K half-chains, `steps` = half-window length).
+    """
+    a, b = np.asarray(block_a, dtype=np.float64), np.asarray(block_b, dtype=np.float64)
+    if a.shape != b.shape or a[0] != b[0] or a[1] != b[1] or a[4] != b[4]:
+        raise ValueError("summarize_split needs two blocks of the same chains and window length")
+    c = a.copy()
+    c[0] = a[0] + b[0]                     # 2K half-chains
+    c[2] = a[2] + b[2]                     # accepts
+    c[3] = a[3] + b[3]                     # overflow events
+    H = 6
+    c[H:] = a[H:] + b[H:]                  # sum m, sum m^2, sum v over the 2K half-chains
+    out = summarize_block(c)
+    out["accept_rate"] = c[2] / max(a[0] * (a[4] + b[4]), 1.0)
+    return out

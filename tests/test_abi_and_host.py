@@ -207,3 +207,30 @@ def test_bench_line_contract():
     spec.loader.exec_module(b)
     assert set(b.CHAINS_PER_GPU) == set(b.ALGO_FLOP)
     assert b.METRIC == d["metric"] and b.UNIT == d["unit"]
+
+
+def test_split_rhat_sees_a_common_drift():
+    """summarize_split: chains that all drift the same way have R-hat ~ 1 over the whole window (every chain mean
+    is the same) but split-R-hat > 1; stationary AR(1) chains give ~1 and the right tau either way."""
+    from riemann_b200.distributed import summarize_block, summarize_split
+    rng = np.random.default_rng(3)
+    K, n, phi = 512, 2000, 0.8
+
+    def block(x):
+        m, v = x.mean(0), x.var(0)
+        return np.array([x.shape[1], x.shape[0], 0, 0, x.shape[0], 0, m.sum(), (m * m).sum(), v.sum()])
+
+    e = rng.standard_normal((n + 200, K)) * np.sqrt(1 - phi * phi)
+    x = np.zeros_like(e)
+    for t in range(1, len(e)):
+        x[t] = phi * x[t - 1] + e[t]
+    x = x[200:]
+    s = summarize_split(block(x[:n // 2]), block(x[n // 2:]))
+    assert s["chains"] == 2 * K and abs(s["rhat"][0] - 1) < 0.01
+    assert abs(s["tau"][0] / ((1 + phi) / (1 - phi)) - 1) < 0.2
+    drift = x + np.linspace(-1.0, 1.0, n)[:, None]                 # every chain drifts alike
+    whole = summarize_block(block(drift))
+    split = summarize_split(block(drift[:n // 2]), block(drift[n // 2:]))
+    assert abs(whole["rhat"][0] - 1) < 0.01 and split["rhat"][0] > 1.1
+    with pytest.raises(ValueError):
+        summarize_split(block(x[:100]), block(x[:200]))
