@@ -107,6 +107,12 @@ int rmn_proposal_rw_create(rmn_proposal_t** out, int d, const double* h_L, int a
 int rmn_proposal_adaptcov_create(rmn_proposal_t** out, int d, const double* h_C0, const double* h_L0,
                                  double t_adapt, int marginalize, int smooth_adapt);
 
+/* AdaptScaleProposal mix-in (adaptive.py:11-35) on an already created proposal: AdaptScaleCovRandomWalk
+ * (randomwalk.py:62-75: scale then covariance adaptation every step) = adaptcov_create + this; AdaptScalepCN
+ * (randomwalk.py:103-119, reproduced as written: rho <- tanh(rho / scale) compounding, rho_c fixed) = pcn_create +
+ * this (small-d path only).  Call before rmn_sampler_create. */
+int rmn_proposal_set_scale_adapt(rmn_proposal_t* p, int adapt, double target);
+
 /* VanillaHMC / AdaptScaleHMC (riemann/proposals/hamiltonian.py:13-103); nsteps = 1
  * is MALA.  The gradient is the model's own grad log posterior.  Mass matrix
  * optional: pass h_chM = chol(M), h_Minv = M^{-1}, h_chMinv = chol(M)^{-1}

@@ -344,6 +344,30 @@ def _n5_adaptcov_fixtures(R):
         np.savez_compressed(os.path.join(GOLDEN_DIR, nm + ".npz"), **out)
 
 
+def _example_proposal_fixtures(R):
+    """The remaining proposals examples/test_randomwalk.py:23-37 lists (BASELINE config 0 runs the last one)."""
+    g2 = R.benchmarks.benchmark_gauss2d_corr
+    # :36-38 -- the proposal the script actually runs
+    p = R.AdaptScaleCovHMC(0.1, 5, g2.grad_log_likelihood, np.eye(2), t_adapt=100, smooth_adapt=True)
+    p.scale = 1.0
+    _vector_fixture(R, "adaptscalecovhmc5_gauss2d", g2, p, np.ones(2), 1500, 801,
+                    extra=dict(eps=np.float64(0.1), nsteps=np.int64(5), M0=np.eye(2)), track_scale=True)
+    M2 = np.array([[2.0, 0.3], [0.3, 1.0]])
+    p = R.AdaptScaleCovHMC(0.15, 3, g2.grad_log_likelihood, M2, t_adapt=100, smooth_adapt=True)
+    _vector_fixture(R, "adaptscalecovhmc3_mass_gauss2d", g2, p, np.ones(2), 1000, 802,
+                    extra=dict(eps=np.float64(0.15), nsteps=np.int64(3), M0=M2), track_scale=True)
+    # :25 AdaptScaleCovRandomWalk (smooth: well conditioned, see the AdaptCov fixtures)
+    C0 = 0.05 * np.eye(2)
+    p = R.AdaptScaleCovRandomWalk(C0.copy(), t_adapt=40, smooth_adapt=True)
+    _vector_fixture(R, "adaptscalecov_rw_gauss2d", g2, p, np.ones(2), 1200, 803,
+                    extra=dict(C0=C0, t_adapt=np.float64(40), smooth_adapt=np.int64(1), marginalize=np.int64(0)),
+                    track_scale=True)
+    # :29 AdaptScalepCN
+    p = R.AdaptScalepCN(np.eye(2), 0.5)
+    _vector_fixture(R, "adaptscalepcn_gauss2d", g2, p, np.ones(2), 1000, 804,
+                    extra=dict(C0=np.eye(2), rho=np.float64(0.5)), track_scale=True)
+
+
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
@@ -390,6 +414,9 @@ def main():
         return
     if "--only-n5-adaptcov" in sys.argv:
         _n5_adaptcov_fixtures(R)
+        return
+    if "--only-example-proposals" in sys.argv:
+        _example_proposal_fixtures(R)
         return
     if "--only-n3-pt" in sys.argv:
         _n3_pt_fixtures(R)
@@ -461,6 +488,7 @@ def main():
     _n1_dense_fixtures(R)
     _n3_pt_fixtures(R)
     _n5_adaptcov_fixtures(R)
+    _example_proposal_fixtures(R)
     # pCN ("next" row N2)
     _vector_fixture(R, "pcn_gauss2d", g2, R.pCN(np.eye(2), 0.5), np.ones(2), 800, 305,
                     extra=dict(C0=np.eye(2), rho=np.float64(0.5)))

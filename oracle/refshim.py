@@ -143,6 +143,8 @@ def load_reference():
         AdaptScaleRandomWalk=randomwalk.AdaptScaleRandomWalk,
         pCN=randomwalk.pCN,
         AdaptCovRandomWalk=randomwalk.AdaptCovRandomWalk,
+        AdaptScaleCovRandomWalk=randomwalk.AdaptScaleCovRandomWalk, AdaptScalepCN=randomwalk.AdaptScalepCN,
+        AdaptScaleCovHMC=hamiltonian.AdaptScaleCovHMC, AdaptCovHMC=hamiltonian.AdaptCovHMC,
         AdaptScaleProposal=adaptive.AdaptScaleProposal,
         VanillaHMC=hamiltonian.VanillaHMC, AdaptScaleHMC=hamiltonian.AdaptScaleHMC,
         leapfrog=hamiltonian.leapfrog,

@@ -426,6 +426,35 @@ class pCN(Proposal):
         return theta_p, -0.5 * (np.dot(u_fwd, u_fwd) - np.dot(u_rev, u_rev))
 
 
+class AdaptScalepCN(AdaptScaleProposal, pCN):
+    """randomwalk.py:103-119, target 0.25.  As written there: rho is re-derived from the PREVIOUS rho at every
+    proposal (`rho = tanh(rho / scale)`, compounding -- SURVEY appendix B) and rho_c keeps its initial value."""
+
+    def __init__(self, C, rho):
+        AdaptScaleProposal.__init__(self, 0.25)
+        pCN.__init__(self, C, rho)
+        self.rho0 = self.rho
+
+    def propose(self, theta):
+        self.rho = np.tanh(self.rho / self.scale)
+        return pCN.propose(self, theta)
+
+
+class AdaptScaleCovRandomWalk(AdaptCovRandomWalk):
+    """randomwalk.py:62-75: scale adaptation (target 0.25) followed by covariance adaptation, every step."""
+
+    def __init__(self, C0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        AdaptCovRandomWalk.__init__(self, C0, t_adapt=t_adapt, marginalize=marginalize, smooth_adapt=smooth_adapt)
+        self._sc = AdaptScaleProposal(0.25)
+        self.scale = 1.0
+
+    def adapt(self, theta):
+        self._sc.scale = self.scale
+        self._sc.adapt(theta)                                   # AdaptScaleRandomWalk.adapt  (:73)
+        self.scale, self.accept_rate = self._sc.scale, self._sc.accept_rate
+        AdaptCovRandomWalk.adapt(self, theta)                   # :74
+
+
 def leapfrog(p0, q0, Nsteps, eps, grad, M=None):
     """Stormer-Verlet.                  riemann/proposals/hamiltonian.py:13-52"""
     vel = (lambda p: np.linalg.solve(M, p)) if M is not None else (lambda p: p)
@@ -471,6 +500,17 @@ class AdaptScaleHMC(AdaptScaleProposal, VanillaHMC):
     def propose(self, theta):
         self.eps = self.scale * self.eps0
         return VanillaHMC.propose(self, theta)
+
+
+class AdaptScaleCovHMC(AdaptScaleHMC):
+    """hamiltonian.py:121-135.  Its `adapt` resolves to AdaptScaleProposal.adapt (MRO: AdaptScaleCovHMC, AdaptScaleHMC,
+    AdaptScaleProposal, AdaptCovHMC, AdaptCovProposal, ...), which does not chain to AdaptCovProposal.adapt: the
+    covariance is never adapted and the class behaves as AdaptScaleHMC with the fixed mass matrix M0 (probed: _S stays 0)."""
+
+    def __init__(self, eps, Nsteps, gradlogpost, M0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        AdaptScaleHMC.__init__(self, eps, Nsteps, gradlogpost, M=np.array(M0, dtype=np.float64))
+        self.C0 = self.C = self.M
+        self.L = self.chM
 
 
 def MALA(eps, gradlogpost, M=None):

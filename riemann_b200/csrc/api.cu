@@ -204,6 +204,17 @@ extern "C" int rmn_proposal_adaptcov_create(rmn_proposal_t** out, int d, const d
     return RMN_OK;
 }
 
+extern "C" int rmn_proposal_set_scale_adapt(rmn_proposal_t* p, int adapt, double target) {
+    RMN_REQUIRE(p, "rmn_proposal_set_scale_adapt: null proposal");
+    RMN_REQUIRE(p->kind == RMN_PROP_RW || p->kind == RMN_PROP_HMC || p->kind == RMN_PROP_PCN,
+                "rmn_proposal_set_scale_adapt: random-walk, pCN and HMC proposals only");
+    RMN_REQUIRE(!adapt || (target > 0 && target < 1), "rmn_proposal_set_scale_adapt: target must be in (0,1)");
+    RMN_REQUIRE(!(adapt && p->kind == RMN_PROP_PCN && p->d > RMN_SMALL_D_MAX),
+                "AdaptScalepCN runs on the small-d path only (d <= %d)", RMN_SMALL_D_MAX);
+    p->adapt = adapt ? 1 : 0; p->target = target;
+    return RMN_OK;
+}
+
 extern "C" int rmn_proposal_hmc_create(rmn_proposal_t** out, int d, double eps, int nsteps,
                                        const double* h_chM, const double* h_Minv,
                                        const double* h_chMinv, int adapt, double target) {

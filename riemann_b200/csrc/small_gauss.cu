@@ -60,6 +60,7 @@ struct SGState {
     double* acSX;           // [D][K]
     double* acSX2;          // [D*D][K]
     double* acL;            // [TRI][K]
+    double* rho;            // [K]   AdaptScalepCN: the chain's current rho (randomwalk.py:118)
 };
 
 template <int D>
@@ -232,6 +233,10 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         for (int i = 0; i < SGParams<D>::TRI; ++i) acl[ACOV ? i : 0] = st.acL[(int64_t)i * K + c];
     }
     long long dacc = st.dacc[c];
+    // AdaptScalepCN (randomwalk.py:103-119): rho is re-derived from the previous rho at every proposal,
+    // rho_c keeps its initial value -- as written in the reference
+    const bool pcn_adapt = (P.kind == RMN_PROP_PCN) && P.adapt;
+    double rho = pcn_adapt ? st.rho[c] : P.rho;
     double s1[D], s2[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) { s1[i] = 0.0; s2[i] = 0.0; }
@@ -283,11 +288,12 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
             for (int i = 0; i < D; ++i) q[i] = th[i] + ad.scale * lx[i];
         } else if (P.kind == RMN_PROP_PCN) {
             double lx[D], df[D], dr[D], uf[D], ur[D];
+            if (pcn_adapt) rho = tanh(rho / ad.scale);                 // randomwalk.py:118
             tri_mv<D>(P.lprop, xi, lx);
 #pragma unroll
-            for (int i = 0; i < D; ++i) q[i] = P.rho * th[i] + P.rho_c * lx[i];
+            for (int i = 0; i < D; ++i) q[i] = rho * th[i] + P.rho_c * lx[i];
 #pragma unroll
-            for (int i = 0; i < D; ++i) { df[i] = q[i] - P.rho * th[i]; dr[i] = th[i] - P.rho * q[i]; }
+            for (int i = 0; i < D; ++i) { df[i] = q[i] - rho * th[i]; dr[i] = th[i] - rho * q[i]; }
             tri_mv<D>(P.lpinv, df, uf);
             tri_mv<D>(P.lpinv, dr, ur);
             double a = 0.0, b = 0.0;
@@ -414,6 +420,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         st.S2[(int64_t)i * K + c] += s2[i];
     }
     st.lp[c] = lp;
+    if (pcn_adapt) st.rho[c] = rho;
     if (ACOV) {
         st.acS[c] = acn;
 #pragma unroll
@@ -504,7 +511,7 @@ struct SmallGaussSampler : SamplerImpl {
 
     size_t workspace_bytes() const override {
         const size_t K = (size_t)s->K;
-        size_t n = align256(D * K * 8) * 3 + align256(K * 8) * 6 + 256;
+        size_t n = align256(D * K * 8) * 3 + align256(K * 8) * 7 + 256;
         if (s->prop->acov) n += align256(K * 8) + align256(D * K * 8) + align256(D * D * K * 8) + align256(SGParams<D>::TRI * K * 8);
         return n;
     }
@@ -520,6 +527,7 @@ struct SmallGaussSampler : SamplerImpl {
         st.nsamp = (long long*)p; p += align256(K * 8);
         st.nacc = (long long*)p; p += align256(K * 8);
         st.dacc = (long long*)p; p += align256(K * 8);
+        st.rho = (double*)p; p += align256(K * 8);
         if (s->prop->acov) {
             st.acS = (double*)p; p += align256(K * 8);
             st.acSX = (double*)p; p += align256(D * K * 8);
@@ -562,6 +570,7 @@ struct SmallGaussSampler : SamplerImpl {
         RMN_CUDA(cudaMalloc(&d_params, sizeof(h)));
         RMN_CUDA(cudaMemcpy(d_params, &h, sizeof(h), cudaMemcpyHostToDevice));
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        if (int rc3 = rmn_fill_f64(st.rho, s->K, pr->rho, 0)) return rc3;
         if (pr->acov) {                                   // every chain starts from chol(C0) (adaptive.py:61)
             for (int q = 0; q < SGParams<D>::TRI; ++q) {
                 int rc2 = rmn_fill_f64(st.acL + (size_t)q * K, s->K, h.lprop[q], 0);

@@ -71,6 +71,20 @@ class AdaptScaleHMC(AdaptScaleProposal, VanillaHMC):
         self.eps0 = self.eps
 
 
+class AdaptScaleCovHMC(AdaptScaleHMC):
+    """hamiltonian.py:121-135 -- what examples/test_randomwalk.py:36-38 (BASELINE config 0) runs.  In the reference its
+    `adapt` resolves to AdaptScaleProposal.adapt (MRO: AdaptScaleCovHMC, AdaptScaleHMC, AdaptScaleProposal, AdaptCovHMC,
+    AdaptCovProposal, ...), which never chains to AdaptCovProposal.adapt: the mass matrix stays M0 for the whole run
+    (probed on the reference: `_S` stays 0).  So this is AdaptScaleHMC with the fixed mass matrix M0; `t_adapt`,
+    `marginalize` and `smooth_adapt` are accepted and, like there, have no effect."""
+
+    def __init__(self, eps, Nsteps, gradlogpost, M0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        AdaptScaleHMC.__init__(self, eps, Nsteps, gradlogpost, M=np.array(M0, dtype=np.float64))
+        self.C0 = self.C = np.array(M0, dtype=np.float64)
+        self.L = np.linalg.cholesky(self.C)
+        self.t_adapt, self.marginalize, self.smooth_adapt = t_adapt, marginalize, smooth_adapt
+
+
 def MALA(eps, gradlogpost, M=None):
     """Metropolis-adjusted Langevin == VanillaHMC(eps, 1, grad[, M])."""
     return VanillaHMC(eps, 1, gradlogpost, M=M)

@@ -74,6 +74,20 @@ class AdaptCovRandomWalk(MetropolisRandomWalk):
 AdaptiveMetropolisRandomWalk = HaarioRandomWalk = AdaptCovRandomWalk
 
 
+class AdaptScaleCovRandomWalk(AdaptScaleProposal, AdaptCovRandomWalk):
+    """randomwalk.py:62-75: adapts both the scale (target 0.25) and the covariance, in that order, every step."""
+
+    def __init__(self, C0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        AdaptScaleProposal.__init__(self, 0.25)
+        AdaptCovRandomWalk.__init__(self, C0, t_adapt=t_adapt, marginalize=marginalize, smooth_adapt=smooth_adapt)
+        self._adaptive = True
+
+    def _create_handle(self, d):
+        h = AdaptCovRandomWalk._create_handle(self, d)
+        _lib.check(_lib.load().rmn_proposal_set_scale_adapt(h, 1, float(self.target_accept_rate)))
+        return h
+
+
 class pCN(DeviceProposal):
     """Preconditioned Crank-Nicolson (randomwalk.py:78-100)."""
 
@@ -93,4 +107,21 @@ class pCN(DeviceProposal):
         Linv = np.ascontiguousarray(np.linalg.solve(self.L, np.eye(d)))
         _lib.check(_lib.load().rmn_proposal_pcn_create(C.byref(h), d, _lib.ptr(L), _lib.ptr(Linv),
                                                        float(self.rho)))
+        return h
+
+
+class AdaptScalepCN(AdaptScaleProposal, pCN):
+    """randomwalk.py:103-119, target 0.25 -- reproduced as written: every proposal re-derives rho from the previous
+    rho (`rho = tanh(rho / scale)`, compounding) while rho_c keeps its initial value.  Per chain on
+    the device; `.rho` is not refreshed on the host.  Small-d path (d <= 8)."""
+
+    def __init__(self, C_, rho):
+        AdaptScaleProposal.__init__(self, 0.25)
+        pCN.__init__(self, C_, rho)
+        self.rho0 = self.rho
+        self._adaptive = True
+
+    def _create_handle(self, d):
+        h = pCN._create_handle(self, d)
+        _lib.check(_lib.load().rmn_proposal_set_scale_adapt(h, 1, float(self.target_accept_rate)))
         return h

@@ -265,3 +265,50 @@ def test_adapt_cov_limits():
         Sampler(benchmarks.benchmark_gauss2d_corr, AdaptCovRandomWalk(np.eye(2), t_adapt=100), np.ones(2))
     with pytest.raises(ParameterError):      # dense path
         Sampler(benchmarks.benchmark_gauss100d_corr, AdaptCovRandomWalk(np.eye(100)), np.zeros(100))
+
+
+# ---------------------------------------------------------------------------------------
+# the remaining proposals of examples/test_randomwalk.py:23-37 (BASELINE config 0 runs AdaptScaleCovHMC)
+# ---------------------------------------------------------------------------------------
+def _example_proposal(name, g, m):
+    from riemann_b200.proposals import hamiltonian as hm, randomwalk as rw
+    if name.startswith("adaptscalecovhmc"):
+        return hm.AdaptScaleCovHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood, g["M0"], t_adapt=100,
+                                   smooth_adapt=True)
+    if name.startswith("adaptscalecov_rw"):
+        return rw.AdaptScaleCovRandomWalk(g["C0"], t_adapt=float(g["t_adapt"]), smooth_adapt=True)
+    return rw.AdaptScalepCN(g["C0"], float(g["rho"]))
+
+
+@pytest.mark.parametrize("name", ["adaptscalecovhmc5_gauss2d", "adaptscalecovhmc3_mass_gauss2d",
+                                  "adaptscalecov_rw_gauss2d", "adaptscalepcn_gauss2d"])
+def test_example_script_proposals_match_reference(golden, name):
+    from riemann_b200 import Sampler
+    g = golden(name)
+    m = device_gauss(g, 2)
+    p = _example_proposal(name, g, m)
+    s = Sampler(m, p, g["thetas"][0])
+    ex = s.run_injected(xi=g["xi"], u=g["u"])
+    assert relerr(np.array(s._chain_thetas), g["thetas"]) < 1e-8
+    assert relerr(s._chain_logpost, g["logpost"]) < 1e-8
+    assert np.array_equal(ex["accepted"][:, 0], np.any(g["thetas"][1:] != g["thetas"][:-1], axis=1))
+    assert abs(p.scale - g["scales"][-1]) < 1e-9 * g["scales"][-1]
+    assert abs(p.accept_rate - float(g["accept_rate"])) < 1e-12
+
+
+def test_example_script_runs_as_written():
+    """examples/test_randomwalk.py:36-41 with only the imports changed."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models.benchmarks import benchmark_gauss2d_corr
+    from riemann_b200.proposals.hamiltonian import AdaptScaleCovHMC
+    from riemann_b200 import diagnostics
+    proposal = AdaptScaleCovHMC(0.1, 5, benchmark_gauss2d_corr.grad_log_likelihood,
+                                np.eye(2), t_adapt=100, smooth_adapt=True)
+    proposal.scale = 1.0
+    sampler = Sampler(benchmark_gauss2d_corr, proposal, np.ones(2))
+    sampler.run(10000, 1000, 1)
+    chain = np.array(sampler._chain_thetas)
+    assert chain.shape == (9001, 2)
+    tau = diagnostics.integrated_time(chain)                    # emcee.autocorr.integrated_time(chain), :42
+    assert 0.6 < np.mean(np.any(chain[:-1] != chain[1:], axis=1)) < 0.9      # AdaptScaleHMC targets 0.75
+    assert np.all(tau < 60) and abs(chain[:, 0].std() - 1.0) < 0.25

@@ -197,3 +197,24 @@ def test_adapt_cov_random_walk(golden, name, d):
                                    smooth_adapt=bool(g["smooth_adapt"]))
     _replay(g, _gauss(g, d), prop, g["thetas"][0])
     assert np.max(np.abs(prop.L - g["L_final"])) < 1e-12 * np.max(np.abs(g["L_final"]))
+
+
+def test_example_script_proposals(golden):
+    """The remaining proposals of examples/test_randomwalk.py:23-37 (BASELINE config 0 runs AdaptScaleCovHMC)."""
+    g = golden("adaptscalecovhmc5_gauss2d")
+    m = _gauss(g, 2)
+    p = port.AdaptScaleCovHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood, g["M0"], t_adapt=100,
+                              smooth_adapt=True)
+    _replay(g, m, p, g["thetas"][0])
+    assert abs(p.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
+    g = golden("adaptscalecovhmc3_mass_gauss2d")
+    p = port.AdaptScaleCovHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood, g["M0"])
+    _replay(g, m, p, g["thetas"][0])
+    g = golden("adaptscalecov_rw_gauss2d")
+    p = port.AdaptScaleCovRandomWalk(g["C0"], t_adapt=float(g["t_adapt"]), smooth_adapt=True)
+    _replay(g, m, p, g["thetas"][0])
+    assert abs(p.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
+    g = golden("adaptscalepcn_gauss2d")
+    p = port.AdaptScalepCN(g["C0"], float(g["rho"]))
+    _replay(g, m, p, g["thetas"][0])
+    assert abs(p.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
