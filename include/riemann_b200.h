@@ -107,6 +107,11 @@ int rmn_proposal_rw_create(rmn_proposal_t** out, int d, const double* h_L, int a
 int rmn_proposal_adaptcov_create(rmn_proposal_t** out, int d, const double* h_C0, const double* h_L0,
                                  double t_adapt, int marginalize, int smooth_adapt);
 
+/* AdaptCovHMC (hamiltonian.py:106-119): the mass matrix of an HMC proposal created WITHOUT one becomes the chain's adapted
+ * covariance (M = C, chM = L of adaptive.py:101-102), starting from M0 / chol(M0).  Small-d path only. */
+int rmn_proposal_hmc_set_cov_adapt(rmn_proposal_t* p, const double* h_M0, const double* h_L0, double t_adapt,
+                                   int marginalize, int smooth_adapt);
+
 /* AdaptScaleProposal mix-in (adaptive.py:11-35) on an already created proposal: AdaptScaleCovRandomWalk
  * (randomwalk.py:62-75: scale then covariance adaptation every step) = adaptcov_create + this; AdaptScalepCN
  * (randomwalk.py:103-119, reproduced as written: rho <- tanh(rho / scale) compounding, rho_c fixed) = pcn_create +

@@ -362,6 +362,11 @@ def _example_proposal_fixtures(R):
     _vector_fixture(R, "adaptscalecov_rw_gauss2d", g2, p, np.ones(2), 1200, 803,
                     extra=dict(C0=C0, t_adapt=np.float64(40), smooth_adapt=np.int64(1), marginalize=np.int64(0)),
                     track_scale=True)
+    # :34-35 AdaptCovHMC (smooth adaptation as in the script; the mass matrix adapts inside the leapfrog)
+    p = R.AdaptCovHMC(0.1, 5, g2.grad_log_likelihood, np.eye(2), t_adapt=100, smooth_adapt=True)
+    _vector_fixture(R, "adaptcovhmc5_gauss2d", g2, p, np.ones(2), 1200, 805,
+                    extra=dict(eps=np.float64(0.1), nsteps=np.int64(5), M0=np.eye(2), t_adapt=np.float64(100),
+                               smooth_adapt=np.int64(1), marginalize=np.int64(0)))
     # :29 AdaptScalepCN
     p = R.AdaptScalepCN(np.eye(2), 0.5)
     _vector_fixture(R, "adaptscalepcn_gauss2d", g2, p, np.ones(2), 1000, 804,

@@ -369,19 +369,19 @@ class AdaptScaleRandomWalk(AdaptScaleProposal, MetropolisRandomWalk):
         MetropolisRandomWalk.__init__(self, C)
 
 
-class AdaptCovRandomWalk(MetropolisRandomWalk):
-    """randomwalk.py:40-56 + adaptive.py:38-103 (Haario et al. 2001): the proposal covariance follows the sample
-    covariance of the chain history, recomputed when the number of states n is a perfect square > 2.
+class AdaptCovProposal(Proposal):
+    """adaptive.py:38-103 (Haario et al. 2001): C follows the sample covariance of the chain history, recomputed when
+    `np.sqrt(n)**2 == n and n > 2` (the perfect squares and, through rounding, about half of the other n).
     The strict (non-smooth) mode with n < t_adapt is not restated: there the reference divides its current C in
     place (adaptive.py:89-91 stores to a dead attribute, :101 then rescales the old C, which on the first occasion
     is the caller's C0 array itself); t_adapt <= 4 never gets there."""
 
     def __init__(self, C0, t_adapt=1, marginalize=False, smooth_adapt=False):
-        MetropolisRandomWalk.__init__(self, C0)
         if not smooth_adapt and t_adapt > 4:
             raise ParameterError("strict Haario mode with t_adapt > 4 is an in-place aliasing bug in the reference")
         self.C0 = np.array(np.atleast_2d(C0), dtype=np.float64)
         self.C = self.C0
+        self.L = np.linalg.cholesky(self.C0)
         self.t_adapt, self.marginalize, self.smooth_adapt = t_adapt, marginalize, smooth_adapt
         self._S, self._SX, self._SX2 = 0.0, 0.0, 0.0
 
@@ -405,6 +405,14 @@ class AdaptCovRandomWalk(MetropolisRandomWalk):
             d = C.shape[0]
             self.C = C / d ** 0.4                                                 # :101
             self.L = np.linalg.cholesky(self.C) / d ** 0.2                        # :102
+
+
+class AdaptCovRandomWalk(AdaptCovProposal, MetropolisRandomWalk):
+    """randomwalk.py:40-56."""
+
+    def __init__(self, C0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        MetropolisRandomWalk.__init__(self, C0)
+        AdaptCovProposal.__init__(self, C0, t_adapt=t_adapt, marginalize=marginalize, smooth_adapt=smooth_adapt)
 
 
 class pCN(Proposal):
@@ -511,6 +519,19 @@ class AdaptScaleCovHMC(AdaptScaleHMC):
         AdaptScaleHMC.__init__(self, eps, Nsteps, gradlogpost, M=np.array(M0, dtype=np.float64))
         self.C0 = self.C = self.M
         self.L = self.chM
+
+
+class AdaptCovHMC(AdaptCovProposal, VanillaHMC):
+    """hamiltonian.py:106-119: the leapfrog's mass matrix is the adapted covariance, M = C and chM = L -- where
+    L = chol(C) / d**0.2 (adaptive.py:102), so after the first adaptation chM chM^T = M / d**0.4, as in the reference."""
+
+    def __init__(self, eps, Nsteps, gradlogpost, M0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        VanillaHMC.__init__(self, eps, Nsteps, gradlogpost, M=np.array(M0, dtype=np.float64))
+        AdaptCovProposal.__init__(self, M0, t_adapt=t_adapt, marginalize=marginalize, smooth_adapt=smooth_adapt)
+
+    def propose(self, theta):
+        self.M, self.chM = self.C, self.L
+        return VanillaHMC.propose(self, theta)
 
 
 def MALA(eps, gradlogpost, M=None):

@@ -83,6 +83,7 @@ SIGNATURES = {
     "rmn_sampler_get_adaptcov": (_I, [_P, _P, _P]),
     "rmn_proposal_adaptcov_create": (_I, [_PP, _I, _P, _P, _D, _I, _I]),
     "rmn_proposal_set_scale_adapt": (_I, [_P, _I, _D]),
+    "rmn_proposal_hmc_set_cov_adapt": (_I, [_P, _P, _P, _D, _I, _I]),
     "rmn_sampler_enable_kernel_timing": (_I, [_P, _I]),
     "rmn_sampler_kernel_timing": (_I, [_P, _P, _P, _P, _P]),
     "rmn_philox_raw": (_I, [_L, _P, _P, _P, _P]),

@@ -204,6 +204,23 @@ extern "C" int rmn_proposal_adaptcov_create(rmn_proposal_t** out, int d, const d
     return RMN_OK;
 }
 
+extern "C" int rmn_proposal_hmc_set_cov_adapt(rmn_proposal_t* p, const double* h_M0, const double* h_L0, double t_adapt,
+                                              int marginalize, int smooth_adapt) {
+    RMN_REQUIRE(p && h_M0 && h_L0, "rmn_proposal_hmc_set_cov_adapt: bad argument");
+    RMN_REQUIRE(p->kind == RMN_PROP_HMC && !p->has_mass, "rmn_proposal_hmc_set_cov_adapt: an HMC proposal created without a mass matrix");
+    RMN_REQUIRE(p->d <= RMN_SMALL_D_MAX, "AdaptCovHMC runs on the small-d path only (d <= %d, got %d)", RMN_SMALL_D_MAX, p->d);
+    if (int rc = lower_ok(h_L0, p->d, "rmn_proposal_hmc_set_cov_adapt")) return rc;
+    RMN_REQUIRE(t_adapt >= 0 && isfinite(t_adapt), "rmn_proposal_hmc_set_cov_adapt: t_adapt must be >= 0");
+    RMN_REQUIRE(smooth_adapt || t_adapt <= 4.0,
+                "AdaptCovHMC: strict Haario mode with t_adapt > 4 is not reproduced (adaptive.py:89-101); use smooth_adapt "
+                "or t_adapt <= 4");
+    const size_t n = (size_t)p->d * p->d;
+    p->h_L.assign(h_L0, h_L0 + n);
+    p->h_C0.assign(h_M0, h_M0 + n);
+    p->acov = 1; p->ac_marginalize = marginalize ? 1 : 0; p->ac_smooth = smooth_adapt ? 1 : 0; p->ac_t_adapt = t_adapt;
+    return RMN_OK;
+}
+
 extern "C" int rmn_proposal_set_scale_adapt(rmn_proposal_t* p, int adapt, double target) {
     RMN_REQUIRE(p, "rmn_proposal_set_scale_adapt: null proposal");
     RMN_REQUIRE(p->kind == RMN_PROP_RW || p->kind == RMN_PROP_HMC || p->kind == RMN_PROP_PCN,
@@ -295,6 +312,11 @@ static SamplerImpl* make_impl(rmn_sampler* s, int* rc) {
     if (p->d != m->d) {
         rmn_set_error("theta and proposal have incompatible shapes (model d=%d, proposal d=%d)", m->d, p->d);
         *rc = RMN_ERR_PARAM;
+        return nullptr;
+    }
+    if (p->acov && !(m->kind == RMN_MODEL_GAUSS && m->d <= RMN_SMALL_D_MAX && s->precision == RMN_PREC_F64)) {
+        rmn_set_error("covariance-adapting proposals (AdaptCov*) run on the small-d Gaussian path only (d <= %d, fp64)",
+                      RMN_SMALL_D_MAX);
         return nullptr;
     }
     if (s->precision == RMN_PREC_TF32X3)

@@ -124,6 +124,29 @@ __device__ __forceinline__ void gauss_grad(const SGParams<D>& P, const double* t
     for (int i = 0; i < D; ++i) g[i] = -g[i];
 }
 
+// y = L^-1 x (forward substitution), L packed lower
+template <int D>
+__device__ __forceinline__ void tri_solve(const double* L, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = x[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) s -= L[i * (i + 1) / 2 + j] * y[j];
+        y[i] = s / L[i * (i + 1) / 2 + i];
+    }
+}
+// y = L^-T x (backward substitution), L packed lower
+template <int D>
+__device__ __forceinline__ void tri_solve_t(const double* L, const double* x, double* y) {
+#pragma unroll
+    for (int i = D - 1; i >= 0; --i) {
+        double s = x[i];
+#pragma unroll
+        for (int j = i + 1; j < D; ++j) s -= L[j * (j + 1) / 2 + i] * y[j];
+        y[i] = s / L[i * (i + 1) / 2 + i];
+    }
+}
+
 template <int D>
 __device__ __forceinline__ void velocity(const SGParams<D>& P, const double* p, double* v) {
     if (P.has_mass) {
@@ -303,7 +326,22 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         } else {   // HMC / MALA
             const double eps = P.adapt ? ad.scale * P.eps0 : P.eps0;
             double p0[D], p[D], g[D], v[D];
-            if (P.has_mass) tri_mv<D>(P.chM, xi, p0);
+            // AdaptCovHMC (hamiltonian.py:106-119): M = C, chM = L of THIS chain.  L = chol(C) / d**0.2 after the first
+            // adaptation (n >= 4) and chol(C0) before it, so C^-1 p = L^-T L^-1 p / cfac with cfac = d**0.4 resp. 1.
+            const double cfac = (ACOV && acn >= 4.0) ? P.dpow04 : 1.0;
+            auto vel = [&](const double* pp, double* vv) {
+                if (ACOV) {
+                    double y1[D];
+                    tri_solve<D>(acl, pp, y1);
+                    tri_solve_t<D>(acl, y1, vv);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) vv[i] = vv[i] / cfac;
+                } else {
+                    velocity<D>(P, pp, vv);
+                }
+            };
+            if (ACOV) tri_mv<D>(acl, xi, p0);
+            else if (P.has_mass) tri_mv<D>(P.chM, xi, p0);
             else {
 #pragma unroll
                 for (int i = 0; i < D; ++i) p0[i] = xi[i];
@@ -311,14 +349,14 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
             gauss_grad<D>(P, th, g);
 #pragma unroll
             for (int i = 0; i < D; ++i) p[i] = p0[i] + 0.5 * eps * g[i];
-            velocity<D>(P, p, v);
+            vel(p, v);
 #pragma unroll
             for (int i = 0; i < D; ++i) q[i] = th[i] + eps * v[i];
             for (int s = 1; s < P.nsteps; ++s) {
                 gauss_grad<D>(P, q, g);
 #pragma unroll
                 for (int i = 0; i < D; ++i) p[i] = p[i] + eps * g[i];
-                velocity<D>(P, p, v);
+                vel(p, v);
 #pragma unroll
                 for (int i = 0; i < D; ++i) q[i] = q[i] + eps * v[i];
             }
@@ -326,7 +364,13 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
 #pragma unroll
             for (int i = 0; i < D; ++i) p[i] = p[i] + 0.5 * eps * g[i];
             double k0 = 0.0, k1 = 0.0;
-            if (P.has_mass) {
+            if (ACOV) {
+                double w0[D], w1[D];
+                tri_solve<D>(acl, p0, w0);                      // solve(chM, p), hamiltonian.py:86-87
+                tri_solve<D>(acl, p, w1);
+#pragma unroll
+                for (int i = 0; i < D; ++i) { k0 += w0[i] * w0[i]; k1 += w1[i] * w1[i]; }
+            } else if (P.has_mass) {
                 double w0[D], w1[D];
                 tri_mv<D>(P.chMinv, p0, w0);
                 tri_mv<D>(P.chMinv, p, w1);

@@ -71,6 +71,36 @@ class AdaptScaleHMC(AdaptScaleProposal, VanillaHMC):
         self.eps0 = self.eps
 
 
+class AdaptCovHMC(VanillaHMC):
+    """hamiltonian.py:106-119: HMC whose mass matrix is the chain's adapted covariance (adaptive.py:38-103), M = C and
+    chM = L -- L = chol(C) / d**0.2 there, so chM chM^T = M / d**0.4 after the first adaptation; reproduced as written.
+    Per chain on the device; `.C` / `.L` / `.M` / `.chM` refreshed after every batch.  Small-d path (d <= 8)."""
+
+    _adapt_cov = True
+
+    def __init__(self, eps, Nsteps, gradlogpost, M0, t_adapt=1, marginalize=False, smooth_adapt=False):
+        VanillaHMC.__init__(self, eps, Nsteps, gradlogpost, M=None)
+        self.C0 = np.array(np.atleast_2d(M0), dtype=np.float64)
+        self.C = self.M = self.C0
+        self.L = self.chM = np.linalg.cholesky(self.C0)
+        self.t_adapt, self.marginalize, self.smooth_adapt = t_adapt, marginalize, smooth_adapt
+
+    def _create_handle(self, d):
+        if self.C0.shape != (d, d):
+            raise ParameterError("theta and M0 have incompatible shapes")
+        M_save, chM_save = self.M, self.chM
+        self.M = self.chM = None                              # created WITHOUT a mass matrix; the adapted one takes its place
+        try:
+            h = VanillaHMC._create_handle(self, d)
+        finally:
+            self.M, self.chM = M_save, chM_save
+        C0 = np.ascontiguousarray(self.C0)
+        L0 = np.ascontiguousarray(np.linalg.cholesky(self.C0))
+        _lib.check(_lib.load().rmn_proposal_hmc_set_cov_adapt(h, _lib.ptr(C0), _lib.ptr(L0), float(self.t_adapt),
+                                                              int(bool(self.marginalize)), int(bool(self.smooth_adapt))))
+        return h
+
+
 class AdaptScaleCovHMC(AdaptScaleHMC):
     """hamiltonian.py:121-135 -- what examples/test_randomwalk.py:36-38 (BASELINE config 0) runs.  In the reference its
     `adapt` resolves to AdaptScaleProposal.adapt (MRO: AdaptScaleCovHMC, AdaptScaleHMC, AdaptScaleProposal, AdaptCovHMC,

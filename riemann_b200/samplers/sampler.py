@@ -388,9 +388,11 @@ class Sampler(object):
             L = torch.empty((self.K, self.d, self.d), dtype=torch.float64, device="cuda")
             _lib.check(_lib.load().rmn_sampler_get_adaptcov(self._handle, _lib.ptr(L), _lib.stream_ptr()))
             L = L.cpu().numpy()
-            dd = float(self.d) ** 0.2
-            Cm = np.einsum("kij,klj->kil", L * dd, L * dd)          # L = chol(C) / d**0.2
+            dd = float(self.d) ** 0.2 if self.total_steps >= 4 else 1.0   # before the first adaptation L = chol(C0)
+            Cm = np.einsum("kij,klj->kil", L * dd, L * dd)          # L = chol(C) / d**0.2  (adaptive.py:101-102)
             p.L, p.C = (L[0], Cm[0]) if self.K == 1 else (L, Cm)
+            if hasattr(p, "chM"):                                   # AdaptCovHMC: M = C, chM = L (hamiltonian.py:117)
+                p.M, p.chM = p.C, p.L
         if not getattr(p, "_adaptive", False):
             return
         torch, K = self._torch, self.K

@@ -218,3 +218,7 @@ def test_example_script_proposals(golden):
     p = port.AdaptScalepCN(g["C0"], float(g["rho"]))
     _replay(g, m, p, g["thetas"][0])
     assert abs(p.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
+    g = golden("adaptcovhmc5_gauss2d")
+    p = port.AdaptCovHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood, g["M0"], t_adapt=float(g["t_adapt"]),
+                         smooth_adapt=True)
+    _replay(g, m, p, g["thetas"][0])
