@@ -219,7 +219,9 @@ __device__ __forceinline__ void haario_adapt(const SGParams<D>& P, const double*
     for (int q = 0; q < SGParams<D>::TRI; ++q) L[q] = L[q] / P.dpow02;
 }
 
-template <int D, bool INJ, bool ACOV, bool PT>
+// RWONLY: instantiation for the plain random walk (config 1's throughput case): pCN / HMC / adaptation code is
+// compiled out, which keeps it at the register count the one-proposal kernel had.
+template <int D, bool INJ, bool ACOV, bool PT, bool RWONLY = false>
 __global__ void __launch_bounds__(128, (D <= 2 && !ACOV) ? 4 : 1)   // d <= 2: 128 registers = 16 warps/SM (config 1)
 small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t K, int64_t T,
                    int64_t step0, uint64_t seed, int64_t chain_offset, const double* __restrict__ inj_xi,
@@ -236,6 +238,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
     bool active;
     const int64_t c = chain_of_thread<D>(P, blockIdx.x * (int64_t)blockDim.x + threadIdx.x, K, ti, active);
     constexpr bool pt = PT;                       // compile-time: the plain kernel carries no ladder logic
+    const int kind = RWONLY ? (int)RMN_PROP_RW : P.kind;
     if (!pt && !active) return;                 // tempered warps keep their idle threads for the shuffles
     const double beta = pt ? P.betas[ti] : 1.0;
 
@@ -258,7 +261,7 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
     long long dacc = st.dacc[c];
     // AdaptScalepCN (randomwalk.py:103-119): rho is re-derived from the previous rho at every proposal,
     // rho_c keeps its initial value -- as written in the reference
-    const bool pcn_adapt = (P.kind == RMN_PROP_PCN) && P.adapt;
+    const bool pcn_adapt = !RWONLY && (P.kind == RMN_PROP_PCN) && P.adapt;
     double rho = pcn_adapt ? st.rho[c] : P.rho;
     double s1[D], s2[D];
 #pragma unroll
@@ -303,13 +306,13 @@ small_gauss_kernel(const SGParams<D>* __restrict__ gparams, SGState st, int64_t 
         const bool regular = active && !is_init && !is_part;
 
         double q[D], lqr = 0.0;
-        if (P.kind == RMN_PROP_RW) {
+        if (kind == RMN_PROP_RW) {
             double lx[D];
             if (ACOV) tri_mv<D>(acl, xi, lx);            // this chain's adapted factor
             else tri_mv<D>(P.lprop, xi, lx);
 #pragma unroll
             for (int i = 0; i < D; ++i) q[i] = th[i] + ad.scale * lx[i];
-        } else if (P.kind == RMN_PROP_PCN) {
+        } else if (kind == RMN_PROP_PCN) {
             double lx[D], df[D], dr[D], uf[D], ur[D];
             if (pcn_adapt) rho = tanh(rho / ad.scale);                 // randomwalk.py:118
             tri_mv<D>(P.lprop, xi, lx);
@@ -682,6 +685,9 @@ struct SmallGaussSampler : SamplerImpl {
         } else {
             if (ptm) RMN_SG_LAUNCH(false, false, true, nullptr, nullptr, nullptr);
             else if (ac) RMN_SG_LAUNCH(false, true, false, nullptr, nullptr, nullptr);
+            else if (hparams.kind == RMN_PROP_RW)
+                small_gauss_kernel<D, false, false, false, true><<<run_grid(), 128, 0, stream>>>(
+                    d_params, st, s->K, T, step0, s->seed, s->chain_offset, nullptr, nullptr, nullptr, t0);
             else RMN_SG_LAUNCH(false, false, false, nullptr, nullptr, nullptr);
         }
 #undef RMN_SG_LAUNCH
