@@ -376,8 +376,13 @@ def _example_proposal_fixtures(R):
 def _portmodel_through_reference(R, name, kind, seed):
     """Logistic / mMALA are not in the reference: run the PORT's model (and, for
     mMALA, proposal) through the reference's own Sampler.sample and VanillaHMC."""
+    nsteps = 1
     if kind == "mala":
         N, d, T, eps = 500, 8, 400, 0.35
+    elif kind == "hmc3":                        # "next" row N1 on the logistic family: the reference's leapfrog, 3 steps
+        N, d, T, eps, nsteps = 500, 8, 300, 0.2, 3
+    elif kind == "adapthmc4":                   # AdaptScaleHMC, 4 steps, d = 20 (the dense-in-d device path)
+        N, d, T, eps, nsteps = 600, 20, 300, 0.1, 4
     else:
         N, d, T, eps = 400, 6, 300, 0.9
     X, y, theta_star, pv = port.make_logistic_problem(N, d, seed=port.SEED_BASE + 40 + d)
@@ -391,8 +396,12 @@ def _portmodel_through_reference(R, name, kind, seed):
             return pmodel.log_likelihood(theta)
 
     model = RefLogistic()
-    if kind == "mala":
-        prop = R.VanillaHMC(eps, 1, pmodel.grad_log_posterior)     # reference proposal
+    track = False
+    if kind in ("mala", "hmc3"):
+        prop = R.VanillaHMC(eps, nsteps, pmodel.grad_log_posterior)     # reference proposal
+    elif kind == "adapthmc4":
+        prop = R.AdaptScaleHMC(eps, nsteps, pmodel.grad_log_posterior)
+        track = True
     else:
         class RefMMALA(R.Proposal):
             inner = port.SimplifiedMMALA(eps, pmodel)
@@ -402,7 +411,8 @@ def _portmodel_through_reference(R, name, kind, seed):
         prop = RefMMALA()
     theta0 = theta_star + 0.05 * np.ones(d)
     _vector_fixture(R, name, model, prop, theta0, T, seed,
-                    extra=dict(X=X, y=y, prior_var=np.float64(pv), eps=np.float64(eps)))
+                    extra=dict(X=X, y=y, prior_var=np.float64(pv), eps=np.float64(eps), nsteps=np.int64(nsteps)),
+                    track_scale=track)
 
 
 def main():
@@ -422,6 +432,10 @@ def main():
         return
     if "--only-example-proposals" in sys.argv:
         _example_proposal_fixtures(R)
+        return
+    if "--only-n1-logistic" in sys.argv:
+        _portmodel_through_reference(R, "hmc3_logistic", "hmc3", 503)
+        _portmodel_through_reference(R, "adapthmc4_logistic", "adapthmc4", 504)
         return
     if "--only-n3-pt" in sys.argv:
         _n3_pt_fixtures(R)
@@ -506,6 +520,8 @@ def main():
     # --- models/proposals the reference lacks, driven through the reference Sampler
     _portmodel_through_reference(R, "mala_logistic", "mala", 501)
     _portmodel_through_reference(R, "mmala_logistic", "mmala", 502)
+    _portmodel_through_reference(R, "hmc3_logistic", "hmc3", 503)
+    _portmodel_through_reference(R, "adapthmc4_logistic", "adapthmc4", 504)
 
 
 if __name__ == "__main__":

@@ -574,6 +574,26 @@ lg_tc_reduce_kernel(LogisticState st, LgTC tc, int64_t c0, int kb, int nsplit_us
     }
 }
 
+// Interior leapfrog step (hamiltonian.py:33-37, Nsteps > 1) for the chains' proposal slots: with the gradient of
+// the log-posterior at the trajectory point just swept, g = sum_splits gpart - theta / pv,
+//   p <- p + eps g,   theta <- theta + eps p      (in place; p lives in Xi)
+__global__ void __launch_bounds__(256)
+lg_leapfrog_mid_kernel(LogisticState st) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= st.K * st.dp) return;
+    const int64_t r = i / st.dp;
+    const int j = (int)(i % st.dp);
+    if (j >= st.d) return;
+    const double eps = st.epsrow[r];
+    double* th = st.Th + ((int64_t)(st.cur[r] ^ 1) * st.K + r) * st.dp + j;
+    double g = 0.0;
+    for (int s = 0; s < st.nsplit; ++s) g += st.gpart[((int64_t)s * st.K + r) * st.dp + j];
+    g -= *th / st.pv;
+    const double p = st.Xi[i] + eps * g;
+    st.Xi[i] = p;
+    *th = *th + eps * p;
+}
+
 // ---------------------------------------------------------------------------------------
 // finish / propose, one warp per chain.
 // ---------------------------------------------------------------------------------------
@@ -668,7 +688,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             grp[j] = gp;
             tt += th * th;
             if (!MMALA) {
-                const double p1 = xi[j] + 0.5 * eps * (grc[j] + gp);     // hamiltonian.py:27,40
+                const double p1 = xi[j] + 0.5 * eps * gp;                // final half step (hamiltonian.py:40); Xi holds p
                 k1 += p1 * p1;
             }
         }
@@ -768,11 +788,12 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             if (want_trace && j < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j] = tv;
             if (!sp.propose) continue;
             k0 += xi[q] * xi[q];
-            xo[j] = xi[q];
             if (!MMALA) {
                 const double ph = xi[q] + 0.5 * eps * gr[j];             // hamiltonian.py:27
                 thn[j] = tv + eps * ph;                                  // :30
+                xo[j] = ph;        // the momentum rides in Xi through the trajectory (Nsteps >= 1)
             } else {
+                xo[j] = xi[q];
                 v1[j] = xi[q];
             }
         }
@@ -1166,6 +1187,15 @@ struct LogisticSampler : SamplerImpl {
             RMN_KERNEL_CHECK(); launches++;
             if (t == T) break;
             if (int rc = eval(-1, stream)) return rc;
+            if (!mmala) {
+                // Nsteps - 1 interior leapfrog steps: each one a full likelihood sweep at the new trajectory point
+                for (int l = 1; l < pr->nsteps; ++l) {
+                    const int64_t n = st.K * st.dp;
+                    lg_leapfrog_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st);
+                    RMN_KERNEL_CHECK(); launches++;
+                    if (int rc = eval(-1, stream)) return rc;
+                }
+            }
         }
         step0 += T; diag_steps += T;
         return RMN_OK;
@@ -1209,9 +1239,9 @@ SamplerImpl* make_logistic_sampler(rmn_sampler* s) {
         }
         return new LogisticSampler(s);
     }
-    if (p->kind == RMN_PROP_HMC && p->nsteps == 1 && !p->has_mass) return new LogisticSampler(s);
-    rmn_set_error("logistic model: device kernels exist for MALA (VanillaHMC Nsteps=1, no mass matrix) "
-                  "and SimplifiedMMALA");
+    if (p->kind == RMN_PROP_HMC && !p->has_mass) return new LogisticSampler(s);
+    rmn_set_error("logistic model: device kernels exist for VanillaHMC / AdaptScaleHMC without a mass matrix "
+                  "(Nsteps = 1 is MALA) and SimplifiedMMALA");
     return nullptr;
 }
 

@@ -51,14 +51,22 @@ def test_extreme_logits_are_stable():
     assert relerr(dm.grad_log_posterior_batch(Th).cpu().numpy(), [om.grad_log_posterior(t) for t in Th]) < 1e-8
 
 
-@pytest.mark.parametrize("name,tol", [("mala_logistic", 1e-9), ("mmala_logistic", 1e-8)])
+@pytest.mark.parametrize("name,tol", [("mala_logistic", 1e-9), ("mmala_logistic", 1e-8),
+                                      # "next" row N1 on this family: the reference's leapfrog with Nsteps > 1
+                                      ("hmc3_logistic", 1e-9), ("adapthmc4_logistic", 1e-9)])
 def test_injected_chain_matches_fixture(golden, name, tol):
     from riemann_b200 import Sampler
-    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
+    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA, VanillaHMC, AdaptScaleHMC
     g = golden(name)
     dm, _ = _models(g["X"], g["y"], float(g["prior_var"]))
-    p = (MALA(float(g["eps"]), dm.grad_log_posterior) if name == "mala_logistic"
-         else SimplifiedMMALA(float(g["eps"]), dm))
+    if name == "mala_logistic":
+        p = MALA(float(g["eps"]), dm.grad_log_posterior)
+    elif name == "hmc3_logistic":
+        p = VanillaHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior)
+    elif name == "adapthmc4_logistic":
+        p = AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior)
+    else:
+        p = SimplifiedMMALA(float(g["eps"]), dm)
     s = Sampler(dm, p, g["thetas"][0])
     ex = s.run_injected(xi=g["xi"], u=g["u"])
     assert relerr(np.array(s._chain_thetas), g["thetas"]) < tol

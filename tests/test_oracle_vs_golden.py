@@ -113,13 +113,17 @@ def test_pcn(golden, name, d):
     _replay(g, _gauss(g, d), port.pCN(g["C0"], float(g["rho"])), g["thetas"][0])
 
 
-@pytest.mark.parametrize("name", ["mala_logistic", "mmala_logistic"])
+@pytest.mark.parametrize("name", ["mala_logistic", "mmala_logistic", "hmc3_logistic", "adapthmc4_logistic"])
 def test_logistic(golden, name):
-    """Port model (+ port mMALA) were driven through the REFERENCE Sampler/VanillaHMC."""
+    """Port model (+ port mMALA) were driven through the REFERENCE Sampler/VanillaHMC/AdaptScaleHMC."""
     g = golden(name)
     m = port.LogisticRegression(g["X"], g["y"], float(g["prior_var"]))
     if name == "mala_logistic":
         prop = port.MALA(float(g["eps"]), m.grad_log_posterior)
+    elif name == "hmc3_logistic":
+        prop = port.VanillaHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_posterior)
+    elif name == "adapthmc4_logistic":
+        prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_posterior)
     else:
         prop = port.SimplifiedMMALA(float(g["eps"]), m)
     _replay(g, m, prop, g["thetas"][0])
