@@ -253,6 +253,13 @@ def _n1_dense_fixtures(R):
     g12z = R.MultiGaussianDist(np.zeros(12), C12)                  # pCN shrinks towards 0: zero-mean target
     _vector_fixture(R, "pcn_gauss12d", g12z, R.pCN(0.6 * C12, 0.85), np.full(12, 0.3), 600, 404,
                     extra=dict(C0=0.6 * C12, rho=np.float64(0.85), mu=np.zeros(12), C=C12))
+    # leapfrog with a mass matrix (hamiltonian.py:18-21, 76-91) on the dense path: M close to the target precision
+    M12 = np.linalg.inv(C12) + 0.3 * np.diag(np.arange(1, 13) / 6.0)
+    M12 = 0.5 * (M12 + M12.T)
+    _vector_fixture(R, "hmcmass3_gauss12d", g12, R.VanillaHMC(0.35, 3, g12.grad_log_likelihood, M=M12), mu12 + 0.4, 500, 405,
+                    extra=dict(eps=np.float64(0.35), nsteps=np.int64(3), mu=mu12, C=C12, M=M12))
+    _vector_fixture(R, "adaptmalamass_gauss12d", g12, R.AdaptScaleHMC(0.3, 1, g12.grad_log_likelihood, M=M12), mu12 - 0.3, 800, 406,
+                    extra=dict(eps=np.float64(0.3), nsteps=np.int64(1), mu=mu12, C=C12, M=M12), track_scale=True)
     g100 = R.benchmarks.benchmark_gauss100d_corr
     _vector_fixture(R, "hmc5_gauss100d", g100, R.VanillaHMC(0.1, 5, g100.grad_log_likelihood), np.zeros(100), 200, 403,
                     extra=dict(eps=np.float64(0.1), nsteps=np.int64(5)))

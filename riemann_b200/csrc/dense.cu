@@ -35,7 +35,8 @@ constexpr int GEMM_THREADS = 256;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * (BM + BN) * LDT * 8;
 constexpr int ND_MAX = 8;          // tracked functionals: first 7 coordinates + mean(theta)
 
-enum { EPI_LOGPOST_RW = 0, EPI_LOGPOST_MALA = 1, EPI_RWPROP = 2, EPI_PCNPROP = 3, EPI_PCNREV = 4 };
+enum { EPI_LOGPOST_RW = 0, EPI_LOGPOST_MALA = 1, EPI_RWPROP = 2, EPI_PCNPROP = 3, EPI_PCNREV = 4,
+       EPI_MASS_P0 = 5, EPI_MASS_STEP = 6, EPI_LOGPOST_MASS = 7, EPI_MASS_W1 = 8 };
 
 struct DenseState {
     int64_t K; int d, dp, nblk;    // nblk = column blocks of 32 (partials per row)
@@ -53,6 +54,8 @@ struct DenseState {
     double* S1; double* S2;        // [ND_MAX][K]
     const double* mu;              // [dp] (padded copy)
     double rho, rho_c;             // pCN (randomwalk.py:83-86)
+    double* Pm;                    // [K][dp]   momentum of the trajectory (HMC with a mass matrix)
+    int mass_base_prop;            // EPI_MASS_STEP: the position step starts from the proposal slot (interior steps)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -99,7 +102,8 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
         const int64_t m = m0 + row;
         a_ok[i] = m < K;
         const int64_t mm = a_ok[i] ? m : 0;
-        if (EPI == EPI_RWPROP || EPI == EPI_PCNPROP) a_src[i] = st.Xi + mm * dp + c2;
+        if (EPI == EPI_RWPROP || EPI == EPI_PCNPROP || EPI == EPI_MASS_P0) a_src[i] = st.Xi + mm * dp + c2;
+        else if (EPI == EPI_MASS_STEP || EPI == EPI_MASS_W1) a_src[i] = st.Pm + mm * dp + c2;
         else if (EPI == EPI_PCNREV) a_src[i] = st.V + ((int64_t)(st.cur[mm] ^ 1) * K + mm) * dp + c2;   // D, see below
         else a_src[i] = st.Y + ((int64_t)(st.cur[mm] ^ 1) * K + mm) * dp + c2;
         const int n = n0 + row;
@@ -159,7 +163,44 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
         const int64_t mm = rok ? m : 0;
         const int c = st.cur[mm];
         double pq = 0.0, pk = 0.0;
-        if (EPI == EPI_PCNPROP) {
+        if (EPI == EPI_MASS_P0) {
+            // p0 = chM xi (hamiltonian.py:81), then the initial half step p = p0 + eps/2 g(theta), g = -V (:27)
+            const double he = 0.5 * st.epsrow[mm];
+            const double* vc = st.V + ((int64_t)c * K + mm) * dp;
+            double* pm = st.Pm + mm * dp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) {
+                    const double2 w = *reinterpret_cast<const double2*>(vc + n);
+                    *reinterpret_cast<double2*>(pm + n) = make_double2(acc[i][j][0] - he * w.x, acc[i][j][1] - he * w.y);
+                }
+            }
+        } else if (EPI == EPI_MASS_STEP) {
+            // position step q <- q + eps M^-1 p (hamiltonian.py:29-30, 36-37): acc = p Minv^T
+            const double eps = st.epsrow[mm];
+            const double* yb = st.Y + ((int64_t)(st.mass_base_prop ? (c ^ 1) : c) * K + mm) * dp;
+            double* yp = st.Y + ((int64_t)(c ^ 1) * K + mm) * dp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) {
+                    const double2 y = *reinterpret_cast<const double2*>(yb + n);
+                    *reinterpret_cast<double2*>(yp + n) = make_double2((n < st.d) ? y.x + eps * acc[i][j][0] : 0.0,
+                                                                       (n + 1 < st.d) ? y.y + eps * acc[i][j][1] : 0.0);
+                }
+            }
+        } else if (EPI == EPI_MASS_W1) {
+            // whitened final momentum solve(chM, p') (hamiltonian.py:87): acc = p' chMinv^T; only its squared norm is needed
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * t;
+                if (rok && n < dp) pk += acc[i][j][0] * acc[i][j][0] + acc[i][j][1] * acc[i][j][1];
+            }
+            pk += __shfl_xor_sync(0xffffffffu, pk, 1);
+            pk += __shfl_xor_sync(0xffffffffu, pk, 2);
+            if (rok && t == 0 && blk < st.nblk) st.partk[(int64_t)blk * K + m] = pk;
+        } else if (EPI == EPI_PCNPROP) {
             // pCN (randomwalk.py:88-94): theta' = rho theta + rho_c L xi; the residual of the REVERSE move,
             // D = theta - rho theta', is parked in the proposal slot of V (free until the log-posterior GEMM)
             const double* yc = st.Y + ((int64_t)c * K + mm) * dp;
@@ -222,6 +263,12 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
                     *reinterpret_cast<double2*>(vp + n) = make_double2(v0, v1);
                     const double2 y = *reinterpret_cast<const double2*>(yp + n);
                     pq += y.x * v0 + y.y * v1;
+                    if (EPI == EPI_LOGPOST_MASS) {
+                        // final half step of the momentum, kept for the whitening GEMM: p' = p + eps/2 g' (:40)
+                        double* pm = st.Pm + mm * dp;
+                        const double2 p = *reinterpret_cast<const double2*>(pm + n);
+                        *reinterpret_cast<double2*>(pm + n) = make_double2(p.x - he * v0, p.y - he * v1);
+                    }
                     if (EPI == EPI_LOGPOST_MALA) {
                         // final half step  p' = p + eps/2 g',  g' = -V'   (hamiltonian.py:40); Xi holds p
                         const double2 x = *reinterpret_cast<const double2*>(xi + n);
@@ -245,7 +292,7 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
 
 struct DenseStep {
     int prop_kind;          // RMN_PROP_RW / RMN_PROP_HMC
-    int adapt, rw_diag, finish, propose, diag;
+    int adapt, rw_diag, finish, propose, diag, has_mass;
     double target, eps0, c1, c2;
     const double* Ldiag;    // [dp] diagonal of chol(C0) when the RW covariance is diagonal
     uint64_t seed; int64_t chain_offset;
@@ -338,7 +385,7 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
                 if (j4 + q >= d) xi[q] = 0.0;
         }
         double out[4];
-        if (sp.prop_kind == RMN_PROP_HMC) {
+        if (sp.prop_kind == RMN_PROP_HMC && !sp.has_mass) {
             const double2 va = *reinterpret_cast<const double2*>(v + j4);
             const double2 vb = *reinterpret_cast<const double2*>(v + j4 + 2);
             const double vv[4] = {va.x, va.y, vb.x, vb.y};
@@ -399,6 +446,20 @@ leapfrog_mid_kernel(DenseState st) {
     *reinterpret_cast<double2*>(st.Y + o) = y;
 }
 
+// HMC with a mass matrix, interior step: p <- p + eps g(q), g = -V' (hamiltonian.py:35); the position step is a GEMM
+__global__ void __launch_bounds__(256)
+mass_mid_kernel(DenseState st) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 2;
+    if (i >= st.K * st.dp) return;
+    const int64_t r = i / st.dp;
+    const int j = (int)(i % st.dp);
+    const double eps = st.epsrow[r];
+    const double2 v = *reinterpret_cast<const double2*>(st.V + ((int64_t)(st.cur[r] ^ 1) * st.K + r) * st.dp + j);
+    double2 p = *reinterpret_cast<double2*>(st.Pm + i);
+    p.x -= eps * v.x; p.y -= eps * v.y;
+    *reinterpret_cast<double2*>(st.Pm + i) = p;
+}
+
 // state i/o: theta[K][d] <-> centred slot-0/current rows; V recomputed by a GEMM on set
 __global__ void dense_set_kernel(DenseState st, const double* __restrict__ theta) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -445,20 +506,24 @@ struct DenseGaussSampler : SamplerImpl {
     double* d_Ppad = nullptr;     // [dp][dp] zero-padded precision
     double* d_Lpad = nullptr;     // [dp][dp] zero-padded chol(C0) (dense RW, pCN) or nullptr
     double* d_Linvpad = nullptr;  // [dp][dp] zero-padded chol(C0)^-1 (pCN)
+    double* d_chM = nullptr; double* d_Minv = nullptr; double* d_chMinv = nullptr;   // [dp][dp] HMC mass matrix factors
+    bool has_mass = false;
     double* d_Ldiag = nullptr;    // [dp]
     double* d_mupad = nullptr;
     bool rw_diag = true;
     bool pending = false;         // a proposal is in flight (written, GEMM done, not finished)
     explicit DenseGaussSampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 15) / 16 * 16; st.nblk = (st.dp + 31) / 32;
+        has_mass = s->prop->kind == RMN_PROP_HMC && s->prop->has_mass;
     }
     ~DenseGaussSampler() override {
         cudaFree(d_Ppad); cudaFree(d_Lpad); cudaFree(d_Linvpad); cudaFree(d_Ldiag); cudaFree(d_mupad);
+        cudaFree(d_chM); cudaFree(d_Minv); cudaFree(d_chMinv);
     }
     size_t row_bytes() const { return align256((size_t)st.K * st.dp * 8); }
     size_t workspace_bytes() const override {
         const size_t K = (size_t)st.K;
-        return 5 * row_bytes() + 2 * align256((size_t)st.nblk * K * 8) + 7 * align256(K * 8) +
+        return (has_mass ? 6 : 5) * row_bytes() + 2 * align256((size_t)st.nblk * K * 8) + 7 * align256(K * 8) +
                align256(K * 4) + 2 * align256(ND_MAX * K * 8) + 256;
     }
     int bind(void* ws) override {
@@ -479,6 +544,7 @@ struct DenseGaussSampler : SamplerImpl {
         st.cur = (int*)p; p += align256(K * 4);
         st.S1 = (double*)p; p += align256(ND_MAX * K * 8);
         st.S2 = (double*)p; p += align256(ND_MAX * K * 8);
+        if (has_mass) { st.Pm = (double*)p; p += row_bytes(); }
         // Y and V slots are contiguous pairs: slot b of array X is X + b*K*dp (row_bytes may pad)
         // -> keep the two slots exactly K*dp apart by laying them out inside one 2*row_bytes block
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
@@ -511,6 +577,23 @@ struct DenseGaussSampler : SamplerImpl {
                 RMN_CUDA(cudaMalloc(&d_Lpad, hl.size() * 8));
                 RMN_CUDA(cudaMemcpy(d_Lpad, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice));
             }
+        }
+        if (has_mass) {
+            auto up = [&](const std::vector<double>& full, double** dst, bool lower) -> int {
+                std::vector<double> h((size_t)dp * dp, 0.0);
+                for (int i = 0; i < d; ++i)
+                    for (int j = 0; j < (lower ? i + 1 : d); ++j) h[(size_t)i * dp + j] = full[(size_t)i * d + j];
+                RMN_CUDA(cudaMalloc(dst, h.size() * 8));
+                RMN_CUDA(cudaMemcpy(*dst, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+                return RMN_OK;
+            };
+            if (int rc = up(pr->h_chM, &d_chM, true)) return rc;
+            if (int rc = up(pr->h_Minv, &d_Minv, false)) return rc;
+            if (int rc = up(pr->h_chMinv, &d_chMinv, true)) return rc;
+            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_MASS_P0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_MASS_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_MASS_W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         }
         if (pr->kind == RMN_PROP_PCN) {
             rw_diag = false;
@@ -580,6 +663,8 @@ struct DenseGaussSampler : SamplerImpl {
         sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.rw_diag = rw_diag ? 1 : 0;
         sp.target = pr->target; sp.eps0 = pr->eps; sp.c1 = c1(); sp.c2 = s->model->logdetC;
         sp.Ldiag = d_Ldiag; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
+        sp.has_mass = has_mass ? 1 : 0;
+        if (has_mass) sp.rw_diag = 0;                 // the propose pass only writes xi; the trajectory is a GEMM chain
         const int64_t K = st.K;
         const int d = st.d;
         // iteration t: [finish step t-1 | propose step t] ; GEMM(s).  A last call finishes step T-1.
@@ -608,7 +693,23 @@ struct DenseGaussSampler : SamplerImpl {
                 if (int rc = gemm<EPI_PCNPROP>(d_Lpad, stream)) return rc;
                 if (int rc = gemm<EPI_PCNREV>(d_Linvpad, stream)) return rc;
             }
-            if (pr->kind == RMN_PROP_HMC) {
+            if (pr->kind == RMN_PROP_HMC && has_mass) {
+                // leapfrog with a mass matrix (hamiltonian.py:13-52, 76-91): p0 = chM xi, positions move by
+                // eps M^-1 p, and the kinetic energies use the whitened momenta chM^-1 p -- one GEMM each
+                const int64_t n2 = st.K * st.dp / 2;
+                if (int rc = gemm<EPI_MASS_P0>(d_chM, stream)) return rc;
+                st.mass_base_prop = 0;
+                if (int rc = gemm<EPI_MASS_STEP>(d_Minv, stream)) return rc;
+                for (int l = 1; l < pr->nsteps; ++l) {
+                    if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc;
+                    mass_mid_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, stream>>>(st);
+                    RMN_KERNEL_CHECK(); launches++;
+                    st.mass_base_prop = 1;
+                    if (int rc = gemm<EPI_MASS_STEP>(d_Minv, stream)) return rc;
+                }
+                if (int rc = gemm<EPI_LOGPOST_MASS>(d_Ppad, stream)) return rc;
+                if (int rc = gemm<EPI_MASS_W1>(d_chMinv, stream)) return rc;
+            } else if (pr->kind == RMN_PROP_HMC) {
                 // Nsteps - 1 interior leapfrog steps, each one gradient GEMM + an in-place update
                 for (int l = 1; l < pr->nsteps; ++l) {
                     if (int rc = gemm<EPI_LOGPOST_RW>(d_Ppad, stream)) return rc;
@@ -674,12 +775,7 @@ gauss_point_kernel(int d, const double* __restrict__ mu, const double* __restric
 
 SamplerImpl* make_dense_gauss_sampler(rmn_sampler* s) {
     const rmn_proposal* p = s->prop;
-    if (p->kind == RMN_PROP_HMC && p->has_mass) {
-        rmn_set_error("dense Gaussian path (d > %d) supports RW, pCN and VanillaHMC / AdaptScaleHMC (any Nsteps, "
-                      "Nsteps = 1 is MALA) without a mass matrix; mass matrices run on the small-d path only",
-                      RMN_SMALL_D_MAX);
-        return nullptr;
-    }
+    (void)p;
     return new DenseGaussSampler(s);
 }
 

@@ -25,6 +25,11 @@ def _prop(name, g, m):
         return rw.AdaptScaleRandomWalk(g["C0"])
     if name.startswith("pcn"):
         return rw.pCN(g["C0"], float(g["rho"]))
+    M = g["M"] if "M" in g else None
+    if name.startswith("adaptmalamass"):
+        return hm.AdaptScaleHMC(float(g["eps"]), 1, m.grad_log_likelihood, M=M)
+    if name.startswith("hmcmass"):
+        return hm.VanillaHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood, M=M)
     if name.startswith("adaptmala"):
         return hm.AdaptScaleHMC(float(g["eps"]), 1, m.grad_log_likelihood)
     if name.startswith("adapthmc"):
@@ -39,6 +44,8 @@ def _prop(name, g, m):
                                     ("mala_gauss100d", 100), ("mala_gauss1000d", 1000),
                                     # "next" row N1: leapfrog with Nsteps > 1 on the dense path
                                     ("hmc4_gauss12d", 12), ("adapthmc3_gauss12d", 12), ("hmc5_gauss100d", 100),
+                                    # leapfrog with a mass matrix (hamiltonian.py:18-21) on the dense path
+                                    ("hmcmass3_gauss12d", 12), ("adaptmalamass_gauss12d", 12),
                                     # "next" row N2: pCN on the dense path
                                     ("pcn_gauss12d", 12)])
 def test_injected_chain_matches_reference(golden, name, d):

@@ -72,7 +72,7 @@ def test_mala_is_hmc1(golden, name, d):
 
 
 @pytest.mark.parametrize("name,d", [("hmc5_gauss2d", 2), ("hmc3_mass_gauss2d", 2), ("hmc4_gauss12d", 12),
-                                    ("hmc5_gauss100d", 100)])
+                                    ("hmc5_gauss100d", 100), ("hmcmass3_gauss12d", 12)])
 def test_hmc(golden, name, d):
     g = golden(name)
     m = _gauss(g, d)
@@ -88,11 +88,13 @@ def test_mala_mass(golden):
             g["thetas"][0])
 
 
-@pytest.mark.parametrize("name,d", [("adapthmc5_gauss2d", 2), ("adapthmc3_gauss12d", 12)])
+@pytest.mark.parametrize("name,d", [("adapthmc5_gauss2d", 2), ("adapthmc3_gauss12d", 12),
+                                    ("adaptmalamass_gauss12d", 12)])
 def test_adapt_scale_hmc(golden, name, d):
     g = golden(name)
     m = _gauss(g, d)
-    prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood)
+    prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_likelihood,
+                              M=g["M"] if "M" in g else None)
     _replay(g, m, prop, g["thetas"][0])
     assert abs(prop.scale - g["scales"][-1]) < 1e-12 * g["scales"][-1]
 
