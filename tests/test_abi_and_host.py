@@ -33,6 +33,14 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     assert L.rmn_version() == 100
 
 
+def test_every_entry_point_is_documented_with_the_interface_it_replaces():
+    """INTEGRATION.md section 2 holds one row per exported function (reference file:line or `(absent)`)."""
+    hdr = open(os.path.join(ROOT, "include", "riemann_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in sorted(set(re.findall(r"\b(rmn_[a-z0-9_]+)\s*\(", hdr))) if n not in doc]
+    assert not missing, missing
+
+
 def test_header_constants_match_host_and_oracle(lib):
     from oracle import riemann_port as port
     hdr = open(os.path.join(ROOT, "include", "riemann_b200.h")).read()
