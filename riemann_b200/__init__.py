@@ -7,10 +7,10 @@ gradient, proposal, Philox RNG, accept/reject, state swap) runs in hand-written 
 for sm_100a behind the C ABI of include/riemann_b200.h.  No CPU fallback.
 """
 from .sampling_errors import ParameterError, RiemannBaseError
-from .models.model import Model, DeviceModel
+from .models.model import Model, DeviceModel, grad
 from .proposals.proposal import Proposal, DeviceProposal
 from .samplers.sampler import Sampler
 from .samplers.ptsampler import PTSampler, TemperedModel
 
 __all__ = ["Model", "Sampler", "Proposal", "ParameterError", "RiemannBaseError",
-           "DeviceModel", "DeviceProposal"]
+           "DeviceModel", "DeviceProposal", "PTSampler", "TemperedModel", "grad"]

@@ -112,3 +112,20 @@ class DeviceModel(Model):
 
     def grad_log_posterior(self, theta):
         return self.grad_log_posterior_batch(np.atleast_1d(theta))[0].cpu().numpy()
+
+
+def grad(fun):
+    """Stand-in for ``autograd.grad`` at the one place the reference's scripts use it on a model:
+    ``gradlogpost = grad(model.log_posterior)`` (examples/riemann_ex1.py:237).  For a method of a device
+    model it returns that model's own gradient method -- the kernel the engine evaluates in-flight -- so
+    ``VanillaHMC(eps, Nsteps, grad(model.log_posterior))`` binds to the device gradient.  Anything else has
+    no device kernel and is refused (there is no automatic differentiation and no CPU fallback)."""
+    from ..sampling_errors import ParameterError
+    owner = getattr(fun, "__self__", None)
+    name = getattr(fun, "__name__", "")
+    if isinstance(owner, DeviceModel) and name in ("log_posterior", "__call__"):
+        return owner.grad_log_posterior
+    if isinstance(owner, DeviceModel) and name in ("log_likelihood", "logL") and hasattr(owner, "grad_log_likelihood"):
+        return owner.grad_log_likelihood
+    raise ParameterError("grad() takes log_posterior / log_likelihood of a riemann_b200 device model; "
+                         "no device kernel exists for the gradient of an arbitrary Python callable")

@@ -45,7 +45,9 @@ class Sampler(object):
     def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64", _tempering=None):
         """
         :param theta0: starting point.  Fixed-d models: shape (d,) (shared by all K
-            chains) or (K, d).  Changepoint model: a ChangepointParams or a list of K.
+            chains) or (K, d); a length-1 start is broadcast over the d coordinates, as numpy does inside
+            the reference's model when examples/riemann_ex1.py:233 starts a d = 2 chain from a (1,) array.
+            Changepoint model: a ChangepointParams or a list of K.
         :param K: number of independent chains on this device (default 1, the reference's case)
         :param seed, chain_offset: Philox key and the global id of chain 0 on this device
         :param precision: "f64" (default; fp64 like the reference) or "tf32x3" (dense Gaussian
@@ -80,6 +82,8 @@ class Sampler(object):
             th = np.asarray(theta0, dtype=np.float64)
             self._scalar_theta0 = (th.ndim == 0)
             th = np.atleast_1d(th)
+            if th.ndim == 1 and th.shape[0] == 1 and model.Ndim > 1:
+                th = np.repeat(th, model.Ndim)
             if th.ndim == 1:
                 th = np.tile(th[None, :], (K or 1, 1))
             elif K is not None and K != th.shape[0]:

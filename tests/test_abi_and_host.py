@@ -88,6 +88,15 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
 
 
+def test_grad_stand_in_refuses_arbitrary_callables():
+    """riemann_b200.grad (for examples/riemann_ex1.py:237) only binds device-model methods."""
+    from riemann_b200 import ParameterError, grad
+    with pytest.raises(ParameterError):
+        grad(lambda th: -0.5 * np.sum(th ** 2))
+    with pytest.raises(ParameterError):
+        grad(np.sum)
+
+
 def test_shard_chains():
     from riemann_b200.distributed import shard_chains
     for K, G in [(65536, 8), (10, 3), (7, 8), (16384, 4)]:

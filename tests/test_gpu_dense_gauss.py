@@ -90,6 +90,39 @@ def test_ragged_chain_count_and_per_chain_streams(golden):
         assert relerr(s._chain_logpost[:, c], np.array(o._chain_logpost)) < TOL
 
 
+def test_ragged_mass_matrix_trajectories_match_oracle():
+    """HMC with a mass matrix on the dense path at K = 131 (not a multiple of the 128-row tile) and d = 37
+    (padded to 48): every chain has its own start and noise; six chains are replayed by the oracle."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.models.gaussian import MultiGaussianDist
+    from riemann_b200.proposals.hamiltonian import VanillaHMC
+    K, T, d = 131, 12, 37
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((d, d))
+    C = A @ A.T / d + 0.3 * np.eye(d)
+    mu = rng.standard_normal(d)
+    M = np.linalg.inv(C) + np.diag(rng.uniform(0.1, 0.5, d))
+    M = 0.5 * (M + M.T)
+    xi = rng.standard_normal((T, K, d))
+    u = rng.uniform(size=(T, K))
+    th0 = mu + 0.5 * rng.standard_normal((K, d))
+    m = MultiGaussianDist(mu, C)
+    s = Sampler(m, VanillaHMC(0.45, 3, m.grad_log_likelihood, M=M), th0)
+    s.run_injected(xi=xi, u=u)
+    om = port.MultiGaussianDist(mu, C)
+    nacc = 0
+    for c in (0, 1, 64, 127, 128, 130):
+        o = port.Sampler(om, port.VanillaHMC(0.45, 3, om.grad_log_likelihood, M=M), th0[c],
+                         draws=port.VectorTapeDraws(xi[:, c], u[:, c]))
+        o.run(T)
+        ot = np.array(o._chain_thetas)
+        assert relerr(s._chain_thetas[:, c], ot) < TOL
+        assert relerr(s._chain_logpost[:, c], np.array(o._chain_logpost)) < TOL
+        nacc += int(np.any(ot[1:] != ot[:-1], axis=1).sum())
+    assert 0 < nacc < 6 * T          # both accepts and rejects occur in the replayed chains
+
+
 def test_thinned_trace_and_resume(golden):
     from riemann_b200 import Sampler
     from riemann_b200.proposals.hamiltonian import MALA

@@ -316,3 +316,28 @@ def test_example_script_runs_as_written():
     tau = diagnostics.integrated_time(chain)                    # emcee.autocorr.integrated_time(chain), :42
     assert 0.6 < np.mean(np.any(chain[:-1] != chain[1:], axis=1)) < 0.9      # AdaptScaleHMC targets 0.75
     assert np.all(tau < 60) and abs(chain[:, 0].std() - 1.0) < 0.25
+
+
+def test_riemann_ex1_runs_as_written():
+    """examples/riemann_ex1.py:232-250 (`test_sampling_gauss1d`, the script's only live path) with only the
+    imports changed: `grad` comes from riemann_b200 instead of autograd, and the start state is the script's
+    own `np.random.normal((d,))` -- a length-1 array (the tuple is taken as `loc`), broadcast over d = 2."""
+    from riemann_b200 import Sampler, grad
+    from riemann_b200.models.gaussian import MultiGaussianDist
+    from riemann_b200.proposals.hamiltonian import VanillaHMC as HMC
+    np.random.seed(0)
+    N, d = 1000, 2
+    theta0 = np.random.normal((d,))
+    assert theta0.shape == (1,)
+    model = MultiGaussianDist(np.zeros(d), np.eye(d))
+    gradlogpost = grad(model.log_posterior)
+    proposal = HMC(1.5, 3, gradlogpost)
+    sampler = Sampler(model, proposal, theta0, seed=1)
+    sampler.run(N)
+    Xd = np.array(sampler._chain_thetas)
+    assert Xd.shape == (N + 1, d) and np.all(Xd[0] == theta0[0])
+    if len(Xd.shape) > 1:
+        Xd = Xd[:, 0]
+    # the script's check is a histogram against the unit normal pdf
+    assert abs(Xd[100:].mean()) < 0.25 and abs(Xd[100:].std() - 1.0) < 0.2
+    assert np.mean(Xd[1:] != Xd[:-1]) > 0.5
