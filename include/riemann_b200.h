@@ -234,6 +234,17 @@ int rmn_sampler_get_adaptcov(rmn_sampler_t* s, double* d_L, void* stream);
  * Call before rmn_sampler_set_state. */
 int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double* h_betas, double pswap);
 
+/* Row-sharded data mode (absent in the reference, whose models hold all their data in one numpy array; SURVEY.md 8f N4:
+ * "data-parallel over N when X does not fit").  Every rank creates the logistic model from ITS slice of the rows and a
+ * sampler over the SAME K chains (same seed and chain_offset); after every likelihood sweep the per-chain partial
+ * log-likelihoods, gradients and (mMALA) metrics are summed over the ranks with one grouped NCCL all-reduce on the
+ * sampler's stream, so every rank takes the same accept decisions and the chains stay bit-identical across ranks.
+ * rmn_nccl_unique_id: rank 0 fills `out` (>= 128 bytes) with an ncclUniqueId and sends it to the other ranks (any
+ * transport; the Python host uses torch.distributed).  rmn_sampler_set_row_comm: collective over the `world` ranks
+ * (ncclCommInitRank); call before rmn_sampler_set_state.  f64 precision.  world = 1 is allowed (no-op exchange). */
+int rmn_nccl_unique_id(void* out, size_t nbytes);
+int rmn_sampler_set_row_comm(rmn_sampler_t* s, const void* unique_id, size_t nbytes, int rank, int world);
+
 /* = Sampler.__init__ (sampler.py:34-42): store the states and evaluate their
  * log-posterior (and gradient / metric caches) on the device. */
 int rmn_sampler_set_state(rmn_sampler_t* s, const double* d_theta, void* stream);

@@ -80,6 +80,8 @@ SIGNATURES = {
     "rmn_sampler_reduce_diagnostics": (_I, [_P, _P, _P]),
     "rmn_sampler_launch_count": (_L, [_P]),
     "rmn_sampler_set_tempering": (_I, [_P, _I, _P, _D]),
+    "rmn_nccl_unique_id": (_I, [_P, C.c_size_t]),
+    "rmn_sampler_set_row_comm": (_I, [_P, _P, C.c_size_t, _I, _I]),
     "rmn_sampler_get_adaptcov": (_I, [_P, _P, _P]),
     "rmn_proposal_adaptcov_create": (_I, [_PP, _I, _P, _P, _D, _I, _I]),
     "rmn_proposal_set_scale_adapt": (_I, [_P, _I, _D]),

@@ -465,6 +465,13 @@ extern "C" int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double*
     return s->impl->set_tempering(nt, h_betas, pswap);
 }
 
+extern "C" int rmn_nccl_unique_id(void* out, size_t nbytes) { return rmn_rowcomm_unique_id(out, nbytes); }
+
+extern "C" int rmn_sampler_set_row_comm(rmn_sampler_t* s, const void* unique_id, size_t nbytes, int rank, int world) {
+    RMN_REQUIRE(s && s->impl, "rmn_sampler_set_row_comm: null sampler");
+    return s->impl->set_row_comm(unique_id, nbytes, rank, world);
+}
+
 extern "C" int64_t rmn_sampler_launch_count(const rmn_sampler_t* s) { return (s && s->impl) ? s->impl->launches : 0; }
 
 extern "C" int rmn_sampler_enable_kernel_timing(rmn_sampler_t* s, int enable) {

@@ -242,6 +242,13 @@ struct KernelTimer {
 };
 
 struct rmn_sampler;
+// Row-sharded likelihood (comm.cu): an NCCL communicator over the ranks that each hold a slice of the data rows.
+struct RowComm { void* comm = nullptr; int rank = 0, world = 1; };
+int rmn_rowcomm_unique_id(void* out, size_t nbytes);
+int rmn_rowcomm_init(RowComm* rc, const void* unique_id, size_t nbytes, int rank, int world);
+int rmn_rowcomm_allreduce_f64(RowComm* rc, double* const* bufs, const size_t* counts, int nbuf, cudaStream_t stream);
+void rmn_rowcomm_destroy(RowComm* rc);
+
 struct SamplerImpl {
     virtual ~SamplerImpl() {}
     KernelTimer ktimer;
@@ -253,6 +260,7 @@ struct SamplerImpl {
     virtual int cp_get_state(int32_t*, double*, double*, double*, double*, cudaStream_t) { return unsupported("cp_get_state"); }
     virtual int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t st) = 0;
     virtual int get_adaptcov(double*, cudaStream_t) { return unsupported("get_adaptcov (small-d AdaptCovRandomWalk samplers only)"); }
+    virtual int set_row_comm(const void*, size_t, int, int) { return unsupported("row-sharded data mode (logistic samplers in f64 precision only)"); }
     virtual int set_tempering(int, const double*, double) { return unsupported("parallel tempering (small-d Gaussian samplers only)"); }
     virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }
     virtual int set_adapt(const double*, const int64_t*, const int64_t*, cudaStream_t) { return unsupported("set_adapt"); }

@@ -574,6 +574,25 @@ lg_tc_reduce_kernel(LogisticState st, LgTC tc, int64_t c0, int kb, int nsplit_us
     }
 }
 
+// Row-sharded data mode: fold the row splits of this rank into slot 0 (same fixed order the finish kernels use), so
+// ONE contiguous block per quantity goes through the all-reduce over ranks; afterwards slot 0 holds the sum over all
+// rows of all ranks and the finish kernels run with nsplit = 1.
+__global__ void __launch_bounds__(256)
+lg_fold_splits_kernel(LogisticState st) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n = st.K * st.dp;
+    if (i < n) {
+        double g = 0.0;
+        for (int s = 0; s < st.nsplit; ++s) g += st.gpart[(int64_t)s * n + i];
+        st.gpart[i] = g;
+    }
+    if (i < st.K) {
+        double ll = 0.0;
+        for (int s = 0; s < st.nsplit; ++s) ll += st.llpart[(int64_t)s * st.K + i];
+        st.llpart[i] = ll;
+    }
+}
+
 // Interior leapfrog step (hamiltonian.py:33-37, Nsteps > 1) for the chains' proposal slots: with the gradient of
 // the log-posterior at the trajectory point just swept, g = sum_splits gpart - theta / pv,
 //   p <- p + eps g,   theta <- theta + eps p      (in place; p lives in Xi)
@@ -956,6 +975,26 @@ struct LogisticSampler : SamplerImpl {
     LgTC tcb{};
     tc::GemmMaps maps_z, maps_g;               // Z = Theta X^T (A map rebuilt per chain block) ; G = R X
     std::vector<tc::GemmMaps> maps_z_blk;
+    RowComm rowc;               // row-sharded data mode: the ranks that hold the other slices of X
+    ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); }
+    int set_row_comm(const void* id, size_t nbytes, int rank, int world) override {
+        if (tcx3 || tf32m) {
+            rmn_set_error("row-sharded data mode runs in f64 precision");
+            return RMN_ERR_UNSUPPORTED;
+        }
+        return rmn_rowcomm_init(&rowc, id, nbytes, rank, world);
+    }
+    // the state the finish / adopt / leapfrog kernels see: after the exchange the sums live in slot 0
+    LogisticState fst() const { LogisticState f = st; if (rowc.comm) f.nsplit = 1; return f; }
+    int exchange(cudaStream_t stream) {
+        if (!rowc.comm) return RMN_OK;
+        const int64_t n = st.K * st.dp;
+        lg_fold_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st);
+        RMN_KERNEL_CHECK(); launches++;
+        double* bufs[3] = {st.llpart, st.gpart, st.Gm};
+        const size_t counts[3] = {(size_t)st.K, (size_t)n, mmala ? (size_t)st.K * st.d * st.d : 0};
+        return rmn_rowcomm_allreduce_f64(&rowc, bufs, counts, 3, stream);
+    }
     explicit LogisticSampler(rmn_sampler* s_) : s(s_) {
         fill_geometry(st, s->model, s->K);
         mmala = (s->prop->kind == RMN_PROP_MMALA);
@@ -1138,15 +1177,15 @@ struct LogisticSampler : SamplerImpl {
             ktimer.end(stream);
             RMN_KERNEL_CHECK(); launches++;
         }
-        return RMN_OK;
+        return exchange(stream);
     }
     int set_state(const double* d_theta, cudaStream_t stream) override {
         const int64_t n = st.K * st.dp;
         lg_set_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta);
         RMN_KERNEL_CHECK(); launches++;
         if (int rc = eval(1, stream)) return rc;
-        if (mmala) lg_adopt_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(st);
-        else lg_adopt_kernel<false><<<row_grid(), 128, 0, stream>>>(st);
+        if (mmala) lg_adopt_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(fst());
+        else lg_adopt_kernel<false><<<row_grid(), 128, 0, stream>>>(fst());
         RMN_KERNEL_CHECK(); launches++;
         return RMN_OK;
     }
@@ -1182,8 +1221,8 @@ struct LogisticSampler : SamplerImpl {
                 const int64_t i = t;
                 if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
             }
-            if (mmala) lg_finish_propose_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(st, sp);
-            else lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(st, sp);
+            if (mmala) lg_finish_propose_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(fst(), sp);
+            else lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(fst(), sp);
             RMN_KERNEL_CHECK(); launches++;
             if (t == T) break;
             if (int rc = eval(-1, stream)) return rc;
@@ -1191,7 +1230,7 @@ struct LogisticSampler : SamplerImpl {
                 // Nsteps - 1 interior leapfrog steps: each one a full likelihood sweep at the new trajectory point
                 for (int l = 1; l < pr->nsteps; ++l) {
                     const int64_t n = st.K * st.dp;
-                    lg_leapfrog_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st);
+                    lg_leapfrog_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fst());
                     RMN_KERNEL_CHECK(); launches++;
                     if (int rc = eval(-1, stream)) return rc;
                 }

@@ -27,6 +27,27 @@ def shard_chains(K_total, rank=None, world=None):
     return offset, k_local
 
 
+def shard_rows(N_total, rank=None, world=None):
+    """Contiguous split of the N data rows of a row-sharded model: (row_offset, N_local) for this rank."""
+    return shard_chains(N_total, rank, world)
+
+
+def exchange_unique_id(make_id, nbytes=128):
+    """Rank 0 calls make_id(buffer, nbytes) (rmn_nccl_unique_id) and the bytes go to every rank of the
+    torch.distributed group (any backend; a single process needs no group).  Returns a ctypes buffer."""
+    import ctypes
+    rank, world = rank_world()
+    buf = ctypes.create_string_buffer(nbytes)
+    if rank == 0:
+        make_id(buf, nbytes)
+    if world > 1:
+        import torch.distributed as dist
+        box = [buf.raw if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        buf = ctypes.create_string_buffer(box[0], nbytes)
+    return buf
+
+
 def reduce_block(blk):
     """Sum a diagnostics block over ranks (no-op without an initialised process group)."""
     import torch.distributed as dist

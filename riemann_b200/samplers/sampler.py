@@ -42,7 +42,8 @@ class ChangepointTrace(object):
 
 
 class Sampler(object):
-    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64", _tempering=None):
+    def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64", _tempering=None,
+                 row_sharded=False):
         """
         :param theta0: starting point.  Fixed-d models: shape (d,) (shared by all K
             chains) or (K, d); a length-1 start is broadcast over the d coordinates, as numpy does inside
@@ -52,6 +53,10 @@ class Sampler(object):
         :param seed, chain_offset: Philox key and the global id of chain 0 on this device
         :param precision: "f64" (default; fp64 like the reference) or "tf32x3" (dense Gaussian
             model: fp32 state, tcgen05 tensor-core product with a 3xTF32 split, fp64 accept test)
+        :param row_sharded: logistic model only.  Every rank of the torch.distributed group built its model from its
+            own slice of the data rows (`distributed.shard_rows`) and runs the SAME K chains (same seed, chain_offset
+            and start states); after every likelihood sweep the per-chain partial sums are all-reduced (NCCL, inside
+            the library), so all ranks hold identical chains of the full-data posterior.
         """
         if not isinstance(model, DeviceModel):
             raise ParameterError("model has no device kernel: riemann_b200 samples only device "
@@ -112,6 +117,12 @@ class Sampler(object):
         self.seed, self.chain_offset = int(seed), int(chain_offset)
         self.total_steps = 0
 
+        self.row_sharded = bool(row_sharded)
+        if self.row_sharded:                  # before the first evaluation: it already sums over the ranks' rows
+            from ..distributed import exchange_unique_id, rank_world
+            uid = exchange_unique_id(lambda buf, n: _lib.check(lib.rmn_nccl_unique_id(buf, n)))
+            rank, world = rank_world()
+            _lib.check(lib.rmn_sampler_set_row_comm(h, uid, len(uid), rank, world))
         if _tempering is not None:            # PTSampler: ladders along the chain axis, before the first evaluation
             betas, pswap = _tempering
             b = np.ascontiguousarray(betas, dtype=np.float64)

@@ -251,3 +251,35 @@ def test_split_rhat_sees_a_common_drift():
     assert abs(whole["rhat"][0] - 1) < 0.01 and split["rhat"][0] > 1.1
     with pytest.raises(ValueError):
         summarize_split(block(x[:100]), block(x[:200]))
+
+
+_ROW_SCRIPT = r"""
+import os, sys, ctypes, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from riemann_b200.distributed import exchange_unique_id, shard_rows
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+calls = []
+def fake_id(buf, n):
+    calls.append(n)
+    ctypes.memmove(buf, bytes(range(128)), 128)
+uid = exchange_unique_id(fake_id)
+assert uid.raw == bytes(range(128)), "rank %d got a different id" % rank
+assert len(calls) == (1 if rank == 0 else 0)          # only rank 0 asks NCCL for an id
+off, n = shard_rows(1001)
+assert (off, n) == ((0, 501) if rank == 0 else (501, 500))
+print("rank %d ok" % rank, flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_row_shard_host_logic_two_ranks_gloo(tmp_path):
+    """The host side of the row-sharded data mode: one NCCL unique id reaches every rank, rows split contiguously."""
+    script = tmp_path / "rows.py"
+    script.write_text(_ROW_SCRIPT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29544", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
