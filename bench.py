@@ -217,15 +217,14 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------
 def build_workload(name, K, seed, chain_offset, precision="f64"):
     """Returns (sampler, host_inputs dict for the e2e leg, description)."""
-    from oracle import riemann_port as port        # synthetic-input recipes only (SURVEY 8d)
-    from riemann_b200 import Sampler
+    from riemann_b200 import Sampler, synthetic    # synthetic-input recipes (SURVEY 8d); the engine arm never imports oracle/
     if name == "changepoint":
         from riemann_b200.models.changepoint import ChangepointParams, ChangepointRegression1D
         from riemann_b200.proposals.changepoint import ChangepointRegression1DProp
-        pm, pp, th0, _ = port.make_changepoint_problem()
-        model = ChangepointRegression1D(pm.x, pm.y, pm.xmin, pm.xmax, pm.lamb, pm.kmax, pm.alpha, pm.beta)
-        prop = ChangepointRegression1DProp(model, pp.hscale)
-        s = Sampler(model, prop, ChangepointParams(th0.cpx, th0.cpv, th0.sig), K=K, seed=seed,
+        c = synthetic.changepoint_problem()
+        model = ChangepointRegression1D(c["x"], c["y"], c["xmin"], c["xmax"], c["lamb"], c["kmax"], c["alpha"], c["beta"])
+        prop = ChangepointRegression1DProp(model, c["hscale"])
+        s = Sampler(model, prop, ChangepointParams(*c["theta0"]), K=K, seed=seed,
                     chain_offset=chain_offset)
         return s, "changepoint regression (examples/test_changepoint.py recipe: M=100, 5 true changepoints)"
     if name == "gauss2d_rw":
@@ -250,7 +249,7 @@ def build_workload(name, K, seed, chain_offset, precision="f64"):
         from riemann_b200.models import benchmarks
         from riemann_b200.proposals.hamiltonian import MALA
         m = benchmarks.gauss_corr(1000)
-        rng = np.random.Generator(np.random.Philox(port.SEED_BASE + 3))
+        rng = np.random.Generator(np.random.Philox(synthetic.SEED_BASE + 3))
         th0 = rng.standard_normal((K, 1000))
         s = Sampler(m, MALA(0.08, m.grad_log_likelihood), th0, seed=seed, chain_offset=chain_offset,
                     precision=precision)
@@ -259,9 +258,9 @@ def build_workload(name, K, seed, chain_offset, precision="f64"):
         from riemann_b200.models.logistic import LogisticRegression
         from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
         N, d = (100000, 64) if name == "logistic_mmala" else (1000000, 100)
-        X, y, ts, pv = port.make_logistic_problem(N, d)
+        X, y, ts, pv = synthetic.logistic_problem(N, d)
         m = LogisticRegression(X, y, pv)
-        rng = np.random.Generator(np.random.Philox(port.SEED_BASE + 5))
+        rng = np.random.Generator(np.random.Philox(synthetic.SEED_BASE + 5))
         th0 = ts[None, :] + 0.01 * rng.standard_normal((K, d))
         prop = SimplifiedMMALA(0.5, m) if name == "logistic_mmala" else MALA(0.02, m.grad_log_posterior)
         if precision == "tf32-metric" and name != "logistic_mmala":

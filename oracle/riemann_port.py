@@ -762,21 +762,15 @@ SEED_BASE = 20261018
 
 def make_changepoint_problem(seed=SEED_BASE + 2, Ncpx=5, Ndata=100, xmin=1.0, xmax=3.0,
                              hmin=1.0, hmax=3.0, sig=0.1):
-    """Recipe of examples/test_changepoint.py:137-150,167 with a seeded generator."""
-    rng = np.random.Generator(np.random.Philox(seed))
-    cpx = np.sort(rng.uniform(xmin, xmax, size=Ncpx))
-    cpv = rng.uniform(hmin, hmax, size=Ncpx + 1)
-    theta_true = ChangepointParams(cpx, cpv, sig)
-    x = np.sort(xmin + (xmax - xmin) * rng.uniform(size=Ndata))
-    model = ChangepointRegression1D(x, x * 0, xmin, xmax, 1.0 * Ncpx, 2 * Ncpx, 1, 1)
-    model.y = model.predict(theta_true, x) + sig * rng.normal(size=Ndata)
-    theta0 = ChangepointParams([0.5 * (xmin + xmax)], [hmin, hmax], 0.1)
-    return model, ChangepointRegression1DProp(model, hmax - hmin), theta0, theta_true
+    """Recipe of examples/test_changepoint.py:137-150,167 with a seeded generator: the arrays of
+    riemann_b200/synthetic.py (plain numpy, the one source of the bench inputs) wrapped in the port's classes."""
+    from riemann_b200 import synthetic
+    c = synthetic.changepoint_problem(seed, Ncpx, Ndata, xmin, xmax, hmin, hmax, sig)
+    model = ChangepointRegression1D(c["x"], c["y"], c["xmin"], c["xmax"], c["lamb"], c["kmax"], c["alpha"], c["beta"])
+    theta0 = ChangepointParams(list(c["theta0"][0]), list(c["theta0"][1]), c["theta0"][2])
+    return model, ChangepointRegression1DProp(model, c["hscale"]), theta0, ChangepointParams(*c["theta_true"])
 
 
 def make_logistic_problem(N, d, seed=SEED_BASE + 4, prior_var=100.0, dtype=np.float64):
-    rng = np.random.Generator(np.random.Philox(seed))
-    X = (rng.standard_normal((N, d)) / np.sqrt(d)).astype(dtype)
-    theta_star = rng.standard_normal(d)
-    y = (rng.uniform(size=N) < expit(X.astype(np.float64) @ theta_star)).astype(np.float64)
-    return X, y, theta_star, prior_var
+    from riemann_b200 import synthetic
+    return synthetic.logistic_problem(N, d, seed, prior_var, dtype)

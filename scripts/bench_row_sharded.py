@@ -51,12 +51,9 @@ def main():
     from riemann_b200.models.logistic import LogisticRegression
     from riemann_b200.proposals.hamiltonian import MALA
 
-    # synthetic data of SURVEY.md 8d config 4: X_ij ~ N(0, 1/d), theta* ~ N(0, I), y_i ~ Bernoulli(sigmoid(x_i . theta*))
-    rng = np.random.Generator(np.random.Philox(20261018 + 4))
-    X = rng.standard_normal((a.rows, a.dim)) / np.sqrt(a.dim)
-    ts = rng.standard_normal(a.dim)
-    y = (rng.uniform(size=a.rows) < 1.0 / (1.0 + np.exp(-(X @ ts)))).astype(np.float64)
-    pv = 100.0
+    from riemann_b200 import synthetic
+    X, y, ts, pv = synthetic.logistic_problem(a.rows, a.dim)
+    rng = np.random.Generator(np.random.Philox(synthetic.SEED_BASE + 5))
     th0 = ts[None, :] + 0.01 * rng.standard_normal((a.chains, a.dim))
 
     ms_plain = None

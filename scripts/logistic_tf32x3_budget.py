@@ -5,14 +5,14 @@ the DIFFERENCE between a state and a MALA proposal from it (what enters the acce
 import sys, os, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import riemann_port as port          # synthetic-input recipe only
+from riemann_b200 import synthetic
 from riemann_b200 import Sampler
 from riemann_b200.models.logistic import LogisticRegression
 from riemann_b200.proposals.hamiltonian import MALA
 
 res = {}
 for name, N, d, K, eps in (("config4", 1000000, 100, 512, 0.02), ("config5", 100000, 64, 512, 0.05)):
-    X, y, ts, pv = port.make_logistic_problem(N, d)
+    X, y, ts, pv = synthetic.logistic_problem(N, d)
     dm = LogisticRegression(X, y, pv)
     rng = np.random.default_rng(8)
     th0 = ts[None] + 0.01 * rng.standard_normal((K, d))

@@ -27,7 +27,7 @@ def main():
     from riemann_b200.models.changepoint import ChangepointParams, ChangepointRegression1D
     from riemann_b200.proposals.changepoint import ChangepointRegression1DProp
     from riemann_b200.proposals import randomwalk as rw, hamiltonian as hm
-    from oracle import riemann_port as port            # problem generators only
+    from riemann_b200 import synthetic
 
     rng = np.random.default_rng(0)
 
@@ -48,10 +48,10 @@ def main():
         print("%-34s ok  accept=%.2f" % (tag, dg["accept_rate"]), flush=True)
 
     # changepoint, K not a multiple of the 8 chains a warp holds
-    pm, pprop, pth0, _ = port.make_changepoint_problem()
-    cm = ChangepointRegression1D(pm.x, pm.y, pm.xmin, pm.xmax, pm.lamb, pm.kmax, pm.alpha, pm.beta)
-    run("changepoint K=203", lambda: Sampler(cm, ChangepointRegression1DProp(cm, pprop.hscale),
-                                     ChangepointParams(pth0.cpx, pth0.cpv, pth0.sig), K=203, seed=1), T=40, trace=False)
+    c = synthetic.changepoint_problem()
+    cm = ChangepointRegression1D(c["x"], c["y"], c["xmin"], c["xmax"], c["lamb"], c["kmax"], c["alpha"], c["beta"])
+    run("changepoint K=203", lambda: Sampler(cm, ChangepointRegression1DProp(cm, c["hscale"]),
+                                             ChangepointParams(*c["theta0"]), K=203, seed=1), T=40, trace=False)
 
     # small-d Gaussian family
     for d in (1, 2, 5, 8):
@@ -86,7 +86,7 @@ def main():
 
     # logistic family, N and d ragged
     for (N, d) in ((333, 7), (1500, 20)):
-        X, y, ts, pv = port.make_logistic_problem(N, d, seed=5)
+        X, y, ts, pv = synthetic.logistic_problem(N, d, seed=5)
         lm = LogisticRegression(X, y, pv)
         th0 = ts[None] + 0.05 * rng.standard_normal((45, d))
         for prec in ("f64", "tf32x3"):

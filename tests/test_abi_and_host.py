@@ -97,6 +97,27 @@ def test_grad_stand_in_refuses_arbitrary_callables():
         grad(np.sum)
 
 
+def test_bench_engine_arm_never_imports_oracle():
+    """bench.py may execute oracle/ only in its CPU legs (cpu_baseline and --impl reference share _cpu_worker)."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    where = []
+    for fn in ast.walk(tree):
+        if isinstance(fn, (ast.FunctionDef, ast.Module)):
+            for node in ast.iter_child_nodes(fn) if isinstance(fn, ast.Module) else ast.walk(fn):
+                mods = ([a.name for a in node.names] if isinstance(node, ast.Import)
+                        else [node.module or ""] if isinstance(node, ast.ImportFrom) else [])
+                if any(m.split(".")[0] == "oracle" for m in mods):
+                    where.append(getattr(fn, "name", "<module>"))
+    assert where and set(where) == {"_cpu_worker"}, where
+    # the synthetic inputs both arms use come from one neutral numpy module
+    from oracle import riemann_port as port
+    from riemann_b200 import synthetic
+    pm = port.make_changepoint_problem()[0]
+    c = synthetic.changepoint_problem()
+    assert np.array_equal(pm.x, c["x"]) and np.array_equal(pm.y, c["y"])
+
+
 def test_shard_chains():
     from riemann_b200.distributed import shard_chains
     for K, G in [(65536, 8), (10, 3), (7, 8), (16384, 4)]:
