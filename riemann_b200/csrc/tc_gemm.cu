@@ -63,7 +63,7 @@ enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 //   TMA warp   --full/empty[STAGES]-->   MMA thread   --tmem_full/tmem_empty[ACC_STAGES]-->   8 epilogue warps
 // The accumulator is double buffered in TMEM (2 x 256 columns), so the epilogue of tile i runs while the
 // tensor cores work on tile i+1.
-// PASSES = 3: fp32-accurate split product (Ah Bh + Ah Bl + Al Bh), 2 stages of 96 KB.
+// PASSES = 3: fp32-accurate split product (Ah Bh + Ah Bl + Al Bh), k-blocks of TK3 = 16 (SWIZZLE_64B): 4 stages of 48 KB.
 // PASSES = 1: plain TF32 product of the "hi" maps only (the Fisher-metric GEMM of the logistic sampler,
 //             where the product only shapes a proposal), 4 stages of 48 KB so the TMA latency stays hidden
 //             behind one third of the tensor work per stage.
