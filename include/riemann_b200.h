@@ -234,6 +234,17 @@ int rmn_sampler_get_adaptcov(rmn_sampler_t* s, double* d_L, void* stream);
  * Call before rmn_sampler_set_state. */
 int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double* h_betas, double pswap);
 
+/* = emcee.autocorr.integrated_time(chain) as called at examples/test_randomwalk.py:42 ("steps per independent sample"),
+ * on the device: d_x is a thinned trace x[n][nchains][nfunc] exactly as rmn_trace_t.d_theta holds it.  Per functional:
+ * FFT autocorrelation function of every chain (centred, zero-padded to 2 * next_pow2(n); batched cuFFT, resolved at
+ * run time), normalised per chain and averaged over the chains ("walkers"), tau(W) = 2 sum_{t<=W} rho(t) - 1, Sokal's
+ * automatic window = first W >= c * tau(W) (emcee's default c = 5; the last lag if none).  h_tau[nfunc] (host) receives
+ * tau in units of trace rows, h_window[nfunc] (host, may be NULL) the window.  Synchronous; allocates its own scratch
+ * (2 * 8 * nchains * nfunc * 2 * next_pow2(n) bytes).  emcee is not vendored by the reference: parity unpinned, the
+ * algorithm is restated from its publication (host twin: riemann_b200/diagnostics.py; the tests compare the two). */
+int rmn_autocorr_tau(const double* d_x, int64_t n, int64_t nchains, int64_t nfunc, double c, double* h_tau,
+                     int64_t* h_window, void* stream);
+
 /* Row-sharded data mode (absent in the reference, whose models hold all their data in one numpy array; SURVEY.md 8f N4:
  * "data-parallel over N when X does not fit").  Every rank creates the logistic model from ITS slice of the rows and a
  * sampler over the SAME K chains (same seed and chain_offset); after every likelihood sweep the per-chain partial

@@ -465,6 +465,11 @@ extern "C" int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double*
     return s->impl->set_tempering(nt, h_betas, pswap);
 }
 
+extern "C" int rmn_autocorr_tau(const double* d_x, int64_t n, int64_t nchains, int64_t nfunc, double c, double* h_tau,
+                                int64_t* h_window, void* stream) {
+    return rmn_autocorr_tau_impl(d_x, n, nchains, nfunc, c, h_tau, h_window, (cudaStream_t)stream);
+}
+
 extern "C" int rmn_nccl_unique_id(void* out, size_t nbytes) { return rmn_rowcomm_unique_id(out, nbytes); }
 
 extern "C" int rmn_sampler_set_row_comm(rmn_sampler_t* s, const void* unique_id, size_t nbytes, int rank, int world) {

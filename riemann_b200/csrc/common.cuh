@@ -242,6 +242,10 @@ struct KernelTimer {
 };
 
 struct rmn_sampler;
+// integrated autocorrelation time of a device trace (acf.cu)
+int rmn_autocorr_tau_impl(const double* d_x, int64_t n, int64_t K, int64_t nd, double c, double* h_tau,
+                          int64_t* h_window, cudaStream_t stream);
+
 // Row-sharded likelihood (comm.cu): an NCCL communicator over the ranks that each hold a slice of the data rows.
 struct RowComm { void* comm = nullptr; int rank = 0, world = 1; };
 int rmn_rowcomm_unique_id(void* out, size_t nbytes);

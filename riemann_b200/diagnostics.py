@@ -52,8 +52,32 @@ def integrated_time(x, c=5.0):
     return np.array([_tau_from_acov(acov[:, j], c) for j in range(x.shape[1])])
 
 
-def integrated_time_chains(x, c=5.0):
-    """K chains x [N, K] or [N, K, d] -> tau per functional, ACF averaged over the chains."""
+def integrated_time_device(x, c=5.0, return_window=False):
+    """The same estimator on the GPU (`rmn_autocorr_tau`: batched cuFFT + windowing kernels).  x is a trace
+    [N, K] or [N, K, d], a numpy array (uploaded) or a float64 CUDA tensor (used in place, e.g. the device trace
+    of a run).  Returns tau per functional (and the windows)."""
+    import ctypes as C
+    from . import _lib
+    torch = _lib.require_cuda()
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+    if t.dtype != torch.float64 or not t.is_cuda:
+        raise ValueError("integrated_time_device needs float64 data on the GPU")
+    if t.ndim == 2:
+        t = t[:, :, None]
+    t = t.contiguous()
+    n, K, nd = t.shape
+    tau = np.empty(nd, dtype=np.float64)
+    win = np.empty(nd, dtype=np.int64)
+    _lib.check(_lib.load().rmn_autocorr_tau(_lib.ptr(t), n, K, nd, float(c), tau.ctypes.data_as(C.c_void_p),
+                                            win.ctypes.data_as(C.c_void_p), _lib.stream_ptr()))
+    return (tau, win) if return_window else tau
+
+
+def integrated_time_chains(x, c=5.0, device=False):
+    """K chains x [N, K] or [N, K, d] -> tau per functional, ACF averaged over the chains.
+    device=True evaluates it on the GPU (integrated_time_device)."""
+    if device:
+        return integrated_time_device(x, c)
     x = np.asarray(x, dtype=np.float64)
     if x.ndim == 2:
         x = x[:, :, None]
