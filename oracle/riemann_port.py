@@ -19,7 +19,21 @@ import math
 
 import numpy as np
 from scipy.special import gammaln, expit
-from scipy.linalg import solve_triangular
+from scipy.linalg.lapack import dtrtrs
+
+
+def solve_triangular(a, b, lower, check_finite=False):
+    """scipy.linalg.solve_triangular without its per-call argument validation (11 us of Python per call, more than the
+    whole d = 2 solve): the same LAPACK dtrtrs call scipy makes, transposed system for a C-ordered factor exactly like
+    scipy's `_solve_triangular`, so results are bit-identical.  Non-finite inputs give non-finite outputs, as the
+    reference's np.linalg.solve does (gaussian.py:51), instead of scipy's ValueError."""
+    if a.flags.f_contiguous:
+        x, info = dtrtrs(a, b, lower=lower, trans=0)
+    else:
+        x, info = dtrtrs(a.T, b, lower=not lower, trans=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("dtrtrs: singular triangular factor (info = %d)" % info)
+    return x
 
 # --------------------------------------------------------------------------
 # tape layout for the changepoint proposal (mirrors RMN_CP_SLOT_* in
@@ -159,14 +173,14 @@ class MultiGaussianDist(Model):
         # gaussian.py:49-52; the reference uses a general solve on the triangular
         # factor, a triangular solve gives the same u to fp64 round-off
         y = theta - self.mu
-        u = solve_triangular(self.L, y, lower=True)
+        u = solve_triangular(self.L, y, lower=True, check_finite=False)
         return -0.5 * (np.dot(u, u) + len(y) * np.log(2 * np.pi) + self.logdetC)
 
     def grad_log_likelihood(self, theta):
         # gaussian.py:54-58:  -C^{-1} (theta - mu)
         y = theta - self.mu
-        u = solve_triangular(self.L, y, lower=True)
-        return -solve_triangular(self.L.T, u, lower=False)
+        u = solve_triangular(self.L, y, lower=True, check_finite=False)
+        return -solve_triangular(self.L.T, u, lower=False, check_finite=False)
 
     grad_log_posterior = grad_log_likelihood                 # prior is flat
 
@@ -429,8 +443,8 @@ class pCN(Proposal):
         xi = self.draws.normal("xi", theta.shape[0])
         theta_p = self.rho * theta + self.rho_c * np.dot(self.L, xi)
         Ls = self.L * self.rho_c
-        u_fwd = solve_triangular(Ls, theta_p - self.rho * theta, lower=True)
-        u_rev = solve_triangular(Ls, theta - self.rho * theta_p, lower=True)
+        u_fwd = solve_triangular(Ls, theta_p - self.rho * theta, lower=True, check_finite=False)
+        u_rev = solve_triangular(Ls, theta - self.rho * theta_p, lower=True, check_finite=False)
         return theta_p, -0.5 * (np.dot(u_fwd, u_fwd) - np.dot(u_rev, u_rev))
 
 
@@ -492,8 +506,8 @@ class VanillaHMC(Proposal):
             p0 = np.dot(self.chM, p0)                                  # :81
         p1, theta_new = leapfrog(p0, theta, self.Nsteps, self.eps, self._grad, self.M)
         if self.chM is not None:                                       # :85-87
-            p0 = solve_triangular(self.chM, p0, lower=True)
-            p1 = solve_triangular(self.chM, p1, lower=True)
+            p0 = solve_triangular(self.chM, p0, lower=True, check_finite=False)
+            p1 = solve_triangular(self.chM, p1, lower=True, check_finite=False)
         return theta_new, 0.5 * (np.sum(p1 ** 2) - np.sum(p0 ** 2))   # :89
 
 
@@ -560,7 +574,7 @@ class SimplifiedMMALA(Proposal):
         G = self.model.metric(theta)
         L = np.linalg.cholesky(G)
         g = self.model.grad_log_posterior(theta)
-        nat = solve_triangular(L.T, solve_triangular(L, g, lower=True), lower=False)
+        nat = solve_triangular(L.T, solve_triangular(L, g, lower=True, check_finite=False), lower=False, check_finite=False)
         mean = theta + 0.5 * self.eps ** 2 * nat
         return L, mean, 2.0 * np.sum(np.log(np.diag(L)))
 
@@ -574,7 +588,7 @@ class SimplifiedMMALA(Proposal):
         theta = np.atleast_1d(theta)
         xi = self.draws.normal("xi", theta.shape[0])
         L, mean, logdet = self._geometry(theta)
-        theta_p = mean + self.eps * solve_triangular(L.T, xi, lower=False)
+        theta_p = mean + self.eps * solve_triangular(L.T, xi, lower=False, check_finite=False)
         Lp, mean_p, logdet_p = self._geometry(theta_p)
         lqr = self._logq(L, mean, logdet, theta_p) - self._logq(Lp, mean_p, logdet_p, theta)
         return theta_p, lqr
@@ -590,9 +604,17 @@ class ChangepointRegression1DProp(Proposal):
         self.model = model
         self.Ndata = len(model.x)
         self.hscale = hscale
+        self.k = None
 
     def step_sizes(self, k):
-        """sqrt of the isotropic variances at test_changepoint.py:36-38."""
+        """sqrt of the isotropic variances at test_changepoint.py:36-38; like the reference (:45-46, `self.k`) the
+        three Cholesky factors are rebuilt only when the number of changepoints has changed."""
+        if k == self.k:
+            return self._steps
+        self.k, self._steps = k, self._step_sizes(k)
+        return self._steps
+
+    def _step_sizes(self, k):
         xmin, xmax = self.model.xmin, self.model.xmax
         sx = np.linalg.cholesky(0.01 * (xmax - xmin) / (k + 1) * np.eye(max(k, 1)))[0, 0]
         sv = np.linalg.cholesky(0.01 * self.hscale ** 2 / self.Ndata * np.eye(k + 1))[0, 0]
