@@ -41,6 +41,20 @@ def test_every_entry_point_is_documented_with_the_interface_it_replaces():
     assert not missing, missing
 
 
+def test_c99_consumer_compiles_links_and_gets_error_codes(tmp_path, lib):
+    """The boundary is a C ABI: a -std=c99 -pedantic translation unit includes the header, links the shared
+    library and sees RMN_ERR_PARAM + a message for bad arguments (no GPU involved)."""
+    lib.load()
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.join(ROOT, "riemann_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", libdir,
+                        "-l:libriemann_b200.so", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "abi consumer ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_header_constants_match_host_and_oracle(lib):
     from oracle import riemann_port as port
     hdr = open(os.path.join(ROOT, "include", "riemann_b200.h")).read()
