@@ -55,6 +55,24 @@ def test_c99_consumer_compiles_links_and_gets_error_codes(tmp_path, lib):
     assert r.returncode == 0 and "abi consumer ok" in r.stdout, r.stdout + r.stderr
 
 
+def test_library_carries_tcgen05_tma_and_dmma_sass(lib):
+    """Static evidence that the tensor-core paths are native sm_100a code (mnemonics per the B200 profiling recipe):
+    tcgen05.mma = UTC*MMA, tcgen05.ld = LDTM, TMA = UTMALDG in the GEMM object; fp64 DMMA in the dense / logistic ones."""
+    lib.load()
+    import __graft_entry__ as ge
+    import shutil
+    if shutil.which("cuobjdump") is None or not os.path.exists(os.path.join(ge.OBJ, "tc_gemm.o")):
+        pytest.skip("needs cuobjdump and the build objects")
+
+    def sass(obj):
+        return subprocess.run(["cuobjdump", "-sass", os.path.join(ge.OBJ, obj)], capture_output=True, text=True).stdout
+    tc = sass("tc_gemm.o")
+    assert "sm_100a" in tc
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "SYNCS"):
+        assert mnemonic in tc, mnemonic
+    assert "DMMA" in sass("dense.o") and "DMMA" in sass("logistic.o")
+
+
 def test_header_constants_match_host_and_oracle(lib):
     from oracle import riemann_port as port
     hdr = open(os.path.join(ROOT, "include", "riemann_b200.h")).read()
