@@ -231,6 +231,9 @@ __device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const doubl
     return combine_logpost(logp, logl);
 }
 
+#ifndef RMN_CP_SHARED_MV
+#define RMN_CP_SHARED_MV 0
+#endif
 #ifndef RMN_CP_MINBLOCKS
 #define RMN_CP_MINBLOCKS 5   /* 96 regs, 20 warps/SM: best of 4..8 measured (gpurun r17) */
 #endif
@@ -334,8 +337,11 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                     xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
                 }
             }
-            const uint32_t z0 = __shfl_sync(0xffffffffu, r.z, 0, GL), w0 = __shfl_sync(0xffffffffu, r.w, 0, GL);
-            const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, GL), w1 = __shfl_sync(0xffffffffu, r.w, 1, GL);
+            // (RMN_CP_SHARED_MV = 1, an unmeasured build variant: the move-type words come from the first chain of the
+            // warp, so the warp's chains share one move schedule -- see DESIGN.md section 5; off in the product)
+            constexpr int MVW = RMN_CP_SHARED_MV ? 32 : GL;
+            const uint32_t z0 = __shfl_sync(0xffffffffu, r.z, 0, MVW), w0 = __shfl_sync(0xffffffffu, r.w, 0, MVW);
+            const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, MVW), w1 = __shfl_sync(0xffffffffu, r.w, 1, GL);
             const uint32_t z2 = __shfl_sync(0xffffffffu, r.z, 2, GL), w2 = __shfl_sync(0xffffffffu, r.w, 2, GL);
             const uint32_t z3 = __shfl_sync(0xffffffffu, r.z, 3, GL), w3 = __shfl_sync(0xffffffffu, r.w, 3, GL);
             mv = (z0 < P.t1) ? 0 : ((w0 < P.t2) ? 1 : ((z1 < P.t3) ? 2 : 3));   // same tests on raw words
