@@ -377,7 +377,8 @@ def run_engine(args):
         s2.run(8000, 0, 1)
         tr = s2._chain_thetas
         x = np.stack([tr.sig[1:], tr.k[1:].astype(np.float64)], axis=2)          # [N, K, 2]: sigma, k
-        tau_s = dgn.integrated_time_chains(x)
+        # RMN_BENCH_DEVICE_TAU=1: the same estimator on the GPU (rmn_autocorr_tau); host FFT by default
+        tau_s = dgn.integrated_time_chains(x, device=os.environ.get("RMN_BENCH_DEVICE_TAU", "0") == "1")
         tau_m = diag["tau"][:2]
         tau_check = {"functionals": ["sigma", "k"], "sokal_tau_steps": [float(t) for t in tau_s],
                      "moment_tau_steps": [float(t) for t in tau_m],
