@@ -1,30 +1,40 @@
 #!/usr/bin/env python
 """
-bench.py -- MH chain-steps/sec (and min-ESS/sec) of the B200 engine on BASELINE.json's
-metric, next to the CPU sampler timed on the same box.
+bench.py -- MH chain-steps/sec and min-ESS/sec of the B200 engine on BASELINE.json's metric, next to the
+CPU sampler timed on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload NAME [--precision P] [--chains C] [--iters T]] [--no-configs] [--no-cpu]
 
-Headline workload (N=1 default) is BASELINE.json configs[1]: the changepoint model of
-examples/test_changepoint.py, 4-way RW/birth/death Metropolis proposal, 65,536 chains per
-GPU.  One bench "step" = one launch of the hot path: T MH iterations of every chain
-(`--iters`, default 1000), device-resident.  Chains shard over GPUs with no data-path
-collective (weak scaling: 65,536 chains per GPU); the only exchange is the per-batch
-diagnostics all-reduce (NCCL), which is inside the timed region.
+The line printed by the default invocation (the one the driver runs):
 
-Other workloads (`--workload gauss1000_mala | logistic_mala | logistic_mmala | gauss2d_rw`)
-print the same JSON line for BASELINE configs 3, 4, 5 and 1, `gauss2d_pt` for the parallel-tempering
-"next" row; `--precision tf32x3 | tf32-metric` selects the tcgen05 tensor-core modes of the dense
-Gaussian and logistic workloads (default f64 = the parity mode).  They are for profiling and DESIGN.md;
-the driver's line is the default one.
+* headline = BASELINE.json configs[1]: the changepoint model of examples/test_changepoint.py, 4-way
+  RW/birth/death Metropolis proposal, 65,536 chains per GPU (weak scaling).  One bench "step" = one launch of the
+  hot path: T MH iterations of every chain (`--iters`, default 1000), device-resident.  `value` is device-timed
+  with the state resident, `e2e` goes through the public API with host buffers.
+* `configs` = one entry per remaining BASELINE config AT BASELINE'S OWN SHARDING (fixed total chain counts split
+  over the N GPUs = strong scaling): gauss2d_rw (K = 1 latency as examples/test_randomwalk.py:39-40 runs it, and
+  2^20 chains per GPU), gauss1000_mala (16,384 chains / N; f64 and tf32x3), logistic_mala (8,192 / N; f64 and
+  tf32x3), logistic_mmala (4,096 / N; f64 and tf32x3).  Every entry carries value, e2e, dtype, a live roofline of
+  its dominant kernel, diagnostics and (N = 1 only) a short CPU leg.
+* `ess` (changepoint): min-ESS/sec as a MEASUREMENT -- a separate device-timed phase whose two half-windows are
+  long enough for the slowest tracked functional (window_over_tau, split-R-hat < 1.05 required, else null with
+  the reason), plus the Sokal-window estimator of examples/test_randomwalk.py:42 on a traced subset, the same
+  estimator the CPU arm applies to its chains.
+* `multi_gpu_checks` (N >= 2): chain-shard invariance of the Philox streams at N ranks (bitwise) and the
+  row-sharded data mode replaying the reference-stream fixtures with the rows split over the N ranks.
 
-`roofline.achieved` is the algorithmic work of the timed region divided by the DOMINANT kernel's own time
-in it (CUDA events around each of its launches, rmn_sampler_kernel_timing); `tau_check` (changepoint) puts
-the Sokal-window autocorrelation time of a traced subset next to the moment-based one behind min_ess_per_sec.
+`--workload NAME` prints the line of that single workload (profiling).
 
-Timing: W untimed warm-up steps, then K steps each bracketed by CUDA events on the
-launching stream, L2 flushed (256 MiB write) between steps outside the event pairs,
-barrier + synchronize on both sides, MAX over ranks.
+Timing: W untimed warm-up steps, then K steps each bracketed by CUDA events on the launching stream, L2 flushed
+(256 MiB write) between steps outside the event pairs, barrier + synchronize on both sides, MAX over ranks.
+`roofline.achieved` is the algorithmic work of the timed region divided by the DOMINANT kernel's own time in it
+(CUDA events around each of its launches, rmn_sampler_kernel_timing).
+
+CPU arm (`--impl reference`, and `cpu_baseline` at N = 1): the UNMODIFIED reference sampler
+(riemann/samplers/sampler.py:44-90, staged by oracle/build_ref.py under oracle/_ref/, imported through
+oracle/refshim.py) for configs 1-3, `kind: "reference"`; the numpy port (oracle/riemann_port.py) for the two
+models the reference does not contain (logistic regression: configs 4, 5), `kind: "port"`.  One chain per host core.
 """
 import argparse
 import json
@@ -42,33 +52,44 @@ if ROOT not in sys.path:
 
 METRIC = "mh_chain_steps_per_sec"
 UNIT = "chain-steps/s"
+SEED = 20261018
 CHAINS_PER_GPU = {"changepoint": 65536, "gauss2d_rw": 1 << 20, "gauss1000_mala": 16384,
                   "logistic_mala": 1024, "logistic_mmala": 512, "gauss2d_pt": 5 * (1 << 17)}
-# SURVEY.md section 8d / BASELINE.md section 4: algorithmic work per chain-step
-ALGO_FLOP = {"changepoint": 650.0, "gauss2d_rw": 40.0, "gauss1000_mala": 2.0e6,
+# BASELINE.json's own chain counts ("16,384 chains sharded over 1/2/4/8", "8,192 chains over 8", "4,096 chains")
+CHAINS_TOTAL = {"gauss1000_mala": 16384, "logistic_mala": 8192, "logistic_mmala": 4096}
+ITERS = {"changepoint": 1000, "gauss2d_rw": 2000, "gauss1000_mala": 20, "logistic_mala": 2, "logistic_mmala": 2,
+         "gauss2d_pt": 2000}
+# algorithmic work per chain-step.  changepoint: 350 flop (+ 300 compares, reported
+# separately as `algo_compares_per_chain_step`, not counted as flop).
+ALGO_FLOP = {"changepoint": 350.0, "gauss2d_rw": 40.0, "gauss1000_mala": 2.0e6,
              "logistic_mala": 4.0e8, "logistic_mmala": 4.4e8, "gauss2d_pt": 40.0}
+ALGO_COMPARES = {"changepoint": 300.0}
+
+# The `configs` array of the default line: (key, workload, precision, sharding, iters/step, steps).
+#   sharding "strong": BASELINE's total chain count split over the ranks; "weak": per-GPU count; "replica": K = 1.
+SUBCONFIGS = [
+    ("gauss2d_rw_k1", "gauss2d_rw", "f64", "replica", 10000, 5),
+    ("gauss2d_rw", "gauss2d_rw", "f64", "weak", 2000, 5),
+    ("gauss1000_mala_f64", "gauss1000_mala", "f64", "strong", 20, 5),
+    ("gauss1000_mala_tf32x3", "gauss1000_mala", "tf32x3", "strong", 20, 5),
+    ("logistic_mala_f64", "logistic_mala", "f64", "strong", 1, 4),
+    ("logistic_mala_tf32x3", "logistic_mala", "tf32x3", "strong", 1, 4),
+    ("logistic_mmala_f64", "logistic_mmala", "f64", "strong", 1, 4),
+    ("logistic_mmala_tf32x3", "logistic_mmala", "tf32x3", "strong", 1, 4),
+]
+
+# From the committed ncu captures (`ncu --set full`, one launch of the dominant kernel): DRAM bytes per launch and
+# pipe/issue utilisation.  STATIC evidence, reported under roofline.profiled only -- the live numbers of a run are
+# `value`, `ms_per_step`, `roofline.achieved`.
+PROFILED_FILE = os.path.join(ROOT, "profiles", "profiled_kernels.json")
 
 
-# From the committed ncu captures (profiles/r1_*.md; `ncu --set full`, one launch of the dominant
-# kernel on this code): DRAM bytes per launch and the pipe/issue utilisation.  Static evidence,
-# NOT re-measured by this script -- the live numbers of a run are `value`, `ms_per_step`, `roofline.achieved`.
-PROFILED = {
-    ("gauss2d_rw", "f64"): {"kernel": "small_gauss_kernel<2,0,0,0>", "traffic": 92.7e6 + 36.6e6, "issue_slot_util": 0.652,
-                            "fp64_pipe_active": 0.281, "source": "profiles/r1_gauss2d_small_gauss.md"},
-    ("changepoint", "f64"): {"kernel": "changepoint_kernel<0,2,4>", "traffic": 27.58e6 + 0.07e6, "issue_slot_util": 0.673,
-                             "fp64_pipe_active": 0.219, "warp_inst_per_chain_step": 159, "source": "profiles/r1_changepoint_gl4.md"},
-    ("gauss1000_mala", "f64"): {"kernel": "gemm_abt_kernel<1>", "traffic": 455.6e6 + 125.1e6, "tensor_pipe_active": 0.770,
-                                "source": "profiles/r1_gauss1000.md"},
-    ("gauss1000_mala", "tf32x3"): {"kernel": "tf32x3_gemm_kernel<0,3>", "traffic": 144.8e6 + 42.0e6, "tensor_pipe_active": 0.855,
-                                   "source": "profiles/r1_gauss1000_tf32x3_gemm.md"},
-    ("logistic_mala", "f64"): {"kernel": "lg_eval_kernel", "traffic": 812.9e6 + 7.9e6, "tensor_pipe_active": 0.683,
-                               "source": "profiles/r1_logistic.md"},
-    ("logistic_mmala", "f64"): {"kernel": "lg_metric_kernel", "traffic": 149.1e6 + 104.5e6, "tensor_pipe_active": 0.687,
-                                "source": "profiles/r1_mmala_metric_f64.md"},
-    ("logistic_mmala", "tf32-metric"): {"kernel": "tf32x3_gemm_kernel<0,1> (metric GEMM; lg_eval_kernel is the larger share of the step)",
-                                        "traffic": 3398.4e6 + 22.5e6, "tensor_pipe_active": 0.953,
-                                        "source": "profiles/r1_mmala_metric_tf32_gemm.md"},
-}
+def load_profiled():
+    try:
+        with open(PROFILED_FILE) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def load_peaks():
@@ -89,61 +110,154 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------
-# CPU baseline: the numpy port of the reference Sampler (oracle/), one chain per core
+# CPU arm: the unmodified reference (oracle/_ref via refshim) or the numpy port, one chain per core
 # ----------------------------------------------------------------------------
+def cpu_kind(workload):
+    """'reference' where the reference contains the model and its staged copy is present, else 'port'."""
+    if workload in ("changepoint", "gauss2d_rw", "gauss1000_mala"):
+        from oracle import refshim
+        if refshim.reference_available():
+            return "reference"
+    return "port"
+
+
+def _cp_functionals(thetas, xq):
+    """sigma, k, y_hat(x_q) (changepoint.py:175-181) of a list of ChangepointParams -> [n, 2 + len(xq)]."""
+    out = np.empty((len(thetas), 2 + len(xq)))
+    for i, th in enumerate(thetas):
+        cpx = np.atleast_1d(np.asarray(th.cpx, dtype=np.float64))
+        cpv = np.atleast_1d(np.asarray(th.cpv, dtype=np.float64))
+        out[i, 0] = float(np.squeeze(th.sig))
+        out[i, 1] = len(cpx)
+        out[i, 2:] = cpv[np.searchsorted(cpx, xq)]
+    return out
+
+
+def _vec_functionals(thetas):
+    th = np.asarray(thetas, dtype=np.float64).reshape(len(thetas), -1)
+    if th.shape[1] <= 8:
+        return th
+    return np.concatenate([th[:, :7], th.mean(axis=1, keepdims=True)], axis=1)
+
+
 def _cpu_worker(args):
-    workload, seed, budget_s = args
+    workload, seed, budget_s, kind = args
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
     import numpy as np
-    from oracle import riemann_port as port
+    from riemann_b200 import synthetic
     np.random.seed(seed)
-    if workload == "changepoint":
-        model, prop, th0, _ = port.make_changepoint_problem()
-        chunk = 500
-    elif workload == "gauss2d_rw":
-        model = port.benchmark_gauss(2)
-        prop = port.MetropolisRandomWalk(0.5 * np.eye(2))
-        th0 = np.ones(2)
-        chunk = 2000
-    elif workload == "gauss1000_mala":
-        model = port.benchmark_gauss(1000)
-        prop = port.MALA(0.08, model.grad_log_likelihood)
-        th0 = np.zeros(1000)
-        chunk = 5
+    quiet = None
+    if kind == "reference":
+        from oracle import refshim
+        R = refshim.load_reference()
+        quiet = refshim.quiet
+        if workload == "changepoint":
+            c = synthetic.changepoint_problem()
+            model = R.ChangepointRegression1D(c["x"], c["y"], c["xmin"], c["xmax"], c["lamb"], c["kmax"],
+                                              c["alpha"], c["beta"])
+            prop = R.ChangepointRegression1DProp(model, c["hscale"])
+            th0 = R.ChangepointParams(np.array(c["theta0"][0]), np.array(c["theta0"][1]), c["theta0"][2])
+            chunk = 500
+        elif workload == "gauss2d_rw":
+            model = R.benchmarks.benchmark_gauss2d_corr
+            prop = R.MetropolisRandomWalk(0.5 * np.eye(2))
+            th0 = np.ones(2)
+            chunk = 2000
+        else:
+            model = R.MultiGaussianDist(np.zeros(1000), 0.1 * np.eye(1000) + 0.9 * np.ones((1000, 1000)))
+            prop = R.VanillaHMC(0.08, 1, model.grad_log_likelihood)         # = MALA (hamiltonian.py:55-91)
+            th0 = np.zeros(1000)
+            chunk = 2
+        s = R.Sampler(model, prop, th0)
     else:
-        N, d = (100000, 64) if workload == "logistic_mmala" else (1000000, 100)
-        X, y, ts, pv = port.make_logistic_problem(N, d)
-        model = port.LogisticRegression(X, y, pv)
-        prop = (port.SimplifiedMMALA(0.5, model) if workload == "logistic_mmala"
-                else port.MALA(0.02, model.grad_log_posterior))
-        th0 = ts.copy()
-        chunk = 1
-    s = port.Sampler(model, prop, th0)
-    n = 0
-    trace = []
-    t0 = time.perf_counter()
-    with np.errstate(all="ignore"):
-        while time.perf_counter() - t0 < budget_s:
-            s.run(chunk)
+        from oracle import riemann_port as port
+        if workload == "changepoint":
+            model, prop, th0, _ = port.make_changepoint_problem()
+            chunk = 500
+        elif workload == "gauss2d_rw":
+            model, prop, th0, chunk = port.benchmark_gauss(2), port.MetropolisRandomWalk(0.5 * np.eye(2)), np.ones(2), 2000
+        elif workload == "gauss1000_mala":
+            model = port.benchmark_gauss(1000)
+            prop, th0, chunk = port.MALA(0.08, model.grad_log_likelihood), np.zeros(1000), 5
+        else:
+            N, d = (100000, 64) if workload == "logistic_mmala" else (1000000, 100)
+            X, y, ts, pv = port.make_logistic_problem(N, d)
+            model = port.LogisticRegression(X, y, pv)
+            prop = (port.SimplifiedMMALA(0.5, model) if workload == "logistic_mmala"
+                    else port.MALA(0.02, model.grad_log_posterior))
+            th0, chunk = ts.copy(), 1
+        s = port.Sampler(model, prop, th0)
+    xq = None
+    if workload == "changepoint":
+        c = synthetic.changepoint_problem()
+        xq = c["xmin"] + (c["xmax"] - c["xmin"]) * (np.arange(6) + 0.5) / 6.0
+    n, spent, funcs = 0, 0.0, []
+    import contextlib
+    with np.errstate(all="ignore"), (quiet() if quiet else contextlib.nullcontext()):
+        while spent < budget_s:
+            t0 = time.perf_counter()
+            s.run(chunk)                                   # Sampler.run (sampler.py:44-54): chunk x Sampler.sample
+            spent += time.perf_counter() - t0
             n += chunk
-            if workload == "changepoint":
-                trace.append(s._chain_thetas[-1].sig)
-    return n, time.perf_counter() - t0
+            new = s._chain_thetas[1:]                      # run() keeps [last state] + the chunk
+            funcs.append(_cp_functionals(new, xq) if xq is not None else _vec_functionals(new))
+    return n, spent, np.concatenate(funcs, axis=0)
 
 
-def cpu_baseline(workload, budget_s=12.0, cores=None):
+def chain_ess(funcs_list, wall, names):
+    """Sokal-window tau (emcee's estimator, examples/test_randomwalk.py:42; riemann_b200/diagnostics.py) with the
+    chains as walkers, and the moment-based tau = n B / W, of traced chains [n, chains, nf]."""
+    from riemann_b200 import diagnostics as dgn
+    n = min(f.shape[0] for f in funcs_list)
+    if n < 64:
+        return {"min_ess_per_sec": None, "reason": "only %d steps per chain in the sample" % n}
+    x = np.stack([f[:n] for f in funcs_list], axis=1)                  # [n, chains, nf]
+    with np.errstate(all="ignore"):
+        tau = dgn.integrated_time_chains(x)
+        m, v = x.mean(axis=0), x.var(axis=0, ddof=1)
+        B, W = m.var(axis=0, ddof=1) if x.shape[1] > 1 else np.full(x.shape[2], np.nan), v.mean(axis=0)
+        tau_m = n * B / W
+    tmax = float(np.nanmax(tau))
+    chains = x.shape[1]
+    out = {"estimator": "Sokal window (c = 5), ACF averaged over the chains; tau in MH steps",
+           "functionals": names, "sokal_tau_steps": [float(t) for t in tau],
+           "moment_tau_steps": [float(t) for t in tau_m], "steps_per_chain": int(n), "chains": int(chains),
+           "window_over_tau": n / tmax, "reliable": bool(n >= 50 * tmax),
+           "min_ess": chains * n / tmax, "min_ess_per_sec": chains * n / tmax / wall}
+    if not out["reliable"]:
+        out["reason"] = "chain length is %.1f tau of the slowest functional (< 50 tau: emcee would refuse)" % (n / tmax)
+    return out
+
+
+FUNC_NAMES = {"changepoint": ["sigma", "k"] + ["yhat(xq%d)" % q for q in range(6)],
+              "gauss2d_rw": ["theta0", "theta1"]}
+
+
+def cpu_baseline(workload, budget_s=12.0, cores=None, with_ess=True):
     import multiprocessing as mp
     cores = cores or len(os.sched_getaffinity(0))
+    if workload.startswith("logistic"):
+        cores = min(cores, 16)                           # every worker builds its own copy of X (0.8 GB at config 4)
+    kind = cpu_kind(workload)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(workload, 1000 + i, budget_s) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(workload, 1000 + i, budget_s, kind) for i in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
-    return {"value": steps / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d independent chains (one per host core) of the numpy restatement of "
-                      "riemann's Sampler.sample on the same synthetic %s problem, %.0f s each, "
-                      "%d chain-steps total" % (cores, workload, budget_s, steps)}
+    what = ("the UNMODIFIED reference (riemann/samplers/sampler.py:44-90 via oracle/refshim.py)" if kind == "reference"
+            else "the numpy restatement of riemann's Sampler.sample (oracle/riemann_port.py; the reference has no such model)")
+    out = {"value": steps / wall, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "%d independent chains (one per host core) of %s on the same synthetic %s problem, %.1f s each, "
+                     "%d chain-steps total" % (cores, what, workload, budget_s, steps)}
+    if with_ess:
+        names = FUNC_NAMES.get(workload, ["theta%d" % j for j in range(7)] + ["mean(theta)"])
+        e = chain_ess([r[2] for r in res], wall, names[:res[0][2].shape[1]])
+        out["ess"] = e
+        out["min_ess_per_sec"] = e.get("min_ess_per_sec") if e.get("reliable") else None
+        if out["min_ess_per_sec"] is None:
+            out["min_ess_per_sec_unreliable"] = e.get("min_ess_per_sec")
+    return out
 
 
 # ----------------------------------------------------------------------------
@@ -151,7 +265,7 @@ def cpu_baseline(workload, budget_s=12.0, cores=None):
 # ----------------------------------------------------------------------------
 class ClockSampler(object):
     """nvidia-smi sampled every 50 ms in the background; started BEFORE warm-up (the tool needs
-    a few hundred ms to come up) and filtered to the wall-clock window of the timed region."""
+    a few hundred ms to come up) and filtered to the wall-clock windows of the timed regions."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -159,7 +273,7 @@ class ClockSampler(object):
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
-        self.t0 = self.t1 = None
+        self.rows = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "50", "-i", str(gpu_index)], stdout=self.f,
@@ -167,17 +281,12 @@ class ClockSampler(object):
         except Exception:
             self.p = None
 
-    def begin(self):
-        self.t0 = time.time()
-
-    def end(self):
-        self.t1 = time.time()
-
     def stop(self):
+        """Terminate the sampler and parse its log (call once, after the last timed region)."""
         import datetime
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.rows = []
         if self.p is None:
-            return out
+            return
         time.sleep(0.12)
         self.p.terminate()
         try:
@@ -187,23 +296,25 @@ class ClockSampler(object):
         self.f.flush()
         self.f.seek(0)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = []
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
                 ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(parts[1]), float(parts[2]),
-                             [nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
+                self.rows.append((ts, float(parts[1]), float(parts[2]),
+                                  [nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
         self.f.close()
         os.unlink(self.f.name)
-        inwin = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
-        use = inwin
-        if not use and rows and self.t0 is not None:          # window shorter than the sampling period
-            mid = 0.5 * (self.t0 + self.t1)
+
+    def window(self, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        rows = self.rows or []
+        use = [r for r in rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+        if not use and rows:                                   # window shorter than the sampling period
+            mid = 0.5 * (t0 + t1)
             use = sorted(rows, key=lambda r: abs(r[0] - mid))[:2]
             out["note"] = "timed window shorter than the 50 ms sampling period: nearest samples used"
         if use:
@@ -215,8 +326,24 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------
+_DATA_CACHE = {}
+
+
+def _logistic_model(N, d):
+    """One device copy of the synthetic design matrix per (N, d), shared by the precisions of a config."""
+    from riemann_b200 import synthetic
+    from riemann_b200.models.logistic import LogisticRegression
+    key = ("logistic", N, d)
+    if key not in _DATA_CACHE:
+        X, y, ts, pv = synthetic.logistic_problem(N, d)
+        _DATA_CACHE.clear()                                # at most one data set resident
+        _DATA_CACHE[key] = (LogisticRegression(X, y, pv), ts)
+    return _DATA_CACHE[key]
+
+
 def build_workload(name, K, seed, chain_offset, precision="f64"):
-    """Returns (sampler, host_inputs dict for the e2e leg, description)."""
+    """Returns (sampler, description).  Start states are keyed by GLOBAL chain id, so a shard is the
+    corresponding slice of the one-GPU problem."""
     from riemann_b200 import Sampler, synthetic    # synthetic-input recipes (SURVEY 8d); the engine arm never imports oracle/
     if name == "changepoint":
         from riemann_b200.models.changepoint import ChangepointParams, ChangepointRegression1D
@@ -249,18 +376,16 @@ def build_workload(name, K, seed, chain_offset, precision="f64"):
         from riemann_b200.models import benchmarks
         from riemann_b200.proposals.hamiltonian import MALA
         m = benchmarks.gauss_corr(1000)
-        rng = np.random.Generator(np.random.Philox(synthetic.SEED_BASE + 3))
+        rng = np.random.Generator(np.random.Philox(key=[synthetic.SEED_BASE + 3, chain_offset]))
         th0 = rng.standard_normal((K, 1000))
         s = Sampler(m, MALA(0.08, m.grad_log_likelihood), th0, seed=seed, chain_offset=chain_offset,
                     precision=precision)
         return s, "dense Gaussian d=1000 (0.1 I + 0.9 11^T), MALA eps=0.08, precision " + precision
     if name in ("logistic_mala", "logistic_mmala"):
-        from riemann_b200.models.logistic import LogisticRegression
         from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA
         N, d = (100000, 64) if name == "logistic_mmala" else (1000000, 100)
-        X, y, ts, pv = synthetic.logistic_problem(N, d)
-        m = LogisticRegression(X, y, pv)
-        rng = np.random.Generator(np.random.Philox(synthetic.SEED_BASE + 5))
+        m, ts = _logistic_model(N, d)
+        rng = np.random.Generator(np.random.Philox(key=[synthetic.SEED_BASE + 5, chain_offset]))
         th0 = ts[None, :] + 0.01 * rng.standard_normal((K, d))
         prop = SimplifiedMMALA(0.5, m) if name == "logistic_mmala" else MALA(0.02, m.grad_log_posterior)
         if precision == "tf32-metric" and name != "logistic_mmala":
@@ -269,66 +394,139 @@ def build_workload(name, K, seed, chain_offset, precision="f64"):
         return s, "logistic regression N=%d d=%d, %s%s" % (
             N, d, "simplified mMALA" if "mm" in name else "MALA",
             {"f64": "", "tf32-metric": ", Fisher metric on tcgen05 (TF32 GEMM)",
-             "tf32x3": ", likelihood sweep on tcgen05 (3xTF32 GEMMs, fp64 pointwise stage)"}[precision])
+             "tf32x3": ", likelihood sweep on tcgen05"}[precision])
     raise SystemExit("unknown workload %r" % name)
 
 
-def run_engine(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import __graft_entry__ as ge
-    if rank == 0 and not os.path.exists(ge.OUT):
-        ge.build()
-    if world > 1:
-        dist.barrier()
+DTYPE_NOTE = {"f64": "f64",
+              "tf32x3": "tf32x3 tensor-core products (fp32-accurate), f64 accept test",
+              "tf32-metric": "f64 (proposal metric: tf32 tensor cores)"}
+
+
+class Ctx(object):
+    """Process-wide measurement context: rank / world, stream, L2 flush buffer, clock sampler."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        import __graft_entry__ as ge
+        if self.rank == 0 and not os.path.exists(ge.OUT):
+            ge.build()
+        if self.world > 1:
+            dist.barrier()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        self.clocks = ClockSampler(self.local) if self.rank == 0 else None
+        self.peaks, self.peak_src = load_peaks()
+        self.profiled = load_profiled()
+        self.windows = []
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def roofline_for(ctx, wl, precision, Kg, T, steps, kt, ms):
+    """roofline.achieved = ALGORITHMIC work of the timed region / the dominant kernel's OWN time in it
+    (CUDA events on the launching stream, rmn_sampler_kernel_timing); the kernel's share of the step is
+    reported next to it and must agree with the ncu launch list under profiles/."""
+    peaks, extra = ctx.peaks, ctx.peaks.get("extra", {})
+    algo_flop_step = ALGO_FLOP[wl] * Kg * T              # per bench step, per GPU
+    if wl == "logistic_mmala" and precision == "tf32-metric":
+        algo_flop_step = 4.0 * 100000 * 64 * Kg * T      # lg_eval_kernel's part: logits + gradient, 4 N d
+    kernel_ms = kt["total_ms"] if kt["launches"] > 0 else ms
+    ach = algo_flop_step * steps / (kernel_ms * 1e-3) / 1e12
+    computed_fp64 = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12      # fp64 FMA lanes x clock
+    if wl in ("changepoint", "gauss2d_rw", "gauss2d_pt"):
+        peak = extra.get("fp64_dfma_tflops", computed_fp64)
+        roof = {"bound": "alu", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "algo_flop_per_chain_step": ALGO_FLOP[wl],
+                "note": "issue-bound fp64/integer kernel (SURVEY 8d: not HBM, not tensor, ~0 algorithmic HBM bytes); achieved = "
+                        "%.0f algorithmic flop/chain-step x rate against the fp64 DFMA rate %s; the binding resource is "
+                        "the warp-instruction issue rate, see `profiled` (issue-slot utilisation, instructions per "
+                        "chain-step from ncu)"
+                        % (ALGO_FLOP[wl], "measured by scripts/peaks (profiles/measured_peaks_extra.json)"
+                           if "fp64_dfma_tflops" in extra else "computed as 148 SM x 64 lanes x 2 x clocks.max.sm")}
+        if wl in ALGO_COMPARES:
+            roof["algo_compares_per_chain_step"] = ALGO_COMPARES[wl]
+    elif precision == "tf32-metric" and wl == "logistic_mmala":
+        peak = extra.get("fp64_dmma_tflops", computed_fp64)
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "note": "dominant kernel = lg_eval_kernel (fp64 DMMA, 4 N d = 2.6e7 flop per chain-step) against the "
+                        "measured DMMA peak; the metric GEMM (4.2e8 flop per chain-step) runs on tcgen05 in TF32"}
+    elif precision == "tf32x3" and wl.startswith("logistic"):
+        peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
+        n_, d_ = (100000, 64) if wl == "logistic_mmala" else (1000000, 100)
+        ach = 4.0 * n_ * d_ * Kg * T * steps / (kernel_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "note": "likelihood sweep on tcgen05, timed as a whole (CUDA events around its launches); achieved counts "
+                        "the ALGORITHMIC 4 N d flop per chain-step once (3 TF32 MMAs are issued per fp32-accurate product "
+                        "and the d-wide gradient tile fills d/256 of the MMA's N), against the cuBLAS TF32 peak"}
+    elif precision == "tf32x3":
+        peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "note": "tcgen05 kind::tf32, 3 MMAs per product (fp32-accurate): achieved counts the ALGORITHMIC "
+                        "2 d^2 flop per chain-step once, so 1/3 is the ceiling of this scheme; peak = %s"
+                        % ("cuBLAS TF32 8192^3 measured by scripts/peaks (profiles/measured_peaks_extra.json)"
+                           if "tf32_cublas_tflops" in extra else "half the %s bf16 figure of MEASURED_PEAKS.json" % ctx.peak_src)}
+    else:
+        peak = extra.get("fp64_dmma_tflops", computed_fp64)
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "note": "fp64 tensor path (DMMA m8n8k4); peak = %s"
+                        % ("mma.sync.m8n8k4.f64 rate measured by scripts/peaks (profiles/measured_peaks_extra.json)"
+                           if "fp64_dmma_tflops" in extra else "computed 148 SM x 64 lanes x 2 x clocks.max.sm")}
+    roof["kernel"] = kt["kernel"]
+    roof["kernel_launches"] = kt["launches"]
+    roof["kernel_ms_per_launch"] = kernel_ms / max(kt["launches"], 1)
+    roof["kernel_share_of_step"] = kernel_ms / ms if ms > 0 else None
+    prof = ctx.profiled.get("%s/%s" % (wl, precision))
+    if prof:
+        roof["profiled"] = prof            # static ncu evidence (DRAM bytes per launch, pipe utilisation), with its source file
+    return roof
+
+
+def measure(ctx, wl, precision, Kg, T, steps, warmup, burn, chain_offset, K_total, scaling, cpu_seconds=0.0, e2e=True):
+    """One workload on this rank's shard: burn-in, warm-up, `steps` timed launches (CUDA events, L2 flush between
+    them), split-chain diagnostics over the two halves of the timed region, the end-to-end leg, roofline."""
+    torch = ctx.torch
     from riemann_b200 import _lib
     from riemann_b200.distributed import reduce_block, summarize_block, summarize_split
-
-    wl = args.workload
-    Kg = args.chains or CHAINS_PER_GPU[wl]
-    T = args.iters or {"changepoint": 1000, "gauss2d_rw": 2000, "gauss1000_mala": 20,
-                       "logistic_mala": 2, "logistic_mmala": 2, "gauss2d_pt": 2000}[wl]
-    seed = 20261018
-    s, desc = build_workload(wl, Kg, seed, rank * Kg, args.precision)
+    s, desc = build_workload(wl, Kg, SEED, chain_offset, precision)
     stream = torch.cuda.current_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # burn-in (untimed setup), then warm-up steps
-    clocks = ClockSampler(local) if rank == 0 else None
-    burn = args.burn if args.burn is not None else {"changepoint": 10000}.get(wl, 2 * T)
+    lib = _lib.load()
     s.run(burn, trace=False)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         s.run(T, trace=False)
         blk = reduce_block(s.diagnostics_block())
     s.reset_diagnostics()
-    sync_all()
-
-    lib = _lib.load()
+    ctx.sync_all()
     launches0 = s.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     s.enable_kernel_timing(True)                   # CUDA events around the dominant kernel's launches
-    sync_all()
-    if clocks:
-        clocks.begin()
-    half = args.steps // 2 if args.steps >= 2 and args.steps % 2 == 0 else 0
+    ctx.sync_all()
+    w0 = time.time()
+    half = steps // 2 if steps >= 2 and steps % 2 == 0 else 0
     blk_first = None
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)                      # L2 flush, outside the event pair
+    for i in range(steps):
+        ctx.flush.fill_(i & 0xff)                  # L2 flush, outside the event pair
         if half and i == half:                     # second half-window of the split-chain diagnostics
             blk_first = blk.clone()
             s.reset_diagnostics()
@@ -337,21 +535,15 @@ def run_engine(args):
         s.total_steps += T
         blk = reduce_block(s.diagnostics_block())  # per-batch diagnostics all-reduce (NCCL)
         ev[i][1].record(stream)
-    sync_all()
-    if clocks:
-        clocks.end()
+    ctx.sync_all()
+    w1 = time.time()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     kt = s.kernel_timing()                         # dominant kernel only: total ms / launches in the timed region
     s.enable_kernel_timing(False)
-    clk = clocks.stop() if clocks else None
     launches = s.launch_count - launches0
-    t_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    ms = float(t_all.item())
-    diag = None
+    ms = ctx.max_over_ranks(ms)
+    diag, diag_kind = None, "whole window"
     if blk_first is not None:
-        # split-chain diagnostics over the two halves of the timed region (split-R-hat, ESS of 2K half-chains)
         try:
             diag = summarize_split(blk_first.cpu().numpy(), blk.cpu().numpy())
             diag_kind = "split: %d half-chains of %d MH steps" % (diag["chains"], diag["steps"])
@@ -359,134 +551,37 @@ def run_engine(args):
             diag = None
     if diag is None:
         diag = summarize_block(blk.cpu().numpy())
-        diag_kind = "whole window"
-    K_total = Kg * world
-    value = K_total * T * args.steps / (ms * 1e-3)
-
-    # ---- end-to-end leg: host buffers in, host results out, copies inside the timed region
-    e2e = run_e2e(args, s, T, Kg, world, sync_all)
-
-    # ---- estimator cross-check (outside every timed region): Sokal-window integrated autocorrelation time
-    #      (emcee's estimator, examples/test_randomwalk.py:42) of a traced subset of chains next to the
-    #      moment-based tau = n B / W of the diagnostics block that min_ess_per_sec is computed from
-    tau_check = None
-    if rank == 0 and wl == "changepoint":
-        from riemann_b200 import diagnostics as dgn
-        s2, _ = build_workload(wl, 128, seed + 1, 0, args.precision)
-        s2.run(burn, trace=False)
-        s2.run(8000, 0, 1)
-        tr = s2._chain_thetas
-        x = np.stack([tr.sig[1:], tr.k[1:].astype(np.float64)], axis=2)          # [N, K, 2]: sigma, k
-        # RMN_BENCH_DEVICE_TAU=1: the same estimator on the GPU (rmn_autocorr_tau); host FFT by default
-        tau_s = dgn.integrated_time_chains(x, device=os.environ.get("RMN_BENCH_DEVICE_TAU", "0") == "1")
-        tau_m = diag["tau"][:2]
-        tau_check = {"functionals": ["sigma", "k"], "sokal_tau_steps": [float(t) for t in tau_s],
-                     "moment_tau_steps": [float(t) for t in tau_m],
-                     "note": "Sokal tau (c = 5) of 128 traced chains x 8000 steps vs tau = n B / W of the "
-                             "%d bench chains (MH steps per independent sample)" % K_total}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    peaks, peak_src = load_peaks()
-    ms_launch = ms / args.steps
-    # roofline.achieved = ALGORITHMIC work of the timed region / the dominant kernel's OWN time in it
-    # (CUDA events on the launching stream, rmn_sampler_kernel_timing); the kernel's share of the step is
-    # reported next to it and must agree with the ncu launch list under profiles/.
-    algo_flop_step = ALGO_FLOP[wl] * Kg * T              # per bench step, per GPU
-    if wl == "logistic_mmala" and args.precision == "tf32-metric":
-        algo_flop_step = 4.0 * 100000 * 64 * Kg * T      # lg_eval_kernel's part: logits + gradient, 4 N d
-    kernel_ms = kt["total_ms"] if kt["launches"] > 0 else ms
-    ach_tflops = algo_flop_step * args.steps / (kernel_ms * 1e-3) / 1e12
-    extra = peaks.get("extra", {})
-    computed_fp64 = 148 * 64 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12      # fp64 FMA lanes x clock
-    if wl in ("changepoint", "gauss2d_rw", "gauss2d_pt"):
-        peak = extra.get("fp64_dfma_tflops", computed_fp64)
-        roof = {"bound": "alu", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / peak, "traffic": None,
-                "note": "issue-bound fp64/integer kernel (SURVEY 8d: not HBM, not tensor); achieved = "
-                        "%.0f algorithmic op/chain-step x rate; peak = fp64 DFMA rate %s; the binding resource "
-                        "is the warp-instruction issue rate, see `profiled` (issue-slot utilisation from ncu)"
-                        % (ALGO_FLOP[wl], "measured by scripts/peaks (profiles/measured_peaks_extra.json)"
-                           if "fp64_dfma_tflops" in extra else "computed as 148 SM x 64 lanes x 2 x clocks.max.sm")}
-    elif args.precision == "tf32-metric" and wl == "logistic_mmala":
-        peak = extra.get("fp64_dmma_tflops", computed_fp64)
-        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / peak, "traffic": None,
-                "note": "dominant kernel = lg_eval_kernel (fp64 DMMA, 4 N d = 2.6e7 flop per chain-step) against the "
-                        "measured DMMA peak; the metric GEMM (4.2e8 flop per chain-step) runs on tcgen05 in TF32 at 95 % "
-                        "tensor-pipe utilisation (profiles/r1_mmala_metric_tf32_gemm.md) and is the smaller share of the step"}
-    elif args.precision == "tf32x3" and wl.startswith("logistic"):
-        peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
-        n_, d_ = (100000, 64) if wl == "logistic_mmala" else (1000000, 100)
-        ach_tflops = 4.0 * n_ * d_ * Kg * T * args.steps / (kernel_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / peak, "traffic": None,
-                "note": "likelihood sweep = logits GEMM + fp64 pointwise kernel + split-K gradient GEMM, timed together "
-                        "(CUDA events around the three launches); achieved counts the ALGORITHMIC 4 N d flop per chain-step "
-                        "once (3 TF32 MMAs are issued per product, and the d-wide gradient tile fills 100/256 resp. 64/256 "
-                        "of the MMA's N), so the fraction of the cuBLAS TF32 peak is small by construction; the sweep is "
-                        "bounded by the fp64 pointwise stage and the 12 B/(chain,row) of Z/R traffic"}
-    elif args.precision == "tf32x3":
-        peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
-        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / peak, "traffic": None,
-                "note": "tcgen05 kind::tf32, 3 MMAs per product (fp32-accurate): achieved counts the ALGORITHMIC "
-                        "2 d^2 flop per chain-step once, so 1/3 is the ceiling of this scheme; peak = %s"
-                        % ("cuBLAS TF32 8192^3 measured by scripts/peaks (profiles/measured_peaks_extra.json)"
-                           if "tf32_cublas_tflops" in extra else "half the %s bf16 figure of MEASURED_PEAKS.json" % peak_src)}
-    else:
-        peak = extra.get("fp64_dmma_tflops", computed_fp64)
-        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / peak, "traffic": None,
-                "note": "fp64 tensor path (DMMA m8n8k4); peak = %s (bf16 %s peak %.0f TF/s for context only)"
-                        % ("mma.sync.m8n8k4.f64 rate measured by scripts/peaks (profiles/measured_peaks_extra.json)"
-                           if "fp64_dmma_tflops" in extra else "computed 148 SM x 64 lanes x 2 x clocks.max.sm",
-                           peak_src, peaks["bf16_tflops"])}
-    roof["kernel"] = kt["kernel"]
-    roof["kernel_launches"] = kt["launches"]
-    roof["kernel_ms_per_launch"] = kernel_ms / max(kt["launches"], 1)
-    roof["kernel_share_of_step"] = kernel_ms / ms if ms > 0 else None
-    prof = PROFILED.get((wl, args.precision))
-    if prof:
-        roof["traffic"] = prof["traffic"]
-        roof["profiled"] = prof
-    cpu = None if args.no_cpu else cpu_baseline(wl, args.cpu_seconds)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_launch, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": {"f64": "f64", "tf32x3": ("tf32x3 likelihood GEMMs, f64 pointwise + accept test" if wl.startswith("logistic")
-                                                                       else "tf32x3/f32 state, f64 accept test"),
-                                                            "tf32-metric": "f64 (proposal metric: tf32 tensor cores)"}[args.precision],
-        "data": "synthetic",
-        "config": {"workload": "%s: %s; %d chains/GPU x %d MH iterations per step; Philox4x32-10 RNG; "
-                               "L2 flushed (256 MiB write) between steps, per-step CUDA events summed"
-                               % (wl, desc, Kg, T),
-                   "chains_per_gpu": Kg, "chains_total": K_total, "iters_per_step": T,
-                   "burn_in_iters": burn, "parallelism": "chains sharded, dp%d" % world},
-        "min_ess_per_sec": (diag["min_ess"] * 1.0) / (ms * 1e-3) if np.isfinite(diag["min_ess"]) else None,
-        "diagnostics": {"estimator": diag_kind, "accept_rate": diag["accept_rate"], "max_rhat": float(np.nanmax(diag["rhat"])),
-                        "min_ess": diag["min_ess"], "overflows": diag["overflows"],
-                        "chains": diag["chains"], "steps_per_chain": diag["steps"]},
-        "tau_check": tau_check,
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-        "clocks": clk, "peaks_source": peak_src,
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    nworld = 1 if scaling == "replica" else ctx.world
+    value = Kg * nworld * T * steps / (ms * 1e-3)
+    e2e_d = run_e2e(ctx, s, T, Kg, nworld, steps) if e2e else None
+    out = {"workload": wl, "precision": precision, "value": value, "unit": UNIT, "ms_per_step": ms / steps,
+           "steps": steps, "warmup": max(warmup, 3), "scaling": scaling, "dtype": DTYPE_NOTE[precision],
+           "chains_per_gpu": Kg, "chains_total": Kg * nworld, "iters_per_step": T, "burn_in_iters": burn,
+           "desc": desc, "e2e": e2e_d, "gpu_launches": int(launches), "window": (w0, w1)}
+    rhat = float(np.nanmax(diag["rhat"])) if np.any(np.isfinite(diag["rhat"])) else None
+    ess_ok = rhat is not None and rhat < 1.05 and np.isfinite(diag["min_ess"])
+    out["min_ess_per_sec"] = diag["min_ess"] / (ms * 1e-3) if ess_ok else None
+    out["diagnostics"] = {"estimator": diag_kind + "; tau = n B / W over all chains", "accept_rate": diag["accept_rate"],
+                          "max_rhat": rhat, "min_ess": diag["min_ess"] if np.isfinite(diag["min_ess"]) else None,
+                          "overflows": diag["overflows"], "chains": diag["chains"], "steps_per_chain": diag["steps"]}
+    if not ess_ok:
+        out["diagnostics"]["min_ess_reason"] = ("split-R-hat %.3f >= 1.05 over the timed window (%d MH steps per half): "
+                                               "the window is shorter than ~10 tau of the slowest functional"
+                                               % (rhat, diag["steps"]) if rhat is not None else "no finite R-hat")
+    if ctx.rank == 0:
+        out["roofline"] = roofline_for(ctx, wl, precision, Kg, T, steps, kt, ms)
+    out["_sampler"] = s
+    return out
 
 
-def run_e2e(args, s, T, Kg, world, sync_all):
+def run_e2e(ctx, s, T, Kg, nworld, steps):
     """Same metric through the public API with HOST buffers: every step uploads the chains'
     start states from pinned host memory, runs T iterations, and reads states, log-posteriors
     and the diagnostics block back to the host."""
-    import torch
-    import torch.distributed as dist
+    torch = ctx.torch
     from riemann_b200 import _lib
     lib = _lib.load()
-    steps = max(2, min(args.steps, 5))
+    steps = max(2, min(steps, 5))
     if s._is_cp:
         (k, cpx, cpv, sig), lp = s._download_state()
         host_in = [torch.from_numpy(a).pin_memory() for a in (k, cpx, cpv, sig)]
@@ -523,45 +618,318 @@ def run_e2e(args, s, T, Kg, world, sync_all):
         torch.cuda.current_stream().synchronize()
 
     one()
-    sync_all()
+    ctx.sync_all()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
-    sync_all()
-    dt = time.perf_counter() - t0
-    t_all = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-    dt = float(t_all.item())
-    return {"value": Kg * world * T * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+    ctx.sync_all()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    return {"value": Kg * nworld * T * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "steps": steps,
             "note": "host wall clock around upload(pinned) -> set_state -> run -> get_state -> download"}
 
 
+def ess_phase(ctx, s, T, half_launches, K_total):
+    """min-ESS/sec of the changepoint workload as a measurement: two consecutive half-windows of half_launches x T
+    MH steps each, device-timed like the bench steps (the diagnostics block is reduced once per half), evaluated
+    split-chain over ALL chains.  Reported per functional with window_over_tau; min_ess_per_sec only when
+    split-R-hat < 1.05, i.e. when each half-window holds >= ~10 tau of the slowest functional."""
+    torch = ctx.torch
+    from riemann_b200 import _lib
+    from riemann_b200.distributed import reduce_block, summarize_split
+    lib = _lib.load()
+    stream = torch.cuda.current_stream()
+    blks = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.sync_all()
+    e0.record(stream)
+    for h in range(2):
+        s.reset_diagnostics()
+        for _ in range(half_launches):
+            _lib.check(lib.rmn_sampler_run(s._handle, T, None, None, _lib.stream_ptr()))
+            s.total_steps += T
+        blks.append(reduce_block(s.diagnostics_block()).clone())
+    e1.record(stream)
+    ctx.sync_all()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    d = summarize_split(blks[0].cpu().numpy(), blks[1].cpu().numpy())
+    n_half = half_launches * T
+    tau = np.asarray(d["tau"], dtype=np.float64)
+    tmax = float(np.nanmax(tau))
+    rhat = float(np.nanmax(d["rhat"]))
+    ok = rhat < 1.05
+    out = {"estimator": "split-chain moments over all %d chains: tau = n B / W, ESS = chains x n / tau; two half-windows "
+                        "of %d MH steps, device-timed (CUDA events), diagnostics all-reduce included" % (K_total, n_half),
+           "functionals": FUNC_NAMES["changepoint"], "tau_steps": [float(t) for t in tau],
+           "ess": [float(e) for e in d["ess"]], "rhat": [float(r) for r in d["rhat"]],
+           "window_steps": n_half, "window_over_tau": n_half / tmax, "max_rhat": rhat, "seconds": ms * 1e-3,
+           "min_ess": d["min_ess"], "min_ess_per_sec": d["min_ess"] / (ms * 1e-3) if ok else None,
+           "chain_steps_per_sec": K_total * 2 * n_half / (ms * 1e-3)}
+    if not ok:
+        out["reason"] = "split-R-hat %.3f >= 1.05: half-window = %.1f tau of the slowest functional" % (rhat, n_half / tmax)
+        out["min_ess_per_sec_unconverged"] = d["min_ess"] / (ms * 1e-3)
+    return out
+
+
+def sokal_check(ctx, nchains=256, nsteps=120000, thin=8, burn=60000):
+    """The reference's own estimator (emcee.autocorr.integrated_time, examples/test_randomwalk.py:42; restated in
+    riemann_b200/diagnostics.py) on a traced subset of device chains -- the same estimator and functionals the CPU arm
+    reports -- next to the moment-based tau of the full population."""
+    from riemann_b200 import diagnostics as dgn, synthetic
+    s2, _ = build_workload("changepoint", nchains, SEED + 1, 0, "f64")
+    s2.run(burn, trace=False)
+    t0 = time.perf_counter()
+    s2.run(nsteps, thin, thin)
+    dt = time.perf_counter() - t0
+    tr = s2._chain_thetas
+    c = synthetic.changepoint_problem()
+    xq = c["xmin"] + (c["xmax"] - c["xmin"]) * (np.arange(6) + 0.5) / 6.0
+    k = tr.k.astype(np.int64)                                              # [rec, K]
+    # y_hat(x_q) = cpv[#{cpx < x_q}] with the padded layout (entries >= k are not changepoints)
+    idx = np.arange(tr.cpx.shape[2])[None, None, :]
+    cols = [tr.sig, k.astype(np.float64)]
+    for q in range(6):
+        cnt = np.sum((tr.cpx < xq[q]) & (idx < k[:, :, None]), axis=2)
+        cols.append(np.take_along_axis(tr.cpv, cnt[:, :, None], axis=2)[:, :, 0])
+    x = np.stack(cols, axis=2)
+    tau = dgn.integrated_time_chains(x) * thin
+    n = x.shape[0] * thin
+    tmax = float(np.nanmax(tau))
+    return {"estimator": "Sokal window (c = 5), ACF averaged over the chains; tau in MH steps",
+            "functionals": FUNC_NAMES["changepoint"], "sokal_tau_steps": [float(t) for t in tau],
+            "chains": nchains, "steps_per_chain": n, "thin": thin, "window_over_tau": n / tmax,
+            "reliable": bool(n >= 50 * tmax), "trace_seconds": dt}
+
+
+# ----------------------------------------------------------------------------
+# multi-GPU self-checks (N >= 2, untimed)
+# ----------------------------------------------------------------------------
+def multi_gpu_checks(ctx):
+    """(1) chain-shard invariance: the N ranks' shards of a Philox run equal, bit for bit, the same chains of the
+    unsharded run (rank 0 runs all of them).  (2) row-sharded data mode: the rows of the reference-stream fixtures
+    (tests/golden/{mala,hmc3,mmala}_logistic.npz, recorded through the reference's own Sampler) are split over the N
+    ranks, the injected stream is replayed; chain within 1e-9 / 1e-8 of the recorded one, ranks bit-identical."""
+    torch, dist = ctx.torch, ctx.dist
+    from riemann_b200 import Sampler
+    from riemann_b200.distributed import shard_chains, shard_rows
+    res = {}
+    # ---- (1)
+    Ktot, Tn = 1024 * ctx.world, 300
+    off, Kl = shard_chains(Ktot, ctx.rank, ctx.world)
+    s, _ = build_workload("changepoint", Kl, SEED + 7, off, "f64")
+    s.run(Tn, trace=False)
+    (k, cpx, cpv, sig), lp = s._download_state()
+    mine = torch.as_tensor(np.concatenate([k[:, None].astype(np.float64), cpx, cpv, sig[:, None], lp[:, None]], axis=1),
+                           device="cuda")
+    parts = [torch.empty_like(mine) for _ in range(ctx.world)]
+    dist.all_gather(parts, mine)
+    ok = True
+    if ctx.rank == 0:
+        sf, _ = build_workload("changepoint", Ktot, SEED + 7, 0, "f64")
+        sf.run(Tn, trace=False)
+        (k, cpx, cpv, sig), lp = sf._download_state()
+        full = np.concatenate([k[:, None].astype(np.float64), cpx, cpv, sig[:, None], lp[:, None]], axis=1)
+        ok = bool(np.array_equal(torch.cat(parts).cpu().numpy(), full, equal_nan=True))
+        del sf
+    res["chain_shard_invariance"] = {"ok": ok, "chains": Ktot, "steps": Tn, "ranks": ctx.world,
+                                     "check": "gathered shards == unsharded run on rank 0, bitwise"}
+    del s
+    # ---- (2)
+    from riemann_b200.models.logistic import LogisticRegression
+    from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA, VanillaHMC
+    rows = {}
+    all_ok = True
+    for name, tol in (("mala_logistic", 1e-9), ("hmc3_logistic", 1e-9), ("mmala_logistic", 1e-8)):
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        if not os.path.exists(path):
+            rows[name] = "fixture missing"
+            all_ok = False
+            continue
+        g = np.load(path)
+        offr, n = shard_rows(len(g["y"]), ctx.rank, ctx.world)
+        dm = LogisticRegression(g["X"][offr:offr + n], g["y"][offr:offr + n], float(g["prior_var"]))
+        if name == "mala_logistic":
+            p = MALA(float(g["eps"]), dm.grad_log_posterior)
+        elif name == "hmc3_logistic":
+            p = VanillaHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior)
+        else:
+            p = SimplifiedMMALA(float(g["eps"]), dm)
+        sr = Sampler(dm, p, g["thetas"][0], row_sharded=True)
+        sr.run_injected(xi=g["xi"], u=g["u"])
+        th = np.array(sr._chain_thetas)
+        err = float(np.max(np.abs(th - g["thetas"]) / np.maximum(1.0, np.abs(g["thetas"]))))
+        mine = torch.as_tensor(th, device="cuda")
+        other = [torch.empty_like(mine) for _ in range(ctx.world)]
+        dist.all_gather(other, mine)
+        same = all(torch.equal(o, mine) for o in other)
+        flag = torch.tensor([1.0 if (err < tol and same) else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        rows[name] = {"rel_err_vs_reference_chain": err, "tol": tol, "ranks_bit_identical": bool(same),
+                      "ok": bool(flag.item() > 0.5)}
+        all_ok = all_ok and rows[name]["ok"]
+        del sr, dm
+    res["row_sharded"] = {"ok": bool(all_ok), "ranks": ctx.world, "fixtures": rows}
+    torch.cuda.empty_cache()
+    return res
+
+
+# ----------------------------------------------------------------------------
+# engine arm
+# ----------------------------------------------------------------------------
+def shard_for(ctx, wl, sharding, chains_override=None):
+    """-> (chains on this rank, global id of its first chain, total chains, `scaling` word)."""
+    if sharding == "replica":
+        return 1, 0, 1, "none (K = 1 latency; one replica per rank, the value is a single chain's)"
+    if sharding == "strong":
+        Kt = chains_override or CHAINS_TOTAL[wl]
+        if Kt % ctx.world:
+            raise SystemExit("%s: %d chains do not split over %d ranks" % (wl, Kt, ctx.world))
+        Kg = Kt // ctx.world
+        return Kg, ctx.rank * Kg, Kt, "strong"
+    Kg = chains_override or CHAINS_PER_GPU[wl]
+    return Kg, ctx.rank * Kg, Kg * ctx.world, "weak"
+
+
+def public_entry(ctx, r, cpu=None):
+    """Strip the private fields of a measure() result into the JSON entry of the `configs` array."""
+    e = {k: v for k, v in r.items() if not k.startswith("_") and k not in ("window", "desc")}
+    e["config"] = {"workload": "%s: %s; %d chains/GPU x %d MH iterations per step; Philox4x32-10 RNG; L2 flushed "
+                               "(256 MiB write) between steps" % (r["workload"], r["desc"], r["chains_per_gpu"], r["iters_per_step"]),
+                   "chains_per_gpu": r["chains_per_gpu"], "chains_total": r["chains_total"],
+                   "iters_per_step": r["iters_per_step"]}
+    if ctx.clocks:
+        e["clocks"] = ctx.clocks.window(*r["window"])
+    e["cpu_baseline"] = cpu
+    return e
+
+
+def run_engine(args):
+    ctx = Ctx(args)
+    torch = ctx.torch
+    single = args.workload is not None
+    wl = args.workload or "changepoint"
+    T = args.iters or ITERS[wl]
+    sharding = "weak"
+    if single and args.strong:
+        sharding = "strong"
+    Kg, off, Ktot, scaling = shard_for(ctx, wl, sharding, args.chains)
+    burn = args.burn if args.burn is not None else {"changepoint": 50000}.get(wl, 2 * T)
+    head = measure(ctx, wl, args.precision, Kg, T, args.steps, args.warmup, burn, off, Ktot, scaling)
+    s = head.pop("_sampler")
+
+    ess = sokal = None
+    if wl == "changepoint" and not args.no_ess:
+        ess = ess_phase(ctx, s, T, args.ess_half_launches, Ktot)
+        if ctx.rank == 0:
+            sokal = sokal_check(ctx)
+    del s
+    torch.cuda.empty_cache()
+
+    configs, pending_cpu = [], []
+    if not single and not args.no_configs:
+        only = set(args.only.split(",")) if args.only else None
+        for key, w, prec, shd, Tn, steps in SUBCONFIGS:
+            if only and key not in only and w not in only:
+                continue
+            Kg2, off2, Kt2, sc2 = shard_for(ctx, w, shd)
+            try:
+                r = measure(ctx, w, prec, Kg2, Tn, steps, 3, 2 * Tn if shd != "replica" else 1000, off2, Kt2, sc2)
+            except Exception as e:                       # a config that cannot run must not take the line down
+                configs.append({"key": key, "workload": w, "precision": prec, "error": "%s: %s" % (type(e).__name__, e)})
+                torch.cuda.empty_cache()
+                continue
+            r.pop("_sampler", None)
+            r["key"] = key
+            configs.append(r)
+            torch.cuda.empty_cache()
+        _DATA_CACHE.clear()
+        torch.cuda.empty_cache()
+
+    checks = None
+    if ctx.world > 1 and not args.no_checks:
+        checks = multi_gpu_checks(ctx)
+
+    if ctx.clocks:
+        ctx.clocks.stop()
+    if ctx.rank != 0:
+        ctx.close()
+        return
+    do_cpu = (not args.no_cpu) and ctx.world == 1            # contract: rank 0 at N = 1 only
+    cpu_head = cpu_baseline(wl, args.cpu_seconds) if do_cpu else None
+    entries = []
+    cpu_cache = {}
+    for r in configs:
+        if "error" in r:
+            entries.append(r)
+            continue
+        cpu = None
+        if do_cpu and r["key"] != "gauss2d_rw_k1":
+            if r["workload"] not in cpu_cache:
+                cpu_cache[r["workload"]] = cpu_baseline(r["workload"], args.cpu_seconds_config)
+            cpu = cpu_cache[r["workload"]]
+        elif do_cpu:
+            cpu = {"note": "K = 1: the CPU figure for one chain is cpu_baseline.value / cores of the gauss2d_rw entry"}
+        entries.append(public_entry(ctx, r, cpu))
+
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": scaling, "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+        "config": {"workload": "%s: %s; %d chains/GPU x %d MH iterations per step; Philox4x32-10 RNG; "
+                               "L2 flushed (256 MiB write) between steps, per-step CUDA events summed"
+                               % (wl, head["desc"], Kg, T),
+                   "chains_per_gpu": Kg, "chains_total": head["chains_total"], "iters_per_step": T,
+                   "burn_in_iters": burn, "parallelism": "chains sharded, dp%d" % ctx.world},
+        "min_ess_per_sec": (ess or {}).get("min_ess_per_sec") if ess is not None else head["min_ess_per_sec"],
+        "diagnostics": head["diagnostics"],
+        "ess": ess, "ess_sokal": sokal,
+        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+        "cpu_baseline": cpu_head,
+        "clocks": ctx.clocks.window(*head["window"]) if ctx.clocks else None, "peaks_source": ctx.peak_src,
+        "configs": entries, "multi_gpu_checks": checks,
+    }
+    if checks is not None:
+        line["row_sharded_parity"] = checks["row_sharded"]["ok"]
+        line["chain_shard_invariance"] = checks["chain_shard_invariance"]["ok"]
+    print(json.dumps(line))
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the CPU sampler on this box's host cores, same metric/config.
-    The reference is pure Python and cannot travel to the GPU box, so this arm times the
-    numpy port (oracle/riemann_port.py, pinned to the reference's chains by tests/golden)."""
+    """--impl reference: the reference's own CPU sampler on this box's host cores, same metric / config.  The
+    UNMODIFIED riemann package (staged under oracle/_ref/ by oracle/build_ref.py, imported through oracle/refshim.py)
+    for the changepoint / Gaussian configs; the numpy port for the logistic models the reference does not contain."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = args.workload
+    wl = args.workload or "changepoint"
     W, K = max(args.warmup, 1), max(args.steps, 1)
     per = max(2.0, min(20.0, 60.0 / (W + K)))
-    for _ in range(1):
-        cpu_baseline(wl, 1.0)                       # warm the pool / imports
+    cpu_baseline(wl, 1.0, with_ess=False)               # warm the pool / imports
     vals = [cpu_baseline(wl, per) for _ in range(K)]
     v = float(np.mean([c["value"] for c in vals]))
     cb = dict(vals[-1], value=v)
+    # ESS over the concatenated steps would need the chains to continue; each step restarts its chains, so the ESS
+    # figure is the best (longest-window) single step's
     Kg = args.chains or CHAINS_PER_GPU[wl]
+    entries = []
+    if args.workload is None and not args.no_configs:
+        for w in ("gauss2d_rw", "gauss1000_mala", "logistic_mala", "logistic_mmala"):
+            c = cpu_baseline(w, args.cpu_seconds_config)
+            entries.append({"key": w, "workload": w, "value": c["value"], "unit": UNIT, "dtype": "f64",
+                            "min_ess_per_sec": c.get("min_ess_per_sec"), "cpu_baseline": c})
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s (CPU reference arm: one chain per host core, %.0f s per step)" % (wl, per),
+            "config": {"workload": "%s (CPU reference arm: one chain per host core, %.1f s per step)" % (wl, per),
                        "chains_per_gpu": Kg},
+            "min_ess_per_sec": cb.get("min_ess_per_sec"),
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "configs": entries}
     print(json.dumps(line))
 
 
@@ -571,15 +939,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--workload", default="changepoint", choices=sorted(CHAINS_PER_GPU))
-    ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    ap.add_argument("--workload", default=None, choices=sorted(CHAINS_PER_GPU),
+                    help="single-workload line (profiling); default: changepoint headline + the `configs` array")
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (total chains with --strong)")
+    ap.add_argument("--strong", action="store_true", help="single workload: --chains (or BASELINE's count) is the total")
     ap.add_argument("--iters", type=int, default=None, help="MH iterations per step")
     ap.add_argument("--burn", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds-config", type=float, default=3.0)
+    ap.add_argument("--ess-half-launches", type=int, default=200,
+                    help="changepoint ESS phase: launches (of --iters MH steps) per half-window")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-checks", action="store_true")
+    ap.add_argument("--only", default=None, help="comma-separated keys / workloads of the configs array to run")
     ap.add_argument("--precision", default="f64", choices=["f64", "tf32x3", "tf32-metric"],
-                    help="tf32x3: tcgen05 tensor-core mode of the dense Gaussian workload; tf32-metric: "
-                         "tcgen05 Fisher-metric GEMM of the logistic mMALA workload")
+                    help="single workload: tf32x3 = tcgen05 tensor-core modes; tf32-metric = tcgen05 Fisher-metric GEMM")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

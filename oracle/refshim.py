@@ -1,5 +1,6 @@
 """
-TEST INFRASTRUCTURE -- build-container only (needs /root/reference).
+TEST INFRASTRUCTURE -- needs the reference tree: /root/reference in the build container, or the unmodified copy
+staged by oracle/build_ref.py under oracle/_ref/ (which is what travels to the GPU box).
 
 Import the UNMODIFIED reference (rscalzo/riemann) with the harness-side shims
 listed in SURVEY.md section 8c.  Nothing in the reference tree is touched; every
@@ -32,7 +33,21 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("RIEMANN_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py (unmodified copy)
+
+
+def _default_root():
+    """The live reference tree in the build container; on the GPU box the unmodified copy that
+    `oracle/build_ref.py` staged under oracle/_ref/ (git-ignored, travels with the snapshot like the .so)."""
+    env = os.environ.get("RIEMANN_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/riemann"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available():
