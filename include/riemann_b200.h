@@ -294,6 +294,23 @@ int rmn_sampler_diag_dim(const rmn_sampler_t* s);
 int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream);
 int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stream);
 
+/* Per-chain mean and biased variance of the tracked functionals since the last reset: d_mean[nd][K], d_var[nd][K]
+ * (chain fastest; either may be NULL).  What `Sampler._chain_thetas` gives the reference's scripts for one chain
+ * (examples/test_randomwalk.py:41-46 computes its statistics from the trace) without keeping a trace of K chains;
+ * used for per-chain R-hat and for the independence checks of the shared move schedule. */
+int rmn_sampler_chain_moments(rmn_sampler_t* s, double* d_mean, double* d_var, void* stream);
+
+/* Changepoint samplers, Philox mode: how the move type of a step (ChangepointRegression1DProp.propose draws it
+ * independently of the state, examples/test_changepoint.py:48-54) is assigned to chains.
+ *   1 (default)  the chains of an aligned group of 8 consecutive GLOBAL chain ids (one warp) share the three
+ *                selection draws of a step, so a warp executes one move-specific code path per step.  Every chain
+ *                still sees an i.i.d. move sequence with the reference's probabilities, independent of its state:
+ *                each chain is an exact replica of the reference sampler; chains of a group are conditionally
+ *                independent given the schedule and uncorrelated in stationarity.  Independent of the sharding.
+ *   0            every chain draws its own move types.
+ * Injected runs always replay the per-chain move types of the tape.  Call before rmn_sampler_run. */
+int rmn_sampler_set_move_schedule(rmn_sampler_t* s, int mode);
+
 /* Number of kernel launches this handle has enqueued so far. */
 int64_t rmn_sampler_launch_count(const rmn_sampler_t* s);
 

@@ -79,6 +79,8 @@ SIGNATURES = {
     "rmn_sampler_reset_diagnostics": (_I, [_P, _P]),
     "rmn_sampler_reduce_diagnostics": (_I, [_P, _P, _P]),
     "rmn_sampler_launch_count": (_L, [_P]),
+    "rmn_sampler_chain_moments": (_I, [_P, _P, _P, _P]),
+    "rmn_sampler_set_move_schedule": (_I, [_P, _I]),
     "rmn_sampler_set_tempering": (_I, [_P, _I, _P, _D]),
     "rmn_autocorr_tau": (_I, [_P, _L, _L, _L, _D, _P, _P, _P]),
     "rmn_nccl_unique_id": (_I, [_P, C.c_size_t]),

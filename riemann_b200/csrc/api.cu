@@ -465,6 +465,20 @@ extern "C" int rmn_sampler_set_tempering(rmn_sampler_t* s, int nt, const double*
     return s->impl->set_tempering(nt, h_betas, pswap);
 }
 
+extern "C" int rmn_sampler_set_move_schedule(rmn_sampler_t* s, int mode) {
+    RMN_REQUIRE(s && s->impl, "rmn_sampler_set_move_schedule: null sampler");
+    return s->impl->set_move_schedule(mode);
+}
+
+extern "C" int rmn_sampler_chain_moments(rmn_sampler_t* s, double* d_mean, double* d_var, void* stream) {
+    RMN_REQUIRE(s && s->impl, "rmn_sampler_chain_moments: null sampler");
+    const double *S1 = nullptr, *S2 = nullptr;
+    int64_t n = 0;
+    const int rc = s->impl->chain_sums(&S1, &S2, &n);
+    if (rc != RMN_OK) return rc;
+    return rmn_chain_moments(s->K, s->impl->diag_dim(), n, S1, S2, d_mean, d_var, (cudaStream_t)stream);
+}
+
 extern "C" int rmn_autocorr_tau(const double* d_x, int64_t n, int64_t nchains, int64_t nfunc, double c, double* h_tau,
                                 int64_t* h_window, void* stream) {
     return rmn_autocorr_tau_impl(d_x, n, nchains, nfunc, c, h_tau, h_window, (cudaStream_t)stream);

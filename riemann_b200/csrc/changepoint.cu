@@ -25,15 +25,6 @@
 #include "changepoint.cuh"
 #include <stdlib.h>
 
-#ifndef RMN_CP_PREFETCH
-#define RMN_CP_PREFETCH 1
-#endif
-#ifndef RMN_CP_UNCOND_TD
-#define RMN_CP_UNCOND_TD 0
-#endif
-#ifndef RMN_CP_UNCOND_SEARCH
-#define RMN_CP_UNCOND_SEARCH 1   /* the search joins the evaluation's basic block: +7 % (gpurun r20) */
-#endif
 #ifndef RMN_CP_DEFAULT_GL
 #define RMN_CP_DEFAULT_GL 4
 #endif
@@ -164,89 +155,148 @@ __device__ __forceinline__ int count_below(const double (&cx)[Geo<GL>::EPL], int
 }
 
 // ---------------------------------------------------------------------------------------
-// Log-posterior of one state held across the GL lanes of a group.  Per element: residual sum
-// of squares of its run of data (prefix sums), gap to the previous changepoint, height-prior
-// term.  The sum over changepoints of log(gap) (changepoint.py:142-143) is taken as ONE log of
-// the product of the gaps (a negative gap poisons the product with nan, exactly what a sum
-// containing log(negative) gives numpy; a zero gap gives -inf either way), and that log is
-// batched with the step's other fp64 logarithms -- log sigma^2, log u (accept test), log|J| --
-// on lanes 0..3 of the group: ONE `log` call per warp-step.  log(1/sigma^2) (:148) is
-// -log(sigma^2) (+inf where 1/sigma^2 overflows, as in numpy).  The reference's nan -> -inf and
-// inf/nan -> -inf rules are applied at the end.  Differences from numpy's term-by-term sums are
-// O(1e-15) relative (tests: 1e-9).
+// Log-posterior of one state held across the GL lanes of a group, in three pieces, so that a move
+// which leaves part of the state alone reuses the cached pieces of the current state:
+//   cp_terms     per element: residual sum of squares of its run of data (prefix sums) -> ss,
+//                height-prior term (changepoint.py:18-19,136) -> vt, gap to the previous changepoint
+//                (:142-143) -> product gp.  The sum over changepoints of log(gap) is taken as ONE log of
+//                the product of the gaps (a negative gap poisons the product with nan, exactly what a sum
+//                containing log(negative) gives numpy; a zero gap gives -inf either way).
+//   log4         the step's fp64 logarithms -- log gp, log sigma^2, log u (accept test), log|J| -- batched
+//                on lanes 0..3 of the group: ONE `log` call per warp-step.
+//   cp_assemble  the scalar arithmetic of changepoint.py:118-125,128-160 and model.py:50-54;
+//                log(1/sigma^2) (:148) is -log(sigma^2) (+inf where 1/sigma^2 overflows, as in numpy).
+// Every floating-point operation that is shared between the general path and the move-specific fast
+// paths of the kernel is written with explicit round-to-nearest intrinsics, so all paths give the same
+// bits (no context-dependent FMA contraction).  Differences from numpy's term-by-term sums are O(1e-15)
+// relative (tests: 1e-9).
 // ---------------------------------------------------------------------------------------
-template <int GL>
-__device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const double* __restrict__ cy,
-                                                  const double* __restrict__ cyy, int lane, int kw, int kk,
-                                                  const double (&nx)[Geo<GL>::EPL], const double (&nv)[Geo<GL>::EPL],
-                                                  const int (&nbu)[Geo<GL>::EPL], double nsig, double uacc,
-                                                  double jarg, double& logu, double& ljac, int which) {
+template <int GL, bool WSS, bool WVT, bool WGP>
+__device__ __forceinline__ void cp_terms(const CPParams& P, const double* __restrict__ cy,
+                                         const double* __restrict__ cyy, int lane, int kw, int kk,
+                                         const double (&nx)[Geo<GL>::EPL], const double (&nv)[Geo<GL>::EPL],
+                                         const int (&nbu)[Geo<GL>::EPL], double& ss, double& vt, double& gp) {
     constexpr int EPL = Geo<GL>::EPL;
     double px[EPL];
     int pb[EPL];
-    shift_prev<GL, double>(nx, px, P.xmin, lane, kw);
-    shift_prev<GL, int>(nbu, pb, 0, lane, kw);
-    double ss = 0.0, vt = 0.0, gp = 1.0;
+    if (WGP) shift_prev<GL, double>(nx, px, P.xmin, lane, kw);
+    if (WSS) shift_prev<GL, int>(nbu, pb, 0, lane, kw);
+    double a = 0.0, b = 0.0, g = 1.0;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
         if (ROW_ON(j)) {
             const int e = lane + GL * j;
             if (e <= kk) {
-                const int bu = nbu[j], bl = pb[j];
-                const double n = (double)(bu - bl);
-                const double s1 = cy[bu] - cy[bl];
-                const double s2 = cyy[bu] - cyy[bl];
-                const double vc = nv[j] - P.ycenter;
-                ss += n * vc * vc - 2.0 * vc * s1 + s2;
-                const double gap = ((e < kk) ? nx[j] : P.xmax) - px[j];            // changepoint.py:142-143
-                gp *= (gap < 0.0) ? NAN : gap;
-                double t = -P.beta * nv[j] + P.cv;                                 // changepoint.py:18-19,136
-                if (!P.alpha_is_one) t += (P.alpha - 1.0) * log(nv[j]);
-                else if (!(nv[j] > 0.0)) t = NAN;                                  // 0 * log(v<=0) is nan in numpy
-                vt += t;
+                if (WSS) {
+                    const int bu = nbu[j], bl = pb[j];
+                    const double n = (double)(bu - bl);
+                    const double s1 = __dsub_rn(cy[bu], cy[bl]);
+                    const double s2 = __dsub_rn(cyy[bu], cyy[bl]);
+                    const double vc = __dsub_rn(nv[j], P.ycenter);
+                    // n vc^2 - 2 vc s1 + s2
+                    a = __dadd_rn(a, __fma_rn(__dmul_rn(n, vc), vc, __fma_rn(-2.0 * vc, s1, s2)));
+                }
+                if (WGP) {
+                    const double gap = __dsub_rn((e < kk) ? nx[j] : P.xmax, px[j]);       // changepoint.py:142-143
+                    g = __dmul_rn(g, (gap < 0.0) ? NAN : gap);
+                }
+                if (WVT) {
+                    double t = __fma_rn(-P.beta, nv[j], P.cv);                            // changepoint.py:18-19,136
+                    if (!P.alpha_is_one) t = __fma_rn(P.alpha - 1.0, log(nv[j]), t);
+                    else if (!(nv[j] > 0.0)) t = NAN;                                     // 0 * log(v<=0) is nan in numpy
+                    b = __dadd_rn(b, t);
+                }
             }
         }
     }
-    ss = gsum<GL>(ss);
-    vt = gsum<GL>(vt);
-    gp = gprod<GL>(gp);
-    const double s2v = nsig * nsig;
+    if (WSS) ss = gsum<GL>(a);
+    if (WVT) vt = gsum<GL>(b);
+    if (WGP) gp = gprod<GL>(g);
+}
+
+// log of four per-chain arguments with one call: lane (l & 3) of the group takes argument l & 3
+template <int GL>
+__device__ __forceinline__ void log4(int lane, double a0, double a1, double a2, double a3, double& l0, double& l1,
+                                     double& l2, double& l3) {
     const int sl = lane & 3;
-    const double larg = (sl == 0) ? gp : ((sl == 1) ? s2v : ((sl == 2) ? uacc : jarg));
+    const double larg = (sl == 0) ? a0 : ((sl == 1) ? a1 : ((sl == 2) ? a2 : a3));
     const double lres = log(larg);
-    const double lg = __shfl_sync(0xffffffffu, lres, 0, GL);
-    const double log_s2 = __shfl_sync(0xffffffffu, lres, 1, GL);
-    logu = __shfl_sync(0xffffffffu, lres, 2, GL);
-    ljac = __shfl_sync(0xffffffffu, lres, 3, GL);
+    l0 = __shfl_sync(0xffffffffu, lres, 0, GL);
+    l1 = __shfl_sync(0xffffffffu, lres, 1, GL);
+    l2 = __shfl_sync(0xffffffffu, lres, 2, GL);
+    l3 = __shfl_sync(0xffffffffu, lres, 3, GL);
+}
+
+// which: 0 = log posterior (model.py:43-55), 1 = log likelihood, 2 = log prior
+__device__ __forceinline__ double cp_assemble(const CPParams& P, int kk, double ss, double vt, double lg, double nsig,
+                                              double log_s2, int which) {
+    const double s2v = __dmul_rn(nsig, nsig);
     const int ks = kk + 1;                                     // number of steps
-    double logl = -0.5 * ((ss / s2v + (double)P.M * log_s2) + P.Mlog2pi);   // :118-120
+    double logl = -0.5 * __dadd_rn(__fma_rn((double)P.M, log_s2, __ddiv_rn(ss, s2v)), P.Mlog2pi);   // :118-120
     if (isnan(logl)) logl = -INFINITY;                         // :124-125
     double lsig = (s2v < 5.562684646268003e-309) ? INFINITY : -log_s2;      // log(1/sigma^2), :148
     if (nsig < 0.0) lsig = NAN;                                // :146-147
-    const double lps = (P.tab2[ks] + lg) - (double)ks * P.logL;
-    double logp = ((P.tab1[ks] + vt) + lps) + lsig;            // :156
+    const double lps = __fma_rn(-(double)ks, P.logL, __dadd_rn(P.tab2[ks], lg));
+    double logp = __dadd_rn(__dadd_rn(__dadd_rn(P.tab1[ks], vt), lps), lsig);              // :156
     if (isnan(logp)) logp = -INFINITY;                         // :158-159
     if (which == 1) return logl;
     if (which == 2) return logp;
     return combine_logpost(logp, logl);
 }
 
-#ifndef RMN_CP_SHARED_MV
-#define RMN_CP_SHARED_MV 0
-#endif
+// full evaluation (pointwise entry, state caches at kernel entry)
+template <int GL>
+__device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const double* __restrict__ cy,
+                                                  const double* __restrict__ cyy, int lane, int kw, int kk,
+                                                  const double (&nx)[Geo<GL>::EPL], const double (&nv)[Geo<GL>::EPL],
+                                                  const int (&nbu)[Geo<GL>::EPL], double nsig, int which,
+                                                  double& ss, double& vt, double& lg, double& log_s2) {
+    double gp, d2, d3;
+    cp_terms<GL, true, true, true>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, ss, vt, gp);
+    log4<GL>(lane, gp, __dmul_rn(nsig, nsig), 1.0, 1.0, lg, log_s2, d2, d3);
+    return cp_assemble(P, kk, ss, vt, lg, nsig, log_s2, which);
+}
+
 #ifndef RMN_CP_MINBLOCKS
 #define RMN_CP_MINBLOCKS 5   /* 96 regs, 20 warps/SM: best of 4..8 measured (gpurun r17) */
 #endif
+#ifndef RMN_CP_FASTPATHS
+#define RMN_CP_FASTPATHS 1   /* move-specific paths for warps whose chains all drew the same move type */
+#endif
 
+// ---------------------------------------------------------------------------------------
+// The T-step kernel.
+//
+// Move schedule (Philox mode).  Which of the four moves a chain attempts at step t is drawn
+// independently of its state (three fresh uniforms, test_changepoint.py:48-54).  shared_mv = 1: the
+// 32/GL chains of a warp -- global chain ids aligned to 32/GL, so the grouping does not depend on how the
+// chains are sharded -- take the three selection words from the group's first chain.  Each chain still
+// sees an i.i.d. sequence of move types with the reference's probabilities, independent of its state,
+// so each is an exact replica of the reference sampler; given the schedule the chains of a group are
+// independent, and in stationarity their ergodic averages are uncorrelated (every schedule's kernel
+// preserves the target).  The warp then executes ONE move type per step: a real branch to a
+// move-specific path instead of the union of all four by selection.  shared_mv = 0: per-chain move
+// types (the general path every step).  Injected mode replays per-chain move types from the tape and
+// takes a fast path whenever the warp happens to be uniform (always for K = 1), so the fast paths are
+// covered by the reference-stream parity tests.
+//
+// Fast paths (cached per chain: ss, vt, lg = log gap product, ls2 = log sigma^2 of the CURRENT state):
+//   sigma move  test_changepoint.py:54-56   likelihood and prior from the cached sums, no search
+//   cpv move    :51-53                      residual / height-prior sums; gaps and run boundaries cached
+//   cpx move    :48-50                      searches, residual sums, gap product; height-prior sum cached
+//   birth/death :57-71                      the general path
+// ---------------------------------------------------------------------------------------
 // DATA: 0 = data tables read from global memory (too large for shared memory), 1 = staged in shared
 // memory, 2 = staged and 64 <= M < 128 (P2 = 64: fully unrolled 7-level search; the bench shape)
 template <bool INJ, int DATA, int GL>
 __global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
 changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
                    int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
-                   const double* __restrict__ tape, rmn_trace_t tr) {
+                   const double* __restrict__ tape, rmn_trace_t tr, int shared_mv) {
     constexpr int EPL = Geo<GL>::EPL;
     constexpr int NS = Geo<GL>::NS;
+    constexpr int CPW = 32 / GL;                  // chains per warp = chains per schedule group
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double smem[];
     const double* xs = gdata;
     constexpr int LOGP2 = (DATA == 2) ? 6 : -1;
@@ -260,9 +310,11 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     const double* cyy = cy + P.M + 1;
 
     const int lane = threadIdx.x & (GL - 1);
-    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GL;
-    const bool live = c_raw < K;
-    const int64_t c = live ? c_raw : K - 1;       // dead groups shadow the last chain, never store
+    // schedule groups are aligned to GLOBAL chain ids: `head` leading groups of the grid are dead
+    const int head = shared_mv ? (int)(chain_offset & (CPW - 1)) : 0;
+    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GL - head;
+    const bool live = c_raw >= 0 && c_raw < K;
+    const int64_t c = c_raw < 0 ? 0 : (c_raw < K ? c_raw : K - 1);   // dead groups shadow a live chain, never store
 
     int k = st.k[c];
     double cx[EPL], cv[EPL];
@@ -276,74 +328,69 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     }
     double sig = st.sig[c];
     double lp = st.lp[c];
+    double ss_c, vt_c, lg_c, ls2_c;               // pieces of lp (see cp_terms / cp_assemble)
+    cp_logpost_rows<GL>(P, cy, cyy, lane, LANES, k, cx, cv, bu, sig, 0, ss_c, vt_c, lg_c, ls2_c);
     int nacc = 0, novf = 0;
     double s1[NS], s2[NS];                        // lane l, slot s accumulates functional l + GL*s
 #pragma unroll
     for (int s = 0; s < NS; ++s) { s1[s] = 0.0; s2[s] = 0.0; }
-    const RngKey rk(seed, (uint64_t)(chain_offset + c));
+    const RngKey rk(seed, (uint64_t)(chain_offset + c_raw));
     const TraceSel ts{tr.first, tr.thin > 0 ? tr.thin : 1};
     const bool tracing = tr.d_k || tr.d_cpx || tr.d_cpv || tr.d_sig || tr.d_logpost;
     const bool tracing_prop = tr.d_prop_logpost || tr.d_accepted || tr.d_logqratio || tr.d_prop_k ||
                               tr.d_prop_sig || tr.d_prop_cpx || tr.d_prop_cpv;
+    const bool fast_ok = RMN_CP_FASTPATHS && (INJ || shared_mv);
 
-#if RMN_CP_PREFETCH
-    // software pipelining: the Philox blocks of step t+1 are issued in the middle of step t (they depend
-    // on nothing but the counter), so their integer multiplies fill the fp64 / LDS latency of the evaluation
-    uint4 rA = make_uint4(0, 0, 0, 0), rB = make_uint4(0, 0, 0, 0);
-    if (!INJ) {
-        rA = rk.block((uint64_t)step0, (uint32_t)lane);
-        if (EPL > 2) rB = rk.block((uint64_t)step0, (uint32_t)(GL + lane));
-    }
-#endif
+    // per-step proposal record (parity harness): what Proposal.propose returned, what the sampler decided
+    auto trace_prop = [&](int64_t t, double lpn, bool acc, double lqr, int kk, double nsig,
+                          const double (&nx)[EPL], const double (&nv)[EPL]) {
+        if (!(live && tracing_prop)) return;
+        if (lane == 0) {
+            if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpn;
+            if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
+            if (tr.d_logqratio) tr.d_logqratio[t * K + c] = lqr;
+            if (tr.d_prop_k) tr.d_prop_k[t * K + c] = kk;
+            if (tr.d_prop_sig) tr.d_prop_sig[t * K + c] = nsig;
+        }
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int e = lane + GL * j;
+            if (tr.d_prop_cpx) tr.d_prop_cpx[(t * K + c) * LANES + e] = nx[j];
+            if (tr.d_prop_cpv) tr.d_prop_cpv[(t * K + c) * LANES + e] = nv[j];
+        }
+    };
+
+    // the Philox block of step t+1 is issued during step t (it depends on nothing but the counter), so its
+    // integer multiplies fill the fp64 / LDS latency of the evaluation
+    uint4 rA = make_uint4(0, 0, 0, 0);
+    if (!INJ) rA = rk.block((uint64_t)step0, (uint32_t)lane);
+
     for (int64_t t = 0; t < T; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
-        const int kw = __reduce_max_sync(0xffffffffu, k);
-        double snew, du, uacc, xi[EPL];
+        const int kw = __reduce_max_sync(FULL, k);
+        double snew, du, uacc;
         int nrand, mv;
         bool birth;
+        const double* row = nullptr;
+        const uint4 r = rA;
         if (INJ) {
-            const double* row = tape + (t * K + c) * RMN_CP_NSLOT;
+            row = tape + (t * K + c) * RMN_CP_NSLOT;
             const double u1 = row[RMN_CP_SLOT_SEL1], u2 = row[RMN_CP_SLOT_SEL2], u3 = row[RMN_CP_SLOT_SEL3];
             const double ubd = row[RMN_CP_SLOT_BD];
             snew = row[RMN_CP_SLOT_S]; du = row[RMN_CP_SLOT_DU];
             nrand = (int)row[RMN_CP_SLOT_N]; uacc = row[RMN_CP_SLOT_ACC];
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) xi[j] = row[RMN_CP_SLOT_XI + lane + GL * j];
             // which block moves (fresh uniform per elif, test_changepoint.py:48-54); birth/death :59
             mv = (u1 < P.p1) ? 0 : ((u2 < P.p2) ? 1 : ((u3 < P.p3) ? 2 : 3));
             birth = (k == 0) || (ubd > 0.5);
         } else {
-            // ONE Philox block per lane and step: words x,y -> Box-Muller pair = the normals of this
-            // lane's rows 0 and 1; the spare words z,w of lanes 0..3 carry the chain-level uniforms.
-            // Rows 2,3 (GL = 4, only when some chain of the warp has >= 7 changepoints) take a second block.
-#if RMN_CP_PREFETCH
-            const uint4 r = rA;
-#else
-            const uint4 r = rk.block(step, (uint32_t)lane);
-#endif
-            float n0, n1;
-            box_muller(r.x, r.y, n0, n1);
-            xi[0] = (double)n0;
-            if (EPL > 1) xi[1 % EPL] = (double)n1;
-            if (EPL > 2) {
-                xi[2 % EPL] = 0.0; xi[3 % EPL] = 0.0;
-                if (ROW_ON(2)) {
-#if RMN_CP_PREFETCH
-                    const uint4 q = rB;
-#else
-                    const uint4 q = rk.block(step, (uint32_t)(GL + lane));
-#endif
-                    box_muller(q.x, q.y, n0, n1);
-                    xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
-                }
-            }
-            // (RMN_CP_SHARED_MV = 1, an unmeasured build variant: the move-type words come from the first chain of the
-            // warp, so the warp's chains share one move schedule -- see DESIGN.md section 5; off in the product)
-            constexpr int MVW = RMN_CP_SHARED_MV ? 32 : GL;
-            const uint32_t z0 = __shfl_sync(0xffffffffu, r.z, 0, MVW), w0 = __shfl_sync(0xffffffffu, r.w, 0, MVW);
-            const uint32_t z1 = __shfl_sync(0xffffffffu, r.z, 1, MVW), w1 = __shfl_sync(0xffffffffu, r.w, 1, GL);
-            const uint32_t z2 = __shfl_sync(0xffffffffu, r.z, 2, GL), w2 = __shfl_sync(0xffffffffu, r.w, 2, GL);
-            const uint32_t z3 = __shfl_sync(0xffffffffu, r.z, 3, GL), w3 = __shfl_sync(0xffffffffu, r.w, 3, GL);
+            // ONE Philox block per lane and step: words x,y -> Box-Muller pair = the normals of this lane's
+            // rows 0 and 1; the spare words z,w of lanes 0..3 carry the chain-level uniforms (the three
+            // move-selection words come from the schedule group's first chain when shared_mv).
+            const int mvw = shared_mv ? 32 : GL;
+            const uint32_t z0 = __shfl_sync(FULL, r.z, 0, mvw), w0 = __shfl_sync(FULL, r.w, 0, mvw);
+            const uint32_t z1 = __shfl_sync(FULL, r.z, 1, mvw), w1 = __shfl_sync(FULL, r.w, 1, GL);
+            const uint32_t z2 = __shfl_sync(FULL, r.z, 2, GL), w2 = __shfl_sync(FULL, r.w, 2, GL);
+            const uint32_t z3 = __shfl_sync(FULL, r.z, 3, GL), w3 = __shfl_sync(FULL, r.w, 3, GL);
             mv = (z0 < P.t1) ? 0 : ((w0 < P.t2) ? 1 : ((z1 < P.t3) ? 2 : 3));   // same tests on raw words
             birth = (k == 0) || (w1 >= 0x80000000u);                            // u > 0.5
             snew = P.xmin + (P.xmax - P.xmin) * u01_fast(z2);
@@ -352,120 +399,237 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             uacc = u01_fast(w3);
         }
         nrand = max(0, min(nrand, k - 1));
+        const int mvu = __shfl_sync(FULL, mv, 0);
+        const bool uniform = __all_sync(FULL, mv == mvu);
+        const int path = (fast_ok && uniform) ? mvu : 3;           // warp-uniform
 
-        // ---- build the proposal by selection (the chains of a warp never diverge on mv)
-        int kk = k, nbu[EPL];
-        double nx[EPL], nv[EPL], nsig = sig, jarg = 1.0;
-        bool ovf = false;
-        const double sxk = P.sx[k];
+        // normals of the block moves: rows 0,1 from this step's block, rows 2,3 (only when some chain of the
+        // warp has an element there) from a second block
+        auto normals = [&](double (&xi)[EPL]) {
+            if (INJ) {
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-            const int e = lane + GL * j;
-            nx[j] = cx[j]; nv[j] = cv[j]; nbu[j] = bu[j];
-            if (ROW_ON(j)) {
-                if (mv == 0 && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));   // randomwalk.py:26, scale = 1
-                if (mv == 1 && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));
-            }
-        }
-        const double xi0 = __shfl_sync(0xffffffffu, xi[0], 0, GL);
-        if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
-        int nb = 0;
-        if (RMN_CP_UNCOND_TD || __any_sync(0xffffffffu, mv == 3)) {     // warp-uniform
-            nb = count_below<GL>(cx, lane, k, snew, kw);                // searchsorted(cpx, s), :206
-            const double hb = elem_at<GL>(cv, nb, kw);
-            const double h1d = elem_at<GL>(cv, nrand, kw);
-            const double h2d = elem_at<GL>(cv, nrand + 1, kw);
-            // birth (changepoint.py:57,61,72-74) and death (:67-68,76-78) share one instruction
-            // stream: the operands of each division / square root are selected per chain
-            const double q1 = birth ? du / P.sqrtM : h2d / h1d;
-            const double ub = 0.5 + q1;                                 // birth: u, :61
-            const double q2 = birth ? (1.0 - ub) / ub : 1.0 / (1.0 + q1);       // birth: f^2; death: u, :68
-            const double u = birth ? ub : q2;
-            const double r = sqrt(birth ? q2 : h1d * h2d);              // birth: f, :57; death: h, :67
-            jarg = fabs((birth ? hb : r) / (u * (1.0 - u)));            // |J| resp. 1/|J^-1|
-            const double hbf = hb / r;
-            ovf = (mv == 3) && birth && (k + 1 > LANES - 1);
-            const bool td = (mv == 3) && !ovf;
-            if (!(mv == 3)) jarg = 1.0;
-            // insert / delete = every element reads its neighbour below (birth, above the insertion
-            // point) or above (death, from the removed element on); other chains read themselves
-            const int dir = birth ? -1 : 1;
-            const int pivot = birth ? nb : nrand - 1;                   // elements <= pivot stay
-            int off[EPL];
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) off[j] = (td && lane + GL * j > pivot) ? dir : 0;
-            double sx_[EPL], sv_[EPL];
-            int sb_[EPL];
-            shift_by<GL, double>(cx, sx_, 0.0, lane, dir, off, kw);
-            shift_by<GL, double>(cv, sv_, 0.0, lane, dir, off, kw);
-            shift_by<GL, int>(bu, sb_, P.M, lane, dir, off, kw);
-            if (td) {
-                kk = birth ? k + 1 : k - 1;
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) {
-                    const int e = lane + GL * j;
-                    nx[j] = sx_[j]; nv[j] = sv_[j]; nbu[j] = sb_[j];
-                    if (birth) {
-                        if (e == nb) { nx[j] = snew; nv[j] = hbf; nbu[j] = bu[j]; }   // boundary searched below
-                        if (e == nb + 1) nv[j] = hb * r;
-                    } else if (e == nrand) {
-                        nv[j] = r;
+                for (int j = 0; j < EPL; ++j) xi[j] = row[RMN_CP_SLOT_XI + lane + GL * j];
+            } else {
+                float n0, n1;
+                box_muller(r.x, r.y, n0, n1);
+                xi[0] = (double)n0;
+                if (EPL > 1) xi[1 % EPL] = (double)n1;
+                if (EPL > 2) {
+                    xi[2 % EPL] = 0.0; xi[3 % EPL] = 0.0;
+                    if (kw >= 2 * GL) {
+                        const uint4 q = rk.block(step, (uint32_t)(GL + lane));
+                        box_muller(q.x, q.y, n0, n1);
+                        xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
                     }
                 }
             }
-        }
-        // elements beyond the new extent hold zeros (canonical padding)
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-            const int e = lane + GL * j;
-            if (e >= kk) { nx[j] = 0.0; nbu[j] = P.M; }
-            if (e > kk) nv[j] = 0.0;
-        }
-        // run boundaries only move when a location moves: a cpx block move (every element) or a
-        // birth (the new element).
-        const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
-        if (RMN_CP_UNCOND_SEARCH || __any_sync(0xffffffffu, moved_x)) {
-            constexpr int NA = Geo<GL>::ALWAYS;
-            double qa[NA];
-            int sa[NA];
-#pragma unroll
-            for (int j = 0; j < NA; ++j) qa[j] = nx[j];
-            upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
+        };
+
+        if (path == 2) {
+            // ---- sigma move (test_changepoint.py:54-56): only the sigma terms change
+            double n0d;
+            if (INJ) n0d = row[RMN_CP_SLOT_XI + lane];
+            else { float n0, n1; box_muller(r.x, r.y, n0, n1); n0d = (double)n0; }
+            const double xi0 = __shfl_sync(FULL, n0d, 0, GL);
+            const double nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
+            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
+            double d0, nls2, logu, d3;
+            log4<GL>(lane, 1.0, __dmul_rn(nsig, nsig), uacc, 1.0, d0, nls2, logu, d3);
+            const double lpn = cp_assemble(P, k, ss_c, vt_c, lg_c, nsig, nls2, 0);
+            const double delta = lpn - lp;                      // logqratio = 0
+            const double mh = (delta < 0.0) ? delta : 0.0;      // sampler.py:83-84 with Python's min(0, nan) == 0
+            const bool acc = logu < mh;
+            trace_prop(t, lpn, acc, 0.0, k, nsig, cx, cv);
+            if (acc) { sig = nsig; lp = lpn; ls2_c = nls2; }
+            nacc += acc ? 1 : 0;
+        } else if (path == 1) {
+            // ---- height move (:51-53): gaps and run boundaries stay
+            double xi[EPL], nv[EPL];
+            normals(xi);
 #pragma unroll
             for (int j = 0; j < EPL; ++j) {
                 const int e = lane + GL * j;
-                int sb = 0;
-                if (j < NA) sb = sa[j < NA ? j : 0];
-                else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
-                if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
+                nv[j] = cv[j];
+                if (ROW_ON(j) && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));   // randomwalk.py:26, scale = 1
             }
-        }
-
-#if RMN_CP_PREFETCH
-        if (!INJ) {
-            rA = rk.block(step + 1, (uint32_t)lane);
-            if (EPL > 2) rB = rk.block(step + 1, (uint32_t)(GL + lane));
-        }
-#endif
-        // ---- log-posterior of the proposal; every fp64 log of the step in one call
-        double logu, ljac;
-        const double lpn = cp_logpost_rows<GL>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, nsig, uacc, jarg, logu, ljac, 0);
-        const double lqr = (mv == 3) ? (birth ? ljac : -ljac) : 0.0;
-
-        // sampler.py:83-84 with Python's min(0, nan) == 0
-        const double delta = lpn - lp - lqr;
-        const double mh = (delta < 0.0) ? delta : 0.0;
-        const bool acc = !ovf && (logu < mh);
-        if (acc) {
-            k = kk; sig = nsig; lp = lpn;
+            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
+            double nss, nvt, dgp;
+            cp_terms<GL, true, true, false>(P, cy, cyy, lane, kw, k, cx, nv, bu, nss, nvt, dgp);
+            double d0, d1, logu, d3;
+            log4<GL>(lane, 1.0, 1.0, uacc, 1.0, d0, d1, logu, d3);
+            const double lpn = cp_assemble(P, k, nss, nvt, lg_c, sig, ls2_c, 0);
+            const double delta = lpn - lp;
+            const double mh = (delta < 0.0) ? delta : 0.0;
+            const bool acc = logu < mh;
+            trace_prop(t, lpn, acc, 0.0, k, sig, cx, nv);
+            if (acc) {
+                lp = lpn; ss_c = nss; vt_c = nvt;
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; cv[j] = nv[j]; bu[j] = nbu[j]; }
+                for (int j = 0; j < EPL; ++j) cv[j] = nv[j];
+            }
+            nacc += acc ? 1 : 0;
+        } else if (path == 0) {
+            // ---- location move (:48-50): every run boundary is searched again, heights stay
+            double xi[EPL], nx[EPL];
+            int nbu[EPL];
+            normals(xi);
+            const double sxk = P.sx[k];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + GL * j;
+                nx[j] = cx[j];
+                if (ROW_ON(j) && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));
+            }
+            {
+                constexpr int NA = Geo<GL>::ALWAYS;
+                double qa[NA];
+                int sa[NA];
+#pragma unroll
+                for (int j = 0; j < NA; ++j) qa[j] = nx[j];
+                upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const int e = lane + GL * j;
+                    int sb = P.M;
+                    if (j < NA) sb = sa[j < NA ? j : 0];
+                    else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
+                    nbu[j] = (e < k) ? sb : P.M;
+                }
+            }
+            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
+            double nss, dvt, gp;
+            cp_terms<GL, true, false, true>(P, cy, cyy, lane, kw, k, nx, cv, nbu, nss, dvt, gp);
+            double nlg, d1, logu, d3;
+            log4<GL>(lane, gp, 1.0, uacc, 1.0, nlg, d1, logu, d3);
+            const double lpn = cp_assemble(P, k, nss, vt_c, nlg, sig, ls2_c, 0);
+            const double delta = lpn - lp;
+            const double mh = (delta < 0.0) ? delta : 0.0;
+            const bool acc = logu < mh;
+            trace_prop(t, lpn, acc, 0.0, k, sig, nx, cv);
+            if (acc) {
+                lp = lpn; ss_c = nss; lg_c = nlg;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; bu[j] = nbu[j]; }
+            }
+            nacc += acc ? 1 : 0;
+        } else {
+            // ---- general path: the proposal is built by selection (the chains of a warp never diverge on mv);
+            //      also the only path with the trans-dimensional moves
+            double xi[EPL];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) xi[j] = 0.0;
+            if (!(uniform && mvu == 3)) normals(xi);            // a warp of birth/death moves needs no normals
+            int kk = k, nbu[EPL];
+            double nx[EPL], nv[EPL], nsig = sig, jarg = 1.0;
+            bool ovf = false;
+            const double sxk = P.sx[k];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + GL * j;
+                nx[j] = cx[j]; nv[j] = cv[j]; nbu[j] = bu[j];
+                if (ROW_ON(j)) {
+                    if (mv == 0 && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));   // randomwalk.py:26, scale = 1
+                    if (mv == 1 && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));
+                }
+            }
+            const double xi0 = __shfl_sync(FULL, xi[0], 0, GL);
+            if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
+            int nb = 0;
+            if (__any_sync(FULL, mv == 3)) {                            // warp-uniform
+                nb = count_below<GL>(cx, lane, k, snew, kw);            // searchsorted(cpx, s), :206
+                const double hb = elem_at<GL>(cv, nb, kw);
+                const double h1d = elem_at<GL>(cv, nrand, kw);
+                const double h2d = elem_at<GL>(cv, nrand + 1, kw);
+                // birth (changepoint.py:57,61,72-74) and death (:67-68,76-78) share one instruction
+                // stream: the operands of each division / square root are selected per chain
+                const double q1 = birth ? du / P.sqrtM : h2d / h1d;
+                const double ub = 0.5 + q1;                                 // birth: u, :61
+                const double q2 = birth ? (1.0 - ub) / ub : 1.0 / (1.0 + q1);       // birth: f^2; death: u, :68
+                const double u = birth ? ub : q2;
+                const double rr = sqrt(birth ? q2 : h1d * h2d);             // birth: f, :57; death: h, :67
+                jarg = fabs((birth ? hb : rr) / (u * (1.0 - u)));           // |J| resp. 1/|J^-1|
+                const double hbf = hb / rr;
+                ovf = (mv == 3) && birth && (k + 1 > LANES - 1);
+                const bool td = (mv == 3) && !ovf;
+                if (!(mv == 3)) jarg = 1.0;
+                // insert / delete = every element reads its neighbour below (birth, above the insertion
+                // point) or above (death, from the removed element on); other chains read themselves
+                const int dir = birth ? -1 : 1;
+                const int pivot = birth ? nb : nrand - 1;                   // elements <= pivot stay
+                int off[EPL];
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) off[j] = (td && lane + GL * j > pivot) ? dir : 0;
+                double sx_[EPL], sv_[EPL];
+                int sb_[EPL];
+                shift_by<GL, double>(cx, sx_, 0.0, lane, dir, off, kw);
+                shift_by<GL, double>(cv, sv_, 0.0, lane, dir, off, kw);
+                shift_by<GL, int>(bu, sb_, P.M, lane, dir, off, kw);
+                if (td) {
+                    kk = birth ? k + 1 : k - 1;
+#pragma unroll
+                    for (int j = 0; j < EPL; ++j) {
+                        const int e = lane + GL * j;
+                        nx[j] = sx_[j]; nv[j] = sv_[j]; nbu[j] = sb_[j];
+                        if (birth) {
+                            if (e == nb) { nx[j] = snew; nv[j] = hbf; nbu[j] = bu[j]; }   // boundary searched below
+                            if (e == nb + 1) nv[j] = hb * rr;
+                        } else if (e == nrand) {
+                            nv[j] = rr;
+                        }
+                    }
+                }
+            }
+            // elements beyond the new extent hold zeros (canonical padding)
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + GL * j;
+                if (e >= kk) { nx[j] = 0.0; nbu[j] = P.M; }
+                if (e > kk) nv[j] = 0.0;
+            }
+            // run boundaries only move when a location moves: a cpx block move (every element) or a
+            // birth (the new element).
+            const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
+            {
+                constexpr int NA = Geo<GL>::ALWAYS;
+                double qa[NA];
+                int sa[NA];
+#pragma unroll
+                for (int j = 0; j < NA; ++j) qa[j] = nx[j];
+                upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const int e = lane + GL * j;
+                    int sb = 0;
+                    if (j < NA) sb = sa[j < NA ? j : 0];
+                    else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
+                    if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
+                }
+            }
+            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
+            // ---- log-posterior of the proposal; every fp64 log of the step in one call
+            double nss, nvt, gp, nlg, nls2, logu, ljac;
+            cp_terms<GL, true, true, true>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, nss, nvt, gp);
+            log4<GL>(lane, gp, __dmul_rn(nsig, nsig), uacc, jarg, nlg, nls2, logu, ljac);
+            const double lpn = cp_assemble(P, kk, nss, nvt, nlg, nsig, nls2, 0);
+            const double lqr = (mv == 3) ? (birth ? ljac : -ljac) : 0.0;
+
+            // sampler.py:83-84 with Python's min(0, nan) == 0
+            const double delta = lpn - lp - lqr;
+            const double mh = (delta < 0.0) ? delta : 0.0;
+            const bool acc = !ovf && (logu < mh);
+            trace_prop(t, lpn, acc, lqr, kk, nsig, nx, nv);
+            if (acc) {
+                k = kk; sig = nsig; lp = lpn;
+                ss_c = nss; vt_c = nvt; lg_c = nlg; ls2_c = nls2;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; cv[j] = nv[j]; bu[j] = nbu[j]; }
+            }
+            nacc += acc ? 1 : 0;
+            novf += ovf ? 1 : 0;
         }
-        nacc += acc ? 1 : 0;
-        novf += ovf ? 1 : 0;
 
         if ((step % RMN_CP_DIAG_EVERY) == 0) {              // thinned accumulation (warp-uniform)
-            // (k <= kw + 1 after an accepted birth, so the step's row guard still covers the state)
+            const int kd = __reduce_max_sync(FULL, k);      // (an accepted birth may have raised the extent)
             double f[NS];
 #pragma unroll
             for (int s = 0; s < NS; ++s) f[s] = 0.0;
@@ -473,8 +637,8 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             if (lane == 1 % GL) f[1 / GL] = (double)k;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const int cnt = count_below<GL>(cx, lane, k, P.xq[q], kw);
-                const double yq = elem_at<GL>(cv, cnt, kw);
+                const int cnt = count_below<GL>(cx, lane, k, P.xq[q], kd);
+                const double yq = elem_at<GL>(cv, cnt, kd);
                 if (lane == (2 + q) % GL) f[(2 + q) / GL] = yq;
             }
 #pragma unroll
@@ -482,34 +646,19 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                 if (lane + GL * s < RMN_CP_NDIAG) { s1[s] += f[s]; s2[s] += f[s] * f[s]; }
         }
 
-        if (live && (tracing || tracing_prop)) {
-            if (lane == 0) {
-                if (tr.d_prop_logpost) tr.d_prop_logpost[t * K + c] = lpn;
-                if (tr.d_accepted) tr.d_accepted[t * K + c] = acc ? 1 : 0;
-                if (tr.d_logqratio) tr.d_logqratio[t * K + c] = lqr;
-                if (tr.d_prop_k) tr.d_prop_k[t * K + c] = kk;
-                if (tr.d_prop_sig) tr.d_prop_sig[t * K + c] = nsig;
-            }
+        if (live && tracing) {
+            const long long rrec = ts.slot(t + 1);
+            if (rrec >= 0) {
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const int e = lane + GL * j;
-                if (tr.d_prop_cpx) tr.d_prop_cpx[(t * K + c) * LANES + e] = nx[j];
-                if (tr.d_prop_cpv) tr.d_prop_cpv[(t * K + c) * LANES + e] = nv[j];
-            }
-            if (tracing) {
-                const long long r = ts.slot(t + 1);
-                if (r >= 0) {
-#pragma unroll
-                    for (int j = 0; j < EPL; ++j) {
-                        const int e = lane + GL * j;
-                        if (tr.d_cpx) tr.d_cpx[(r * K + c) * LANES + e] = cx[j];
-                        if (tr.d_cpv) tr.d_cpv[(r * K + c) * LANES + e] = cv[j];
-                    }
-                    if (lane == 0) {
-                        if (tr.d_k) tr.d_k[r * K + c] = k;
-                        if (tr.d_sig) tr.d_sig[r * K + c] = sig;
-                        if (tr.d_logpost) tr.d_logpost[r * K + c] = lp;
-                    }
+                for (int j = 0; j < EPL; ++j) {
+                    const int e = lane + GL * j;
+                    if (tr.d_cpx) tr.d_cpx[(rrec * K + c) * LANES + e] = cx[j];
+                    if (tr.d_cpv) tr.d_cpv[(rrec * K + c) * LANES + e] = cv[j];
+                }
+                if (lane == 0) {
+                    if (tr.d_k) tr.d_k[rrec * K + c] = k;
+                    if (tr.d_sig) tr.d_sig[rrec * K + c] = sig;
+                    if (tr.d_logpost) tr.d_logpost[rrec * K + c] = lp;
                 }
             }
         }
@@ -560,8 +709,8 @@ cp_eval_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gd
     int b1[1] = {(lane < k) ? upper_bound<-1>(xs, P.P2, x1[0]) : P.M};
     if (lane >= k) x1[0] = 0.0;
     if (lane > k) v1[0] = 0.0;
-    double logu, ljac;
-    const double v = cp_logpost_rows<GL>(P, cy, cyy, lane, kw, k, x1, v1, b1, sig[c], 1.0, 1.0, logu, ljac, which);
+    double ss, vt, lg, ls2;
+    const double v = cp_logpost_rows<GL>(P, cy, cyy, lane, kw, k, x1, v1, b1, sig[c], which, ss, vt, lg, ls2);
     if (live && lane == 0) out[c] = v;
 }
 
@@ -624,12 +773,15 @@ struct ChangepointSampler : SamplerImpl {
     bool use_smem;
     size_t smem_bytes;
     int gl = RMN_CP_DEFAULT_GL;     // lanes per chain (4, 8 or 16); RMN_CP_GL overrides (A/B measurements)
+    int shared_mv = 1;              // Philox mode: move types shared by aligned groups of 32/gl chains (see the kernel);
+                                    // rmn_sampler_set_move_schedule / RMN_CP_SCHEDULE=chain select per-chain move types
     explicit ChangepointSampler(rmn_sampler* s_) : s(s_) {
         P = make_params(s->model, s->prop);
         if (const char* e = getenv("RMN_CP_GL")) {
             const int v = atoi(e);
             if (v == 4 || v == 8 || v == 16) gl = v;
         }
+        if (const char* e = getenv("RMN_CP_SCHEDULE")) shared_mv = (e[0] == 'c' || e[0] == '0') ? 0 : 1;
         smem_bytes = (size_t)(P.XP + 2 * P.M + 2) * 8;
         use_smem = smem_bytes <= 96 * 1024;
     }
@@ -666,6 +818,17 @@ struct ChangepointSampler : SamplerImpl {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     }
     unsigned grid(int gl = LANES) const { return (unsigned)((s->K * gl + 127) / 128); }
+    // grid of the T-step kernel: schedule groups are aligned to global chain ids, so up to 32/gl - 1 leading
+    // groups of the grid are dead when the shard does not start on a group boundary
+    unsigned run_grid(int gl, int shared) const {
+        const int64_t head = shared ? (s->chain_offset & (int64_t)(32 / gl - 1)) : 0;
+        return (unsigned)(((s->K + head) * gl + 127) / 128);
+    }
+    int set_move_schedule(int mode) override {
+        RMN_REQUIRE(mode == 0 || mode == 1, "move schedule: 0 = per chain, 1 = shared by aligned groups of chains");
+        shared_mv = mode;
+        return RMN_OK;
+    }
 
     int cp_set_state(const int32_t* d_k, const double* d_cpx, const double* d_cpv,
                      const double* d_sig, cudaStream_t stream) override {
@@ -698,15 +861,17 @@ struct ChangepointSampler : SamplerImpl {
     }
     template <bool INJ, int GL>
     void launch_gl(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
+        const int sh = INJ ? 0 : shared_mv;
+        const unsigned g = run_grid(GL, sh);
         if (use_smem && P.P2 == 64)
-            changepoint_kernel<INJ, 2, GL><<<grid(GL), 128, smem_bytes, stream>>>(
-                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
+            changepoint_kernel<INJ, 2, GL><<<g, 128, smem_bytes, stream>>>(
+                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);
         else if (use_smem)
-            changepoint_kernel<INJ, 1, GL><<<grid(GL), 128, smem_bytes, stream>>>(
-                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
+            changepoint_kernel<INJ, 1, GL><<<g, 128, smem_bytes, stream>>>(
+                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);
         else
-            changepoint_kernel<INJ, 0, GL><<<grid(GL), 128, 0, stream>>>(
-                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0);
+            changepoint_kernel<INJ, 0, GL><<<g, 128, 0, stream>>>(
+                P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);
     }
     int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
         rmn_trace_t t0{};
@@ -735,6 +900,10 @@ struct ChangepointSampler : SamplerImpl {
         RMN_CUDA(cudaMemsetAsync(st.dacc, 0, (size_t)s->K * 8, stream));
         RMN_CUDA(cudaMemsetAsync(st.dovf, 0, (size_t)s->K * 8, stream));
         diag_steps = 0; diag_samples = 0;
+        return RMN_OK;
+    }
+    int chain_sums(const double** S1, const double** S2, int64_t* n) override {
+        *S1 = st.S1; *S2 = st.S2; *n = diag_samples;
         return RMN_OK;
     }
     int reduce_diag(double* d_block, cudaStream_t stream) override {

@@ -268,6 +268,9 @@ struct SamplerImpl {
     virtual int set_tempering(int, const double*, double) { return unsupported("parallel tempering (small-d Gaussian samplers only)"); }
     virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }
     virtual int set_adapt(const double*, const int64_t*, const int64_t*, cudaStream_t) { return unsupported("set_adapt"); }
+    virtual int set_move_schedule(int) { return unsupported("move schedule (changepoint samplers only)"); }
+    // raw per-chain diagnostics sums S1, S2 [nd][K] (chain fastest) and the number of samples behind them
+    virtual int chain_sums(const double** S1, const double** S2, int64_t* nsamples) { return unsupported("per-chain moments"); }
     virtual int diag_dim() const = 0;
     virtual int reset_diag(cudaStream_t st) = 0;
     virtual int reduce_diag(double* d_block, cudaStream_t st) = 0;
@@ -314,5 +317,9 @@ int rmn_copy_adapt(int64_t K, const double* sc_in, const int64_t* ns_in, const i
 int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsamples, int64_t nsteps, const double* S1, const double* S2,
                           const long long* acc, const long long* ovf, double* d_block,
                           cudaStream_t st);
+
+// per-chain mean / biased variance of the tracked functionals from the raw sums (util.cu)
+int rmn_chain_moments(int64_t K, int nd, int64_t nsamples, const double* S1, const double* S2, double* d_mean,
+                      double* d_var, cudaStream_t st);
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }

@@ -742,6 +742,10 @@ struct DenseGaussSampler : SamplerImpl {
         diag_steps = 0;
         return RMN_OK;
     }
+    int chain_sums(const double** S1, const double** S2, int64_t* n) override {
+        *S1 = st.S1; *S2 = st.S2; *n = diag_steps;
+        return RMN_OK;
+    }
     int reduce_diag(double* d_block, cudaStream_t stream) override {
         launches++;
         return rmn_reduce_diag_block(st.K, diag_dim(), diag_steps, diag_steps, st.S1, st.S2, st.dacc, nullptr, d_block, stream);

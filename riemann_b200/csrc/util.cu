@@ -98,7 +98,26 @@ __global__ void rng_draws_kernel(uint64_t seed, int64_t chain0, int64_t step, in
     uniform[i] = u01(rk.block((uint64_t)step, RMN_BLOCK_ACCEPT).x);
 }
 
+__global__ void chain_moments_kernel(int64_t n, double inv, const double* __restrict__ S1, const double* __restrict__ S2,
+                                     double* __restrict__ mean, double* __restrict__ var) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = S1[i] * inv;
+    if (mean) mean[i] = m;
+    if (var) var[i] = S2[i] * inv - m * m;
+}
+
 }  // namespace
+
+int rmn_chain_moments(int64_t K, int nd, int64_t nsamples, const double* S1, const double* S2, double* d_mean,
+                      double* d_var, cudaStream_t st) {
+    const int64_t n = K * (int64_t)nd;
+    if (n <= 0) return RMN_OK;
+    RMN_REQUIRE(nsamples > 0, "rmn_sampler_chain_moments: no samples accumulated since the last reset");
+    chain_moments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, 1.0 / (double)nsamples, S1, S2, d_mean, d_var);
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}
 
 int rmn_fill_f64(double* p, int64_t n, double v, cudaStream_t st) {
     if (n <= 0) return RMN_OK;

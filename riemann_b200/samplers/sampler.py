@@ -43,7 +43,7 @@ class ChangepointTrace(object):
 
 class Sampler(object):
     def __init__(self, model, proposal, theta0, K=None, seed=0, chain_offset=0, precision="f64", _tempering=None,
-                 row_sharded=False):
+                 row_sharded=False, move_schedule=None):
         """
         :param theta0: starting point.  Fixed-d models: shape (d,) (shared by all K
             chains) or (K, d); a length-1 start is broadcast over the d coordinates, as numpy does inside
@@ -53,6 +53,8 @@ class Sampler(object):
         :param seed, chain_offset: Philox key and the global id of chain 0 on this device
         :param precision: "f64" (default; fp64 like the reference) or "tf32x3" (dense Gaussian
             model: fp32 state, tcgen05 tensor-core product with a 3xTF32 split, fp64 accept test)
+        :param move_schedule: changepoint model, Philox mode: "group" (default; aligned groups of 8 global chain ids
+            share the move-type draws of a step, rmn_sampler_set_move_schedule) or "chain" (every chain draws its own).
         :param row_sharded: logistic model only.  Every rank of the torch.distributed group built its model from its
             own slice of the data rows (`distributed.shard_rows`) and runs the SAME K chains (same seed, chain_offset
             and start states); after every likelihood sweep the per-chain partial sums are all-reduced (NCCL, inside
@@ -117,6 +119,10 @@ class Sampler(object):
         self.seed, self.chain_offset = int(seed), int(chain_offset)
         self.total_steps = 0
 
+        if move_schedule is not None:
+            if move_schedule not in ("group", "chain"):
+                raise ParameterError('move_schedule must be "group" or "chain"')
+            _lib.check(lib.rmn_sampler_set_move_schedule(h, 1 if move_schedule == "group" else 0))
         self.row_sharded = bool(row_sharded)
         if self.row_sharded:                  # before the first evaluation: it already sums over the ranks' rows
             from ..distributed import exchange_unique_id, rank_world
@@ -471,6 +477,16 @@ class Sampler(object):
         _lib.check(_lib.load().rmn_sampler_reduce_diagnostics(self._handle, _lib.ptr(blk),
                                                               _lib.stream_ptr()))
         return blk
+
+    def chain_moments(self):
+        """Per-chain mean and (biased) variance of the tracked functionals since the last reset: two host arrays
+        [nd, K] (rmn_sampler_chain_moments)."""
+        torch = self._torch
+        nd = _lib.load().rmn_sampler_diag_dim(self._handle)
+        m = torch.empty((nd, self.K), dtype=torch.float64, device="cuda")
+        v = torch.empty((nd, self.K), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().rmn_sampler_chain_moments(self._handle, _lib.ptr(m), _lib.ptr(v), _lib.stream_ptr()))
+        return m.cpu().numpy(), v.cpu().numpy()
 
     def diagnostics(self, allreduce=True):
         """
