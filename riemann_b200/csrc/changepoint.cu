@@ -171,47 +171,58 @@ __device__ __forceinline__ int count_below(const double (&cx)[Geo<GL>::EPL], int
 // bits (no context-dependent FMA contraction).  Differences from numpy's term-by-term sums are O(1e-15)
 // relative (tests: 1e-9).
 // ---------------------------------------------------------------------------------------
-template <int GL, bool WSS, bool WVT, bool WGP>
+template <int GL>
 __device__ __forceinline__ void cp_terms(const CPParams& P, const double* __restrict__ cy,
                                          const double* __restrict__ cyy, int lane, int kw, int kk,
                                          const double (&nx)[Geo<GL>::EPL], const double (&nv)[Geo<GL>::EPL],
-                                         const int (&nbu)[Geo<GL>::EPL], double& ss, double& vt, double& gp) {
+                                         const int (&nbu)[Geo<GL>::EPL], bool wss, bool wvt, bool wgp,
+                                         double& ss, double& vt, double& gp) {
+    // wss / wvt / wgp are WARP-UNIFORM: which of the three sums any chain of the warp needs recomputed
     constexpr int EPL = Geo<GL>::EPL;
-    double px[EPL];
-    int pb[EPL];
-    if (WGP) shift_prev<GL, double>(nx, px, P.xmin, lane, kw);
-    if (WSS) shift_prev<GL, int>(nbu, pb, 0, lane, kw);
-    double a = 0.0, b = 0.0, g = 1.0;
+    if (wss) {
+        int pb[EPL];
+        shift_prev<GL, int>(nbu, pb, 0, lane, kw);
+        double a = 0.0;
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-        if (ROW_ON(j)) {
-            const int e = lane + GL * j;
-            if (e <= kk) {
-                if (WSS) {
-                    const int bu = nbu[j], bl = pb[j];
-                    const double n = (double)(bu - bl);
-                    const double s1 = __dsub_rn(cy[bu], cy[bl]);
-                    const double s2 = __dsub_rn(cyy[bu], cyy[bl]);
-                    const double vc = __dsub_rn(nv[j], P.ycenter);
-                    // n vc^2 - 2 vc s1 + s2
-                    a = __dadd_rn(a, __fma_rn(__dmul_rn(n, vc), vc, __fma_rn(-2.0 * vc, s1, s2)));
-                }
-                if (WGP) {
-                    const double gap = __dsub_rn((e < kk) ? nx[j] : P.xmax, px[j]);       // changepoint.py:142-143
-                    g = __dmul_rn(g, (gap < 0.0) ? NAN : gap);
-                }
-                if (WVT) {
-                    double t = __fma_rn(-P.beta, nv[j], P.cv);                            // changepoint.py:18-19,136
-                    if (!P.alpha_is_one) t = __fma_rn(P.alpha - 1.0, log(nv[j]), t);
-                    else if (!(nv[j] > 0.0)) t = NAN;                                     // 0 * log(v<=0) is nan in numpy
-                    b = __dadd_rn(b, t);
-                }
+        for (int j = 0; j < EPL; ++j) {
+            if (ROW_ON(j) && lane + GL * j <= kk) {
+                const int bu = nbu[j], bl = pb[j];
+                const double n = (double)(bu - bl);
+                const double s1 = __dsub_rn(cy[bu], cy[bl]);
+                const double s2 = __dsub_rn(cyy[bu], cyy[bl]);
+                const double vc = __dsub_rn(nv[j], P.ycenter);
+                a = __dadd_rn(a, __fma_rn(__dmul_rn(n, vc), vc, __fma_rn(-2.0 * vc, s1, s2)));   // n vc^2 - 2 vc s1 + s2
             }
         }
+        ss = gsum<GL>(a);
     }
-    if (WSS) ss = gsum<GL>(a);
-    if (WVT) vt = gsum<GL>(b);
-    if (WGP) gp = gprod<GL>(g);
+    if (wgp) {
+        double px[EPL];
+        shift_prev<GL, double>(nx, px, P.xmin, lane, kw);
+        double g = 1.0;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            const int e = lane + GL * j;
+            if (ROW_ON(j) && e <= kk) {
+                const double gap = __dsub_rn((e < kk) ? nx[j] : P.xmax, px[j]);           // changepoint.py:142-143
+                g = __dmul_rn(g, (gap < 0.0) ? NAN : gap);
+            }
+        }
+        gp = gprod<GL>(g);
+    }
+    if (wvt) {
+        double b = 0.0;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+            if (ROW_ON(j) && lane + GL * j <= kk) {
+                double t = __fma_rn(-P.beta, nv[j], P.cv);                                // changepoint.py:18-19,136
+                if (!P.alpha_is_one) t = __fma_rn(P.alpha - 1.0, log(nv[j]), t);
+                else if (!(nv[j] > 0.0)) t = NAN;                                         // 0 * log(v<=0) is nan in numpy
+                b = __dadd_rn(b, t);
+            }
+        }
+        vt = gsum<GL>(b);
+    }
 }
 
 // log of four per-chain arguments with one call: lane (l & 3) of the group takes argument l & 3
@@ -252,7 +263,7 @@ __device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const doubl
                                                   const int (&nbu)[Geo<GL>::EPL], double nsig, int which,
                                                   double& ss, double& vt, double& lg, double& log_s2) {
     double gp, d2, d3;
-    cp_terms<GL, true, true, true>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, ss, vt, gp);
+    cp_terms<GL>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, true, true, true, ss, vt, gp);
     log4<GL>(lane, gp, __dmul_rn(nsig, nsig), 1.0, 1.0, lg, log_s2, d2, d3);
     return cp_assemble(P, kk, ss, vt, lg, nsig, log_s2, which);
 }
@@ -339,7 +350,6 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     const bool tracing = tr.d_k || tr.d_cpx || tr.d_cpv || tr.d_sig || tr.d_logpost;
     const bool tracing_prop = tr.d_prop_logpost || tr.d_accepted || tr.d_logqratio || tr.d_prop_k ||
                               tr.d_prop_sig || tr.d_prop_cpx || tr.d_prop_cpv;
-    const bool fast_ok = RMN_CP_FASTPATHS && (INJ || shared_mv);
 
     // per-step proposal record (parity harness): what Proposal.propose returned, what the sampler decided
     auto trace_prop = [&](int64_t t, double lpn, bool acc, double lqr, int kk, double nsig,
@@ -399,183 +409,91 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             uacc = u01_fast(w3);
         }
         nrand = max(0, min(nrand, k - 1));
-        const int mvu = __shfl_sync(FULL, mv, 0);
-        const bool uniform = __all_sync(FULL, mv == mvu);
-        const int path = (fast_ok && uniform) ? mvu : 3;           // warp-uniform
+        // What the warp as a whole needs this step (warp-uniform).  With a shared move schedule all chains of the
+        // warp drew the same move, so most of the step's blocks are skipped by real branches; with per-chain move types
+        // the guards are almost always taken and the warp executes the union, selecting per chain.
+        const bool any0 = __any_sync(FULL, mv == 0), any1 = __any_sync(FULL, mv == 1);
+        const bool any3 = __any_sync(FULL, mv == 3);
+        const bool skip = RMN_CP_FASTPATHS && (INJ || shared_mv);      // per-chain Philox mode keeps ONE instruction stream
+        const bool need_xi = !skip || __any_sync(FULL, mv != 3);
 
         // normals of the block moves: rows 0,1 from this step's block, rows 2,3 (only when some chain of the
-        // warp has an element there) from a second block
-        auto normals = [&](double (&xi)[EPL]) {
-            if (INJ) {
+        // warp has an element there and a location / height move is being made) from a second block
+        double xi[EPL];
 #pragma unroll
-                for (int j = 0; j < EPL; ++j) xi[j] = row[RMN_CP_SLOT_XI + lane + GL * j];
-            } else {
-                float n0, n1;
-                box_muller(r.x, r.y, n0, n1);
-                xi[0] = (double)n0;
-                if (EPL > 1) xi[1 % EPL] = (double)n1;
-                if (EPL > 2) {
-                    xi[2 % EPL] = 0.0; xi[3 % EPL] = 0.0;
-                    if (kw >= 2 * GL) {
-                        const uint4 q = rk.block(step, (uint32_t)(GL + lane));
-                        box_muller(q.x, q.y, n0, n1);
-                        xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
-                    }
-                }
+        for (int j = 0; j < EPL; ++j) xi[j] = 0.0;
+        if (INJ) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) xi[j] = row[RMN_CP_SLOT_XI + lane + GL * j];
+        } else if (need_xi) {
+            float n0, n1;
+            box_muller(r.x, r.y, n0, n1);
+            xi[0] = (double)n0;
+            if (EPL > 1) xi[1 % EPL] = (double)n1;
+            if (EPL > 2 && kw >= 2 * GL && (!skip || any0 || any1)) {
+                const uint4 q = rk.block(step, (uint32_t)(GL + lane));
+                box_muller(q.x, q.y, n0, n1);
+                xi[2 % EPL] = (double)n0; xi[3 % EPL] = (double)n1;
             }
-        };
+        }
 
-        if (path == 2) {
-            // ---- sigma move (test_changepoint.py:54-56): only the sigma terms change
-            double n0d;
-            if (INJ) n0d = row[RMN_CP_SLOT_XI + lane];
-            else { float n0, n1; box_muller(r.x, r.y, n0, n1); n0d = (double)n0; }
-            const double xi0 = __shfl_sync(FULL, n0d, 0, GL);
-            const double nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
-            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
-            double d0, nls2, logu, d3;
-            log4<GL>(lane, 1.0, __dmul_rn(nsig, nsig), uacc, 1.0, d0, nls2, logu, d3);
-            const double lpn = cp_assemble(P, k, ss_c, vt_c, lg_c, nsig, nls2, 0);
-            const double delta = lpn - lp;                      // logqratio = 0
-            const double mh = (delta < 0.0) ? delta : 0.0;      // sampler.py:83-84 with Python's min(0, nan) == 0
-            const bool acc = logu < mh;
-            trace_prop(t, lpn, acc, 0.0, k, nsig, cx, cv);
-            if (acc) { sig = nsig; lp = lpn; ls2_c = nls2; }
-            nacc += acc ? 1 : 0;
-        } else if (path == 1) {
-            // ---- height move (:51-53): gaps and run boundaries stay
-            double xi[EPL], nv[EPL];
-            normals(xi);
+        // ---- build the proposal by selection (the chains of a warp never diverge on mv)
+        int kk = k, nbu[EPL];
+        double nx[EPL], nv[EPL], nsig = sig, jarg = 1.0;
+        bool ovf = false;
+        const double sxk = P.sx[k];
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const int e = lane + GL * j;
-                nv[j] = cv[j];
-                if (ROW_ON(j) && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));   // randomwalk.py:26, scale = 1
+        for (int j = 0; j < EPL; ++j) {
+            const int e = lane + GL * j;
+            nx[j] = cx[j]; nv[j] = cv[j]; nbu[j] = bu[j];
+            if (ROW_ON(j)) {
+                if (mv == 0 && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));   // randomwalk.py:26, scale = 1
+                if (mv == 1 && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));
             }
-            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
-            double nss, nvt, dgp;
-            cp_terms<GL, true, true, false>(P, cy, cyy, lane, kw, k, cx, nv, bu, nss, nvt, dgp);
-            double d0, d1, logu, d3;
-            log4<GL>(lane, 1.0, 1.0, uacc, 1.0, d0, d1, logu, d3);
-            const double lpn = cp_assemble(P, k, nss, nvt, lg_c, sig, ls2_c, 0);
-            const double delta = lpn - lp;
-            const double mh = (delta < 0.0) ? delta : 0.0;
-            const bool acc = logu < mh;
-            trace_prop(t, lpn, acc, 0.0, k, sig, cx, nv);
-            if (acc) {
-                lp = lpn; ss_c = nss; vt_c = nvt;
+        }
+        const double xi0 = __shfl_sync(FULL, xi[0], 0, GL);
+        if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
+        int nb = 0;
+        if (any3) {                                                     // warp-uniform
+            nb = count_below<GL>(cx, lane, k, snew, kw);                // searchsorted(cpx, s), :206
+            const double hb = elem_at<GL>(cv, nb, kw);
+            const double h1d = elem_at<GL>(cv, nrand, kw);
+            const double h2d = elem_at<GL>(cv, nrand + 1, kw);
+            // birth (changepoint.py:57,61,72-74) and death (:67-68,76-78) share one instruction
+            // stream: the operands of each division / square root are selected per chain
+            const double q1 = birth ? du / P.sqrtM : h2d / h1d;
+            const double ub = 0.5 + q1;                                 // birth: u, :61
+            const double q2 = birth ? (1.0 - ub) / ub : 1.0 / (1.0 + q1);       // birth: f^2; death: u, :68
+            const double u = birth ? ub : q2;
+            const double rr = sqrt(birth ? q2 : h1d * h2d);             // birth: f, :57; death: h, :67
+            jarg = fabs((birth ? hb : rr) / (u * (1.0 - u)));           // |J| resp. 1/|J^-1|
+            const double hbf = hb / rr;
+            ovf = (mv == 3) && birth && (k + 1 > LANES - 1);
+            const bool td = (mv == 3) && !ovf;
+            if (!(mv == 3)) jarg = 1.0;
+            // insert / delete = every element reads its neighbour below (birth, above the insertion
+            // point) or above (death, from the removed element on); other chains read themselves
+            const int dir = birth ? -1 : 1;
+            const int pivot = birth ? nb : nrand - 1;                   // elements <= pivot stay
+            int off[EPL];
 #pragma unroll
-                for (int j = 0; j < EPL; ++j) cv[j] = nv[j];
-            }
-            nacc += acc ? 1 : 0;
-        } else if (path == 0) {
-            // ---- location move (:48-50): every run boundary is searched again, heights stay
-            double xi[EPL], nx[EPL];
-            int nbu[EPL];
-            normals(xi);
-            const double sxk = P.sx[k];
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const int e = lane + GL * j;
-                nx[j] = cx[j];
-                if (ROW_ON(j) && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));
-            }
-            {
-                constexpr int NA = Geo<GL>::ALWAYS;
-                double qa[NA];
-                int sa[NA];
-#pragma unroll
-                for (int j = 0; j < NA; ++j) qa[j] = nx[j];
-                upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
+            for (int j = 0; j < EPL; ++j) off[j] = (td && lane + GL * j > pivot) ? dir : 0;
+            double sx_[EPL], sv_[EPL];
+            int sb_[EPL];
+            shift_by<GL, double>(cx, sx_, 0.0, lane, dir, off, kw);
+            shift_by<GL, double>(cv, sv_, 0.0, lane, dir, off, kw);
+            shift_by<GL, int>(bu, sb_, P.M, lane, dir, off, kw);
+            if (td) {
+                kk = birth ? k + 1 : k - 1;
 #pragma unroll
                 for (int j = 0; j < EPL; ++j) {
                     const int e = lane + GL * j;
-                    int sb = P.M;
-                    if (j < NA) sb = sa[j < NA ? j : 0];
-                    else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
-                    nbu[j] = (e < k) ? sb : P.M;
-                }
-            }
-            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
-            double nss, dvt, gp;
-            cp_terms<GL, true, false, true>(P, cy, cyy, lane, kw, k, nx, cv, nbu, nss, dvt, gp);
-            double nlg, d1, logu, d3;
-            log4<GL>(lane, gp, 1.0, uacc, 1.0, nlg, d1, logu, d3);
-            const double lpn = cp_assemble(P, k, nss, vt_c, nlg, sig, ls2_c, 0);
-            const double delta = lpn - lp;
-            const double mh = (delta < 0.0) ? delta : 0.0;
-            const bool acc = logu < mh;
-            trace_prop(t, lpn, acc, 0.0, k, sig, nx, cv);
-            if (acc) {
-                lp = lpn; ss_c = nss; lg_c = nlg;
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; bu[j] = nbu[j]; }
-            }
-            nacc += acc ? 1 : 0;
-        } else {
-            // ---- general path: the proposal is built by selection (the chains of a warp never diverge on mv);
-            //      also the only path with the trans-dimensional moves
-            double xi[EPL];
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) xi[j] = 0.0;
-            if (!(uniform && mvu == 3)) normals(xi);            // a warp of birth/death moves needs no normals
-            int kk = k, nbu[EPL];
-            double nx[EPL], nv[EPL], nsig = sig, jarg = 1.0;
-            bool ovf = false;
-            const double sxk = P.sx[k];
-#pragma unroll
-            for (int j = 0; j < EPL; ++j) {
-                const int e = lane + GL * j;
-                nx[j] = cx[j]; nv[j] = cv[j]; nbu[j] = bu[j];
-                if (ROW_ON(j)) {
-                    if (mv == 0 && e < k) nx[j] = __dadd_rn(cx[j], __dmul_rn(sxk, xi[j]));   // randomwalk.py:26, scale = 1
-                    if (mv == 1 && e <= k) nv[j] = __dadd_rn(cv[j], __dmul_rn(P.sv, xi[j]));
-                }
-            }
-            const double xi0 = __shfl_sync(FULL, xi[0], 0, GL);
-            if (mv == 2) nsig = __dadd_rn(sig, __dmul_rn(P.ss, xi0));
-            int nb = 0;
-            if (__any_sync(FULL, mv == 3)) {                            // warp-uniform
-                nb = count_below<GL>(cx, lane, k, snew, kw);            // searchsorted(cpx, s), :206
-                const double hb = elem_at<GL>(cv, nb, kw);
-                const double h1d = elem_at<GL>(cv, nrand, kw);
-                const double h2d = elem_at<GL>(cv, nrand + 1, kw);
-                // birth (changepoint.py:57,61,72-74) and death (:67-68,76-78) share one instruction
-                // stream: the operands of each division / square root are selected per chain
-                const double q1 = birth ? du / P.sqrtM : h2d / h1d;
-                const double ub = 0.5 + q1;                                 // birth: u, :61
-                const double q2 = birth ? (1.0 - ub) / ub : 1.0 / (1.0 + q1);       // birth: f^2; death: u, :68
-                const double u = birth ? ub : q2;
-                const double rr = sqrt(birth ? q2 : h1d * h2d);             // birth: f, :57; death: h, :67
-                jarg = fabs((birth ? hb : rr) / (u * (1.0 - u)));           // |J| resp. 1/|J^-1|
-                const double hbf = hb / rr;
-                ovf = (mv == 3) && birth && (k + 1 > LANES - 1);
-                const bool td = (mv == 3) && !ovf;
-                if (!(mv == 3)) jarg = 1.0;
-                // insert / delete = every element reads its neighbour below (birth, above the insertion
-                // point) or above (death, from the removed element on); other chains read themselves
-                const int dir = birth ? -1 : 1;
-                const int pivot = birth ? nb : nrand - 1;                   // elements <= pivot stay
-                int off[EPL];
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) off[j] = (td && lane + GL * j > pivot) ? dir : 0;
-                double sx_[EPL], sv_[EPL];
-                int sb_[EPL];
-                shift_by<GL, double>(cx, sx_, 0.0, lane, dir, off, kw);
-                shift_by<GL, double>(cv, sv_, 0.0, lane, dir, off, kw);
-                shift_by<GL, int>(bu, sb_, P.M, lane, dir, off, kw);
-                if (td) {
-                    kk = birth ? k + 1 : k - 1;
-#pragma unroll
-                    for (int j = 0; j < EPL; ++j) {
-                        const int e = lane + GL * j;
-                        nx[j] = sx_[j]; nv[j] = sv_[j]; nbu[j] = sb_[j];
-                        if (birth) {
-                            if (e == nb) { nx[j] = snew; nv[j] = hbf; nbu[j] = bu[j]; }   // boundary searched below
-                            if (e == nb + 1) nv[j] = hb * rr;
-                        } else if (e == nrand) {
-                            nv[j] = rr;
-                        }
+                    nx[j] = sx_[j]; nv[j] = sv_[j]; nbu[j] = sb_[j];
+                    if (birth) {
+                        if (e == nb) { nx[j] = snew; nv[j] = hbf; nbu[j] = bu[j]; }   // boundary searched below
+                        if (e == nb + 1) nv[j] = hb * rr;
+                    } else if (e == nrand) {
+                        nv[j] = rr;
                     }
                 }
             }
@@ -586,47 +504,51 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
                 if (e >= kk) { nx[j] = 0.0; nbu[j] = P.M; }
                 if (e > kk) nv[j] = 0.0;
             }
-            // run boundaries only move when a location moves: a cpx block move (every element) or a
-            // birth (the new element).
-            const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
-            {
-                constexpr int NA = Geo<GL>::ALWAYS;
-                double qa[NA];
-                int sa[NA];
-#pragma unroll
-                for (int j = 0; j < NA; ++j) qa[j] = nx[j];
-                upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) {
-                    const int e = lane + GL * j;
-                    int sb = 0;
-                    if (j < NA) sb = sa[j < NA ? j : 0];
-                    else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
-                    if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
-                }
-            }
-            if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
-            // ---- log-posterior of the proposal; every fp64 log of the step in one call
-            double nss, nvt, gp, nlg, nls2, logu, ljac;
-            cp_terms<GL, true, true, true>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, nss, nvt, gp);
-            log4<GL>(lane, gp, __dmul_rn(nsig, nsig), uacc, jarg, nlg, nls2, logu, ljac);
-            const double lpn = cp_assemble(P, kk, nss, nvt, nlg, nsig, nls2, 0);
-            const double lqr = (mv == 3) ? (birth ? ljac : -ljac) : 0.0;
-
-            // sampler.py:83-84 with Python's min(0, nan) == 0
-            const double delta = lpn - lp - lqr;
-            const double mh = (delta < 0.0) ? delta : 0.0;
-            const bool acc = !ovf && (logu < mh);
-            trace_prop(t, lpn, acc, lqr, kk, nsig, nx, nv);
-            if (acc) {
-                k = kk; sig = nsig; lp = lpn;
-                ss_c = nss; vt_c = nvt; lg_c = nlg; ls2_c = nls2;
-#pragma unroll
-                for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; cv[j] = nv[j]; bu[j] = nbu[j]; }
-            }
-            nacc += acc ? 1 : 0;
-            novf += ovf ? 1 : 0;
         }
+        // run boundaries only move when a location moves: a cpx block move (every element) or a
+        // birth (the new element).
+        const bool moved_x = (mv == 0) || (mv == 3 && birth && !ovf);
+        if (!skip || any0 || any3) {
+            constexpr int NA = Geo<GL>::ALWAYS;
+            double qa[NA];
+            int sa[NA];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) qa[j] = nx[j];
+            upper_bound_rows<LOGP2, NA>(xs, P.P2, qa, sa);
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const int e = lane + GL * j;
+                int sb = 0;
+                if (j < NA) sb = sa[j < NA ? j : 0];
+                else if (ROW_ON(j)) sb = upper_bound<LOGP2>(xs, P.P2, nx[j]);
+                if (moved_x && e < kk && (mv == 0 || e == nb)) nbu[j] = sb;
+            }
+        }
+        if (!INJ) rA = rk.block(step + 1, (uint32_t)lane);
+        // ---- log-posterior of the proposal from the pieces that changed (a sigma move: none of the three sums;
+        //      a height move: ss, vt; a location move: ss, gp; birth / death: all), every fp64 log of the step in
+        //      one call.  A chain whose move leaves a piece alone recomputes the cached value bit for bit.
+        double nss = ss_c, nvt = vt_c, gp = 1.0, nlg, nls2, logu, ljac;
+        const bool wss = !skip || any0 || any1 || any3, wvt = !skip || any1 || any3, wgp = !skip || any0 || any3;
+        cp_terms<GL>(P, cy, cyy, lane, kw, kk, nx, nv, nbu, wss, wvt, wgp, nss, nvt, gp);
+        log4<GL>(lane, gp, __dmul_rn(nsig, nsig), uacc, jarg, nlg, nls2, logu, ljac);
+        if (!wgp) nlg = lg_c;
+        const double lpn = cp_assemble(P, kk, nss, nvt, nlg, nsig, nls2, 0);
+        const double lqr = (mv == 3) ? (birth ? ljac : -ljac) : 0.0;
+
+        // sampler.py:83-84 with Python's min(0, nan) == 0
+        const double delta = lpn - lp - lqr;
+        const double mh = (delta < 0.0) ? delta : 0.0;
+        const bool acc = !ovf && (logu < mh);
+        trace_prop(t, lpn, acc, lqr, kk, nsig, nx, nv);
+        if (acc) {
+            k = kk; sig = nsig; lp = lpn;
+            ss_c = nss; vt_c = nvt; lg_c = nlg; ls2_c = nls2;
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) { cx[j] = nx[j]; cv[j] = nv[j]; bu[j] = nbu[j]; }
+        }
+        nacc += acc ? 1 : 0;
+        novf += ovf ? 1 : 0;
 
         if ((step % RMN_CP_DIAG_EVERY) == 0) {              // thinned accumulation (warp-uniform)
             const int kd = __reduce_max_sync(FULL, k);      // (an accepted birth may have raised the extent)
@@ -811,11 +733,9 @@ struct ChangepointSampler : SamplerImpl {
         return RMN_OK;
     }
     template <int GL> cudaError_t set_smem_attr() {
-        cudaError_t e = cudaFuncSetAttribute(changepoint_kernel<false, 1, GL>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaError_t e = rmn_raise_dyn_smem((const void*)changepoint_kernel<false, 1, GL>, smem_bytes);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(changepoint_kernel<true, 1, GL>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        return rmn_raise_dyn_smem((const void*)changepoint_kernel<true, 1, GL>, smem_bytes);
     }
     unsigned grid(int gl = LANES) const { return (unsigned)((s->K * gl + 127) / 128); }
     // grid of the T-step kernel: schedule groups are aligned to global chain ids, so up to 32/gl - 1 leading

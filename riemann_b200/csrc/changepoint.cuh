@@ -6,7 +6,9 @@ namespace cp {
 
 constexpr int LANES = RMN_CP_LANES;
 constexpr int NQ = 6;   // prediction query points tracked by the diagnostics
+#ifndef RMN_CP_DIAG_EVERY
 #define RMN_CP_DIAG_EVERY 4   // diagnostics functionals are accumulated every 4th MH step
+#endif
 
 struct CPParams {
     int M, P2, alpha_is_one, XP;  // XP = 2*P2: padded length of the x table (device data = xpad[XP] | cy[M+1] | cyy[M+1])

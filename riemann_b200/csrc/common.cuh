@@ -322,4 +322,10 @@ int rmn_reduce_diag_block(int64_t K, int nd, int64_t nsamples, int64_t nsteps, c
 int rmn_chain_moments(int64_t K, int nd, int64_t nsamples, const double* S1, const double* S2, double* d_mean,
                       double* d_var, cudaStream_t st);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of the KERNEL, shared by every sampler in the
+// process: only ever raise it, so a sampler created later with a smaller shape cannot lower the limit under one
+// that is still alive (util.cu keeps the largest value requested per (device, kernel)).
+cudaError_t rmn_raise_dyn_smem(const void* kernel, size_t bytes);
+#define RMN_RAISE_SMEM(kernel, bytes) RMN_CUDA(rmn_raise_dyn_smem((const void*)(kernel), (size_t)(bytes)))
+
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }

@@ -590,10 +590,10 @@ struct DenseGaussSampler : SamplerImpl {
             if (int rc = up(pr->h_chM, &d_chM, true)) return rc;
             if (int rc = up(pr->h_Minv, &d_Minv, false)) return rc;
             if (int rc = up(pr->h_chMinv, &d_chMinv, true)) return rc;
-            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_MASS_P0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_MASS_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_MASS_W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+            RMN_RAISE_SMEM(gemm_abt_kernel<EPI_MASS_P0>, (int)GEMM_SMEM);
+            RMN_RAISE_SMEM(gemm_abt_kernel<EPI_MASS_STEP>, (int)GEMM_SMEM);
+            RMN_RAISE_SMEM(gemm_abt_kernel<EPI_LOGPOST_MASS>, (int)GEMM_SMEM);
+            RMN_RAISE_SMEM(gemm_abt_kernel<EPI_MASS_W1>, (int)GEMM_SMEM);
         }
         if (pr->kind == RMN_PROP_PCN) {
             rw_diag = false;
@@ -608,17 +608,12 @@ struct DenseGaussSampler : SamplerImpl {
             RMN_CUDA(cudaMemcpy(d_Lpad, hl.data(), hl.size() * 8, cudaMemcpyHostToDevice));
             RMN_CUDA(cudaMalloc(&d_Linvpad, hi.size() * 8));
             RMN_CUDA(cudaMemcpy(d_Linvpad, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice));
-            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_PCNPROP>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-            RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_PCNREV>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+            RMN_RAISE_SMEM(gemm_abt_kernel<EPI_PCNPROP>, (int)GEMM_SMEM);
+            RMN_RAISE_SMEM(gemm_abt_kernel<EPI_PCNREV>, (int)GEMM_SMEM);
         }
-        RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_RW>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_LOGPOST_MALA>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        RMN_CUDA(cudaFuncSetAttribute(gemm_abt_kernel<EPI_RWPROP>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        RMN_RAISE_SMEM(gemm_abt_kernel<EPI_LOGPOST_RW>, (int)GEMM_SMEM);
+        RMN_RAISE_SMEM(gemm_abt_kernel<EPI_LOGPOST_MALA>, (int)GEMM_SMEM);
+        RMN_RAISE_SMEM(gemm_abt_kernel<EPI_RWPROP>, (int)GEMM_SMEM);
         int rc = rmn_fill_f64(st.scale, st.K, 1.0, 0);
         if (rc) return rc;
         RMN_CUDA(cudaDeviceSynchronize());

@@ -380,7 +380,7 @@ struct DenseTF32Sampler : SamplerImpl {
         const size_t sm = (size_t)TEX_RB * st.d * 8;
         static bool attr_set = false;
         if (!attr_set && sm > 48 * 1024) {
-            RMN_CUDA(cudaFuncSetAttribute(texact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            RMN_RAISE_SMEM(texact_kernel, 200 * 1024);
             attr_set = true;
         }
         RMN_REQUIRE(sm <= 200 * 1024, "tf32x3 dense path: d = %d exceeds the exact-refresh kernel's shared memory", st.d);

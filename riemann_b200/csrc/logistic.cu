@@ -47,6 +47,8 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "logistic_math.cuh"
+#include "logistic_fused.cuh"
+#include <stdlib.h>
 
 namespace tc {
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
@@ -974,6 +976,12 @@ struct LogisticSampler : SamplerImpl {
     tc::GemmMaps maps;          // metric GEMM
     LgTC tcb{};
     tc::GemmMaps maps_z, maps_g;               // Z = Theta X^T (A map rebuilt per chain block) ; G = R X
+    // RMN_PREC_TF32X3, fused sweep (logistic_fused.cu; d <= 128): ONE tcgen05 kernel per sweep.  RMN_LG_FUSED=0 selects the
+    // three-kernel pipeline above (A/B measurements, and the only one for d > 128).
+    bool fused = false;
+    lgf::Geometry fg{};
+    lgf::Maps fmaps{};
+    float* fXh = nullptr; float* fXl = nullptr; uint32_t* fys = nullptr; double* fllp = nullptr; float* fgp = nullptr;
     std::vector<tc::GemmMaps> maps_z_blk;
     RowComm rowc;               // row-sharded data mode: the ranks that hold the other slices of X
     ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); }
@@ -1003,6 +1011,11 @@ struct LogisticSampler : SamplerImpl {
         if (tf32m || tcx3) st.Npad = (st.N + 31) / 32 * 32;
         if (tf32m) st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
         if (tcx3) {
+            const char* e = getenv("RMN_LG_FUSED");
+            fused = lgf::supported(st.d) && !(e && e[0] == '0');
+            if (fused) lgf::make_geometry(&fg, st.N, st.d, st.K);
+        }
+        if (tcx3 && !fused) {
             tcb.Npad = st.Npad;
             tcb.dp32 = (st.d + 31) / 32 * 32;
             tcb.Kb = (int)(st.K < 2048 ? st.K : 2048);
@@ -1029,6 +1042,14 @@ struct LogisticSampler : SamplerImpl {
             default: return align256(Np);
         }
     }
+    size_t f_bytes(int which) const {      // fused sweep: 0 Xh (= Xl), 1 label masks, 2 llp, 3 gp
+        switch (which) {
+            case 0: return align256((size_t)st.N * fg.dp32 * 4);
+            case 1: return align256((size_t)fg.nys * 4);
+            case 2: return align256((size_t)2 * fg.ns * st.K * 8);
+            default: return align256((size_t)fg.ns * st.K * fg.dp32 * 4);
+        }
+    }
     size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * 4); }
     size_t w_bytes() const { return align256((size_t)st.K * st.Npad * 4); }
     size_t gp_bytes() const { return align256((size_t)st.K * st.NP * 4); }
@@ -1043,7 +1064,8 @@ struct LogisticSampler : SamplerImpl {
                    2 * align256(ND_MAX * K * 8) + 256;
         if (mmala) n += 3 * align256(K * st.d * st.d * 8) + 2 * align256(K * 8) + 2 * rowb();
         if (tf32m) n += kr_bytes() + w_bytes() + gp_bytes();
-        if (tcx3) for (int w = 0; w < 8; ++w) n += tc_bytes(w);
+        if (tcx3 && !fused) for (int w = 0; w < 8; ++w) n += tc_bytes(w);
+        if (fused) n += 2 * f_bytes(0) + f_bytes(1) + f_bytes(2) + f_bytes(3);
         return n;
     }
     int bind(void* ws) override {
@@ -1075,7 +1097,13 @@ struct LogisticSampler : SamplerImpl {
             st.W = (float*)p; p += w_bytes();
             st.Gp = (float*)p; p += gp_bytes();
         }
-        if (tcx3) {
+        if (fused) {
+            fXh = (float*)p; p += f_bytes(0); fXl = (float*)p; p += f_bytes(0);
+            fys = (uint32_t*)p; p += f_bytes(1);
+            fllp = (double*)p; p += f_bytes(2);
+            fgp = (float*)p; p += f_bytes(3);
+        }
+        if (tcx3 && !fused) {
             const size_t N = (size_t)st.N, Np = (size_t)tcb.Npad, dp32 = (size_t)tcb.dp32, Kb = (size_t)tcb.Kb;
             tcb.Xh = (float*)p; p += align256(N * dp32 * 4);  tcb.Xl = (float*)p; p += align256(N * dp32 * 4);
             tcb.XTh = (float*)p; p += align256(dp32 * Np * 4); tcb.XTl = (float*)p; p += align256(dp32 * Np * 4);
@@ -1088,7 +1116,11 @@ struct LogisticSampler : SamplerImpl {
         }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
         if (int rc = lg_tables_ready()) return rc;
-        if (tcx3) {
+        if (fused) {
+            if (int rc = lgf::prep_x(st.N, st.d, fg, st.X, st.y, fXh, fXl, fys, 0)) return rc;
+            if (int rc = lgf::make_maps(&fmaps, fg, st.N, fXh, fXl)) return rc;
+        }
+        if (tcx3 && !fused) {
             const size_t psm = (size_t)32 * (tcb.dp32 + 1) * 8;
             lg_tc_prep_x_kernel<<<(unsigned)(tcb.Npad / 32), 256, psm>>>(st, tcb);
             RMN_KERNEL_CHECK();
@@ -1115,11 +1147,11 @@ struct LogisticSampler : SamplerImpl {
             if (int rc = tc::make_tmap_2d(&maps.bh, st.KR, (uint64_t)st.NP, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TN)) return rc;
             maps.al = maps.ah; maps.bl = maps.bh;
         }
-        RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem()));
+        RMN_RAISE_SMEM(lg_eval_kernel, (int)eval_smem());
         if (mmala) {
-            RMN_CUDA(cudaFuncSetAttribute(lg_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)metric_smem()));
-            RMN_CUDA(cudaFuncSetAttribute(lg_finish_propose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem()));
-            RMN_CUDA(cudaFuncSetAttribute(lg_adopt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem()));
+            RMN_RAISE_SMEM(lg_metric_kernel, (int)metric_smem());
+            RMN_RAISE_SMEM(lg_finish_propose_kernel<true>, (int)fp_smem());
+            RMN_RAISE_SMEM(lg_adopt_kernel<true>, (int)fp_smem());
         }
         int rc = rmn_fill_f64(st.scale, st.K, 1.0, 0);
         if (rc) return rc;
@@ -1130,7 +1162,20 @@ struct LogisticSampler : SamplerImpl {
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 127) / 128); }
 
     // RMN_PREC_TF32X3: logits GEMM -> pointwise -> split-K gradient GEMM -> partial sums, per chain block
+    int eval_fused(int fixed_slot, cudaStream_t stream) {
+        lgf::SweepArgs a{};
+        a.ys = fys; a.Th = st.Th; a.cur = st.cur; a.fixed_slot = fixed_slot;
+        a.K = st.K; a.N = st.N; a.d = st.d; a.dp = st.dp;
+        a.llp = fllp; a.gp = fgp; a.W = st.W; a.ldw = st.Npad;
+        ktimer.begin("lg_fused_sweep_kernel", stream);
+        if (int rc = lgf::sweep(fmaps, fg, a, stream)) return rc;
+        ktimer.end(stream);
+        if (int rc = lgf::reduce(fg, st.K, st.dp, fllp, fgp, st.llpart, st.gpart, stream)) return rc;
+        launches += 2;
+        return RMN_OK;
+    }
     int eval_tc(int fixed_slot, cudaStream_t stream) {
+        if (fused) return eval_fused(fixed_slot, stream);
         const int64_t nth = st.K * tcb.dp32;
         lg_tc_split_theta_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, stream>>>(st, tcb, fixed_slot);
         RMN_KERNEL_CHECK(); launches++;
@@ -1320,13 +1365,13 @@ int logistic_pointwise(rmn_model* m, int which, int64_t n, const double* d_theta
     if (int rc = lg_tables_ready()) return rc;
     const size_t esm = eval_smem_bytes(st.ldt);
     const size_t msm = ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8;
-    RMN_CUDA(cudaFuncSetAttribute(lg_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+    RMN_RAISE_SMEM(lg_eval_kernel, (int)esm);
     const int64_t ne = n * st.dp;
     lg_set_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(st, d_theta);
     dim3 grid((unsigned)((n + BC - 1) / BC), st.nsplit);
     lg_eval_kernel<<<grid, EVAL_THREADS, esm, stream>>>(st, 1);
     if (d_metric) {
-        RMN_CUDA(cudaFuncSetAttribute(lg_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+        RMN_RAISE_SMEM(lg_metric_kernel, (int)msm);
         lg_metric_kernel<<<(unsigned)((n + 3) / 4), 256, msm, stream>>>(st, 1);
     }
     lg_point_out_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, stream>>>(st, which, d_out, d_grad, d_metric);

@@ -1,0 +1,417 @@
+// riemann_b200 -- fused tcgen05 likelihood sweep of the logistic-regression model:
+// ONE kernel per sweep, "flash-attention shaped".  Z and R never touch HBM.
+//
+//   log L(theta_c) = sum_i y_i z_ci - softplus(z_ci),   z_ci = theta_c . x_i        (model, absent in the reference;
+//   grad_c         = sum_i (y_i - sigmoid(z_ci)) x_i                                  Model protocol model.py:27-55,
+//   (mMALA)  w_ci  = p_ci (1 - p_ci)                                                  driven by hamiltonian.py:76-91)
+//
+// A CTA owns 128 chains (one TMEM lane each) and a contiguous range of data rows, streamed as tiles of 64 rows:
+//
+//   TMA warp      X tile (hi and lo parts, fp32, [64][dp32], SWIZZLE_128B boxes of 32 columns) + the tile's label
+//                 sign masks -> 3-stage shared-memory ring (full / empty mbarriers)
+//   MMA thread    GEMM1  Z[128 x 64] = Theta_h Xh^T + Theta_h Xl^T + Theta_l Xh^T   (3 x TF32, fp32-accurate);
+//                        A = Theta from TENSOR MEMORY (loaded once per CTA), B = X tile, K-major
+//                 GEMM2  G[128 x dp32] += R[128 x 64] Xh[64 x dp32]                  (single-pass TF32: the gradient
+//                        only shapes the proposal); A = R from tensor memory, written in place over Z by the
+//                        pointwise warps, B = THE SAME Xh tile read MN-major (no transposed copy of X anywhere)
+//   2 x 4 warps   pointwise stage, one warpgroup per Z buffer (tiles alternate): tcgen05.ld the logits, fp32
+//                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element),
+//                 log-likelihood partial sums in fp64, R = y - p rounded to TF32 -> tcgen05.st back into the same
+//                 TMEM columns (and W = p(1-p) to HBM for the mMALA metric GEMM)
+//
+//   TMEM columns: Theta_h [0, dp32) | Theta_l [dp32, 2 dp32) | G [2 dp32, 3 dp32) | Z/R buffer 0, 1 (64 each)
+//
+// The MMA thread issues GEMM1 of tile t+1 before it waits for the R of tile t, so the tensor pipe works on the
+// next logits while the pointwise warps process the current ones; tcgen05.mma executes in issue order, which is
+// what makes reusing a Z buffer two tiles later safe without another barrier.
+//
+// Accuracy.  hi / lo parts are rounded to nearest TF32, so (hi + lo) carries 22 bits and z is fp32-accurate; the
+// per-row terms are fp32 (|error| ~1e-7 each), summed in fp64.  Measured budget: tests/test_gpu_logistic.py.
+// The result is a deterministic function of theta (fixed tile order, no atomics).
+#include <algorithm>
+#include "common.cuh"
+#include "tc_gemm.cuh"
+#include "logistic_fused.cuh"
+
+namespace lgf {
+using namespace tc;
+
+namespace {
+
+constexpr int NT = 64;                     // data rows per tile = UMMA N of GEMM1 = K extent of GEMM2
+constexpr int CB = 128;                    // chains per CTA = UMMA M
+constexpr int STAGES = 3;
+constexpr int BOX_BYTES = NT * 128;        // one TMA box: 64 rows x 32 fp32
+constexpr int THREADS = 384;               // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 / 8..11 pointwise warpgroups
+constexpr int TMEM_COLS_ALLOC = 512;
+
+template <int DP32> struct Cfg {
+    static constexpr int NBOX = DP32 / 32;
+    static constexpr int XPART = NBOX * BOX_BYTES;                 // Xh (or Xl) tile
+    static constexpr int STAGE_BYTES = 2 * XPART + 1024;           // Xh | Xl | label masks (256 B, padded to keep 1024-B alignment)
+    static constexpr int TX_BYTES = 2 * XPART + NT * 4;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int COL_TH = 0, COL_TL = DP32, COL_G = 2 * DP32, COL_Z = 3 * DP32;
+    static_assert(3 * DP32 + 2 * NT <= 512, "TMEM columns");
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// shared-memory matrix descriptor, MN-major, SWIZZLE_128B: 32 fp32 of the MN index are contiguous (one 128-byte
+// row), MN blocks of 32 are `lbo` bytes apart; the K index walks 128-byte rows, groups of 8 rows `sbo` bytes apart
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float rn_tf32(float x) {          // round to nearest TF32 (10 explicit mantissa bits)
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void split_rn(double x, float& hi, float& lo) {
+    hi = rn_tf32((float)x);
+    lo = rn_tf32((float)(x - (double)hi));
+}
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// log1p(e), e in [0, 1]: degree-9 Chebyshev interpolant in t = 2e - 1 (|error| < 7e-8 in fp32 Horner form)
+__device__ __forceinline__ float log1p_unit(float e) {
+    const float t = fmaf(2.0f, e, -1.0f);
+    float p = 7.152816828e-06f;
+    p = fmaf(p, t, -2.401530172e-05f);
+    p = fmaf(p, t, 6.393497408e-05f);
+    p = fmaf(p, t, -2.240642703e-04f);
+    p = fmaf(p, t, 8.235513423e-04f);
+    p = fmaf(p, t, -3.088083925e-03f);
+    p = fmaf(p, t, 1.234561512e-02f);
+    p = fmaf(p, t, -5.555534548e-02f);
+    p = fmaf(p, t, 3.333333346e-01f);
+    p = fmaf(p, t, 4.054651039e-01f);
+    return p;
+}
+
+template <int DP32, bool HASW>
+__global__ void __launch_bounds__(THREADS, 1)
+lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SweepArgs a) {
+    using C = Cfg<DP32>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* z_full = empty + STAGES;           // [2] GEMM1 of a tile complete
+    uint64_t* r_full = z_full + 2;               // [2] pointwise stage wrote R
+    uint64_t* th_ready = r_full + 2;             // Theta is in TMEM
+    uint64_t* g_full = th_ready + 1;             // last GEMM2 complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cb = blockIdx.x % a.nblk, rs = blockIdx.x / a.nblk;
+    const int64_t t_begin = (int64_t)rs * a.tps;
+    const int64_t t_end = min(a.tiles_total, t_begin + a.tps);
+    const int ntile = (int)max((int64_t)0, t_end - t_begin);
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_xh); tma_prefetch_desc(&map_xl); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4); }
+        mbar_init(th_ready, 4);
+        mbar_init(g_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS_ALLOC);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int t = 0; t < ntile; ++t) {
+            const int s = t % STAGES;
+            mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+            uint8_t* st = smem + s * C::STAGE_BYTES;
+            const int row0 = (int)((t_begin + t) * NT);
+            mbar_expect_tx(&full[s], C::TX_BYTES);
+#pragma unroll
+            for (int b = 0; b < C::NBOX; ++b) {
+                tma_load_2d(st + b * BOX_BYTES, &map_xh, &full[s], b * 32, row0);
+                tma_load_2d(st + C::XPART + b * BOX_BYTES, &map_xl, &full[s], b * 32, row0);
+            }
+            bulk_load_1d(st + 2 * C::XPART, a.ys + row0, NT * 4, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        const uint32_t idesc1 = umma_idesc_tf32(CB, NT);
+        const uint32_t idesc2 = umma_idesc_tf32(CB, DP32) | (1u << 16);          // B is MN-major
+        const uint32_t t_th = tmem_base + C::COL_TH, t_tl = tmem_base + C::COL_TL, t_g = tmem_base + C::COL_G;
+        const int d8 = (a.d + 7) / 8;                                            // K steps of GEMM1
+        auto gemm1 = [&](int t) {
+            const int s = t % STAGES;
+            mbar_wait(&full[s], (t / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t sx = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint32_t tz = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
+            for (int ks = 0; ks < d8; ++ks) {
+                const uint32_t boff = (uint32_t)((ks >> 2) * BOX_BYTES + (ks & 3) * 32);      // box, 32 bytes per K step
+                const uint64_t dbh = umma_desc_kmajor<128>(sx + boff);
+                const uint64_t dbl = umma_desc_kmajor<128>(sx + C::XPART + boff);
+                umma_tf32_ts(tz, t_th + ks * 8, dbh, idesc1, ks != 0);
+                umma_tf32_ts(tz, t_th + ks * 8, dbl, idesc1, 1);
+                umma_tf32_ts(tz, t_tl + ks * 8, dbh, idesc1, 1);
+            }
+            umma_commit(&z_full[t & 1]);
+        };
+        if (ntile > 0) {
+            mbar_wait(th_ready, 0);
+            tc_fence_after();
+            gemm1(0);
+            for (int t = 0; t < ntile; ++t) {
+                if (t + 1 < ntile) gemm1(t + 1);
+                mbar_wait(&r_full[t & 1], (t >> 1) & 1);
+                tc_fence_after();
+                const int s = t % STAGES;
+                const uint32_t sx = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint32_t tr = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
+#pragma unroll
+                for (int ks = 0; ks < NT / 8; ++ks) {
+                    const uint64_t db = umma_desc_mnmajor_sw128(sx + ks * 1024, BOX_BYTES, 1024);
+                    umma_tf32_ts(t_g, tr + ks * 8, db, idesc2, (t | ks) != 0);
+                }
+                umma_commit(&empty[s]);              // the stage (X tile, label masks) is free once GEMM2 has read it
+            }
+            umma_commit(g_full);
+        }
+    } else if (warp >= 4) {
+        // ===== pointwise warpgroups: thread = chain (TMEM lane 32 q + lane) =====
+        const int q = warp & 3, wg = (warp - 4) >> 2;
+        const int64_t c = (int64_t)cb * CB + q * 32 + lane;
+        const bool okc = c < a.K;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (wg == 0 && ntile > 0) {
+            // Theta of this chain -> TMEM (hi and lo parts)
+            const int slot = (a.fixed_slot >= 0) ? a.fixed_slot : (okc ? (a.cur[c] ^ 1) : 0);
+            const double* th = a.Th + ((int64_t)slot * a.K + (okc ? c : 0)) * a.dp;
+            for (int j0 = 0; j0 < DP32; j0 += 32) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int j = j0 + e;
+                    const double v = (okc && j < a.d) ? th[j] : 0.0;
+                    float h, l;
+                    split_rn(v, h, l);
+                    hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
+                }
+                tmem_st_32x32(lane_base + C::COL_TH + j0, hi);
+                tmem_st_32x32(lane_base + C::COL_TL + j0, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(th_ready);
+        }
+        double ll = 0.0;
+        float* wrow = HASW ? a.W + (okc ? c : 0) * a.ldw : nullptr;
+        for (int t = wg; t < ntile; t += 2) {
+            const int s = t % STAGES;
+            const uint32_t* ysm = reinterpret_cast<const uint32_t*>(smem + s * C::STAGE_BYTES + 2 * C::XPART);
+            const int64_t row0 = (t_begin + t) * NT;
+            const bool ragged = row0 + NT > a.N;
+            mbar_wait(&z_full[t & 1], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tz = lane_base + C::COL_Z + (uint32_t)((t & 1) * NT);
+#pragma unroll
+            for (int ch = 0; ch < NT / 32; ++ch) {
+                float v[32];
+                tmem_ld_32x32(tz + ch * 32, v);
+                uint32_t rr[32];
+                float wv[HASW ? 32 : 1];
+                float part = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const uint32_t ym = ysm[ch * 32 + e];                       // 0x80000000 where y = 1
+                    const float sv = __uint_as_float(__float_as_uint(v[e]) ^ ym);   // s = (1 - 2y) z
+                    const float ex = ex2_approx(-1.4426950408889634f * fabsf(sv));   // e = exp(-|s|)
+                    const float sp = fmaxf(sv, 0.0f) + log1p_unit(ex);          // softplus(s) = softplus(z) - y z
+                    const float inv = rcp_approx(1.0f + ex);
+                    const float sg = (sv >= 0.0f) ? inv : ex * inv;             // sigmoid(s);  y - p = (2y - 1) sigmoid(s)
+                    float term = -sp;
+                    if (ragged && row0 + ch * 32 + e >= a.N) term = 0.0f;       // padding rows (zero X rows) do not count
+                    part += term;
+                    if ((e & 7) == 7) { ll += (double)part; part = 0.0f; }
+                    const uint32_t rb = __float_as_uint(sg) | (~ym & 0x80000000u);
+                    rr[e] = (rb + 0x1000u) & 0xFFFFE000u;                      // nearest TF32
+                    if (HASW) wv[e] = ex * inv * inv;
+                }
+                tmem_st_32x32(tz + ch * 32, rr);
+                if (HASW && okc && row0 + ch * 32 < a.ldw) {          // ldw is a multiple of 32
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(wrow + row0 + ch * 32 + e) = make_float4(wv[e], wv[e + 1], wv[e + 2], wv[e + 3]);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&r_full[t & 1]);
+        }
+        if (okc) a.llp[((int64_t)rs * 2 + wg) * a.K + c] = ll;
+        if (wg == 0) {
+            // gradient partial of this (chain block, row split)
+            float* gout = a.gp + ((int64_t)rs * a.K + (okc ? c : 0)) * DP32;
+            if (ntile > 0) {
+                mbar_wait(g_full, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int j0 = 0; j0 < DP32; j0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(lane_base + C::COL_G + j0, v);
+                    if (okc) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(gout + j0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    }
+                }
+            } else if (okc) {
+                for (int j = 0; j < DP32; ++j) gout[j] = 0.0f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS_ALLOC);
+    }
+}
+
+// X[N][d] (fp64) -> Xh, Xl [N][dp32] (nearest-TF32 hi / lo parts, zero padded) and the label sign masks
+__global__ void __launch_bounds__(256)
+lgf_prep_kernel(int64_t N, int d, int dp32, int64_t nys, const double* __restrict__ X, const double* __restrict__ y,
+                float* __restrict__ Xh, float* __restrict__ Xl, uint32_t* __restrict__ ys) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx < N * dp32) {
+        const int64_t i = idx / dp32;
+        const int k = (int)(idx % dp32);
+        float hi = 0.0f, lo = 0.0f;
+        if (k < d) split_rn(X[i * d + k], hi, lo);
+        Xh[idx] = hi; Xl[idx] = lo;
+    }
+    if (idx < nys) ys[idx] = (idx < N && y[idx] != 0.0) ? 0x80000000u : 0u;
+}
+
+// sum the partials over the row splits into slot 0 of llpart / gpart (fixed order)
+__global__ void __launch_bounds__(128)
+lgf_reduce_kernel(int64_t K, int ns, int dp32, int dp, const double* __restrict__ llp, const float* __restrict__ gp,
+                  double* __restrict__ llpart, double* __restrict__ gpart) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (c >= K) return;
+    double ll = 0.0;
+    for (int q = lane; q < 2 * ns; q += 32) ll += llp[(int64_t)q * K + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+    if (lane == 0) llpart[c] = ll;
+    for (int j = lane; j < dp; j += 32) {
+        double g = 0.0;
+        if (j < dp32)
+            for (int s = 0; s < ns; ++s) g += (double)gp[((int64_t)s * K + c) * dp32 + j];
+        gpart[c * dp + j] = g;
+    }
+}
+
+}  // namespace
+
+bool supported(int d) { return d >= 1 && d <= 128; }
+int dp32_of(int d) { return d <= 64 ? 64 : 128; }
+
+void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
+    g->dp32 = dp32_of(d);
+    g->tiles_total = (N + NT - 1) / NT;
+    g->nys = g->tiles_total * NT;
+    g->nblk = (int)((K + CB - 1) / CB);
+    // row splits: a grid that is a multiple of the SM count (148 = 4 x 37) when the tile count allows it
+    int gcd = 1;
+    for (int f : {2, 4, 37, 74, 148}) if (g->nblk % f == 0) gcd = f;
+    int ns = 148 / gcd;
+    const int64_t max_ns = std::max<int64_t>(1, g->tiles_total / 8);            // at least ~8 tiles per CTA
+    if (ns > max_ns) ns = (int)max_ns;
+    g->tps = (int)((g->tiles_total + ns - 1) / ns);
+    g->ns = (int)((g->tiles_total + g->tps - 1) / g->tps);
+}
+
+int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y, float* Xh, float* Xl, uint32_t* ys,
+           cudaStream_t st) {
+    const int64_t n = std::max<int64_t>(N * g.dp32, g.nys);
+    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.dp32, g.nys, X, y, Xh, Xl, ys);
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}
+
+int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const float* Xl) {
+    if (int rc = make_tmap_2d(&m->xh, Xh, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT)) return rc;
+    return make_tmap_2d(&m->xl, Xl, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT);
+}
+
+int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {
+    a.nblk = g.nblk; a.tps = g.tps; a.tiles_total = g.tiles_total;
+    static bool attr[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 63]) {
+        RMN_CUDA(cudaFuncSetAttribute(lg_fused_sweep_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        RMN_CUDA(cudaFuncSetAttribute(lg_fused_sweep_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+        RMN_CUDA(cudaFuncSetAttribute(lg_fused_sweep_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        RMN_CUDA(cudaFuncSetAttribute(lg_fused_sweep_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+        attr[dev & 63] = true;
+    }
+    const unsigned grid = (unsigned)(g.nblk * g.ns);
+    if (g.dp32 == 64) {
+        if (a.W) lg_fused_sweep_kernel<64, true><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, a);
+        else lg_fused_sweep_kernel<64, false><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, a);
+    } else {
+        if (a.W) lg_fused_sweep_kernel<128, true><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, a);
+        else lg_fused_sweep_kernel<128, false><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, a);
+    }
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}
+
+int reduce(const Geometry& g, int64_t K, int dp, const double* llp, const float* gp, double* llpart, double* gpart,
+           cudaStream_t st) {
+    lgf_reduce_kernel<<<(unsigned)((K * 32 + 127) / 128), 128, 0, st>>>(K, g.ns, g.dp32, dp, llp, gp, llpart, gpart);
+    RMN_KERNEL_CHECK();
+    return RMN_OK;
+}
+
+}  // namespace lgf

@@ -1,0 +1,45 @@
+// riemann_b200 -- interface of the fused tcgen05 likelihood sweep (logistic_fused.cu), used by logistic.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lgf {
+
+struct Geometry {
+    int dp32;              // columns of the split X copies: 64 (d <= 64) or 128 (d <= 128)
+    int nblk;              // chain blocks of 128
+    int ns;                // row splits (grid = nblk x ns)
+    int tps;               // 64-row tiles per split
+    int64_t tiles_total;
+    int64_t nys;           // entries of the label-mask array (a whole number of tiles)
+};
+
+struct Maps { CUtensorMap xh, xl; };
+
+struct SweepArgs {
+    const uint32_t* ys;    // [nys] 0x80000000 where y = 1
+    const double* Th;      // [2][K][dp] chain states (two slots)
+    const int* cur;        // [K] current slot; the sweep evaluates slot cur ^ 1 unless fixed_slot >= 0
+    int fixed_slot;
+    int64_t K, N;
+    int d, dp;
+    double* llp;           // [2 ns][K]      log-likelihood partial sums (two pointwise warpgroups per split)
+    float* gp;             // [ns][K][dp32]  gradient partial sums
+    float* W;              // [K][ldw] p (1 - p), or NULL
+    int64_t ldw;
+    int nblk, tps;         // filled by sweep()
+    int64_t tiles_total;
+};
+
+bool supported(int d);
+int dp32_of(int d);
+void make_geometry(Geometry* g, int64_t N, int d, int64_t K);
+int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y, float* Xh, float* Xl, uint32_t* ys,
+           cudaStream_t st);
+int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const float* Xl);
+int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st);
+int reduce(const Geometry& g, int64_t K, int dp, const double* llp, const float* gp, double* llpart, double* gpart,
+           cudaStream_t st);
+
+}  // namespace lgf

@@ -1,5 +1,8 @@
 // riemann_b200 -- small generic kernels: fills, diagnostics reduction, RNG test entry points.
 #include "common.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace {
 
@@ -108,6 +111,20 @@ __global__ void chain_moments_kernel(int64_t n, double inv, const double* __rest
 }
 
 }  // namespace
+
+cudaError_t rmn_raise_dyn_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> limit;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = limit[std::make_pair(dev, kernel)];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 int rmn_chain_moments(int64_t K, int nd, int64_t nsamples, const double* S1, const double* S2, double* d_mean,
                       double* d_var, cudaStream_t st) {

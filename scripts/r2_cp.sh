@@ -2,7 +2,7 @@
 # round 2: the restructured changepoint kernel (warp-uniform fast paths + shared move schedule)
 OUT=gpurun_out; TAG=${1:-r2b}; mkdir -p $OUT
 timeout 900 python -m pytest tests/test_gpu_changepoint.py tests/test_gpu_proposals.py tests/test_gpu_ks_marginals.py -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$? $(tail -1 $OUT/${TAG}_pytest.log)"
-for lib in riemann_b200/libriemann_b200.so build/lib_cp_mb4.so build/lib_cp_mb6.so; do
+for lib in riemann_b200/libriemann_b200.so build/lib_cp_mb4.so build/lib_cp_mb6.so build/lib_cp_mb5_DIAGEVERY=16.so build/lib_cp_mb4_DIAGEVERY=16.so; do
  for sched in group chain; do
   n=$(basename $lib .so)_$sched
   RMN_CP_SCHEDULE=$sched RIEMANN_B200_LIB=$PWD/$lib timeout 300 python bench.py --workload changepoint --steps 10 --warmup 3 --no-cpu --no-ess --burn 20000 > $OUT/${TAG}_bench_$n.json 2> $OUT/${TAG}_bench_$n.err
