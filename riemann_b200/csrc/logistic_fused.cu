@@ -7,13 +7,15 @@
 //
 // A CTA owns 128 chains (one TMEM lane each) and a contiguous range of data rows, streamed as tiles of 64 rows:
 //
-//   TMA warp      X tile (hi and lo parts, fp32, [64][dp32], SWIZZLE_128B boxes of 32 columns) + the tile's label
-//                 sign masks -> 3-stage shared-memory ring (full / empty mbarriers)
+//   TMA threads   ring A: X tile, hi and lo parts, fp32 [64][dp32], SWIZZLE_128B boxes of 32 columns (GEMM1, K-major);
+//                 ring B: the hi part again in the 32-byte-atom 128B swizzle -- the only layout tcgen05 accepts for an
+//                 MN-major TF32 operand (GEMM2 reads the tile transposed) -- plus the tile's label sign masks.
+//                 Same global lines (L2 hits), two tensor maps.  A slots are released by GEMM1, B slots by GEMM2.
 //   MMA thread    GEMM1  Z[128 x 64] = Theta_h Xh^T + Theta_h Xl^T + Theta_l Xh^T   (3 x TF32, fp32-accurate);
 //                        A = Theta from TENSOR MEMORY (loaded once per CTA), B = X tile, K-major
 //                 GEMM2  G[128 x dp32] += R[128 x 64] Xh[64 x dp32]                  (single-pass TF32: the gradient
 //                        only shapes the proposal); A = R from tensor memory, written in place over Z by the
-//                        pointwise warps, B = THE SAME Xh tile read MN-major (no transposed copy of X anywhere)
+//                        pointwise warps, B = the Xh tile read MN-major (no transposed copy of X in HBM)
 //   2 x 4 warps   pointwise stage, one warpgroup per Z buffer (tiles alternate): tcgen05.ld the logits, fp32
 //                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element),
 //                 log-likelihood partial sums in fp64, R = y - p rounded to TF32 -> tcgen05.st back into the same
@@ -40,19 +42,24 @@ namespace {
 
 constexpr int NT = 64;                     // data rows per tile = UMMA N of GEMM1 = K extent of GEMM2
 constexpr int CB = 128;                    // chains per CTA = UMMA M
-constexpr int STAGES = 3;
 constexpr int BOX_BYTES = NT * 128;        // one TMA box: 64 rows x 32 fp32
-constexpr int THREADS = 384;               // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 / 8..11 pointwise warpgroups
+constexpr int THREADS = 384;               // warp 0 TMA ring A, 1 MMA, 2 TMEM alloc, 3 TMA ring B, 4..7 / 8..11 pointwise warpgroups
 constexpr int TMEM_COLS_ALLOC = 512;
 
 template <int DP32> struct Cfg {
     static constexpr int NBOX = DP32 / 32;
-    static constexpr int XPART = NBOX * BOX_BYTES;                 // Xh (or Xl) tile
-    static constexpr int STAGE_BYTES = 2 * XPART + 1024;           // Xh | Xl | label masks (256 B, padded to keep 1024-B alignment)
-    static constexpr int TX_BYTES = 2 * XPART + NT * 4;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int XPART = NBOX * BOX_BYTES;                 // one copy of the 64 x dp32 tile
+    static constexpr int SA = (DP32 == 128) ? 2 : 4;               // ring A slots: Xh | Xl (SWIZZLE_128B)
+    static constexpr int SB = (DP32 == 128) ? 2 : 4;               // ring B slots: Xh (32-byte-atom swizzle) | label masks
+    static constexpr int A_BYTES = 2 * XPART;
+    static constexpr int B_BYTES = XPART + 1024;                   // masks: 256 B, padded to keep 1024-byte alignment
+    static constexpr int TXA = 2 * XPART, TXB = XPART + NT * 4;
+    static constexpr int OFF_B = SA * A_BYTES;
+    static constexpr int OFF_BAR = OFF_B + SB * B_BYTES;
+    static constexpr int SMEM = OFF_BAR + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int COL_TH = 0, COL_TL = DP32, COL_G = 2 * DP32, COL_Z = 3 * DP32;
     static_assert(3 * DP32 + 2 * NT <= 512, "TMEM columns");
+    static_assert(SMEM <= 232448, "shared memory");
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
@@ -78,15 +85,17 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// shared-memory matrix descriptor, MN-major, SWIZZLE_128B: 32 fp32 of the MN index are contiguous (one 128-byte
-// row), MN blocks of 32 are `lbo` bytes apart; the K index walks 128-byte rows, groups of 8 rows `sbo` bytes apart
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+// shared-memory matrix descriptor, MN-major, 32-bit elements: tcgen05 accepts ONE layout for an MN-major TF32 operand,
+// the 128-byte swizzle with 32-byte atoms (layout type 1; Swizzle<2,5,2>: 32-byte chunk index ^= row & 3), which TMA
+// writes as CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  32 fp32 of the MN index are contiguous (one 128-byte row), MN blocks
+// of 32 are `lbo` bytes apart; the K index walks 128-byte rows, groups of 4 rows are `sbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                      // SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -123,13 +132,18 @@ __device__ __forceinline__ float log1p_unit(float e) {
 
 template <int DP32, bool HASW>
 __global__ void __launch_bounds__(THREADS, 1)
-lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SweepArgs a) {
+lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                      const __grid_constant__ CUtensorMap map_xt, SweepArgs a) {
     using C = Cfg<DP32>;
+    constexpr int SA = C::SA, SB = C::SB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* z_full = empty + STAGES;           // [2] GEMM1 of a tile complete
+    uint8_t* ringB = smem + C::OFF_B;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t* emptyA = fullA + SA;
+    uint64_t* fullB = emptyA + SA;
+    uint64_t* emptyB = fullB + SB;
+    uint64_t* z_full = emptyB + SB;              // [2] GEMM1 of a tile complete
     uint64_t* r_full = z_full + 2;               // [2] pointwise stage wrote R
     uint64_t* th_ready = r_full + 2;             // Theta is in TMEM
     uint64_t* g_full = th_ready + 1;             // last GEMM2 complete
@@ -141,9 +155,10 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     const int64_t t_end = min(a.tiles_total, t_begin + a.tps);
     const int ntile = (int)max((int64_t)0, t_end - t_begin);
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_xh); tma_prefetch_desc(&map_xl); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_xh); tma_prefetch_desc(&map_xl); tma_prefetch_desc(&map_xt); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4); }
         mbar_init(th_ready, 4);
         mbar_init(g_full, 1);
@@ -156,19 +171,30 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer, ring A: Xh | Xl for GEMM1 =====
         for (int t = 0; t < ntile; ++t) {
-            const int s = t % STAGES;
-            mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
-            uint8_t* st = smem + s * C::STAGE_BYTES;
+            const int s = t % SA;
+            mbar_wait(&emptyA[s], ((t / SA) & 1) ^ 1);
+            uint8_t* st = smem + s * C::A_BYTES;
             const int row0 = (int)((t_begin + t) * NT);
-            mbar_expect_tx(&full[s], C::TX_BYTES);
+            mbar_expect_tx(&fullA[s], C::TXA);
 #pragma unroll
             for (int b = 0; b < C::NBOX; ++b) {
-                tma_load_2d(st + b * BOX_BYTES, &map_xh, &full[s], b * 32, row0);
-                tma_load_2d(st + C::XPART + b * BOX_BYTES, &map_xl, &full[s], b * 32, row0);
+                tma_load_2d(st + b * BOX_BYTES, &map_xh, &fullA[s], b * 32, row0);
+                tma_load_2d(st + C::XPART + b * BOX_BYTES, &map_xl, &fullA[s], b * 32, row0);
             }
-            bulk_load_1d(st + 2 * C::XPART, a.ys + row0, NT * 4, &full[s]);
+        }
+    } else if (warp == 3 && lane == 0) {
+        // ===== TMA producer, ring B: Xh in the MN-major layout for GEMM2, label masks for the pointwise stage =====
+        for (int t = 0; t < ntile; ++t) {
+            const int s = t % SB;
+            mbar_wait(&emptyB[s], ((t / SB) & 1) ^ 1);
+            uint8_t* st = ringB + s * C::B_BYTES;
+            const int row0 = (int)((t_begin + t) * NT);
+            mbar_expect_tx(&fullB[s], C::TXB);
+#pragma unroll
+            for (int b = 0; b < C::NBOX; ++b) tma_load_2d(st + b * BOX_BYTES, &map_xt, &fullB[s], b * 32, row0);
+            bulk_load_1d(st + C::XPART, a.ys + row0, NT * 4, &fullB[s]);
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
@@ -177,10 +203,10 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         const uint32_t t_th = tmem_base + C::COL_TH, t_tl = tmem_base + C::COL_TL, t_g = tmem_base + C::COL_G;
         const int d8 = (a.d + 7) / 8;                                            // K steps of GEMM1
         auto gemm1 = [&](int t) {
-            const int s = t % STAGES;
-            mbar_wait(&full[s], (t / STAGES) & 1);
+            const int s = t % SA;
+            mbar_wait(&fullA[s], (t / SA) & 1);
             tc_fence_after();
-            const uint32_t sx = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint32_t sx = smem_u32(smem + s * C::A_BYTES);
             const uint32_t tz = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
             for (int ks = 0; ks < d8; ++ks) {
                 const uint32_t boff = (uint32_t)((ks >> 2) * BOX_BYTES + (ks & 3) * 32);      // box, 32 bytes per K step
@@ -190,6 +216,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 umma_tf32_ts(tz, t_th + ks * 8, dbl, idesc1, 1);
                 umma_tf32_ts(tz, t_tl + ks * 8, dbh, idesc1, 1);
             }
+            umma_commit(&emptyA[s]);                 // GEMM1 was the only reader of the A slot
             umma_commit(&z_full[t & 1]);
         };
         if (ntile > 0) {
@@ -198,17 +225,18 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             gemm1(0);
             for (int t = 0; t < ntile; ++t) {
                 if (t + 1 < ntile) gemm1(t + 1);
+                const int s = t % SB;
+                mbar_wait(&fullB[s], (t / SB) & 1);
                 mbar_wait(&r_full[t & 1], (t >> 1) & 1);
                 tc_fence_after();
-                const int s = t % STAGES;
-                const uint32_t sx = smem_u32(smem + s * C::STAGE_BYTES);
+                const uint32_t sx = smem_u32(ringB + s * C::B_BYTES);
                 const uint32_t tr = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
 #pragma unroll
                 for (int ks = 0; ks < NT / 8; ++ks) {
-                    const uint64_t db = umma_desc_mnmajor_sw128(sx + ks * 1024, BOX_BYTES, 1024);
+                    const uint64_t db = umma_desc_mnmajor_b32(sx + ks * 1024, BOX_BYTES, 512);
                     umma_tf32_ts(t_g, tr + ks * 8, db, idesc2, (t | ks) != 0);
                 }
-                umma_commit(&empty[s]);              // the stage (X tile, label masks) is free once GEMM2 has read it
+                umma_commit(&emptyB[s]);             // the B slot (X tile, label masks) is free once GEMM2 has read it
             }
             umma_commit(g_full);
         }
@@ -243,10 +271,11 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         double ll = 0.0;
         float* wrow = HASW ? a.W + (okc ? c : 0) * a.ldw : nullptr;
         for (int t = wg; t < ntile; t += 2) {
-            const int s = t % STAGES;
-            const uint32_t* ysm = reinterpret_cast<const uint32_t*>(smem + s * C::STAGE_BYTES + 2 * C::XPART);
+            const int s = t % SB;
+            const uint32_t* ysm = reinterpret_cast<const uint32_t*>(ringB + s * C::B_BYTES + C::XPART);
             const int64_t row0 = (t_begin + t) * NT;
             const bool ragged = row0 + NT > a.N;
+            mbar_wait(&fullB[s], (t / SB) & 1);          // the label masks arrive with ring B
             mbar_wait(&z_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
             const uint32_t tz = lane_base + C::COL_Z + (uint32_t)((t & 1) * NT);
@@ -380,7 +409,8 @@ int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y
 
 int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const float* Xl) {
     if (int rc = make_tmap_2d(&m->xh, Xh, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT)) return rc;
-    return make_tmap_2d(&m->xl, Xl, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT);
+    if (int rc = make_tmap_2d(&m->xl, Xl, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT)) return rc;
+    return make_tmap_2d(&m->xt, Xh, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT, 32, /*atom32=*/true);
 }
 
 int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {
@@ -397,11 +427,11 @@ int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {
     }
     const unsigned grid = (unsigned)(g.nblk * g.ns);
     if (g.dp32 == 64) {
-        if (a.W) lg_fused_sweep_kernel<64, true><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, a);
-        else lg_fused_sweep_kernel<64, false><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, a);
+        if (a.W) lg_fused_sweep_kernel<64, true><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
+        else lg_fused_sweep_kernel<64, false><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
     } else {
-        if (a.W) lg_fused_sweep_kernel<128, true><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, a);
-        else lg_fused_sweep_kernel<128, false><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, a);
+        if (a.W) lg_fused_sweep_kernel<128, true><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
+        else lg_fused_sweep_kernel<128, false><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
     }
     RMN_KERNEL_CHECK();
     return RMN_OK;

@@ -15,7 +15,7 @@ struct Geometry {
     int64_t nys;           // entries of the label-mask array (a whole number of tiles)
 };
 
-struct Maps { CUtensorMap xh, xl; };
+struct Maps { CUtensorMap xh, xl, xt; };   // xt: the hi part again, 32-byte-atom swizzle (MN-major operand of GEMM2)
 
 struct SweepArgs {
     const uint32_t* ys;    // [nys] 0x80000000 where y = 1

@@ -444,7 +444,15 @@ class Sampler(object):
         torch.cuda.current_stream().synchronize()
 
     def get_checkpoint(self):
-        """Everything needed to resume bit-for-bit: states, Philox step counter, adapt state."""
+        """Everything needed to resume bit-for-bit: states, Philox step counter, AdaptScale state.
+        Proposals that carry MORE per-chain state than that -- the Haario accumulators and Cholesky factor of the
+        covariance-adapting proposals (adaptive.py:38-103), AdaptScalepCN's compounding rho (randomwalk.py:118) -- have no
+        read/write ABI for it, so a checkpoint of them would resume silently different chains: refused."""
+        p = self.proposal
+        if getattr(p, "_adapt_cov", False) or type(p).__name__ == "AdaptScalepCN":
+            raise ParameterError("get_checkpoint: {} keeps per-chain adaptation state (covariance accumulators / rho) "
+                                 "that cannot be saved; checkpoint/resume covers fixed and AdaptScale proposals"
+                                 .format(type(p).__name__))
         th, lp = self._download_state()
         ck = {"state": th, "step": int(_lib.load().rmn_sampler_get_step(self._handle)),
               "seed": self.seed, "chain_offset": self.chain_offset}
@@ -496,7 +504,7 @@ class Sampler(object):
         """
         from ..distributed import reduce_block, summarize_block
         blk = self.diagnostics_block()
-        if allreduce:
+        if allreduce and not self.row_sharded:      # row-sharded: every rank holds the SAME K chains, nothing to add up
             blk = reduce_block(blk)
         return summarize_block(blk.cpu().numpy())
 

@@ -11,7 +11,7 @@ for spec in "$@"; do
   mb=${spec%%:*}; extra=""; [ "$spec" != "$mb" ] && extra=$(echo "${spec#*:}" | tr ',' ' ')
   tagx=$(echo "$extra" | tr -cd 'A-Z0-9=' | sed 's/DRMNCP//g'); mbn=${mb}; mb=${mb}${tagx:+_$tagx}
   nvcc $FLAGS -DRMN_CP_MINBLOCKS=$mbn $extra -c riemann_b200/csrc/changepoint.cu -o build/changepoint_mb$mb.o
-  objs="build/api.o build/util.o build/small_gauss.o build/dense.o build/logistic.o build/tc_gemm.o build/dense_tf32.o build/comm.o build/acf.o"
+  objs="build/api.o build/util.o build/small_gauss.o build/dense.o build/logistic.o build/logistic_fused.o build/tc_gemm.o build/dense_tf32.o build/comm.o build/acf.o"
   nvcc -shared -o build/lib_cp_mb$mb.so $objs build/changepoint_mb$mb.o -lcudart -ldl
   echo "built build/lib_cp_mb$mb.so"
 done

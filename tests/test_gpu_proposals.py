@@ -154,3 +154,17 @@ def test_checkpoint_resume_is_bit_exact():
     b.run(300, trace=False)
     assert np.array_equal(np.asarray(a._chain_thetas[-1]), np.asarray(b._chain_thetas[-1]))
     assert np.array_equal(a.proposal.scale, b.proposal.scale)
+
+
+def test_checkpoint_is_refused_where_the_state_cannot_be_saved():
+    """The covariance-adapting proposals and AdaptScalepCN keep per-chain state the ABI cannot read back (Haario
+    accumulators, compounding rho): get_checkpoint must refuse instead of resuming silently different chains."""
+    from riemann_b200 import ParameterError, Sampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import AdaptCovRandomWalk, AdaptScalepCN
+    m = benchmarks.benchmark_gauss2d_corr
+    for prop in (AdaptCovRandomWalk(0.1 * np.eye(2)), AdaptScalepCN(np.eye(2), 0.5)):
+        s = Sampler(m, prop, np.ones(2), K=8, seed=1)
+        s.run(20, trace=False)
+        with pytest.raises(ParameterError):
+            s.get_checkpoint()
