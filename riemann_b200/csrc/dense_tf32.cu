@@ -29,6 +29,7 @@
 
 namespace tc {
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
                 const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
                 int mala, cudaStream_t st);
@@ -217,6 +218,157 @@ finish_propose_f32_kernel(TState st, TStep sp) {
     }
 }
 
+// The same pass with the whole row in registers (dp <= 128 * EPL float4 per lane): every array is read ONCE, all loads
+// of a row are in flight together, and two streams of the first version are gone --
+//   * the increment is stored once, raw (Yph = delta as fp32; kind::tf32 drops the low 13 mantissa bits of its operand
+//     itself, so the GEMM's "hi" pass reads it as is) plus its remainder Ypl = delta - trunc(delta); this pass reads
+//     only the raw array;
+//   * the noise is not stored: p' = p_half - eps/2 (v + P delta) with p_half = delta / eps (hamiltonian.py:27-40; the
+//     increment actually applied, theta' = fl32(y + delta)).
+// Per element: reads delta, V, P delta, y (16 B), writes y, V on accept (8 B) and delta, its remainder (8 B).
+template <int EPL>
+__global__ void __launch_bounds__(128)
+finish_propose_rows_kernel(TState st, TStep sp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int dp = st.dp, d = st.d;
+    const int64_t K = st.K;
+    const size_t ro = (size_t)r * dp;
+    const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 Yv[EPL], Vv[EPL], Dv[EPL], Pv[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int j4 = lane * 4 + 128 * i;
+        const bool in = j4 < dp;
+        Yv[i] = in ? *reinterpret_cast<const float4*>(st.Y + ro + j4) : z4;
+        Vv[i] = in ? *reinterpret_cast<const float4*>(st.V + ro + j4) : z4;
+        Dv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Yph + ro + j4) : z4;
+        Pv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Vp + ro + j4) : z4;
+    }
+    double lp = st.lp[r];
+    bool acc = false;
+    const bool mala = sp.prop_kind == RMN_PROP_HMC;
+    if (sp.finish) {
+        const double eps_old = st.epsrow[r];
+        const double he = 0.5 * eps_old, ie = mala ? 1.0 / eps_old : 0.0;
+        double q = 0.0, k1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const float dl[4] = {Dv[i].x, Dv[i].y, Dv[i].z, Dv[i].w};
+            const float wv[4] = {Vv[i].x, Vv[i].y, Vv[i].z, Vv[i].w};
+            const float pv[4] = {Pv[i].x, Pv[i].y, Pv[i].z, Pv[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double w2 = (double)wv[e] + (double)pv[e];                   // v + P delta = V of the proposal
+                q += (double)dl[e] * ((double)wv[e] + w2);                         // quad' - quad = delta . (2 v + P delta)
+                if (mala) {
+                    const double p1 = (double)dl[e] * ie - he * ((double)wv[e] + w2);   // hamiltonian.py:27,40
+                    k1 += p1 * p1;
+                }
+            }
+        }
+        q = group_sum<32>(q);
+        k1 = group_sum<32>(k1);
+        const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // gaussian.py:52
+        const double lqr = mala ? 0.5 * (k1 - st.k0[r]) : 0.0;      // hamiltonian.py:89
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        acc = mh_accept(lpn, lp, lqr, u);
+        if (acc) lp = lpn;
+        if (lane == 0) {
+            if (acc) st.lp[r] = lp;
+            st.dacc[r] += acc ? 1 : 0;
+            if (sp.adapt) {
+                AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
+                ad.update(acc, sp.target);
+                st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts;
+            }
+            if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
+            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
+            if (sp.tr_lqr) sp.tr_lqr[r] = lqr;
+            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+        }
+        __syncwarp();
+        if (acc || sp.tr_prop_theta) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const int j4 = lane * 4 + 128 * i;
+                if (j4 >= dp) continue;
+                const float4 yp = make_float4(Yv[i].x + Dv[i].x, Yv[i].y + Dv[i].y, Yv[i].z + Dv[i].z, Yv[i].w + Dv[i].w);
+                if (sp.tr_prop_theta) {
+                    const float pvv[4] = {yp.x, yp.y, yp.z, yp.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (j4 + e < d) sp.tr_prop_theta[r * d + j4 + e] = (double)pvv[e] + st.mu[j4 + e];
+                }
+                if (acc) {                                       // accept: y += delta, V += P delta
+                    Yv[i] = yp;
+                    Vv[i] = make_float4(Vv[i].x + Pv[i].x, Vv[i].y + Pv[i].y, Vv[i].z + Pv[i].z, Vv[i].w + Pv[i].w);
+                    *reinterpret_cast<float4*>(st.Y + ro + j4) = Yv[i];
+                    *reinterpret_cast<float4*>(st.V + ro + j4) = Vv[i];
+                }
+            }
+        }
+    }
+    const double scale = sp.adapt ? st.scale[r] : 1.0;
+    const double eps = mala ? scale * sp.eps0 : scale;
+    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+    double k0 = 0.0, rowsum = 0.0;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const int j4 = lane * 4 + 128 * i;
+        if (j4 >= dp) continue;
+        const float yv[4] = {Yv[i].x, Yv[i].y, Yv[i].z, Yv[i].w};
+        const float vv[4] = {Vv[i].x, Vv[i].y, Vv[i].z, Vv[i].w};
+        rowsum += ((double)yv[0] + (double)yv[1]) + ((double)yv[2] + (double)yv[3]);
+        if (want_trace) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j4 + e < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + e] = (double)yv[e] + st.mu[j4 + e];
+        }
+        if (!sp.propose) continue;
+        double xi[4];
+        if (sp.inj_xi) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xi[e] = (j4 + e < d) ? sp.inj_xi[r * d + j4 + e] : 0.0;
+        } else {
+            normal4(rk.block((uint64_t)sp.step_prop, (uint32_t)(j4 >> 2)), xi);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j4 + e >= d) xi[e] = 0.0;
+        }
+        float od[4], ol[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float xf = (float)xi[e];                                           // the noise as the kernels see it
+            double dlt;                                                              // theta' - theta
+            if (mala) dlt = eps * ((double)xf + 0.5 * eps * (-(double)vv[e]));       // hamiltonian.py:27,30
+            else dlt = scale * ((double)st.Ldiag[j4 + e] * (double)xf);              // randomwalk.py:26
+            od[e] = (yv[e] + (float)dlt) - yv[e];                                    // theta' = fl32(y + delta)
+            float hi;
+            tc::split_tf32(od[e], hi, ol[e]);                                        // remainder after the tensor core's truncation
+            k0 += (double)xf * (double)xf;
+        }
+        *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
+        *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+    }
+    if (sp.propose) {
+        k0 = group_sum<32>(k0);
+        if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
+    }
+    if (sp.diag) {
+        rowsum = group_sum<32>(rowsum);
+        const int nd = min(d, ND_MAX - 1) + 1;
+        __syncwarp();                                               // the accept-update of this row is visible to the warp
+        if (lane < nd) {
+            const double f = (lane == nd - 1) ? rowsum / (double)d : (double)st.Y[ro + lane];
+            st.S1[(int64_t)lane * K + r] += f;
+            st.S2[(int64_t)lane * K + r] += f * f;
+        }
+    }
+}
+
 __global__ void tset_kernel(TState st, const double* __restrict__ theta) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= st.K * st.dp) return;
@@ -293,12 +445,15 @@ struct DenseTF32Sampler : SamplerImpl {
     rmn_sampler* s;
     TState st{};
     tc::GemmMaps maps;
+    tc::GemmMaps maps_narrow;     // the same operands with 128-row boxes of P: 128 x 128 output tiles
+    bool narrow = false;          // fewer than #SM tiles of 128 x 256: use the narrow tile (RMN_TF32_NARROW=0|1 overrides)
     float* d_Ph = nullptr; float* d_Pl = nullptr; float* d_Ldiag = nullptr; double* d_mupad = nullptr;
     int64_t refresh = 512;        // exact fp64 recomputation of V / log-posterior every this many steps
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = 2 * ((st.dp + tc::TN - 1) / tc::TN);   // one partial per 128-column half tile
         if (const char* e = getenv("RMN_TF32_FUSED_EPI")) row_reduce = !(e[0] == '1');
+        if (const char* e = getenv("RMN_TF32_ROWS")) rows_kernel = !(e[0] == '0');
     }
     ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
@@ -351,11 +506,36 @@ struct DenseTF32Sampler : SamplerImpl {
         if ((rc = tc::make_tmap_2d(&maps.al, st.Ypl, st.K, dp, dp, tc::TM, tc::TK3))) return rc;
         if ((rc = tc::make_tmap_2d(&maps.bh, d_Ph, dp, dp, dp, tc::TN, tc::TK3))) return rc;
         if ((rc = tc::make_tmap_2d(&maps.bl, d_Pl, dp, dp, dp, tc::TN, tc::TK3))) return rc;
+        maps_narrow.ah = maps.ah; maps_narrow.al = maps.al;
+        if ((rc = tc::make_tmap_2d(&maps_narrow.bh, d_Ph, dp, dp, dp, 128, tc::TK3))) return rc;
+        if ((rc = tc::make_tmap_2d(&maps_narrow.bl, d_Pl, dp, dp, dp, 128, tc::TK3))) return rc;
+        {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int64_t wide = ((st.K + tc::TM - 1) / tc::TM) * ((dp + tc::TN - 1) / tc::TN);
+            narrow = wide < sms;
+            if (const char* e = getenv("RMN_TF32_NARROW")) narrow = (e[0] == '1');
+        }
         if ((rc = rmn_fill_f64(st.scale, st.K, 1.0, 0))) return rc;
         RMN_CUDA(cudaDeviceSynchronize());
         return RMN_OK;
     }
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
+    // finish / propose pass: the row-in-registers kernel whenever the row fits (dp <= 1024) and the GEMM runs with the
+    // plain epilogue; RMN_TF32_ROWS=0 keeps the first version (A/B measurements)
+    bool rows_kernel = true;
+    void launch_fp(const TStep& sp, cudaStream_t stream) {
+        const unsigned g4 = (unsigned)((st.K * 32 + 127) / 128);
+        if (rows_kernel && row_reduce && st.dp <= 1024) {
+            if (st.dp <= 128) finish_propose_rows_kernel<1><<<g4, 128, 0, stream>>>(st, sp);
+            else if (st.dp <= 256) finish_propose_rows_kernel<2><<<g4, 128, 0, stream>>>(st, sp);
+            else if (st.dp <= 512) finish_propose_rows_kernel<4><<<g4, 128, 0, stream>>>(st, sp);
+            else finish_propose_rows_kernel<8><<<g4, 128, 0, stream>>>(st, sp);
+        } else {
+            finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
+        }
+    }
     double c1() const { return st.d * log(2.0 * M_PI); }
     // row_reduce (default): plain store-only GEMM epilogue, the MH reductions run in the finish/propose pass;
     // RMN_TF32_FUSED_EPI=1 selects the fused epilogue (kept for A/B measurements, same results to rounding)
@@ -364,7 +544,8 @@ struct DenseTF32Sampler : SamplerImpl {
         launches++;
         ktimer.begin("tf32x3_gemm_kernel", stream);
         int rc;
-        if (row_reduce) rc = tc::launch_plain(maps, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
+        if (row_reduce && narrow) rc = tc::launch_plain_narrow(maps_narrow, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
+        else if (row_reduce) rc = tc::launch_plain(maps, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
         else rc = tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
                                   st.partq, st.partk, mala, stream);
         ktimer.end(stream);
@@ -426,15 +607,15 @@ struct DenseTF32Sampler : SamplerImpl {
             // A pending proposal must be finished before V is overwritten, so split the pass.
             if (refresh > 0 && since_refresh >= refresh && sp.finish && sp.propose) {
                 TStep fin = sp; fin.propose = 0;
-                finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, fin);
+                launch_fp(fin, stream);
                 RMN_KERNEL_CHECK(); launches++;
                 if (int rc = exact(stream)) return rc;
                 TStep pro = sp; pro.finish = 0; pro.diag = 0; pro.trace_slot = -1;
                 pro.tr_prop_lp = nullptr; pro.tr_acc = nullptr; pro.tr_lqr = nullptr; pro.tr_prop_theta = nullptr;
-                finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, pro);
+                launch_fp(pro, stream);
                 RMN_KERNEL_CHECK(); launches++;
             } else {
-                finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
+                launch_fp(sp, stream);
                 RMN_KERNEL_CHECK(); launches++;
             }
             if (t == T) break;

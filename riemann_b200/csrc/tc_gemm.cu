@@ -71,7 +71,10 @@ enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 template <int EPI, int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
-                   int ldc, MalaEpi ep, int ksplit, int kb_per, int64_t split_stride, int m_fastest) {
+                   int ldc, MalaEpi ep, int ksplit, int kb_per, int64_t split_stride, int m_fastest, int tn) {
+    // tn: columns of C per tile, TN = 256 or 128 (the B tensor maps must have been built with box_rows = tn).  The
+    // narrow tile is for outputs with fewer than #SM tiles of 128 x 256 (2,048 chains x 1,024 columns = 64 of them):
+    // it doubles the tile count instead of leaving half of the SMs idle.  Shared-memory regions keep their 256-row size.
     // m_fastest: tile order.  0 = n fastest (CTAs running together share rows of A in L2), 1 = m fastest
     // (they share rows of B: the logits GEMM, whose A -- the chains' Theta -- is tiny and whose B -- the data
     // matrix -- should cross HBM once).
@@ -98,7 +101,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB_all = Kdim / TK;
     // kb_per = k-blocks per split (the last one may be short, none is empty: launch_common)
-    const int n_tiles = (N + TN - 1) / TN;
+    const int n_tiles = (N + tn - 1) / tn;
     const int64_t m_tiles = (M + TM - 1) / TM;
     const int64_t mn_tiles = m_tiles * n_tiles;
     const int64_t num_tiles = mn_tiles * ksplit;
@@ -126,12 +129,13 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             const int kb0 = (int)(tile / mn_tiles) * kb_per;
             const int kb1 = min(KB_all, kb0 + kb_per);
             const int m0 = (int)(m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
-            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * TN;
+            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn;
+            const uint32_t tx_bytes = (uint32_t)((PASSES == 1 ? 1 : 2) * (A_BYTES + tn * ROWB));
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], STAGE_BYTES);
+                mbar_expect_tx(&full[s], tx_bytes);
                 tma_load_2d(st, &maps.ah, &full[s], kb * TK, m0);
                 tma_load_2d(st + OFF_BH, &maps.bh, &full[s], kb * TK, n0);
                 if (PASSES == 3) {
@@ -143,7 +147,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer (one thread) =====
         // UMMA N = the valid width of B rounded up to 16 (a d-wide gradient tile does not pay for 256 columns)
-        const int n_eff = (N >= TN) ? TN : ((N + 15) / 16 * 16);
+        const int n_eff = (N >= tn) ? tn : ((N + 15) / 16 * 16);
         const uint32_t idesc = umma_idesc_tf32(TM, n_eff);
         uint32_t it = 0, ti = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
@@ -183,7 +187,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             const int a = ti % ACC_STAGES;
             const int64_t mn = tile % mn_tiles;
             const int64_t m0 = (m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
-            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * TN;
+            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn;
             float* Cs = (EPI == EPI_PLAIN) ? C + (tile / mn_tiles) * split_stride : C;
             if (EPI == EPI_MALA) {
                 // The epilogue's inputs do not depend on the accumulator: pull this warp's 32 rows x 128 columns of
@@ -192,7 +196,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int64_t mr = m0 + q * 32 + it * 8 + (lane >> 2);
-                    const int nn = n0 + half * (TN / 2) + (lane & 3) * 32;
+                    const int nn = n0 + half * (tn / 2) + (lane & 3) * 32;
                     if (mr < M && nn < N) {
                         const size_t off = (size_t)mr * ldc + nn;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.yph + off));
@@ -218,9 +222,9 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                     if (mr < M) hev[it] = 0.5 * ep.epsrow[mr];
                 }
             }
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (TN / 2));
-            for (int c0 = 0; c0 < TN / 2; c0 += 16) {
-                const int n = n0 + half * (TN / 2) + c0;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (tn / 2));
+            for (int c0 = 0; c0 < tn / 2; c0 += 16) {
+                const int n = n0 + half * (tn / 2) + c0;
                 if (n >= N) continue;                                   // warp-uniform
                 // (MALA) issue the chunk's 16 independent global loads FIRST: their L2 latency (well over
                 // 1,000 cycles under the TMA traffic) then overlaps the TMEM read and the staging below
@@ -306,14 +310,16 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
 }
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
-                         cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0) {
+                         cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0,
+                         int tn = TN) {
+    if (tn != TN && (tn != 128 || ep)) { rmn_set_error("tf32x3 gemm: tile width must be 256, or 128 with the plain epilogue"); return RMN_ERR_PARAM; }
     const int tk = (passes == 1) ? TK : TK3;                           // k-block of the kernel variant
     if (Kdim % 32 != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
     if (ksplit < 1 || ksplit > Kdim / tk || (ep && ksplit != 1)) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
     // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
     const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
     ksplit = (Kdim / tk + kbp - 1) / kbp;
-    const int64_t tiles = (int64_t)((N + TN - 1) / TN) * ((M + TM - 1) / TM) * ksplit;
+    const int64_t tiles = (int64_t)((N + tn - 1) / tn) * ((M + TM - 1) / TM) * ksplit;
     static int sms_of[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -330,15 +336,19 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep, 1, kbp, 0, 0);
-    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest);
-    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest);
+    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep, 1, kbp, 0, 0, TN);
+    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest, tn);
+    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest, tn);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
 
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st);
+}
+// 3-pass product with 128-column tiles (B maps built with box_rows = 128)
+int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 3, 1, 0, 0, 128);
 }
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 1);
