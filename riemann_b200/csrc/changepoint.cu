@@ -269,7 +269,7 @@ __device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const doubl
 }
 
 #ifndef RMN_CP_MINBLOCKS
-#define RMN_CP_MINBLOCKS 5   /* 96 regs, 20 warps/SM: best of 4..8 measured (gpurun r17) */
+#define RMN_CP_MINBLOCKS 4   /* 128 regs, 16 warps/SM, no spills: best of 4, 5, 6 with the move-specific guards (gpurun r2e) */
 #endif
 #ifndef RMN_CP_FASTPATHS
 #define RMN_CP_FASTPATHS 1   /* move-specific paths for warps whose chains all drew the same move type */

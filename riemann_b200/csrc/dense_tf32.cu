@@ -218,20 +218,24 @@ finish_propose_f32_kernel(TState st, TStep sp) {
     }
 }
 
-// The same pass with the whole row in registers (dp <= 128 * EPL float4 per lane): every array is read ONCE, all loads
-// of a row are in flight together, and two streams of the first version are gone --
+// The same pass with the whole row in registers, ONE BLOCK (4 warps) PER CHAIN ROW (dp <= 512 * EPL): every array is read
+// once, all loads of a row are in flight together, 24 warps per SM keep HBM busy, and two streams of the first version
+// are gone --
 //   * the increment is stored once, raw (Yph = delta as fp32; kind::tf32 drops the low 13 mantissa bits of its operand
 //     itself, so the GEMM's "hi" pass reads it as is) plus its remainder Ypl = delta - trunc(delta); this pass reads
 //     only the raw array;
 //   * the noise is not stored: p' = p_half - eps/2 (v + P delta) with p_half = delta / eps (hamiltonian.py:27-40; the
 //     increment actually applied, theta' = fl32(y + delta)).
 // Per element: reads delta, V, P delta, y (16 B), writes y, V on accept (8 B) and delta, its remainder (8 B).
+// Row reductions: warp butterflies, then the four warp partials through shared memory in a fixed order (deterministic).
+constexpr int ROWS_THREADS = 128;
 template <int EPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(ROWS_THREADS)
 finish_propose_rows_kernel(TState st, TStep sp) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (r >= st.K) return;
+    __shared__ double red[2][ROWS_THREADS / 32];
+    __shared__ int acc_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r = blockIdx.x;
     const int dp = st.dp, d = st.d;
     const int64_t K = st.K;
     const size_t ro = (size_t)r * dp;
@@ -240,16 +244,15 @@ finish_propose_rows_kernel(TState st, TStep sp) {
     float4 Yv[EPL], Vv[EPL], Dv[EPL], Pv[EPL];
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
-        const int j4 = lane * 4 + 128 * i;
+        const int j4 = tid * 4 + 4 * ROWS_THREADS * i;
         const bool in = j4 < dp;
         Yv[i] = in ? *reinterpret_cast<const float4*>(st.Y + ro + j4) : z4;
         Vv[i] = in ? *reinterpret_cast<const float4*>(st.V + ro + j4) : z4;
         Dv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Yph + ro + j4) : z4;
         Pv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Vp + ro + j4) : z4;
     }
-    double lp = st.lp[r];
-    bool acc = false;
     const bool mala = sp.prop_kind == RMN_PROP_HMC;
+    bool acc = false;
     if (sp.finish) {
         const double eps_old = st.epsrow[r];
         const double he = 0.5 * eps_old, ie = mala ? 1.0 / eps_old : 0.0;
@@ -264,36 +267,42 @@ finish_propose_rows_kernel(TState st, TStep sp) {
                 const double w2 = (double)wv[e] + (double)pv[e];                   // v + P delta = V of the proposal
                 q += (double)dl[e] * ((double)wv[e] + w2);                         // quad' - quad = delta . (2 v + P delta)
                 if (mala) {
-                    const double p1 = (double)dl[e] * ie - he * ((double)wv[e] + w2);   // hamiltonian.py:27,40
+                    const double p1 = (double)dl[e] * ie - he * w2;                // p' = p_half + eps/2 g(theta'), hamiltonian.py:40
                     k1 += p1 * p1;
                 }
             }
         }
         q = group_sum<32>(q);
         k1 = group_sum<32>(k1);
-        const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // gaussian.py:52
-        const double lqr = mala ? 0.5 * (k1 - st.k0[r]) : 0.0;      // hamiltonian.py:89
-        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
-        acc = mh_accept(lpn, lp, lqr, u);
-        if (acc) lp = lpn;
-        if (lane == 0) {
-            if (acc) st.lp[r] = lp;
-            st.dacc[r] += acc ? 1 : 0;
+        if (lane == 0) { red[0][warp] = q; red[1][warp] = k1; }
+        __syncthreads();
+        if (tid == 0) {
+            double lp = st.lp[r];
+            q = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
+            k1 = ((red[1][0] + red[1][1]) + red[1][2]) + red[1][3];
+            const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // gaussian.py:52
+            const double lqr = mala ? 0.5 * (k1 - st.k0[r]) : 0.0;      // hamiltonian.py:89
+            const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+            const bool a1 = mh_accept(lpn, lp, lqr, u);
+            if (a1) { lp = lpn; st.lp[r] = lp; }
+            st.dacc[r] += a1 ? 1 : 0;
             if (sp.adapt) {
                 AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
-                ad.update(acc, sp.target);
+                ad.update(a1, sp.target);
                 st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts;
             }
             if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
-            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
+            if (sp.tr_acc) sp.tr_acc[r] = a1 ? 1 : 0;
             if (sp.tr_lqr) sp.tr_lqr[r] = lqr;
             if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+            acc_sh = a1 ? 1 : 0;
         }
-        __syncwarp();
+        __syncthreads();                                             // acc_sh, and st.scale[r] for the proposal below
+        acc = acc_sh != 0;
         if (acc || sp.tr_prop_theta) {
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
-                const int j4 = lane * 4 + 128 * i;
+                const int j4 = tid * 4 + 4 * ROWS_THREADS * i;
                 if (j4 >= dp) continue;
                 const float4 yp = make_float4(Yv[i].x + Dv[i].x, Yv[i].y + Dv[i].y, Yv[i].z + Dv[i].z, Yv[i].w + Dv[i].w);
                 if (sp.tr_prop_theta) {
@@ -317,7 +326,7 @@ finish_propose_rows_kernel(TState st, TStep sp) {
     double k0 = 0.0, rowsum = 0.0;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
-        const int j4 = lane * 4 + 128 * i;
+        const int j4 = tid * 4 + 4 * ROWS_THREADS * i;
         if (j4 >= dp) continue;
         const float yv[4] = {Yv[i].x, Yv[i].y, Yv[i].z, Yv[i].w};
         const float vv[4] = {Vv[i].x, Vv[i].y, Vv[i].z, Vv[i].w};
@@ -326,6 +335,16 @@ finish_propose_rows_kernel(TState st, TStep sp) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (j4 + e < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + e] = (double)yv[e] + st.mu[j4 + e];
+        }
+        if (sp.diag && j4 < ND_MAX - 1) {                            // the first coordinates are tracked functionals
+            const int nd1 = min(d, ND_MAX - 1);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (j4 + e < nd1) {
+                    const double f = (double)yv[e];
+                    st.S1[(int64_t)(j4 + e) * K + r] += f;
+                    st.S2[(int64_t)(j4 + e) * K + r] += f * f;
+                }
         }
         if (!sp.propose) continue;
         double xi[4];
@@ -353,18 +372,23 @@ finish_propose_rows_kernel(TState st, TStep sp) {
         *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
         *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
     }
-    if (sp.propose) {
+    if (sp.propose || sp.diag) {
         k0 = group_sum<32>(k0);
-        if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
-    }
-    if (sp.diag) {
         rowsum = group_sum<32>(rowsum);
-        const int nd = min(d, ND_MAX - 1) + 1;
-        __syncwarp();                                               // the accept-update of this row is visible to the warp
-        if (lane < nd) {
-            const double f = (lane == nd - 1) ? rowsum / (double)d : (double)st.Y[ro + lane];
-            st.S1[(int64_t)lane * K + r] += f;
-            st.S2[(int64_t)lane * K + r] += f * f;
+        __syncthreads();                                             // red[] of the finish phase has been read
+        if (lane == 0) { red[0][warp] = k0; red[1][warp] = rowsum; }
+        __syncthreads();
+        if (tid == 0) {
+            if (sp.propose) {
+                st.k0[r] = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
+                st.epsrow[r] = eps;
+            }
+            if (sp.diag) {
+                const int nd = min(d, ND_MAX - 1) + 1;
+                const double f = (((red[1][0] + red[1][1]) + red[1][2]) + red[1][3]) / (double)d;
+                st.S1[(int64_t)(nd - 1) * K + r] += f;
+                st.S2[(int64_t)(nd - 1) * K + r] += f * f;
+            }
         }
     }
 }
@@ -522,16 +546,16 @@ struct DenseTF32Sampler : SamplerImpl {
         return RMN_OK;
     }
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
-    // finish / propose pass: the row-in-registers kernel whenever the row fits (dp <= 1024) and the GEMM runs with the
+    // finish / propose pass: the row-in-registers kernel whenever the row fits (dp <= 4096) and the GEMM runs with the
     // plain epilogue; RMN_TF32_ROWS=0 keeps the first version (A/B measurements)
     bool rows_kernel = true;
     void launch_fp(const TStep& sp, cudaStream_t stream) {
-        const unsigned g4 = (unsigned)((st.K * 32 + 127) / 128);
-        if (rows_kernel && row_reduce && st.dp <= 1024) {
-            if (st.dp <= 128) finish_propose_rows_kernel<1><<<g4, 128, 0, stream>>>(st, sp);
-            else if (st.dp <= 256) finish_propose_rows_kernel<2><<<g4, 128, 0, stream>>>(st, sp);
-            else if (st.dp <= 512) finish_propose_rows_kernel<4><<<g4, 128, 0, stream>>>(st, sp);
-            else finish_propose_rows_kernel<8><<<g4, 128, 0, stream>>>(st, sp);
+        const unsigned gk = (unsigned)st.K;                      // one block per chain row
+        if (rows_kernel && row_reduce && st.dp <= 4096) {
+            if (st.dp <= 512) finish_propose_rows_kernel<1><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
+            else if (st.dp <= 1024) finish_propose_rows_kernel<2><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
+            else if (st.dp <= 2048) finish_propose_rows_kernel<4><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
+            else finish_propose_rows_kernel<8><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
         } else {
             finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
         }

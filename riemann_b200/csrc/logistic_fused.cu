@@ -16,8 +16,9 @@
 //                 GEMM2  G[128 x dp32] += R[128 x 64] Xh[64 x dp32]                  (single-pass TF32: the gradient
 //                        only shapes the proposal); A = R from tensor memory, written in place over Z by the
 //                        pointwise warps, B = the Xh tile read MN-major (no transposed copy of X in HBM)
-//   2 x 4 warps   pointwise stage, one warpgroup per Z buffer (tiles alternate): tcgen05.ld the logits, fp32
-//                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element),
+//   2 x 4 warps   pointwise stage, both warpgroups on every tile (32 of its 64 rows each): tcgen05.ld the logits, fp32
+//                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element, two
+//                 elements per instruction with the packed fp32 FMA of sm_100),
 //                 log-likelihood partial sums in fp64, R = y - p rounded to TF32 -> tcgen05.st back into the same
 //                 TMEM columns (and W = p(1-p) to HBM for the mMALA metric GEMM)
 //
@@ -114,19 +115,21 @@ __device__ __forceinline__ void split_rn(double x, float& hi, float& lo) {
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// log1p(e), e in [0, 1]: degree-9 Chebyshev interpolant in t = 2e - 1 (|error| < 7e-8 in fp32 Horner form)
-__device__ __forceinline__ float log1p_unit(float e) {
-    const float t = fmaf(2.0f, e, -1.0f);
-    float p = 7.152816828e-06f;
-    p = fmaf(p, t, -2.401530172e-05f);
-    p = fmaf(p, t, 6.393497408e-05f);
-    p = fmaf(p, t, -2.240642703e-04f);
-    p = fmaf(p, t, 8.235513423e-04f);
-    p = fmaf(p, t, -3.088083925e-03f);
-    p = fmaf(p, t, 1.234561512e-02f);
-    p = fmaf(p, t, -5.555534548e-02f);
-    p = fmaf(p, t, 3.333333346e-01f);
-    p = fmaf(p, t, 4.054651039e-01f);
+// log1p(e) for two elements at once, e in [0, 1]: degree-9 Chebyshev interpolant in t = 2e - 1, Horner form with the
+// packed fp32 FMA of sm_100 (FFMA2: one instruction, two lanes); |error| < 7e-8
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 log1p_unit2(float2 e) {
+    const float2 t = __ffma2_rn(f2(2.0f), e, f2(-1.0f));
+    float2 p = f2(7.152816828e-06f);
+    p = __ffma2_rn(p, t, f2(-2.401530172e-05f));
+    p = __ffma2_rn(p, t, f2(6.393497408e-05f));
+    p = __ffma2_rn(p, t, f2(-2.240642703e-04f));
+    p = __ffma2_rn(p, t, f2(8.235513423e-04f));
+    p = __ffma2_rn(p, t, f2(-3.088083925e-03f));
+    p = __ffma2_rn(p, t, f2(1.234561512e-02f));
+    p = __ffma2_rn(p, t, f2(-5.555534548e-02f));
+    p = __ffma2_rn(p, t, f2(3.333333346e-01f));
+    p = __ffma2_rn(p, t, f2(4.054651039e-01f));
     return p;
 }
 
@@ -159,7 +162,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
         for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 8); }
         mbar_init(th_ready, 4);
         mbar_init(g_full, 1);
         fence_barrier_init();
@@ -268,51 +271,64 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(th_ready);
         }
+        // Every tile is split between the two warpgroups (32 of its 64 data rows each), so a tile's pointwise latency is
+        // half of what one warpgroup per tile gave and R(t) is ready while GEMM1(t+1) is still running.
         double ll = 0.0;
         float* wrow = HASW ? a.W + (okc ? c : 0) * a.ldw : nullptr;
-        for (int t = wg; t < ntile; t += 2) {
+        const int col0 = wg * 32;
+        for (int t = 0; t < ntile; ++t) {
             const int s = t % SB;
-            const uint32_t* ysm = reinterpret_cast<const uint32_t*>(ringB + s * C::B_BYTES + C::XPART);
-            const int64_t row0 = (t_begin + t) * NT;
-            const bool ragged = row0 + NT > a.N;
+            const uint2* ysm = reinterpret_cast<const uint2*>(ringB + s * C::B_BYTES + C::XPART) + col0 / 2;
+            const int64_t row0 = (t_begin + t) * NT + col0;
             mbar_wait(&fullB[s], (t / SB) & 1);          // the label masks arrive with ring B
             mbar_wait(&z_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
-            const uint32_t tz = lane_base + C::COL_Z + (uint32_t)((t & 1) * NT);
+            const uint32_t tz = lane_base + C::COL_Z + (uint32_t)((t & 1) * NT + col0);
+            float v[32];
+            tmem_ld_32x32(tz, v);
+            uint32_t rr[32];
+            float wv[HASW ? 32 : 2];
+            float2 part = f2(0.0f);
 #pragma unroll
-            for (int ch = 0; ch < NT / 32; ++ch) {
-                float v[32];
-                tmem_ld_32x32(tz + ch * 32, v);
-                uint32_t rr[32];
-                float wv[HASW ? 32 : 1];
-                float part = 0.0f;
+            for (int e = 0; e < 32; e += 2) {
+                const uint2 ym = ysm[e >> 1];                                   // 0x80000000 where y = 1
+                const float s0 = __uint_as_float(__float_as_uint(v[e]) ^ ym.x);    // s = (1 - 2y) z
+                const float s1 = __uint_as_float(__float_as_uint(v[e + 1]) ^ ym.y);
+                const float2 ex = make_float2(ex2_approx(-1.4426950408889634f * fabsf(v[e])),     // e = exp(-|z|)
+                                              ex2_approx(-1.4426950408889634f * fabsf(v[e + 1])));
+                // softplus(s) = max(s, 0) + log1p(e) = softplus(z) - y z;  the log-likelihood term is its negative
+                const float2 sp = __ffma2_rn(log1p_unit2(ex), f2(1.0f), make_float2(fmaxf(s0, 0.0f), fmaxf(s1, 0.0f)));
+                part = __ffma2_rn(sp, f2(-1.0f), part);
+                const float2 q = __ffma2_rn(ex, f2(1.0f), f2(1.0f));
+                const float2 inv = make_float2(rcp_approx(q.x), rcp_approx(q.y));
+                const float2 ei = __ffma2_rn(ex, inv, f2(0.0f));
+                const float g0 = (s0 >= 0.0f) ? inv.x : ei.x;                   // sigmoid(s);  y - p = (2y - 1) sigmoid(s)
+                const float g1 = (s1 >= 0.0f) ? inv.y : ei.y;
+                rr[e] = ((__float_as_uint(g0) | (~ym.x & 0x80000000u)) + 0x1000u) & 0xFFFFE000u;      // nearest TF32
+                rr[e + 1] = ((__float_as_uint(g1) | (~ym.y & 0x80000000u)) + 0x1000u) & 0xFFFFE000u;
+                if (HASW) { const float2 w2 = __ffma2_rn(ei, inv, f2(0.0f)); wv[e] = w2.x; wv[e + 1] = w2.y; }
+                if ((e & 6) == 6) { ll += (double)(part.x + part.y); part = f2(0.0f); }
+            }
+            tmem_st_32x32(tz, rr);
+            if (HASW && okc && row0 < a.ldw) {                       // ldw is a multiple of 32
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const uint32_t ym = ysm[ch * 32 + e];                       // 0x80000000 where y = 1
-                    const float sv = __uint_as_float(__float_as_uint(v[e]) ^ ym);   // s = (1 - 2y) z
-                    const float ex = ex2_approx(-1.4426950408889634f * fabsf(sv));   // e = exp(-|s|)
-                    const float sp = fmaxf(sv, 0.0f) + log1p_unit(ex);          // softplus(s) = softplus(z) - y z
-                    const float inv = rcp_approx(1.0f + ex);
-                    const float sg = (sv >= 0.0f) ? inv : ex * inv;             // sigmoid(s);  y - p = (2y - 1) sigmoid(s)
-                    float term = -sp;
-                    if (ragged && row0 + ch * 32 + e >= a.N) term = 0.0f;       // padding rows (zero X rows) do not count
-                    part += term;
-                    if ((e & 7) == 7) { ll += (double)part; part = 0.0f; }
-                    const uint32_t rb = __float_as_uint(sg) | (~ym & 0x80000000u);
-                    rr[e] = (rb + 0x1000u) & 0xFFFFE000u;                      // nearest TF32
-                    if (HASW) wv[e] = ex * inv * inv;
-                }
-                tmem_st_32x32(tz + ch * 32, rr);
-                if (HASW && okc && row0 + ch * 32 < a.ldw) {          // ldw is a multiple of 32
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        *reinterpret_cast<float4*>(wrow + row0 + ch * 32 + e) = make_float4(wv[e], wv[e + 1], wv[e + 2], wv[e + 3]);
-                }
+                for (int e = 0; e < 32; e += 4)
+                    *reinterpret_cast<float4*>(wrow + row0 + e) = make_float4(wv[e], wv[e + 1], wv[e + 2], wv[e + 3]);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&r_full[t & 1]);
+        }
+        // rows beyond N (the last tile's padding) are zero rows of X: z = 0 exactly, and each contributed
+        // -softplus(0) in the arithmetic above -- take those terms out again
+        if (t_end == a.tiles_total && ntile > 0) {
+            const int64_t lo = (a.tiles_total - 1) * NT + col0;
+            const int64_t npad = lo + 32 - max(a.N, lo);
+            if (npad > 0) {
+                const float2 sp0 = log1p_unit2(f2(ex2_approx(-0.0f)));
+                ll += (double)npad * (double)sp0.x;
+            }
         }
         if (okc) a.llp[((int64_t)rs * 2 + wg) * a.K + c] = ll;
         if (wg == 0) {
