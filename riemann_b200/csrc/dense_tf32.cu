@@ -218,33 +218,38 @@ finish_propose_f32_kernel(TState st, TStep sp) {
     }
 }
 
-// The same pass with the whole row in registers, ONE BLOCK (4 warps) PER CHAIN ROW (dp <= 512 * EPL): every array is read
-// once, all loads of a row are in flight together, 24 warps per SM keep HBM busy, and two streams of the first version
-// are gone --
+// The same pass with the whole row in registers: WPR warps per chain row (a block of 4 warps holds 4 / WPR rows), EPL float4
+// per lane (dp <= 128 * WPR * EPL).  Every array is read once and all loads of a row are in flight together; two streams
+// of the first version are gone --
 //   * the increment is stored once, raw (Yph = delta as fp32; kind::tf32 drops the low 13 mantissa bits of its operand
 //     itself, so the GEMM's "hi" pass reads it as is) plus its remainder Ypl = delta - trunc(delta); this pass reads
 //     only the raw array;
 //   * the noise is not stored: p' = p_half - eps/2 (v + P delta) with p_half = delta / eps (hamiltonian.py:27-40; the
 //     increment actually applied, theta' = fl32(y + delta)).
 // Per element: reads delta, V, P delta, y (16 B), writes y, V on accept (8 B) and delta, its remainder (8 B).
-// Row reductions: warp butterflies, then the four warp partials through shared memory in a fixed order (deterministic).
+// Row reductions: warp butterflies, then (WPR > 1) the warps' partials through shared memory, summed in a fixed order by
+// every warp of the row, which all take the same accept decision -- no serial section.
 constexpr int ROWS_THREADS = 128;
-template <int EPL>
+template <int WPR, int EPL>
 __global__ void __launch_bounds__(ROWS_THREADS)
 finish_propose_rows_kernel(TState st, TStep sp) {
-    __shared__ double red[2][ROWS_THREADS / 32];
-    __shared__ int acc_sh;
+    constexpr int RPB = (ROWS_THREADS / 32) / WPR;                   // rows per block
+    __shared__ double red[2][RPB][WPR];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t r = blockIdx.x;
+    const int rib = warp / WPR, wsub = warp % WPR;                   // row in block, warp within the row
+    const int64_t r_raw = (int64_t)blockIdx.x * RPB + rib;
+    const bool live = r_raw < st.K;
+    const int64_t r = live ? r_raw : st.K - 1;                       // dead rows shadow the last one, never store
     const int dp = st.dp, d = st.d;
     const int64_t K = st.K;
     const size_t ro = (size_t)r * dp;
     const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
     const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int jbase = (wsub * 32 + lane) * 4;
     float4 Yv[EPL], Vv[EPL], Dv[EPL], Pv[EPL];
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
-        const int j4 = tid * 4 + 4 * ROWS_THREADS * i;
+        const int j4 = jbase + 128 * WPR * i;
         const bool in = j4 < dp;
         Yv[i] = in ? *reinterpret_cast<const float4*>(st.Y + ro + j4) : z4;
         Vv[i] = in ? *reinterpret_cast<const float4*>(st.V + ro + j4) : z4;
@@ -252,7 +257,9 @@ finish_propose_rows_kernel(TState st, TStep sp) {
         Pv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Vp + ro + j4) : z4;
     }
     const bool mala = sp.prop_kind == RMN_PROP_HMC;
+    const bool writer = live && wsub == 0 && lane == 0;
     bool acc = false;
+    double scale = sp.adapt ? st.scale[r] : 1.0;
     if (sp.finish) {
         const double eps_old = st.epsrow[r];
         const double he = 0.5 * eps_old, ie = mala ? 1.0 / eps_old : 0.0;
@@ -274,38 +281,42 @@ finish_propose_rows_kernel(TState st, TStep sp) {
         }
         q = group_sum<32>(q);
         k1 = group_sum<32>(k1);
-        if (lane == 0) { red[0][warp] = q; red[1][warp] = k1; }
-        __syncthreads();
-        if (tid == 0) {
-            double lp = st.lp[r];
-            q = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
-            k1 = ((red[1][0] + red[1][1]) + red[1][2]) + red[1][3];
-            const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // gaussian.py:52
-            const double lqr = mala ? 0.5 * (k1 - st.k0[r]) : 0.0;      // hamiltonian.py:89
-            const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
-            const bool a1 = mh_accept(lpn, lp, lqr, u);
-            if (a1) { lp = lpn; st.lp[r] = lp; }
-            st.dacc[r] += a1 ? 1 : 0;
-            if (sp.adapt) {
-                AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
-                ad.update(a1, sp.target);
-                st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts;
-            }
+        if (WPR > 1) {
+            if (lane == 0) { red[0][rib][wsub] = q; red[1][rib][wsub] = k1; }
+            __syncthreads();
+            q = 0.0; k1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { q += red[0][rib][w]; k1 += red[1][rib][w]; }
+        }
+        double lp = st.lp[r];
+        const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // gaussian.py:52
+        const double lqr = mala ? 0.5 * (k1 - st.k0[r]) : 0.0;      // hamiltonian.py:89
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        acc = mh_accept(lpn, lp, lqr, u);
+        if (acc) lp = lpn;
+        AdaptState ad{scale, 0, 0};
+        if (sp.adapt) {
+            ad.nsamples = st.nsamp[r]; ad.naccepts = st.nacc[r];
+            ad.update(acc, sp.target);
+            scale = ad.scale;
+        }
+        if (WPR > 1) __syncthreads();                                // every warp of the row has read lp / k0 / the adapt state
+        if (writer) {
+            if (acc) st.lp[r] = lp;
+            st.dacc[r] += acc ? 1 : 0;
+            if (sp.adapt) { st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts; }
             if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
-            if (sp.tr_acc) sp.tr_acc[r] = a1 ? 1 : 0;
+            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
             if (sp.tr_lqr) sp.tr_lqr[r] = lqr;
             if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
-            acc_sh = a1 ? 1 : 0;
         }
-        __syncthreads();                                             // acc_sh, and st.scale[r] for the proposal below
-        acc = acc_sh != 0;
         if (acc || sp.tr_prop_theta) {
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
-                const int j4 = tid * 4 + 4 * ROWS_THREADS * i;
+                const int j4 = jbase + 128 * WPR * i;
                 if (j4 >= dp) continue;
                 const float4 yp = make_float4(Yv[i].x + Dv[i].x, Yv[i].y + Dv[i].y, Yv[i].z + Dv[i].z, Yv[i].w + Dv[i].w);
-                if (sp.tr_prop_theta) {
+                if (sp.tr_prop_theta && live) {
                     const float pvv[4] = {yp.x, yp.y, yp.z, yp.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -314,19 +325,20 @@ finish_propose_rows_kernel(TState st, TStep sp) {
                 if (acc) {                                       // accept: y += delta, V += P delta
                     Yv[i] = yp;
                     Vv[i] = make_float4(Vv[i].x + Pv[i].x, Vv[i].y + Pv[i].y, Vv[i].z + Pv[i].z, Vv[i].w + Pv[i].w);
-                    *reinterpret_cast<float4*>(st.Y + ro + j4) = Yv[i];
-                    *reinterpret_cast<float4*>(st.V + ro + j4) = Vv[i];
+                    if (live) {
+                        *reinterpret_cast<float4*>(st.Y + ro + j4) = Yv[i];
+                        *reinterpret_cast<float4*>(st.V + ro + j4) = Vv[i];
+                    }
                 }
             }
         }
     }
-    const double scale = sp.adapt ? st.scale[r] : 1.0;
     const double eps = mala ? scale * sp.eps0 : scale;
-    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+    const bool want_trace = live && sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
     double k0 = 0.0, rowsum = 0.0;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
-        const int j4 = tid * 4 + 4 * ROWS_THREADS * i;
+        const int j4 = jbase + 128 * WPR * i;
         if (j4 >= dp) continue;
         const float yv[4] = {Yv[i].x, Yv[i].y, Yv[i].z, Yv[i].w};
         const float vv[4] = {Vv[i].x, Vv[i].y, Vv[i].z, Vv[i].w};
@@ -336,7 +348,7 @@ finish_propose_rows_kernel(TState st, TStep sp) {
             for (int e = 0; e < 4; ++e)
                 if (j4 + e < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + e] = (double)yv[e] + st.mu[j4 + e];
         }
-        if (sp.diag && j4 < ND_MAX - 1) {                            // the first coordinates are tracked functionals
+        if (sp.diag && live && j4 < ND_MAX - 1) {                    // the first coordinates are tracked functionals
             const int nd1 = min(d, ND_MAX - 1);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -369,23 +381,27 @@ finish_propose_rows_kernel(TState st, TStep sp) {
             tc::split_tf32(od[e], hi, ol[e]);                                        // remainder after the tensor core's truncation
             k0 += (double)xf * (double)xf;
         }
-        *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
-        *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+        if (live) {
+            *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
+            *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+        }
     }
     if (sp.propose || sp.diag) {
         k0 = group_sum<32>(k0);
         rowsum = group_sum<32>(rowsum);
-        __syncthreads();                                             // red[] of the finish phase has been read
-        if (lane == 0) { red[0][warp] = k0; red[1][warp] = rowsum; }
-        __syncthreads();
-        if (tid == 0) {
-            if (sp.propose) {
-                st.k0[r] = ((red[0][0] + red[0][1]) + red[0][2]) + red[0][3];
-                st.epsrow[r] = eps;
-            }
+        if (WPR > 1) {
+            __syncthreads();                                         // red[] of the finish phase has been read
+            if (lane == 0) { red[0][rib][wsub] = k0; red[1][rib][wsub] = rowsum; }
+            __syncthreads();
+            k0 = 0.0; rowsum = 0.0;
+#pragma unroll
+            for (int w = 0; w < WPR; ++w) { k0 += red[0][rib][w]; rowsum += red[1][rib][w]; }
+        }
+        if (writer) {
+            if (sp.propose) { st.k0[r] = k0; st.epsrow[r] = eps; }
             if (sp.diag) {
                 const int nd = min(d, ND_MAX - 1) + 1;
-                const double f = (((red[1][0] + red[1][1]) + red[1][2]) + red[1][3]) / (double)d;
+                const double f = rowsum / (double)d;
                 st.S1[(int64_t)(nd - 1) * K + r] += f;
                 st.S2[(int64_t)(nd - 1) * K + r] += f * f;
             }
@@ -478,6 +494,7 @@ struct DenseTF32Sampler : SamplerImpl {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = 2 * ((st.dp + tc::TN - 1) / tc::TN);   // one partial per 128-column half tile
         if (const char* e = getenv("RMN_TF32_FUSED_EPI")) row_reduce = !(e[0] == '1');
         if (const char* e = getenv("RMN_TF32_ROWS")) rows_kernel = !(e[0] == '0');
+        if (const char* e = getenv("RMN_TF32_WPR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) wpr = v; }
     }
     ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
@@ -549,13 +566,19 @@ struct DenseTF32Sampler : SamplerImpl {
     // finish / propose pass: the row-in-registers kernel whenever the row fits (dp <= 4096) and the GEMM runs with the
     // plain epilogue; RMN_TF32_ROWS=0 keeps the first version (A/B measurements)
     bool rows_kernel = true;
+    int wpr = 2;
     void launch_fp(const TStep& sp, cudaStream_t stream) {
-        const unsigned gk = (unsigned)st.K;                      // one block per chain row
         if (rows_kernel && row_reduce && st.dp <= 4096) {
-            if (st.dp <= 512) finish_propose_rows_kernel<1><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
-            else if (st.dp <= 1024) finish_propose_rows_kernel<2><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
-            else if (st.dp <= 2048) finish_propose_rows_kernel<4><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
-            else finish_propose_rows_kernel<8><<<gk, ROWS_THREADS, 0, stream>>>(st, sp);
+            const int w = (st.dp <= 1024) ? wpr : 4;                 // warps per row (RMN_TF32_WPR = 1 | 2 | 4 for dp <= 1024)
+            const unsigned g = (unsigned)((st.K * w + 3) / 4);       // 4 warps per block
+#define RMN_ROWS(W, E) finish_propose_rows_kernel<W, E><<<g, ROWS_THREADS, 0, stream>>>(st, sp)
+            if (w == 1) RMN_ROWS(1, 8);
+            else if (w == 2) { if (st.dp <= 512) RMN_ROWS(2, 2); else RMN_ROWS(2, 4); }
+            else if (st.dp <= 512) RMN_ROWS(4, 1);
+            else if (st.dp <= 1024) RMN_ROWS(4, 2);
+            else if (st.dp <= 2048) RMN_ROWS(4, 4);
+            else RMN_ROWS(4, 8);
+#undef RMN_ROWS
         } else {
             finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
         }

@@ -296,7 +296,9 @@ def _decision_gate(dm, ex, lp_start, u, th_start, budget):
         with np.errstate(divide="ignore"):
             margin = np.log(u[t]) - mh
         want = margin < 0
-        band = np.abs(margin) < budget
+        forced = u[t] >= 1.0                      # log u = 0 is never below min(0, delta): a forced rejection, not a close call
+        assert not np.any(ex["accepted"][t][forced])
+        band = (np.abs(margin) < budget) & ~forced
         assert np.array_equal(ex["accepted"][t][~band], want[~band]), "decision differs outside the budget band at step %d" % t
         n_band += int(band.sum())
         acc = ex["accepted"][t]
@@ -341,10 +343,11 @@ def test_tf32x3_logpost_and_proposal_budget(kind, N, d, K):
     assert np.max(np.abs(e1)) < off
     assert np.max(np.abs(e1 - e0)) < dif                              # what enters the accept test
     # accept decisions of all three steps against fp64 log-posteriors of the device's own states
-    n, n_band = _decision_gate(dm, out["tf32x3"], lp0["f64"], u, th0, dif)
+    h = K // 2                                                        # (chains h.. repeat chain 0: count it once)
+    sub = {k: v[:, :h] for k, v in out["tf32x3"].items()}
+    n, n_band = _decision_gate(dm, sub, lp0["f64"][:h], u[:, :h], th0[:h], dif)
     assert n_band <= max(2, int(0.01 * n))
     # determinism: chains K/2.. hold the same state and noise as chain K/2
-    h = K // 2
     for key in ("prop_theta", "prop_logpost", "logqratio"):
         a = out["tf32x3"][key]
         assert np.array_equal(a[:, h:], np.repeat(a[:, h:h + 1], K - h, axis=1)), key
