@@ -962,7 +962,7 @@ def main():
     ap.add_argument("--burn", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-seconds-config", type=float, default=3.0)
-    ap.add_argument("--ess-half-launches", type=int, default=200,
+    ap.add_argument("--ess-half-launches", type=int, default=400,
                     help="changepoint ESS phase: launches (of --iters MH steps) per half-window")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ess", action="store_true")

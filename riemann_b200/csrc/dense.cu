@@ -53,6 +53,7 @@ struct DenseState {
     long long* dacc;               // accepts since diagnostics reset
     double* S1; double* S2;        // [ND_MAX][K]
     const double* mu;              // [dp] (padded copy)
+    double mubar;                  // mean(mu): the tracked functionals are those of theta, not of the centred state
     double rho, rho_c;             // pCN (randomwalk.py:83-86)
     double* Pm;                    // [K][dp]   momentum of the trajectory (HMC with a mass matrix)
     int mass_base_prop;            // EPI_MASS_STEP: the position step starts from the proposal slot (interior steps)
@@ -420,7 +421,7 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
         rowsum = group_sum<32>(rowsum);
         const int nd = min(d, ND_MAX - 1) + 1;
         if (lane < nd) {
-            const double f = (lane == nd - 1) ? rowsum / (double)d + 0.0 : y[lane];
+            const double f = (lane == nd - 1) ? rowsum / (double)d + st.mubar : y[lane] + st.mu[lane];
             st.S1[(int64_t)lane * K + r] += f;
             st.S2[(int64_t)lane * K + r] += f * f;
         }
@@ -560,6 +561,8 @@ struct DenseGaussSampler : SamplerImpl {
         RMN_CUDA(cudaMalloc(&d_mupad, (size_t)dp * 8));
         RMN_CUDA(cudaMemcpy(d_mupad, hm.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
         st.mu = d_mupad;
+        st.mubar = 0.0;
+        for (int i = 0; i < d; ++i) st.mubar += hm[i] / (double)d;
         const rmn_proposal* pr = s->prop;
         if (pr->kind == RMN_PROP_RW) {
             rw_diag = true;

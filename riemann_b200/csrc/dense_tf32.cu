@@ -30,9 +30,6 @@
 namespace tc {
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
-int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
-                const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
-                int mala, cudaStream_t st);
 }
 
 namespace {
@@ -40,23 +37,21 @@ namespace {
 constexpr int ND_MAX = 8;
 
 struct TState {
-    int64_t K; int d, dp, nblk;
+    int64_t K; int d, dp;
     float* Y; float* V;            // current state (centred) and V = Y P           [K][dp]
-    float* Yph; float* Ypl;        // increment delta, split into TF32-exact hi + remainder [K][dp]
+    float* Yph; float* Ypl;        // increment delta: raw fp32, and its remainder delta - trunc_tf32(delta)  [K][dp]
     float* Vp;                     // P delta (GEMM output)                          [K][dp]
     const double* prec;            // fp64 P [d][d] (exact start / refresh pass)
-    float* Xi;                     // noise of the pending proposal                  [K][dp]
-    double* partq; double* partk;  // [nblk][K]
     double* lp; double* k0; double* epsrow;
     double* scale; long long* nsamp; long long* nacc; long long* dacc;
     double* S1; double* S2;
     const double* mu;              // [dp]
+    double mubar;                  // mean(mu): the tracked functionals are those of theta, not of the centred state
     const float* Ldiag;            // [dp]
 };
 
 struct TStep {
     int prop_kind, adapt, finish, propose, diag;
-    int row_reduce;      // 1: the GEMM used the plain epilogue (V' only); this pass forms quad' - quad and |p'|^2 itself
     double target, eps0, c1, c2;
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
     const double* inj_xi; const double* inj_u;
@@ -77,39 +72,33 @@ finish_propose_f32_kernel(TState st, TStep sp) {
     const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
 
     if (sp.finish) {
+        // quad' - quad = delta . (2 V + P delta) and |p'|^2 from the row itself, in a fixed lane-strided order
+        // (deterministic).  p' = p_half - eps/2 (v + P delta) with p_half = delta / eps (hamiltonian.py:27-40; the
+        // increment actually applied, theta' = fl32(y + delta)), so the noise is not stored.  The row is re-read from L2
+        // by the update loop below; the GEMM keeps its plain, store-only epilogue.
         double q = 0.0, k1 = 0.0;
-        if (sp.row_reduce) {
-            // quad' - quad = delta . (2 V + P delta) and |p'|^2 from the row itself: the same arithmetic the fused
-            // GEMM epilogue did, in a fixed lane-strided order (deterministic).  The row is re-read from L2 by the
-            // update loop below; the GEMM keeps its plain, store-only epilogue (140 us instead of 235 at config 3).
+        {
             const size_t ro0 = (size_t)r * dp;
-            const double he = 0.5 * st.epsrow[r];
+            const double eps_old = st.epsrow[r];
+            const double he = 0.5 * eps_old;
             const bool mala = sp.prop_kind == RMN_PROP_HMC;
+            const double ie = mala ? 1.0 / eps_old : 0.0;
             for (int j4 = lane * 4; j4 < dp; j4 += 128) {
-                const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro0 + j4);
-                const float4 b = *reinterpret_cast<const float4*>(st.Ypl + ro0 + j4);
+                const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro0 + j4);       // delta (raw fp32)
                 const float4 w = *reinterpret_cast<const float4*>(st.V + ro0 + j4);
                 const float4 pd = *reinterpret_cast<const float4*>(st.Vp + ro0 + j4);
-                const double dl[4] = {(double)a.x + (double)b.x, (double)a.y + (double)b.y,
-                                      (double)a.z + (double)b.z, (double)a.w + (double)b.w};
-                const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
-                const double pv[4] = {(double)pd.x, (double)pd.y, (double)pd.z, (double)pd.w};
+                const float dl[4] = {a.x, a.y, a.z, a.w};
+                const float wv[4] = {w.x, w.y, w.z, w.w};
+                const float pv[4] = {pd.x, pd.y, pd.z, pd.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) q += dl[e] * (2.0 * wv[e] + pv[e]);
-                if (mala) {
-                    const float4 x = *reinterpret_cast<const float4*>(st.Xi + ro0 + j4);
-                    const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + pv[e]);   // hamiltonian.py:27,40
+                for (int e = 0; e < 4; ++e) {
+                    const double w2 = (double)wv[e] + (double)pv[e];                        // V of the proposal
+                    q += (double)dl[e] * ((double)wv[e] + w2);
+                    if (mala) {
+                        const double p1 = (double)dl[e] * ie - he * w2;                     // hamiltonian.py:40
                         k1 += p1 * p1;
                     }
                 }
-            }
-        } else {
-            for (int b = lane; b < st.nblk; b += 32) {
-                q += st.partq[(int64_t)b * K + r];
-                if (sp.prop_kind == RMN_PROP_HMC) k1 += st.partk[(int64_t)b * K + r];
             }
         }
         q = group_sum<32>(q);
@@ -147,9 +136,8 @@ finish_propose_f32_kernel(TState st, TStep sp) {
         float4 vc = *reinterpret_cast<const float4*>(st.V + ro + j4);
         if (sp.finish && (acc || sp.tr_prop_theta)) {
             const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro + j4);
-            const float4 b = *reinterpret_cast<const float4*>(st.Ypl + ro + j4);
             // the proposal as a state: theta' = fl32(y + delta)
-            const float4 yp = make_float4(yc.x + (a.x + b.x), yc.y + (a.y + b.y), yc.z + (a.z + b.z), yc.w + (a.w + b.w));
+            const float4 yp = make_float4(yc.x + a.x, yc.y + a.y, yc.z + a.z, yc.w + a.w);
             if (sp.tr_prop_theta) {
                 const float pv[4] = {yp.x, yp.y, yp.z, yp.w};
 #pragma unroll
@@ -183,7 +171,7 @@ finish_propose_f32_kernel(TState st, TStep sp) {
             for (int q = 0; q < 4; ++q)
                 if (j4 + q >= d) xi[q] = 0.0;
         }
-        float oh[4], ol[4], xf[4];
+        float od[4], ol[4], xf[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             xf[q] = (float)xi[q];                                        // the noise as the kernels see it
@@ -195,13 +183,15 @@ finish_propose_f32_kernel(TState st, TStep sp) {
                 dlt = scale * ((double)st.Ldiag[j4 + q] * (double)xf[q]);            // randomwalk.py:26
             }
             // the increment actually applied is the fp32 one: theta' = fl32(y + delta)
-            const float dl32 = (yv[q] + (float)dlt) - yv[q];
+            od[q] = (yv[q] + (float)dlt) - yv[q];
             k0 += (double)xf[q] * (double)xf[q];
-            tc::split_tf32(dl32, oh[q], ol[q]);
+            float hi;
+            tc::split_tf32(od[q], hi, ol[q]);            // remainder after the tensor core's own truncation of delta
         }
-        *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+        // the increment is stored ONCE, raw: kind::tf32 drops the low 13 mantissa bits of its operand itself, so the
+        // GEMM's "hi" pass reads this array as is and its "lo" pass the remainder
+        *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
         *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
-        *reinterpret_cast<float4*>(st.Xi + ro + j4) = make_float4(xf[0], xf[1], xf[2], xf[3]);
     }
     if (sp.propose) {
         k0 = group_sum<32>(k0);
@@ -211,200 +201,9 @@ finish_propose_f32_kernel(TState st, TStep sp) {
         rowsum = group_sum<32>(rowsum);
         const int nd = min(d, ND_MAX - 1) + 1;
         if (lane < nd) {
-            const double f = (lane == nd - 1) ? rowsum / (double)d : (double)st.Y[ro + lane];
+            const double f = (lane == nd - 1) ? rowsum / (double)d + st.mubar : (double)st.Y[ro + lane] + st.mu[lane];
             st.S1[(int64_t)lane * K + r] += f;
             st.S2[(int64_t)lane * K + r] += f * f;
-        }
-    }
-}
-
-// The same pass with the whole row in registers: WPR warps per chain row (a block of 4 warps holds 4 / WPR rows), EPL float4
-// per lane (dp <= 128 * WPR * EPL).  Every array is read once and all loads of a row are in flight together; two streams
-// of the first version are gone --
-//   * the increment is stored once, raw (Yph = delta as fp32; kind::tf32 drops the low 13 mantissa bits of its operand
-//     itself, so the GEMM's "hi" pass reads it as is) plus its remainder Ypl = delta - trunc(delta); this pass reads
-//     only the raw array;
-//   * the noise is not stored: p' = p_half - eps/2 (v + P delta) with p_half = delta / eps (hamiltonian.py:27-40; the
-//     increment actually applied, theta' = fl32(y + delta)).
-// Per element: reads delta, V, P delta, y (16 B), writes y, V on accept (8 B) and delta, its remainder (8 B).
-// Row reductions: warp butterflies, then (WPR > 1) the warps' partials through shared memory, summed in a fixed order by
-// every warp of the row, which all take the same accept decision -- no serial section.
-constexpr int ROWS_THREADS = 128;
-template <int WPR, int EPL>
-__global__ void __launch_bounds__(ROWS_THREADS)
-finish_propose_rows_kernel(TState st, TStep sp) {
-    constexpr int RPB = (ROWS_THREADS / 32) / WPR;                   // rows per block
-    __shared__ double red[2][RPB][WPR];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rib = warp / WPR, wsub = warp % WPR;                   // row in block, warp within the row
-    const int64_t r_raw = (int64_t)blockIdx.x * RPB + rib;
-    const bool live = r_raw < st.K;
-    const int64_t r = live ? r_raw : st.K - 1;                       // dead rows shadow the last one, never store
-    const int dp = st.dp, d = st.d;
-    const int64_t K = st.K;
-    const size_t ro = (size_t)r * dp;
-    const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
-    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    const int jbase = (wsub * 32 + lane) * 4;
-    float4 Yv[EPL], Vv[EPL], Dv[EPL], Pv[EPL];
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        const int j4 = jbase + 128 * WPR * i;
-        const bool in = j4 < dp;
-        Yv[i] = in ? *reinterpret_cast<const float4*>(st.Y + ro + j4) : z4;
-        Vv[i] = in ? *reinterpret_cast<const float4*>(st.V + ro + j4) : z4;
-        Dv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Yph + ro + j4) : z4;
-        Pv[i] = (in && sp.finish) ? *reinterpret_cast<const float4*>(st.Vp + ro + j4) : z4;
-    }
-    const bool mala = sp.prop_kind == RMN_PROP_HMC;
-    const bool writer = live && wsub == 0 && lane == 0;
-    bool acc = false;
-    double scale = sp.adapt ? st.scale[r] : 1.0;
-    if (sp.finish) {
-        const double eps_old = st.epsrow[r];
-        const double he = 0.5 * eps_old, ie = mala ? 1.0 / eps_old : 0.0;
-        double q = 0.0, k1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            const float dl[4] = {Dv[i].x, Dv[i].y, Dv[i].z, Dv[i].w};
-            const float wv[4] = {Vv[i].x, Vv[i].y, Vv[i].z, Vv[i].w};
-            const float pv[4] = {Pv[i].x, Pv[i].y, Pv[i].z, Pv[i].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const double w2 = (double)wv[e] + (double)pv[e];                   // v + P delta = V of the proposal
-                q += (double)dl[e] * ((double)wv[e] + w2);                         // quad' - quad = delta . (2 v + P delta)
-                if (mala) {
-                    const double p1 = (double)dl[e] * ie - he * w2;                // p' = p_half + eps/2 g(theta'), hamiltonian.py:40
-                    k1 += p1 * p1;
-                }
-            }
-        }
-        q = group_sum<32>(q);
-        k1 = group_sum<32>(k1);
-        if (WPR > 1) {
-            if (lane == 0) { red[0][rib][wsub] = q; red[1][rib][wsub] = k1; }
-            __syncthreads();
-            q = 0.0; k1 = 0.0;
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) { q += red[0][rib][w]; k1 += red[1][rib][w]; }
-        }
-        double lp = st.lp[r];
-        const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // gaussian.py:52
-        const double lqr = mala ? 0.5 * (k1 - st.k0[r]) : 0.0;      // hamiltonian.py:89
-        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
-        acc = mh_accept(lpn, lp, lqr, u);
-        if (acc) lp = lpn;
-        AdaptState ad{scale, 0, 0};
-        if (sp.adapt) {
-            ad.nsamples = st.nsamp[r]; ad.naccepts = st.nacc[r];
-            ad.update(acc, sp.target);
-            scale = ad.scale;
-        }
-        if (WPR > 1) __syncthreads();                                // every warp of the row has read lp / k0 / the adapt state
-        if (writer) {
-            if (acc) st.lp[r] = lp;
-            st.dacc[r] += acc ? 1 : 0;
-            if (sp.adapt) { st.scale[r] = ad.scale; st.nsamp[r] = ad.nsamples; st.nacc[r] = ad.naccepts; }
-            if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
-            if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
-            if (sp.tr_lqr) sp.tr_lqr[r] = lqr;
-            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
-        }
-        if (acc || sp.tr_prop_theta) {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                const int j4 = jbase + 128 * WPR * i;
-                if (j4 >= dp) continue;
-                const float4 yp = make_float4(Yv[i].x + Dv[i].x, Yv[i].y + Dv[i].y, Yv[i].z + Dv[i].z, Yv[i].w + Dv[i].w);
-                if (sp.tr_prop_theta && live) {
-                    const float pvv[4] = {yp.x, yp.y, yp.z, yp.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (j4 + e < d) sp.tr_prop_theta[r * d + j4 + e] = (double)pvv[e] + st.mu[j4 + e];
-                }
-                if (acc) {                                       // accept: y += delta, V += P delta
-                    Yv[i] = yp;
-                    Vv[i] = make_float4(Vv[i].x + Pv[i].x, Vv[i].y + Pv[i].y, Vv[i].z + Pv[i].z, Vv[i].w + Pv[i].w);
-                    if (live) {
-                        *reinterpret_cast<float4*>(st.Y + ro + j4) = Yv[i];
-                        *reinterpret_cast<float4*>(st.V + ro + j4) = Vv[i];
-                    }
-                }
-            }
-        }
-    }
-    const double eps = mala ? scale * sp.eps0 : scale;
-    const bool want_trace = live && sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
-    double k0 = 0.0, rowsum = 0.0;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        const int j4 = jbase + 128 * WPR * i;
-        if (j4 >= dp) continue;
-        const float yv[4] = {Yv[i].x, Yv[i].y, Yv[i].z, Yv[i].w};
-        const float vv[4] = {Vv[i].x, Vv[i].y, Vv[i].z, Vv[i].w};
-        rowsum += ((double)yv[0] + (double)yv[1]) + ((double)yv[2] + (double)yv[3]);
-        if (want_trace) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (j4 + e < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + e] = (double)yv[e] + st.mu[j4 + e];
-        }
-        if (sp.diag && live && j4 < ND_MAX - 1) {                    // the first coordinates are tracked functionals
-            const int nd1 = min(d, ND_MAX - 1);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (j4 + e < nd1) {
-                    const double f = (double)yv[e];
-                    st.S1[(int64_t)(j4 + e) * K + r] += f;
-                    st.S2[(int64_t)(j4 + e) * K + r] += f * f;
-                }
-        }
-        if (!sp.propose) continue;
-        double xi[4];
-        if (sp.inj_xi) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) xi[e] = (j4 + e < d) ? sp.inj_xi[r * d + j4 + e] : 0.0;
-        } else {
-            normal4(rk.block((uint64_t)sp.step_prop, (uint32_t)(j4 >> 2)), xi);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (j4 + e >= d) xi[e] = 0.0;
-        }
-        float od[4], ol[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float xf = (float)xi[e];                                           // the noise as the kernels see it
-            double dlt;                                                              // theta' - theta
-            if (mala) dlt = eps * ((double)xf + 0.5 * eps * (-(double)vv[e]));       // hamiltonian.py:27,30
-            else dlt = scale * ((double)st.Ldiag[j4 + e] * (double)xf);              // randomwalk.py:26
-            od[e] = (yv[e] + (float)dlt) - yv[e];                                    // theta' = fl32(y + delta)
-            float hi;
-            tc::split_tf32(od[e], hi, ol[e]);                                        // remainder after the tensor core's truncation
-            k0 += (double)xf * (double)xf;
-        }
-        if (live) {
-            *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
-            *reinterpret_cast<float4*>(st.Ypl + ro + j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
-        }
-    }
-    if (sp.propose || sp.diag) {
-        k0 = group_sum<32>(k0);
-        rowsum = group_sum<32>(rowsum);
-        if (WPR > 1) {
-            __syncthreads();                                         // red[] of the finish phase has been read
-            if (lane == 0) { red[0][rib][wsub] = k0; red[1][rib][wsub] = rowsum; }
-            __syncthreads();
-            k0 = 0.0; rowsum = 0.0;
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) { k0 += red[0][rib][w]; rowsum += red[1][rib][w]; }
-        }
-        if (writer) {
-            if (sp.propose) { st.k0[r] = k0; st.epsrow[r] = eps; }
-            if (sp.diag) {
-                const int nd = min(d, ND_MAX - 1) + 1;
-                const double f = rowsum / (double)d;
-                st.S1[(int64_t)(nd - 1) * K + r] += f;
-                st.S2[(int64_t)(nd - 1) * K + r] += f * f;
-            }
         }
     }
 }
@@ -415,7 +214,7 @@ __global__ void tset_kernel(TState st, const double* __restrict__ theta) {
     const int64_t r = i / st.dp;
     const int j = (int)(i % st.dp);
     st.Y[i] = (j < st.d) ? (float)(theta[r * st.d + j] - st.mu[j]) : 0.0f;
-    st.Yph[i] = 0.0f; st.Ypl[i] = 0.0f; st.Xi[i] = 0.0f; st.Vp[i] = 0.0f; st.V[i] = 0.0f;
+    st.Yph[i] = 0.0f; st.Ypl[i] = 0.0f; st.Vp[i] = 0.0f; st.V[i] = 0.0f;
     if (j == 0) { st.k0[r] = 0.0; st.epsrow[r] = 0.0; }
 }
 // Exact (fp64) V = P y and log-posterior of the CURRENT fp32 states: start of a run and the
@@ -491,16 +290,13 @@ struct DenseTF32Sampler : SamplerImpl {
     int64_t refresh = 512;        // exact fp64 recomputation of V / log-posterior every this many steps
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
-        st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32; st.nblk = 2 * ((st.dp + tc::TN - 1) / tc::TN);   // one partial per 128-column half tile
-        if (const char* e = getenv("RMN_TF32_FUSED_EPI")) row_reduce = !(e[0] == '1');
-        if (const char* e = getenv("RMN_TF32_ROWS")) rows_kernel = !(e[0] == '0');
-        if (const char* e = getenv("RMN_TF32_WPR")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) wpr = v; }
+        st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32;
     }
     ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
     size_t workspace_bytes() const override {
         const size_t K = (size_t)st.K;
-        return 6 * rowb() + 2 * align256((size_t)st.nblk * K * 8) + 7 * align256(K * 8) +
+        return 5 * rowb() + 7 * align256(K * 8) +
                2 * align256(ND_MAX * K * 8) + 256;
     }
     int bind(void* ws) override {
@@ -508,9 +304,7 @@ struct DenseTF32Sampler : SamplerImpl {
         char* p = (char*)ws;
         st.Y = (float*)p; p += rowb();   st.V = (float*)p; p += rowb();
         st.Yph = (float*)p; p += rowb(); st.Ypl = (float*)p; p += rowb();
-        st.Vp = (float*)p; p += rowb();  st.Xi = (float*)p; p += rowb();
-        st.partq = (double*)p; p += align256((size_t)st.nblk * K * 8);
-        st.partk = (double*)p; p += align256((size_t)st.nblk * K * 8);
+        st.Vp = (float*)p; p += rowb();
         st.lp = (double*)p; p += align256(K * 8);
         st.k0 = (double*)p; p += align256(K * 8);
         st.epsrow = (double*)p; p += align256(K * 8);
@@ -542,6 +336,8 @@ struct DenseTF32Sampler : SamplerImpl {
         RMN_CUDA(cudaMemcpy(d_Ldiag, ld.data(), (size_t)dp * 4, cudaMemcpyHostToDevice));
         RMN_CUDA(cudaMemcpy(d_mupad, hm.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
         st.mu = d_mupad; st.Ldiag = d_Ldiag; st.prec = s->model->d_prec;
+        st.mubar = 0.0;
+        for (int i = 0; i < d; ++i) st.mubar += hm[i] / (double)d;
         int rc;
         if ((rc = tc::make_tmap_2d(&maps.ah, st.Yph, st.K, dp, dp, tc::TM, tc::TK3))) return rc;
         if ((rc = tc::make_tmap_2d(&maps.al, st.Ypl, st.K, dp, dp, tc::TM, tc::TK3))) return rc;
@@ -563,38 +359,19 @@ struct DenseTF32Sampler : SamplerImpl {
         return RMN_OK;
     }
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
-    // finish / propose pass: the row-in-registers kernel whenever the row fits (dp <= 4096) and the GEMM runs with the
-    // plain epilogue; RMN_TF32_ROWS=0 keeps the first version (A/B measurements)
-    bool rows_kernel = true;
-    int wpr = 2;
     void launch_fp(const TStep& sp, cudaStream_t stream) {
-        if (rows_kernel && row_reduce && st.dp <= 4096) {
-            const int w = (st.dp <= 1024) ? wpr : 4;                 // warps per row (RMN_TF32_WPR = 1 | 2 | 4 for dp <= 1024)
-            const unsigned g = (unsigned)((st.K * w + 3) / 4);       // 4 warps per block
-#define RMN_ROWS(W, E) finish_propose_rows_kernel<W, E><<<g, ROWS_THREADS, 0, stream>>>(st, sp)
-            if (w == 1) RMN_ROWS(1, 8);
-            else if (w == 2) { if (st.dp <= 512) RMN_ROWS(2, 2); else RMN_ROWS(2, 4); }
-            else if (st.dp <= 512) RMN_ROWS(4, 1);
-            else if (st.dp <= 1024) RMN_ROWS(4, 2);
-            else if (st.dp <= 2048) RMN_ROWS(4, 4);
-            else RMN_ROWS(4, 8);
-#undef RMN_ROWS
-        } else {
-            finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
-        }
+        finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
     }
     double c1() const { return st.d * log(2.0 * M_PI); }
-    // row_reduce (default): plain store-only GEMM epilogue, the MH reductions run in the finish/propose pass;
-    // RMN_TF32_FUSED_EPI=1 selects the fused epilogue (kept for A/B measurements, same results to rounding)
-    bool row_reduce = true;
-    int gemm(int mala, cudaStream_t stream) {
+    // The GEMM keeps a plain, store-only epilogue (V' only); the MH row reductions run in the finish/propose pass.  (A fused
+    // MH epilogue was built and measured in round 1: its eight epilogue warps stalled on L2 latency, 235 us against
+    // 139 + the row pass's share -- DESIGN.md section 4.)
+    int gemm(cudaStream_t stream) {
         launches++;
         ktimer.begin("tf32x3_gemm_kernel", stream);
         int rc;
-        if (row_reduce && narrow) rc = tc::launch_plain_narrow(maps_narrow, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
-        else if (row_reduce) rc = tc::launch_plain(maps, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
-        else rc = tc::launch_mala(maps, st.K, st.dp, st.dp, st.dp, st.Yph, st.Ypl, st.Xi, st.V, st.Vp, st.epsrow,
-                                  st.partq, st.partk, mala, stream);
+        if (narrow) rc = tc::launch_plain_narrow(maps_narrow, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
+        else rc = tc::launch_plain(maps, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
         ktimer.end(stream);
         return rc;
     }
@@ -632,7 +409,6 @@ struct DenseTF32Sampler : SamplerImpl {
         TStep sp{};
         sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
         sp.c1 = c1(); sp.c2 = s->model->logdetC; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
-        sp.row_reduce = row_reduce ? 1 : 0;
         const int64_t K = st.K;
         const int d = st.d;
         for (int64_t t = 0; t <= T; ++t) {
@@ -667,7 +443,7 @@ struct DenseTF32Sampler : SamplerImpl {
             }
             if (t == T) break;
             since_refresh++;
-            if (int rc = gemm(pr->kind == RMN_PROP_HMC ? 1 : 0, stream)) return rc;
+            if (int rc = gemm(stream)) return rc;
         }
         step0 += T; diag_steps += T;
         return RMN_OK;

@@ -30,19 +30,11 @@
 // SAME deterministic function theta -> G~(theta) enters the forward and the reverse proposal density,
 // and the log-posterior / gradient stay fp64, so the chain still targets the exact posterior.
 //
-// Precision mode RMN_PREC_TF32X3 (MALA and mMALA): the likelihood sweep itself on the tcgen05 tensor
-// cores, fp32-accurate (3xTF32), as three passes over materialised fp32 matrices instead of the fused
-// fp64 DMMA kernel:
-//   Z[K][N]  = Theta' X^T          GEMM (M = chains, N = data rows, contraction d)      tc_gemm.cu
-//   pointwise: p, softplus in fp64 from z; log-likelihood partial sums in fp64; R = y - p as fp32
-//              (and W = p(1-p) for the mMALA metric)                                    lg_tc_pointwise_kernel
-//   G[K][d]  = R X                 split-K GEMM (M = chains, N = d, contraction over data rows), SINGLE-pass
-//                                  TF32: like the metric, the gradient only shapes the proposal (the same
-//                                  function theta -> g~(theta) enters both proposal densities)
-// Chains are processed in blocks of at most 2,048 so Z and R stay at 8 bytes x N x 2,048.  The log-
-// likelihood carries the fp32 rounding of z (~1e-6 per row, |error| <~ 1e-3 at N = 1e6, measured in
-// tests/test_gpu_logistic.py) as a deterministic function of theta; the accept test, prior, proposal
-// arithmetic and Cholesky stay fp64.
+// Precision mode RMN_PREC_TF32X3 (MALA and mMALA): the likelihood sweep itself on the tcgen05 tensor cores, fp32-accurate
+// (3xTF32), as ONE fused kernel (logistic_fused.cu): Z = Theta' X^T into tensor memory, sigmoid / softplus straight out
+// of it, the log-likelihood summed in fp64, R = y - p written back into tensor memory as the A operand of G += R X; Z and
+// R never touch HBM.  The log-likelihood is a deterministic function of theta within the budget of
+// riemann_b200/budgets.py; the accept test, prior, proposal arithmetic and Cholesky stay fp64.
 #include <algorithm>
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -51,11 +43,7 @@
 #include <stdlib.h>
 
 namespace tc {
-int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
-int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
-                        int64_t split_stride, int* used, cudaStream_t st, int passes);
-int launch_plain_mfast(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 }
 
 namespace {
@@ -439,140 +427,6 @@ lg_build_kr_kernel(LogisticState st) {
         while (pr >= base + a + 1) { base += a + 1; ++a; }
         const int b = pr - base;
         st.KR[(int64_t)pr * st.Npad + i0 + lane] = (float)(xr[a] * xr[b]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// RMN_PREC_TF32X3: buffers and kernels of the tensor-core likelihood sweep
-// ---------------------------------------------------------------------------------------
-struct LgTC {
-    float* Xh; float* Xl;      // [N][dp32]      X split, the B operand of Z = Theta X^T
-    float* XTh; float* XTl;    // [dp32][Npad]   X^T split, the B operand of G = R X
-    float* Th; float* Tl;      // [K][dp32]      Theta' split
-    float* Z;                  // [Kb][Npad]     logits of the chain block in flight
-    float* Rh;                 // [Kb][Npad]     y - p (fp32; the gradient GEMM is single-pass TF32)
-    float* Gp32;               // [ksplit][Kb][dp32]  split-K partial gradients
-    double* llp;               // [nchunk][Kb]   log-likelihood partial sums
-    uint8_t* yb;               // [Npad]         labels as bytes (y is 0/1)
-    int dp32, Kb, nchunk, ksplit; int64_t Npad;
-};
-
-__device__ __forceinline__ void split_f64(double x, float& hi, float& lo) {
-    const float xf = (float)x;
-    hi = __uint_as_float(__float_as_uint(xf) & 0xFFFFE000u);         // TF32-exact
-    lo = (float)(x - (double)hi);
-}
-
-// X[N][d] (fp64) -> Xh/Xl[N][dp32] and the transposed XTh/XTl[dp32][Npad]; one block per 32 data rows
-__global__ void __launch_bounds__(256)
-lg_tc_prep_x_kernel(LogisticState st, LgTC tc) {
-    extern __shared__ __align__(16) double sm[];                  // [32][dp32 + 1]
-    const int d = st.d, dp32 = tc.dp32, ld = dp32 + 1;
-    const int64_t i0 = (int64_t)blockIdx.x * 32;
-    for (int q = threadIdx.x; q < 32 * dp32; q += blockDim.x) {
-        const int r = q / dp32, k = q % dp32;
-        const double v = (i0 + r < st.N && k < d) ? st.X[(i0 + r) * d + k] : 0.0;
-        sm[r * ld + k] = v;
-        if (i0 + r < st.N) {
-            float hi, lo;
-            split_f64(v, hi, lo);
-            tc.Xh[(i0 + r) * dp32 + k] = hi;
-            tc.Xl[(i0 + r) * dp32 + k] = lo;
-        }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (i0 + lane >= tc.Npad) return;
-    if (warp == 0) tc.yb[i0 + lane] = (i0 + lane < st.N && st.y[i0 + lane] != 0.0) ? 1 : 0;
-    for (int k = warp; k < dp32; k += nw) {
-        float hi, lo;
-        split_f64(sm[lane * ld + k], hi, lo);
-        tc.XTh[(int64_t)k * tc.Npad + i0 + lane] = hi;
-        tc.XTl[(int64_t)k * tc.Npad + i0 + lane] = lo;
-    }
-}
-
-// Theta' (proposal slot, or `fixed_slot`) -> Th/Tl[K][dp32]
-__global__ void lg_tc_split_theta_kernel(LogisticState st, LgTC tc, int fixed_slot) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= st.K * tc.dp32) return;
-    const int64_t c = idx / tc.dp32;
-    const int k = (int)(idx % tc.dp32);
-    double v = 0.0;
-    if (k < st.d) {
-        const int slot = (fixed_slot >= 0) ? fixed_slot : (st.cur[c] ^ 1);
-        v = st.Th[((int64_t)slot * st.K + c) * st.dp + k];
-    }
-    float hi, lo;
-    split_f64(v, hi, lo);
-    tc.Th[idx] = hi; tc.Tl[idx] = lo;
-}
-
-// pointwise stage for the chain block [c0, c0 + kb): block = (row chunk, chain).  Rows i >= N (padding up
-// to Npad) are computed like the others -- their R and W values multiply zero columns of X^T / KR in the
-// GEMMs that follow -- and only the log-likelihood sum masks them.  NaN logits (a NaN state) need no
-// handling here: the prior term of such a state is already NaN -> log-posterior -inf (model.py:50-54).
-constexpr int PW_THREADS = 256;
-template <bool HASW>
-__global__ void __launch_bounds__(PW_THREADS)
-lg_tc_pointwise_kernel(LogisticState st, LgTC tc, int64_t c0, int kb) {
-    __shared__ double tab[lgmath::TAB_DOUBLES];
-    __shared__ double red[PW_THREADS / 32];
-    for (int q = threadIdx.x; q < lgmath::TAB_DOUBLES; q += PW_THREADS) tab[q] = g_lg_tab[q];
-    __syncthreads();
-    const int cl = blockIdx.y;                                      // chain within the block
-    const int64_t rows_per = ((tc.Npad / 4 + tc.nchunk - 1) / tc.nchunk) * 4;
-    const int64_t i_begin = (int64_t)blockIdx.x * rows_per;
-    const int64_t i_end = min(tc.Npad, i_begin + rows_per);
-    const float* zrow = tc.Z + (int64_t)cl * tc.Npad;
-    float* rh = tc.Rh + (int64_t)cl * tc.Npad;
-    float* wrow = HASW ? st.W + (c0 + cl) * st.Npad : nullptr;      // st.Npad == tc.Npad
-    const int64_t N = st.N;
-    double ll = 0.0;
-    for (int64_t i4 = i_begin + 4 * (int64_t)threadIdx.x; i4 < i_end; i4 += 4 * PW_THREADS) {
-        const float4 z4 = *reinterpret_cast<const float4*>(zrow + i4);
-        const uint32_t y4 = *reinterpret_cast<const uint32_t*>(tc.yb + i4);     // four 0/1 bytes
-        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
-        float h[4], w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const double zz = (double)zv[e];
-            const bool y1 = (y4 >> (8 * e)) & 1u;
-            double p, sp, pq;
-            lgmath::sigmoid_softplus<false>(zz, tab, p, sp, pq);
-            const double t = (y1 ? zz : 0.0) - sp;                  // y z - softplus(z)
-            ll += (i4 + e < N) ? t : 0.0;
-            h[e] = (float)((y1 ? 1.0 : 0.0) - p);
-            if (HASW) w[e] = (float)pq;
-        }
-        *reinterpret_cast<float4*>(rh + i4) = make_float4(h[0], h[1], h[2], h[3]);
-        if (HASW) *reinterpret_cast<float4*>(wrow + i4) = make_float4(w[0], w[1], w[2], w[3]);
-    }
-    ll = group_sum<32>(ll);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int q = 0; q < PW_THREADS / 32; ++q) t += red[q];       // fixed order
-        tc.llp[(int64_t)blockIdx.x * tc.Kb + cl] = t;
-    }
-}
-
-// sum the partials of the chain block into slot 0 of llpart / gpart (the layout the finish kernels read)
-__global__ void __launch_bounds__(128)
-lg_tc_reduce_kernel(LogisticState st, LgTC tc, int64_t c0, int kb, int nsplit_used) {
-    const int lane = threadIdx.x & 31;
-    const int64_t cl = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (cl >= kb) return;
-    const int64_t c = c0 + cl;
-    double ll = 0.0;
-    for (int q = lane; q < tc.nchunk; q += 32) ll += tc.llp[(int64_t)q * tc.Kb + cl];
-    ll = group_sum<32>(ll);
-    if (lane == 0) st.llpart[c] = ll;
-    for (int j = lane; j < st.dp; j += 32) {
-        double g = 0.0;
-        for (int s2 = 0; s2 < nsplit_used; ++s2) g += (double)tc.Gp32[((int64_t)s2 * tc.Kb + cl) * tc.dp32 + j];
-        st.gpart[c * st.dp + j] = g;
     }
 }
 
@@ -972,17 +826,13 @@ struct LogisticSampler : SamplerImpl {
     LogisticState st{};
     bool mmala;
     bool tf32m;                 // tcgen05 metric GEMM instead of lg_metric_kernel (TF32_METRIC and TF32X3)
-    bool tcx3;                  // RMN_PREC_TF32X3: the likelihood sweep on tcgen05 (LgTC pipeline)
+    bool tcx3;                  // RMN_PREC_TF32X3: the likelihood sweep on tcgen05 (fused kernel, logistic_fused.cu)
     tc::GemmMaps maps;          // metric GEMM
-    LgTC tcb{};
-    tc::GemmMaps maps_z, maps_g;               // Z = Theta X^T (A map rebuilt per chain block) ; G = R X
-    // RMN_PREC_TF32X3, fused sweep (logistic_fused.cu; d <= 128): ONE tcgen05 kernel per sweep.  RMN_LG_FUSED=0 selects the
-    // three-kernel pipeline above (A/B measurements, and the only one for d > 128).
+    // RMN_PREC_TF32X3: the fused sweep (logistic_fused.cu) covers every d this family supports (d <= 128)
     bool fused = false;
     lgf::Geometry fg{};
     lgf::Maps fmaps{};
     float* fXh = nullptr; float* fXl = nullptr; uint32_t* fys = nullptr; double* fllp = nullptr; float* fgp = nullptr;
-    std::vector<tc::GemmMaps> maps_z_blk;
     RowComm rowc;               // row-sharded data mode: the ranks that hold the other slices of X
     ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); }
     int set_row_comm(const void* id, size_t nbytes, int rank, int world) override {
@@ -1011,35 +861,8 @@ struct LogisticSampler : SamplerImpl {
         if (tf32m || tcx3) st.Npad = (st.N + 31) / 32 * 32;
         if (tf32m) st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
         if (tcx3) {
-            const char* e = getenv("RMN_LG_FUSED");
-            fused = lgf::supported(st.d) && !(e && e[0] == '0');
+            fused = lgf::supported(st.d);
             if (fused) lgf::make_geometry(&fg, st.N, st.d, st.K);
-        }
-        if (tcx3 && !fused) {
-            tcb.Npad = st.Npad;
-            tcb.dp32 = (st.d + 31) / 32 * 32;
-            tcb.Kb = (int)(st.K < 2048 ? st.K : 2048);
-            tcb.nchunk = 64;
-            while (tcb.nchunk > 1 && st.Npad / tcb.nchunk < 4096) tcb.nchunk /= 2;
-            const int m_tiles = (tcb.Kb + tc::TM - 1) / tc::TM;
-            int ks = (2 * 148 + m_tiles - 1) / m_tiles;                  // ~2 tiles per SM
-            const int kball = (int)(st.Npad / tc::TK);
-            if (ks > kball) ks = kball;
-            if (ks < 1) ks = 1;
-            tcb.ksplit = ks;
-        }
-    }
-    size_t tc_bytes(int which) const {     // 0 X split, 1 XT split, 2 Theta split, 3 Z, 4 R, 5 Gp32, 6 llp, 7 y bytes
-        const size_t N = (size_t)st.N, Np = (size_t)tcb.Npad, dp32 = (size_t)tcb.dp32, Kb = (size_t)tcb.Kb;
-        switch (which) {
-            case 0: return 2 * align256(N * dp32 * 4);
-            case 1: return 2 * align256(dp32 * Np * 4);
-            case 2: return 2 * align256((size_t)st.K * dp32 * 4);
-            case 3: return align256(Kb * Np * 4);
-            case 4: return align256(Kb * Np * 4);
-            case 5: return align256((size_t)tcb.ksplit * Kb * dp32 * 4);
-            case 6: return align256((size_t)tcb.nchunk * Kb * 8);
-            default: return align256(Np);
         }
     }
     size_t f_bytes(int which) const {      // fused sweep: 0 Xh (= Xl), 1 label masks, 2 llp, 3 gp
@@ -1064,7 +887,6 @@ struct LogisticSampler : SamplerImpl {
                    2 * align256(ND_MAX * K * 8) + 256;
         if (mmala) n += 3 * align256(K * st.d * st.d * 8) + 2 * align256(K * 8) + 2 * rowb();
         if (tf32m) n += kr_bytes() + w_bytes() + gp_bytes();
-        if (tcx3 && !fused) for (int w = 0; w < 8; ++w) n += tc_bytes(w);
         if (fused) n += 2 * f_bytes(0) + f_bytes(1) + f_bytes(2) + f_bytes(3);
         return n;
     }
@@ -1103,41 +925,11 @@ struct LogisticSampler : SamplerImpl {
             fllp = (double*)p; p += f_bytes(2);
             fgp = (float*)p; p += f_bytes(3);
         }
-        if (tcx3 && !fused) {
-            const size_t N = (size_t)st.N, Np = (size_t)tcb.Npad, dp32 = (size_t)tcb.dp32, Kb = (size_t)tcb.Kb;
-            tcb.Xh = (float*)p; p += align256(N * dp32 * 4);  tcb.Xl = (float*)p; p += align256(N * dp32 * 4);
-            tcb.XTh = (float*)p; p += align256(dp32 * Np * 4); tcb.XTl = (float*)p; p += align256(dp32 * Np * 4);
-            tcb.Th = (float*)p; p += align256((size_t)st.K * dp32 * 4); tcb.Tl = (float*)p; p += align256((size_t)st.K * dp32 * 4);
-            tcb.Z = (float*)p; p += tc_bytes(3);
-            tcb.Rh = (float*)p; p += align256(Kb * Np * 4);
-            tcb.Gp32 = (float*)p; p += tc_bytes(5);
-            tcb.llp = (double*)p; p += tc_bytes(6);
-            tcb.yb = (uint8_t*)p; p += tc_bytes(7);
-        }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
         if (int rc = lg_tables_ready()) return rc;
         if (fused) {
             if (int rc = lgf::prep_x(st.N, st.d, fg, st.X, st.y, fXh, fXl, fys, 0)) return rc;
             if (int rc = lgf::make_maps(&fmaps, fg, st.N, fXh, fXl)) return rc;
-        }
-        if (tcx3 && !fused) {
-            const size_t psm = (size_t)32 * (tcb.dp32 + 1) * 8;
-            lg_tc_prep_x_kernel<<<(unsigned)(tcb.Npad / 32), 256, psm>>>(st, tcb);
-            RMN_KERNEL_CHECK();
-            const uint64_t Np = (uint64_t)tcb.Npad, dp32 = (uint64_t)tcb.dp32;
-            const int nblk = (int)((st.K + tcb.Kb - 1) / tcb.Kb);
-            maps_z_blk.resize(nblk);
-            for (int b = 0; b < nblk; ++b) {
-                const uint64_t rows = (uint64_t)std::min<int64_t>(tcb.Kb, st.K - (int64_t)b * tcb.Kb);
-                tc::GemmMaps& m = maps_z_blk[b];
-                if (int rc = tc::make_tmap_2d(&m.ah, tcb.Th + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM, tc::TK3)) return rc;
-                if (int rc = tc::make_tmap_2d(&m.al, tcb.Tl + (size_t)b * tcb.Kb * dp32, rows, dp32, dp32, tc::TM, tc::TK3)) return rc;
-                if (int rc = tc::make_tmap_2d(&m.bh, tcb.Xh, (uint64_t)st.N, dp32, dp32, tc::TN, tc::TK3)) return rc;
-                if (int rc = tc::make_tmap_2d(&m.bl, tcb.Xl, (uint64_t)st.N, dp32, dp32, tc::TN, tc::TK3)) return rc;
-            }
-            if (int rc = tc::make_tmap_2d(&maps_g.ah, tcb.Rh, (uint64_t)tcb.Kb, Np, Np, tc::TM)) return rc;
-            if (int rc = tc::make_tmap_2d(&maps_g.bh, tcb.XTh, dp32, Np, Np, tc::TN)) return rc;
-            maps_g.al = maps_g.ah; maps_g.bl = maps_g.bh;
         }
         if (tf32m) {
             const size_t ksm = (size_t)32 * (st.d + 1) * 8;
@@ -1174,33 +966,9 @@ struct LogisticSampler : SamplerImpl {
         launches += 2;
         return RMN_OK;
     }
-    int eval_tc(int fixed_slot, cudaStream_t stream) {
-        if (fused) return eval_fused(fixed_slot, stream);
-        const int64_t nth = st.K * tcb.dp32;
-        lg_tc_split_theta_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, stream>>>(st, tcb, fixed_slot);
-        RMN_KERNEL_CHECK(); launches++;
-        const int nblk = (int)maps_z_blk.size();
-        for (int b = 0; b < nblk; ++b) {
-            const int64_t c0 = (int64_t)b * tcb.Kb;
-            const int kb = (int)std::min<int64_t>(tcb.Kb, st.K - c0);
-            ktimer.begin("tf32x3_gemm_kernel+lg_tc_pointwise_kernel", stream);
-            if (int rc = tc::launch_plain_mfast(maps_z_blk[b], kb, (int)tcb.Npad, tcb.dp32, tcb.Z, (int)tcb.Npad, stream)) return rc;
-            if (st.W) lg_tc_pointwise_kernel<true><<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
-            else lg_tc_pointwise_kernel<false><<<dim3((unsigned)tcb.nchunk, (unsigned)kb), PW_THREADS, 0, stream>>>(st, tcb, c0, kb);
-            RMN_KERNEL_CHECK();
-            int used = 1;
-            if (int rc = tc::launch_plain_splitk(maps_g, kb, tcb.dp32, (int)tcb.Npad, tcb.Gp32, tcb.dp32, tcb.ksplit,
-                                                 (int64_t)tcb.Kb * tcb.dp32, &used, stream, 1)) return rc;
-            ktimer.end(stream);
-            lg_tc_reduce_kernel<<<(unsigned)(((int64_t)kb * 32 + 127) / 128), 128, 0, stream>>>(st, tcb, c0, kb, used);
-            RMN_KERNEL_CHECK();
-            launches += 4;
-        }
-        return RMN_OK;
-    }
     int eval(int fixed_slot, cudaStream_t stream) {
         if (tcx3) {
-            if (int rc = eval_tc(fixed_slot, stream)) return rc;
+            if (int rc = eval_fused(fixed_slot, stream)) return rc;
             if (tf32m) {
                 if (int rc = tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
                 launches++;

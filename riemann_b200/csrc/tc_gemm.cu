@@ -1,12 +1,9 @@
-// riemann_b200 -- tcgen05 3xTF32 GEMM kernel (see tc_gemm.cuh) with two epilogues:
-//   EPI_PLAIN : C[m][n] (fp32) stored                        -- validation entry point
-//   EPI_MALA  : dense-Gaussian MH epilogue in DELTA form.  A = delta = theta' - theta (split), so the
-//               accumulator holds P delta; stored, and rowsum(delta.(2 v + P delta)) = quad' - quad
-//               and rowsum(p'^2) are reduced per (row, 256-column block) in fp64, no atomics.
-//               (Forming P y' directly would cancel 30 - 29.97 in fp32 for the 0.1 I + 0.9 11^T
-//               target; the increment has no common mode, so the MH ratio keeps ~1e-5 accuracy.)
-// This is the fp32-accurate tensor-core counterpart of gemm_abt_kernel (fp64 DMMA) for
-// SURVEY.md row D4 / BASELINE config 3.
+// riemann_b200 -- tcgen05 3xTF32 GEMM kernel (see tc_gemm.cuh): C[m][n] (fp32) = A B^T, store-only epilogue.
+// The dense-Gaussian sampler multiplies the INCREMENT delta = theta' - theta by P with it (forming P y' directly would
+// cancel 30 - 29.97 in fp32 for the 0.1 I + 0.9 11^T target; the increment has no common mode), the logistic sampler
+// its Fisher-metric product.  This is the fp32-accurate tensor-core counterpart of gemm_abt_kernel (fp64 DMMA) for
+// SURVEY.md row D4 / BASELINE config 3.  (Round 1 also carried an epilogue that fused the MH row reductions; its
+// eight epilogue warps stalled on L2 latency and it measured slower than a separate row pass -- removed.)
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -46,18 +43,6 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t co
     return RMN_OK;
 }
 
-struct MalaEpi {
-    const float* yph; const float* ypl;   // increment delta (split), [K][dp]
-    const float* xi;                      // noise, [K][dp]
-    const float* vcur;                    // V = P y of the current state, [K][dp]
-    float* vp;                            // P delta (output), [K][dp]
-    const double* epsrow;                 // [K]
-    double* partq; double* partk;         // [nblk][K]
-    int mala;                             // 0: RW (no p' partials)
-};
-
-enum { EPI_PLAIN = 0, EPI_MALA = 1 };
-
 // Persistent kernel: gridDim.x CTAs (one per SM) walk the tile list  tile = blockIdx.x + i * gridDim.x,
 // tile -> (m_tile, n_tile) with n fastest, so concurrently running CTAs share the same rows of A in L2.
 // Three independent pipelines (Blackwell canonical form):
@@ -68,17 +53,17 @@ enum { EPI_PLAIN = 0, EPI_MALA = 1 };
 // PASSES = 1: plain TF32 product of the "hi" maps only (the Fisher-metric GEMM of the logistic sampler,
 //             where the product only shapes a proposal), 4 stages of 48 KB so the TMA latency stays hidden
 //             behind one third of the tensor work per stage.
-template <int EPI, int PASSES>
+template <int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
-                   int ldc, MalaEpi ep, int ksplit, int kb_per, int64_t split_stride, int m_fastest, int tn) {
+                   int ldc, int ksplit, int kb_per, int64_t split_stride, int m_fastest, int tn) {
     // tn: columns of C per tile, TN = 256 or 128 (the B tensor maps must have been built with box_rows = tn).  The
     // narrow tile is for outputs with fewer than #SM tiles of 128 x 256 (2,048 chains x 1,024 columns = 64 of them):
     // it doubles the tile count instead of leaving half of the SMs idle.  Shared-memory regions keep their 256-row size.
     // m_fastest: tile order.  0 = n fastest (CTAs running together share rows of A in L2), 1 = m fastest
     // (they share rows of B: the logits GEMM, whose A -- the chains' Theta -- is tiny and whose B -- the data
     // matrix -- should cross HBM once).
-    // ksplit > 1 (EPI_PLAIN only): the k-blocks are divided into ksplit contiguous ranges; a tile is
+    // ksplit > 1: the k-blocks are divided into ksplit contiguous ranges; a tile is
     // (m_tile, n_tile, split) and split s stores its partial product at C + s * split_stride (summed by
     // the caller) -- this is how a product with few output tiles but a long contraction (the logistic
     // gradient R X: K x d output, N data rows deep) still fills all SMs.
@@ -188,24 +173,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             const int64_t mn = tile % mn_tiles;
             const int64_t m0 = (m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
             const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn;
-            float* Cs = (EPI == EPI_PLAIN) ? C + (tile / mn_tiles) * split_stride : C;
-            if (EPI == EPI_MALA) {
-                // The epilogue's inputs do not depend on the accumulator: pull this warp's 32 rows x 128 columns of
-                // delta (hi, lo), V and xi towards L2 now, so the chunk loop below waits on L2, not on HBM
-                // (the MALA epilogue, not the mainloop, bounds this kernel: 272 us vs 140 us with the plain one).
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int64_t mr = m0 + q * 32 + it * 8 + (lane >> 2);
-                    const int nn = n0 + half * (tn / 2) + (lane & 3) * 32;
-                    if (mr < M && nn < N) {
-                        const size_t off = (size_t)mr * ldc + nn;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.yph + off));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.ypl + off));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.vcur + off));
-                        if (ep.mala) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.xi + off));
-                    }
-                }
-            }
+            float* Cs = C + (tile / mn_tiles) * split_stride;
             mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
             tc_fence_after();
             // Epilogue data mapping: tcgen05.ld hands each thread one TMEM lane (= output row) x 16 columns;
@@ -214,34 +182,13 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             // Lane L then works on rows it*8 + L/4 (it = 0..3), columns 4 (L%4) .. +3 of the chunk.
             float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
             const int rsub = lane >> 2, cg = (lane & 3) * 4;
-            double pq4[4] = {0.0, 0.0, 0.0, 0.0}, pk4[4] = {0.0, 0.0, 0.0, 0.0}, hev[4] = {0.0, 0.0, 0.0, 0.0};
-            if (EPI == EPI_MALA) {
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int64_t mr = m0 + q * 32 + it * 8 + rsub;
-                    if (mr < M) hev[it] = 0.5 * ep.epsrow[mr];
-                }
-            }
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (tn / 2));
             for (int c0 = 0; c0 < tn / 2; c0 += 16) {
                 const int n = n0 + half * (tn / 2) + c0;
                 if (n >= N) continue;                                   // warp-uniform
-                // (MALA) issue the chunk's 16 independent global loads FIRST: their L2 latency (well over
-                // 1,000 cycles under the TMA traffic) then overlaps the TMEM read and the staging below
-                float4 A4[4], B4[4], W4[4], X4[4];
                 bool okr[4];
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int64_t mr = m0 + q * 32 + it * 8 + rsub;
-                    okr[it] = (mr < M) && (n + cg < N);
-                    if (EPI == EPI_MALA) {
-                        const size_t off = (size_t)(okr[it] ? mr : m0) * ldc + (okr[it] ? n + cg : n0);
-                        A4[it] = *reinterpret_cast<const float4*>(ep.yph + off);
-                        B4[it] = *reinterpret_cast<const float4*>(ep.ypl + off);
-                        W4[it] = *reinterpret_cast<const float4*>(ep.vcur + off);
-                        if (ep.mala) X4[it] = *reinterpret_cast<const float4*>(ep.xi + off);
-                    }
-                }
+                for (int it = 0; it < 4; ++it) okr[it] = (m0 + q * 32 + it * 8 + rsub < M) && (n + cg < N);
                 float v[16];
                 tmem_ld_32x16(trow + (uint32_t)c0, v);
                 float4* w4 = reinterpret_cast<float4*>(stg + lane * 20);
@@ -254,30 +201,7 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                     const int64_t mr = m0 + q * 32 + rr;
                     if (!okr[it]) continue;
                     const float4 val = *reinterpret_cast<const float4*>(stg + rr * 20 + cg);
-                    if (EPI == EPI_PLAIN) {
-                        *reinterpret_cast<float4*>(Cs + mr * ldc + n + cg) = val;
-                    } else {
-                        const size_t off = (size_t)mr * ldc + n + cg;
-                        *reinterpret_cast<float4*>(ep.vp + off) = val;
-                        const float4 a4 = A4[it], b4 = B4[it], w = W4[it];
-                        const double dl[4] = {(double)a4.x + (double)b4.x, (double)a4.y + (double)b4.y,
-                                              (double)a4.z + (double)b4.z, (double)a4.w + (double)b4.w};
-                        const double wv[4] = {(double)w.x, (double)w.y, (double)w.z, (double)w.w};
-                        const double pv[4] = {(double)val.x, (double)val.y, (double)val.z, (double)val.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) pq4[it] += dl[e] * (2.0 * wv[e] + pv[e]);          // quad' - quad
-                        if (ep.mala) {
-                            // p' = xi + eps/2 g + eps/2 g',  g = -V, g' = -(V + P delta)   (hamiltonian.py:27,40)
-                            const float4 x = X4[it];
-                            const double xv[4] = {(double)x.x, (double)x.y, (double)x.z, (double)x.w};
-                            const double he = hev[it];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const double p1 = (xv[e] - he * wv[e]) - he * (wv[e] + pv[e]);
-                                pk4[it] += p1 * p1;
-                            }
-                        }
-                    }
+                    *reinterpret_cast<float4*>(Cs + mr * ldc + n + cg) = val;
                 }
                 __syncwarp();
             }
@@ -285,20 +209,6 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[a]);
-            if (EPI == EPI_MALA) {
-                const size_t blk = (size_t)(n0 / TN) * 2 + half;                   // 128-column block index
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    double sq = pq4[it], sk = pk4[it];
-                    sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-                    sk += __shfl_xor_sync(0xffffffffu, sk, 1); sk += __shfl_xor_sync(0xffffffffu, sk, 2);
-                    const int64_t mr = m0 + q * 32 + it * 8 + rsub;
-                    if ((lane & 3) == 0 && mr < M) {
-                        ep.partq[blk * M + mr] = sq;
-                        if (ep.mala) ep.partk[blk * M + mr] = sk;
-                    }
-                }
-            }
         }
     }
     tc_fence_before();
@@ -309,13 +219,13 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     }
 }
 
-static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, const MalaEpi* ep,
+static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc,
                          cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0,
                          int tn = TN) {
-    if (tn != TN && (tn != 128 || ep)) { rmn_set_error("tf32x3 gemm: tile width must be 256, or 128 with the plain epilogue"); return RMN_ERR_PARAM; }
+    if (tn != TN && tn != 128) { rmn_set_error("tf32x3 gemm: tile width must be 256 or 128"); return RMN_ERR_PARAM; }
     const int tk = (passes == 1) ? TK : TK3;                           // k-block of the kernel variant
     if (Kdim % 32 != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
-    if (ksplit < 1 || ksplit > Kdim / tk || (ep && ksplit != 1)) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
+    if (ksplit < 1 || ksplit > Kdim / tk) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
     // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
     const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
     ksplit = (Kdim / tk + kbp - 1) / kbp;
@@ -331,27 +241,25 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
     cudaGetDevice(&dev_id);
     bool& attr = attr_done[dev_id & 63];
     if (!attr) {
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_PLAIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<EPI_MALA, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    if (ep) tf32x3_gemm_kernel<EPI_MALA, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, nullptr, ldc, *ep, 1, kbp, 0, 0, TN);
-    else if (passes == 1) tf32x3_gemm_kernel<EPI_PLAIN, 1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest, tn);
-    else tf32x3_gemm_kernel<EPI_PLAIN, 3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, MalaEpi{}, ksplit, kbp, split_stride, m_fastest, tn);
+    if (passes == 1) tf32x3_gemm_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn);
+    else tf32x3_gemm_kernel<3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
 
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
-    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st);
+    return launch_common(maps, M, N, Kdim, C, ldc, st);
 }
 // 3-pass product with 128-column tiles (B maps built with box_rows = 128)
 int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
-    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 3, 1, 0, 0, 128);
+    return launch_common(maps, M, N, Kdim, C, ldc, st, 3, 1, 0, 0, 128);
 }
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
-    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 1);
+    return launch_common(maps, M, N, Kdim, C, ldc, st, 1);
 }
 // 3-pass product with the contraction split into `ksplit` ranges; returns the number of splits actually
 // used through *used (<= ksplit); partial s is at C + s * split_stride
@@ -360,19 +268,8 @@ int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float*
     const int tk = (passes == 1) ? TK : TK3;
     const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
     if (used) *used = (Kdim / tk + kbp - 1) / kbp;
-    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, passes, ksplit, split_stride);
+    return launch_common(maps, M, N, Kdim, C, ldc, st, passes, ksplit, split_stride);
 }
-// 3-pass product, m-fastest tile order (A small and L2-resident, B streamed once)
-int launch_plain_mfast(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
-    return launch_common(maps, M, N, Kdim, C, ldc, nullptr, st, 3, 1, 0, 1);
-}
-int launch_mala(const GemmMaps& maps, int64_t M, int N, int Kdim, int ld, const float* yph, const float* ypl,
-                const float* xi, const float* vcur, float* vp, const double* epsrow, double* partq, double* partk,
-                int mala, cudaStream_t st) {
-    MalaEpi ep{yph, ypl, xi, vcur, vp, epsrow, partq, partk, mala};
-    return launch_common(maps, M, N, Kdim, nullptr, ld, &ep, st);
-}
-
 }  // namespace tc
 
 // Validation entry of the single-pass mode: C[M][N] (fp32, ld = N) ~= A B^T with TF32 operands

@@ -202,3 +202,25 @@ def test_philox_hmc5_d100_matches_target():
     assert stats.kstest((th[:, 0] - th[:, 1]) / np.sqrt(0.2), "norm").pvalue > 1e-3
     lp = np.asarray(s._chain_logpost[-1])
     assert relerr(lp, m.log_posterior_batch(th).cpu().numpy()) < 1e-10
+
+
+@pytest.mark.parametrize("precision", ["f64", "tf32x3"])
+def test_diagnostics_are_those_of_theta_when_mu_is_not_zero(precision):
+    """The dense paths keep the centred state y = theta - mu; the tracked functionals (first 7 coordinates and
+    mean(theta)) must still be those of theta (riemann/models/gaussian.py:49-52 is a density of theta)."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models.gaussian import MultiGaussianDist
+    from riemann_b200.proposals.hamiltonian import MALA
+    d, K = 24, 4096
+    rng = np.random.default_rng(2)
+    mu = 3.0 + rng.standard_normal(d)
+    C = 0.5 * np.eye(d) + 0.5 * np.ones((d, d)) / d
+    m = MultiGaussianDist(mu, C)
+    th0 = mu[None] + rng.multivariate_normal(np.zeros(d), C, size=K)
+    s = Sampler(m, MALA(0.3, m.grad_log_likelihood), th0, seed=3, precision=precision)
+    s.run(50, trace=False)
+    s.reset_diagnostics()
+    s.run(100, trace=False)
+    dg = s.diagnostics(allreduce=False)
+    assert np.all(np.abs(dg["mean"][:7] - mu[:7]) < 0.05)
+    assert abs(dg["mean"][7] - mu.mean()) < 0.03

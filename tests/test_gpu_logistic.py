@@ -308,9 +308,9 @@ def _decision_gate(dm, ex, lp_start, u, th_start, budget):
 
 
 @pytest.mark.parametrize("kind,N,d,K", [("mala", 20000, 20, 300), ("mmala", 9000, 12, 70), ("mala", 4099, 100, 130),
-                                        ("mala", 30011, 64, 257), ("mala", 6000, 150, 64)])
+                                        ("mala", 30011, 64, 257), ("mmala", 12000, 64, 129)])
 def test_tf32x3_logpost_and_proposal_budget(kind, N, d, K):
-    """The tensor-core sweep (fused tcgen05 kernel for d <= 128, three-kernel pipeline above) against fp64 evaluations
+    """The tensor-core sweep (fused tcgen05 kernel, logistic_fused.cu) against fp64 evaluations
     of the same states, with the budgets of riemann_b200/budgets.py: the offset of one state's log-posterior, the
     DIFFERENCE proposal - state that enters the accept test, the accept decisions themselves, the proposals against
     the fp64 sampler on the same noise, and determinism across tile positions.  Ragged shapes (N % 64, K % 128)."""
