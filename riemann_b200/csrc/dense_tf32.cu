@@ -30,6 +30,7 @@
 namespace tc {
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+int prepare_kernels();
 }
 
 namespace {
@@ -54,6 +55,7 @@ struct TStep {
     int prop_kind, adapt, finish, propose, diag;
     double target, eps0, c1, c2;
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
+    const int64_t* d_step_base;   // CUDA-graph replays: step_fin / step_prop are relative to *d_step_base (else NULL)
     const double* inj_xi; const double* inj_u;
     int64_t trace_slot;
     double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc; double* tr_lqr; double* tr_prop_theta;
@@ -70,6 +72,8 @@ finish_propose_f32_kernel(TState st, TStep sp) {
     double lp = st.lp[r];
     bool acc = false;
     const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
+    const int64_t sbase = sp.d_step_base ? *sp.d_step_base : 0;
+    const int64_t step_fin = sp.step_fin + sbase, step_prop = sp.step_prop + sbase;
 
     if (sp.finish) {
         // quad' - quad = delta . (2 V + P delta) and |p'|^2 from the row itself, in a fixed lane-strided order
@@ -105,7 +109,7 @@ finish_propose_f32_kernel(TState st, TStep sp) {
         k1 = group_sum<32>(k1);
         const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // q = quad' - quad (gaussian.py:52)
         const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r]) : 0.0; // hamiltonian.py:89
-        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)step_fin, RMN_BLOCK_ACCEPT).x);
         acc = mh_accept(lpn, lp, lqr, u);
         if (acc) lp = lpn;
         if (lane == 0) {
@@ -166,7 +170,7 @@ finish_propose_f32_kernel(TState st, TStep sp) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) xi[q] = (j4 + q < d) ? sp.inj_xi[r * d + j4 + q] : 0.0;
         } else {
-            normal4(rk.block((uint64_t)sp.step_prop, (uint32_t)(j4 >> 2)), xi);
+            normal4(rk.block((uint64_t)step_prop, (uint32_t)(j4 >> 2)), xi);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (j4 + q >= d) xi[q] = 0.0;
@@ -207,6 +211,8 @@ finish_propose_f32_kernel(TState st, TStep sp) {
         }
     }
 }
+
+__global__ void tstep_base_kernel(int64_t* p, int64_t v) { *p = v; }
 
 __global__ void tset_kernel(TState st, const double* __restrict__ theta) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -287,12 +293,25 @@ struct DenseTF32Sampler : SamplerImpl {
     tc::GemmMaps maps_narrow;     // the same operands with 128-row boxes of P: 128 x 128 output tiles
     bool narrow = false;          // fewer than #SM tiles of 128 x 256: use the narrow tile (RMN_TF32_NARROW=0|1 overrides)
     float* d_Ph = nullptr; float* d_Pl = nullptr; float* d_Ldiag = nullptr; double* d_mupad = nullptr;
+    // The MH loop is two short kernels per step (GEMM + finish/propose pass); for a plain Philox run without trace the
+    // T steps of a call are captured ONCE into a CUDA graph and replayed (the step counter the Philox streams need comes
+    // from device memory), which removes the per-launch gaps: 2,048 chains per GPU -- BASELINE's 16,384 over 8 -- is
+    // 57 us per step with ~16 us of them between kernels.  RMN_TF32_GRAPH=0 turns it off.
+    bool use_graph = true;
+    cudaGraphExec_t gexec = nullptr;
+    int64_t g_T = -1;
+    int64_t g_nodes = 0;
+    int64_t* d_step_base = nullptr;
     int64_t refresh = 512;        // exact fp64 recomputation of V / log-posterior every this many steps
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32;
+        if (const char* e = getenv("RMN_TF32_GRAPH")) use_graph = !(e[0] == '0');
     }
-    ~DenseTF32Sampler() override { cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); }
+    ~DenseTF32Sampler() override {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base);
+    }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
     size_t workspace_bytes() const override {
         const size_t K = (size_t)st.K;
@@ -343,6 +362,7 @@ struct DenseTF32Sampler : SamplerImpl {
         if ((rc = tc::make_tmap_2d(&maps.al, st.Ypl, st.K, dp, dp, tc::TM, tc::TK3))) return rc;
         if ((rc = tc::make_tmap_2d(&maps.bh, d_Ph, dp, dp, dp, tc::TN, tc::TK3))) return rc;
         if ((rc = tc::make_tmap_2d(&maps.bl, d_Pl, dp, dp, dp, tc::TN, tc::TK3))) return rc;
+        if ((rc = tc::prepare_kernels())) return rc;
         maps_narrow.ah = maps.ah; maps_narrow.al = maps.al;
         if ((rc = tc::make_tmap_2d(&maps_narrow.bh, d_Ph, dp, dp, dp, 128, tc::TK3))) return rc;
         if ((rc = tc::make_tmap_2d(&maps_narrow.bl, d_Pl, dp, dp, dp, 128, tc::TK3))) return rc;
@@ -401,6 +421,41 @@ struct DenseTF32Sampler : SamplerImpl {
         return RMN_OK;
     }
     int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
+        const bool traced = tr && (tr->d_theta || tr->d_logpost || tr->d_prop_logpost || tr->d_accepted ||
+                                   tr->d_logqratio || tr->d_prop_theta);
+        const bool graphable = use_graph && !inj && !traced && !ktimer.on && T >= 2 &&
+                               !(refresh > 0 && since_refresh + T >= refresh);
+        if (!graphable) return run_steps(T, inj, tr, stream, nullptr);
+        if (!d_step_base) RMN_CUDA(cudaMalloc(&d_step_base, 8));
+        if (!gexec || g_T != T) {
+            if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+            const int64_t l0 = launches, s0 = step0, d0 = diag_steps, r0 = since_refresh;
+            cudaGraph_t graph = nullptr;
+            RMN_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = run_steps(T, nullptr, nullptr, stream, d_step_base);
+            const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            g_nodes = launches - l0;
+            launches = l0; step0 = s0; diag_steps = d0; since_refresh = r0;       // nothing ran yet
+            if (rc != RMN_OK || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                use_graph = false;                                               // fall back to plain launches for good
+                return run_steps(T, inj, tr, stream, nullptr);
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { gexec = nullptr; cudaGetLastError(); use_graph = false; return run_steps(T, inj, tr, stream, nullptr); }
+            g_T = T;
+        }
+        tstep_base_kernel<<<1, 1, 0, stream>>>(d_step_base, step0);
+        RMN_KERNEL_CHECK();
+        RMN_CUDA(cudaGraphLaunch(gexec, stream));
+        launches += g_nodes + 1;
+        step0 += T; diag_steps += T; since_refresh += T;
+        return RMN_OK;
+    }
+    // the loop itself; d_base != NULL: step indices relative to *d_base (graph capture)
+    int run_steps(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream, const int64_t* d_base) {
         const rmn_proposal* pr = s->prop;
         if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
         rmn_trace_t t0{};
@@ -409,11 +464,13 @@ struct DenseTF32Sampler : SamplerImpl {
         TStep sp{};
         sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
         sp.c1 = c1(); sp.c2 = s->model->logdetC; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
+        sp.d_step_base = d_base;
+        const int64_t sb = d_base ? 0 : step0;
         const int64_t K = st.K;
         const int d = st.d;
         for (int64_t t = 0; t <= T; ++t) {
             sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
-            sp.step_fin = step0 + t - 1; sp.step_prop = step0 + t;
+            sp.step_fin = sb + t - 1; sp.step_prop = sb + t;
             sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;
             sp.inj_xi = (inj && t < T) ? inj->d_xi + t * K * d : nullptr;
             sp.trace_slot = -1;

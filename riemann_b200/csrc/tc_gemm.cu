@@ -219,6 +219,20 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     }
 }
 
+// function attributes (dynamic shared memory limit) are per device; set them outside any stream capture
+int prepare_kernels() {
+    static bool attr_done[64] = {false};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool& attr = attr_done[dev_id & 63];
+    if (!attr) {
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    return RMN_OK;
+}
+
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc,
                          cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0,
                          int tn = TN) {
@@ -236,15 +250,7 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
     int& sms = sms_of[dev & 63];
     if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));          // persistent: one CTA per SM
-    static bool attr_done[64] = {false};          // function attributes are per device
-    int dev_id = 0;
-    cudaGetDevice(&dev_id);
-    bool& attr = attr_done[dev_id & 63];
-    if (!attr) {
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr = true;
-    }
+    if (int rc = prepare_kernels()) return rc;
     if (passes == 1) tf32x3_gemm_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn);
     else tf32x3_gemm_kernel<3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn);
     RMN_KERNEL_CHECK();

@@ -12,28 +12,59 @@ import re
 import subprocess
 import sys
 
-REGIONS = [   # (file suffix, first line, last line, label) -- riemann_b200/csrc at the profiled commit
-    ("common.cuh", 40, 75, "Philox4x32-10 rounds"),
-    ("common.cuh", 76, 100, "Box-Muller normals"),
-    ("changepoint.cuh", 40, 95, "binary search of the x table / uniforms"),
-    ("changepoint.cu", 63, 82, "group ballot / butterfly sums"),
-    ("changepoint.cu", 83, 119, "shift_prev / shift_next (neighbour element)"),
-    ("changepoint.cu", 120, 141, "shift_by (insert / delete gather)"),
-    ("changepoint.cu", 142, 165, "elem_at / count_below"),
-    ("changepoint.cu", 166, 233, "log-posterior of the proposal"),
-    ("changepoint.cu", 240, 294, "prologue (state load, Philox prefetch)"),
-    ("changepoint.cu", 295, 349, "per-step randoms and move selection"),
-    ("changepoint.cu", 350, 366, "fixed-dimension proposal by selection"),
-    ("changepoint.cu", 367, 410, "birth / death arithmetic and rebuild"),
-    ("changepoint.cu", 411, 437, "padding + run-boundary search"),
-    ("changepoint.cu", 438, 460, "Philox prefetch, accept, state update"),
-    ("changepoint.cu", 461, 478, "thinned diagnostics"),
-    ("changepoint.cu", 479, 540, "trace stores + epilogue"),
-]
+# Source regions are found by ANCHOR text in the current sources (the capture must be of the same commit): a region
+# runs from its anchor line to the line before the next anchor of the same file.
+ANCHORS = {
+    "common.cuh": [("__device__ __forceinline__ uint4 philox4x32_10", "Philox4x32-10 rounds"),
+                   ("// uniform on (0,1): (x + 0.5)", "Box-Muller normals / uniforms"),
+                   ("// Metropolis-Hastings accept rule", "accept rule helpers")],
+    "changepoint.cuh": [("template <int LOGP2>", "binary search of the x table"),
+                        ("// uniform on (0,1) from 32 random bits", "fast uniforms")],
+    "changepoint.cu": [("__device__ __forceinline__ unsigned gballot", "group ballot / butterfly sums"),
+                       ("// value of element e-1 for every row", "shift_prev / shift_next (neighbour element)"),
+                       ("// value of element e + off, off in", "shift_by (insert / delete gather)"),
+                       ("// a[idx] for a per-chain element index", "elem_at / count_below"),
+                       ("__device__ __forceinline__ void cp_terms", "likelihood / prior sums (cp_terms)"),
+                       ("// log of four per-chain arguments with one call", "batched log (log4)"),
+                       ("__device__ __forceinline__ double cp_assemble", "log-posterior assembly (cp_assemble)"),
+                       ("// full evaluation (pointwise entry", "full evaluation helper"),
+                       ("changepoint_kernel(const __grid_constant__ CPParams P", "prologue (state load, caches, Philox prefetch)"),
+                       ("    for (int64_t t = 0; t < T; ++t) {", "per-step randoms and move selection"),
+                       ("        // What the warp as a whole needs this step", "warp votes"),
+                       ("        // normals of the block moves", "normals (Box-Muller calls, second Philox block)"),
+                       ("        // ---- build the proposal by selection", "fixed-dimension proposal by selection"),
+                       ("        if (any3) {", "birth / death arithmetic and rebuild"),
+                       ("        // run boundaries only move when a location moves", "run-boundary search"),
+                       ("        if (!INJ) rA = rk.block(step + 1", "Philox prefetch"),
+                       ("        // ---- log-posterior of the proposal from the pieces", "evaluation calls"),
+                       ("        // sampler.py:83-84 with Python's min(0, nan) == 0", "accept, state update"),
+                       ("        if ((step % RMN_CP_DIAG_EVERY) == 0) {", "thinned diagnostics"),
+                       ("        if (live && tracing) {", "trace stores + epilogue"),
+                       ("// evaluate n states given in the canonical layout", "(other kernels)")],
+}
+
+
+def find_regions(root):
+    import os
+    out = []
+    for fname, anchors in ANCHORS.items():
+        lines = open(os.path.join(root, "riemann_b200", "csrc", fname)).read().splitlines()
+        pos = []
+        for text, label in anchors:
+            hits = [i + 1 for i, l in enumerate(lines) if text in l]
+            if not hits:
+                raise SystemExit("anchor not found in %s: %r" % (fname, text))
+            pos.append((hits[0], label))
+        for k, (lo, label) in enumerate(pos):
+            hi = pos[k + 1][0] - 1 if k + 1 < len(pos) else len(lines)
+            out.append((fname, lo, hi, label))
+    return out
 
 
 def main():
+    import os
     rep, warps, iters = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    REGIONS = find_regions(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     base = float(warps * iters)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
                          capture_output=True, text=True).stdout

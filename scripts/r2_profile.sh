@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2 ncu evidence (one GPU).  Each capture only after the same command has exited 0 without ncu.
+#   launch list: --metrics gpu__time_duration.sum (per-launch times are cold-cache and serialised: shares, not absolutes)
+#   full capture of the dominant kernel: --set full --import-source on
+OUT=gpurun_out; TAG=${1:-r2p}; mkdir -p $OUT
+prof() {  # name, kernel regex, skip, bench args...
+  local n=$1 k=$2 skip=$3; shift 3
+  timeout 600 python bench.py "$@" --no-cpu --no-ess > $OUT/${TAG}_${n}_plain.json 2> $OUT/${TAG}_${n}_plain.err || { echo "$n: plain run failed"; tail -3 $OUT/${TAG}_${n}_plain.err; return; }
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_${n}_launches.csv python bench.py "$@" --no-cpu --no-ess > /dev/null 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $OUT/${TAG}_${n}_full python bench.py "$@" --no-cpu --no-ess > $OUT/${TAG}_${n}_ncu.log 2>&1
+  echo "$n: $(ls -la $OUT/${TAG}_${n}_full.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
+}
+prof cp changepoint_kernel 3 --workload changepoint --steps 2 --warmup 3 --burn 20000
+prof lgf lg_fused_sweep 3 --workload logistic_mala --precision tf32x3 --iters 1 --steps 2 --warmup 3
+prof lgf_mmala lg_fused_sweep 3 --workload logistic_mmala --precision tf32x3 --strong --iters 1 --steps 2 --warmup 3
+prof g1000_fp finish_propose_f32 10 --workload gauss1000_mala --precision tf32x3 --iters 5 --steps 2 --warmup 3
+prof g1000_gemm tf32x3_gemm_kernel 10 --workload gauss1000_mala --precision tf32x3 --iters 5 --steps 2 --warmup 3
