@@ -302,6 +302,7 @@ struct DenseTF32Sampler : SamplerImpl {
     int64_t g_T = -1;
     int64_t g_nodes = 0;
     int64_t* d_step_base = nullptr;
+    cudaStream_t cap_stream = nullptr;
     int64_t refresh = 512;        // exact fp64 recomputation of V / log-posterior every this many steps
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
@@ -310,6 +311,7 @@ struct DenseTF32Sampler : SamplerImpl {
     }
     ~DenseTF32Sampler() override {
         if (gexec) cudaGraphExecDestroy(gexec);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
         cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base);
     }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
@@ -428,18 +430,27 @@ struct DenseTF32Sampler : SamplerImpl {
         if (!graphable) return run_steps(T, inj, tr, stream, nullptr);
         if (!d_step_base) RMN_CUDA(cudaMalloc(&d_step_base, 8));
         if (!gexec || g_T != T) {
+            // capture on a stream of our own (the caller's may be the legacy default stream, which cannot capture);
+            // nothing executes during capture, and the graph is then launched into the CALLER's stream
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+            if (!cap_stream && cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError(); use_graph = false;
+                return run_steps(T, inj, tr, stream, nullptr);
+            }
+            if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError(); use_graph = false;
+                return run_steps(T, inj, tr, stream, nullptr);
+            }
             const int64_t l0 = launches, s0 = step0, d0 = diag_steps, r0 = since_refresh;
             cudaGraph_t graph = nullptr;
-            RMN_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            const int rc = run_steps(T, nullptr, nullptr, stream, d_step_base);
-            const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            const int rc = run_steps(T, nullptr, nullptr, cap_stream, d_step_base);
+            const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
             g_nodes = launches - l0;
             launches = l0; step0 = s0; diag_steps = d0; since_refresh = r0;       // nothing ran yet
             if (rc != RMN_OK || ce != cudaSuccess || !graph) {
                 if (graph) cudaGraphDestroy(graph);
                 cudaGetLastError();
-                use_graph = false;                                               // fall back to plain launches for good
+                use_graph = false;                                               // plain launches from now on
                 return run_steps(T, inj, tr, stream, nullptr);
             }
             const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);

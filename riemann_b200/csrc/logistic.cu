@@ -102,6 +102,9 @@ struct LogisticState {
     double* lp; double* k0; double* epsrow; int* cur;
     double* scale; long long* nsamp; long long* nacc; long long* dacc;
     double* S1; double* S2;
+    // random walk / pCN (randomwalk.py:12-26, 78-100): L = chol(C) and, for pCN, its inverse, d x d row-major
+    const double* PL; const double* PLinv;
+    double rho, rho_c;
     // mMALA
     double* Gm;      // [K][d][d]   metric of the pending proposal (likelihood part)
     double* Lc;      // [2][K][d][d] Cholesky factors (current / proposal slot follows cur)
@@ -472,8 +475,10 @@ lg_leapfrog_mid_kernel(LogisticState st) {
 // ---------------------------------------------------------------------------------------
 // finish / propose, one warp per chain.
 // ---------------------------------------------------------------------------------------
+enum { LG_HMC = 0, LG_RW = 1, LG_PCN = 2 };   // the non-mMALA proposals of lg_finish_propose_kernel<false>
 struct LgStep {
     int mmala, adapt, finish, propose, diag;
+    int pkind;
     double target, eps0;
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
     const double* inj_xi; const double* inj_u;
@@ -562,9 +567,22 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             const double gp = (j < d) ? gsum - th * pvinv : 0.0;
             grp[j] = gp;
             tt += th * th;
-            if (!MMALA) {
+            if (!MMALA && sp.pkind == LG_HMC) {
                 const double p1 = xi[j] + 0.5 * eps * gp;                // final half step (hamiltonian.py:40); Xi holds p
                 k1 += p1 * p1;
+            }
+        }
+        if (!MMALA && sp.pkind == LG_PCN) {
+            // u_rev = (rho_c L)^-1 (theta - rho theta')  (randomwalk.py:95,98); |u_fwd|^2 = |xi|^2 = k0
+            double* v = st.Xi + r * dp;                                  // the noise is no longer needed: staging
+            __syncwarp();
+            for (int j = lane; j < d; j += 32) v[j] = thc[j] - st.rho * thp[j];
+            __syncwarp();
+            for (int j = lane; j < d; j += 32) {
+                double sacc = 0.0;
+                for (int i = 0; i <= j; ++i) sacc += st.PLinv[(size_t)j * d + i] * v[i];
+                sacc /= st.rho_c;
+                k1 += sacc * sacc;
             }
         }
         tt = group_sum<32>(tt);
@@ -573,7 +591,9 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
         const double lpn = combine_logpost(lprior, ll);
         double lqr;
         if (!MMALA) {
-            lqr = 0.5 * (k1 - st.k0[r]);                                  // hamiltonian.py:89
+            if (sp.pkind == LG_HMC) lqr = 0.5 * (k1 - st.k0[r]);          // hamiltonian.py:89
+            else if (sp.pkind == LG_PCN) lqr = -0.5 * (st.k0[r] - k1);    // randomwalk.py:99-100
+            else lqr = 0.0;                                               // randomwalk.py:26
         } else {
             // geometry of the proposal: L' = chol(G'), logdet', nat' = G'^-1 grad'
             for (int q = lane; q < d * d; q += 32) {
@@ -634,7 +654,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
     double* thn = st.Th + ((int64_t)(c ^ 1) * K + r) * dp;
     double* xo = st.Xi + r * dp;
     const double scale = sp.adapt ? st.scale[r] : 1.0;
-    const double eps = scale * sp.eps0;
+    const double eps = scale * sp.eps0;                                  // RW: eps0 = 1, so eps is the scale (randomwalk.py:26)
     const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
     double k0 = 0.0, rowsum = 0.0;
 
@@ -663,7 +683,9 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             if (want_trace && j < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j] = tv;
             if (!sp.propose) continue;
             k0 += xi[q] * xi[q];
-            if (!MMALA) {
+            if (!MMALA && sp.pkind != LG_HMC) {
+                xo[j] = xi[q];     // staged for the L xi product below
+            } else if (!MMALA) {
                 const double ph = xi[q] + 0.5 * eps * gr[j];             // hamiltonian.py:27
                 thn[j] = tv + eps * ph;                                  // :30
                 xo[j] = ph;        // the momentum rides in Xi through the trajectory (Nsteps >= 1)
@@ -671,6 +693,17 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
                 xo[j] = xi[q];
                 v1[j] = xi[q];
             }
+        }
+    }
+    if (!MMALA && sp.propose && sp.pkind != LG_HMC) {
+        // theta' = theta + scale L xi (randomwalk.py:25-26) or rho theta + rho_c L xi (:93), L lower triangular
+        __syncwarp();
+        const double a0 = (sp.pkind == LG_PCN) ? st.rho : 1.0, a1 = (sp.pkind == LG_PCN) ? st.rho_c : eps;
+        for (int j = lane; j < dp; j += 32) {
+            double sacc = 0.0;
+            if (j < d)
+                for (int i = 0; i <= j; ++i) sacc += st.PL[(size_t)j * d + i] * xo[i];
+            thn[j] = (j < d) ? a0 * th[j] + a1 * sacc : 0.0;
         }
     }
     if (MMALA && sp.propose) {
@@ -830,11 +863,13 @@ struct LogisticSampler : SamplerImpl {
     tc::GemmMaps maps;          // metric GEMM
     // RMN_PREC_TF32X3: the fused sweep (logistic_fused.cu) covers every d this family supports (d <= 128)
     bool fused = false;
+    int pkind = LG_HMC;
+    double* d_PL = nullptr; double* d_PLinv = nullptr;
     lgf::Geometry fg{};
     lgf::Maps fmaps{};
     float* fXh = nullptr; float* fXl = nullptr; uint32_t* fys = nullptr; double* fllp = nullptr; float* fgp = nullptr;
     RowComm rowc;               // row-sharded data mode: the ranks that hold the other slices of X
-    ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); }
+    ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); cudaFree(d_PL); cudaFree(d_PLinv); }
     int set_row_comm(const void* id, size_t nbytes, int rank, int world) override {
         if (tcx3 || tf32m) {
             rmn_set_error("row-sharded data mode runs in f64 precision");
@@ -856,6 +891,7 @@ struct LogisticSampler : SamplerImpl {
     explicit LogisticSampler(rmn_sampler* s_) : s(s_) {
         fill_geometry(st, s->model, s->K);
         mmala = (s->prop->kind == RMN_PROP_MMALA);
+        pkind = (s->prop->kind == RMN_PROP_RW) ? LG_RW : ((s->prop->kind == RMN_PROP_PCN) ? LG_PCN : LG_HMC);
         tcx3 = s->precision == RMN_PREC_TF32X3;
         tf32m = mmala && (s->precision == RMN_PREC_TF32_METRIC || tcx3);
         if (tf32m || tcx3) st.Npad = (st.N + 31) / 32 * 32;
@@ -926,6 +962,19 @@ struct LogisticSampler : SamplerImpl {
             fgp = (float*)p; p += f_bytes(3);
         }
         RMN_CUDA(cudaMemset(ws, 0, workspace_bytes()));
+        if (pkind != LG_HMC) {
+            const rmn_proposal* pr = s->prop;
+            const size_t nb = (size_t)st.d * st.d * 8;
+            RMN_CUDA(cudaMalloc(&d_PL, nb));
+            RMN_CUDA(cudaMemcpy(d_PL, pr->h_L.data(), nb, cudaMemcpyHostToDevice));
+            st.PL = d_PL;
+            if (pkind == LG_PCN) {
+                RMN_CUDA(cudaMalloc(&d_PLinv, nb));
+                RMN_CUDA(cudaMemcpy(d_PLinv, pr->h_Linv.data(), nb, cudaMemcpyHostToDevice));
+                st.PLinv = d_PLinv;
+                st.rho = pr->rho; st.rho_c = sqrt(1.0 - pr->rho * pr->rho);     // randomwalk.py:85
+            }
+        }
         if (int rc = lg_tables_ready()) return rc;
         if (fused) {
             if (int rc = lgf::prep_x(st.N, st.d, fg, st.X, st.y, fXh, fXl, fys, 0)) return rc;
@@ -1015,7 +1064,8 @@ struct LogisticSampler : SamplerImpl {
         if (tr) t0 = *tr;
         if (t0.thin <= 0) t0.thin = 1;
         LgStep sp{};
-        sp.mmala = mmala; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
+        sp.mmala = mmala; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = (pkind == LG_HMC) ? pr->eps : 1.0;
+        sp.pkind = pkind;
         sp.seed = s->seed; sp.chain_offset = s->chain_offset;
         const int64_t K = st.K;
         const int d = st.d;
@@ -1039,7 +1089,7 @@ struct LogisticSampler : SamplerImpl {
             RMN_KERNEL_CHECK(); launches++;
             if (t == T) break;
             if (int rc = eval(-1, stream)) return rc;
-            if (!mmala) {
+            if (!mmala && pkind == LG_HMC) {
                 // Nsteps - 1 interior leapfrog steps: each one a full likelihood sweep at the new trajectory point
                 for (int l = 1; l < pr->nsteps; ++l) {
                     const int64_t n = st.K * st.dp;
@@ -1096,8 +1146,10 @@ SamplerImpl* make_logistic_sampler(rmn_sampler* s) {
         return new LogisticSampler(s);
     }
     if (p->kind == RMN_PROP_HMC && !p->has_mass) return new LogisticSampler(s);
-    rmn_set_error("logistic model: device kernels exist for VanillaHMC / AdaptScaleHMC without a mass matrix "
-                  "(Nsteps = 1 is MALA) and SimplifiedMMALA");
+    if (p->kind == RMN_PROP_RW && !p->acov) return new LogisticSampler(s);            // MetropolisRandomWalk / AdaptScaleRandomWalk
+    if (p->kind == RMN_PROP_PCN && !p->adapt) return new LogisticSampler(s);          // pCN (AdaptScalepCN: small-d family only)
+    rmn_set_error("logistic model: device kernels exist for MetropolisRandomWalk / AdaptScaleRandomWalk, pCN, VanillaHMC / "
+                  "AdaptScaleHMC without a mass matrix (Nsteps = 1 is MALA) and SimplifiedMMALA");
     return nullptr;
 }
 

@@ -102,6 +102,53 @@ def test_ragged_chains_vs_oracle(kind):
     assert 0.2 < acc < 0.99
 
 
+@pytest.mark.parametrize("kind,prec", [("rw", "f64"), ("adaptrw", "f64"), ("pcn", "f64"), ("rw", "tf32x3"), ("pcn", "tf32x3")])
+def test_random_walk_and_pcn_on_the_logistic_model(kind, prec):
+    """MetropolisRandomWalk / AdaptScaleRandomWalk (riemann/proposals/randomwalk.py:12-37) and pCN (:78-100) with a
+    DENSE proposal covariance on the logistic model: the oracle's classes driven by the reference's accept rule on the
+    same injected stream.  f64: chains to 1e-8; tf32x3: same decisions except inside the stated difference budget."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler, budgets
+    from riemann_b200.proposals.randomwalk import AdaptScaleRandomWalk, MetropolisRandomWalk, pCN
+    N, d, K, T = 2500, 12, 37, 30
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=91)
+    dm, om = _models(X, y, pv)
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((d, d))
+    C = 2e-3 * (A @ A.T / d + 0.5 * np.eye(d))
+    th0 = ts[None, :] + 0.05 * rng.standard_normal((K, d))
+    xi, u = rng.standard_normal((T, K, d)), rng.uniform(size=(T, K))
+    if kind == "pcn":
+        C = 200.0 * C                    # pCN is reversible for N(0, C): a wide C keeps rho theta near the mode
+        mk_d, mk_o = (lambda: pCN(C, 0.999)), (lambda: port.pCN(C, 0.999))
+    elif kind == "rw":
+        mk_d, mk_o = (lambda: MetropolisRandomWalk(C)), (lambda: port.MetropolisRandomWalk(C))
+    else:
+        mk_d, mk_o = (lambda: AdaptScaleRandomWalk(C)), (lambda: port.AdaptScaleRandomWalk(C))
+    s = Sampler(dm, mk_d(), th0, precision=prec)
+    ex = s.run_injected(xi=xi, u=u)
+    n_diff = 0
+    for c in (0, 5, 31, 36):
+        o = port.Sampler(om, mk_o(), th0[c], draws=port.VectorTapeDraws(xi[:, c], u[:, c]))
+        o.run(T)
+        oth, olp = np.array(o._chain_thetas), np.array(o._chain_logpost)
+        if prec == "f64":
+            assert relerr(s._chain_thetas[:, c], oth) < 1e-8
+            assert relerr(s._chain_logpost[:, c], olp) < 1e-8
+        else:
+            same = np.all(np.abs(s._chain_thetas[:, c] - oth) < 1e-9, axis=1)
+            n_diff += int(not same.all())
+            k = int(np.argmin(same)) if not same.all() else T + 1       # first step the two chains part (a close call)
+            assert np.max(np.abs(s._chain_logpost[:k, c] - olp[:k])) < budgets.logistic_tf32x3_offset(N)
+    assert n_diff <= 1
+    acc = ex["accepted"].mean()
+    assert 0.05 < acc < 0.98, acc
+    if kind == "adaptrw":
+        o = port.Sampler(om, mk_o(), th0[0], draws=port.VectorTapeDraws(xi[:, 0], u[:, 0]))
+        o.run(T)
+        assert abs(np.atleast_1d(s.proposal.scale)[0] / o.proposal.scale - 1) < 1e-9
+
+
 @pytest.mark.parametrize("kind", ["mala", "mmala"])
 def test_philox_run_agrees_with_oracle_posterior(kind):
     """Distributional gate vs a long CPU chain of the oracle (same model, own numpy stream)."""
