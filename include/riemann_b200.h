@@ -204,13 +204,15 @@ size_t rmn_sampler_workspace_bytes(const rmn_model_t* m, const rmn_proposal_t* p
 int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, int64_t K,
                        int64_t chain_offset, uint64_t seed, void* d_workspace,
                        size_t workspace_bytes);
-/* Precision modes.  RMN_PREC_F64 (default): fp64 state and arithmetic like the reference's numpy
- * (DMMA / DFMA).  RMN_PREC_TF32X3: dense Gaussian model only -- fp32 chain state, the K x d by
- * d x d product on tcgen05 tensor cores with a 3xTF32 split (fp32-accurate), everything that
- * enters the accept test reduced in fp64; |log-posterior error| <~ 5e-3 at d = 1000. */
-/* RMN_PREC_TF32X3 on the logistic model (MALA or mMALA): logits Z = Theta X^T and gradient R X as 3xTF32
- * tcgen05 GEMMs over materialised fp32 matrices, sigmoid/softplus and the log-likelihood sum in fp64 from the
- * fp32 logits (|log-likelihood error| <~ 1e-3 at N = 1e6), mMALA metric as in RMN_PREC_TF32_METRIC. */
+/* Precision modes.  RMN_PREC_F64 (default): fp64 state and arithmetic like the reference's numpy (DMMA / DFMA).
+ * RMN_PREC_TF32X3: the path's dense contraction on the tcgen05 tensor cores, fp32-accurate (three TF32 MMAs per product),
+ * everything that enters the accept test reduced in fp64.  ONE stated budget per mode (riemann_b200/budgets.py, asserted by
+ * the tests together with an accept-decision gate) on the log-posterior DIFFERENCE proposal - state of sampler.py:83:
+ *   dense Gaussian model (fp32 chain state, the K x d by d x d product of the INCREMENT):  5e-7 d   (5e-4 at d = 1000)
+ *   logistic model, MALA / HMC / RW / pCN / mMALA (ONE fused kernel per likelihood sweep, logistic_fused.cu: logits into
+ *   tensor memory, sigmoid / softplus out of it, R = y - p back into tensor memory as the operand of the gradient
+ *   product):  2e-3 sqrt(N / 1e6)   (2e-3 at N = 1e6).  A state's log-posterior also carries a constant offset (<= 5e-8 N,
+ *   the fp32 softplus) that is the same for every state and cancels in every Metropolis-Hastings ratio. */
 #define RMN_PREC_F64 0
 #define RMN_PREC_TF32X3 1
 /* RMN_PREC_TF32_METRIC: logistic model + simplified mMALA only -- the Fisher metric of the proposal,

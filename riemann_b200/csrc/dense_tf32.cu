@@ -56,6 +56,7 @@ struct TStep {
     double target, eps0, c1, c2;
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
     const int64_t* d_step_base;   // CUDA-graph replays: step_fin / step_prop are relative to *d_step_base (else NULL)
+    int64_t row0, nrows;          // the chain rows [row0, row0 + nrows) this launch works on (nrows = 0: all K)
     const double* inj_xi; const double* inj_u;
     int64_t trace_slot;
     double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc; double* tr_lqr; double* tr_prop_theta;
@@ -65,8 +66,9 @@ struct TStep {
 __global__ void __launch_bounds__(256)
 finish_propose_f32_kernel(TState st, TStep sp) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (r >= st.K) return;
+    const int64_t rl = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (rl >= (sp.nrows ? sp.nrows : st.K)) return;
+    const int64_t r = sp.row0 + rl;
     const int dp = st.dp, d = st.d;
     const int64_t K = st.K;
     double lp = st.lp[r];
@@ -297,6 +299,17 @@ struct DenseTF32Sampler : SamplerImpl {
     // T steps of a call are captured ONCE into a CUDA graph and replayed (the step counter the Philox streams need comes
     // from device memory), which removes the per-launch gaps: 2,048 chains per GPU -- BASELINE's 16,384 over 8 -- is
     // 57 us per step with ~16 us of them between kernels.  RMN_TF32_GRAPH=0 turns it off.
+    // Inside the graph the chains are processed as TWO half-batches on two captured branches.  The GEMM is tensor-bound
+    // (93 registers x 384 threads, one persistent CTA per SM) and the finish/propose pass memory-bound (64 registers):
+    // a block of the pass fits next to a GEMM CTA on every SM, so the GEMM of one half overlaps the pass of the other
+    // instead of the two alternating on an otherwise idle resource.  Results do not change (rows are independent and
+    // the Philox streams are keyed by the global chain id).
+    tc::GemmMaps maps_h[2];
+    bool narrow_h[2] = {false, false};
+    int64_t row0_h[2] = {0, 0}, nrows_h[2] = {0, 0};
+    cudaStream_t cap_stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool two_halves = true;       // RMN_TF32_HALVES=0: one branch over all rows
     bool use_graph = true;
     cudaGraphExec_t gexec = nullptr;
     int64_t g_T = -1;
@@ -308,10 +321,14 @@ struct DenseTF32Sampler : SamplerImpl {
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32;
         if (const char* e = getenv("RMN_TF32_GRAPH")) use_graph = !(e[0] == '0');
+        if (const char* e = getenv("RMN_TF32_HALVES")) two_halves = !(e[0] == '0');
     }
     ~DenseTF32Sampler() override {
         if (gexec) cudaGraphExecDestroy(gexec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (cap_stream2) cudaStreamDestroy(cap_stream2);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base);
     }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
@@ -376,13 +393,38 @@ struct DenseTF32Sampler : SamplerImpl {
             narrow = wide < sms;
             if (const char* e = getenv("RMN_TF32_NARROW")) narrow = (e[0] == '1');
         }
+        {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int64_t k0 = std::min<int64_t>(st.K, ((st.K / 2 + tc::TM - 1) / tc::TM) * tc::TM);
+            row0_h[0] = 0; nrows_h[0] = k0; row0_h[1] = k0; nrows_h[1] = st.K - k0;
+            for (int h = 0; h < 2; ++h) {
+                if (nrows_h[h] <= 0) continue;
+                const size_t off = (size_t)row0_h[h] * dp;
+                narrow_h[h] = ((nrows_h[h] + tc::TM - 1) / tc::TM) * ((dp + tc::TN - 1) / tc::TN) < sms;
+                if (const char* e = getenv("RMN_TF32_NARROW")) narrow_h[h] = (e[0] == '1');
+                const uint32_t brows = narrow_h[h] ? 128 : tc::TN;
+                if ((rc = tc::make_tmap_2d(&maps_h[h].ah, st.Yph + off, nrows_h[h], dp, dp, tc::TM, tc::TK3))) return rc;
+                if ((rc = tc::make_tmap_2d(&maps_h[h].al, st.Ypl + off, nrows_h[h], dp, dp, tc::TM, tc::TK3))) return rc;
+                if ((rc = tc::make_tmap_2d(&maps_h[h].bh, d_Ph, dp, dp, dp, brows, tc::TK3))) return rc;
+                if ((rc = tc::make_tmap_2d(&maps_h[h].bl, d_Pl, dp, dp, dp, brows, tc::TK3))) return rc;
+            }
+        }
         if ((rc = rmn_fill_f64(st.scale, st.K, 1.0, 0))) return rc;
         RMN_CUDA(cudaDeviceSynchronize());
         return RMN_OK;
     }
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
     void launch_fp(const TStep& sp, cudaStream_t stream) {
-        finish_propose_f32_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
+        const int64_t n = sp.nrows ? sp.nrows : st.K;
+        finish_propose_f32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(st, sp);
+    }
+    int gemm_half(int h, cudaStream_t stream) {
+        launches++;
+        float* C = st.Vp + (size_t)row0_h[h] * st.dp;
+        if (narrow_h[h]) return tc::launch_plain_narrow(maps_h[h], nrows_h[h], st.dp, st.dp, C, st.dp, stream);
+        return tc::launch_plain(maps_h[h], nrows_h[h], st.dp, st.dp, C, st.dp, stream);
     }
     double c1() const { return st.d * log(2.0 * M_PI); }
     // The GEMM keeps a plain, store-only epilogue (V' only); the MH row reductions run in the finish/propose pass.  (A fused
@@ -427,7 +469,7 @@ struct DenseTF32Sampler : SamplerImpl {
                                    tr->d_logqratio || tr->d_prop_theta);
         const bool graphable = use_graph && !inj && !traced && !ktimer.on && T >= 2 &&
                                !(refresh > 0 && since_refresh + T >= refresh);
-        if (!graphable) return run_steps(T, inj, tr, stream, nullptr);
+        if (!graphable) return run_steps(T, inj, tr, stream, nullptr, -1);
         if (!d_step_base) RMN_CUDA(cudaMalloc(&d_step_base, 8));
         if (!gexec || g_T != T) {
             // capture on a stream of our own (the caller's may be the legacy default stream, which cannot capture);
@@ -435,15 +477,36 @@ struct DenseTF32Sampler : SamplerImpl {
             if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
             if (!cap_stream && cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
                 cudaGetLastError(); use_graph = false;
-                return run_steps(T, inj, tr, stream, nullptr);
+                return run_steps(T, inj, tr, stream, nullptr, -1);
+            }
+            if (!cap_stream2 && two_halves) {
+                if (cudaStreamCreateWithFlags(&cap_stream2, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+                    cudaGetLastError(); cap_stream2 = nullptr;
+                }
             }
             if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
                 cudaGetLastError(); use_graph = false;
-                return run_steps(T, inj, tr, stream, nullptr);
+                return run_steps(T, inj, tr, stream, nullptr, -1);
             }
             const int64_t l0 = launches, s0 = step0, d0 = diag_steps, r0 = since_refresh;
             cudaGraph_t graph = nullptr;
-            const int rc = run_steps(T, nullptr, nullptr, cap_stream, d_step_base);
+            int rc = RMN_OK;
+            if (nrows_h[1] > 0 && cap_stream2 && ev_fork && ev_join) {
+                // fork: branch 0 on cap_stream, branch 1 on cap_stream2, joined before the capture ends
+                cudaEventRecord(ev_fork, cap_stream);
+                cudaStreamWaitEvent(cap_stream2, ev_fork, 0);
+                rc = run_steps(T, nullptr, nullptr, cap_stream, d_step_base, 0);
+                const int64_t l1 = launches, s1 = step0, d1 = diag_steps, r1 = since_refresh;
+                step0 = s0; diag_steps = d0; since_refresh = r0;
+                if (rc == RMN_OK) rc = run_steps(T, nullptr, nullptr, cap_stream2, d_step_base, 1);
+                (void)l1; step0 = s1; diag_steps = d1; since_refresh = r1;
+                cudaEventRecord(ev_join, cap_stream2);
+                cudaStreamWaitEvent(cap_stream, ev_join, 0);
+            } else {
+                rc = run_steps(T, nullptr, nullptr, cap_stream, d_step_base, -1);
+            }
             const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
             g_nodes = launches - l0;
             launches = l0; step0 = s0; diag_steps = d0; since_refresh = r0;       // nothing ran yet
@@ -451,11 +514,11 @@ struct DenseTF32Sampler : SamplerImpl {
                 if (graph) cudaGraphDestroy(graph);
                 cudaGetLastError();
                 use_graph = false;                                               // plain launches from now on
-                return run_steps(T, inj, tr, stream, nullptr);
+                return run_steps(T, inj, tr, stream, nullptr, -1);
             }
             const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
             cudaGraphDestroy(graph);
-            if (ie != cudaSuccess) { gexec = nullptr; cudaGetLastError(); use_graph = false; return run_steps(T, inj, tr, stream, nullptr); }
+            if (ie != cudaSuccess) { gexec = nullptr; cudaGetLastError(); use_graph = false; return run_steps(T, inj, tr, stream, nullptr, -1); }
             g_T = T;
         }
         tstep_base_kernel<<<1, 1, 0, stream>>>(d_step_base, step0);
@@ -466,7 +529,9 @@ struct DenseTF32Sampler : SamplerImpl {
         return RMN_OK;
     }
     // the loop itself; d_base != NULL: step indices relative to *d_base (graph capture)
-    int run_steps(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream, const int64_t* d_base) {
+    // half = 0 | 1: only that half-batch of rows (graph branches); -1: all rows
+    int run_steps(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream, const int64_t* d_base,
+                  int half) {
         const rmn_proposal* pr = s->prop;
         if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
         rmn_trace_t t0{};
@@ -476,6 +541,7 @@ struct DenseTF32Sampler : SamplerImpl {
         sp.prop_kind = pr->kind; sp.adapt = pr->adapt; sp.target = pr->target; sp.eps0 = pr->eps;
         sp.c1 = c1(); sp.c2 = s->model->logdetC; sp.seed = s->seed; sp.chain_offset = s->chain_offset;
         sp.d_step_base = d_base;
+        if (half >= 0) { sp.row0 = row0_h[half]; sp.nrows = nrows_h[half]; }
         const int64_t sb = d_base ? 0 : step0;
         const int64_t K = st.K;
         const int d = st.d;
@@ -511,7 +577,7 @@ struct DenseTF32Sampler : SamplerImpl {
             }
             if (t == T) break;
             since_refresh++;
-            if (int rc = gemm(stream)) return rc;
+            if (int rc = (half >= 0) ? gemm_half(half, stream) : gemm(stream)) return rc;
         }
         step0 += T; diag_steps += T;
         return RMN_OK;
