@@ -302,8 +302,9 @@ struct DenseTF32Sampler : SamplerImpl {
     // Inside the graph the chains are processed as TWO half-batches on two captured branches.  The GEMM is tensor-bound
     // (93 registers x 384 threads, one persistent CTA per SM) and the finish/propose pass memory-bound (64 registers):
     // a block of the pass fits next to a GEMM CTA on every SM, so the GEMM of one half overlaps the pass of the other
-    // instead of the two alternating on an otherwise idle resource.  Results do not change (rows are independent and
-    // the Philox streams are keyed by the global chain id).
+    // instead of the two alternating on an otherwise idle resource: +5 % at 16,384 chains (237 us per step against 250,
+    // gpurun r2j); below 8,192 chains it is neutral or worse and one branch is used.  Results do not change (rows are
+    // independent and the Philox streams are keyed by the global chain id).
     tc::GemmMaps maps_h[2];
     bool narrow_h[2] = {false, false};
     int64_t row0_h[2] = {0, 0}, nrows_h[2] = {0, 0};
@@ -493,7 +494,7 @@ struct DenseTF32Sampler : SamplerImpl {
             const int64_t l0 = launches, s0 = step0, d0 = diag_steps, r0 = since_refresh;
             cudaGraph_t graph = nullptr;
             int rc = RMN_OK;
-            if (nrows_h[1] > 0 && cap_stream2 && ev_fork && ev_join) {
+            if (nrows_h[1] >= 4096 && cap_stream2 && ev_fork && ev_join) {
                 // fork: branch 0 on cap_stream, branch 1 on cap_stream2, joined before the capture ends
                 cudaEventRecord(ev_fork, cap_stream);
                 cudaStreamWaitEvent(cap_stream2, ev_fork, 0);
