@@ -563,7 +563,7 @@ def measure(ctx, wl, precision, Kg, T, steps, warmup, burn, chain_offset, K_tota
             diag = None
     if diag is None:
         diag = summarize_block(blk.cpu().numpy())
-    nworld = 1 if scaling == "replica" else ctx.world
+    nworld = 1 if scaling.startswith("none") else ctx.world      # K = 1 replicas: the value is a single chain's
     value = Kg * nworld * T * steps / (ms * 1e-3)
     e2e_d = run_e2e(ctx, s, T, Kg, nworld, steps) if e2e else None
     out = {"workload": wl, "precision": precision, "value": value, "unit": UNIT, "ms_per_step": ms / steps,
