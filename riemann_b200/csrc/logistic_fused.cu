@@ -7,8 +7,7 @@
 //
 // A CTA owns 128 chains (one TMEM lane each) and a contiguous range of data rows, streamed as tiles of 64 rows:
 //
-//   TMA threads   ring A: X tile, hi and lo parts, fp32 [64][dp32], SWIZZLE_128B boxes of 32 columns (GEMM1, K-major), eight
-//                 one-box slots released box by box;
+//   TMA threads   ring A: X tile, hi and lo parts, fp32 [64][dp32], SWIZZLE_128B boxes of 32 columns (GEMM1, K-major);
 //                 ring B: the hi part again in the 32-byte-atom 128B swizzle -- the only layout tcgen05 accepts for an
 //                 MN-major TF32 operand (GEMM2 reads the tile transposed) -- plus the tile's label sign masks.
 //                 Same global lines (L2 hits), two tensor maps.  A slots are released by GEMM1, B slots by GEMM2.
@@ -28,6 +27,10 @@
 // The MMA thread issues GEMM1 of tile t+1 before it waits for the R of tile t, so the tensor pipe works on the
 // next logits while the pointwise warps process the current ones; tcgen05.mma executes in issue order, which is
 // what makes reusing a Z buffer two tiles later safe without another barrier.
+//
+// Measured dead end (gpurun r2k): releasing ring A box by box (eight one-box slots, TMA two tiles ahead) was SLOWER, 2.35 ms
+// per 1,024-chain sweep against 1.77 -- four commits and four barrier waits per tile cost the MMA thread more than the
+// exposed TMA latency it hid.
 //
 // Accuracy.  hi / lo parts are rounded to nearest TF32, so (hi + lo) carries 22 bits and z is fp32-accurate; the
 // per-row terms are fp32 (|error| ~1e-7 each), summed in fp64.  Measured budget: tests/test_gpu_logistic.py.
@@ -51,14 +54,11 @@ constexpr int TMEM_COLS_ALLOC = 512;
 template <int DP32> struct Cfg {
     static constexpr int NBOX = DP32 / 32;
     static constexpr int XPART = NBOX * BOX_BYTES;                 // one copy of the 64 x dp32 tile
-    // ring A: slots of ONE 32-column box of the tile, hi | lo (SWIZZLE_128B), released box by box as GEMM1 consumes them,
-    // so the TMA of tile t+2's first columns is in flight while GEMM1 of tile t is still running (the TMA latency,
-    // ~2,500 cycles, is longer than one GEMM1)
-    static constexpr int SA = 8;
-    static constexpr int SB = (DP32 == 128) ? 2 : 4;               // ring B slots: whole Xh tile (32-byte-atom swizzle) | label masks
-    static constexpr int A_BYTES = 2 * BOX_BYTES;
+    static constexpr int SA = (DP32 == 128) ? 2 : 4;               // ring A slots: Xh | Xl (SWIZZLE_128B)
+    static constexpr int SB = (DP32 == 128) ? 2 : 4;               // ring B slots: Xh (32-byte-atom swizzle) | label masks
+    static constexpr int A_BYTES = 2 * XPART;
     static constexpr int B_BYTES = XPART + 1024;                   // masks: 256 B, padded to keep 1024-byte alignment
-    static constexpr int TXA = 2 * BOX_BYTES, TXB = XPART + NT * 4;
+    static constexpr int TXA = 2 * XPART, TXB = XPART + NT * 4;
     static constexpr int OFF_B = SA * A_BYTES;
     static constexpr int OFF_BAR = OFF_B + SB * B_BYTES;
     static constexpr int SMEM = OFF_BAR + 1024 /*align*/ + 256 /*barriers*/;
@@ -178,18 +178,17 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer, ring A: Xh | Xl for GEMM1, one 32-column box per slot =====
-        const int nbox = (a.d + 31) / 32;                          // boxes that hold data (<= NBOX)
-        uint32_t it = 0;
+        // ===== TMA producer, ring A: Xh | Xl for GEMM1 =====
         for (int t = 0; t < ntile; ++t) {
+            const int s = t % SA;
+            mbar_wait(&emptyA[s], ((t / SA) & 1) ^ 1);
+            uint8_t* st = smem + s * C::A_BYTES;
             const int row0 = (int)((t_begin + t) * NT);
-            for (int b = 0; b < nbox; ++b, ++it) {
-                const int s = it % SA;
-                mbar_wait(&emptyA[s], ((it / SA) & 1) ^ 1);
-                uint8_t* st = smem + s * C::A_BYTES;
-                mbar_expect_tx(&fullA[s], C::TXA);
-                tma_load_2d(st, &map_xh, &fullA[s], b * 32, row0);
-                tma_load_2d(st + BOX_BYTES, &map_xl, &fullA[s], b * 32, row0);
+            mbar_expect_tx(&fullA[s], C::TXA);
+#pragma unroll
+            for (int b = 0; b < C::NBOX; ++b) {
+                tma_load_2d(st + b * BOX_BYTES, &map_xh, &fullA[s], b * 32, row0);
+                tma_load_2d(st + C::XPART + b * BOX_BYTES, &map_xl, &fullA[s], b * 32, row0);
             }
         }
     } else if (warp == 3 && lane == 0) {
@@ -210,26 +209,21 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         const uint32_t idesc2 = umma_idesc_tf32(CB, DP32) | (1u << 16);          // B is MN-major
         const uint32_t t_th = tmem_base + C::COL_TH, t_tl = tmem_base + C::COL_TL, t_g = tmem_base + C::COL_G;
         const int d8 = (a.d + 7) / 8;                                            // K steps of GEMM1
-        const int nbox = (a.d + 31) / 32;
-        uint32_t ita = 0;                                           // ring A slot counter (boxes consumed so far)
         auto gemm1 = [&](int t) {
+            const int s = t % SA;
+            mbar_wait(&fullA[s], (t / SA) & 1);
+            tc_fence_after();
+            const uint32_t sx = smem_u32(smem + s * C::A_BYTES);
             const uint32_t tz = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
-            for (int b = 0; b < nbox; ++b, ++ita) {
-                const int s = ita % SA;
-                mbar_wait(&fullA[s], (ita / SA) & 1);
-                tc_fence_after();
-                const uint32_t sx = smem_u32(smem + s * C::A_BYTES);
-                const int ks1 = min(4, d8 - 4 * b);                                        // K steps in this box
-                for (int k = 0; k < ks1; ++k) {
-                    const int ks = 4 * b + k;
-                    const uint64_t dbh = umma_desc_kmajor<128>(sx + k * 32);                // 32 bytes per K step
-                    const uint64_t dbl = umma_desc_kmajor<128>(sx + BOX_BYTES + k * 32);
-                    umma_tf32_ts(tz, t_th + ks * 8, dbh, idesc1, ks != 0);
-                    umma_tf32_ts(tz, t_th + ks * 8, dbl, idesc1, 1);
-                    umma_tf32_ts(tz, t_tl + ks * 8, dbh, idesc1, 1);
-                }
-                umma_commit(&emptyA[s]);             // GEMM1 is the only reader of ring A
+            for (int ks = 0; ks < d8; ++ks) {
+                const uint32_t boff = (uint32_t)((ks >> 2) * BOX_BYTES + (ks & 3) * 32);      // box, 32 bytes per K step
+                const uint64_t dbh = umma_desc_kmajor<128>(sx + boff);
+                const uint64_t dbl = umma_desc_kmajor<128>(sx + C::XPART + boff);
+                umma_tf32_ts(tz, t_th + ks * 8, dbh, idesc1, ks != 0);
+                umma_tf32_ts(tz, t_th + ks * 8, dbl, idesc1, 1);
+                umma_tf32_ts(tz, t_tl + ks * 8, dbh, idesc1, 1);
             }
+            umma_commit(&emptyA[s]);                 // GEMM1 was the only reader of the A slot
             umma_commit(&z_full[t & 1]);
         };
         if (ntile > 0) {

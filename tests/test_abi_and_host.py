@@ -280,6 +280,41 @@ def test_bench_line_contract():
     assert b.METRIC == d["metric"] and b.UNIT == d["unit"]
 
 
+def test_bench_line_contract_round2():
+    """The line the default `bench.py` invocation printed on a B200 in round 2 (tests/golden/bench_line_r2.json, gpurun
+    r2w): the headline keys of the contract, the `configs` array with every BASELINE config at its own sharding, the
+    ESS phase, and the consistency of each entry's numbers."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "bench_line_r2.json")) as f:
+        d = json.load(f)
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert d["metric"] == b.METRIC and d["unit"] == b.UNIT and d["vs_baseline"] is None and d["scaling"] == "weak"
+    assert d["roofline"]["traffic"] is None and "profiled" in d["roofline"]          # static ncu numbers only under `profiled`
+    assert d["roofline"]["algo_flop_per_chain_step"] == 350.0 and d["roofline"]["algo_compares_per_chain_step"] == 300.0
+    assert d["cpu_baseline"]["kind"] == "reference"
+    e = d["ess"]
+    assert e["max_rhat"] < 1.05 and e["window_over_tau"] > 10 and d["min_ess_per_sec"] == e["min_ess_per_sec"] > 0
+    assert len(e["tau_steps"]) == len(e["functionals"]) == 8
+    keys = [c["key"] for c in d["configs"]]
+    assert keys == [k for k, *_ in b.SUBCONFIGS]
+    for c in d["configs"]:
+        assert "error" not in c, c
+        for k in ("value", "e2e", "dtype", "roofline", "diagnostics", "clocks", "cpu_baseline", "scaling", "ms_per_step"):
+            assert k in c, (c["key"], k)
+        T, K, steps = c["config"]["iters_per_step"], c["config"]["chains_total"], c["steps"]
+        assert abs(c["value"] - K * T / (c["ms_per_step"] * 1e-3)) < 1e-6 * c["value"]
+        assert c["e2e"]["h2d_bytes_per_step"] > 0 and c["e2e"]["value"] != c["value"]
+        r = c["roofline"]
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["kernel_launches"] > 0 and "timed_in" in r
+    tot = {c["key"]: c["config"]["chains_total"] for c in d["configs"]}
+    assert tot["gauss1000_mala_f64"] == tot["gauss1000_mala_tf32x3"] == 16384          # BASELINE.json's own chain counts
+    assert tot["logistic_mala_f64"] == 8192 and tot["logistic_mmala_tf32x3"] == 4096 and tot["gauss2d_rw_k1"] == 1
+
+
 def test_split_rhat_sees_a_common_drift():
     """summarize_split: chains that all drift the same way have R-hat ~ 1 over the whole window (every chain mean
     is the same) but split-R-hat > 1; stationary AR(1) chains give ~1 and the right tau either way."""
