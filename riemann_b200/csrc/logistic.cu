@@ -41,6 +41,7 @@
 #include "logistic_math.cuh"
 #include "logistic_fused.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace tc {
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
@@ -905,7 +906,7 @@ struct LogisticSampler : SamplerImpl {
         switch (which) {
             case 0: return align256((size_t)st.N * fg.dp32 * 4);
             case 1: return align256((size_t)fg.nys * 4);
-            case 2: return align256((size_t)2 * fg.ns * st.K * 8);
+            case 2: return align256((size_t)lgf::LLP_PER_SPLIT * fg.ns * st.K * 8);
             default: return align256((size_t)fg.ns * st.K * fg.dp32 * 4);
         }
     }
@@ -1008,10 +1009,23 @@ struct LogisticSampler : SamplerImpl {
         a.ys = fys; a.Th = st.Th; a.cur = st.cur; a.fixed_slot = fixed_slot;
         a.K = st.K; a.N = st.N; a.d = st.d; a.dp = st.dp;
         a.llp = fllp; a.gp = fgp; a.W = st.W; a.ldw = st.Npad;
+        static long long* d_tl = nullptr;                          // RMN_LGF_TIMELINE=1: clock64 stamps of CTA 0 (debug aid)
+        if (const char* e = getenv("RMN_LGF_TIMELINE")) {
+            if (e[0] == '1' && !d_tl) { cudaMalloc(&d_tl, 256 * 8 * 8); }
+            if (e[0] == '1' && d_tl) { cudaMemsetAsync(d_tl, 0, 256 * 8 * 8, stream); a.dbg = d_tl; }
+        }
         ktimer.begin("lg_fused_sweep_kernel", stream);
         if (int rc = lgf::sweep(fmaps, fg, a, stream)) return rc;
         ktimer.end(stream);
         if (int rc = lgf::reduce(fg, st.K, st.dp, fllp, fgp, st.llpart, st.gpart, stream)) return rc;
+        if (a.dbg) {
+            if (const char* f = getenv("RMN_LGF_TIMELINE_FILE")) {
+                std::vector<long long> h(256 * 8);
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(h.data(), a.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+                if (FILE* fp = fopen(f, "wb")) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }
+            }
+        }
         launches += 2;
         return RMN_OK;
     }

@@ -9,14 +9,14 @@
 //
 //   TMA threads   ring A: X tile, hi and lo parts, fp32 [64][dp32], SWIZZLE_128B boxes of 32 columns (GEMM1, K-major);
 //                 ring B: the hi part again in the 32-byte-atom 128B swizzle -- the only layout tcgen05 accepts for an
-//                 MN-major TF32 operand (GEMM2 reads the tile transposed) -- plus the tile's label sign masks.
+//                 MN-major TF32 operand (GEMM2 reads the tile transposed).
 //                 Same global lines (L2 hits), two tensor maps.  A slots are released by GEMM1, B slots by GEMM2.
 //   MMA thread    GEMM1  Z[128 x 64] = Theta_h Xh^T + Theta_h Xl^T + Theta_l Xh^T   (3 x TF32, fp32-accurate);
 //                        A = Theta from TENSOR MEMORY (loaded once per CTA), B = X tile, K-major
 //                 GEMM2  G[128 x dp32] += R[128 x 64] Xh[64 x dp32]                  (single-pass TF32: the gradient
 //                        only shapes the proposal); A = R from tensor memory, written in place over Z by the
 //                        pointwise warps, B = the Xh tile read MN-major (no transposed copy of X in HBM)
-//   2 x 4 warps   pointwise stage, both warpgroups on every tile (32 of its 64 rows each): tcgen05.ld the logits, fp32
+//   4 x 4 warps   pointwise stage, all four warpgroups on every tile (16 of its 64 rows each): tcgen05.ld the logits, fp32
 //                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element, two
 //                 elements per instruction with the packed fp32 FMA of sm_100),
 //                 log-likelihood partial sums in fp64, R = y - p rounded to TF32 -> tcgen05.st back into the same
@@ -48,17 +48,19 @@ namespace {
 constexpr int NT = 64;                     // data rows per tile = UMMA N of GEMM1 = K extent of GEMM2
 constexpr int CB = 128;                    // chains per CTA = UMMA M
 constexpr int BOX_BYTES = NT * 128;        // one TMA box: 64 rows x 32 fp32
-constexpr int THREADS = 384;               // warp 0 TMA ring A, 1 MMA, 2 TMEM alloc, 3 TMA ring B, 4..7 / 8..11 pointwise warpgroups
+constexpr int PWG = 4;                     // pointwise warpgroups: each takes NT / PWG = 16 of a tile's 64 rows
+constexpr int PCOLS = NT / PWG;
+constexpr int THREADS = 128 + 128 * PWG;   // warp 0 TMA ring A, 1 MMA, 2 TMEM alloc, 3 TMA ring B, then PWG x 4 pointwise warps
 constexpr int TMEM_COLS_ALLOC = 512;
 
 template <int DP32> struct Cfg {
     static constexpr int NBOX = DP32 / 32;
     static constexpr int XPART = NBOX * BOX_BYTES;                 // one copy of the 64 x dp32 tile
     static constexpr int SA = (DP32 == 128) ? 2 : 4;               // ring A slots: Xh | Xl (SWIZZLE_128B)
-    static constexpr int SB = (DP32 == 128) ? 2 : 4;               // ring B slots: Xh (32-byte-atom swizzle) | label masks
+    static constexpr int SB = (DP32 == 128) ? 3 : 4;               // ring B slots: Xh (32-byte-atom swizzle)
     static constexpr int A_BYTES = 2 * XPART;
-    static constexpr int B_BYTES = XPART + 1024;                   // masks: 256 B, padded to keep 1024-byte alignment
-    static constexpr int TXA = 2 * XPART, TXB = XPART + NT * 4;
+    static constexpr int B_BYTES = XPART;
+    static constexpr int TXA = 2 * XPART, TXB = XPART;
     static constexpr int OFF_B = SA * A_BYTES;
     static constexpr int OFF_BAR = OFF_B + SB * B_BYTES;
     static constexpr int SMEM = OFF_BAR + 1024 /*align*/ + 256 /*barriers*/;
@@ -78,6 +80,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r)
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] . B[smem]
@@ -88,6 +98,31 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// MMA issue for a warp in UNIFORM control flow: every lane executes the statement, `elect.sync` picks the one that issues.
+// The B descriptor comes as two 32-bit words (only the start-address field in the low word changes from MMA to MMA, so
+// advancing it is ONE integer add) and the accumulate flag is a literal.  With warp-uniform operands the compiler keeps
+// them in uniform registers and an MMA costs two or three instructions instead of a divergent issue sequence.
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa;\n"
+        ".reg .b64 bd;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %5, 0;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, pa;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // shared-memory matrix descriptor, MN-major, 32-bit elements: tcgen05 accepts ONE layout for an MN-major TF32 operand,
@@ -102,11 +137,6 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_b32(uint32_t saddr, uint32
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)1 << 61;                      // SWIZZLE_128B_BASE32B
     return d;
-}
-
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ float rn_tf32(float x) {          // round to nearest TF32 (10 explicit mantissa bits)
@@ -166,7 +196,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
         for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4 * PWG); }
         mbar_init(th_ready, 4);
         mbar_init(g_full, 1);
         fence_barrier_init();
@@ -192,7 +222,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             }
         }
     } else if (warp == 3 && lane == 0) {
-        // ===== TMA producer, ring B: Xh in the MN-major layout for GEMM2, label masks for the pointwise stage =====
+        // ===== TMA producer, ring B: Xh in the MN-major layout for GEMM2 =====
         for (int t = 0; t < ntile; ++t) {
             const int s = t % SB;
             mbar_wait(&emptyB[s], ((t / SB) & 1) ^ 1);
@@ -201,32 +231,51 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             mbar_expect_tx(&fullB[s], C::TXB);
 #pragma unroll
             for (int b = 0; b < C::NBOX; ++b) tma_load_2d(st + b * BOX_BYTES, &map_xt, &fullB[s], b * 32, row0);
-            bulk_load_1d(st + C::XPART, a.ys + row0, NT * 4, &fullB[s]);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: the WHOLE warp runs the loop in uniform control flow, `elect.sync` inside each issue =====
+        // Measured with the per-tile clock stamps (RMN_LGF_TIMELINE): with one thread building a 64-bit descriptor per
+        // MMA, GEMM1 issued at ~70 cycles per MMA against the 32 the tensor pipe needs for M = 128, N = 64, K = 8 -- the
+        // issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512 TMEM
+        // columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
         const uint32_t idesc1 = umma_idesc_tf32(CB, NT);
         const uint32_t idesc2 = umma_idesc_tf32(CB, DP32) | (1u << 16);          // B is MN-major
-        const uint32_t t_th = tmem_base + C::COL_TH, t_tl = tmem_base + C::COL_TL, t_g = tmem_base + C::COL_G;
-        const int d8 = (a.d + 7) / 8;                                            // K steps of GEMM1
+        constexpr uint32_t t_th = C::COL_TH, t_tl = C::COL_TL, t_g = C::COL_G;
+        const int nbox = (a.d + 31) / 32, d8 = (a.d + 7) / 8;                   // boxes / K steps of GEMM1 that hold data
+        const uint64_t dk0 = umma_desc_kmajor<128>(0);                           // descriptors with a zero start address
+        const uint64_t dm0 = umma_desc_mnmajor_b32(0, BOX_BYTES, 512);
+        const uint32_t dk_hi = (uint32_t)(dk0 >> 32), dk_lo0 = (uint32_t)dk0;
+        const uint32_t dm_hi = (uint32_t)(dm0 >> 32), dm_lo0 = (uint32_t)dm0;
+        const uint32_t smem0 = smem_u32(smem);
+        const bool dbg = a.dbg && blockIdx.x == 0 && lane == 0;
+        auto stamp = [&](int t, int k) { if (dbg && t < 256) a.dbg[t * 8 + k] = clock64(); };
         auto gemm1 = [&](int t) {
             const int s = t % SA;
             mbar_wait(&fullA[s], (t / SA) & 1);
             tc_fence_after();
-            const uint32_t sx = smem_u32(smem + s * C::A_BYTES);
-            const uint32_t tz = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
-            for (int ks = 0; ks < d8; ++ks) {
-                const uint32_t boff = (uint32_t)((ks >> 2) * BOX_BYTES + (ks & 3) * 32);      // box, 32 bytes per K step
-                const uint64_t dbh = umma_desc_kmajor<128>(sx + boff);
-                const uint64_t dbl = umma_desc_kmajor<128>(sx + C::XPART + boff);
-                umma_tf32_ts(tz, t_th + ks * 8, dbh, idesc1, ks != 0);
-                umma_tf32_ts(tz, t_th + ks * 8, dbl, idesc1, 1);
-                umma_tf32_ts(tz, t_tl + ks * 8, dbh, idesc1, 1);
+            stamp(t, 0);
+            const uint32_t tz = C::COL_Z + (uint32_t)((t & 1) * NT);
+            const uint32_t lo_h = dk_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES)) & 0x3FFFF) >> 4), lo_l = lo_h + (C::XPART >> 4);
+            for (int b = 0; b < nbox; ++b) {
+                const int ksn = min(4, d8 - 4 * b);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < ksn) {                                                          // warp-uniform
+                        const uint32_t off = (uint32_t)(b * (BOX_BYTES >> 4) + k * 2);       // 16-byte units: box, 32 B per K step
+                        const uint32_t ta = (uint32_t)((4 * b + k) * 8);
+                        if (b == 0 && k == 0) umma_tf32_ts_w<false>(tz, t_th + ta, lo_h + off, dk_hi, idesc1);
+                        else umma_tf32_ts_w<true>(tz, t_th + ta, lo_h + off, dk_hi, idesc1);
+                        umma_tf32_ts_w<true>(tz, t_th + ta, lo_l + off, dk_hi, idesc1);
+                        umma_tf32_ts_w<true>(tz, t_tl + ta, lo_h + off, dk_hi, idesc1);
+                    }
+                }
             }
-            umma_commit(&emptyA[s]);                 // GEMM1 was the only reader of the A slot
-            umma_commit(&z_full[t & 1]);
+            umma_commit_elect(&emptyA[s]);           // GEMM1 was the only reader of the A slot
+            umma_commit_elect(&z_full[t & 1]);
+            stamp(t, 1);
         };
         if (ntile > 0) {
+            if (tmem_base != 0) __trap();            // 512 columns allocated: the base cannot be anything else
             mbar_wait(th_ready, 0);
             tc_fence_after();
             gemm1(0);
@@ -236,16 +285,18 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 mbar_wait(&fullB[s], (t / SB) & 1);
                 mbar_wait(&r_full[t & 1], (t >> 1) & 1);
                 tc_fence_after();
-                const uint32_t sx = smem_u32(ringB + s * C::B_BYTES);
-                const uint32_t tr = tmem_base + C::COL_Z + (uint32_t)((t & 1) * NT);
+                stamp(t, 2);
+                const uint32_t tr = C::COL_Z + (uint32_t)((t & 1) * NT);
+                const uint32_t lo_b = dm_lo0 + (((smem0 + (uint32_t)(C::OFF_B + s * C::B_BYTES)) & 0x3FFFF) >> 4);
+                if (t == 0) umma_tf32_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
+                else umma_tf32_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
 #pragma unroll
-                for (int ks = 0; ks < NT / 8; ++ks) {
-                    const uint64_t db = umma_desc_mnmajor_b32(sx + ks * 1024, BOX_BYTES, 512);
-                    umma_tf32_ts(t_g, tr + ks * 8, db, idesc2, (t | ks) != 0);
-                }
-                umma_commit(&emptyB[s]);             // the B slot (X tile, label masks) is free once GEMM2 has read it
+                for (int ks = 1; ks < NT / 8; ++ks)
+                    umma_tf32_ts_w<true>(t_g, tr + ks * 8, lo_b + ks * (1024 >> 4), dm_hi, idesc2);
+                umma_commit_elect(&emptyB[s]);       // the B slot is free once GEMM2 has read it
+                stamp(t, 3);
             }
-            umma_commit(g_full);
+            umma_commit_elect(g_full);
         }
     } else if (warp >= 4) {
         // ===== pointwise warpgroups: thread = chain (TMEM lane 32 q + lane) =====
@@ -275,27 +326,44 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(th_ready);
         }
-        // Every tile is split between the two warpgroups (32 of its 64 data rows each), so a tile's pointwise latency is
-        // half of what one warpgroup per tile gave and R(t) is ready while GEMM1(t+1) is still running.
+        // Every tile is split between the PWG warpgroups (16 of its 64 data rows each).  The per-element arithmetic is a
+        // long dependent chain (EX2, ten FMAs, RCP); with one warpgroup per tile the tile's pointwise LATENCY, not its
+        // instruction count, set the pace (the tensor pipe idled waiting for R).  Four warps per scheduler, each with a
+        // quarter of the tile, bring R(t) in while GEMM1(t+1) is still running.
         double ll = 0.0;
         float* wrow = HASW ? a.W + (okc ? c : 0) * a.ldw : nullptr;
-        const int col0 = wg * 32;
+        const int col0 = wg * PCOLS;
+        // The tile's label sign masks (16 words per warpgroup, the same for every chain) come straight from global
+        // memory into registers, one tile AHEAD, so the stage starts the moment GEMM1 completes.  (They used to ride in
+        // ring B; with two 32-KB slots that ring is refilled ~2,500 cycles after GEMM2 of tile t-2, later than GEMM1 of
+        // tile t finishes, and the pointwise warps sat waiting for 256 bytes.)
+        const uint4* ysg = reinterpret_cast<const uint4*>(a.ys + t_begin * NT + col0);
+        uint4 ymn[PCOLS / 4];
+#pragma unroll
+        for (int i = 0; i < PCOLS / 4; ++i) ymn[i] = (ntile > 0) ? __ldg(ysg + i) : make_uint4(0, 0, 0, 0);
         for (int t = 0; t < ntile; ++t) {
-            const int s = t % SB;
-            const uint2* ysm = reinterpret_cast<const uint2*>(ringB + s * C::B_BYTES + C::XPART) + col0 / 2;
+            uint32_t ymv[PCOLS];
+#pragma unroll
+            for (int i = 0; i < PCOLS / 4; ++i) { ymv[4 * i] = ymn[i].x; ymv[4 * i + 1] = ymn[i].y; ymv[4 * i + 2] = ymn[i].z; ymv[4 * i + 3] = ymn[i].w; }
+            if (t + 1 < ntile) {
+#pragma unroll
+                for (int i = 0; i < PCOLS / 4; ++i) ymn[i] = __ldg(ysg + (size_t)(t + 1) * (NT / 4) + i);
+            }
             const int64_t row0 = (t_begin + t) * NT + col0;
-            mbar_wait(&fullB[s], (t / SB) & 1);          // the label masks arrive with ring B
             mbar_wait(&z_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
+            const bool dbgp = a.dbg && blockIdx.x == 0 && warp == 4 && lane == 0 && t < 256;
+            if (dbgp) a.dbg[t * 8 + 4] = clock64();
             const uint32_t tz = lane_base + C::COL_Z + (uint32_t)((t & 1) * NT + col0);
-            float v[32];
-            tmem_ld_32x32(tz, v);
-            uint32_t rr[32];
-            float wv[HASW ? 32 : 2];
+            float v[PCOLS];
+            tmem_ld_32x16(tz, v);
+            if (dbgp) a.dbg[t * 8 + 5] = clock64();
+            uint32_t rr[PCOLS];
+            float wv[HASW ? PCOLS : 2];
             float2 part = f2(0.0f);
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                const uint2 ym = ysm[e >> 1];                                   // 0x80000000 where y = 1
+            for (int e = 0; e < PCOLS; e += 2) {
+                const uint2 ym = make_uint2(ymv[e], ymv[e + 1]);                // 0x80000000 where y = 1
                 const float s0 = __uint_as_float(__float_as_uint(v[e]) ^ ym.x);    // s = (1 - 2y) z
                 const float s1 = __uint_as_float(__float_as_uint(v[e + 1]) ^ ym.y);
                 const float2 ex = make_float2(ex2_approx(-1.4426950408889634f * fabsf(v[e])),     // e = exp(-|z|)
@@ -313,28 +381,30 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 if (HASW) { const float2 w2 = __ffma2_rn(ei, inv, f2(0.0f)); wv[e] = w2.x; wv[e + 1] = w2.y; }
                 if ((e & 6) == 6) { ll += (double)(part.x + part.y); part = f2(0.0f); }
             }
-            tmem_st_32x32(tz, rr);
-            if (HASW && okc && row0 < a.ldw) {                       // ldw is a multiple of 32
+            if (dbgp) a.dbg[t * 8 + 6] = clock64();
+            tmem_st_32x16(tz, rr);
+            if (HASW && okc && row0 < a.ldw) {                       // ldw is a multiple of 32, row0 of 16
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
+                for (int e = 0; e < PCOLS; e += 4)
                     *reinterpret_cast<float4*>(wrow + row0 + e) = make_float4(wv[e], wv[e + 1], wv[e + 2], wv[e + 3]);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&r_full[t & 1]);
+            if (dbgp) a.dbg[t * 8 + 7] = clock64();
         }
         // rows beyond N (the last tile's padding) are zero rows of X: z = 0 exactly, and each contributed
         // -softplus(0) in the arithmetic above -- take those terms out again
         if (t_end == a.tiles_total && ntile > 0) {
             const int64_t lo = (a.tiles_total - 1) * NT + col0;
-            const int64_t npad = lo + 32 - max(a.N, lo);
+            const int64_t npad = lo + PCOLS - max(a.N, lo);
             if (npad > 0) {
                 const float2 sp0 = log1p_unit2(f2(ex2_approx(-0.0f)));
                 ll += (double)npad * (double)sp0.x;
             }
         }
-        if (okc) a.llp[((int64_t)rs * 2 + wg) * a.K + c] = ll;
+        if (okc) a.llp[((int64_t)rs * PWG + wg) * a.K + c] = ll;
         if (wg == 0) {
             // gradient partial of this (chain block, row split)
             float* gout = a.gp + ((int64_t)rs * a.K + (okc ? c : 0)) * DP32;
@@ -387,7 +457,7 @@ lgf_reduce_kernel(int64_t K, int ns, int dp32, int dp, const double* __restrict_
     const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (c >= K) return;
     double ll = 0.0;
-    for (int q = lane; q < 2 * ns; q += 32) ll += llp[(int64_t)q * K + c];
+    for (int q = lane; q < PWG * ns; q += 32) ll += llp[(int64_t)q * K + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
     if (lane == 0) llpart[c] = ll;

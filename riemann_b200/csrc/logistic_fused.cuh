@@ -15,6 +15,8 @@ struct Geometry {
     int64_t nys;           // entries of the label-mask array (a whole number of tiles)
 };
 
+constexpr int LLP_PER_SPLIT = 4;
+
 struct Maps { CUtensorMap xh, xl, xt; };   // xt: the hi part again, 32-byte-atom swizzle (MN-major operand of GEMM2)
 
 struct SweepArgs {
@@ -24,10 +26,11 @@ struct SweepArgs {
     int fixed_slot;
     int64_t K, N;
     int d, dp;
-    double* llp;           // [2 ns][K]      log-likelihood partial sums (two pointwise warpgroups per split)
+    double* llp;           // [LLP_PER_SPLIT ns][K]  log-likelihood partial sums (one per pointwise warpgroup and split)
     float* gp;             // [ns][K][dp32]  gradient partial sums
     float* W;              // [K][ldw] p (1 - p), or NULL
     int64_t ldw;
+    long long* dbg;        // optional timeline of CTA 0 (clock64 stamps, RMN_LGF_TIMELINE=1; scripts/lgf_timeline.py), else NULL
     int nblk, tps;         // filled by sweep()
     int64_t tiles_total;
 };
