@@ -334,7 +334,7 @@ int rmn_rng_draws(uint64_t seed, int64_t chain0, int64_t step, int64_t n, int nn
 
 /* fp32-accurate tensor-core product (tcgen05.mma.kind::tf32, TMA, TMEM), validation entry:
  * C[M][N] (fp32, row-major) ~= (Ah + Al)(Bh + Bl)^T  with Ah Bh^T + Ah Bl^T + Al Bh^T accumulated
- * in fp32; A* are [M][K], B* are [N][K] fp32 with the "hi" parts TF32-exact; K % 32 == 0, N % 4 == 0.
+ * in fp32; A* are [M][K], B* are [N][K] fp32 with the "hi" parts TF32-exact; K % 16 == 0, N % 4 == 0.
  * It is the GEMM behind the tf32x3 precision mode of the dense Gaussian sampler. */
 int rmn_tf32x3_gemm(int64_t M, int N, int K, const float* d_Ah, const float* d_Al, const float* d_Bh,
                     const float* d_Bl, float* d_C, void* stream);

@@ -86,6 +86,13 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
     n1 = r * s;
 }
 
+// nanosecond wall clock common to all SMs (timeline aids)
+__device__ __forceinline__ long long rmn_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // four N(0,1) from one Philox block
 __device__ __forceinline__ void normal4(const uint4 r, double out[4]) {
     float a, b, c, d;

@@ -23,6 +23,9 @@
 //
 // TMA boxes cannot follow a per-row "current slot" bit, so this mode keeps ONE increment buffer
 // and fuses the accept-update (y += delta, V += P delta) into the finish/propose pass.
+#include <climits>
+#include <string>
+#include <vector>
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include <stdlib.h>
@@ -30,6 +33,8 @@
 namespace tc {
 int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+int launch_plain_mixed(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+void set_debug_stamp(long long* p);
 int prepare_kernels();
 }
 
@@ -57,16 +62,26 @@ struct TStep {
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
     const int64_t* d_step_base;   // CUDA-graph replays: step_fin / step_prop are relative to *d_step_base (else NULL)
     int64_t row0, nrows;          // the chain rows [row0, row0 + nrows) this launch works on (nrows = 0: all K)
+    long long* dbg;               // optional {first block start, last block end} globaltimer stamps (RMN_TF32_TIMELINE)
     const double* inj_xi; const double* inj_u;
     int64_t trace_slot;
     double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc; double* tr_lqr; double* tr_prop_theta;
 };
 
-// one warp per chain row
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// One warp per chain row.  128-thread blocks inside a 48-register budget: next to the GEMM's persistent CTA (384 threads x
+// 56 registers, all of the shared memory) an SM still takes 7 of these blocks, which is what lets the pass of one
+// half-batch run under the GEMM of the other (DenseTF32Sampler below).
+constexpr int FP_THREADS = 128;
+#ifndef RMN_TF32_FP_MINB
+#define RMN_TF32_FP_MINB 8
+#endif
+__global__ void __launch_bounds__(FP_THREADS, RMN_TF32_FP_MINB)
 finish_propose_f32_kernel(TState st, TStep sp) {
     const int lane = threadIdx.x & 31;
     const int64_t rl = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (sp.dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(sp.dbg), (unsigned long long)rmn_globaltimer());
     if (rl >= (sp.nrows ? sp.nrows : st.K)) return;
     const int64_t r = sp.row0 + rl;
     const int dp = st.dp, d = st.d;
@@ -89,10 +104,15 @@ finish_propose_f32_kernel(TState st, TStep sp) {
             const double he = 0.5 * eps_old;
             const bool mala = sp.prop_kind == RMN_PROP_HMC;
             const double ie = mala ? 1.0 / eps_old : 0.0;
+            // software pipeline: the loads of iteration i + 1 are issued before the arithmetic of iteration i
+            const float* __restrict__ gD = st.Yph + ro0;
+            const float* __restrict__ gV = st.V + ro0;
+            const float* __restrict__ gP = st.Vp + ro0;
+            float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nw = na, npd = na;
+            if (lane * 4 < dp) { na = ldg4(gD + lane * 4); nw = ldg4(gV + lane * 4); npd = ldg4(gP + lane * 4); }
             for (int j4 = lane * 4; j4 < dp; j4 += 128) {
-                const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro0 + j4);       // delta (raw fp32)
-                const float4 w = *reinterpret_cast<const float4*>(st.V + ro0 + j4);
-                const float4 pd = *reinterpret_cast<const float4*>(st.Vp + ro0 + j4);
+                const float4 a = na, w = nw, pd = npd;                                      // delta (raw fp32), V, P delta
+                if (j4 + 128 < dp) { na = ldg4(gD + j4 + 128); nw = ldg4(gV + j4 + 128); npd = ldg4(gP + j4 + 128); }
                 const float dl[4] = {a.x, a.y, a.z, a.w};
                 const float wv[4] = {w.x, w.y, w.z, w.w};
                 const float pv[4] = {pd.x, pd.y, pd.z, pd.w};
@@ -112,7 +132,10 @@ finish_propose_f32_kernel(TState st, TStep sp) {
         const double lpn = combine_logpost(0.0, lp - 0.5 * q);      // q = quad' - quad (gaussian.py:52)
         const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r]) : 0.0; // hamiltonian.py:89
         const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)step_fin, RMN_BLOCK_ACCEPT).x);
-        acc = mh_accept(lpn, lp, lqr, u);
+        {   // mh_accept (common.cuh) without the fp64 log where the ratio is >= 1: log(u) < 0 for every u in [0, 1)
+            const double dl = lpn - lp - lqr;
+            acc = (dl < 0.0) ? (log(u) < dl) : (u < 1.0);
+        }
         if (acc) lp = lpn;
         if (lane == 0) {
             if (acc) st.lp[r] = lp;
@@ -134,14 +157,26 @@ finish_propose_f32_kernel(TState st, TStep sp) {
     const double scale = sp.adapt ? st.scale[r] : 1.0;
     const double eps = (sp.prop_kind == RMN_PROP_HMC) ? scale * sp.eps0 : scale;
     double k0 = 0.0, rowsum = 0.0;
+    const float eps_f = (float)eps, heps_f = (float)(0.5 * eps), scale_f = (float)scale;
     const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
 
+    // Same software pipeline: Y, V (and delta, P delta when the row moves or the proposal is traced) of iteration i + 1 are
+    // requested before iteration i generates its noise; the stores of iteration i go to other addresses.
+    const bool need_a = sp.finish && (acc || sp.tr_prop_theta);
+    float4 nyc = make_float4(0.f, 0.f, 0.f, 0.f), nvc = nyc, nda = nyc, npd2 = nyc;
+    if (lane * 4 < dp) {
+        nyc = ldg4(st.Y + ro + lane * 4); nvc = ldg4(st.V + ro + lane * 4);
+        if (need_a) { nda = ldg4(st.Yph + ro + lane * 4); if (acc) npd2 = ldg4(st.Vp + ro + lane * 4); }
+    }
     for (int j4 = lane * 4; j4 < dp; j4 += 128) {
         // the row's (new) current state: the accepted proposal or the old state
-        float4 yc = *reinterpret_cast<const float4*>(st.Y + ro + j4);
-        float4 vc = *reinterpret_cast<const float4*>(st.V + ro + j4);
-        if (sp.finish && (acc || sp.tr_prop_theta)) {
-            const float4 a = *reinterpret_cast<const float4*>(st.Yph + ro + j4);
+        float4 yc = nyc, vc = nvc;
+        const float4 a = nda, pd = npd2;
+        if (j4 + 128 < dp) {
+            nyc = ldg4(st.Y + ro + j4 + 128); nvc = ldg4(st.V + ro + j4 + 128);
+            if (need_a) { nda = ldg4(st.Yph + ro + j4 + 128); if (acc) npd2 = ldg4(st.Vp + ro + j4 + 128); }
+        }
+        if (need_a) {
             // the proposal as a state: theta' = fl32(y + delta)
             const float4 yp = make_float4(yc.x + a.x, yc.y + a.y, yc.z + a.z, yc.w + a.w);
             if (sp.tr_prop_theta) {
@@ -151,7 +186,6 @@ finish_propose_f32_kernel(TState st, TStep sp) {
                     if (j4 + q < d) sp.tr_prop_theta[r * d + j4 + q] = (double)pv[q] + st.mu[j4 + q];
             }
             if (acc) {                                           // accept: y += delta, V += P delta
-                const float4 pd = *reinterpret_cast<const float4*>(st.Vp + ro + j4);
                 yc = yp;
                 vc = make_float4(vc.x + pd.x, vc.y + pd.y, vc.z + pd.z, vc.w + pd.w);
                 *reinterpret_cast<float4*>(st.Y + ro + j4) = yc;
@@ -160,40 +194,42 @@ finish_propose_f32_kernel(TState st, TStep sp) {
         }
         const float yv[4] = {yc.x, yc.y, yc.z, yc.w};
         const float vv[4] = {vc.x, vc.y, vc.z, vc.w};
-        rowsum += ((double)yv[0] + (double)yv[1]) + ((double)yv[2] + (double)yv[3]);
+        rowsum += (double)((yv[0] + yv[1]) + (yv[2] + yv[3]));
         if (want_trace) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (j4 + q < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + q] = (double)yv[q] + st.mu[j4 + q];
         }
         if (!sp.propose) continue;
-        double xi[4];
+        // The proposal in fp32: the noise is drawn in fp32 (Box-Muller on 32-bit uniforms), the increment is rounded to
+        // the grid of y anyway (theta' = fl32(y + delta)), and the acceptance works from the increment actually applied
+        // (p_half = delta / eps above), so fp64 here bought nothing but 6 conversions and 4 fp64 operations per element.
+        float xf[4];
         if (sp.inj_xi) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) xi[q] = (j4 + q < d) ? sp.inj_xi[r * d + j4 + q] : 0.0;
+            for (int q = 0; q < 4; ++q) xf[q] = (j4 + q < d) ? (float)sp.inj_xi[r * d + j4 + q] : 0.0f;
         } else {
-            normal4(rk.block((uint64_t)step_prop, (uint32_t)(j4 >> 2)), xi);
+            const uint4 rb = rk.block((uint64_t)step_prop, (uint32_t)(j4 >> 2));
+            box_muller(rb.x, rb.y, xf[0], xf[1]);
+            box_muller(rb.z, rb.w, xf[2], xf[3]);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (j4 + q >= d) xi[q] = 0.0;
+                if (j4 + q >= d) xf[q] = 0.0f;
         }
-        float od[4], ol[4], xf[4];
+        float od[4], ol[4];
+        float ksum = 0.0f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            xf[q] = (float)xi[q];                                        // the noise as the kernels see it
-            double dlt;                                                              // theta' - theta
-            if (sp.prop_kind == RMN_PROP_HMC) {
-                const double ph = (double)xf[q] + 0.5 * eps * (-(double)vv[q]);      // hamiltonian.py:27
-                dlt = eps * ph;                                                      // :30
-            } else {
-                dlt = scale * ((double)st.Ldiag[j4 + q] * (double)xf[q]);            // randomwalk.py:26
-            }
+            float dlt;                                                               // theta' - theta
+            if (sp.prop_kind == RMN_PROP_HMC) dlt = eps_f * fmaf(-heps_f, vv[q], xf[q]);     // hamiltonian.py:27,30
+            else dlt = scale_f * (st.Ldiag[j4 + q] * xf[q]);                                 // randomwalk.py:26
             // the increment actually applied is the fp32 one: theta' = fl32(y + delta)
-            od[q] = (yv[q] + (float)dlt) - yv[q];
-            k0 += (double)xf[q] * (double)xf[q];
+            od[q] = (yv[q] + dlt) - yv[q];
+            ksum = fmaf(xf[q], xf[q], ksum);
             float hi;
             tc::split_tf32(od[q], hi, ol[q]);            // remainder after the tensor core's own truncation of delta
         }
+        k0 += (double)ksum;
         // the increment is stored ONCE, raw: kind::tf32 drops the low 13 mantissa bits of its operand itself, so the
         // GEMM's "hi" pass reads this array as is and its "lo" pass the remainder
         *reinterpret_cast<float4*>(st.Yph + ro + j4) = make_float4(od[0], od[1], od[2], od[3]);
@@ -212,6 +248,7 @@ finish_propose_f32_kernel(TState st, TStep sp) {
             st.S2[(int64_t)lane * K + r] += f * f;
         }
     }
+    if (sp.dbg && lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(sp.dbg + 1), (unsigned long long)rmn_globaltimer());
 }
 
 __global__ void tstep_base_kernel(int64_t* p, int64_t v) { *p = v; }
@@ -294,6 +331,8 @@ struct DenseTF32Sampler : SamplerImpl {
     tc::GemmMaps maps;
     tc::GemmMaps maps_narrow;     // the same operands with 128-row boxes of P: 128 x 128 output tiles
     bool narrow = false;          // fewer than #SM tiles of 128 x 256: use the narrow tile (RMN_TF32_NARROW=0|1 overrides)
+    bool mixed = true;            // 128 x 256 tiles, the last partly filled round of the persistent loop cut into 128 x 128
+                                  // halves (tc_gemm.cu); RMN_TF32_MIXED=0: one tile width per launch as in round 1
     float* d_Ph = nullptr; float* d_Pl = nullptr; float* d_Ldiag = nullptr; double* d_mupad = nullptr;
     // The MH loop is two short kernels per step (GEMM + finish/propose pass); for a plain Philox run without trace the
     // T steps of a call are captured ONCE into a CUDA graph and replayed (the step counter the Philox streams need comes
@@ -317,20 +356,30 @@ struct DenseTF32Sampler : SamplerImpl {
     int64_t g_nodes = 0;
     int64_t* d_step_base = nullptr;
     cudaStream_t cap_stream = nullptr;
+    // RMN_TF32_TIMELINE=<file>: every kernel of a captured graph stamps its start / end (globaltimer); after each replay the
+    // list is appended to the file (scripts/dense_timeline.py reads it).  Measurement aid, off by default.
+    std::string tl_path;
+    long long* d_tl = nullptr;
+    std::vector<std::string> tl_labels;
     int64_t refresh = 512;        // exact fp64 recomputation of V / log-posterior every this many steps
     int64_t since_refresh = 0;
     explicit DenseTF32Sampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 31) / 32 * 32;
         if (const char* e = getenv("RMN_TF32_GRAPH")) use_graph = !(e[0] == '0');
         if (const char* e = getenv("RMN_TF32_HALVES")) two_halves = !(e[0] == '0');
+        if (const char* e = getenv("RMN_TF32_MIXED")) mixed = !(e[0] == '0');
+        if (const char* e = getenv("RMN_TF32_TIMELINE")) tl_path = e;
+        if (getenv("RMN_TF32_NARROW") || st.dp % tc::TN != 0) mixed = false;
     }
+    // contraction length handed to the GEMM: the k-blocks beyond d hold only padding zeros
+    int kdim() const { return (st.d + tc::TK3 - 1) / tc::TK3 * tc::TK3; }
     ~DenseTF32Sampler() override {
         if (gexec) cudaGraphExecDestroy(gexec);
         if (cap_stream) cudaStreamDestroy(cap_stream);
         if (cap_stream2) cudaStreamDestroy(cap_stream2);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
-        cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base);
+        cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base); cudaFree(d_tl);
     }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
     size_t workspace_bytes() const override {
@@ -398,14 +447,16 @@ struct DenseTF32Sampler : SamplerImpl {
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const int64_t k0 = std::min<int64_t>(st.K, ((st.K / 2 + tc::TM - 1) / tc::TM) * tc::TM);
+            int64_t ma = ((st.K + tc::TM - 1) / tc::TM + 1) / 2;            // row tiles of the first part: half of them, or
+            if (const char* e = getenv("RMN_TF32_SPLIT_MTILES")) ma = std::max<int64_t>(1, atoll(e));   // as given
+            const int64_t k0 = std::min<int64_t>(st.K, ma * tc::TM);
             row0_h[0] = 0; nrows_h[0] = k0; row0_h[1] = k0; nrows_h[1] = st.K - k0;
             for (int h = 0; h < 2; ++h) {
                 if (nrows_h[h] <= 0) continue;
                 const size_t off = (size_t)row0_h[h] * dp;
                 narrow_h[h] = ((nrows_h[h] + tc::TM - 1) / tc::TM) * ((dp + tc::TN - 1) / tc::TN) < sms;
                 if (const char* e = getenv("RMN_TF32_NARROW")) narrow_h[h] = (e[0] == '1');
-                const uint32_t brows = narrow_h[h] ? 128 : tc::TN;
+                const uint32_t brows = (narrow_h[h] || mixed) ? 128 : tc::TN;
                 if ((rc = tc::make_tmap_2d(&maps_h[h].ah, st.Yph + off, nrows_h[h], dp, dp, tc::TM, tc::TK3))) return rc;
                 if ((rc = tc::make_tmap_2d(&maps_h[h].al, st.Ypl + off, nrows_h[h], dp, dp, tc::TM, tc::TK3))) return rc;
                 if ((rc = tc::make_tmap_2d(&maps_h[h].bh, d_Ph, dp, dp, dp, brows, tc::TK3))) return rc;
@@ -417,15 +468,28 @@ struct DenseTF32Sampler : SamplerImpl {
         return RMN_OK;
     }
     unsigned row_grid() const { return (unsigned)((st.K * 32 + 255) / 256); }
-    void launch_fp(const TStep& sp, cudaStream_t stream) {
+    static constexpr int TL_MAX = 4096;
+    long long* tl_slot(const char* what, int half, int64_t t) {
+        if (!d_tl || (int)tl_labels.size() >= TL_MAX) return nullptr;
+        char b[64];
+        snprintf(b, sizeof b, "%s h=%d t=%lld", what, half, (long long)t);
+        tl_labels.push_back(b);
+        return d_tl + 2 * (tl_labels.size() - 1);
+    }
+    int tl_half = -1; int64_t tl_t = 0;
+    void launch_fp(const TStep& sp_in, cudaStream_t stream) {
+        TStep sp = sp_in;
+        sp.dbg = tl_slot("pass", tl_half, tl_t);
         const int64_t n = sp.nrows ? sp.nrows : st.K;
-        finish_propose_f32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, stream>>>(st, sp);
+        finish_propose_f32_kernel<<<(unsigned)((n * 32 + FP_THREADS - 1) / FP_THREADS), FP_THREADS, 0, stream>>>(st, sp);
     }
     int gemm_half(int h, cudaStream_t stream) {
         launches++;
         float* C = st.Vp + (size_t)row0_h[h] * st.dp;
-        if (narrow_h[h]) return tc::launch_plain_narrow(maps_h[h], nrows_h[h], st.dp, st.dp, C, st.dp, stream);
-        return tc::launch_plain(maps_h[h], nrows_h[h], st.dp, st.dp, C, st.dp, stream);
+        tc::set_debug_stamp(tl_slot("gemm", h, tl_t));
+        if (mixed) return tc::launch_plain_mixed(maps_h[h], nrows_h[h], st.dp, kdim(), C, st.dp, stream);
+        if (narrow_h[h]) return tc::launch_plain_narrow(maps_h[h], nrows_h[h], st.dp, kdim(), C, st.dp, stream);
+        return tc::launch_plain(maps_h[h], nrows_h[h], st.dp, kdim(), C, st.dp, stream);
     }
     double c1() const { return st.d * log(2.0 * M_PI); }
     // The GEMM keeps a plain, store-only epilogue (V' only); the MH row reductions run in the finish/propose pass.  (A fused
@@ -434,9 +498,11 @@ struct DenseTF32Sampler : SamplerImpl {
     int gemm(cudaStream_t stream) {
         launches++;
         ktimer.begin("tf32x3_gemm_kernel", stream);
+        tc::set_debug_stamp(tl_slot("gemm", -1, tl_t));
         int rc;
-        if (narrow) rc = tc::launch_plain_narrow(maps_narrow, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
-        else rc = tc::launch_plain(maps, st.K, st.dp, st.dp, st.Vp, st.dp, stream);
+        if (mixed) rc = tc::launch_plain_mixed(maps_narrow, st.K, st.dp, kdim(), st.Vp, st.dp, stream);
+        else if (narrow) rc = tc::launch_plain_narrow(maps_narrow, st.K, st.dp, kdim(), st.Vp, st.dp, stream);
+        else rc = tc::launch_plain(maps, st.K, st.dp, kdim(), st.Vp, st.dp, stream);
         ktimer.end(stream);
         return rc;
     }
@@ -487,6 +553,10 @@ struct DenseTF32Sampler : SamplerImpl {
                     cudaGetLastError(); cap_stream2 = nullptr;
                 }
             }
+            if (!tl_path.empty()) {
+                if (!d_tl) RMN_CUDA(cudaMalloc(&d_tl, (size_t)TL_MAX * 16));
+                tl_labels.clear();
+            }
             if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
                 cudaGetLastError(); use_graph = false;
                 return run_steps(T, inj, tr, stream, nullptr, -1);
@@ -524,7 +594,23 @@ struct DenseTF32Sampler : SamplerImpl {
         }
         tstep_base_kernel<<<1, 1, 0, stream>>>(d_step_base, step0);
         RMN_KERNEL_CHECK();
+        if (d_tl) {
+            std::vector<long long> init(2 * TL_MAX);
+            for (int i = 0; i < TL_MAX; ++i) { init[2 * i] = LLONG_MAX; init[2 * i + 1] = 0; }
+            RMN_CUDA(cudaMemcpyAsync(d_tl, init.data(), init.size() * 8, cudaMemcpyHostToDevice, stream));
+            RMN_CUDA(cudaStreamSynchronize(stream));
+        }
         RMN_CUDA(cudaGraphLaunch(gexec, stream));
+        if (d_tl) {
+            std::vector<long long> h(2 * tl_labels.size());
+            RMN_CUDA(cudaStreamSynchronize(stream));
+            RMN_CUDA(cudaMemcpy(h.data(), d_tl, h.size() * 8, cudaMemcpyDeviceToHost));
+            if (FILE* f = fopen(tl_path.c_str(), "a")) {
+                fprintf(f, "# replay T=%lld K=%lld\n", (long long)T, (long long)st.K);
+                for (size_t i = 0; i < tl_labels.size(); ++i) fprintf(f, "%s %lld %lld\n", tl_labels[i].c_str(), h[2 * i], h[2 * i + 1]);
+                fclose(f);
+            }
+        }
         launches += g_nodes + 1;
         step0 += T; diag_steps += T; since_refresh += T;
         return RMN_OK;
@@ -547,6 +633,7 @@ struct DenseTF32Sampler : SamplerImpl {
         const int64_t K = st.K;
         const int d = st.d;
         for (int64_t t = 0; t <= T; ++t) {
+            tl_half = half; tl_t = t;
             sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
             sp.step_fin = sb + t - 1; sp.step_prop = sb + t;
             sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;

@@ -904,7 +904,7 @@ struct LogisticSampler : SamplerImpl {
     }
     size_t f_bytes(int which) const {      // fused sweep: 0 Xh (= Xl), 1 label masks, 2 llp, 3 gp
         switch (which) {
-            case 0: return align256((size_t)st.N * fg.dp32 * 4);
+            case 0: return align256((size_t)st.N * fg.ldx * 4);
             case 1: return align256((size_t)fg.nys * 4);
             case 2: return align256((size_t)lgf::LLP_PER_SPLIT * fg.ns * st.K * 8);
             default: return align256((size_t)fg.ns * st.K * fg.dp32 * 4);

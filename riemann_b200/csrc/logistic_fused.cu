@@ -434,14 +434,14 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     }
 }
 
-// X[N][d] (fp64) -> Xh, Xl [N][dp32] (nearest-TF32 hi / lo parts, zero padded) and the label sign masks
+// X[N][d] (fp64) -> Xh, Xl [N][ldx] (nearest-TF32 hi / lo parts, row pitch ldx = d rounded up to 4) and the label sign masks
 __global__ void __launch_bounds__(256)
-lgf_prep_kernel(int64_t N, int d, int dp32, int64_t nys, const double* __restrict__ X, const double* __restrict__ y,
+lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, const double* __restrict__ X, const double* __restrict__ y,
                 float* __restrict__ Xh, float* __restrict__ Xl, uint32_t* __restrict__ ys) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx < N * dp32) {
-        const int64_t i = idx / dp32;
-        const int k = (int)(idx % dp32);
+    if (idx < N * ldx) {
+        const int64_t i = idx / ldx;
+        const int k = (int)(idx % ldx);
         float hi = 0.0f, lo = 0.0f;
         if (k < d) split_rn(X[i * d + k], hi, lo);
         Xh[idx] = hi; Xl[idx] = lo;
@@ -476,6 +476,7 @@ int dp32_of(int d) { return d <= 64 ? 64 : 128; }
 
 void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
     g->dp32 = dp32_of(d);
+    g->ldx = (d + 3) / 4 * 4;
     g->tiles_total = (N + NT - 1) / NT;
     g->nys = g->tiles_total * NT;
     g->nblk = (int)((K + CB - 1) / CB);
@@ -491,16 +492,17 @@ void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
 
 int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y, float* Xh, float* Xl, uint32_t* ys,
            cudaStream_t st) {
-    const int64_t n = std::max<int64_t>(N * g.dp32, g.nys);
-    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.dp32, g.nys, X, y, Xh, Xl, ys);
+    const int64_t n = std::max<int64_t>(N * g.ldx, g.nys);
+    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.ldx, g.nys, X, y, Xh, Xl, ys);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
 
 int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const float* Xl) {
-    if (int rc = make_tmap_2d(&m->xh, Xh, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT)) return rc;
-    if (int rc = make_tmap_2d(&m->xl, Xl, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT)) return rc;
-    return make_tmap_2d(&m->xt, Xh, (uint64_t)N, (uint64_t)g.dp32, (uint64_t)g.dp32, NT, 32, /*atom32=*/true);
+    // the maps are ldx columns wide: the boxes of the last 32-column block reach past it and are zero-filled there
+    if (int rc = make_tmap_2d(&m->xh, Xh, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
+    if (int rc = make_tmap_2d(&m->xl, Xl, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
+    return make_tmap_2d(&m->xt, Xh, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT, 32, /*atom32=*/true);
 }
 
 int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {

@@ -53,10 +53,23 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t co
 // PASSES = 1: plain TF32 product of the "hi" maps only (the Fisher-metric GEMM of the logistic sampler,
 //             where the product only shapes a proposal), 4 stages of 48 KB so the TMA latency stays hidden
 //             behind one third of the tensor work per stage.
+// Launch bounds: the kernel runs ONE persistent CTA per SM (its shared memory sees to that); the "3" only caps the
+// registers at 56 per thread (no spills) so that memory-bound kernels of another stream -- the dense sampler's row pass of
+// the other half-batch -- find 44K free registers on the SM while the tensor cores work (RMN_TC_MINB to change).
+#ifndef RMN_TC_MINB
+#define RMN_TC_MINB 3
+#endif
 template <int PASSES>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, RMN_TC_MINB)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
-                   int ldc, int ksplit, int kb_per, int64_t split_stride, int m_fastest, int tn) {
+                   int ldc, int ksplit, int kb_per, int64_t split_stride, int m_fastest, int tn, int bbox,
+                   int64_t wide_tiles, long long* dbg) {
+    // dbg: optional {first CTA start, last CTA end} in globaltimer ns (set_debug_stamp; the dense sampler's timeline aid)
+    if (dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(dbg), (unsigned long long)rmn_globaltimer());
+    // Tile list: the first `wide_tiles` tiles are tn columns wide; every further one is a HALF tile (tn / 2 columns, two
+    // per remaining full tile).  512 tiles of 128 x 256 on 148 SMs are 3.46 waves = 4 rounds of the persistent loop with
+    // the last one 46 % full; with the last 68 tiles cut in two, 136 CTAs work half a round: 3.5 rounds.  bbox = rows of
+    // B per TMA box (the B maps' box height): a tile issues (width / bbox) loads per operand.
     // tn: columns of C per tile, TN = 256 or 128 (the B tensor maps must have been built with box_rows = tn).  The
     // narrow tile is for outputs with fewer than #SM tiles of 128 x 256 (2,048 chains x 1,024 columns = 64 of them):
     // it doubles the tile count instead of leaving half of the SMs idle.  Shared-memory regions keep their 256-row size.
@@ -89,7 +102,12 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     const int n_tiles = (N + tn - 1) / tn;
     const int64_t m_tiles = (M + TM - 1) / TM;
     const int64_t mn_tiles = m_tiles * n_tiles;
-    const int64_t num_tiles = mn_tiles * ksplit;
+    const int64_t num_tiles = wide_tiles + 2 * (mn_tiles * ksplit - wide_tiles);
+    // tile index -> (output tile, column offset inside it, width)
+    auto decode = [&](int64_t tile, int64_t& wt, int& noff, int& w) {
+        if (tile < wide_tiles) { wt = tile; noff = 0; w = tn; }
+        else { const int64_t j = tile - wide_tiles; wt = wide_tiles + (j >> 1); w = tn >> 1; noff = (int)(j & 1) * w; }
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.bh);
@@ -110,37 +128,40 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         // ===== TMA producer: runs ahead across tiles, bounded by the stage ring =====
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int64_t mn = tile % mn_tiles;
-            const int kb0 = (int)(tile / mn_tiles) * kb_per;
+            int64_t wt; int noff, w;
+            decode(tile, wt, noff, w);
+            const int64_t mn = wt % mn_tiles;
+            const int kb0 = (int)(wt / mn_tiles) * kb_per;
             const int kb1 = min(KB_all, kb0 + kb_per);
             const int m0 = (int)(m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
-            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn;
-            const uint32_t tx_bytes = (uint32_t)((PASSES == 1 ? 1 : 2) * (A_BYTES + tn * ROWB));
+            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn + noff;
+            const uint32_t tx_bytes = (uint32_t)((PASSES == 1 ? 1 : 2) * (A_BYTES + w * ROWB));
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], tx_bytes);
                 tma_load_2d(st, &maps.ah, &full[s], kb * TK, m0);
-                tma_load_2d(st + OFF_BH, &maps.bh, &full[s], kb * TK, n0);
-                if (PASSES == 3) {
-                    tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, m0);
-                    tma_load_2d(st + 2 * A_BYTES + B_BYTES, &maps.bl, &full[s], kb * TK, n0);
+                if (PASSES == 3) tma_load_2d(st + A_BYTES, &maps.al, &full[s], kb * TK, m0);
+                for (int b = 0; b < w; b += bbox) {               // consecutive boxes continue the same swizzled layout
+                    tma_load_2d(st + OFF_BH + b * ROWB, &maps.bh, &full[s], kb * TK, n0 + b);
+                    if (PASSES == 3) tma_load_2d(st + 2 * A_BYTES + B_BYTES + b * ROWB, &maps.bl, &full[s], kb * TK, n0 + b);
                 }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer (one thread) =====
         // UMMA N = the valid width of B rounded up to 16 (a d-wide gradient tile does not pay for 256 columns)
-        const int n_eff = (N >= tn) ? tn : ((N + 15) / 16 * 16);
-        const uint32_t idesc = umma_idesc_tf32(TM, n_eff);
         uint32_t it = 0, ti = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int a = ti % ACC_STAGES;
             mbar_wait(&tmem_empty[a], ((ti / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(a * TN);
-            const int kb0 = (int)(tile / mn_tiles) * kb_per;
+            int64_t wt; int noff, w;
+            decode(tile, wt, noff, w);
+            const uint32_t idesc = umma_idesc_tf32(TM, (N >= tn) ? w : ((N + 15) / 16 * 16));
+            const int kb0 = (int)(wt / mn_tiles) * kb_per;
             const int kb1 = min(KB_all, kb0 + kb_per);
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % STAGES;
@@ -170,10 +191,12 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         uint32_t ti = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int a = ti % ACC_STAGES;
-            const int64_t mn = tile % mn_tiles;
+            int64_t wt; int noff, w;
+            decode(tile, wt, noff, w);
+            const int64_t mn = wt % mn_tiles;
             const int64_t m0 = (m_fastest ? mn % m_tiles : mn / n_tiles) * TM;
-            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn;
-            float* Cs = C + (tile / mn_tiles) * split_stride;
+            const int n0 = (int)(m_fastest ? mn / m_tiles : mn % n_tiles) * tn + noff;
+            float* Cs = C + (wt / mn_tiles) * split_stride;
             mbar_wait(&tmem_full[a], (ti / ACC_STAGES) & 1);
             tc_fence_after();
             // Epilogue data mapping: tcgen05.ld hands each thread one TMEM lane (= output row) x 16 columns;
@@ -182,9 +205,9 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             // Lane L then works on rows it*8 + L/4 (it = 0..3), columns 4 (L%4) .. +3 of the chunk.
             float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
             const int rsub = lane >> 2, cg = (lane & 3) * 4;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (tn / 2));
-            for (int c0 = 0; c0 < tn / 2; c0 += 16) {
-                const int n = n0 + half * (tn / 2) + c0;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + half * (w / 2));
+            for (int c0 = 0; c0 < w / 2; c0 += 16) {
+                const int n = n0 + half * (w / 2) + c0;
                 if (n >= N) continue;                                   // warp-uniform
                 bool okr[4];
 #pragma unroll
@@ -217,7 +240,12 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (dbg && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(dbg + 1), (unsigned long long)rmn_globaltimer());
 }
+
+static thread_local long long* g_dbg_stamp = nullptr;
+// the NEXT launch of this thread records {start, end} globaltimer stamps at p[0], p[1] (p[0] preset to LLONG_MAX, p[1] to 0)
+void set_debug_stamp(long long* p) { g_dbg_stamp = p; }
 
 // function attributes (dynamic shared memory limit) are per device; set them outside any stream capture
 int prepare_kernels() {
@@ -235,10 +263,10 @@ int prepare_kernels() {
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc,
                          cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0,
-                         int tn = TN) {
+                         int tn = TN, bool mixed = false) {
     if (tn != TN && tn != 128) { rmn_set_error("tf32x3 gemm: tile width must be 256 or 128"); return RMN_ERR_PARAM; }
     const int tk = (passes == 1) ? TK : TK3;                           // k-block of the kernel variant
-    if (Kdim % 32 != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of 32, ld of 4"); return RMN_ERR_PARAM; }
+    if (Kdim % tk != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of the k-block (%d), ld of 4", tk); return RMN_ERR_PARAM; }
     if (ksplit < 1 || ksplit > Kdim / tk) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
     // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
     const int kbp = (Kdim / tk + ksplit - 1) / ksplit;
@@ -249,10 +277,23 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
     cudaGetDevice(&dev);
     int& sms = sms_of[dev & 63];
     if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    dim3 grid((unsigned)(tiles < sms ? tiles : sms));          // persistent: one CTA per SM
+    // mixed: the B maps have 128-row boxes; the tiles of the last, partly filled round become half tiles when those fit
+    // one round (2 R <= #SM; fewer than #SM/2 tiles in all: every tile is a half tile = the narrow configuration)
+    int64_t wide = tiles;
+    int bbox = tn;
+    if (mixed) {
+        if (tn != TN || N % TN != 0) { rmn_set_error("tf32x3 gemm: mixed tiles need N to be a multiple of 256"); return RMN_ERR_PARAM; }
+        bbox = 128;
+        const int64_t rem = tiles % sms;
+        if (rem > 0 && 2 * rem <= sms) wide = tiles - rem;
+    }
+    const int64_t launched = wide + 2 * (tiles - wide);
+    dim3 grid((unsigned)(launched < sms ? launched : sms));    // persistent: one CTA per SM
     if (int rc = prepare_kernels()) return rc;
-    if (passes == 1) tf32x3_gemm_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn);
-    else tf32x3_gemm_kernel<3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn);
+    long long* dbg = g_dbg_stamp;
+    g_dbg_stamp = nullptr;
+    if (passes == 1) tf32x3_gemm_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn, bbox, wide, dbg);
+    else tf32x3_gemm_kernel<3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn, bbox, wide, dbg);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
@@ -263,6 +304,10 @@ int launch_plain(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int
 // 3-pass product with 128-column tiles (B maps built with box_rows = 128)
 int launch_plain_narrow(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, st, 3, 1, 0, 0, 128);
+}
+// 3-pass product, 128 x 256 tiles with the last partly filled round cut into 128 x 128 tiles (B maps: box_rows = 128)
+int launch_plain_mixed(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, st, 3, 1, 0, 0, TN, true);
 }
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, st, 1);
@@ -306,16 +351,19 @@ extern "C" int rmn_tf32x3_gemm_splitk(int64_t M, int N, int Kdim, int ksplit, co
     return tc::launch_plain_splitk(maps, M, N, Kdim, d_C, N, ksplit, (int64_t)M * N, used_splits, (cudaStream_t)stream, 3);
 }
 
-// Validation entry: C[M][N] (fp32, ld = N) ~= (Ah + Al)(Bh + Bl)^T; A* are [M][K], B* are [N][K], fp32, K % 32 == 0.
+// Validation entry: C[M][N] (fp32, ld = N) ~= (Ah + Al)(Bh + Bl)^T; A* are [M][K], B* are [N][K], fp32, K % 16 == 0.
+// N a multiple of 256 goes through the mixed tile list (the dense sampler's path), anything else through plain tiles.
 extern "C" int rmn_tf32x3_gemm(int64_t M, int N, int Kdim, const float* d_Ah, const float* d_Al, const float* d_Bh,
                                const float* d_Bl, float* d_C, void* stream) {
-    RMN_REQUIRE(M >= 1 && N >= 1 && Kdim >= 32 && Kdim % 32 == 0 && N % 4 == 0, "rmn_tf32x3_gemm: bad shape");
+    RMN_REQUIRE(M >= 1 && N >= 1 && Kdim >= 16 && Kdim % tc::TK3 == 0 && N % 4 == 0, "rmn_tf32x3_gemm: bad shape");
     RMN_REQUIRE(d_Ah && d_Al && d_Bh && d_Bl && d_C, "rmn_tf32x3_gemm: null pointer");
     tc::GemmMaps maps;
     int rc;
     if ((rc = tc::make_tmap_2d(&maps.ah, d_Ah, M, Kdim, Kdim, tc::TM, tc::TK3))) return rc;
     if ((rc = tc::make_tmap_2d(&maps.al, d_Al, M, Kdim, Kdim, tc::TM, tc::TK3))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, tc::TN, tc::TK3))) return rc;
-    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, tc::TN, tc::TK3))) return rc;
+    const bool mixed = N % tc::TN == 0;
+    if ((rc = tc::make_tmap_2d(&maps.bh, d_Bh, N, Kdim, Kdim, mixed ? 128 : tc::TN, tc::TK3))) return rc;
+    if ((rc = tc::make_tmap_2d(&maps.bl, d_Bl, N, Kdim, Kdim, mixed ? 128 : tc::TN, tc::TK3))) return rc;
+    if (mixed) return tc::launch_plain_mixed(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
     return tc::launch_plain(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
 }

@@ -14,7 +14,9 @@ def _split(x):
     return hi, (x - hi).astype(np.float32)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 256), (300, 512, 1024), (1000, 1024, 1024), (64, 96, 64)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 256), (300, 512, 1024), (1000, 1024, 1024), (64, 96, 64),
+                                   (4864, 1024, 48),     # 152 tiles of 128 x 256: 148 full ones + 4 cut into 8 halves
+                                   (19000, 256, 16)])    # 149 tiles, one k-block
 def test_tf32x3_gemm_matches_fp64(M, N, K):
     import torch
     from riemann_b200 import _lib
