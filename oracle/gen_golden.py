@@ -390,6 +390,10 @@ def _portmodel_through_reference(R, name, kind, seed):
         N, d, T, eps, nsteps = 500, 8, 300, 0.2, 3
     elif kind == "adapthmc4":                   # AdaptScaleHMC, 4 steps, d = 20 (the dense-in-d device path)
         N, d, T, eps, nsteps = 600, 20, 300, 0.1, 4
+    elif kind == "hmcmass3":                    # VanillaHMC with a (dense, fixed) mass matrix, hamiltonian.py:70-89
+        N, d, T, eps, nsteps = 500, 8, 300, 0.25, 3
+    elif kind == "adaptmalamass":               # AdaptScaleHMC, one step, mass matrix
+        N, d, T, eps, nsteps = 600, 20, 300, 0.3, 1
     else:
         N, d, T, eps = 400, 6, 300, 0.9
     X, y, theta_star, pv = port.make_logistic_problem(N, d, seed=port.SEED_BASE + 40 + d)
@@ -404,7 +408,22 @@ def _portmodel_through_reference(R, name, kind, seed):
 
     model = RefLogistic()
     track = False
-    if kind in ("mala", "hmc3"):
+    extra_m = {}
+    if kind in ("hmcmass3", "adaptmalamass"):
+        # a mass matrix of the posterior's scale: the Fisher information at theta_star plus the prior precision, mixed
+        # with a random SPD perturbation so that it is dense and not the exact metric
+        rng = np.random.RandomState(seed)
+        pstar = 1.0 / (1.0 + np.exp(-X.dot(theta_star)))
+        F = (X * (pstar * (1 - pstar))[:, None]).T.dot(X) + np.eye(d) / pv
+        A = rng.standard_normal((d, d))
+        M = F / np.mean(np.diag(F)) + 0.05 * A.dot(A.T) / d
+        extra_m = dict(M=M)
+        if kind == "hmcmass3":
+            prop = R.VanillaHMC(eps, nsteps, pmodel.grad_log_posterior, M=M)
+        else:
+            prop = R.AdaptScaleHMC(eps, nsteps, pmodel.grad_log_posterior, M=M)
+            track = True
+    elif kind in ("mala", "hmc3"):
         prop = R.VanillaHMC(eps, nsteps, pmodel.grad_log_posterior)     # reference proposal
     elif kind == "adapthmc4":
         prop = R.AdaptScaleHMC(eps, nsteps, pmodel.grad_log_posterior)
@@ -418,7 +437,7 @@ def _portmodel_through_reference(R, name, kind, seed):
         prop = RefMMALA()
     theta0 = theta_star + 0.05 * np.ones(d)
     _vector_fixture(R, name, model, prop, theta0, T, seed,
-                    extra=dict(X=X, y=y, prior_var=np.float64(pv), eps=np.float64(eps), nsteps=np.int64(nsteps)),
+                    extra=dict(X=X, y=y, prior_var=np.float64(pv), eps=np.float64(eps), nsteps=np.int64(nsteps), **extra_m),
                     track_scale=track)
 
 
@@ -443,6 +462,10 @@ def main():
     if "--only-n1-logistic" in sys.argv:
         _portmodel_through_reference(R, "hmc3_logistic", "hmc3", 503)
         _portmodel_through_reference(R, "adapthmc4_logistic", "adapthmc4", 504)
+        return
+    if "--only-mass-logistic" in sys.argv:
+        _portmodel_through_reference(R, "hmcmass3_logistic", "hmcmass3", 505)
+        _portmodel_through_reference(R, "adaptmalamass_logistic", "adaptmalamass", 506)
         return
     if "--only-n3-pt" in sys.argv:
         _n3_pt_fixtures(R)
@@ -529,6 +552,8 @@ def main():
     _portmodel_through_reference(R, "mmala_logistic", "mmala", 502)
     _portmodel_through_reference(R, "hmc3_logistic", "hmc3", 503)
     _portmodel_through_reference(R, "adapthmc4_logistic", "adapthmc4", 504)
+    _portmodel_through_reference(R, "hmcmass3_logistic", "hmcmass3", 505)
+    _portmodel_through_reference(R, "adaptmalamass_logistic", "adaptmalamass", 506)
 
 
 if __name__ == "__main__":

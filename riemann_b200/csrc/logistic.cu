@@ -104,7 +104,8 @@ struct LogisticState {
     double* scale; long long* nsamp; long long* nacc; long long* dacc;
     double* S1; double* S2;
     // random walk / pCN (randomwalk.py:12-26, 78-100): L = chol(C) and, for pCN, its inverse, d x d row-major
-    const double* PL; const double* PLinv;
+    const double* PL; const double* PLinv;     // RW / pCN: L and L^-1 of the proposal covariance; HMC with a mass matrix: chM, chM^-1
+    const double* Minv;                        // HMC with a mass matrix: M^-1 (NULL otherwise)
     double rho, rho_c;
     // mMALA
     double* Gm;      // [K][d][d]   metric of the pending proposal (likelihood part)
@@ -473,6 +474,30 @@ lg_leapfrog_mid_kernel(LogisticState st) {
     *th = *th + eps * p;
 }
 
+// The same step with a mass matrix: p <- p + eps g, theta <- theta + eps solve(M, p); one warp per chain.
+__global__ void __launch_bounds__(128)
+lg_leapfrog_mid_mass_kernel(LogisticState st) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.K) return;
+    const int d = st.d, dp = st.dp;
+    const double eps = st.epsrow[r];
+    double* th = st.Th + ((int64_t)(st.cur[r] ^ 1) * st.K + r) * dp;
+    double* p = st.Xi + r * dp;
+    for (int j = lane; j < d; j += 32) {
+        double g = 0.0;
+        for (int s = 0; s < st.nsplit; ++s) g += st.gpart[((int64_t)s * st.K + r) * dp + j];
+        g -= th[j] / st.pv;
+        p[j] = p[j] + eps * g;
+    }
+    __syncwarp();
+    for (int j = lane; j < d; j += 32) {
+        double sacc = 0.0;
+        for (int i = 0; i < d; ++i) sacc += st.Minv[(size_t)j * d + i] * p[i];
+        th[j] = th[j] + eps * sacc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // finish / propose, one warp per chain.
 // ---------------------------------------------------------------------------------------
@@ -570,8 +595,20 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             tt += th * th;
             if (!MMALA && sp.pkind == LG_HMC) {
                 const double p1 = xi[j] + 0.5 * eps * gp;                // final half step (hamiltonian.py:40); Xi holds p
-                k1 += p1 * p1;
+                if (st.Minv) st.Xi[r * dp + j] = (j < d) ? p1 : 0.0;     // staged for solve(chM, p) below
+                else k1 += p1 * p1;
             }
+        }
+        if (!MMALA && sp.pkind == LG_HMC && st.Minv) {
+            // kinetic energy in the mass metric: |solve(chM, p')|^2 (hamiltonian.py:86-89); PLinv = chM^-1, lower triangular
+            const double* v = st.Xi + r * dp;
+            __syncwarp();
+            for (int j = lane; j < d; j += 32) {
+                double sacc = 0.0;
+                for (int i = 0; i <= j; ++i) sacc += st.PLinv[(size_t)j * d + i] * v[i];
+                k1 += sacc * sacc;
+            }
+            __syncwarp();
         }
         if (!MMALA && sp.pkind == LG_PCN) {
             // u_rev = (rho_c L)^-1 (theta - rho theta')  (randomwalk.py:95,98); |u_fwd|^2 = |xi|^2 = k0
@@ -684,8 +721,8 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             if (want_trace && j < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j] = tv;
             if (!sp.propose) continue;
             k0 += xi[q] * xi[q];
-            if (!MMALA && sp.pkind != LG_HMC) {
-                xo[j] = xi[q];     // staged for the L xi product below
+            if (!MMALA && (sp.pkind != LG_HMC || st.Minv)) {
+                xo[j] = xi[q];     // staged for the L xi (chM xi) product below
             } else if (!MMALA) {
                 const double ph = xi[q] + 0.5 * eps * gr[j];             // hamiltonian.py:27
                 thn[j] = tv + eps * ph;                                  // :30
@@ -705,6 +742,34 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             if (j < d)
                 for (int i = 0; i <= j; ++i) sacc += st.PL[(size_t)j * d + i] * xo[i];
             thn[j] = (j < d) ? a0 * th[j] + a1 * sacc : 0.0;
+        }
+    }
+    if (!MMALA && sp.propose && sp.pkind == LG_HMC && st.Minv) {
+        // VanillaHMC with a mass matrix (hamiltonian.py:79-88, leapfrog :26-30):
+        //   p0 = chM xi,  k0 = |solve(chM, p0)|^2,  p_half = p0 + eps/2 grad,  theta' = theta + eps solve(M, p_half)
+        // staged through the chain's own rows: xi in Xi, p0 in the proposal slot, then p_half in Xi
+        __syncwarp();
+        for (int j = lane; j < dp; j += 32) {
+            double sacc = 0.0;
+            if (j < d)
+                for (int i = 0; i <= j; ++i) sacc += st.PL[(size_t)j * d + i] * xo[i];
+            thn[j] = sacc;
+        }
+        __syncwarp();
+        k0 = 0.0;
+        for (int j = lane; j < dp; j += 32) {
+            double sacc = 0.0;
+            if (j < d)
+                for (int i = 0; i <= j; ++i) sacc += st.PLinv[(size_t)j * d + i] * thn[i];
+            k0 += sacc * sacc;
+            xo[j] = (j < d) ? thn[j] + 0.5 * eps * gr[j] : 0.0;          // the momentum rides in Xi through the trajectory
+        }
+        __syncwarp();
+        for (int j = lane; j < dp; j += 32) {
+            double sacc = 0.0;
+            if (j < d)
+                for (int i = 0; i < d; ++i) sacc += st.Minv[(size_t)j * d + i] * xo[i];
+            thn[j] = (j < d) ? th[j] + eps * sacc : 0.0;
         }
     }
     if (MMALA && sp.propose) {
@@ -865,12 +930,12 @@ struct LogisticSampler : SamplerImpl {
     // RMN_PREC_TF32X3: the fused sweep (logistic_fused.cu) covers every d this family supports (d <= 128)
     bool fused = false;
     int pkind = LG_HMC;
-    double* d_PL = nullptr; double* d_PLinv = nullptr;
+    double* d_PL = nullptr; double* d_PLinv = nullptr; double* d_Minv = nullptr;
     lgf::Geometry fg{};
     lgf::Maps fmaps{};
     float* fXh = nullptr; float* fXl = nullptr; uint32_t* fys = nullptr; double* fllp = nullptr; float* fgp = nullptr;
     RowComm rowc;               // row-sharded data mode: the ranks that hold the other slices of X
-    ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); cudaFree(d_PL); cudaFree(d_PLinv); }
+    ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); cudaFree(d_PL); cudaFree(d_PLinv); cudaFree(d_Minv); }
     int set_row_comm(const void* id, size_t nbytes, int rank, int world) override {
         if (tcx3 || tf32m) {
             rmn_set_error("row-sharded data mode runs in f64 precision");
@@ -975,6 +1040,17 @@ struct LogisticSampler : SamplerImpl {
                 st.PLinv = d_PLinv;
                 st.rho = pr->rho; st.rho_c = sqrt(1.0 - pr->rho * pr->rho);     // randomwalk.py:85
             }
+        }
+        if (pkind == LG_HMC && s->prop->has_mass) {
+            const rmn_proposal* pr = s->prop;
+            const size_t nb = (size_t)st.d * st.d * 8;
+            RMN_CUDA(cudaMalloc(&d_PL, nb));
+            RMN_CUDA(cudaMemcpy(d_PL, pr->h_chM.data(), nb, cudaMemcpyHostToDevice));
+            RMN_CUDA(cudaMalloc(&d_PLinv, nb));
+            RMN_CUDA(cudaMemcpy(d_PLinv, pr->h_chMinv.data(), nb, cudaMemcpyHostToDevice));
+            RMN_CUDA(cudaMalloc(&d_Minv, nb));
+            RMN_CUDA(cudaMemcpy(d_Minv, pr->h_Minv.data(), nb, cudaMemcpyHostToDevice));
+            st.PL = d_PL; st.PLinv = d_PLinv; st.Minv = d_Minv;
         }
         if (int rc = lg_tables_ready()) return rc;
         if (fused) {
@@ -1107,7 +1183,8 @@ struct LogisticSampler : SamplerImpl {
                 // Nsteps - 1 interior leapfrog steps: each one a full likelihood sweep at the new trajectory point
                 for (int l = 1; l < pr->nsteps; ++l) {
                     const int64_t n = st.K * st.dp;
-                    lg_leapfrog_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fst());
+                    if (st.Minv) lg_leapfrog_mid_mass_kernel<<<row_grid(), 128, 0, stream>>>(fst());
+                    else lg_leapfrog_mid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(fst());
                     RMN_KERNEL_CHECK(); launches++;
                     if (int rc = eval(-1, stream)) return rc;
                 }
@@ -1159,11 +1236,11 @@ SamplerImpl* make_logistic_sampler(rmn_sampler* s) {
         }
         return new LogisticSampler(s);
     }
-    if (p->kind == RMN_PROP_HMC && !p->has_mass) return new LogisticSampler(s);
+    if (p->kind == RMN_PROP_HMC && !p->acov) return new LogisticSampler(s);           // VanillaHMC / AdaptScaleHMC, with or without M
     if (p->kind == RMN_PROP_RW && !p->acov) return new LogisticSampler(s);            // MetropolisRandomWalk / AdaptScaleRandomWalk
     if (p->kind == RMN_PROP_PCN && !p->adapt) return new LogisticSampler(s);          // pCN (AdaptScalepCN: small-d family only)
     rmn_set_error("logistic model: device kernels exist for MetropolisRandomWalk / AdaptScaleRandomWalk, pCN, VanillaHMC / "
-                  "AdaptScaleHMC without a mass matrix (Nsteps = 1 is MALA) and SimplifiedMMALA");
+                  "AdaptScaleHMC (Nsteps = 1 is MALA; fixed mass matrix or none) and SimplifiedMMALA");
     return nullptr;
 }
 

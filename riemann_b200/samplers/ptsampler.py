@@ -133,4 +133,25 @@ class PTSampler(object):
         return [s.current_state() for s in self.samplers]
 
     def diagnostics(self, allreduce=True):
-        return self._sampler.diagnostics(allreduce=allreduce)
+        """Posterior summaries of the beta = betas[0] chains ONLY (one per ladder): the device accumulators hold every
+        rung of every ladder, and pooling the tempered rungs (beta < 1) would inflate the variance.  Built from the
+        per-chain moments (`Sampler.chain_moments`), rank-local (`allreduce` is accepted for interface symmetry:
+        ladders on other ranks are independent replicas, combine their summaries on the host if needed).
+        `accept_rate` is that of the flat engine -- accepted within-chain moves per chain-step over all temperatures,
+        a swap step counting as no move -- and is reported as `accept_rate_all_rungs`; `swap_fraction` = Pswap."""
+        from ..distributed import summarize_block
+        flat = self._sampler.diagnostics(allreduce=False)
+        m, v = self._sampler.chain_moments()                      # [nd, K * Nt], chain fastest
+        m0, v0 = m[:, ::self.Nt], v[:, ::self.Nt]                 # rung 0 of every ladder
+        nd = m0.shape[0]
+        blk = np.zeros(6 + 3 * nd)
+        blk[0], blk[1], blk[4] = self.K, flat["samples"], flat["steps"]
+        blk[6:6 + nd] = m0.sum(axis=1)
+        blk[6 + nd:6 + 2 * nd] = (m0 * m0).sum(axis=1)
+        blk[6 + 2 * nd:] = v0.sum(axis=1)
+        out = summarize_block(blk)
+        out.pop("accept_rate", None)
+        out["accept_rate_all_rungs"] = flat["accept_rate"]
+        out["swap_fraction"] = float(self.Pswap)
+        out["temperatures"] = self.Nt
+        return out

@@ -53,7 +53,9 @@ def test_extreme_logits_are_stable():
 
 @pytest.mark.parametrize("name,tol", [("mala_logistic", 1e-9), ("mmala_logistic", 1e-8),
                                       # "next" row N1 on this family: the reference's leapfrog with Nsteps > 1
-                                      ("hmc3_logistic", 1e-9), ("adapthmc4_logistic", 1e-9)])
+                                      ("hmc3_logistic", 1e-9), ("adapthmc4_logistic", 1e-9),
+                                      # ... and with a fixed dense mass matrix (hamiltonian.py:70-89)
+                                      ("hmcmass3_logistic", 1e-9), ("adaptmalamass_logistic", 1e-9)])
 def test_injected_chain_matches_fixture(golden, name, tol):
     from riemann_b200 import Sampler
     from riemann_b200.proposals.hamiltonian import MALA, SimplifiedMMALA, VanillaHMC, AdaptScaleHMC
@@ -65,6 +67,10 @@ def test_injected_chain_matches_fixture(golden, name, tol):
         p = VanillaHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior)
     elif name == "adapthmc4_logistic":
         p = AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior)
+    elif name == "hmcmass3_logistic":
+        p = VanillaHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior, M=g["M"])
+    elif name == "adaptmalamass_logistic":
+        p = AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), dm.grad_log_posterior, M=g["M"])
     else:
         p = SimplifiedMMALA(float(g["eps"]), dm)
     s = Sampler(dm, p, g["thetas"][0])

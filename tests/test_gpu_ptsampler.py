@@ -122,3 +122,22 @@ def test_philox_ladder_with_pcn():
     for i, beta in enumerate(pt.betas):
         assert stats.kstest(th[:, i, 0] * np.sqrt(beta), "norm").pvalue > 1e-3
         assert stats.kstest((th[:, i, 0] + th[:, i, 1]) * np.sqrt(beta / 3.8), "norm").pvalue > 1e-3
+
+
+def test_diagnostics_use_the_base_temperature_only():
+    """PTSampler.diagnostics(): mean / variance of the beta = 1 chains (one per ladder), not of all rungs pooled.
+    benchmark_gauss2d_corr has unit marginal variances; the tempered rungs have 1 / beta."""
+    from riemann_b200 import PTSampler
+    from riemann_b200.models import benchmarks
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    pt = PTSampler(benchmarks.benchmark_gauss2d_corr, MetropolisRandomWalk(0.5 * np.eye(2)), np.ones(2), K=2048, seed=4)
+    pt.run(500, trace=False)
+    pt._sampler.reset_diagnostics()
+    pt.run(3000, trace=False)
+    dg = pt.diagnostics()
+    flat = pt._sampler.diagnostics(allreduce=False)
+    assert dg["chains"] == 2048 and dg["temperatures"] == 5
+    assert np.all(np.abs(dg["var"][:2] - 1.0) < 0.06), dg["var"]
+    assert np.all(np.abs(dg["mean"][:2]) < 0.05), dg["mean"]
+    assert np.all(flat["var"][:2] > 3.0)                     # pooled over beta = 1 .. 1/16: (1+2+4+8+16)/5 = 6.2
+    assert 0.0 < dg["accept_rate_all_rungs"] < 1.0 and dg["swap_fraction"] == 0.1

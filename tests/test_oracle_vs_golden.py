@@ -115,7 +115,8 @@ def test_pcn(golden, name, d):
     _replay(g, _gauss(g, d), port.pCN(g["C0"], float(g["rho"])), g["thetas"][0])
 
 
-@pytest.mark.parametrize("name", ["mala_logistic", "mmala_logistic", "hmc3_logistic", "adapthmc4_logistic"])
+@pytest.mark.parametrize("name", ["mala_logistic", "mmala_logistic", "hmc3_logistic", "adapthmc4_logistic",
+                                  "hmcmass3_logistic", "adaptmalamass_logistic"])
 def test_logistic(golden, name):
     """Port model (+ port mMALA) were driven through the REFERENCE Sampler/VanillaHMC/AdaptScaleHMC."""
     g = golden(name)
@@ -126,6 +127,10 @@ def test_logistic(golden, name):
         prop = port.VanillaHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_posterior)
     elif name == "adapthmc4_logistic":
         prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_posterior)
+    elif name == "hmcmass3_logistic":           # fixed dense mass matrix, hamiltonian.py:70-89
+        prop = port.VanillaHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_posterior, M=g["M"])
+    elif name == "adaptmalamass_logistic":
+        prop = port.AdaptScaleHMC(float(g["eps"]), int(g["nsteps"]), m.grad_log_posterior, M=g["M"])
     else:
         prop = port.SimplifiedMMALA(float(g["eps"]), m)
     _replay(g, m, prop, g["thetas"][0])
