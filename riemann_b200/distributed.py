@@ -52,9 +52,10 @@ def reduce_block(blk):
     """Sum a diagnostics block over ranks (no-op without an initialised process group)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        same = blk[[1, 4]].clone()
         dist.all_reduce(blk, op=dist.ReduceOp.SUM)
-        blk[[1, 4]] = same        # samples / steps per chain are identical on every rank, not additive
+        # entries 1 and 4 (samples / steps per chain) are identical on every rank, not additive: undo the sum with ONE
+        # strided in-place division (exact: W n / W == n in fp64) instead of index gathers / puts with host-built indices
+        blk[1:5:3].div_(float(dist.get_world_size()))
     return blk
 
 
