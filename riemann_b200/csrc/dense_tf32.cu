@@ -68,7 +68,18 @@ struct TStep {
     double* tr_theta; double* tr_logpost; double* tr_prop_lp; uint8_t* tr_acc; double* tr_lqr; double* tr_prop_theta;
 };
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// streaming loads of the row pass: L2 only (ld.global.cg).  Next to the GEMM's CTA (218 KB of shared memory) the SM keeps
+// ~28 KB of L1, less than the pass's loads in flight; lines allocated there only throttle the load pipe.
+#ifndef RMN_TF32_FP_LDCG
+#define RMN_TF32_FP_LDCG 1
+#endif
+__device__ __forceinline__ float4 ldg4(const float* p) {
+#if RMN_TF32_FP_LDCG
+    return __ldcg(reinterpret_cast<const float4*>(p));
+#else
+    return *reinterpret_cast<const float4*>(p);
+#endif
+}
 
 // One warp per chain row.  128-thread blocks inside a 48-register budget: next to the GEMM's persistent CTA (384 threads x
 // 56 registers, all of the shared memory) an SM still takes 7 of these blocks, which is what lets the pass of one

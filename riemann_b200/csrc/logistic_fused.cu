@@ -39,6 +39,7 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "logistic_fused.cuh"
+#include <stdlib.h>
 
 namespace lgf {
 using namespace tc;
@@ -476,7 +477,11 @@ int dp32_of(int d) { return d <= 64 ? 64 : 128; }
 
 void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
     g->dp32 = dp32_of(d);
-    g->ldx = (d + 3) / 4 * 4;
+    g->ldx = (d + 7) / 8 * 8;                  // rows start on 32-byte sectors
+    if (const char* e = getenv("RMN_LGF_PADX")) {   // A/B: 1 = rows padded to the tile width, 2 = 16-byte granularity
+        if (e[0] == '1') g->ldx = g->dp32;
+        if (e[0] == '2') g->ldx = (d + 3) / 4 * 4;
+    }
     g->tiles_total = (N + NT - 1) / NT;
     g->nys = g->tiles_total * NT;
     g->nblk = (int)((K + CB - 1) / CB);

@@ -8,8 +8,8 @@ namespace lgf {
 
 struct Geometry {
     int dp32;              // columns of the operand tiles: 64 (d <= 64) or 128 (d <= 128)
-    int ldx;               // row pitch of the split X copies in floats: d rounded up to 4 (16-byte rows for TMA); the
-                           // columns from ldx to dp32 are never stored nor read -- TMA zero-fills them in the tile
+    int ldx;               // row pitch of the split X copies in floats: d rounded up to 8 (rows start on 32-byte sectors);
+                           // the columns from ldx to dp32 are never stored nor read -- TMA zero-fills them in the tile
     int nblk;              // chain blocks of 128
     int ns;                // row splits (grid = nblk x ns)
     int tps;               // 64-row tiles per split
