@@ -346,6 +346,10 @@ int rmn_tf32x3_gemm_splitk(int64_t M, int N, int K, int ksplit, const float* d_A
  * B [N][K] fp32 (the tensor core drops the low 13 mantissa bits of each operand); K % 32 == 0, N % 4 == 0.
  * It is the GEMM behind RMN_PREC_TF32_METRIC. */
 int rmn_tf32_gemm(int64_t M, int N, int K, const float* d_A, const float* d_B, float* d_C, void* stream);
+/* The same kernel with bf16 operands (tcgen05.mma.kind::f16, fp32 accumulate): C[M][N] (fp32) = A B^T, A [M][K] and
+ * B [N][K] bf16 row-major; K % 64 == 0, N % 4 == 0.  Used for the Fisher metric of the mMALA proposal in the tf32x3
+ * precision mode (a product that only shapes a proposal; the reference has no counterpart). */
+int rmn_bf16_gemm(int64_t M, int N, int K, const void* d_A, const void* d_B, float* d_C, void* stream);
 
 /* The logistic likelihood's pointwise stage (riemann_b200/csrc/logistic_math.cuh), validation entry:
  * p[i] = sigmoid(z[i]), sp[i] = softplus(z[i]), pq[i] = p (1 - p), fp64, |error| <~ 2e-16 absolute. */

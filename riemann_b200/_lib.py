@@ -95,6 +95,7 @@ SIGNATURES = {
     "rmn_rng_draws": (_I, [C.c_uint64, _L, _L, _L, _I, _P, _P, _P]),
     "rmn_tf32x3_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "rmn_tf32_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P]),
+    "rmn_bf16_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P]),
     "rmn_tf32x3_gemm_splitk": (_I, [_L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "rmn_logistic_math": (_I, [_L, _P, _P, _P, _P, _P]),
 }

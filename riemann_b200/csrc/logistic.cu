@@ -36,6 +36,7 @@
 // R never touch HBM.  The log-likelihood is a deterministic function of theta within the budget of
 // riemann_b200/budgets.py; the accept test, prior, proposal arithmetic and Cholesky stay fp64.
 #include <algorithm>
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "logistic_math.cuh"
@@ -45,6 +46,7 @@
 
 namespace tc {
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+int launch_plain_bf16(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 }
 
 namespace {
@@ -117,6 +119,7 @@ struct LogisticState {
     float* KR;       // [NP][Npad]   x_ia x_ib for a >= b, pair index a(a+1)/2 + b
     float* Gp;       // [K][NP]      packed lower triangle of the metric (likelihood part)
     int64_t Npad; int NP;
+    int kr_bf16;     // W and KR are bf16 arrays (tf32x3 mode: the metric GEMM runs as kind::f16)
 };
 
 // likelihood part of the metric entry (a, b) of chain r, from whichever representation is live
@@ -431,7 +434,9 @@ lg_build_kr_kernel(LogisticState st) {
     for (int pr = warp; pr < npair; pr += nw) {
         while (pr >= base + a + 1) { base += a + 1; ++a; }
         const int b = pr - base;
-        st.KR[(int64_t)pr * st.Npad + i0 + lane] = (float)(xr[a] * xr[b]);
+        const float v = (float)(xr[a] * xr[b]);
+        if (st.kr_bf16) reinterpret_cast<__nv_bfloat16*>(st.KR)[(int64_t)pr * st.Npad + i0 + lane] = __float2bfloat16_rn(v);
+        else st.KR[(int64_t)pr * st.Npad + i0 + lane] = v;
     }
 }
 
@@ -925,6 +930,7 @@ struct LogisticSampler : SamplerImpl {
     LogisticState st{};
     bool mmala;
     bool tf32m;                 // tcgen05 metric GEMM instead of lg_metric_kernel (TF32_METRIC and TF32X3)
+    bool bf16m = false;         // ... with bf16 operands (TF32X3)
     bool tcx3;                  // RMN_PREC_TF32X3: the likelihood sweep on tcgen05 (fused kernel, logistic_fused.cu)
     tc::GemmMaps maps;          // metric GEMM
     // RMN_PREC_TF32X3: the fused sweep (logistic_fused.cu) covers every d this family supports (d <= 128)
@@ -960,7 +966,12 @@ struct LogisticSampler : SamplerImpl {
         pkind = (s->prop->kind == RMN_PROP_RW) ? LG_RW : ((s->prop->kind == RMN_PROP_PCN) ? LG_PCN : LG_HMC);
         tcx3 = s->precision == RMN_PREC_TF32X3;
         tf32m = mmala && (s->precision == RMN_PREC_TF32_METRIC || tcx3);
-        if (tf32m || tcx3) st.Npad = (st.N + 31) / 32 * 32;
+        // tf32x3: the fused sweep hands p(1-p) over as bf16 and the metric GEMM contracts bf16 operands (k-blocks of 64
+        // rows); RMN_MMALA_BF16=0 keeps the single-pass TF32 product of the tf32-metric mode
+        bf16m = mmala && tcx3;
+        if (const char* e = getenv("RMN_MMALA_BF16")) bf16m = bf16m && !(e[0] == '0');
+        st.kr_bf16 = bf16m ? 1 : 0;
+        if (tf32m || tcx3) st.Npad = bf16m ? (st.N + 63) / 64 * 64 : (st.N + 31) / 32 * 32;
         if (tf32m) st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
         if (tcx3) {
             fused = lgf::supported(st.d);
@@ -975,8 +986,8 @@ struct LogisticSampler : SamplerImpl {
             default: return align256((size_t)fg.ns * st.K * fg.dp32 * 4);
         }
     }
-    size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * 4); }
-    size_t w_bytes() const { return align256((size_t)st.K * st.Npad * 4); }
+    size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * (bf16m ? 2 : 4)); }
+    size_t w_bytes() const { return align256((size_t)st.K * st.Npad * (bf16m ? 2 : 4)); }
     size_t gp_bytes() const { return align256((size_t)st.K * st.NP * 4); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 8); }
     size_t eval_smem() const { return eval_smem_bytes(st.ldt); }
@@ -1061,8 +1072,13 @@ struct LogisticSampler : SamplerImpl {
             const size_t ksm = (size_t)32 * (st.d + 1) * 8;
             lg_build_kr_kernel<<<(unsigned)(st.Npad / 32), 256, ksm>>>(st);
             RMN_KERNEL_CHECK();
-            if (int rc = tc::make_tmap_2d(&maps.ah, st.W, (uint64_t)st.K, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TM)) return rc;
-            if (int rc = tc::make_tmap_2d(&maps.bh, st.KR, (uint64_t)st.NP, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TN)) return rc;
+            if (bf16m) {
+                if (int rc = tc::make_tmap_2d_bf16(&maps.ah, st.W, (uint64_t)st.K, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TM)) return rc;
+                if (int rc = tc::make_tmap_2d_bf16(&maps.bh, st.KR, (uint64_t)st.NP, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TN)) return rc;
+            } else {
+                if (int rc = tc::make_tmap_2d(&maps.ah, st.W, (uint64_t)st.K, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TM)) return rc;
+                if (int rc = tc::make_tmap_2d(&maps.bh, st.KR, (uint64_t)st.NP, (uint64_t)st.Npad, (uint64_t)st.Npad, tc::TN)) return rc;
+            }
             maps.al = maps.ah; maps.bl = maps.bh;
         }
         RMN_RAISE_SMEM(lg_eval_kernel, (int)eval_smem());
@@ -1084,7 +1100,7 @@ struct LogisticSampler : SamplerImpl {
         lgf::SweepArgs a{};
         a.ys = fys; a.Th = st.Th; a.cur = st.cur; a.fixed_slot = fixed_slot;
         a.K = st.K; a.N = st.N; a.d = st.d; a.dp = st.dp;
-        a.llp = fllp; a.gp = fgp; a.W = st.W; a.ldw = st.Npad;
+        a.llp = fllp; a.gp = fgp; a.W = st.W; a.ldw = st.Npad; a.w_bf16 = bf16m ? 1 : 0;
         static long long* d_tl = nullptr;                          // RMN_LGF_TIMELINE=1: clock64 stamps of CTA 0 (debug aid)
         if (const char* e = getenv("RMN_LGF_TIMELINE")) {
             if (e[0] == '1' && !d_tl) { cudaMalloc(&d_tl, 256 * 8 * 8); }
@@ -1109,7 +1125,8 @@ struct LogisticSampler : SamplerImpl {
         if (tcx3) {
             if (int rc = eval_fused(fixed_slot, stream)) return rc;
             if (tf32m) {
-                if (int rc = tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
+                if (int rc = bf16m ? tc::launch_plain_bf16(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)
+                                   : tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
                 launches++;
             }
             return RMN_OK;

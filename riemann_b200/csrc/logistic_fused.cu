@@ -38,6 +38,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include <cuda_bf16.h>
 #include "logistic_fused.cuh"
 #include <stdlib.h>
 
@@ -385,9 +386,22 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             if (dbgp) a.dbg[t * 8 + 6] = clock64();
             tmem_st_32x16(tz, rr);
             if (HASW && okc && row0 < a.ldw) {                       // ldw is a multiple of 32, row0 of 16
+                if (a.w_bf16) {
+                    __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(a.W) + (okc ? c : 0) * a.ldw + row0;
+                    uint32_t pk[PCOLS / 2];
 #pragma unroll
-                for (int e = 0; e < PCOLS; e += 4)
-                    *reinterpret_cast<float4*>(wrow + row0 + e) = make_float4(wv[e], wv[e + 1], wv[e + 2], wv[e + 3]);
+                    for (int e = 0; e < PCOLS; e += 2) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(wv[e], wv[e + 1]);
+                        pk[e / 2] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+#pragma unroll
+                    for (int e = 0; e < PCOLS / 2; e += 4)
+                        *reinterpret_cast<uint4*>(wb + 2 * e) = make_uint4(pk[e], pk[e + 1], pk[e + 2], pk[e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < PCOLS; e += 4)
+                        *reinterpret_cast<float4*>(wrow + row0 + e) = make_float4(wv[e], wv[e + 1], wv[e + 2], wv[e + 3]);
+                }
             }
             tmem_st_wait();
             tc_fence_before();

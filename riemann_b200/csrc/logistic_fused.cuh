@@ -31,7 +31,8 @@ struct SweepArgs {
     double* llp;           // [LLP_PER_SPLIT ns][K]  log-likelihood partial sums (one per pointwise warpgroup and split)
     float* gp;             // [ns][K][dp32]  gradient partial sums
     float* W;              // [K][ldw] p (1 - p), or NULL
-    int64_t ldw;
+    int64_t ldw;           // (elements; a multiple of 64)
+    int w_bf16;            // W points to bf16 storage (round to nearest): the operand of the bf16 metric GEMM
     long long* dbg;        // optional timeline of CTA 0 (clock64 stamps, RMN_LGF_TIMELINE=1; scripts/lgf_timeline.py), else NULL
     int nblk, tps;         // filled by sweep()
     int64_t tiles_total;

@@ -43,6 +43,20 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t co
     return RMN_OK;
 }
 
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { rmn_set_error("cuTensorMapEncodeTiled not available from the driver"); return RMN_ERR_CUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { rmn_set_error("cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r); return RMN_ERR_CUDA; }
+    return RMN_OK;
+}
+
 // Persistent kernel: gridDim.x CTAs (one per SM) walk the tile list  tile = blockIdx.x + i * gridDim.x,
 // tile -> (m_tile, n_tile) with n fastest, so concurrently running CTAs share the same rows of A in L2.
 // Three independent pipelines (Blackwell canonical form):
@@ -59,7 +73,9 @@ int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t co
 #ifndef RMN_TC_MINB
 #define RMN_TC_MINB 3
 #endif
-template <int PASSES>
+// BF16 (PASSES = 1 only): the operands are bf16 [rows][64] k-blocks and the instruction is kind::f16 -- twice the
+//             contraction depth per 128-byte row and per MMA, for products that only shape a proposal.
+template <int PASSES, bool BF16 = false>
 __global__ void __launch_bounds__(THREADS, RMN_TC_MINB)
 tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int Kdim, float* __restrict__ C,
                    int ldc, int ksplit, int kb_per, int64_t split_stride, int m_fastest, int tn, int bbox,
@@ -80,8 +96,10 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
     // (m_tile, n_tile, split) and split s stores its partial product at C + s * split_stride (summed by
     // the caller) -- this is how a product with few output tiles but a long contraction (the logistic
     // gradient R X: K x d output, N data rows deep) still fills all SMs.
-    constexpr int TK = (PASSES == 1) ? tc::TK : tc::TK3;               // fp32 per k-block
-    constexpr int ROWB = TK * 4;                                       // bytes per tile row = swizzle span
+    static_assert(!BF16 || PASSES == 1, "the bf16 operands have no split form");
+    constexpr int TK = BF16 ? 64 : ((PASSES == 1) ? tc::TK : tc::TK3);  // elements per k-block
+    constexpr int UK = BF16 ? 16 : tc::UK;                              // contraction depth of one MMA
+    constexpr int ROWB = TK * (BF16 ? 2 : 4);                           // bytes per tile row = swizzle span
     constexpr int A_BYTES = TM * ROWB, B_BYTES = TN * ROWB;
     constexpr int STAGE_BYTES = (PASSES == 1) ? (A_BYTES + B_BYTES) : 2 * (A_BYTES + B_BYTES);
     constexpr int STAGES = (tc::STAGES * tc::STAGE_BYTES) / STAGE_BYTES;   // 4 x 48 KB (or 2 x 96 KB with TK3 = 32)
@@ -160,7 +178,8 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
             const uint32_t tacc = tmem_base + (uint32_t)(a * TN);
             int64_t wt; int noff, w;
             decode(tile, wt, noff, w);
-            const uint32_t idesc = umma_idesc_tf32(TM, (N >= tn) ? w : ((N + 15) / 16 * 16));
+            const int n_eff = (N >= tn) ? w : ((N + 15) / 16 * 16);
+            const uint32_t idesc = BF16 ? umma_idesc_bf16(TM, n_eff) : umma_idesc_tf32(TM, n_eff);
             const int kb0 = (int)(wt / mn_tiles) * kb_per;
             const int kb1 = min(KB_all, kb0 + kb_per);
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -174,8 +193,9 @@ tf32x3_gemm_kernel(const __grid_constant__ GemmMaps maps, int64_t M, int N, int 
                 const uint64_t dbl = umma_desc_kmajor<ROWB>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int k = 0; k < TK / UK; ++k) {
-                    const uint64_t adv = (uint64_t)((k * UK * 4) >> 4);   // +32 bytes per K step, 16-byte units
-                    umma_tf32(tacc, dah + adv, dbh + adv, idesc, ((kb - kb0) | k) != 0);
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);       // +32 bytes per K step, 16-byte units
+                    if (BF16) umma_bf16(tacc, dah + adv, dbh + adv, idesc, ((kb - kb0) | k) != 0);
+                    else umma_tf32(tacc, dah + adv, dbh + adv, idesc, ((kb - kb0) | k) != 0);
                     if (PASSES == 3) {
                         umma_tf32(tacc, dah + adv, dbl + adv, idesc, 1);
                         umma_tf32(tacc, dal + adv, dbh + adv, idesc, 1);
@@ -256,6 +276,7 @@ int prepare_kernels() {
     if (!attr) {
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        RMN_CUDA(cudaFuncSetAttribute(tf32x3_gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
     return RMN_OK;
@@ -263,9 +284,10 @@ int prepare_kernels() {
 
 static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc,
                          cudaStream_t st, int passes = 3, int ksplit = 1, int64_t split_stride = 0, int m_fastest = 0,
-                         int tn = TN, bool mixed = false) {
+                         int tn = TN, bool mixed = false, bool bf16 = false) {
     if (tn != TN && tn != 128) { rmn_set_error("tf32x3 gemm: tile width must be 256 or 128"); return RMN_ERR_PARAM; }
-    const int tk = (passes == 1) ? TK : TK3;                           // k-block of the kernel variant
+    const int tk = bf16 ? 64 : ((passes == 1) ? TK : TK3);              // k-block of the kernel variant (elements)
+    if (bf16 && passes != 1) { rmn_set_error("tf32x3 gemm: bf16 operands are single pass"); return RMN_ERR_PARAM; }
     if (Kdim % tk != 0 || ldc % 4 != 0) { rmn_set_error("tf32x3 gemm: K must be a multiple of the k-block (%d), ld of 4", tk); return RMN_ERR_PARAM; }
     if (ksplit < 1 || ksplit > Kdim / tk) { rmn_set_error("tf32x3 gemm: bad ksplit"); return RMN_ERR_PARAM; }
     // every split must own at least one k-block (an empty range would leave its accumulator unwritten)
@@ -292,7 +314,8 @@ static int launch_common(const GemmMaps& maps, int64_t M, int N, int Kdim, float
     if (int rc = prepare_kernels()) return rc;
     long long* dbg = g_dbg_stamp;
     g_dbg_stamp = nullptr;
-    if (passes == 1) tf32x3_gemm_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn, bbox, wide, dbg);
+    if (bf16) tf32x3_gemm_kernel<1, true><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn, bbox, wide, dbg);
+    else if (passes == 1) tf32x3_gemm_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn, bbox, wide, dbg);
     else tf32x3_gemm_kernel<3><<<grid, THREADS, SMEM_BYTES, st>>>(maps, M, N, Kdim, C, ldc, ksplit, kbp, split_stride, m_fastest, tn, bbox, wide, dbg);
     RMN_KERNEL_CHECK();
     return RMN_OK;
@@ -311,6 +334,10 @@ int launch_plain_mixed(const GemmMaps& maps, int64_t M, int N, int Kdim, float* 
 }
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, st, 1);
+}
+// single pass with bf16 operands (maps.ah / maps.bh from make_tmap_2d_bf16), fp32 accumulate and output
+int launch_plain_bf16(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, st, 1, 1, 0, 0, TN, false, true);
 }
 // 3-pass product with the contraction split into `ksplit` ranges; returns the number of splits actually
 // used through *used (<= ksplit); partial s is at C + s * split_stride
@@ -334,6 +361,18 @@ extern "C" int rmn_tf32_gemm(int64_t M, int N, int Kdim, const float* d_A, const
     if ((rc = tc::make_tmap_2d(&maps.bh, d_B, N, Kdim, Kdim, tc::TN))) return rc;
     maps.al = maps.ah; maps.bl = maps.bh;
     return tc::launch_plain_tf32(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
+}
+
+// Validation entry of the bf16 mode: C[M][N] (fp32, ld = N) = A B^T with bf16 operands A [M][K], B [N][K]; K % 64 == 0.
+extern "C" int rmn_bf16_gemm(int64_t M, int N, int Kdim, const void* d_A, const void* d_B, float* d_C, void* stream) {
+    RMN_REQUIRE(M >= 1 && N >= 1 && Kdim >= 64 && Kdim % 64 == 0 && N % 4 == 0, "rmn_bf16_gemm: bad shape");
+    RMN_REQUIRE(d_A && d_B && d_C, "rmn_bf16_gemm: null pointer");
+    tc::GemmMaps maps;
+    int rc;
+    if ((rc = tc::make_tmap_2d_bf16(&maps.ah, d_A, M, Kdim, Kdim, tc::TM))) return rc;
+    if ((rc = tc::make_tmap_2d_bf16(&maps.bh, d_B, N, Kdim, Kdim, tc::TN))) return rc;
+    maps.al = maps.ah; maps.bl = maps.bh;
+    return tc::launch_plain_bf16(maps, M, N, Kdim, d_C, N, (cudaStream_t)stream);
 }
 
 // Validation entry of the split-K mode: C[ksplit][M][N] partial products (the caller sums them).

@@ -102,6 +102,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 with bf16 operands, fp32 accumulate (K = 16 per instruction): the proposal-only Fisher-metric GEMM
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -152,6 +165,8 @@ struct GemmMaps {
     CUtensorMap ah, al, bh, bl;
 };
 
+// host: 2-D bf16 row-major [rows][cols] tensor map, box = [box_rows][64] (one 128-byte swizzle row), OOB -> 0
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows);
 // host: 2-D fp32 row-major [rows][cols] tensor map, box = [box_rows][tk], tk = 32 (SWIZZLE_128B, single-pass
 // kernels) or TK3 (3-pass kernels; SWIZZLE_64B when 16), OOB -> 0
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (tk = 32 only) -- the layout of an MN-major TF32 operand

@@ -82,3 +82,24 @@ def test_split_k_partials_sum_to_the_product(M, N, K, ks):
     scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
     assert np.all(np.isfinite(got))
     assert np.max(np.abs(got - ref) / scale) < 3e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 2080, 4096), (70, 12, 1024), (512, 2080, 100032)])
+def test_bf16_gemm(M, N, K):
+    """rmn_bf16_gemm (kind::f16, bf16 operands, fp32 accumulate): exact products of the bf16 inputs, so the result
+    matches an fp64 product of the SAME bf16 values to fp32 accumulation accuracy."""
+    import torch
+    from riemann_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = (torch.rand((M, K), generator=g) * 0.25).to(torch.bfloat16)              # like the p(1-p) weights
+    B = (torch.randn((N, K), generator=g) * 0.1).to(torch.bfloat16)
+    dA, dB = A.cuda(), B.cuda()
+    C = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().rmn_bf16_gemm(M, N, K, _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(C), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = C.cpu().numpy().astype(np.float64)
+    A64, B64 = A.to(torch.float64).numpy(), B.to(torch.float64).numpy()
+    ref = A64 @ B64.T
+    scale = np.abs(A64) @ np.abs(B64).T
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - ref) / scale) < 2e-6 * max(1.0, np.sqrt(K / 4096.0))
