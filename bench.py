@@ -72,10 +72,10 @@ SUBCONFIGS = [
     ("gauss2d_rw", "gauss2d_rw", "f64", "weak", 2000, 5),
     ("gauss1000_mala_f64", "gauss1000_mala", "f64", "strong", 20, 5),
     ("gauss1000_mala_tf32x3", "gauss1000_mala", "tf32x3", "strong", 20, 5),
-    ("logistic_mala_f64", "logistic_mala", "f64", "strong", 1, 4),
-    ("logistic_mala_tf32x3", "logistic_mala", "tf32x3", "strong", 1, 4),
-    ("logistic_mmala_f64", "logistic_mmala", "f64", "strong", 1, 4),
-    ("logistic_mmala_tf32x3", "logistic_mmala", "tf32x3", "strong", 1, 4),
+    ("logistic_mala_f64", "logistic_mala", "f64", "strong", 2, 4),
+    ("logistic_mala_tf32x3", "logistic_mala", "tf32x3", "strong", 4, 4),
+    ("logistic_mmala_f64", "logistic_mmala", "f64", "strong", 2, 4),
+    ("logistic_mmala_tf32x3", "logistic_mmala", "tf32x3", "strong", 4, 4),
 ]
 
 # From the committed ncu captures (`ncu --set full`, one launch of the dominant kernel): DRAM bytes per launch and

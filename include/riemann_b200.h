@@ -212,7 +212,9 @@ int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, i
  *   logistic model, MALA / HMC / RW / pCN / mMALA (ONE fused kernel per likelihood sweep, logistic_fused.cu: logits into
  *   tensor memory, sigmoid / softplus out of it, R = y - p back into tensor memory as the operand of the gradient
  *   product):  2e-3 sqrt(N / 1e6)   (2e-3 at N = 1e6).  A state's log-posterior also carries a constant offset (<= 5e-8 N,
- *   the fp32 softplus) that is the same for every state and cancels in every Metropolis-Hastings ratio. */
+ *   the fp32 softplus) that is the same for every state and cancels in every Metropolis-Hastings ratio.
+ *   With simplified mMALA the Fisher metric of the proposal is one GEMM with bf16 operands (round to nearest, fp32
+ *   accumulate; see RMN_PREC_TF32_METRIC for why any deterministic metric keeps the sampler exact). */
 #define RMN_PREC_F64 0
 #define RMN_PREC_TF32X3 1
 /* RMN_PREC_TF32_METRIC: logistic model + simplified mMALA only -- the Fisher metric of the proposal,

@@ -518,47 +518,50 @@ struct LgStep {
     double* tr_lqr; double* tr_prop_theta;
 };
 
-// In-place Cholesky of the d x d matrix A (row-major, leading dim d) held in shared memory,
+// In-place Cholesky of the d x d matrix A (row-major, leading dimension ld) held in shared memory,
 // executed by one warp.  Returns log det = 2 sum log L_jj; NaN if not positive definite.
-__device__ double warp_cholesky(double* A, int d, int lane) {
+// ld = d + 1 (LDL below): the column sweeps read A[i * ld + k] with the LANE in i; with ld = d = 64 every lane hit the
+// same bank (a 32-way conflict on every load of the O(d^3) loop), with an odd ld the lanes spread over all banks.
+__device__ __forceinline__ int LDL(int d) { return d + 1; }
+__device__ double warp_cholesky(double* A, int d, int ld, int lane) {
     double logdet = 0.0;
     for (int j = 0; j < d; ++j) {
         double s = 0.0;
-        for (int k = lane; k < j; k += 32) s += A[j * d + k] * A[j * d + k];
+        for (int k = lane; k < j; k += 32) s += A[j * ld + k] * A[j * ld + k];
         s = group_sum<32>(s);
-        const double djj = A[j * d + j] - s;
+        const double djj = A[j * ld + j] - s;
         const double ljj = sqrt(djj);
         logdet += 2.0 * log(ljj);
         __syncwarp();
-        if (lane == 0) A[j * d + j] = ljj;
+        if (lane == 0) A[j * ld + j] = ljj;
         for (int i = j + 1 + lane; i < d; i += 32) {
-            double v = A[i * d + j];
-            for (int k = 0; k < j; ++k) v -= A[i * d + k] * A[j * d + k];
-            A[i * d + j] = v / ljj;
+            double v = A[i * ld + j];
+            for (int k = 0; k < j; ++k) v -= A[i * ld + k] * A[j * ld + k];
+            A[i * ld + j] = v / ljj;
         }
         __syncwarp();
     }
     return logdet;
 }
 // x <- L^-1 x (forward) ; x in shared memory
-__device__ void warp_trsv_lower(const double* L, double* x, int d, int lane) {
+__device__ void warp_trsv_lower(const double* L, double* x, int d, int ld, int lane) {
     for (int j = 0; j < d; ++j) {
         __syncwarp();
-        const double xj = x[j] / L[j * d + j];
+        const double xj = x[j] / L[j * ld + j];
         __syncwarp();
         if (lane == 0) x[j] = xj;
-        for (int i = j + 1 + lane; i < d; i += 32) x[i] -= L[i * d + j] * xj;
+        for (int i = j + 1 + lane; i < d; i += 32) x[i] -= L[i * ld + j] * xj;
     }
     __syncwarp();
 }
 // x <- L^-T x (backward)
-__device__ void warp_trsv_lower_t(const double* L, double* x, int d, int lane) {
+__device__ void warp_trsv_lower_t(const double* L, double* x, int d, int ld, int lane) {
     for (int j = d - 1; j >= 0; --j) {
         __syncwarp();
-        const double xj = x[j] / L[j * d + j];
+        const double xj = x[j] / L[j * ld + j];
         __syncwarp();
         if (lane == 0) x[j] = xj;
-        for (int i = lane; i < j; i += 32) x[i] -= L[j * d + i] * xj;
+        for (int i = lane; i < j; i += 32) x[i] -= L[j * ld + i] * xj;
     }
     __syncwarp();
 }
@@ -572,8 +575,9 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
     if (r >= st.K) return;
     const int dp = st.dp, d = st.d;
     const int64_t K = st.K;
-    double* Lw = sm + (size_t)wib * (MMALA ? (d * d + 2 * dp) : 0);    // [d][d] + two vectors
-    double* v1 = Lw + d * d;
+    const int ldl = LDL(d);
+    double* Lw = sm + (size_t)wib * (MMALA ? (d * ldl + 2 * dp) : 0);  // [d][ldl] + two vectors
+    double* v1 = Lw + d * ldl;
     double* v2 = v1 + dp;
     int c = st.cur[r];
     double lp = st.lp[r];
@@ -641,21 +645,21 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             // geometry of the proposal: L' = chol(G'), logdet', nat' = G'^-1 grad'
             for (int q = lane; q < d * d; q += 32) {
                 const int a = q / d, b = q % d;
-                Lw[q] = metric_entry(st, r, a, b) + ((a == b) ? pvinv : 0.0);
+                Lw[a * ldl + b] = metric_entry(st, r, a, b) + ((a == b) ? pvinv : 0.0);
             }
             __syncwarp();
-            const double ld = warp_cholesky(Lw, d, lane);
+            const double ld = warp_cholesky(Lw, d, ldl, lane);
             for (int j = lane; j < d; j += 32) v1[j] = grp[j];
             __syncwarp();
-            warp_trsv_lower(Lw, v1, d, lane);
-            warp_trsv_lower_t(Lw, v1, d, lane);                           // v1 = nat'
+            warp_trsv_lower(Lw, v1, d, ldl, lane);
+            warp_trsv_lower_t(Lw, v1, d, ldl, lane);                      // v1 = nat'
             // reverse residual  r = L'^T (theta - mean'),  mean' = theta' + eps^2/2 nat'
             for (int j = lane; j < d; j += 32) v2[j] = thc[j] - (thp[j] + 0.5 * eps * eps * v1[j]);
             __syncwarp();
             double rr = 0.0;
             for (int j = lane; j < d; j += 32) {
                 double s = 0.0;
-                for (int i = j; i < d; ++i) s += Lw[i * d + j] * v2[i];  // (L^T v)_j
+                for (int i = j; i < d; ++i) s += Lw[i * ldl + j] * v2[i];  // (L^T v)_j
                 rr += s * s;
             }
             rr = group_sum<32>(rr);
@@ -666,7 +670,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             lqr = lq_fwd - lq_rev;
             // stash the proposal's geometry in its slot
             double* Lp = st.Lc + ((int64_t)pslot * K + r) * d * d;
-            for (int q = lane; q < d * d; q += 32) Lp[q] = Lw[q];
+            for (int q = lane; q < d * d; q += 32) Lp[q] = Lw[(q / d) * ldl + q % d];
             double* np_ = st.nat + ((int64_t)pslot * K + r) * dp;
             for (int j = lane; j < d; j += 32) np_[j] = v1[j];
             if (lane == 0) st.logdet[(int64_t)pslot * K + r] = ld;
@@ -703,7 +707,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
 
     if (MMALA && sp.propose) {
         const double* Lcur = st.Lc + ((int64_t)c * K + r) * d * d;
-        for (int q = lane; q < d * d; q += 32) Lw[q] = Lcur[q];
+        for (int q = lane; q < d * d; q += 32) Lw[(q / d) * ldl + q % d] = Lcur[q];
     }
     for (int j4 = lane * 4; j4 < dp; j4 += 128) {
         double xi[4];
@@ -779,7 +783,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
     }
     if (MMALA && sp.propose) {
         __syncwarp();
-        warp_trsv_lower_t(Lw, v1, d, lane);                              // v1 = L^-T xi
+        warp_trsv_lower_t(Lw, v1, d, ldl, lane);                         // v1 = L^-T xi
         const double* nc = st.nat + ((int64_t)c * K + r) * dp;
         for (int j = lane; j < dp; j += 32)
             thn[j] = (j < d) ? (th[j] + 0.5 * eps * eps * nc[j]) + eps * v1[j] : 0.0;
@@ -832,17 +836,18 @@ lg_adopt_kernel(LogisticState st) {
     }
     tt = group_sum<32>(tt);
     if (MMALA) {
-        double* Lw = sm + (size_t)wib * (d * d + dp);
-        double* v1 = Lw + d * d;
-        for (int q = lane; q < d * d; q += 32) Lw[q] = metric_entry(st, r, q / d, q % d) + ((q / d == q % d) ? pvinv : 0.0);
+        const int ldl = LDL(d);
+        double* Lw = sm + (size_t)wib * (d * ldl + dp);
+        double* v1 = Lw + d * ldl;
+        for (int q = lane; q < d * d; q += 32) Lw[(q / d) * ldl + q % d] = metric_entry(st, r, q / d, q % d) + ((q / d == q % d) ? pvinv : 0.0);
         __syncwarp();
-        const double ld = warp_cholesky(Lw, d, lane);
+        const double ld = warp_cholesky(Lw, d, ldl, lane);
         for (int j = lane; j < d; j += 32) v1[j] = gr[j];
         __syncwarp();
-        warp_trsv_lower(Lw, v1, d, lane);
-        warp_trsv_lower_t(Lw, v1, d, lane);
+        warp_trsv_lower(Lw, v1, d, ldl, lane);
+        warp_trsv_lower_t(Lw, v1, d, ldl, lane);
         double* Lp = st.Lc + ((int64_t)1 * K + r) * d * d;
-        for (int q = lane; q < d * d; q += 32) Lp[q] = Lw[q];
+        for (int q = lane; q < d * d; q += 32) Lp[q] = Lw[(q / d) * ldl + q % d];
         double* np_ = st.nat + ((int64_t)1 * K + r) * dp;
         for (int j = lane; j < d; j += 32) np_[j] = v1[j];
         if (lane == 0) st.logdet[(int64_t)1 * K + r] = ld;
@@ -992,7 +997,11 @@ struct LogisticSampler : SamplerImpl {
     size_t rowb() const { return align256((size_t)st.K * st.dp * 8); }
     size_t eval_smem() const { return eval_smem_bytes(st.ldt); }
     size_t metric_smem() const { return ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8; }
-    size_t fp_smem() const { return mmala ? (size_t)4 * (st.d * st.d + 2 * st.dp) * 8 : 0; }
+    // mMALA: one warp per chain with its own [d][d + 1] matrix in shared memory (34 KB at d = 64): blocks of TWO warps, so
+    // that three blocks (six warps) fit an SM instead of one block of four
+    int fp_threads() const { return mmala ? 64 : 128; }
+    unsigned fp_grid() const { return (unsigned)((st.K * 32 + fp_threads() - 1) / fp_threads()); }
+    size_t fp_smem() const { return mmala ? (size_t)(fp_threads() / 32) * (st.d * (st.d + 1) + 2 * st.dp) * 8 : 0; }   // LDL(d) = d + 1
     size_t workspace_bytes() const override {
         const size_t K = (size_t)st.K;
         size_t n = 5 * rowb() + align256((size_t)st.nsplit * K * 8) +
@@ -1153,7 +1162,7 @@ struct LogisticSampler : SamplerImpl {
         lg_set_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, d_theta);
         RMN_KERNEL_CHECK(); launches++;
         if (int rc = eval(1, stream)) return rc;
-        if (mmala) lg_adopt_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(fst());
+        if (mmala) lg_adopt_kernel<true><<<fp_grid(), fp_threads(), fp_smem(), stream>>>(fst());
         else lg_adopt_kernel<false><<<row_grid(), 128, 0, stream>>>(fst());
         RMN_KERNEL_CHECK(); launches++;
         return RMN_OK;
@@ -1191,7 +1200,7 @@ struct LogisticSampler : SamplerImpl {
                 const int64_t i = t;
                 if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
             }
-            if (mmala) lg_finish_propose_kernel<true><<<row_grid(), 128, fp_smem(), stream>>>(fst(), sp);
+            if (mmala) lg_finish_propose_kernel<true><<<fp_grid(), fp_threads(), fp_smem(), stream>>>(fst(), sp);
             else lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(fst(), sp);
             RMN_KERNEL_CHECK(); launches++;
             if (t == T) break;
