@@ -472,6 +472,15 @@ def roofline_for(ctx, wl, precision, Kg, T, steps, kt, ms):
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "note": "dominant kernel = lg_eval_kernel (fp64 DMMA, 4 N d = 2.6e7 flop per chain-step) against the "
                         "measured DMMA peak; the metric GEMM (4.2e8 flop per chain-step) runs on tcgen05 in TF32"}
+    elif precision == "tf32x3" and wl == "logistic_mmala" and "gemm" in kt["kernel"]:
+        bf16 = "bf16" in kt["kernel"]
+        peak = peaks["bf16_tflops"] if bf16 else extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
+        ach = 100000.0 * 64 * 65 * Kg * T * steps / (kernel_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "note": "dominant kernel = the Fisher-metric GEMM of the proposal on tcgen05 (%s operands, fp32 accumulate): "
+                        "N d (d+1) = 4.16e8 flop per chain-step (the symmetric half, SURVEY 8d) against the %s; the fused "
+                        "likelihood sweep (4 N d flop) is the second kernel of the step"
+                        % ("bf16" if bf16 else "TF32", "dense bf16 peak of MEASURED_PEAKS.json" if bf16 else "cuBLAS TF32 peak")}
     elif precision == "tf32x3" and wl.startswith("logistic"):
         peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
         n_, d_ = (100000, 64) if wl == "logistic_mmala" else (1000000, 100)
