@@ -95,6 +95,10 @@ def main():
         run("logistic N=%d d=%d HMC3" % (N, d), lambda: Sampler(lm, hm.VanillaHMC(0.03, 3, lm.grad_log_posterior), th0, seed=6))
         run("logistic N=%d d=%d mMALA tf32-metric" % (N, d), lambda: Sampler(lm, hm.SimplifiedMMALA(0.5, lm), th0, seed=6, precision="tf32-metric"))
         run("logistic N=%d d=%d RW" % (N, d), lambda: Sampler(lm, rw.MetropolisRandomWalk(0.001 * np.eye(d)), th0, seed=6))
+        run("logistic N=%d d=%d pCN tf32x3" % (N, d), lambda: Sampler(lm, rw.pCN(pv * np.eye(d), 0.995), th0, seed=6, precision="tf32x3"))
+        M = spd(d, 50.0)
+        run("logistic N=%d d=%d HMC3 mass" % (N, d), lambda: Sampler(lm, hm.VanillaHMC(0.2, 3, lm.grad_log_posterior, M=M), th0, seed=6))
+        run("logistic N=%d d=%d AdaptMALA mass tf32x3" % (N, d), lambda: Sampler(lm, hm.AdaptScaleHMC(0.2, 1, lm.grad_log_posterior, M=M), th0, seed=6, precision="tf32x3"))
     print("sanitize_small: all cases ran")
 
 
