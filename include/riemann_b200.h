@@ -298,6 +298,19 @@ int rmn_sampler_diag_dim(const rmn_sampler_t* s);
 int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream);
 int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stream);
 
+/* Covariance adaptation POOLED over the chains (Haario's adaptive Metropolis, which the
+ * reference runs per chain in AdaptCovProposal.adapt, riemann/proposals/adaptive.py:38-103, on one chain's history).
+ * With K chains the history of one chain is replaced by the population: every t_adapt MH steps the states of ALL chains
+ * (of all ranks when a communicator is set, rmn_sampler_set_row_comm) are added to running sums
+ * S1 = sum theta, S2 = sum theta theta^T, n; the random-walk covariance becomes sd * (S2 / n - m m^T) + jitter * I, its
+ * Cholesky factor is recomputed on the device and used by every chain from the next step on (randomwalk.py:25-26 with the
+ * new L).  stop_after > 0: no adaptation after that many steps (the chain is a plain MH chain from then on, as a
+ * burn-in-only adaptation should be); 0 = adapt forever (diminishing: the sums keep growing).
+ * Dense Gaussian path (d > 8), f64 precision.  rmn_sampler_get_pooled_cov copies the current estimate out:
+ * d_cov[d][d] = S2 / n - m m^T, d_mean[d], d_count[1] = n (device pointers). */
+int rmn_proposal_rw_set_pooled_cov_adapt(rmn_proposal_t* p, int64_t t_adapt, double sd, double jitter, int64_t stop_after);
+int rmn_sampler_get_pooled_cov(rmn_sampler_t* s, double* d_cov, double* d_mean, double* d_count, void* stream);
+
 /* Per-chain mean and biased variance of the tracked functionals since the last reset: d_mean[nd][K], d_var[nd][K]
  * (chain fastest; either may be NULL).  What `Sampler._chain_thetas` gives the reference's scripts for one chain
  * (examples/test_randomwalk.py:41-46 computes its statistics from the trace) without keeping a trace of K chains;

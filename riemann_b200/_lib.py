@@ -96,6 +96,8 @@ SIGNATURES = {
     "rmn_tf32x3_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P, _P, _P]),
     "rmn_tf32_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P]),
     "rmn_bf16_gemm": (_I, [_L, _I, _I, _P, _P, _P, _P]),
+    "rmn_proposal_rw_set_pooled_cov_adapt": (_I, [_P, _L, _D, _D, _L]),
+    "rmn_sampler_get_pooled_cov": (_I, [_P, _P, _P, _P, _P]),
     "rmn_tf32x3_gemm_splitk": (_I, [_L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "rmn_logistic_math": (_I, [_L, _P, _P, _P, _P, _P]),
 }

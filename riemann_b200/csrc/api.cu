@@ -314,6 +314,10 @@ static SamplerImpl* make_impl(rmn_sampler* s, int* rc) {
         *rc = RMN_ERR_PARAM;
         return nullptr;
     }
+    if (p->pool_cov && !(m->kind == RMN_MODEL_GAUSS && m->d > RMN_SMALL_D_MAX && s->precision == RMN_PREC_F64)) {
+        rmn_set_error("pooled covariance adaptation: dense Gaussian model (d > %d) in f64 precision", RMN_SMALL_D_MAX);
+        return nullptr;
+    }
     if (p->acov && !(m->kind == RMN_MODEL_GAUSS && m->d <= RMN_SMALL_D_MAX && s->precision == RMN_PREC_F64)) {
         rmn_set_error("covariance-adapting proposals (AdaptCov*) run on the small-d Gaussian path only (d <= %d, fp64)",
                       RMN_SMALL_D_MAX);
@@ -454,6 +458,21 @@ extern "C" int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream) {
 extern "C" int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stream) {
     RMN_S(s); RMN_REQUIRE(d_block, "rmn_sampler_reduce_diagnostics: null block");
     return s->impl->reduce_diag(d_block, (cudaStream_t)stream);
+}
+extern "C" int rmn_proposal_rw_set_pooled_cov_adapt(rmn_proposal_t* p, int64_t t_adapt, double sd, double jitter,
+                                                    int64_t stop_after) {
+    RMN_REQUIRE(p, "rmn_proposal_rw_set_pooled_cov_adapt: null proposal");
+    RMN_REQUIRE(p->kind == RMN_PROP_RW && !p->acov, "rmn_proposal_rw_set_pooled_cov_adapt: a random-walk proposal without per-chain covariance adaptation");
+    RMN_REQUIRE(p->d > RMN_SMALL_D_MAX, "pooled covariance adaptation runs on the dense path (d > %d); d <= %d has the per-chain AdaptCovRandomWalk",
+                RMN_SMALL_D_MAX, RMN_SMALL_D_MAX);
+    RMN_REQUIRE(t_adapt >= 1 && sd > 0 && isfinite(sd) && jitter >= 0 && isfinite(jitter) && stop_after >= 0,
+                "rmn_proposal_rw_set_pooled_cov_adapt: need t_adapt >= 1, sd > 0, jitter >= 0, stop_after >= 0");
+    p->pool_cov = 1; p->pool_t_adapt = t_adapt; p->pool_sd = sd; p->pool_jitter = jitter; p->pool_stop = stop_after;
+    return RMN_OK;
+}
+extern "C" int rmn_sampler_get_pooled_cov(rmn_sampler_t* s, double* d_cov, double* d_mean, double* d_count, void* stream) {
+    RMN_REQUIRE(s && s->impl && d_cov && d_mean && d_count, "rmn_sampler_get_pooled_cov: bad argument");
+    return s->impl->get_pooled_cov(d_cov, d_mean, d_count, (cudaStream_t)stream);
 }
 extern "C" int rmn_sampler_get_adaptcov(rmn_sampler_t* s, double* d_L, void* stream) {
     RMN_REQUIRE(s && s->impl && d_L, "rmn_sampler_get_adaptcov: bad argument");

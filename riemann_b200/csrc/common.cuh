@@ -197,6 +197,11 @@ struct rmn_proposal {
     int acov = 0, ac_marginalize = 0, ac_smooth = 0;
     double ac_t_adapt = 1.0;
     std::vector<double> h_C0;            // full d x d
+    // pooled covariance adaptation (SURVEY 8f N5 "pooled across chains"; dense Gaussian path): every pool_t_adapt steps the
+    // proposal covariance becomes pool_sd * (covariance of ALL chains' states accumulated so far) + pool_jitter * I
+    int pool_cov = 0;
+    int64_t pool_t_adapt = 0, pool_stop = 0;
+    double pool_sd = 0.0, pool_jitter = 0.0;
     // changepoint mix
     double hscale = 0.0;
     double p_cum[3] = {0.20, 0.40, 0.60};
@@ -271,6 +276,7 @@ struct SamplerImpl {
     virtual int cp_get_state(int32_t*, double*, double*, double*, double*, cudaStream_t) { return unsupported("cp_get_state"); }
     virtual int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t st) = 0;
     virtual int get_adaptcov(double*, cudaStream_t) { return unsupported("get_adaptcov (small-d AdaptCovRandomWalk samplers only)"); }
+    virtual int get_pooled_cov(double*, double*, double*, cudaStream_t) { return unsupported("get_pooled_cov (dense Gaussian samplers with PooledAdaptCovRandomWalk only)"); }
     virtual int set_row_comm(const void*, size_t, int, int) { return unsupported("row-sharded data mode (logistic samplers in f64 precision only)"); }
     virtual int set_tempering(int, const double*, double) { return unsupported("parallel tempering (small-d Gaussian samplers only)"); }
     virtual int get_adapt(double*, int64_t*, int64_t*, cudaStream_t) { return unsupported("get_adapt"); }

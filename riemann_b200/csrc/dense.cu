@@ -501,6 +501,117 @@ __global__ void dense_get_adapt_kernel(DenseState st, double* scale, int64_t* ns
     if (na) na[c] = st.nacc[c];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pooled covariance adaptation (rmn_proposal_rw_set_pooled_cov_adapt).  Three small kernels that run every
+// t_adapt steps: (1) S1 += sum_chains y, S2 += sum_chains y y^T over the chains' CURRENT centred states (lower triangle,
+// 32 x 32 tiles, fp64 atomics -- the order of the atomics makes the last bits of S2 run-dependent; the proposal
+// covariance is not parity-bound to anything); (2) optional all-reduce over ranks; (3) one block forms
+// sd (S2 / n - m m^T) + jitter I and factors it (right-looking Cholesky on the transposed factor so that the column
+// sweeps are coalesced), then overwrites the padded L the dense random walk multiplies its noise with.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PM_T = 32;            // tile of the second-moment matrix
+constexpr int PM_ROWS = 1024;       // chain rows per block
+__global__ void __launch_bounds__(256)
+pool_moments_kernel(DenseState st, double* __restrict__ S1, double* __restrict__ S2) {
+    __shared__ double a[PM_T][PM_T + 1], b[PM_T][PM_T + 1];       // [row][col] of the two column blocks
+    const int d = st.d, dp = st.dp;
+    // lower-triangular tile pair (ti >= tj) from the linear block index
+    int ti = 0, rem = blockIdx.x;
+    while (rem > ti) { rem -= ti + 1; ++ti; }
+    const int tj = rem;
+    const int i0 = ti * PM_T, j0 = tj * PM_T;
+    const int64_t r0 = (int64_t)blockIdx.y * PM_ROWS, r1 = min(st.K, r0 + PM_ROWS);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, 2 x 2 outputs each
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    double colsum = 0.0;                                          // S1 of column i0 + (tid & 31), by the tj == 0 blocks
+    for (int64_t rb = r0; rb < r1; rb += PM_T) {
+        for (int q = threadIdx.x; q < PM_T * PM_T; q += 256) {
+            const int rr = q / PM_T, cc = q % PM_T;
+            const int64_t r = rb + rr;
+            double va = 0.0, vb = 0.0;
+            if (r < r1) {
+                const double* y = st.Y + ((int64_t)st.cur[r] * st.K + r) * dp;
+                if (i0 + cc < d) va = y[i0 + cc];
+                if (j0 + cc < d) vb = y[j0 + cc];
+            }
+            a[rr][cc] = va; b[rr][cc] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < PM_T; ++rr) {
+            const double a0 = a[rr][2 * ty], a1 = a[rr][2 * ty + 1], b0 = b[rr][2 * tx], b1 = b[rr][2 * tx + 1];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+        if (tj == 0 && threadIdx.x < PM_T)
+            for (int rr = 0; rr < PM_T; ++rr) colsum += a[rr][threadIdx.x];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = i0 + 2 * ty + p, j = j0 + 2 * tx + q;
+            if (i < d && j < d && j <= i) atomicAdd(&S2[(size_t)i * d + j], acc[p][q]);
+        }
+    if (tj == 0 && threadIdx.x < PM_T && i0 + threadIdx.x < d) atomicAdd(&S1[i0 + threadIdx.x], colsum);
+}
+
+// one block: C = sd (S2/n - m m^T) + jitter I (lower), U = chol(C)^T row-major (U[k][i] = L[i][k]); on success L -> Lpad
+__global__ void __launch_bounds__(1024)
+pool_chol_kernel(int d, int dp, const double* __restrict__ S1, const double* __restrict__ S2, double n, double sd,
+                 double jitter, double* __restrict__ U, double* __restrict__ Lpad, int* __restrict__ status) {
+    __shared__ double s_piv;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) s_bad = 0;
+    const double inv = 1.0 / n;
+    for (int64_t q = tid; q < (int64_t)d * d; q += nt) {
+        const int i = (int)(q / d), j = (int)(q % d);
+        if (j <= i) {
+            const double c = sd * (S2[q] * inv - (S1[i] * inv) * (S1[j] * inv)) + ((i == j) ? jitter : 0.0);
+            U[(size_t)j * d + i] = c;                               // transposed: row j of U holds column j of C
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < d; ++j) {
+        // column j of L: U[j][i] (i >= j) currently holds C[i][j]; subtract sum_k L[i][k] L[j][k] = sum_k U[k][i] U[k][j]
+        for (int i = j + tid; i < d; i += nt) {
+            double v = U[(size_t)j * d + i];
+            for (int k = 0; k < j; ++k) v -= U[(size_t)k * d + i] * U[(size_t)k * d + j];
+            U[(size_t)j * d + i] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double piv = U[(size_t)j * d + j];
+            if (!(piv > 0.0) || !isfinite(piv)) s_bad = 1;
+            s_piv = sqrt(piv);
+        }
+        __syncthreads();
+        if (s_bad) break;
+        const double rp = 1.0 / s_piv;
+        for (int i = j + tid; i < d; i += nt) U[(size_t)j * d + i] = (i == j) ? s_piv : U[(size_t)j * d + i] * rp;
+        __syncthreads();
+    }
+    if (s_bad) { if (tid == 0) atomicAdd(status, 1); return; }     // not positive definite: keep the previous factor
+    for (int64_t q = tid; q < (int64_t)d * d; q += nt) {
+        const int i = (int)(q / d), j = (int)(q % d);
+        Lpad[(size_t)i * dp + j] = (j <= i) ? U[(size_t)j * d + i] : 0.0;
+    }
+}
+__global__ void pool_cov_out_kernel(int d, const double* __restrict__ S1, const double* __restrict__ S2, double n,
+                                    const double* __restrict__ mu, double* cov, double* mean, double* count) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double inv = n > 0 ? 1.0 / n : 0.0;
+    if (q < (int64_t)d * d) {
+        const int i = (int)(q / d), j = (int)(q % d);
+        const int hi = i > j ? i : j, lo = i > j ? j : i;
+        cov[q] = S2[(size_t)hi * d + lo] * inv - (S1[i] * inv) * (S1[j] * inv);
+    }
+    if (q < d) mean[q] = S1[q] * inv + mu[q];
+    if (q == 0) *count = n;
+}
+
 struct DenseGaussSampler : SamplerImpl {
     rmn_sampler* s;
     DenseState st{};
@@ -513,6 +624,15 @@ struct DenseGaussSampler : SamplerImpl {
     double* d_mupad = nullptr;
     bool rw_diag = true;
     bool pending = false;         // a proposal is in flight (written, GEMM done, not finished)
+    // pooled covariance adaptation
+    double* d_pS1 = nullptr; double* d_pS2 = nullptr; double* d_pU = nullptr; int* d_pstatus = nullptr;
+    double pool_n = 0.0;          // samples in the sums (all ranks)
+    int64_t pool_updates = 0;
+    RowComm poolc;                // the other ranks' chains join the pool through this communicator (optional)
+    int set_row_comm(const void* id, size_t nbytes, int rank, int world) override {
+        if (!s->prop->pool_cov) return unsupported("a communicator on the dense Gaussian sampler (pooled covariance adaptation only)");
+        return rmn_rowcomm_init(&poolc, id, nbytes, rank, world);
+    }
     explicit DenseGaussSampler(rmn_sampler* s_) : s(s_) {
         st.K = s->K; st.d = s->model->d; st.dp = (st.d + 15) / 16 * 16; st.nblk = (st.dp + 31) / 32;
         has_mass = s->prop->kind == RMN_PROP_HMC && s->prop->has_mass;
@@ -520,6 +640,8 @@ struct DenseGaussSampler : SamplerImpl {
     ~DenseGaussSampler() override {
         cudaFree(d_Ppad); cudaFree(d_Lpad); cudaFree(d_Linvpad); cudaFree(d_Ldiag); cudaFree(d_mupad);
         cudaFree(d_chM); cudaFree(d_Minv); cudaFree(d_chMinv);
+        cudaFree(d_pS1); cudaFree(d_pS2); cudaFree(d_pU); cudaFree(d_pstatus); cudaFree(d_pS1g); cudaFree(d_pS2g);
+        rmn_rowcomm_destroy(&poolc);
     }
     size_t row_bytes() const { return align256((size_t)st.K * st.dp * 8); }
     size_t workspace_bytes() const override {
@@ -573,6 +695,16 @@ struct DenseGaussSampler : SamplerImpl {
             for (int i = 0; i < d; ++i) ld[i] = pr->h_L[(size_t)i * d + i];
             RMN_CUDA(cudaMalloc(&d_Ldiag, (size_t)dp * 8));
             RMN_CUDA(cudaMemcpy(d_Ldiag, ld.data(), (size_t)dp * 8, cudaMemcpyHostToDevice));
+            if (pr->pool_cov) {
+                rw_diag = false;                   // the adapted factor is dense whatever C0 was
+                RMN_CUDA(cudaMalloc(&d_pS1, (size_t)d * 8));
+                RMN_CUDA(cudaMalloc(&d_pS2, (size_t)d * d * 8));
+                RMN_CUDA(cudaMalloc(&d_pU, (size_t)d * d * 8));
+                RMN_CUDA(cudaMalloc(&d_pstatus, 4));
+                RMN_CUDA(cudaMemset(d_pS1, 0, (size_t)d * 8));
+                RMN_CUDA(cudaMemset(d_pS2, 0, (size_t)d * d * 8));
+                RMN_CUDA(cudaMemset(d_pstatus, 0, 4));
+            }
             if (!rw_diag) {
                 std::vector<double> hl((size_t)dp * dp, 0.0);
                 for (int i = 0; i < d; ++i)
@@ -681,8 +813,24 @@ struct DenseGaussSampler : SamplerImpl {
                 const int64_t i = t;                      // history index of the state after step t-1
                 if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
             }
-            finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
-            RMN_KERNEL_CHECK(); launches++;
+            const int64_t gstep = step0 + t;       // index of the step about to be proposed
+            const bool adapt_now = pr->pool_cov && t < T && gstep > 0 && gstep % pr->pool_t_adapt == 0 &&
+                                   (pr->pool_stop == 0 || gstep <= pr->pool_stop);
+            if (adapt_now && sp.finish) {
+                // the new factor must be in place before step gstep is proposed: finish step gstep-1 on its own first
+                DenseStep fin = sp; fin.propose = 0;
+                finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, fin);
+                RMN_KERNEL_CHECK(); launches++;
+                if (int rc = pool_adapt(stream)) return rc;
+                DenseStep pro = sp; pro.finish = 0; pro.diag = 0; pro.trace_slot = -1;
+                pro.tr_prop_lp = nullptr; pro.tr_acc = nullptr; pro.tr_lqr = nullptr; pro.tr_prop_theta = nullptr;
+                finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, pro);
+                RMN_KERNEL_CHECK(); launches++;
+            } else {
+                if (adapt_now) if (int rc = pool_adapt(stream)) return rc;
+                finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, sp);
+                RMN_KERNEL_CHECK(); launches++;
+            }
             if (t == T) break;
             if (pr->kind == RMN_PROP_RW && !rw_diag)
                 if (int rc = gemm<EPI_RWPROP>(d_Lpad, stream)) return rc;
@@ -721,6 +869,41 @@ struct DenseGaussSampler : SamplerImpl {
             }
         }
         step0 += T; diag_steps += T;
+        return RMN_OK;
+    }
+    int pool_adapt(cudaStream_t stream) {
+        const rmn_proposal* pr = s->prop;
+        const int d = st.d;
+        const int nt = (d + PM_T - 1) / PM_T;
+        dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)((st.K + PM_ROWS - 1) / PM_ROWS));
+        pool_moments_kernel<<<grid, 256, 0, stream>>>(st, d_pS1, d_pS2);
+        RMN_KERNEL_CHECK(); launches++;
+        pool_n += (double)st.K * (poolc.comm ? poolc.world : 1);
+        const double* S1 = d_pS1; const double* S2 = d_pS2;
+        if (poolc.comm) {
+            // the sums are LOCAL running sums; the factor is built from their all-reduced copies (kept in d_pU's tail is not
+            // possible -- U is the work matrix -- so reduce into scratch copies)
+            if (!d_pS1g) { RMN_CUDA(cudaMalloc(&d_pS1g, (size_t)d * 8)); RMN_CUDA(cudaMalloc(&d_pS2g, (size_t)d * d * 8)); }
+            RMN_CUDA(cudaMemcpyAsync(d_pS1g, d_pS1, (size_t)d * 8, cudaMemcpyDeviceToDevice, stream));
+            RMN_CUDA(cudaMemcpyAsync(d_pS2g, d_pS2, (size_t)d * d * 8, cudaMemcpyDeviceToDevice, stream));
+            double* bufs[2] = {d_pS1g, d_pS2g};
+            const size_t counts[2] = {(size_t)d, (size_t)d * d};
+            if (int rc = rmn_rowcomm_allreduce_f64(&poolc, bufs, counts, 2, stream)) return rc;
+            S1 = d_pS1g; S2 = d_pS2g;
+        }
+        pool_chol_kernel<<<1, 1024, 0, stream>>>(d, st.dp, S1, S2, pool_n, pr->pool_sd, pr->pool_jitter, d_pU, d_Lpad, d_pstatus);
+        RMN_KERNEL_CHECK(); launches++;
+        pool_updates++;
+        return RMN_OK;
+    }
+    double* d_pS1g = nullptr; double* d_pS2g = nullptr;
+    int get_pooled_cov(double* d_cov, double* d_mean, double* d_count, cudaStream_t stream) override {
+        if (!s->prop->pool_cov) return unsupported("get_pooled_cov (PooledAdaptCovRandomWalk only)");
+        const int d = st.d;
+        const double* S1 = d_pS1; const double* S2 = d_pS2;
+        if (poolc.comm && d_pS1g && pool_updates > 0) { S1 = d_pS1g; S2 = d_pS2g; }   // the last all-reduced sums
+        pool_cov_out_kernel<<<(unsigned)(((int64_t)d * d + 255) / 256), 256, 0, stream>>>(d, S1, S2, pool_n, st.mu, d_cov, d_mean, d_count);
+        RMN_KERNEL_CHECK(); launches++;
         return RMN_OK;
     }
     int get_adapt(double* sc, int64_t* ns, int64_t* na, cudaStream_t stream) override {

@@ -70,6 +70,39 @@ class AdaptCovRandomWalk(MetropolisRandomWalk):
         return h
 
 
+class PooledAdaptCovRandomWalk(MetropolisRandomWalk):
+    """Covariance adaptation POOLED over the chains.  Haario's adaptive Metropolis as the reference
+    runs it (adaptive.py:38-103) learns the proposal covariance from ONE chain's history; a K-chain engine has a better
+    estimator at hand, the population: every `t_adapt` steps the current states of all chains (all ranks, when
+    torch.distributed is initialised) join running sums, and from the next step on every chain proposes with
+    `C = sd * Cov(pool) + jitter * I`, `sd = 2.38^2 / d` by default (Haario et al. 2001).  `stop_after` > 0 freezes the
+    proposal after that many steps (adaptation during burn-in only, after which the chains are plain MH chains);
+    0 adapts forever with ever smaller changes.  Dense Gaussian path (d > 8), precision f64.  After every batch `.C`
+    (the pooled covariance estimate), `.pool_mean` and `.pool_count` are refreshed from the device.
+    `adapt_scale=True` also runs the per-chain AdaptScale rule (adaptive.py:26-35, target 0.25) on top."""
+
+    _adaptive = False
+    _pooled_cov = True
+
+    def __init__(self, C0, t_adapt=100, sd=None, jitter=1e-10, stop_after=0, adapt_scale=False):
+        MetropolisRandomWalk.__init__(self, C0)
+        if not (int(t_adapt) >= 1):
+            raise ParameterError("t_adapt must be a positive number of steps")
+        self.C0 = np.array(np.atleast_2d(C0), dtype=np.float64)
+        self.C, self.pool_mean, self.pool_count = None, None, 0.0
+        self.t_adapt, self.sd, self.jitter, self.stop_after = int(t_adapt), sd, float(jitter), int(stop_after)
+        if adapt_scale:
+            self._adaptive = True
+            self.target_accept_rate = 0.25
+            self.accept_rate = 0.0
+
+    def _create_handle(self, d):
+        h = MetropolisRandomWalk._create_handle(self, d)
+        sd = 2.38 ** 2 / d if self.sd is None else float(self.sd)
+        _lib.check(_lib.load().rmn_proposal_rw_set_pooled_cov_adapt(h, self.t_adapt, sd, self.jitter, self.stop_after))
+        return h
+
+
 # aliases of the reference (randomwalk.py:59)
 AdaptiveMetropolisRandomWalk = HaarioRandomWalk = AdaptCovRandomWalk
 

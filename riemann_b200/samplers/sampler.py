@@ -129,6 +129,12 @@ class Sampler(object):
             uid = exchange_unique_id(lambda buf, n: _lib.check(lib.rmn_nccl_unique_id(buf, n)))
             rank, world = rank_world()
             _lib.check(lib.rmn_sampler_set_row_comm(h, uid, len(uid), rank, world))
+        if getattr(proposal, "_pooled_cov", False):      # the other ranks' chains join the covariance pool
+            from ..distributed import exchange_unique_id, rank_world
+            rank, world = rank_world()
+            if world > 1:
+                uid = exchange_unique_id(lambda buf, n: _lib.check(lib.rmn_nccl_unique_id(buf, n)))
+                _lib.check(lib.rmn_sampler_set_row_comm(h, uid, len(uid), rank, world))
         if _tempering is not None:            # PTSampler: ladders along the chain axis, before the first evaluation
             betas, pswap = _tempering
             b = np.ascontiguousarray(betas, dtype=np.float64)
@@ -414,6 +420,16 @@ class Sampler(object):
             p.L, p.C = (L[0], Cm[0]) if self.K == 1 else (L, Cm)
             if hasattr(p, "chM"):                                   # AdaptCovHMC: M = C, chM = L (hamiltonian.py:117)
                 p.M, p.chM = p.C, p.L
+        if getattr(p, "_pooled_cov", False):           # PooledAdaptCovRandomWalk: the population estimate
+            torch = self._torch
+            Cm = torch.empty((self.d, self.d), dtype=torch.float64, device="cuda")
+            mean = torch.empty(self.d, dtype=torch.float64, device="cuda")
+            cnt = torch.empty(1, dtype=torch.float64, device="cuda")
+            _lib.check(_lib.load().rmn_sampler_get_pooled_cov(self._handle, _lib.ptr(Cm), _lib.ptr(mean), _lib.ptr(cnt),
+                                                              _lib.stream_ptr()))
+            p.pool_count = float(cnt.cpu().numpy()[0])
+            if p.pool_count > 0:
+                p.C, p.pool_mean = Cm.cpu().numpy(), mean.cpu().numpy()
         if not getattr(p, "_adaptive", False):
             return
         torch, K = self._torch, self.K
@@ -449,7 +465,7 @@ class Sampler(object):
         covariance-adapting proposals (adaptive.py:38-103), AdaptScalepCN's compounding rho (randomwalk.py:118) -- have no
         read/write ABI for it, so a checkpoint of them would resume silently different chains: refused."""
         p = self.proposal
-        if getattr(p, "_adapt_cov", False) or type(p).__name__ == "AdaptScalepCN":
+        if getattr(p, "_adapt_cov", False) or getattr(p, "_pooled_cov", False) or type(p).__name__ == "AdaptScalepCN":
             raise ParameterError("get_checkpoint: {} keeps per-chain adaptation state (covariance accumulators / rho) "
                                  "that cannot be saved; checkpoint/resume covers fixed and AdaptScale proposals"
                                  .format(type(p).__name__))
