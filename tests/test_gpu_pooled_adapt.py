@@ -89,3 +89,50 @@ def test_refusals():
     s = Sampler(m12, PooledAdaptCovRandomWalk(np.eye(12)), np.zeros((4, 12)))
     with pytest.raises(ParameterError):
         s.get_checkpoint()
+
+
+_TWO_RANK = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+from riemann_b200 import Sampler
+from riemann_b200.models.gaussian import MultiGaussianDist
+from riemann_b200.proposals.randomwalk import PooledAdaptCovRandomWalk
+d, K = 16, 1024
+rng = np.random.default_rng(7)
+A = rng.standard_normal((d, d)); Sigma = A @ A.T / d + 0.3 * np.eye(d); mu = rng.standard_normal(d)
+m = MultiGaussianDist(mu, Sigma)
+th0 = mu + 0.1 * np.random.default_rng(100 + rank).standard_normal((K, d))
+p = PooledAdaptCovRandomWalk(1e-3 * np.eye(d), t_adapt=20, stop_after=2000)
+s = Sampler(m, p, th0, seed=3, chain_offset=rank * K)
+s.run(2000, trace=False); s.run(20, trace=False)
+assert p.pool_count == world * K * 100, p.pool_count
+mine = torch.as_tensor(p.C, device="cuda"); other = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(other, mine)
+assert all(torch.equal(o, mine) for o in other), "ranks hold different pooled covariances"
+rel = np.max(np.abs(p.C - Sigma) / np.sqrt(np.outer(np.diag(Sigma), np.diag(Sigma))))
+assert rel < 0.25, rel
+if rank == 0: print("pooled covariance over %d ranks: %d samples, max rel err %.3f, ranks bit-identical" % (world, p.pool_count, rel), flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_share_one_pool(tmp_path):
+    """The ranks' chains join ONE pool (NCCL all-reduce of the running sums inside rmn_sampler_run): every rank ends up
+    with the same covariance estimate, built from world x K samples per adaptation."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "two_rank_pool.py"
+    script.write_text(_TWO_RANK)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29579", str(script), root],
+                       capture_output=True, text=True, timeout=420)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ranks bit-identical" in r.stdout, r.stdout
