@@ -318,6 +318,18 @@ def _n3_pt_fixtures(R):
     g5 = R.MultiGaussianDist(mu5, C5)
     _pt_fixture(R, "pt_rw_gauss5d", g5, R.MetropolisRandomWalk(0.3 * C5), np.zeros(5), 800, 602,
                 extra=dict(C0=0.3 * C5, mu=mu5, C=C5))
+    _n3_pt_dense_fixture(R)
+
+
+def _n3_pt_dense_fixture(R):
+    """The same ladder on the dense-Gaussian device path (d = 12 > 8): dense proposal covariance."""
+    rng = np.random.Generator(np.random.Philox(11))
+    A = rng.standard_normal((12, 12))
+    C12 = A @ A.T / 12 + 0.2 * np.eye(12)
+    mu12 = rng.standard_normal(12)
+    g12 = R.MultiGaussianDist(mu12, C12)
+    _pt_fixture(R, "pt_rw_gauss12d", g12, R.MetropolisRandomWalk(0.15 * C12), np.zeros(12), 700, 603,
+                extra=dict(C0=0.15 * C12, mu=mu12, C=C12))
 
 
 def _n5_adaptcov_fixtures(R):
@@ -469,6 +481,9 @@ def main():
         return
     if "--only-n3-pt" in sys.argv:
         _n3_pt_fixtures(R)
+        return
+    if "--only-n3-pt-dense" in sys.argv:
+        _n3_pt_dense_fixture(R)
         return
     B = R.benchmarks
 

@@ -57,6 +57,11 @@ struct DenseState {
     double rho, rho_c;             // pCN (randomwalk.py:83-86)
     double* Pm;                    // [K][dp]   momentum of the trajectory (HMC with a mass matrix)
     int mass_base_prop;            // EPI_MASS_STEP: the position step starts from the proposal slot (interior steps)
+    // parallel tempering (ptsampler.py:11-127): nt = 0 off; rows l*nt .. l*nt + nt - 1 form ladder l
+    int nt; double pswap;
+    const double* betas;           // [nt]
+    double* ll;                    // [K] untempered log-likelihood of the current state (lp = beta * ll)
+    unsigned char* role;           // [K] role in the pending PT step: 0 within-chain step, 1 swap initiator, 2 partner
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -294,6 +299,9 @@ gemm_abt_kernel(DenseState st, const double* __restrict__ B) {
 struct DenseStep {
     int prop_kind;          // RMN_PROP_RW / RMN_PROP_HMC
     int adapt, rw_diag, finish, propose, diag, has_mass;
+    int record;             // write trace / diagnostics of the state after the finished step (= finish, except under
+                            // tempering, where a swap touches two rows and the record is taken by the NEXT launch)
+    const double* inj_usel; // tempering: injected selection uniforms of the step being proposed
     double target, eps0, c1, c2;
     const double* Ldiag;    // [dp] diagonal of chol(C0) when the RW covariance is diagonal
     uint64_t seed; int64_t chain_offset;
@@ -317,7 +325,34 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
     double lp = st.lp[r];
     const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
 
-    if (sp.finish) {
+    const bool pt = st.nt > 0;
+    const int ti = pt ? (int)((sp.chain_offset + r) % st.nt) : 0;
+    const double beta = pt ? st.betas[ti] : 1.0;
+    const int role = (pt && sp.finish) ? st.role[r] : 0;
+    if (sp.finish && role == 1) {
+        // ---- swap proposal with the next rung (ptsampler.py:113-125); this warp moves BOTH rows
+        const int64_t rj = r + 1;
+        const double beta_j = st.betas[ti + 1];
+        const double ll_i = st.ll[r], ll_j = st.ll[rj], lp_j = st.lp[rj];
+        const double lp_ij = combine_logpost(0.0, ll_j * beta);       // model_i at theta_j
+        const double lp_ji = combine_logpost(0.0, ll_i * beta_j);     // model_j at theta_i
+        const double x = exp((lp_ji + lp_ij) - (lp + lp_j));
+        const double mhr = (x < 1.0) ? x : 1.0;                        // Python min(1, x): nan -> 1
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        const bool sw = u < mhr;                                       // :121
+        if (sp.tr_acc && lane == 0) { sp.tr_acc[r] = sw ? 1 : 0; sp.tr_acc[rj] = sw ? 1 : 0; }
+        if (sp.tr_prop_lp && lane == 0) { sp.tr_prop_lp[r] = lp_ij; sp.tr_prop_lp[rj] = lp_ji; }
+        if (sw) {
+            const int cj = st.cur[rj];
+            double* yi = st.Y + ((int64_t)c * K + r) * dp;  double* yj = st.Y + ((int64_t)cj * K + rj) * dp;
+            double* vi = st.V + ((int64_t)c * K + r) * dp;  double* vj = st.V + ((int64_t)cj * K + rj) * dp;
+            for (int j = lane; j < dp; j += 32) {
+                const double a = yi[j], b = yj[j]; yi[j] = b; yj[j] = a;
+                const double e = vi[j], f = vj[j]; vi[j] = f; vj[j] = e;
+            }
+            if (lane == 0) { st.ll[r] = ll_j; st.ll[rj] = ll_i; st.lp[r] = lp_ij; st.lp[rj] = lp_ji; }
+        }
+    } else if (sp.finish && role == 0) {
         double q = 0.0, k1 = 0.0;
         for (int b = lane; b < st.nblk; b += 32) {
             q += st.partq[(int64_t)b * K + r];
@@ -327,7 +362,7 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
         q = group_sum<32>(q);
         k1 = group_sum<32>(k1);
         const double ll = -0.5 * ((q + sp.c1) + sp.c2);            // gaussian.py:52
-        const double lpn = combine_logpost(0.0, ll);
+        const double lpn = combine_logpost(0.0, pt ? ll * beta : ll);   // TemperedModel: logL * beta (ptsampler.py:33-34)
         // HMC: kinetic-energy difference (hamiltonian.py:89); pCN: -(|u_fwd|^2 - |u_rev|^2)/2 with
         // u_fwd = (rho_c L)^-1 (theta' - rho theta) = xi (randomwalk.py:95-100)
         const double lqr = (sp.prop_kind == RMN_PROP_HMC) ? 0.5 * (k1 - st.k0[r])
@@ -341,7 +376,7 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
         if (sp.tr_lqr && lane == 0) sp.tr_lqr[r] = lqr;
         if (acc) { c ^= 1; lp = lpn; }
         if (lane == 0) {
-            if (acc) { st.cur[r] = c; st.lp[r] = lp; }
+            if (acc) { st.cur[r] = c; st.lp[r] = lp; if (pt) st.ll[r] = ll; }
             st.dacc[r] += acc ? 1 : 0;
             if (sp.adapt) {
                 AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
@@ -350,8 +385,28 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
             }
             if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
             if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
-            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+            if (!pt && sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
         }
+    }
+    if (!sp.propose && !sp.record) return;           // tempering: the finish-only launch ends here
+    if (pt && sp.record && lane == 0 && sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+
+    // ---- tempering: roles of the step being proposed (ptsampler.py:102-112): chain i initiates a swap with i+1 iff it
+    //      was not itself swapped by i-1, u <= Pswap and it is not the last rung; sequential along the ladder
+    int role_next = 0;
+    if (pt && sp.propose) {
+        const int64_t r0 = r - ti;
+        double usel = 1.0;
+        if (lane < st.nt) {
+            usel = sp.inj_usel ? sp.inj_usel[r0 + lane]
+                               : u01(RngKey(sp.seed, (uint64_t)(sp.chain_offset + r0 + lane)).block((uint64_t)sp.step_prop, RMN_BLOCK_AUX).x);
+        }
+        const unsigned wmask = __ballot_sync(0xffffffffu, lane < st.nt - 1 && !(usel > st.pswap));
+        unsigned init = 0;
+        for (int b = 0; b < st.nt - 1; ++b)
+            if (((wmask >> b) & 1u) && !(b > 0 && ((init >> (b - 1)) & 1u))) init |= 1u << b;
+        role_next = ((init >> ti) & 1u) ? 1 : ((ti > 0 && ((init >> (ti - 1)) & 1u)) ? 2 : 0);
+        if (lane == 0) st.role[r] = (unsigned char)role_next;
     }
     __syncwarp();
 
@@ -362,7 +417,8 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
     const double scale = sp.adapt ? st.scale[r] : 1.0;
     const double eps = (sp.prop_kind == RMN_PROP_HMC) ? scale * sp.eps0 : scale;
     double k0 = 0.0, rowsum = 0.0;
-    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+    const bool want_trace = sp.record && sp.trace_slot >= 0 && sp.tr_theta;
+    const bool do_propose = sp.propose && role_next == 0;    // swap rows draw no proposal (ptsampler.py:106-125)
 
     for (int j4 = lane * 4; j4 < dp; j4 += 128) {
         const double2 ya = *reinterpret_cast<const double2*>(y + j4);
@@ -374,7 +430,7 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
             for (int q = 0; q < 4; ++q)
                 if (j4 + q < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j4 + q] = yv[q] + st.mu[j4 + q];
         }
-        if (!sp.propose) continue;
+        if (!do_propose) continue;
         double xi[4];
         if (sp.inj_xi) {
 #pragma unroll
@@ -413,7 +469,7 @@ finish_propose_kernel(DenseState st, DenseStep sp) {
         *reinterpret_cast<double2*>(yp + j4) = make_double2(out[0], out[1]);
         *reinterpret_cast<double2*>(yp + j4 + 2) = make_double2(out[2], out[3]);
     }
-    if (sp.propose) {
+    if (do_propose) {
         k0 = group_sum<32>(k0);
         if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
     }
@@ -482,7 +538,13 @@ __global__ void dense_adopt_kernel(DenseState st, double c1, double c2) {
     q = group_sum<32>(q);
     if (lane == 0) {
         st.cur[r] = 1;
-        st.lp[r] = combine_logpost(0.0, -0.5 * ((q + c1) + c2));
+        const double ll = -0.5 * ((q + c1) + c2);
+        if (st.nt > 0) {
+            st.ll[r] = ll;
+            st.lp[r] = combine_logpost(0.0, ll * st.betas[r % st.nt]);   // chain_offset is a multiple of nt (set_tempering)
+        } else {
+            st.lp[r] = combine_logpost(0.0, ll);
+        }
     }
 }
 __global__ void dense_get_kernel(DenseState st, double* theta, double* lp) {
@@ -624,6 +686,28 @@ struct DenseGaussSampler : SamplerImpl {
     double* d_mupad = nullptr;
     bool rw_diag = true;
     bool pending = false;         // a proposal is in flight (written, GEMM done, not finished)
+    // parallel tempering
+    double* d_betas = nullptr;
+    int set_tempering(int nt, const double* betas, double pswap) override {
+        const rmn_proposal* pr = s->prop;
+        RMN_REQUIRE(nt >= 2 && nt <= 32 && betas, "set_tempering: need 2 <= nt <= 32 temperatures");
+        RMN_REQUIRE(pswap > 0.0 && pswap < 1.0, "Pswap must be a number between 0 and 1");
+        RMN_REQUIRE(s->K % nt == 0, "set_tempering: the number of chains (%lld) must be a multiple of nt = %d", (long long)s->K, nt);
+        RMN_REQUIRE(s->chain_offset % nt == 0, "set_tempering: chain_offset must be a multiple of nt");
+        RMN_REQUIRE(!pr->adapt && !pr->pool_cov, "parallel tempering supports non-adaptive proposals only (the reference shares ONE "
+                                                 "proposal object between all temperatures, ptsampler.py:81)");
+        RMN_REQUIRE(pr->kind != RMN_PROP_HMC, "parallel tempering: the HMC gradient is not tempered in the reference; use RW or pCN");
+        for (int i = 0; i < nt; ++i) RMN_REQUIRE(betas[i] >= 0.0 && betas[i] <= 1.0, "beta = %g must be a number between 0 and 1", betas[i]);
+        if (!d_betas) RMN_CUDA(cudaMalloc(&d_betas, 32 * 8));
+        RMN_CUDA(cudaMemcpy(d_betas, betas, (size_t)nt * 8, cudaMemcpyHostToDevice));
+        if (!st.ll) {
+            RMN_CUDA(cudaMalloc(&st.ll, (size_t)st.K * 8));
+            RMN_CUDA(cudaMalloc(&st.role, (size_t)st.K));
+            RMN_CUDA(cudaMemset(st.role, 0, (size_t)st.K));
+        }
+        st.betas = d_betas; st.nt = nt; st.pswap = pswap;
+        return RMN_OK;
+    }
     // pooled covariance adaptation
     double* d_pS1 = nullptr; double* d_pS2 = nullptr; double* d_pU = nullptr; int* d_pstatus = nullptr;
     double pool_n = 0.0;          // samples in the sums (all ranks)
@@ -641,6 +725,7 @@ struct DenseGaussSampler : SamplerImpl {
         cudaFree(d_Ppad); cudaFree(d_Lpad); cudaFree(d_Linvpad); cudaFree(d_Ldiag); cudaFree(d_mupad);
         cudaFree(d_chM); cudaFree(d_Minv); cudaFree(d_chMinv);
         cudaFree(d_pS1); cudaFree(d_pS2); cudaFree(d_pU); cudaFree(d_pstatus); cudaFree(d_pS1g); cudaFree(d_pS2g);
+        cudaFree(d_betas); cudaFree(st.ll); cudaFree(st.role);
         rmn_rowcomm_destroy(&poolc);
     }
     size_t row_bytes() const { return align256((size_t)st.K * st.dp * 8); }
@@ -786,6 +871,7 @@ struct DenseGaussSampler : SamplerImpl {
     int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
         const rmn_proposal* pr = s->prop;
         if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        if (inj && st.nt > 0) RMN_REQUIRE(inj->d_usel, "injected tempered run needs d_usel (selection uniforms)");
         rmn_trace_t t0{};
         if (tr) t0 = *tr;
         if (t0.thin <= 0) t0.thin = 1;
@@ -799,10 +885,11 @@ struct DenseGaussSampler : SamplerImpl {
         const int d = st.d;
         // iteration t: [finish step t-1 | propose step t] ; GEMM(s).  A last call finishes step T-1.
         for (int64_t t = 0; t <= T; ++t) {
-            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
+            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0); sp.record = sp.finish;
             sp.step_fin = step0 + t - 1; sp.step_prop = step0 + t;
             sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;
             sp.inj_xi = (inj && t < T) ? inj->d_xi + t * K * d : nullptr;
+            sp.inj_usel = (inj && st.nt > 0 && t < T) ? inj->d_usel + t * K : nullptr;
             sp.trace_slot = -1;
             sp.tr_theta = t0.d_theta; sp.tr_logpost = t0.d_logpost;
             sp.tr_prop_lp = (t0.d_prop_logpost && t > 0) ? t0.d_prop_logpost + (t - 1) * K : nullptr;
@@ -816,13 +903,25 @@ struct DenseGaussSampler : SamplerImpl {
             const int64_t gstep = step0 + t;       // index of the step about to be proposed
             const bool adapt_now = pr->pool_cov && t < T && gstep > 0 && gstep % pr->pool_t_adapt == 0 &&
                                    (pr->pool_stop == 0 || gstep <= pr->pool_stop);
-            if (adapt_now && sp.finish) {
+            if (st.nt > 0) {
+                // tempering: a swap moves TWO rows, so the step is finished by one launch (the initiator's warp exchanges
+                // both rows) and recorded / followed by the next proposal in a second one
+                if (sp.finish) {
+                    DenseStep fin = sp; fin.propose = 0; fin.record = 0; fin.diag = 0;
+                    finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, fin);
+                    RMN_KERNEL_CHECK(); launches++;
+                }
+                DenseStep pro = sp; pro.finish = 0;
+                pro.tr_prop_lp = nullptr; pro.tr_acc = nullptr; pro.tr_lqr = nullptr; pro.tr_prop_theta = nullptr;
+                finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, pro);
+                RMN_KERNEL_CHECK(); launches++;
+            } else if (adapt_now && sp.finish) {
                 // the new factor must be in place before step gstep is proposed: finish step gstep-1 on its own first
                 DenseStep fin = sp; fin.propose = 0;
                 finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, fin);
                 RMN_KERNEL_CHECK(); launches++;
                 if (int rc = pool_adapt(stream)) return rc;
-                DenseStep pro = sp; pro.finish = 0; pro.diag = 0; pro.trace_slot = -1;
+                DenseStep pro = sp; pro.finish = 0; pro.diag = 0; pro.record = 0; pro.trace_slot = -1;
                 pro.tr_prop_lp = nullptr; pro.tr_acc = nullptr; pro.tr_lqr = nullptr; pro.tr_prop_theta = nullptr;
                 finish_propose_kernel<<<row_grid(), 256, 0, stream>>>(st, pro);
                 RMN_KERNEL_CHECK(); launches++;

@@ -20,7 +20,8 @@ def _pt(g, d, K=1, **kw):
     return PTSampler(device_gauss(g, d), MetropolisRandomWalk(g["C0"]), g["thetas"][0, 0], K=K, **kw)
 
 
-@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5)])
+@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5),
+                                    ("pt_rw_gauss12d", 12)])       # d > 8: the dense-Gaussian device path
 def test_injected_ladder_matches_reference(golden, name, d):
     g = golden(name)
     pt = _pt(g, d)
@@ -35,8 +36,14 @@ def test_injected_ladder_matches_reference(golden, name, d):
     kind = g["kind"]
     moved_ref = np.any(g["thetas"][:, 1:] != g["thetas"][:, :-1], axis=2).T   # [T][nt]
     acc = ex["accepted"].astype(bool)                                         # [T][nt]
-    assert np.array_equal(acc[kind == 1], moved_ref[kind == 1])
-    assert np.array_equal(acc[kind == 2], moved_ref[kind == 2])
+    # (a swap of two IDENTICAL states -- every rung starts at theta0 -- is accepted without anything moving)
+    th = g["thetas"]                                                          # [nt][T+1][d]
+    same_next = np.zeros((T, nt), dtype=bool)
+    same_next[:, :-1] = np.all(th[:-1, :-1] == th[1:, :-1], axis=2).T         # rung i and i+1 equal before step t
+    same_prev = np.zeros((T, nt), dtype=bool)
+    same_prev[:, 1:] = same_next[:, :-1]
+    assert np.array_equal(acc[kind == 1], (moved_ref | same_next)[kind == 1])
+    assert np.array_equal(acc[kind == 2], (moved_ref | same_prev)[kind == 2])
 
 
 def test_many_ladders_each_replay_the_stream(golden):
@@ -141,3 +148,32 @@ def test_diagnostics_use_the_base_temperature_only():
     assert np.all(np.abs(dg["mean"][:2]) < 0.05), dg["mean"]
     assert np.all(flat["var"][:2] > 3.0)                     # pooled over beta = 1 .. 1/16: (1+2+4+8+16)/5 = 6.2
     assert 0.0 < dg["accept_rate_all_rungs"] < 1.0 and dg["swap_fraction"] == 0.1
+
+
+def test_dense_path_ladders_replay_and_sample(golden):
+    """d = 12 (dense path): 7 ladders fed the reference's stream each reproduce it; in Philox mode every rung samples
+    its tempered target N(mu, C / beta) and the carried log-posterior is beta * logL of the state."""
+    from scipy import stats
+    g = golden("pt_rw_gauss12d")
+    K, T = 7, 300
+    pt = _pt(g, 12, K=K)
+    rep = lambda a: np.concatenate([a[:T]] * K, axis=1)
+    pt.run_injected(rep(g["usel"]), rep(g["xi"]), rep(g["u"]))
+    for rung in (0, 2, 4):
+        th, lp = pt.samplers[rung]._chain_thetas, pt.samplers[rung]._chain_logpost
+        for l in (0, 3, 6):
+            assert relerr(th[:, l], g["thetas"][rung, :T + 1]) < TOL
+            assert relerr(lp[:, l], g["logpost"][rung, :T + 1]) < TOL
+    pt2 = _pt(g, 12, K=400, seed=2)
+    pt2.run(4000, trace=False)
+    th = pt2._thetas[-1]                                                      # [K, nt, d]
+    Linv = np.linalg.inv(np.linalg.cholesky(g["C"]))
+    for i, beta in enumerate(pt2.betas):
+        z = (th[:, i] - g["mu"]) @ Linv.T * np.sqrt(beta)                     # whitened: N(0, I) per coordinate
+        assert stats.kstest(z[:, 0], "norm").pvalue > 1e-3, (i, beta)
+        assert stats.kstest(z[:, 7], "norm").pvalue > 1e-3, (i, beta)
+    m = device_gauss(g, 12)
+    ll = m.log_posterior_batch(th.reshape(-1, 12)).cpu().numpy().reshape(400, -1)
+    assert relerr(pt2._logpost[-1], ll * pt2.betas[None, :]) < 1e-10
+    dg = pt2.diagnostics()
+    assert dg["chains"] == 400 and dg["temperatures"] == 5

@@ -180,7 +180,7 @@ def test_live_stream_matches_tape(golden):
     assert np.max(np.abs(np.array(s._chain_logpost) - g["logpost"][0, :1501])) < TOL
 
 
-@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5)])
+@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5), ("pt_rw_gauss12d", 12)])
 def test_parallel_tempering(golden, name, d):
     """N3: port.PTSampler replays the recorded stream of the reference's PTSampler (ptsampler.py:41-127):
     every temperature's chain, log-posterior and swap decision."""
