@@ -38,6 +38,11 @@ void set_debug_stamp(long long* p);
 int prepare_kernels();
 }
 
+size_t dense_exact_scratch_bytes(int64_t K, int d);
+int dense_exact_prepare(int64_t K, int d, const double* d_prec, void* scratch);
+int dense_exact_pass(int64_t K, int d, int dpf, const float* Yf, float* Vf, double* lp, double c1, double c2, void* scratch,
+                     cudaStream_t stream);
+
 namespace {
 
 constexpr int ND_MAX = 8;
@@ -273,53 +278,6 @@ __global__ void tset_kernel(TState st, const double* __restrict__ theta) {
     st.Yph[i] = 0.0f; st.Ypl[i] = 0.0f; st.Vp[i] = 0.0f; st.V[i] = 0.0f;
     if (j == 0) { st.k0[r] = 0.0; st.epsrow[r] = 0.0; }
 }
-// Exact (fp64) V = P y and log-posterior of the CURRENT fp32 states: start of a run and the
-// periodic refresh.  One block per RB = 8 chain rows (their y staged in shared memory), so every row of P a
-// warp reads serves 8 chains: one row per block streamed all of P (8 MB at d = 1000) from L2 per chain,
-// 131 GB per pass and 11.5 ms at config 3; this blocking brings it to the 2 ms range.
-constexpr int TEX_RB = 8;
-__global__ void __launch_bounds__(256) texact_kernel(TState st, double c1, double c2) {
-    extern __shared__ double ysh[];                      // [TEX_RB][d]
-    __shared__ double red[8][TEX_RB];
-    const int64_t r0 = (int64_t)blockIdx.x * TEX_RB;
-    const int d = st.d, dp = st.dp;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = threadIdx.x; q < TEX_RB * d; q += blockDim.x) {
-        const int rr = q / d, j = q % d;
-        ysh[q] = (r0 + rr < st.K) ? (double)st.Y[(size_t)(r0 + rr) * dp + j] : 0.0;
-    }
-    __syncthreads();
-    double quad[TEX_RB];
-#pragma unroll
-    for (int rr = 0; rr < TEX_RB; ++rr) quad[rr] = 0.0;
-    for (int j = warp; j < d; j += 8) {
-        const double* pr = st.prec + (size_t)j * d;
-        double s[TEX_RB];
-#pragma unroll
-        for (int rr = 0; rr < TEX_RB; ++rr) s[rr] = 0.0;
-        for (int k = lane; k < d; k += 32) {
-            const double pk = pr[k];
-#pragma unroll
-            for (int rr = 0; rr < TEX_RB; ++rr) s[rr] += pk * ysh[rr * d + k];
-        }
-#pragma unroll
-        for (int rr = 0; rr < TEX_RB; ++rr) {
-            const double t = group_sum<32>(s[rr]);
-            if (lane == 0 && r0 + rr < st.K) st.V[(size_t)(r0 + rr) * dp + j] = (float)t;
-            quad[rr] += t * ysh[rr * d + j];
-        }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int rr = 0; rr < TEX_RB; ++rr) red[warp][rr] = quad[rr];
-    }
-    __syncthreads();
-    if (threadIdx.x < TEX_RB && r0 + threadIdx.x < st.K) {
-        double q = 0.0;
-        for (int w = 0; w < 8; ++w) q += red[w][threadIdx.x];
-        st.lp[r0 + threadIdx.x] = combine_logpost(0.0, -0.5 * ((q + c1) + c2));
-    }
-}
 __global__ void tget_kernel(TState st, double* theta, double* lp) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= st.K * st.d) return;
@@ -390,7 +348,7 @@ struct DenseTF32Sampler : SamplerImpl {
         if (cap_stream2) cudaStreamDestroy(cap_stream2);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
-        cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base); cudaFree(d_tl);
+        cudaFree(d_Ph); cudaFree(d_Pl); cudaFree(d_Ldiag); cudaFree(d_mupad); cudaFree(d_step_base); cudaFree(d_tl); cudaFree(d_exact);
     }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 4); }
     size_t workspace_bytes() const override {
@@ -523,16 +481,16 @@ struct DenseTF32Sampler : SamplerImpl {
         RMN_KERNEL_CHECK(); launches++;
         return exact(stream);
     }
+    // Exact (fp64) V = Y P and log-posterior of the CURRENT fp32 states: start of a run and the periodic refresh, as one
+    // fp64 DMMA GEMM on widened copies (dense.cu: dense_exact_pass)
+    void* d_exact = nullptr;
     int exact(cudaStream_t stream) {
-        const size_t sm = (size_t)TEX_RB * st.d * 8;
-        static bool attr_set = false;
-        if (!attr_set && sm > 48 * 1024) {
-            RMN_RAISE_SMEM(texact_kernel, 200 * 1024);
-            attr_set = true;
+        if (!d_exact) {
+            RMN_CUDA(cudaMalloc(&d_exact, dense_exact_scratch_bytes(st.K, st.d)));
+            if (int rc = dense_exact_prepare(st.K, st.d, st.prec, d_exact)) return rc;
         }
-        RMN_REQUIRE(sm <= 200 * 1024, "tf32x3 dense path: d = %d exceeds the exact-refresh kernel's shared memory", st.d);
-        texact_kernel<<<(unsigned)((st.K + TEX_RB - 1) / TEX_RB), 256, sm, stream>>>(st, c1(), s->model->logdetC);
-        RMN_KERNEL_CHECK(); launches++;
+        if (int rc = dense_exact_pass(st.K, st.d, st.dp, st.Y, st.V, st.lp, c1(), s->model->logdetC, d_exact, stream)) return rc;
+        launches += 3;
         since_refresh = 0;
         return RMN_OK;
     }
