@@ -231,7 +231,8 @@ int rmn_sampler_destroy(rmn_sampler_t* s);
 /* AdaptCovProposal.L of every chain: d_L[K][d][d] (lower triangular). */
 int rmn_sampler_get_adaptcov(rmn_sampler_t* s, double* d_L, void* stream);
 
-/* PTSampler (riemann/samplers/ptsampler.py:41-127) on the Gaussian models (small-d and dense path, f64): chains c = l*nt + i form ladder l,
+/* PTSampler (riemann/samplers/ptsampler.py:41-127) on the Gaussian models (small-d and dense path, f64) and the logistic
+ * model (any precision; the prior is not tempered): chains c = l*nt + i form ladder l,
  * chain i of a ladder samples TemperedModel(model, h_betas[i]) (likelihood * beta, :33-34); every step each chain either
  * takes a within-chain MH step or, with probability pswap and sequentially along the ladder exactly as :102-125,
  * proposes a swap with its lower neighbour.  K must be a multiple of nt (2..32); non-adaptive RW / pCN proposals.

@@ -319,6 +319,28 @@ def _n3_pt_fixtures(R):
     _pt_fixture(R, "pt_rw_gauss5d", g5, R.MetropolisRandomWalk(0.3 * C5), np.zeros(5), 800, 602,
                 extra=dict(C0=0.3 * C5, mu=mu5, C=C5))
     _n3_pt_dense_fixture(R)
+    _n3_pt_logistic_fixture(R)
+
+
+def _n3_pt_logistic_fixture(R):
+    """The ladder on the logistic model (absent in the reference: the port's model behind the reference's Model base,
+    driven by the reference's own PTSampler / TemperedModel / MetropolisRandomWalk): the prior is NOT tempered."""
+    N, d = 400, 6
+    X, y, theta_star, pv = port.make_logistic_problem(N, d, seed=port.SEED_BASE + 61)
+    pmodel = port.LogisticRegression(X, y, pv)
+
+    class RefLogistic(R.Model):
+        def log_prior(self, theta):
+            return pmodel.log_prior(theta)
+
+        def log_likelihood(self, theta):
+            return pmodel.log_likelihood(theta)
+
+    rng = np.random.Generator(np.random.Philox(13))
+    A = rng.standard_normal((d, d))
+    C0 = 0.02 * (A @ A.T / d + 0.5 * np.eye(d))
+    _pt_fixture(R, "pt_rw_logistic", RefLogistic(), R.MetropolisRandomWalk(C0), theta_star + 0.05, 600, 604,
+                extra=dict(C0=C0, X=X, y=y, prior_var=np.float64(pv)))
 
 
 def _n3_pt_dense_fixture(R):
@@ -484,6 +506,9 @@ def main():
         return
     if "--only-n3-pt-dense" in sys.argv:
         _n3_pt_dense_fixture(R)
+        return
+    if "--only-n3-pt-logistic" in sys.argv:
+        _n3_pt_logistic_fixture(R)
         return
     B = R.benchmarks
 

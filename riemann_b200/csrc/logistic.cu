@@ -109,6 +109,11 @@ struct LogisticState {
     const double* PL; const double* PLinv;     // RW / pCN: L and L^-1 of the proposal covariance; HMC with a mass matrix: chM, chM^-1
     const double* Minv;                        // HMC with a mass matrix: M^-1 (NULL otherwise)
     double rho, rho_c;
+    // parallel tempering (ptsampler.py:11-127): nt = 0 off; rows l*nt .. l*nt + nt - 1 form ladder l; lp = lprior + beta * ll
+    int nt; double pswap;
+    const double* betas;                       // [nt]
+    double* llc; double* lpriorc;              // [K] log-likelihood / log-prior of the current state
+    unsigned char* role;                       // [K] role in the pending step: 0 within-chain, 1 swap initiator, 2 partner
     // mMALA
     double* Gm;      // [K][d][d]   metric of the pending proposal (likelihood part)
     double* Lc;      // [2][K][d][d] Cholesky factors (current / proposal slot follows cur)
@@ -509,6 +514,8 @@ lg_leapfrog_mid_mass_kernel(LogisticState st) {
 enum { LG_HMC = 0, LG_RW = 1, LG_PCN = 2 };   // the non-mMALA proposals of lg_finish_propose_kernel<false>
 struct LgStep {
     int mmala, adapt, finish, propose, diag;
+    int record;             // trace / diagnostics of the state after the finished step (= finish, except under tempering)
+    const double* inj_usel; // tempering: injected selection uniforms of the step being proposed
     int pkind;
     double target, eps0;
     uint64_t seed; int64_t chain_offset, step_fin, step_prop;
@@ -584,7 +591,38 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
     const RngKey rk(sp.seed, (uint64_t)(sp.chain_offset + r));
     const double pvinv = 1.0 / st.pv;
 
-    if (sp.finish) {
+    const bool pt = !MMALA && st.nt > 0;
+    const int ti = pt ? (int)((sp.chain_offset + r) % st.nt) : 0;
+    const double beta = pt ? st.betas[ti] : 1.0;
+    const int role = (pt && sp.finish) ? st.role[r] : 0;
+    if (sp.finish && role == 1) {
+        // ---- swap proposal with the next rung (ptsampler.py:113-125); this warp moves BOTH rows.  TemperedModel scales
+        //      the likelihood only (:33-37): log-posterior of model i at theta_j = lprior_j + beta_i ll_j
+        const int64_t rj = r + 1;
+        const double beta_j = st.betas[ti + 1];
+        const double ll_i = st.llc[r], ll_j = st.llc[rj], pr_i = st.lpriorc[r], pr_j = st.lpriorc[rj], lp_j = st.lp[rj];
+        const double lp_ij = combine_logpost(pr_j, ll_j * beta);
+        const double lp_ji = combine_logpost(pr_i, ll_i * beta_j);
+        const double x = exp((lp_ji + lp_ij) - (lp + lp_j));
+        const double mhr = (x < 1.0) ? x : 1.0;                        // Python min(1, x): nan -> 1
+        const double u = sp.inj_u ? sp.inj_u[r] : u01(rk.block((uint64_t)sp.step_fin, RMN_BLOCK_ACCEPT).x);
+        const bool sw = u < mhr;                                       // :121
+        if (sp.tr_acc && lane == 0) { sp.tr_acc[r] = sw ? 1 : 0; sp.tr_acc[rj] = sw ? 1 : 0; }
+        if (sp.tr_prop_lp && lane == 0) { sp.tr_prop_lp[r] = lp_ij; sp.tr_prop_lp[rj] = lp_ji; }
+        if (sw) {
+            const int cj = st.cur[rj];
+            double* ti_ = st.Th + ((int64_t)c * K + r) * dp;  double* tj_ = st.Th + ((int64_t)cj * K + rj) * dp;
+            double* gi_ = st.Gr + ((int64_t)c * K + r) * dp;  double* gj_ = st.Gr + ((int64_t)cj * K + rj) * dp;
+            for (int j = lane; j < dp; j += 32) {
+                const double a = ti_[j], b = tj_[j]; ti_[j] = b; tj_[j] = a;
+                const double e = gi_[j], f = gj_[j]; gi_[j] = f; gj_[j] = e;
+            }
+            if (lane == 0) {
+                st.llc[r] = ll_j; st.llc[rj] = ll_i; st.lpriorc[r] = pr_j; st.lpriorc[rj] = pr_i;
+                st.lp[r] = lp_ij; st.lp[rj] = lp_ji;
+            }
+        }
+    } else if (sp.finish && role == 0) {
         const int pslot = c ^ 1;
         const double* thp = st.Th + ((int64_t)pslot * K + r) * dp;
         const double* thc = st.Th + ((int64_t)c * K + r) * dp;
@@ -635,7 +673,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
         tt = group_sum<32>(tt);
         k1 = group_sum<32>(k1);
         const double lprior = -0.5 * tt * pvinv - 0.5 * (double)d * log(2.0 * M_PI * st.pv);
-        const double lpn = combine_logpost(lprior, ll);
+        const double lpn = combine_logpost(lprior, pt ? ll * beta : ll);    // TemperedModel (ptsampler.py:33-34)
         double lqr;
         if (!MMALA) {
             if (sp.pkind == LG_HMC) lqr = 0.5 * (k1 - st.k0[r]);          // hamiltonian.py:89
@@ -682,7 +720,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
         if (sp.tr_lqr && lane == 0) sp.tr_lqr[r] = lqr;
         if (acc) { c ^= 1; lp = lpn; }
         if (lane == 0) {
-            if (acc) { st.cur[r] = c; st.lp[r] = lp; }
+            if (acc) { st.cur[r] = c; st.lp[r] = lp; if (pt) { st.llc[r] = ll; st.lpriorc[r] = lprior; } }
             st.dacc[r] += acc ? 1 : 0;
             if (sp.adapt) {
                 AdaptState ad{st.scale[r], st.nsamp[r], st.nacc[r]};
@@ -691,10 +729,29 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             }
             if (sp.tr_prop_lp) sp.tr_prop_lp[r] = lpn;
             if (sp.tr_acc) sp.tr_acc[r] = acc ? 1 : 0;
-            if (sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+            if (!pt && sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
         }
         __syncwarp();
     }
+    if (!sp.propose && !sp.record) return;           // tempering: the finish-only launch ends here
+    if (pt && sp.record && lane == 0 && sp.trace_slot >= 0 && sp.tr_logpost) sp.tr_logpost[sp.trace_slot * K + r] = lp;
+    // tempering: roles of the step being proposed (ptsampler.py:102-112), sequential along the ladder
+    int role_next = 0;
+    if (pt && sp.propose) {
+        const int64_t r0 = r - ti;
+        double usel = 1.0;
+        if (lane < st.nt) {
+            usel = sp.inj_usel ? sp.inj_usel[r0 + lane]
+                               : u01(RngKey(sp.seed, (uint64_t)(sp.chain_offset + r0 + lane)).block((uint64_t)sp.step_prop, RMN_BLOCK_AUX).x);
+        }
+        const unsigned wmask = __ballot_sync(0xffffffffu, lane < st.nt - 1 && !(usel > st.pswap));
+        unsigned init = 0;
+        for (int b = 0; b < st.nt - 1; ++b)
+            if (((wmask >> b) & 1u) && !(b > 0 && ((init >> (b - 1)) & 1u))) init |= 1u << b;
+        role_next = ((init >> ti) & 1u) ? 1 : ((ti > 0 && ((init >> (ti - 1)) & 1u)) ? 2 : 0);
+        if (lane == 0) st.role[r] = (unsigned char)role_next;
+    }
+    const bool do_propose = sp.propose && role_next == 0;    // swap rows draw no proposal
 
     const double* th = st.Th + ((int64_t)c * K + r) * dp;
     const double* gr = st.Gr + ((int64_t)c * K + r) * dp;
@@ -702,7 +759,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
     double* xo = st.Xi + r * dp;
     const double scale = sp.adapt ? st.scale[r] : 1.0;
     const double eps = scale * sp.eps0;                                  // RW: eps0 = 1, so eps is the scale (randomwalk.py:26)
-    const bool want_trace = sp.finish && sp.trace_slot >= 0 && sp.tr_theta;
+    const bool want_trace = sp.record && sp.trace_slot >= 0 && sp.tr_theta;
     double k0 = 0.0, rowsum = 0.0;
 
     if (MMALA && sp.propose) {
@@ -711,7 +768,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
     }
     for (int j4 = lane * 4; j4 < dp; j4 += 128) {
         double xi[4];
-        if (sp.propose) {
+        if (do_propose) {
             if (sp.inj_xi) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) xi[q] = (j4 + q < d) ? sp.inj_xi[r * d + j4 + q] : 0.0;
@@ -728,7 +785,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             const double tv = th[j];
             rowsum += tv;
             if (want_trace && j < d) sp.tr_theta[(sp.trace_slot * K + r) * d + j] = tv;
-            if (!sp.propose) continue;
+            if (!do_propose) continue;
             k0 += xi[q] * xi[q];
             if (!MMALA && (sp.pkind != LG_HMC || st.Minv)) {
                 xo[j] = xi[q];     // staged for the L xi (chM xi) product below
@@ -742,7 +799,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             }
         }
     }
-    if (!MMALA && sp.propose && sp.pkind != LG_HMC) {
+    if (!MMALA && do_propose && sp.pkind != LG_HMC) {
         // theta' = theta + scale L xi (randomwalk.py:25-26) or rho theta + rho_c L xi (:93), L lower triangular
         __syncwarp();
         const double a0 = (sp.pkind == LG_PCN) ? st.rho : 1.0, a1 = (sp.pkind == LG_PCN) ? st.rho_c : eps;
@@ -753,7 +810,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             thn[j] = (j < d) ? a0 * th[j] + a1 * sacc : 0.0;
         }
     }
-    if (!MMALA && sp.propose && sp.pkind == LG_HMC && st.Minv) {
+    if (!MMALA && do_propose && sp.pkind == LG_HMC && st.Minv) {
         // VanillaHMC with a mass matrix (hamiltonian.py:79-88, leapfrog :26-30):
         //   p0 = chM xi,  k0 = |solve(chM, p0)|^2,  p_half = p0 + eps/2 grad,  theta' = theta + eps solve(M, p_half)
         // staged through the chain's own rows: xi in Xi, p0 in the proposal slot, then p_half in Xi
@@ -788,7 +845,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
         for (int j = lane; j < dp; j += 32)
             thn[j] = (j < d) ? (th[j] + 0.5 * eps * eps * nc[j]) + eps * v1[j] : 0.0;
     }
-    if (sp.propose) {
+    if (do_propose) {
         k0 = group_sum<32>(k0);
         if (lane == 0) { st.k0[r] = k0; st.epsrow[r] = eps; }
     }
@@ -854,7 +911,12 @@ lg_adopt_kernel(LogisticState st) {
     }
     if (lane == 0) {
         const double lprior = -0.5 * tt * pvinv - 0.5 * (double)d * log(2.0 * M_PI * st.pv);
-        st.lp[r] = combine_logpost(lprior, ll);
+        if (!MMALA && st.nt > 0) {
+            st.llc[r] = ll; st.lpriorc[r] = lprior;
+            st.lp[r] = combine_logpost(lprior, ll * st.betas[r % st.nt]);     // chain_offset is a multiple of nt
+        } else {
+            st.lp[r] = combine_logpost(lprior, ll);
+        }
         st.cur[r] = 1;
     }
 }
@@ -945,8 +1007,33 @@ struct LogisticSampler : SamplerImpl {
     lgf::Geometry fg{};
     lgf::Maps fmaps{};
     float* fXh = nullptr; float* fXl = nullptr; uint32_t* fys = nullptr; double* fllp = nullptr; float* fgp = nullptr;
+    double* d_betas = nullptr;
+    int set_tempering(int nt, const double* betas, double pswap) override {
+        const rmn_proposal* pr = s->prop;
+        RMN_REQUIRE(nt >= 2 && nt <= 32 && betas, "set_tempering: need 2 <= nt <= 32 temperatures");
+        RMN_REQUIRE(pswap > 0.0 && pswap < 1.0, "Pswap must be a number between 0 and 1");
+        RMN_REQUIRE(s->K % nt == 0, "set_tempering: the number of chains (%lld) must be a multiple of nt = %d", (long long)s->K, nt);
+        RMN_REQUIRE(s->chain_offset % nt == 0, "set_tempering: chain_offset must be a multiple of nt");
+        RMN_REQUIRE(!mmala && pkind != LG_HMC, "parallel tempering on the logistic model: RW or pCN proposals (the reference shares one "
+                                               "proposal between the temperatures and does not temper the HMC gradient, ptsampler.py:81)");
+        RMN_REQUIRE(!pr->adapt, "parallel tempering supports non-adaptive proposals only (ptsampler.py:81)");
+        for (int i = 0; i < nt; ++i) RMN_REQUIRE(betas[i] >= 0.0 && betas[i] <= 1.0, "beta = %g must be a number between 0 and 1", betas[i]);
+        if (!d_betas) RMN_CUDA(cudaMalloc(&d_betas, 32 * 8));
+        RMN_CUDA(cudaMemcpy(d_betas, betas, (size_t)nt * 8, cudaMemcpyHostToDevice));
+        if (!st.llc) {
+            RMN_CUDA(cudaMalloc(&st.llc, (size_t)st.K * 8));
+            RMN_CUDA(cudaMalloc(&st.lpriorc, (size_t)st.K * 8));
+            RMN_CUDA(cudaMalloc(&st.role, (size_t)st.K));
+            RMN_CUDA(cudaMemset(st.role, 0, (size_t)st.K));
+        }
+        st.betas = d_betas; st.nt = nt; st.pswap = pswap;
+        return RMN_OK;
+    }
     RowComm rowc;               // row-sharded data mode: the ranks that hold the other slices of X
-    ~LogisticSampler() override { rmn_rowcomm_destroy(&rowc); cudaFree(d_PL); cudaFree(d_PLinv); cudaFree(d_Minv); }
+    ~LogisticSampler() override {
+        rmn_rowcomm_destroy(&rowc); cudaFree(d_PL); cudaFree(d_PLinv); cudaFree(d_Minv);
+        cudaFree(d_betas); cudaFree(st.llc); cudaFree(st.lpriorc); cudaFree(st.role);
+    }
     int set_row_comm(const void* id, size_t nbytes, int rank, int world) override {
         if (tcx3 || tf32m) {
             rmn_set_error("row-sharded data mode runs in f64 precision");
@@ -1178,6 +1265,7 @@ struct LogisticSampler : SamplerImpl {
     int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {
         const rmn_proposal* pr = s->prop;
         if (inj) RMN_REQUIRE(inj->d_xi && inj->d_u, "injected run needs d_xi and d_u");
+        if (inj && st.nt > 0) RMN_REQUIRE(inj->d_usel, "injected tempered run needs d_usel (selection uniforms)");
         rmn_trace_t t0{};
         if (tr) t0 = *tr;
         if (t0.thin <= 0) t0.thin = 1;
@@ -1188,10 +1276,11 @@ struct LogisticSampler : SamplerImpl {
         const int64_t K = st.K;
         const int d = st.d;
         for (int64_t t = 0; t <= T; ++t) {
-            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0);
+            sp.finish = (t > 0); sp.propose = (t < T); sp.diag = (t > 0); sp.record = sp.finish;
             sp.step_fin = step0 + t - 1; sp.step_prop = step0 + t;
             sp.inj_u = (inj && t > 0) ? inj->d_u + (t - 1) * K : nullptr;
             sp.inj_xi = (inj && t < T) ? inj->d_xi + t * K * d : nullptr;
+            sp.inj_usel = (inj && st.nt > 0 && t < T) ? inj->d_usel + t * K : nullptr;
             sp.trace_slot = -1;
             sp.tr_theta = t0.d_theta; sp.tr_logpost = t0.d_logpost;
             sp.tr_prop_lp = (t0.d_prop_logpost && t > 0) ? t0.d_prop_logpost + (t - 1) * K : nullptr;
@@ -1202,7 +1291,18 @@ struct LogisticSampler : SamplerImpl {
                 const int64_t i = t;
                 if (i >= t0.first && (i - t0.first) % t0.thin == 0) sp.trace_slot = (i - t0.first) / t0.thin;
             }
-            if (mmala) lg_finish_propose_kernel<true><<<fp_grid(), fp_threads(), fp_smem(), stream>>>(fst(), sp);
+            if (st.nt > 0) {
+                // tempering: a swap moves TWO rows -- finish in one launch (the initiator's warp exchanges both rows),
+                // record and propose in a second one
+                if (sp.finish) {
+                    LgStep fin = sp; fin.propose = 0; fin.record = 0; fin.diag = 0;
+                    lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(fst(), fin);
+                    RMN_KERNEL_CHECK(); launches++;
+                }
+                LgStep pro = sp; pro.finish = 0;
+                pro.tr_prop_lp = nullptr; pro.tr_acc = nullptr; pro.tr_lqr = nullptr; pro.tr_prop_theta = nullptr;
+                lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(fst(), pro);
+            } else if (mmala) lg_finish_propose_kernel<true><<<fp_grid(), fp_threads(), fp_smem(), stream>>>(fst(), sp);
             else lg_finish_propose_kernel<false><<<row_grid(), 128, 0, stream>>>(fst(), sp);
             RMN_KERNEL_CHECK(); launches++;
             if (t == T) break;

@@ -6,7 +6,8 @@ prior untouched) and, every step and sequentially along the ladder, lets each ch
 MH step or -- with probability `Pswap` -- propose a swap with the next chain down the ladder.  Here the ladder
 lies along the chain axis of the device engine: chains l*Nt .. l*Nt+Nt-1 are ladder l, the swap is a warp shuffle
 inside the MH kernel on the small-d path (riemann_b200/csrc/small_gauss.cu) and an exchange of the two chain rows by the
-initiator's warp on the dense-Gaussian path (d > 8, riemann_b200/csrc/dense.cu) -- `rmn_sampler_set_tempering` -- and
+initiator's warp on the dense-Gaussian path (d > 8, riemann_b200/csrc/dense.cu) and on the logistic model
+(riemann_b200/csrc/logistic.cu; the prior is not tempered, :33-37) -- `rmn_sampler_set_tempering` -- and
 `K` independent ladders run side by side.
 
 Reference behaviours kept: the default ladder `0.5**arange(5)`; the selection uniform is drawn for every chain,
@@ -16,7 +17,7 @@ chain as `_chain_thetas` / `_chain_logpost` (:83-90).  Reference defects not rep
 in the reference (`isinstance(betas, np.array)`, :62) -- here an explicit ladder is used as given, which is what
 that branch intends; `sample()` returns `np.array(zip(...))` there (:127) and the states here.
 The reference shares ONE proposal object between all temperatures (:81), so only non-adaptive proposals make
-sense; the device engine enforces that (MetropolisRandomWalk, pCN on the Gaussian models of any dimension).
+sense; the device engine enforces that (MetropolisRandomWalk, pCN; Gaussian models of any dimension, logistic model).
 """
 import numpy as np
 

@@ -28,7 +28,7 @@ def _same(tmp, names):
 @pytest.mark.parametrize("which,names", [
     ("_n1_dense_fixtures", ["hmc4_gauss12d", "adapthmc3_gauss12d", "pcn_gauss12d", "hmcmass3_gauss12d",
                             "adaptmalamass_gauss12d", "hmc5_gauss100d"]),
-    ("_n3_pt_fixtures", ["pt_rw_gauss2d", "pt_rw_gauss5d", "pt_rw_gauss12d"]),
+    ("_n3_pt_fixtures", ["pt_rw_gauss2d", "pt_rw_gauss5d", "pt_rw_gauss12d", "pt_rw_logistic"]),
 ])
 def test_generators_reproduce_the_committed_fixtures(tmp_path, monkeypatch, which, names):
     monkeypatch.setattr(gen_golden, "GOLDEN_DIR", str(tmp_path))

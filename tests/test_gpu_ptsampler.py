@@ -177,3 +177,31 @@ def test_dense_path_ladders_replay_and_sample(golden):
     assert relerr(pt2._logpost[-1], ll * pt2.betas[None, :]) < 1e-10
     dg = pt2.diagnostics()
     assert dg["chains"] == 400 and dg["temperatures"] == 5
+
+
+def test_logistic_ladder_matches_reference_and_samples(golden):
+    """Tempering on the logistic model (prior untempered, ptsampler.py:33-37): the reference's PTSampler stream replayed on
+    the device; then many Philox ladders whose carried log-posterior is lprior + beta * logL of the state they hold."""
+    from riemann_b200 import PTSampler
+    from riemann_b200.models.logistic import LogisticRegression
+    from riemann_b200.proposals.randomwalk import MetropolisRandomWalk
+    from oracle import riemann_port as port
+    g = golden("pt_rw_logistic")
+    dm = LogisticRegression(g["X"], g["y"], float(g["prior_var"]))
+    pt = PTSampler(dm, MetropolisRandomWalk(g["C0"]), g["thetas"][0, 0])
+    pt.run_injected(g["usel"], g["xi"], g["u"])
+    for i in range(len(pt.betas)):
+        assert relerr(np.array(pt.samplers[i]._chain_thetas), g["thetas"][i]) < TOL
+        assert relerr(np.array(pt.samplers[i]._chain_logpost), g["logpost"][i]) < TOL
+    K = 64
+    pt2 = PTSampler(dm, MetropolisRandomWalk(g["C0"]), g["thetas"][0, 0], K=K, seed=6)
+    pt2.run(400, trace=False)
+    th, lp = pt2._thetas[-1], pt2._logpost[-1]                              # [K, nt, d], [K, nt]
+    om = port.LogisticRegression(g["X"], g["y"], float(g["prior_var"]))
+    for l in (0, 17, 63):
+        for i, beta in enumerate(pt2.betas):
+            ref = om.log_prior(th[l, i]) + beta * om.log_likelihood(th[l, i])
+            assert abs(lp[l, i] - ref) < 1e-8 * max(1.0, abs(ref))
+    assert np.any(th[:, 0] != th[:, 1])
+    dg = pt2.diagnostics()
+    assert dg["chains"] == K

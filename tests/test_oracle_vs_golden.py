@@ -180,12 +180,13 @@ def test_live_stream_matches_tape(golden):
     assert np.max(np.abs(np.array(s._chain_logpost) - g["logpost"][0, :1501])) < TOL
 
 
-@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5), ("pt_rw_gauss12d", 12)])
+@pytest.mark.parametrize("name,d", [("pt_rw_gauss2d", 2), ("pt_rw_gauss5d", 5), ("pt_rw_gauss12d", 12),
+                                    ("pt_rw_logistic", 6)])
 def test_parallel_tempering(golden, name, d):
     """N3: port.PTSampler replays the recorded stream of the reference's PTSampler (ptsampler.py:41-127):
     every temperature's chain, log-posterior and swap decision."""
     g = golden(name)
-    m = _gauss(g, d)
+    m = port.LogisticRegression(g["X"], g["y"], float(g["prior_var"])) if name == "pt_rw_logistic" else _gauss(g, d)
     pt = port.PTSampler(m, port.MetropolisRandomWalk(g["C0"]), g["thetas"][0, 0],
                         draws=port.PTTapeDraws(g["usel"], g["xi"], g["u"]))
     assert np.array_equal(pt.betas, g["betas"]) and pt.Pswap == float(g["pswap"])
