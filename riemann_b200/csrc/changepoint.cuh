@@ -1,4 +1,4 @@
-// riemann_b200 -- definitions of the changepoint kernels (changepoint.cu; also used by experiments/changepoint_tpc.cu).
+// riemann_b200 -- definitions of the changepoint kernels (changepoint.cu).
 #pragma once
 #include "common.cuh"
 
