@@ -509,6 +509,16 @@ def roofline_for(ctx, wl, precision, Kg, T, steps, kt, ms):
     prof = ctx.profiled.get("%s/%s" % (wl, precision))
     if prof:
         roof["profiled"] = prof            # static ncu evidence (DRAM bytes per launch, pipe utilisation), with its source file
+        if roof["bound"] == "alu" and prof.get("warp_inst_per_chain_step"):
+            # the binding resource of an issue-bound kernel: warp-instructions issued per second (instruction count per
+            # chain-step from the committed ncu capture x the LIVE chain-step rate of the kernel) against what the SMs can
+            # issue (SMs x 4 schedulers x SM clock)
+            rate = Kg * T * steps / (kernel_ms * 1e-3)
+            issue_peak = 148 * 4 * peaks["sm_max_mhz"] * 1e6
+            roof["issue_frac"] = prof["warp_inst_per_chain_step"] * rate / issue_peak
+            roof["issue_note"] = ("%d warp-instructions per chain-step (static, %s) x %.3g chain-steps/s (live) / (148 SM x 4 "
+                                  "schedulers x %.0f MHz)" % (prof["warp_inst_per_chain_step"], prof["source"].split(",")[0],
+                                                              rate, peaks["sm_max_mhz"]))
     return roof
 
 
