@@ -101,6 +101,21 @@ def test_bad_arguments_return_param_error_without_a_gpu(lib):
     assert L.rmn_proposal_mmala_create(C.byref(h), 0, 0.1) == lib.RMN_ERR_PARAM
     assert L.rmn_proposal_changepoint_create(C.byref(h), 2.0, None) == lib.RMN_OK
     assert L.rmn_proposal_destroy(h) == lib.RMN_OK
+    # pooled covariance adaptation: dense path only, sane schedule -- all host-side checks
+    h12, h2 = C.c_void_p(), C.c_void_p()
+    assert L.rmn_proposal_rw_create(C.byref(h12), 12, lib.ptr(np.eye(12)), 0, 0.25) == lib.RMN_OK
+    assert L.rmn_proposal_rw_set_pooled_cov_adapt(h12, 0, 0.5, 1e-10, 0) == lib.RMN_ERR_PARAM          # t_adapt < 1
+    assert L.rmn_proposal_rw_set_pooled_cov_adapt(h12, 10, -1.0, 1e-10, 0) == lib.RMN_ERR_PARAM        # sd <= 0
+    assert L.rmn_proposal_rw_set_pooled_cov_adapt(h12, 10, 0.5, 1e-10, 0) == lib.RMN_OK
+    assert L.rmn_proposal_rw_create(C.byref(h2), 2, lib.ptr(np.eye(2)), 0, 0.25) == lib.RMN_OK
+    assert L.rmn_proposal_rw_set_pooled_cov_adapt(h2, 10, 0.5, 1e-10, 0) == lib.RMN_ERR_PARAM          # small-d path
+    assert b"dense path" in L.rmn_last_error()
+    assert L.rmn_proposal_destroy(h12) == lib.RMN_OK and L.rmn_proposal_destroy(h2) == lib.RMN_OK
+    from riemann_b200.proposals.randomwalk import PooledAdaptCovRandomWalk
+    with pytest.raises(ParameterError):
+        PooledAdaptCovRandomWalk(np.eye(12), t_adapt=0)
+    p = PooledAdaptCovRandomWalk(np.eye(12), t_adapt=50, stop_after=1000, adapt_scale=True)
+    assert p._pooled_cov and p._adaptive and p.target_accept_rate == 0.25 and p.L.shape == (12, 12)
 
 
 def test_no_cpu_fallback(lib):
