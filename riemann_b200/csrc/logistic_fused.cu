@@ -118,6 +118,19 @@ __device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a,
         "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, pa;\n"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
 }
+// the same issue form for kind::f16 (bf16 operands, K = 16 per instruction): A is 16 packed pairs per lane = 8 TMEM columns
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pa;\n"
+        ".reg .b64 bd;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pa, %5, 0;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, pa;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n"
@@ -147,6 +160,18 @@ __device__ __forceinline__ float rn_tf32(float x) {          // round to nearest
 __device__ __forceinline__ void split_rn(double x, float& hi, float& lo) {
     hi = rn_tf32((float)x);
     lo = rn_tf32((float)(x - (double)hi));
+}
+// The correction operand: ONE 32-bit word per element holding two bf16 values that are consecutive along the contraction
+// of a kind::f16 MMA (low half = even k).  For Theta the pair is (bf16(theta), bf16(theta - hi)), for X it is
+// (bf16(x - hi), bf16(x)), so the dot product of the packed rows is  Theta_h . Xl + Theta_l . Xh  to 2^-9 relative.
+__device__ __forceinline__ uint32_t pack_bf16(float even, float odd) {
+    const __nv_bfloat162 b2 = __floats2bfloat162_rn(even, odd);          // .x (low half) = even
+    return *reinterpret_cast<const uint32_t*>(&b2);
+}
+__device__ __forceinline__ void split_corr(double x, bool x_side, float& hi, uint32_t& corr) {
+    hi = rn_tf32((float)x);
+    const float lo = (float)(x - (double)hi);
+    corr = x_side ? pack_bf16(lo, (float)x) : pack_bf16((float)x, lo);
 }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -240,7 +265,8 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         // MMA, GEMM1 issued at ~70 cycles per MMA against the 32 the tensor pipe needs for M = 128, N = 64, K = 8 -- the
         // issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512 TMEM
         // columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
-        const uint32_t idesc1 = umma_idesc_tf32(CB, NT);
+        const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_bf16(CB, NT);
+        const bool corr_bf16 = a.corr != 0;
         const uint32_t idesc2 = umma_idesc_tf32(CB, DP32) | (1u << 16);          // B is MN-major
         constexpr uint32_t t_th = C::COL_TH, t_tl = C::COL_TL, t_g = C::COL_G;
         const int nbox = (a.d + 31) / 32, d8 = (a.d + 7) / 8;                   // boxes / K steps of GEMM1 that hold data
@@ -267,8 +293,13 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                         const uint32_t ta = (uint32_t)((4 * b + k) * 8);
                         if (b == 0 && k == 0) umma_tf32_ts_w<false>(tz, t_th + ta, lo_h + off, dk_hi, idesc1);
                         else umma_tf32_ts_w<true>(tz, t_th + ta, lo_h + off, dk_hi, idesc1);
-                        umma_tf32_ts_w<true>(tz, t_th + ta, lo_l + off, dk_hi, idesc1);
-                        umma_tf32_ts_w<true>(tz, t_tl + ta, lo_h + off, dk_hi, idesc1);
+                        if (corr_bf16) {                                                    // warp-uniform
+                            // Theta_h Xl^T + Theta_l Xh^T as ONE kind::f16 MMA over the packed pairs (K = 16 = these 8 words)
+                            umma_bf16_ts_w<true>(tz, t_tl + ta, lo_l + off, dk_hi, idesc1b);
+                        } else {
+                            umma_tf32_ts_w<true>(tz, t_th + ta, lo_l + off, dk_hi, idesc1);
+                            umma_tf32_ts_w<true>(tz, t_tl + ta, lo_h + off, dk_hi, idesc1);
+                        }
                     }
                 }
             }
@@ -317,8 +348,12 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                     const int j = j0 + e;
                     const double v = (okc && j < a.d) ? th[j] : 0.0;
                     float h, l;
-                    split_rn(v, h, l);
-                    hi[e] = __float_as_uint(h); lo[e] = __float_as_uint(l);
+                    if (a.corr == 0) { split_rn(v, h, l); lo[e] = __float_as_uint(l); }
+                    else {
+                        split_corr(v, false, h, lo[e]);
+                        if (a.corr == 2) lo[e] = __byte_perm(lo[e], 0, 0x1032);     // debug: halves swapped
+                    }
+                    hi[e] = __float_as_uint(h);
                 }
                 tmem_st_32x32(lane_base + C::COL_TH + j0, hi);
                 tmem_st_32x32(lane_base + C::COL_TL + j0, lo);
@@ -451,14 +486,17 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
 
 // X[N][d] (fp64) -> Xh, Xl [N][ldx] (nearest-TF32 hi / lo parts, row pitch ldx = d rounded up to 4) and the label sign masks
 __global__ void __launch_bounds__(256)
-lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, const double* __restrict__ X, const double* __restrict__ y,
+lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, int corr, const double* __restrict__ X, const double* __restrict__ y,
                 float* __restrict__ Xh, float* __restrict__ Xl, uint32_t* __restrict__ ys) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx < N * ldx) {
         const int64_t i = idx / ldx;
         const int k = (int)(idx % ldx);
         float hi = 0.0f, lo = 0.0f;
-        if (k < d) split_rn(X[i * d + k], hi, lo);
+        if (k < d) {
+            if (corr == 0) split_rn(X[i * d + k], hi, lo);
+            else { uint32_t w; split_corr(X[i * d + k], true, hi, w); lo = __uint_as_float(w); }
+        }
         Xh[idx] = hi; Xl[idx] = lo;
     }
     if (idx < nys) ys[idx] = (idx < N && y[idx] != 0.0) ? 0x80000000u : 0u;
@@ -496,6 +534,11 @@ void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
         if (e[0] == '1') g->ldx = g->dp32;
         if (e[0] == '2') g->ldx = (d + 3) / 4 * 4;
     }
+    g->corr = 1;                               // correction terms of GEMM1 as one bf16 MMA over packed pairs
+    if (const char* e = getenv("RMN_LGF_CORR")) {   // A/B: tf32 = the two TF32 correction MMAs (3 x TF32), swap = debug
+        if (e[0] == 't') g->corr = 0;
+        if (e[0] == 's') g->corr = 2;
+    }
     g->tiles_total = (N + NT - 1) / NT;
     g->nys = g->tiles_total * NT;
     g->nblk = (int)((K + CB - 1) / CB);
@@ -512,7 +555,7 @@ void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
 int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y, float* Xh, float* Xl, uint32_t* ys,
            cudaStream_t st) {
     const int64_t n = std::max<int64_t>(N * g.ldx, g.nys);
-    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.ldx, g.nys, X, y, Xh, Xl, ys);
+    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.ldx, g.nys, g.corr, X, y, Xh, Xl, ys);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
@@ -525,7 +568,7 @@ int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const floa
 }
 
 int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {
-    a.nblk = g.nblk; a.tps = g.tps; a.tiles_total = g.tiles_total;
+    a.nblk = g.nblk; a.tps = g.tps; a.tiles_total = g.tiles_total; a.corr = g.corr;
     static bool attr[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -15,6 +15,8 @@ struct Geometry {
     int tps;               // 64-row tiles per split
     int64_t tiles_total;
     int64_t nys;           // entries of the label-mask array (a whole number of tiles)
+    int corr;              // correction terms of the logits GEMM: 1 = one bf16 MMA over packed (hi, lo) pairs (default),
+                           // 0 = two TF32 MMAs on fp32 lo parts (RMN_LGF_CORR=tf32), 2 = debug
 };
 
 constexpr int LLP_PER_SPLIT = 4;
@@ -34,7 +36,7 @@ struct SweepArgs {
     int64_t ldw;           // (elements; a multiple of 64)
     int w_bf16;            // W points to bf16 storage (round to nearest): the operand of the bf16 metric GEMM
     long long* dbg;        // optional timeline of CTA 0 (clock64 stamps, RMN_LGF_TIMELINE=1; scripts/lgf_timeline.py), else NULL
-    int nblk, tps;         // filled by sweep()
+    int nblk, tps, corr;   // filled by sweep()
     int64_t tiles_total;
 };
 
