@@ -7,33 +7,42 @@
 //
 // A CTA owns 128 chains (one TMEM lane each) and a contiguous range of data rows, streamed as tiles of 64 rows:
 //
-//   TMA threads   ring A: X tile, hi and lo parts, fp32 [64][dp32], SWIZZLE_128B boxes of 32 columns (GEMM1, K-major);
-//                 ring B: the hi part again in the 32-byte-atom 128B swizzle -- the only layout tcgen05 accepts for an
-//                 MN-major TF32 operand (GEMM2 reads the tile transposed).
-//                 Same global lines (L2 hits), two tensor maps.  A slots are released by GEMM1, B slots by GEMM2.
-//   MMA thread    GEMM1  Z[128 x 64] = Theta_h Xh^T + Theta_h Xl^T + Theta_l Xh^T   (3 x TF32, fp32-accurate);
-//                        A = Theta from TENSOR MEMORY (loaded once per CTA), B = X tile, K-major
-//                 GEMM2  G[128 x dp32] += R[128 x 64] Xh[64 x dp32]                  (single-pass TF32: the gradient
-//                        only shapes the proposal); A = R from tensor memory, written in place over Z by the
-//                        pointwise warps, B = the Xh tile read MN-major (no transposed copy of X in HBM)
+//   TMA thread    ONE ring of SA slots; a slot holds the 64-row tile three times over the same rows:
+//                   Xh   fp32 (x rounded to nearest TF32)        [64][dp32]   SWIZZLE_128B boxes of 32 columns
+//                   Xlb  bf16 (x - Xh)                           [64][dp32]   SWIZZLE_128B boxes of 64 columns
+//                   Xhb  bf16 (x)                                [64][dp32]   SWIZZLE_128B boxes of 64 columns
+//                 8 bytes per element, all of it read by BOTH products: the slot is released by GEMM2.
+//   MMA warp      GEMM1  Z[128 x 64] = Theta_h Xh^T  (kind::tf32)  +  Theta_hb Xlb^T + Theta_lb Xhb^T  (kind::f16, bf16):
+//                        the two correction terms are 2^-11 of the product, so bf16 operands (2^-9 relative) leave
+//                        z fp32-accurate at HALF the instruction count of a TF32 correction (K = 16 per MMA).
+//                        A = Theta from TENSOR MEMORY (written once per CTA; bf16 parts packed two per column)
+//                 GEMM2  G[128 x dp32] += R[128 x 64] Xhb[64 x dp32]   (kind::f16: the gradient only shapes the
+//                        proposal); A = R as bf16 pairs from tensor memory, written in place over Z by the pointwise
+//                        warps; B = the SAME Xhb boxes read MN-major -- a 16-bit operand may be MN-major in the plain
+//                        128-byte swizzle, so the tile TMA wrote K-major for GEMM1 is, read with the other descriptor,
+//                        the transposed operand of GEMM2.  (Round 2's first version kept the gradient in TF32, whose
+//                        only MN-major layout is the 32-byte-atom swizzle: a second shared-memory copy of the tile in
+//                        a second ring, 96 KB of L2 -> SM traffic per tile instead of 64 -- and that traffic, not the
+//                        tensor pipe, was what bounded the sweep once the correction MMAs were halved.)
 //   4 x 4 warps   pointwise stage, all four warpgroups on every tile (16 of its 64 rows each): tcgen05.ld the logits, fp32
 //                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element, two
 //                 elements per instruction with the packed fp32 FMA of sm_100),
-//                 log-likelihood partial sums in fp64, R = y - p rounded to TF32 -> tcgen05.st back into the same
-//                 TMEM columns (and W = p(1-p) to HBM for the mMALA metric GEMM)
+//                 log-likelihood partial sums in fp64, R = y - p rounded to bf16 -> tcgen05.st back into the first 8 of
+//                 the warpgroup's 16 TMEM columns (and W = p(1-p) to HBM for the mMALA metric GEMM)
 //
-//   TMEM columns: Theta_h [0, dp32) | Theta_l [dp32, 2 dp32) | G [2 dp32, 3 dp32) | Z/R buffer 0, 1 (64 each)
+//   TMEM columns: Theta_h [0, dp32) | Theta_hb, Theta_lb (dp32 / 2 each) | G (dp32) | Z/R buffer 0, 1 (64 each)
 //
-// The MMA thread issues GEMM1 of tile t+1 before it waits for the R of tile t, so the tensor pipe works on the
+// The MMA warp issues GEMM1 of tile t+1 before it waits for the R of tile t, so the tensor pipe works on the
 // next logits while the pointwise warps process the current ones; tcgen05.mma executes in issue order, which is
 // what makes reusing a Z buffer two tiles later safe without another barrier.
 //
-// Measured dead end (gpurun r2k): releasing ring A box by box (eight one-box slots, TMA two tiles ahead) was SLOWER, 2.35 ms
+// Measured dead end (gpurun r2k): releasing the ring box by box (eight one-box slots, TMA two tiles ahead) was SLOWER, 2.35 ms
 // per 1,024-chain sweep against 1.77 -- four commits and four barrier waits per tile cost the MMA thread more than the
 // exposed TMA latency it hid.
 //
-// Accuracy.  hi / lo parts are rounded to nearest TF32, so (hi + lo) carries 22 bits and z is fp32-accurate; the
-// per-row terms are fp32 (|error| ~1e-7 each), summed in fp64.  Measured budget: tests/test_gpu_logistic.py.
+// Accuracy.  Xh / Theta_h are rounded to nearest TF32 and the remainders to bf16, so the pair carries ~19 bits and the
+// dropped terms are ~2^-20 of a product; the per-row terms are fp32 (|error| ~1e-7 each), summed in fp64.  Measured
+// budget: tests/test_gpu_logistic.py (riemann_b200/budgets.py).
 // The result is a deterministic function of theta (fixed tile order, no atomics).
 #include <algorithm>
 #include "common.cuh"
@@ -56,17 +65,16 @@ constexpr int THREADS = 128 + 128 * PWG;   // warp 0 TMA ring A, 1 MMA, 2 TMEM a
 constexpr int TMEM_COLS_ALLOC = 512;
 
 template <int DP32> struct Cfg {
-    static constexpr int NBOX = DP32 / 32;
-    static constexpr int XPART = NBOX * BOX_BYTES;                 // one copy of the 64 x dp32 tile
-    static constexpr int SA = (DP32 == 128) ? 2 : 4;               // ring A slots: Xh | Xl (SWIZZLE_128B)
-    static constexpr int SB = (DP32 == 128) ? 3 : 4;               // ring B slots: Xh (32-byte-atom swizzle)
-    static constexpr int A_BYTES = 2 * XPART;
-    static constexpr int B_BYTES = XPART;
-    static constexpr int TXA = 2 * XPART, TXB = XPART;
-    static constexpr int OFF_B = SA * A_BYTES;
-    static constexpr int OFF_BAR = OFF_B + SB * B_BYTES;
+    static constexpr int NBOX = DP32 / 32;                         // fp32 boxes (32 columns) of the Xh part
+    static constexpr int NB16 = DP32 / 64;                         // bf16 boxes (64 columns) of the Xlb / Xhb parts
+    static constexpr int OFF_LB = NBOX * BOX_BYTES;                // slot: Xh | Xlb | Xhb
+    static constexpr int OFF_HB = OFF_LB + NB16 * BOX_BYTES;
+    static constexpr int A_BYTES = OFF_HB + NB16 * BOX_BYTES;      // 64 KB (dp32 = 128) / 32 KB (64): 8 bytes per element
+    static constexpr int SA = (DP32 == 128) ? 3 : 6;               // ring slots
+    static constexpr int TXA = A_BYTES;
+    static constexpr int OFF_BAR = SA * A_BYTES;
     static constexpr int SMEM = OFF_BAR + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int COL_TH = 0, COL_TL = DP32, COL_G = 2 * DP32, COL_Z = 3 * DP32;
+    static constexpr int COL_TH = 0, COL_TB = DP32, COL_LB = DP32 + DP32 / 2, COL_G = 2 * DP32, COL_Z = 3 * DP32;
     static_assert(3 * DP32 + 2 * NT <= 512, "TMEM columns");
     static_assert(SMEM <= 232448, "shared memory");
 };
@@ -89,6 +97,11 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -140,38 +153,28 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// shared-memory matrix descriptor, MN-major, 32-bit elements: tcgen05 accepts ONE layout for an MN-major TF32 operand,
-// the 128-byte swizzle with 32-byte atoms (layout type 1; Swizzle<2,5,2>: 32-byte chunk index ^= row & 3), which TMA
-// writes as CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  32 fp32 of the MN index are contiguous (one 128-byte row), MN blocks
-// of 32 are `lbo` bytes apart; the K index walks 128-byte rows, groups of 4 rows are `sbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_b32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+// shared-memory matrix descriptor, MN-major, 16-bit elements, plain 128-byte swizzle (layout type 2): 64 elements of the
+// MN index are contiguous (one 128-byte row), MN blocks of 64 are `lbo` bytes apart; the K index walks the 128-byte rows,
+// groups of 8 rows (one swizzle pattern) are `sbo` bytes apart.  This is the box TMA writes for a [rows = K][64 columns =
+// MN] bf16 tile with CU_TENSOR_MAP_SWIZZLE_128B -- the very tile that is a K-major operand when rows are taken as MN.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_b16(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;                      // SWIZZLE_128B_BASE32B
+    d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
     return d;
 }
 
 __device__ __forceinline__ float rn_tf32(float x) {          // round to nearest TF32 (10 explicit mantissa bits)
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-__device__ __forceinline__ void split_rn(double x, float& hi, float& lo) {
-    hi = rn_tf32((float)x);
-    lo = rn_tf32((float)(x - (double)hi));
-}
-// The correction operand: ONE 32-bit word per element holding two bf16 values that are consecutive along the contraction
-// of a kind::f16 MMA (low half = even k).  For Theta the pair is (bf16(theta), bf16(theta - hi)), for X it is
-// (bf16(x - hi), bf16(x)), so the dot product of the packed rows is  Theta_h . Xl + Theta_l . Xh  to 2^-9 relative.
+// two bf16 values in one 32-bit word, `even` in the low half: consecutive along the contraction of a kind::f16 MMA,
+// both in a shared-memory row (little endian) and in a tensor-memory column of an A operand
 __device__ __forceinline__ uint32_t pack_bf16(float even, float odd) {
     const __nv_bfloat162 b2 = __floats2bfloat162_rn(even, odd);          // .x (low half) = even
     return *reinterpret_cast<const uint32_t*>(&b2);
-}
-__device__ __forceinline__ void split_corr(double x, bool x_side, float& hi, uint32_t& corr) {
-    hi = rn_tf32((float)x);
-    const float lo = (float)(x - (double)hi);
-    corr = x_side ? pack_bf16(lo, (float)x) : pack_bf16((float)x, lo);
 }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -196,18 +199,15 @@ __device__ __forceinline__ float2 log1p_unit2(float2 e) {
 
 template <int DP32, bool HASW>
 __global__ void __launch_bounds__(THREADS, 1)
-lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
-                      const __grid_constant__ CUtensorMap map_xt, SweepArgs a) {
+lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xlb,
+                      const __grid_constant__ CUtensorMap map_xhb, SweepArgs a) {
     using C = Cfg<DP32>;
-    constexpr int SA = C::SA, SB = C::SB;
+    constexpr int SA = C::SA;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* ringB = smem + C::OFF_B;
     uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* emptyA = fullA + SA;
-    uint64_t* fullB = emptyA + SA;
-    uint64_t* emptyB = fullB + SB;
-    uint64_t* z_full = emptyB + SB;              // [2] GEMM1 of a tile complete
+    uint64_t* z_full = emptyA + SA;              // [2] GEMM1 of a tile complete
     uint64_t* r_full = z_full + 2;               // [2] pointwise stage wrote R
     uint64_t* th_ready = r_full + 2;             // Theta is in TMEM
     uint64_t* g_full = th_ready + 1;             // last GEMM2 complete
@@ -219,10 +219,9 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     const int64_t t_end = min(a.tiles_total, t_begin + a.tps);
     const int ntile = (int)max((int64_t)0, t_end - t_begin);
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_xh); tma_prefetch_desc(&map_xl); tma_prefetch_desc(&map_xt); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_xh); tma_prefetch_desc(&map_xlb); tma_prefetch_desc(&map_xhb); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4 * PWG); }
         mbar_init(th_ready, 4);
         mbar_init(g_full, 1);
@@ -235,7 +234,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer, ring A: Xh | Xl for GEMM1 =====
+        // ===== TMA producer: Xh | Xlb | Xhb of a tile into one slot (released by GEMM2) =====
         for (int t = 0; t < ntile; ++t) {
             const int s = t % SA;
             mbar_wait(&emptyA[s], ((t / SA) & 1) ^ 1);
@@ -243,35 +242,24 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             const int row0 = (int)((t_begin + t) * NT);
             mbar_expect_tx(&fullA[s], C::TXA);
 #pragma unroll
-            for (int b = 0; b < C::NBOX; ++b) {
-                tma_load_2d(st + b * BOX_BYTES, &map_xh, &fullA[s], b * 32, row0);
-                tma_load_2d(st + C::XPART + b * BOX_BYTES, &map_xl, &fullA[s], b * 32, row0);
-            }
-        }
-    } else if (warp == 3 && lane == 0) {
-        // ===== TMA producer, ring B: Xh in the MN-major layout for GEMM2 =====
-        for (int t = 0; t < ntile; ++t) {
-            const int s = t % SB;
-            mbar_wait(&emptyB[s], ((t / SB) & 1) ^ 1);
-            uint8_t* st = ringB + s * C::B_BYTES;
-            const int row0 = (int)((t_begin + t) * NT);
-            mbar_expect_tx(&fullB[s], C::TXB);
+            for (int b = 0; b < C::NBOX; ++b) tma_load_2d(st + b * BOX_BYTES, &map_xh, &fullA[s], b * 32, row0);
 #pragma unroll
-            for (int b = 0; b < C::NBOX; ++b) tma_load_2d(st + b * BOX_BYTES, &map_xt, &fullB[s], b * 32, row0);
+            for (int b = 0; b < C::NB16; ++b) {
+                tma_load_2d(st + C::OFF_LB + b * BOX_BYTES, &map_xlb, &fullA[s], b * 64, row0);
+                tma_load_2d(st + C::OFF_HB + b * BOX_BYTES, &map_xhb, &fullA[s], b * 64, row0);
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the WHOLE warp runs the loop in uniform control flow, `elect.sync` inside each issue =====
         // Measured with the per-tile clock stamps (RMN_LGF_TIMELINE): with one thread building a 64-bit descriptor per
-        // MMA, GEMM1 issued at ~70 cycles per MMA against the 32 the tensor pipe needs for M = 128, N = 64, K = 8 -- the
-        // issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512 TMEM
-        // columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
+        // MMA the issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512
+        // TMEM columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
         const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_bf16(CB, NT);
-        const bool corr_bf16 = a.corr != 0;
-        const uint32_t idesc2 = umma_idesc_tf32(CB, DP32) | (1u << 16);          // B is MN-major
-        constexpr uint32_t t_th = C::COL_TH, t_tl = C::COL_TL, t_g = C::COL_G;
-        const int nbox = (a.d + 31) / 32, d8 = (a.d + 7) / 8;                   // boxes / K steps of GEMM1 that hold data
+        const uint32_t idesc2 = umma_idesc_bf16(CB, DP32) | (1u << 16);          // B is MN-major
+        constexpr uint32_t t_th = C::COL_TH, t_tb = C::COL_TB, t_lb = C::COL_LB, t_g = C::COL_G;
+        const int d8 = (a.d + 7) / 8, d16 = (a.d + 15) / 16;                    // K steps of GEMM1 that hold data
         const uint64_t dk0 = umma_desc_kmajor<128>(0);                           // descriptors with a zero start address
-        const uint64_t dm0 = umma_desc_mnmajor_b32(0, BOX_BYTES, 512);
+        const uint64_t dm0 = umma_desc_mnmajor_b16(0, BOX_BYTES, 1024);
         const uint32_t dk_hi = (uint32_t)(dk0 >> 32), dk_lo0 = (uint32_t)dk0;
         const uint32_t dm_hi = (uint32_t)(dm0 >> 32), dm_lo0 = (uint32_t)dm0;
         const uint32_t smem0 = smem_u32(smem);
@@ -283,27 +271,18 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             tc_fence_after();
             stamp(t, 0);
             const uint32_t tz = C::COL_Z + (uint32_t)((t & 1) * NT);
-            const uint32_t lo_h = dk_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES)) & 0x3FFFF) >> 4), lo_l = lo_h + (C::XPART >> 4);
-            for (int b = 0; b < nbox; ++b) {
-                const int ksn = min(4, d8 - 4 * b);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < ksn) {                                                          // warp-uniform
-                        const uint32_t off = (uint32_t)(b * (BOX_BYTES >> 4) + k * 2);       // 16-byte units: box, 32 B per K step
-                        const uint32_t ta = (uint32_t)((4 * b + k) * 8);
-                        if (b == 0 && k == 0) umma_tf32_ts_w<false>(tz, t_th + ta, lo_h + off, dk_hi, idesc1);
-                        else umma_tf32_ts_w<true>(tz, t_th + ta, lo_h + off, dk_hi, idesc1);
-                        if (corr_bf16) {                                                    // warp-uniform
-                            // Theta_h Xl^T + Theta_l Xh^T as ONE kind::f16 MMA over the packed pairs (K = 16 = these 8 words)
-                            umma_bf16_ts_w<true>(tz, t_tl + ta, lo_l + off, dk_hi, idesc1b);
-                        } else {
-                            umma_tf32_ts_w<true>(tz, t_th + ta, lo_l + off, dk_hi, idesc1);
-                            umma_tf32_ts_w<true>(tz, t_tl + ta, lo_h + off, dk_hi, idesc1);
-                        }
-                    }
-                }
+            const uint32_t lo_h = dk_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES)) & 0x3FFFF) >> 4);
+            const uint32_t lo_lb = lo_h + (C::OFF_LB >> 4), lo_hb = lo_h + (C::OFF_HB >> 4);
+            // Theta_h Xh^T: TF32, K = 8 = 32 bytes of a row per MMA, four per 32-column box
+            umma_tf32_ts_w<false>(tz, t_th, lo_h, dk_hi, idesc1);
+            for (int k = 1; k < d8; ++k)
+                umma_tf32_ts_w<true>(tz, t_th + (uint32_t)(k * 8), lo_h + (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2), dk_hi, idesc1);
+            // Theta_hb Xlb^T + Theta_lb Xhb^T: bf16, K = 16 = 32 bytes of a row (8 packed TMEM columns) per MMA
+            for (int k = 0; k < d16; ++k) {
+                const uint32_t off = (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2);
+                umma_bf16_ts_w<true>(tz, t_tb + (uint32_t)(k * 8), lo_lb + off, dk_hi, idesc1b);
+                umma_bf16_ts_w<true>(tz, t_lb + (uint32_t)(k * 8), lo_hb + off, dk_hi, idesc1b);
             }
-            umma_commit_elect(&emptyA[s]);           // GEMM1 was the only reader of the A slot
             umma_commit_elect(&z_full[t & 1]);
             stamp(t, 1);
         };
@@ -314,19 +293,20 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             gemm1(0);
             for (int t = 0; t < ntile; ++t) {
                 if (t + 1 < ntile) gemm1(t + 1);
-                const int s = t % SB;
-                mbar_wait(&fullB[s], (t / SB) & 1);
+                const int s = t % SA;
                 mbar_wait(&r_full[t & 1], (t >> 1) & 1);
                 tc_fence_after();
                 stamp(t, 2);
+                // R of warpgroup w (data rows 16 w .. 16 w + 15 of the tile) sits as 8 packed columns at the start of
+                // the warpgroup's 16 logit columns; one K = 16 MMA per warpgroup, 16 rows = 2,048 bytes of the Xhb boxes
                 const uint32_t tr = C::COL_Z + (uint32_t)((t & 1) * NT);
-                const uint32_t lo_b = dm_lo0 + (((smem0 + (uint32_t)(C::OFF_B + s * C::B_BYTES)) & 0x3FFFF) >> 4);
-                if (t == 0) umma_tf32_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
-                else umma_tf32_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
+                const uint32_t lo_b = dm_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES + C::OFF_HB)) & 0x3FFFF) >> 4);
+                if (t == 0) umma_bf16_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
+                else umma_bf16_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
 #pragma unroll
-                for (int ks = 1; ks < NT / 8; ++ks)
-                    umma_tf32_ts_w<true>(t_g, tr + ks * 8, lo_b + ks * (1024 >> 4), dm_hi, idesc2);
-                umma_commit_elect(&emptyB[s]);       // the B slot is free once GEMM2 has read it
+                for (int ks = 1; ks < NT / 16; ++ks)
+                    umma_bf16_ts_w<true>(t_g, tr + ks * PCOLS, lo_b + ks * (2048 >> 4), dm_hi, idesc2);
+                umma_commit_elect(&emptyA[s]);       // the slot is free once GEMM2 has read it
                 stamp(t, 3);
             }
             umma_commit_elect(g_full);
@@ -342,21 +322,25 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             const int slot = (a.fixed_slot >= 0) ? a.fixed_slot : (okc ? (a.cur[c] ^ 1) : 0);
             const double* th = a.Th + ((int64_t)slot * a.K + (okc ? c : 0)) * a.dp;
             for (int j0 = 0; j0 < DP32; j0 += 32) {
-                uint32_t hi[32], lo[32];
+                uint32_t hi[32], hb[16], lb[16];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int j = j0 + e;
-                    const double v = (okc && j < a.d) ? th[j] : 0.0;
-                    float h, l;
-                    if (a.corr == 0) { split_rn(v, h, l); lo[e] = __float_as_uint(l); }
-                    else {
-                        split_corr(v, false, h, lo[e]);
-                        if (a.corr == 2) lo[e] = __byte_perm(lo[e], 0, 0x1032);     // debug: halves swapped
+                for (int e = 0; e < 32; e += 2) {
+                    float h[2], x[2], l[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int j = j0 + e + i;
+                        const double v = (okc && j < a.d) ? th[j] : 0.0;
+                        h[i] = rn_tf32((float)v);
+                        x[i] = (float)v;
+                        l[i] = (float)(v - (double)h[i]);
+                        hi[e + i] = __float_as_uint(h[i]);
                     }
-                    hi[e] = __float_as_uint(h);
+                    hb[e >> 1] = pack_bf16(x[0], x[1]);
+                    lb[e >> 1] = pack_bf16(l[0], l[1]);
                 }
                 tmem_st_32x32(lane_base + C::COL_TH + j0, hi);
-                tmem_st_32x32(lane_base + C::COL_TL + j0, lo);
+                tmem_st_32x16(lane_base + C::COL_TB + (j0 >> 1), hb);
+                tmem_st_32x16(lane_base + C::COL_LB + (j0 >> 1), lb);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -395,7 +379,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             float v[PCOLS];
             tmem_ld_32x16(tz, v);
             if (dbgp) a.dbg[t * 8 + 5] = clock64();
-            uint32_t rr[PCOLS];
+            uint32_t rr[PCOLS / 2];
             float wv[HASW ? PCOLS : 2];
             float2 part = f2(0.0f);
 #pragma unroll
@@ -413,13 +397,13 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 const float2 ei = __ffma2_rn(ex, inv, f2(0.0f));
                 const float g0 = (s0 >= 0.0f) ? inv.x : ei.x;                   // sigmoid(s);  y - p = (2y - 1) sigmoid(s)
                 const float g1 = (s1 >= 0.0f) ? inv.y : ei.y;
-                rr[e] = ((__float_as_uint(g0) | (~ym.x & 0x80000000u)) + 0x1000u) & 0xFFFFE000u;      // nearest TF32
-                rr[e + 1] = ((__float_as_uint(g1) | (~ym.y & 0x80000000u)) + 0x1000u) & 0xFFFFE000u;
+                rr[e >> 1] = pack_bf16(__uint_as_float(__float_as_uint(g0) | (~ym.x & 0x80000000u)),       // nearest bf16
+                                       __uint_as_float(__float_as_uint(g1) | (~ym.y & 0x80000000u)));
                 if (HASW) { const float2 w2 = __ffma2_rn(ei, inv, f2(0.0f)); wv[e] = w2.x; wv[e + 1] = w2.y; }
                 if ((e & 6) == 6) { ll += (double)(part.x + part.y); part = f2(0.0f); }
             }
             if (dbgp) a.dbg[t * 8 + 6] = clock64();
-            tmem_st_32x16(tz, rr);
+            tmem_st_32x8(tz, rr);
             if (HASW && okc && row0 < a.ldw) {                       // ldw is a multiple of 32, row0 of 16
                 if (a.w_bf16) {
                     __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(a.W) + (okc ? c : 0) * a.ldw + row0;
@@ -484,20 +468,21 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     }
 }
 
-// X[N][d] (fp64) -> Xh, Xl [N][ldx] (nearest-TF32 hi / lo parts, row pitch ldx = d rounded up to 4) and the label sign masks
+// X[N][d] (fp64) -> Xh [N][ldx] fp32 (x rounded to nearest TF32), Xlb = bf16(x - Xh), Xhb = bf16(x) [N][ldx] (row pitch
+// ldx = d rounded up to 8), and the label sign masks
 __global__ void __launch_bounds__(256)
-lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, int corr, const double* __restrict__ X, const double* __restrict__ y,
-                float* __restrict__ Xh, float* __restrict__ Xl, uint32_t* __restrict__ ys) {
+lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, const double* __restrict__ X, const double* __restrict__ y,
+                float* __restrict__ Xh, __nv_bfloat16* __restrict__ Xlb, __nv_bfloat16* __restrict__ Xhb,
+                uint32_t* __restrict__ ys) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx < N * ldx) {
         const int64_t i = idx / ldx;
         const int k = (int)(idx % ldx);
-        float hi = 0.0f, lo = 0.0f;
-        if (k < d) {
-            if (corr == 0) split_rn(X[i * d + k], hi, lo);
-            else { uint32_t w; split_corr(X[i * d + k], true, hi, w); lo = __uint_as_float(w); }
-        }
-        Xh[idx] = hi; Xl[idx] = lo;
+        const double x = (k < d) ? X[i * d + k] : 0.0;
+        const float hi = rn_tf32((float)x);
+        Xh[idx] = hi;
+        Xlb[idx] = __float2bfloat16_rn((float)(x - (double)hi));
+        Xhb[idx] = __float2bfloat16_rn((float)x);
     }
     if (idx < nys) ys[idx] = (idx < N && y[idx] != 0.0) ? 0x80000000u : 0u;
 }
@@ -530,15 +515,6 @@ int dp32_of(int d) { return d <= 64 ? 64 : 128; }
 void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
     g->dp32 = dp32_of(d);
     g->ldx = (d + 7) / 8 * 8;                  // rows start on 32-byte sectors
-    if (const char* e = getenv("RMN_LGF_PADX")) {   // A/B: 1 = rows padded to the tile width, 2 = 16-byte granularity
-        if (e[0] == '1') g->ldx = g->dp32;
-        if (e[0] == '2') g->ldx = (d + 3) / 4 * 4;
-    }
-    g->corr = 1;                               // correction terms of GEMM1 as one bf16 MMA over packed pairs
-    if (const char* e = getenv("RMN_LGF_CORR")) {   // A/B: tf32 = the two TF32 correction MMAs (3 x TF32), swap = debug
-        if (e[0] == 't') g->corr = 0;
-        if (e[0] == 's') g->corr = 2;
-    }
     g->tiles_total = (N + NT - 1) / NT;
     g->nys = g->tiles_total * NT;
     g->nblk = (int)((K + CB - 1) / CB);
@@ -555,20 +531,23 @@ void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
 int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y, float* Xh, float* Xl, uint32_t* ys,
            cudaStream_t st) {
     const int64_t n = std::max<int64_t>(N * g.ldx, g.nys);
-    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.ldx, g.nys, g.corr, X, y, Xh, Xl, ys);
+    // the second buffer (N ldx fp32 words) holds the two bf16 copies one after the other
+    __nv_bfloat16* Xlb = reinterpret_cast<__nv_bfloat16*>(Xl);
+    lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.ldx, g.nys, X, y, Xh, Xlb, Xlb + N * g.ldx, ys);
     RMN_KERNEL_CHECK();
     return RMN_OK;
 }
 
 int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const float* Xl) {
-    // the maps are ldx columns wide: the boxes of the last 32-column block reach past it and are zero-filled there
+    // the maps are ldx columns wide: the boxes of the last column block reach past it and are zero-filled there
+    const __nv_bfloat16* Xlb = reinterpret_cast<const __nv_bfloat16*>(Xl);
     if (int rc = make_tmap_2d(&m->xh, Xh, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
-    if (int rc = make_tmap_2d(&m->xl, Xl, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
-    return make_tmap_2d(&m->xt, Xh, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT, 32, /*atom32=*/true);
+    if (int rc = make_tmap_2d_bf16(&m->xlb, Xlb, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
+    return make_tmap_2d_bf16(&m->xhb, Xlb + N * g.ldx, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT);
 }
 
 int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {
-    a.nblk = g.nblk; a.tps = g.tps; a.tiles_total = g.tiles_total; a.corr = g.corr;
+    a.nblk = g.nblk; a.tps = g.tps; a.tiles_total = g.tiles_total;
     static bool attr[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -581,11 +560,11 @@ int sweep(const Maps& m, const Geometry& g, SweepArgs a, cudaStream_t st) {
     }
     const unsigned grid = (unsigned)(g.nblk * g.ns);
     if (g.dp32 == 64) {
-        if (a.W) lg_fused_sweep_kernel<64, true><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
-        else lg_fused_sweep_kernel<64, false><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
+        if (a.W) lg_fused_sweep_kernel<64, true><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xlb, m.xhb, a);
+        else lg_fused_sweep_kernel<64, false><<<grid, THREADS, Cfg<64>::SMEM, st>>>(m.xh, m.xlb, m.xhb, a);
     } else {
-        if (a.W) lg_fused_sweep_kernel<128, true><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
-        else lg_fused_sweep_kernel<128, false><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xl, m.xt, a);
+        if (a.W) lg_fused_sweep_kernel<128, true><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xlb, m.xhb, a);
+        else lg_fused_sweep_kernel<128, false><<<grid, THREADS, Cfg<128>::SMEM, st>>>(m.xh, m.xlb, m.xhb, a);
     }
     RMN_KERNEL_CHECK();
     return RMN_OK;

@@ -8,20 +8,18 @@ namespace lgf {
 
 struct Geometry {
     int dp32;              // columns of the operand tiles: 64 (d <= 64) or 128 (d <= 128)
-    int ldx;               // row pitch of the split X copies in floats: d rounded up to 8 (rows start on 32-byte sectors);
+    int ldx;               // row pitch of the X copies in elements: d rounded up to 8 (fp32 rows start on 32-byte sectors, bf16 rows on 16 bytes);
                            // the columns from ldx to dp32 are never stored nor read -- TMA zero-fills them in the tile
     int nblk;              // chain blocks of 128
     int ns;                // row splits (grid = nblk x ns)
     int tps;               // 64-row tiles per split
     int64_t tiles_total;
     int64_t nys;           // entries of the label-mask array (a whole number of tiles)
-    int corr;              // correction terms of the logits GEMM: 1 = one bf16 MMA over packed (hi, lo) pairs (default),
-                           // 0 = two TF32 MMAs on fp32 lo parts (RMN_LGF_CORR=tf32), 2 = debug
 };
 
 constexpr int LLP_PER_SPLIT = 4;
 
-struct Maps { CUtensorMap xh, xl, xt; };   // xt: the hi part again, 32-byte-atom swizzle (MN-major operand of GEMM2)
+struct Maps { CUtensorMap xh, xlb, xhb; };   // fp32 hi part; bf16 remainder; bf16 copy (GEMM1 correction K-major, GEMM2 MN-major)
 
 struct SweepArgs {
     const uint32_t* ys;    // [nys] 0x80000000 where y = 1
@@ -36,7 +34,7 @@ struct SweepArgs {
     int64_t ldw;           // (elements; a multiple of 64)
     int w_bf16;            // W points to bf16 storage (round to nearest): the operand of the bf16 metric GEMM
     long long* dbg;        // optional timeline of CTA 0 (clock64 stamps, RMN_LGF_TIMELINE=1; scripts/lgf_timeline.py), else NULL
-    int nblk, tps, corr;   // filled by sweep()
+    int nblk, tps;         // filled by sweep()
     int64_t tiles_total;
 };
 
