@@ -487,8 +487,9 @@ def roofline_for(ctx, wl, precision, Kg, T, steps, kt, ms):
         ach = 4.0 * n_ * d_ * Kg * T * steps / (kernel_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "note": "likelihood sweep on tcgen05, timed as a whole (CUDA events around its launches); achieved counts "
-                        "the ALGORITHMIC 4 N d flop per chain-step once (3 TF32 MMAs are issued per fp32-accurate product "
-                        "and the d-wide gradient tile fills d/256 of the MMA's N), against the cuBLAS TF32 peak"}
+                        "the ALGORITHMIC 4 N d flop per chain-step once (the fp32-accurate logits are one TF32 MMA plus two "
+                        "bf16 MMAs of twice the depth for the correction terms, the gradient one bf16 MMA), against the "
+                        "cuBLAS TF32 peak -- the rate of the product that carries the leading term"}
     elif precision == "tf32x3":
         peak = extra.get("tf32_cublas_tflops", 0.5 * peaks["bf16_tflops"])
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,

@@ -12,7 +12,8 @@ import math
 def logistic_tf32x3_difference(N):
     """|(logpost' - logpost)_tf32x3 - (logpost' - logpost)_f64| for a state and a proposal from it: 2e-3 at
     BASELINE config 4 (N = 1e6), scaling with sqrt(N) (independent rounding errors of the fp32-accurate logits,
-    measured 1.2e-3 / 2.7e-4 / 7e-5 at N = 1e6 / 1e5 / 2e4), never below 5e-5."""
+    measured 1.7e-3 / 4.0e-4 / 1.9e-4 at N = 1e6 / 1e5 / 2e4 with the bf16 correction terms of the fused sweep;
+    1.2e-3 / 2.7e-4 / 7e-5 with TF32 correction terms), never below 5e-5."""
     return max(5e-5, 2e-3 * math.sqrt(N / 1.0e6))
 
 

@@ -61,7 +61,7 @@ constexpr int CB = 128;                    // chains per CTA = UMMA M
 constexpr int BOX_BYTES = NT * 128;        // one TMA box: 64 rows x 32 fp32
 constexpr int PWG = 4;                     // pointwise warpgroups: each takes NT / PWG = 16 of a tile's 64 rows
 constexpr int PCOLS = NT / PWG;
-constexpr int THREADS = 128 + 128 * PWG;   // warp 0 TMA ring A, 1 MMA, 2 TMEM alloc, 3 TMA ring B, then PWG x 4 pointwise warps
+constexpr int THREADS = 128 + 128 * PWG;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, then PWG x 4 pointwise warps
 constexpr int TMEM_COLS_ALLOC = 512;
 
 template <int DP32> struct Cfg {
@@ -355,9 +355,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         float* wrow = HASW ? a.W + (okc ? c : 0) * a.ldw : nullptr;
         const int col0 = wg * PCOLS;
         // The tile's label sign masks (16 words per warpgroup, the same for every chain) come straight from global
-        // memory into registers, one tile AHEAD, so the stage starts the moment GEMM1 completes.  (They used to ride in
-        // ring B; with two 32-KB slots that ring is refilled ~2,500 cycles after GEMM2 of tile t-2, later than GEMM1 of
-        // tile t finishes, and the pointwise warps sat waiting for 256 bytes.)
+        // memory into registers, one tile AHEAD, so the stage starts the moment GEMM1 completes.
         const uint4* ysg = reinterpret_cast<const uint4*>(a.ys + t_begin * NT + col0);
         uint4 ymn[PCOLS / 4];
 #pragma unroll
@@ -518,12 +516,20 @@ void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
     g->tiles_total = (N + NT - 1) / NT;
     g->nys = g->tiles_total * NT;
     g->nblk = (int)((K + CB - 1) / CB);
-    // row splits: a grid that is a multiple of the SM count (148 = 4 x 37) when the tile count allows it
-    int gcd = 1;
-    for (int f : {2, 4, 37, 74, 148}) if (g->nblk % f == 0) gcd = f;
-    int ns = 148 / gcd;
-    const int64_t max_ns = std::max<int64_t>(1, g->tiles_total / 8);            // at least ~8 tiles per CTA
-    if (ns > max_ns) ns = (int)max_ns;
+    // Row splits.  One CTA per SM (its shared memory sees to that), so the sweep takes waves x (tiles per CTA + a fixed
+    // start / drain cost per CTA: TMEM allocation, Theta into tensor memory, first TMA round trip, G out -- measured
+    // ~12 us = 8 tiles, gpurun r2bd).  Pick the split count with the least modelled time; at least 8 tiles per CTA.
+    const int sms = 148, ovh = 8;
+    const int64_t max_ns = std::max<int64_t>(1, g->tiles_total / 8);
+    int ns = 1;
+    int64_t best = -1;
+    for (int v = 1; v <= (int)std::min<int64_t>(max_ns, 4 * sms); ++v) {
+        const int64_t tps = (g->tiles_total + v - 1) / v;
+        const int64_t ctas = (int64_t)g->nblk * ((g->tiles_total + tps - 1) / tps);
+        const int64_t cost = ((ctas + sms - 1) / sms) * (tps + ovh);
+        if (best < 0 || cost < best) { best = cost; ns = v; }
+    }
+    if (const char* e = getenv("RMN_LGF_NS")) { const int v = atoi(e); if (v >= 1 && v <= max_ns) ns = v; }   // A/B aid
     g->tps = (int)((g->tiles_total + ns - 1) / ns);
     g->ns = (int)((g->tiles_total + g->tps - 1) / g->tps);
 }

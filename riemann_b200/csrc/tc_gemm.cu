@@ -26,17 +26,17 @@ static PFN_encodeTiled get_encode() {
 }
 
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                 uint32_t box_rows, int tk, bool atom32) {
+                 uint32_t box_rows, int tk) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { rmn_set_error("cuTensorMapEncodeTiled not available from the driver"); return RMN_ERR_CUDA; }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {ld_elems * sizeof(float)};
-    if ((tk != 32 && tk != 16) || (atom32 && tk != 32)) { rmn_set_error("make_tmap_2d: k-block must be 16 or 32"); return RMN_ERR_PARAM; }
+    if (tk != 32 && tk != 16) { rmn_set_error("make_tmap_2d: k-block must be 16 or 32"); return RMN_ERR_PARAM; }
     cuuint32_t box[2] = {(cuuint32_t)tk, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (tk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
+                     tk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { rmn_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RMN_ERR_CUDA; }

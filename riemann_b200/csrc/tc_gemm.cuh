@@ -169,8 +169,7 @@ struct GemmMaps {
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows);
 // host: 2-D fp32 row-major [rows][cols] tensor map, box = [box_rows][tk], tk = 32 (SWIZZLE_128B, single-pass
 // kernels) or TK3 (3-pass kernels; SWIZZLE_64B when 16), OOB -> 0
-// atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (tk = 32 only) -- the layout of an MN-major TF32 operand
 int make_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                 uint32_t box_rows, int tk = TK, bool atom32 = false);
+                 uint32_t box_rows, int tk = TK);
 
 }  // namespace tc
