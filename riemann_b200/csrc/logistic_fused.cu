@@ -61,7 +61,7 @@ constexpr int CB = 128;                    // chains per CTA = UMMA M
 constexpr int BOX_BYTES = NT * 128;        // one TMA box: 64 rows x 32 fp32
 constexpr int PWG = 4;                     // pointwise warpgroups: each takes NT / PWG = 16 of a tile's 64 rows
 constexpr int PCOLS = NT / PWG;
-constexpr int THREADS = 128 + 128 * PWG;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, then PWG x 4 pointwise warps
+constexpr int THREADS = 128 + 128 * PWG;   // warp 0 TMA, 1 MMA (GEMM1), 2 TMEM alloc, 3 MMA (GEMM2), then PWG x 4 pointwise warps
 constexpr int TMEM_COLS_ALLOC = 512;
 
 template <int DP32> struct Cfg {
@@ -144,6 +144,29 @@ __device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a,
         "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, pa;\n"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
 }
+// MMA issue with the issuing lane chosen ONCE (elect_leader) instead of an elect.sync per instruction
+__device__ __forceinline__ uint32_t elect_leader() {
+    uint32_t r;
+    asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\nselp.u32 %0, 1, 0, pe;\n}\n" : "=r"(r));
+    return r;
+}
+template <bool ACC, bool BF16>
+__device__ __forceinline__ void umma_ts_l(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc) {
+    if (BF16)
+        asm volatile("{\n.reg .pred pe, pa;\n.reg .b64 bd;\nsetp.ne.b32 pe, %6, 0;\nsetp.ne.b32 pa, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+                     "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, pa;\n}\n"
+                     ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0), "r"(leader) : "memory");
+    else
+        asm volatile("{\n.reg .pred pe, pa;\n.reg .b64 bd;\nsetp.ne.b32 pe, %6, 0;\nsetp.ne.b32 pa, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+                     "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, pa;\n}\n"
+                     ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_l(uint32_t leader, uint64_t* bar) {
+    asm volatile("{\n.reg .pred pe;\nsetp.ne.b32 pe, %1, 0;\n"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+// all THREADS of the CTA, from either of the two places the roles end at (a named barrier counts arrivals, not places)
+__device__ __forceinline__ void cta_sync_all() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n"
@@ -209,7 +232,8 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     uint64_t* emptyA = fullA + SA;
     uint64_t* z_full = emptyA + SA;              // [2] GEMM1 of a tile complete
     uint64_t* r_full = z_full + 2;               // [2] pointwise stage wrote R
-    uint64_t* th_ready = r_full + 2;             // Theta is in TMEM
+    uint64_t* z_free = r_full + 2;               // [2] GEMM2 of a tile complete: its R (= the Z buffer) may be overwritten
+    uint64_t* th_ready = z_free + 2;             // Theta is in TMEM
     uint64_t* g_full = th_ready + 1;             // last GEMM2 complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 1);
 
@@ -222,7 +246,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_xh); tma_prefetch_desc(&map_xlb); tma_prefetch_desc(&map_xhb); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4 * PWG); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&z_full[b], 1); mbar_init(&r_full[b], 4 * PWG); mbar_init(&z_free[b], 1); }
         mbar_init(th_ready, 4);
         mbar_init(g_full, 1);
         fence_barrier_init();
@@ -233,6 +257,13 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Role dispatch.  Every warp but the GEMM1 issuer works inside this branch and RETURNS from it; the GEMM1 warp's loop is
+    // the kernel's tail.  Code that no other thread can rejoin is convergent for the compiler, so it keeps the descriptors
+    // and tensor-memory addresses of the MMAs in uniform registers and advances them on the uniform datapath: 3-4
+    // instructions per MMA instead of the ~12 (R2UR, elect, vote, ...) it emits for an MMA inside a divergent role branch,
+    // which, sharing a scheduler with four pointwise warps, held GEMM1 to ~70 cycles per MMA where the tensor pipe needs 32
+    // (scratch/mma_rate.cu).
+    if (warp != 1) {
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: Xh | Xlb | Xhb of a tile into one slot (released by GEMM2) =====
         for (int t = 0; t < ntile; ++t) {
@@ -249,68 +280,39 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 tma_load_2d(st + C::OFF_HB + b * BOX_BYTES, &map_xhb, &fullA[s], b * 64, row0);
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the WHOLE warp runs the loop in uniform control flow, `elect.sync` inside each issue =====
-        // Measured with the per-tile clock stamps (RMN_LGF_TIMELINE): with one thread building a 64-bit descriptor per
-        // MMA the issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512
-        // TMEM columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
-        const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_bf16(CB, NT);
+    } else if (warp == 3) {
+        // ===== second MMA issuer: GEMM2.  Its own warp on another scheduler -- an MMA costs its issuing warp ~12
+        // instructions (descriptor arithmetic, R2UR, elect / vote), and with four pointwise warps on the same scheduler
+        // the GEMM1 warp needs ~70 cycles per MMA where the tensor pipe needs 32 (scratch/mma_rate.cu); GEMM2 on that
+        // warp too put 300 more cycles per tile on the critical chain.  Different accumulators (Z / G), so the order
+        // in which the tensor pipe takes the two streams does not change a bit; the one hazard -- GEMM1 of tile t + 2
+        // overwrites the Z buffer GEMM2 of tile t reads R from -- is covered by z_free.
         const uint32_t idesc2 = umma_idesc_bf16(CB, DP32) | (1u << 16);          // B is MN-major
-        constexpr uint32_t t_th = C::COL_TH, t_tb = C::COL_TB, t_lb = C::COL_LB, t_g = C::COL_G;
-        const int d8 = (a.d + 7) / 8, d16 = (a.d + 15) / 16;                    // K steps of GEMM1 that hold data
-        const uint64_t dk0 = umma_desc_kmajor<128>(0);                           // descriptors with a zero start address
+        constexpr uint32_t t_g = C::COL_G;
         const uint64_t dm0 = umma_desc_mnmajor_b16(0, BOX_BYTES, 1024);
-        const uint32_t dk_hi = (uint32_t)(dk0 >> 32), dk_lo0 = (uint32_t)dk0;
         const uint32_t dm_hi = (uint32_t)(dm0 >> 32), dm_lo0 = (uint32_t)dm0;
         const uint32_t smem0 = smem_u32(smem);
         const bool dbg = a.dbg && blockIdx.x == 0 && lane == 0;
         auto stamp = [&](int t, int k) { if (dbg && t < 256) a.dbg[t * 8 + k] = clock64(); };
-        auto gemm1 = [&](int t) {
+        for (int t = 0; t < ntile; ++t) {
             const int s = t % SA;
-            mbar_wait(&fullA[s], (t / SA) & 1);
+            mbar_wait(&r_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
-            stamp(t, 0);
-            const uint32_t tz = C::COL_Z + (uint32_t)((t & 1) * NT);
-            const uint32_t lo_h = dk_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES)) & 0x3FFFF) >> 4);
-            const uint32_t lo_lb = lo_h + (C::OFF_LB >> 4), lo_hb = lo_h + (C::OFF_HB >> 4);
-            // Theta_h Xh^T: TF32, K = 8 = 32 bytes of a row per MMA, four per 32-column box
-            umma_tf32_ts_w<false>(tz, t_th, lo_h, dk_hi, idesc1);
-            for (int k = 1; k < d8; ++k)
-                umma_tf32_ts_w<true>(tz, t_th + (uint32_t)(k * 8), lo_h + (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2), dk_hi, idesc1);
-            // Theta_hb Xlb^T + Theta_lb Xhb^T: bf16, K = 16 = 32 bytes of a row (8 packed TMEM columns) per MMA
-            for (int k = 0; k < d16; ++k) {
-                const uint32_t off = (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2);
-                umma_bf16_ts_w<true>(tz, t_tb + (uint32_t)(k * 8), lo_lb + off, dk_hi, idesc1b);
-                umma_bf16_ts_w<true>(tz, t_lb + (uint32_t)(k * 8), lo_hb + off, dk_hi, idesc1b);
-            }
-            umma_commit_elect(&z_full[t & 1]);
-            stamp(t, 1);
-        };
-        if (ntile > 0) {
-            if (tmem_base != 0) __trap();            // 512 columns allocated: the base cannot be anything else
-            mbar_wait(th_ready, 0);
-            tc_fence_after();
-            gemm1(0);
-            for (int t = 0; t < ntile; ++t) {
-                if (t + 1 < ntile) gemm1(t + 1);
-                const int s = t % SA;
-                mbar_wait(&r_full[t & 1], (t >> 1) & 1);
-                tc_fence_after();
-                stamp(t, 2);
-                // R of warpgroup w (data rows 16 w .. 16 w + 15 of the tile) sits as 8 packed columns at the start of
-                // the warpgroup's 16 logit columns; one K = 16 MMA per warpgroup, 16 rows = 2,048 bytes of the Xhb boxes
-                const uint32_t tr = C::COL_Z + (uint32_t)((t & 1) * NT);
-                const uint32_t lo_b = dm_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES + C::OFF_HB)) & 0x3FFFF) >> 4);
-                if (t == 0) umma_bf16_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
-                else umma_bf16_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
+            stamp(t, 2);
+            // R of warpgroup w (data rows 16 w .. 16 w + 15 of the tile) sits as 8 packed columns at the start of
+            // the warpgroup's 16 logit columns; one K = 16 MMA per warpgroup, 16 rows = 2,048 bytes of the Xhb boxes
+            const uint32_t tr = C::COL_Z + (uint32_t)((t & 1) * NT);
+            const uint32_t lo_b = dm_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES + C::OFF_HB)) & 0x3FFFF) >> 4);
+            if (t == 0) umma_bf16_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
+            else umma_bf16_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
 #pragma unroll
-                for (int ks = 1; ks < NT / 16; ++ks)
-                    umma_bf16_ts_w<true>(t_g, tr + ks * PCOLS, lo_b + ks * (2048 >> 4), dm_hi, idesc2);
-                umma_commit_elect(&emptyA[s]);       // the slot is free once GEMM2 has read it
-                stamp(t, 3);
-            }
-            umma_commit_elect(g_full);
+            for (int ks = 1; ks < NT / 16; ++ks)
+                umma_bf16_ts_w<true>(t_g, tr + ks * PCOLS, lo_b + ks * (2048 >> 4), dm_hi, idesc2);
+            umma_commit_elect(&emptyA[s]);           // the slot is free once GEMM2 has read it
+            umma_commit_elect(&z_free[t & 1]);
+            stamp(t, 3);
         }
+        if (ntile > 0) umma_commit_elect(g_full);
     } else if (warp >= 4) {
         // ===== pointwise warpgroups: thread = chain (TMEM lane 32 q + lane) =====
         const int q = warp & 3, wg = (warp - 4) >> 2;
@@ -459,11 +461,57 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         }
     }
     tc_fence_before();
-    __syncthreads();
+    cta_sync_all();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS_ALLOC);
     }
+    return;
+    }
+    {
+        // ===== MMA issuer: the WHOLE warp runs the loop in uniform control flow, `elect.sync` inside each issue =====
+        // Measured with the per-tile clock stamps (RMN_LGF_TIMELINE): with one thread building a 64-bit descriptor per
+        // MMA the issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512
+        // TMEM columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
+        const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_bf16(CB, NT);
+        constexpr uint32_t t_th = C::COL_TH, t_tb = C::COL_TB, t_lb = C::COL_LB;
+        const int d8 = (a.d + 7) / 8, d16 = (a.d + 15) / 16;                    // K steps of GEMM1 that hold data
+        const uint64_t dk0 = umma_desc_kmajor<128>(0);                           // descriptor with a zero start address
+        const uint32_t dk_hi = (uint32_t)(dk0 >> 32), dk_lo0 = (uint32_t)dk0;
+        const uint32_t smem0 = smem_u32(smem);
+        const bool dbg = a.dbg && blockIdx.x == 0 && lane == 0;
+        auto stamp = [&](int t, int k) { if (dbg && t < 256) a.dbg[t * 8 + k] = clock64(); };
+        const uint32_t leader = elect_leader();
+        if (ntile > 0) {
+            if (tmem_base != 0) __trap();            // 512 columns allocated: the base cannot be anything else
+            mbar_wait(th_ready, 0);
+            tc_fence_after();
+        }
+        for (int t = 0; t < ntile; ++t) {
+            const int s = t % SA;
+            mbar_wait(&fullA[s], (t / SA) & 1);
+            if (t >= 2) mbar_wait(&z_free[t & 1], ((t >> 1) - 1) & 1);          // GEMM2 of tile t - 2 has read its R
+            tc_fence_after();
+            stamp(t, 0);
+            const uint32_t tz = C::COL_Z + (uint32_t)((t & 1) * NT);
+            const uint32_t lo_h = dk_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES)) & 0x3FFFF) >> 4);
+            const uint32_t lo_lb = lo_h + (C::OFF_LB >> 4), lo_hb = lo_h + (C::OFF_HB >> 4);
+            // Theta_h Xh^T: TF32, K = 8 = 32 bytes of a row per MMA, four per 32-column box
+            umma_ts_l<false, false>(leader, tz, t_th, lo_h, dk_hi, idesc1);
+            for (int k = 1; k < d8; ++k)
+                umma_ts_l<true, false>(leader, tz, t_th + (uint32_t)(k * 8), lo_h + (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2), dk_hi, idesc1);
+            // Theta_hb Xlb^T + Theta_lb Xhb^T: bf16, K = 16 = 32 bytes of a row (8 packed TMEM columns) per MMA
+            for (int k = 0; k < d16; ++k) {
+                const uint32_t off = (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2);
+                umma_ts_l<true, true>(leader, tz, t_tb + (uint32_t)(k * 8), lo_lb + off, dk_hi, idesc1b);
+                umma_ts_l<true, true>(leader, tz, t_lb + (uint32_t)(k * 8), lo_hb + off, dk_hi, idesc1b);
+            }
+            umma_commit_l(leader, &z_full[t & 1]);
+            stamp(t, 1);
+        }
+    }
+    tc_fence_before();
+    cta_sync_all();
 }
 
 // X[N][d] (fp64) -> Xh [N][ldx] fp32 (x rounded to nearest TF32), Xlb = bf16(x - Xh), Xhb = bf16(x) [N][ldx] (row pitch

@@ -12,12 +12,12 @@ per = np.median(np.diff(t[:, 1]))
 print("tiles with stamps:", len(t), " median cycles per tile:", per)
 def med(a, b, la):
     print("%-46s %8.0f" % (la, np.median(t[:, b] - t[:, a])))
-med(0, 1, "GEMM1 issue (39 MMAs + 2 commits), same tile")
+med(0, 1, "GEMM1 issue (27 MMAs + commit), same tile")
 med(1, 4, "GEMM1 issued -> logits ready at the pw warp")
 med(4, 5, "tcgen05.ld + wait")
 med(5, 6, "pointwise arithmetic (8 pairs)")
 med(6, 7, "tcgen05.st + wait + fence + arrive")
-med(7, 2, "pw arrived -> MMA thread sees R")
-med(2, 3, "GEMM2 issue (8 MMAs + commit)")
-print("%-46s %8.0f" % ("GEMM2(t) issued -> GEMM1(t+2) after fullA", np.median(t[2:, 0] - t[:-2, 3])))
-print("%-46s %8.0f" % ("GEMM1(t+1) issued -> R(t) ready (MMA idle wait)", np.median(t[:-1, 2] - t[1:, 1])))
+med(7, 2, "pw arrived -> GEMM2 warp sees R (all 16 warps)")
+med(2, 3, "GEMM2 issue (4 MMAs + 2 commits, own warp)")
+print("%-46s %8.0f" % ("GEMM2(t) issued -> GEMM1(t+2) starts (z_free, fullA)", np.median(t[2:, 0] - t[:-2, 3])))
+print("%-46s %8.0f" % ("GEMM1(t+1) issued -> R(t) seen by the GEMM2 warp", np.median(t[:-1, 2] - t[1:, 1])))
