@@ -262,7 +262,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     // and tensor-memory addresses of the MMAs in uniform registers and advances them on the uniform datapath: 3-4
     // instructions per MMA instead of the ~12 (R2UR, elect, vote, ...) it emits for an MMA inside a divergent role branch,
     // which, sharing a scheduler with four pointwise warps, held GEMM1 to ~70 cycles per MMA where the tensor pipe needs 32
-    // (scratch/mma_rate.cu).
+    // (scripts/peaks/mma_rate.cu).
     if (warp != 1) {
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: Xh | Xlb | Xhb of a tile into one slot (released by GEMM2) =====
@@ -283,7 +283,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     } else if (warp == 3) {
         // ===== second MMA issuer: GEMM2.  Its own warp on another scheduler -- an MMA costs its issuing warp ~12
         // instructions (descriptor arithmetic, R2UR, elect / vote), and with four pointwise warps on the same scheduler
-        // the GEMM1 warp needs ~70 cycles per MMA where the tensor pipe needs 32 (scratch/mma_rate.cu); GEMM2 on that
+        // the GEMM1 warp needs ~70 cycles per MMA where the tensor pipe needs 32 (scripts/peaks/mma_rate.cu); GEMM2 on that
         // warp too put 300 more cycles per tile on the critical chain.  Different accumulators (Z / G), so the order
         // in which the tensor pipe takes the two streams does not change a bit; the one hazard -- GEMM1 of tile t + 2
         // overwrites the Z buffer GEMM2 of tile t reads R from -- is covered by z_free.
