@@ -1,6 +1,6 @@
 // microbenchmark: dispatch rate of small tcgen05.mma (M = 128, N = 64 / 128) with A in tensor memory or shared memory,
 // for the issue forms the fused logistic sweep could use.  One CTA; prints cycles per MMA.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I riemann_b200/csrc scripts/peaks/mma_rate.cu -o scratch/mma_rate
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I riemann_b200/csrc scripts/peaks/mma_rate.cu -o scripts/peaks/mma_rate
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "tc_gemm.cuh"
