@@ -32,9 +32,9 @@
 //
 //   TMEM columns: Theta_h [0, dp32) | Theta_hb, Theta_lb (dp32 / 2 each) | G (dp32) | Z/R buffer 0, 1 (64 each)
 //
-// The MMA warp issues GEMM1 of tile t+1 before it waits for the R of tile t, so the tensor pipe works on the
-// next logits while the pointwise warps process the current ones; tcgen05.mma executes in issue order, which is
-// what makes reusing a Z buffer two tiles later safe without another barrier.
+// GEMM1 and GEMM2 are issued by two warps (1 and 3): the accumulators differ, so the order in which the tensor pipe takes the
+// two instruction streams cannot change the result.  GEMM1 of tile t+1 runs while the pointwise warps process tile t;
+// GEMM1 of tile t+2 reuses the Z buffer GEMM2 of tile t reads R from and waits for that GEMM2's commit (z_free).
 //
 // Measured dead end (gpurun r2k): releasing the ring box by box (eight one-box slots, TMA two tiles ahead) was SLOWER, 2.35 ms
 // per 1,024-chain sweep against 1.77 -- four commits and four barrier waits per tile cost the MMA thread more than the
@@ -469,10 +469,9 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     return;
     }
     {
-        // ===== MMA issuer: the WHOLE warp runs the loop in uniform control flow, `elect.sync` inside each issue =====
-        // Measured with the per-tile clock stamps (RMN_LGF_TIMELINE): with one thread building a 64-bit descriptor per
-        // MMA the issue rate, not the pipe, set the tile time.  Here every operand is warp-uniform (the CTA owns all 512
-        // TMEM columns, so its TMEM base is 0 and the addresses are literals) and an MMA costs one add on the descriptor.
+        // ===== GEMM1 issuer (warp 1): the kernel's convergent tail, issuing lane elected once (see the role dispatch) =====
+        // Every operand is thread-invariant (the CTA owns all 512 TMEM columns, so its TMEM base is 0 and the addresses are
+        // literals; descriptors differ by an add on their low word) and lives in uniform registers.
         const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_bf16(CB, NT);
         constexpr uint32_t t_th = C::COL_TH, t_tb = C::COL_TB, t_lb = C::COL_LB;
         const int d8 = (a.d + 7) / 8, d16 = (a.d + 15) / 16;                    // K steps of GEMM1 that hold data
