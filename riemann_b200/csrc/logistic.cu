@@ -1199,8 +1199,8 @@ struct LogisticSampler : SamplerImpl {
         a.llp = fllp; a.gp = fgp; a.W = st.W; a.ldw = st.Npad; a.w_bf16 = bf16m ? 1 : 0;
         static long long* d_tl = nullptr;                          // RMN_LGF_TIMELINE=1: clock64 stamps of CTA 0 (debug aid)
         if (const char* e = getenv("RMN_LGF_TIMELINE")) {
-            if (e[0] == '1' && !d_tl) { cudaMalloc(&d_tl, 256 * 9 * 8); }
-            if (e[0] == '1' && d_tl) { cudaMemsetAsync(d_tl, 0, 256 * 9 * 8, stream); a.dbg = d_tl; }
+            if (e[0] == '1' && !d_tl) { cudaMalloc(&d_tl, 256 * 8 * 8); }
+            if (e[0] == '1' && d_tl) { cudaMemsetAsync(d_tl, 0, 256 * 8 * 8, stream); a.dbg = d_tl; }
         }
         if (!tf32m) ktimer.begin("lg_fused_sweep_kernel", stream);     // mMALA: the metric GEMM is the dominant kernel
         if (int rc = lgf::sweep(fmaps, fg, a, stream)) return rc;
@@ -1208,7 +1208,7 @@ struct LogisticSampler : SamplerImpl {
         if (int rc = lgf::reduce(fg, st.K, st.dp, fllp, fgp, st.llpart, st.gpart, stream)) return rc;
         if (a.dbg) {
             if (const char* f = getenv("RMN_LGF_TIMELINE_FILE")) {
-                std::vector<long long> h(256 * 9);
+                std::vector<long long> h(256 * 8);
                 cudaStreamSynchronize(stream);
                 cudaMemcpy(h.data(), a.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
                 if (FILE* fp = fopen(f, "wb")) { fwrite(h.data(), 8, h.size(), fp); fclose(fp); }

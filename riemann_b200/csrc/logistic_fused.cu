@@ -280,12 +280,6 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 tma_load_2d(st + C::OFF_HB + b * BOX_BYTES, &map_xhb, &fullA[s], b * 64, row0);
             }
         }
-    } else if (warp == 2 && a.dbg && blockIdx.x == 0) {
-        // timeline aid: when GEMM1 of a tile is COMPLETE (an otherwise idle warp watching z_full), stamps 2048 ..
-        for (int t = 0; t < ntile && t < 256; ++t) {
-            mbar_wait(&z_full[t & 1], (t >> 1) & 1);
-            if (lane == 0) a.dbg[2048 + t] = clock64();
-        }
     } else if (warp == 3) {
         // ===== second MMA issuer: GEMM2.  Its own warp on another scheduler -- an MMA costs its issuing warp ~12
         // instructions (descriptor arithmetic, R2UR, elect / vote), and with four pointwise warps on the same scheduler

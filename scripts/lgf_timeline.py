@@ -4,9 +4,7 @@ ready, tcgen05.ld done, arithmetic done, R handed over).  Prints per-phase media
     python scripts/lgf_timeline.py gpurun_out/tl.bin"""
 import sys
 import numpy as np
-raw = np.fromfile(sys.argv[1], dtype=np.int64)
-zc = raw[2048:2304] if raw.size >= 2304 else None          # completion of GEMM1 per tile (watcher warp)
-t = raw[:2048].reshape(256, 8)
+t = np.fromfile(sys.argv[1], dtype=np.int64).reshape(256, 8)
 ok = np.all(t[:, :8] > 0, axis=1)
 t = t[ok][8:200]
 names = ["g1_after_fullA", "g1_issued", "rfull_ready", "g2_issued", "pw_zfull", "pw_ld_done", "pw_math_done", "pw_arrived"]
@@ -23,7 +21,3 @@ med(7, 2, "pw arrived -> GEMM2 warp sees R (all 16 warps)")
 med(2, 3, "GEMM2 issue (4 MMAs + 2 commits, own warp)")
 print("%-46s %8.0f" % ("GEMM2(t) issued -> GEMM1(t+2) starts (z_free, fullA)", np.median(t[2:, 0] - t[:-2, 3])))
 print("%-46s %8.0f" % ("GEMM1(t+1) issued -> R(t) seen by the GEMM2 warp", np.median(t[:-1, 2] - t[1:, 1])))
-if zc is not None:
-    zz = zc[ok][8:200]
-    print("%-46s %8.0f" % ("GEMM1 issued -> GEMM1 complete (watcher warp)", np.median(zz - t[:, 1])))
-    print("%-46s %8.0f" % ("GEMM1 complete -> pointwise warp past z_full", np.median(t[:, 4] - zz)))
