@@ -300,45 +300,39 @@ __device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const doubl
 // DATA: 0 = data tables read from global memory (too large for shared memory), 1 = staged in shared
 // memory, 2 = staged and 64 <= M < 128 (P2 = 64: fully unrolled 7-level search; the bench shape)
 template <bool INJ, int DATA, int GL>
-__global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
-changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
-                   int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
-                   const double* __restrict__ tape, rmn_trace_t tr, int shared_mv) {
+__device__ __forceinline__ void cp_block(const CPParams& P, const double* __restrict__ xs, CPState st,
+                                         int64_t K, int64_t t_begin, int64_t t_end, int64_t step0, uint64_t seed,
+                                         int64_t chain_offset, const double* __restrict__ tape, const rmn_trace_t& tr,
+                                         int shared_mv, int64_t blk) {
+    // iterations [t_begin, t_end) of the launch for the 128 / GL chains of block `blk`; the chain state is read from and
+    // written back to global memory (L2-coherent loads: in the time-sliced kernel another SM wrote it)
     constexpr int EPL = Geo<GL>::EPL;
     constexpr int NS = Geo<GL>::NS;
     constexpr int CPW = 32 / GL;                  // chains per warp = chains per schedule group
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ double smem[];
-    const double* xs = gdata;
     constexpr int LOGP2 = (DATA == 2) ? 6 : -1;
-    if (DATA != 0) {
-        const int n = P.XP + 2 * P.M + 2;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = gdata[i];
-        __syncthreads();
-        xs = smem;
-    }
     const double* cy = xs + P.XP;
     const double* cyy = cy + P.M + 1;
 
     const int lane = threadIdx.x & (GL - 1);
     // schedule groups are aligned to GLOBAL chain ids: `head` leading groups of the grid are dead
     const int head = shared_mv ? (int)(chain_offset & (CPW - 1)) : 0;
-    const int64_t c_raw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GL - head;
+    const int64_t c_raw = (blk * (int64_t)blockDim.x + threadIdx.x) / GL - head;
     const bool live = c_raw >= 0 && c_raw < K;
     const int64_t c = c_raw < 0 ? 0 : (c_raw < K ? c_raw : K - 1);   // dead groups shadow a live chain, never store
 
-    int k = st.k[c];
+    int k = __ldcg(st.k + c);
     double cx[EPL], cv[EPL];
     int bu[EPL];                                  // cached run boundaries of the state
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
         const int e = lane + GL * j;
-        cx[j] = st.cpx[c * LANES + e];
-        cv[j] = st.cpv[c * LANES + e];
+        cx[j] = __ldcg(st.cpx + c * LANES + e);
+        cv[j] = __ldcg(st.cpv + c * LANES + e);
         bu[j] = (e < k) ? upper_bound<LOGP2>(xs, P.P2, cx[j]) : P.M;
     }
-    double sig = st.sig[c];
-    double lp = st.lp[c];
+    double sig = __ldcg(st.sig + c);
+    double lp = __ldcg(st.lp + c);
     double ss_c, vt_c, lg_c, ls2_c;               // pieces of lp (see cp_terms / cp_assemble)
     cp_logpost_rows<GL>(P, cy, cyy, lane, LANES, k, cx, cv, bu, sig, 0, ss_c, vt_c, lg_c, ls2_c);
     int nacc = 0, novf = 0;
@@ -373,9 +367,9 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
     // the Philox block of step t+1 is issued during step t (it depends on nothing but the counter), so its
     // integer multiplies fill the fp64 / LDS latency of the evaluation
     uint4 rA = make_uint4(0, 0, 0, 0);
-    if (!INJ) rA = rk.block((uint64_t)step0, (uint32_t)lane);
+    if (!INJ) rA = rk.block((uint64_t)(step0 + t_begin), (uint32_t)lane);
 
-    for (int64_t t = 0; t < T; ++t) {
+    for (int64_t t = t_begin; t < t_end; ++t) {
         const uint64_t step = (uint64_t)(step0 + t);
         const int kw = __reduce_max_sync(FULL, k);
         double snew, du, uacc;
@@ -597,17 +591,75 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
             st.k[c] = k;
             st.sig[c] = sig;
             st.lp[c] = lp;
-            st.dacc[c] += nacc;
-            st.dovf[c] += novf;
+            st.dacc[c] = __ldcg(st.dacc + c) + nacc;
+            st.dovf[c] = __ldcg(st.dovf + c) + novf;
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const int i = lane + GL * s;
             if (i < RMN_CP_NDIAG) {
-                st.S1[(int64_t)i * K + c] += s1[s];
-                st.S2[(int64_t)i * K + c] += s2[s];
+                st.S1[(int64_t)i * K + c] = __ldcg(st.S1 + (int64_t)i * K + c) + s1[s];
+                st.S2[(int64_t)i * K + c] = __ldcg(st.S2 + (int64_t)i * K + c) + s2[s];
             }
         }
+    }
+}
+
+// DATA: 0 = data tables read from global memory (too large for shared memory), 1 = staged in shared
+// memory, 2 = staged and 64 <= M < 128 (P2 = 64: fully unrolled 7-level search; the bench shape)
+template <bool INJ, int DATA, int GL>
+__global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
+changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
+                   int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
+                   const double* __restrict__ tape, rmn_trace_t tr, int shared_mv) {
+    extern __shared__ double smem[];
+    const double* xs = gdata;
+    if (DATA != 0) {
+        const int n = P.XP + 2 * P.M + 2;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = gdata[i];
+        __syncthreads();
+        xs = smem;
+    }
+    cp_block<INJ, DATA, GL>(P, xs, st, K, 0, T, step0, seed, chain_offset, tape, tr, shared_mv, blockIdx.x);
+}
+
+// Time-sliced form of the same run (plain Philox runs without traces).  A launch of B blocks that do not fit the SMs'
+// resident-block slots S in a whole number of waves ends with a partly filled wave (2,048 blocks on 592 slots = 3.46 waves
+// at the bench shape: 4.5 % of the launch).  Here exactly S persistent blocks walk the items (time slice j, block b), index
+// j B + b, in stripes (item i belongs to persistent block i mod S): every persistent block gets the same number of items
+// to within one, the state of a slice's chains travels through global memory, and a flag per chain block orders the
+// slices of the same chains (its predecessor is B >> S items earlier, so the wait is almost never taken; it cannot
+// deadlock: all S blocks are resident and each walks its items in increasing order).  Philox is keyed by (step, chain),
+// so the chains are bit-identical to the one-slice launch.
+template <int DATA, int GL>
+__global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
+changepoint_sliced_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
+                          int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset, int shared_mv,
+                          int nblk, int slice, int nslice, int* __restrict__ done) {
+    extern __shared__ double smem[];
+    const double* xs = gdata;
+    if (DATA != 0) {
+        const int n = P.XP + 2 * P.M + 2;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) smem[i] = gdata[i];
+        __syncthreads();
+        xs = smem;
+    }
+    rmn_trace_t tr{};
+    const int64_t items = (int64_t)nblk * nslice;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int j = (int)(it / nblk), b = (int)(it % nblk);
+        if (j > 0) {
+            if (threadIdx.x == 0) {
+                while (*reinterpret_cast<volatile int*>(done + b) < j) __nanosleep(64);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        const int64_t t0 = (int64_t)j * slice, t1 = (t0 + slice < T) ? t0 + slice : T;
+        cp_block<false, DATA, GL>(P, xs, st, K, t0, t1, step0, seed, chain_offset, nullptr, tr, shared_mv, b);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(done + b) = j + 1;
     }
 }
 
@@ -704,6 +756,7 @@ struct ChangepointSampler : SamplerImpl {
             if (v == 4 || v == 8 || v == 16) gl = v;
         }
         if (const char* e = getenv("RMN_CP_SCHEDULE")) shared_mv = (e[0] == 'c' || e[0] == '0') ? 0 : 1;
+        if (const char* e = getenv("RMN_CP_SLICED")) sliced = (e[0] == '0') ? 0 : 1;
         smem_bytes = (size_t)(P.XP + 2 * P.M + 2) * 8;
         use_smem = smem_bytes <= 96 * 1024;
     }
@@ -735,7 +788,9 @@ struct ChangepointSampler : SamplerImpl {
     template <int GL> cudaError_t set_smem_attr() {
         cudaError_t e = rmn_raise_dyn_smem((const void*)changepoint_kernel<false, 1, GL>, smem_bytes);
         if (e != cudaSuccess) return e;
-        return rmn_raise_dyn_smem((const void*)changepoint_kernel<true, 1, GL>, smem_bytes);
+        e = rmn_raise_dyn_smem((const void*)changepoint_kernel<true, 1, GL>, smem_bytes);
+        if (e != cudaSuccess || GL != 4) return e;
+        return rmn_raise_dyn_smem((const void*)changepoint_sliced_kernel<1, 4>, smem_bytes);
     }
     unsigned grid(int gl = LANES) const { return (unsigned)((s->K * gl + 127) / 128); }
     // grid of the T-step kernel: schedule groups are aligned to global chain ids, so up to 32/gl - 1 leading
@@ -779,10 +834,55 @@ struct ChangepointSampler : SamplerImpl {
             default: launch_gl<INJ, 4>(T, tape, t0, stream); break;
         }
     }
+    // time-sliced launch (changepoint_sliced_kernel): plain Philox runs whose blocks do not fill a whole number of waves
+    int* d_done = nullptr;
+    int done_cap = 0;
+    int sliced = 1;                 // RMN_CP_SLICED=0 switches it off (A/B)
+    ~ChangepointSampler() override { if (d_done) cudaFree(d_done); }
+    template <int DATA, int GL>
+    bool launch_sliced(int64_t T, unsigned nblk, int sh, size_t smem, cudaStream_t stream) {
+        constexpr int SLICE_MIN = 100;          // iterations: the state round trip and the entry evaluation cost about one
+        if (!sliced || T < 2 * SLICE_MIN) return false;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, changepoint_sliced_kernel<DATA, GL>, 128, smem) != cudaSuccess || per_sm < 1)
+            return false;
+        const unsigned slots = (unsigned)(per_sm * sms);
+        if (nblk <= slots || nblk % slots == 0) return false;       // one wave, or whole waves: nothing to gain
+        // slices: the count with the least modelled time = rounds of the striped walk per item, times the slice overhead
+        // (state round trip + entry evaluation, about 2.5 iterations' worth)
+        int nslice = 2;
+        double best = 0.0;
+        for (int v = 2; v <= 16 && (int64_t)v * SLICE_MIN <= T; ++v) {
+            const double items = (double)nblk * v;
+            const double cost = ceil(items / slots) / (items / slots) * (1.0 + 2.5 * v / (double)T);
+            if (best == 0.0 || cost < best - 1e-9) { best = cost; nslice = v; }
+        }
+        if (best >= ceil((double)nblk / slots) / ((double)nblk / slots)) return false;     // the plain launch is as good
+        const int slice = (int)((T + nslice - 1) / nslice);
+        nslice = (int)((T + slice - 1) / slice);
+        if ((int)nblk > done_cap) {
+            if (d_done) cudaFree(d_done);
+            d_done = nullptr; done_cap = 0;
+            if (cudaMalloc(&d_done, (size_t)nblk * sizeof(int)) != cudaSuccess) return false;
+            done_cap = (int)nblk;
+        }
+        if (cudaMemsetAsync(d_done, 0, (size_t)nblk * sizeof(int), stream) != cudaSuccess) return false;
+        changepoint_sliced_kernel<DATA, GL><<<slots, 128, smem, stream>>>(
+            P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, sh, (int)nblk, slice, nslice, d_done);
+        return true;
+    }
     template <bool INJ, int GL>
     void launch_gl(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
         const int sh = INJ ? 0 : shared_mv;
         const unsigned g = run_grid(GL, sh);
+        const bool traced = t0.d_k || t0.d_cpx || t0.d_cpv || t0.d_sig || t0.d_logpost || t0.d_prop_logpost || t0.d_accepted ||
+                            t0.d_logqratio || t0.d_prop_k || t0.d_prop_sig || t0.d_prop_cpx || t0.d_prop_cpv;
+        if constexpr (!INJ && GL == 4) {
+            if (!traced && use_smem && P.P2 == 64) { if (launch_sliced<2, GL>(T, g, sh, smem_bytes, stream)) return; }
+            else if (!traced && use_smem) { if (launch_sliced<1, GL>(T, g, sh, smem_bytes, stream)) return; }
+        }
         if (use_smem && P.P2 == 64)
             changepoint_kernel<INJ, 2, GL><<<g, 128, smem_bytes, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);

@@ -244,6 +244,34 @@ def test_single_chain_warps_replay_the_reference_through_the_move_specific_guard
         assert np.array_equal(ex1["accepted"][:, 0], ex4["accepted"][:, c])
 
 
+@pytest.mark.parametrize("schedule,off", [("group", 0), ("group", 13), ("chain", 5)])
+def test_time_sliced_launch_is_bit_identical(schedule, off, monkeypatch):
+    """More blocks than the SMs hold at once and not a whole number of waves: the run goes through
+    changepoint_sliced_kernel (persistent blocks, time slices of the launch striped over them, the chain state handed
+    over through global memory).  States, log-posteriors and accept counts must equal those of the one-slice launch
+    (RMN_CP_SLICED=0) bit for bit, across launches that continue each other; the diagnostics sums are added slice by
+    slice, so they agree to rounding."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models.changepoint import ChangepointParams
+    dm, dp, _, _ = _setup()
+    th0 = ChangepointParams([2.0], [1.0, 3.0], 0.1)
+    K = 23000                                     # 719 blocks of 32 chains: more than 592 resident, not a multiple
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RMN_CP_SLICED", mode)
+        s = Sampler(dm, dp, th0, K=K, seed=3, chain_offset=off, move_schedule=schedule)
+        s.run(450, trace=False)
+        s.run(230, trace=False)                   # 2 slices of 115; continues from the first launch's state
+        out[mode] = (s._download_state(), s.diagnostics(allreduce=False), s.chain_moments())
+    (a_st, a_lp), a_d, a_m = out["0"]
+    (b_st, b_lp), b_d, b_m = out["1"]
+    for x, y in zip(a_st, b_st):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a_lp, b_lp)
+    assert a_d["accept_rate"] == b_d["accept_rate"] and a_d["overflows"] == b_d["overflows"]
+    assert np.allclose(a_m[0], b_m[0], rtol=1e-12, atol=0) and np.allclose(a_m[1], b_m[1], rtol=1e-9, atol=1e-18)
+
+
 @pytest.mark.parametrize("schedule", ["group", "chain"])
 def test_move_schedules_are_shard_invariant(schedule):
     """Philox mode: chains [off, off + n) of a sharded run equal the same chains of the unsharded run bit for bit, for
