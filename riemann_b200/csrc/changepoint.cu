@@ -625,12 +625,11 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
 
 // Time-sliced form of the same run (plain Philox runs without traces).  A launch of B blocks that do not fit the SMs'
 // resident-block slots S in a whole number of waves ends with a partly filled wave (2,048 blocks on 592 slots = 3.46 waves
-// at the bench shape: 4.5 % of the launch).  Here exactly S persistent blocks walk the items (time slice j, block b), index
-// j B + b, in stripes (item i belongs to persistent block i mod S): every persistent block gets the same number of items
-// to within one, the state of a slice's chains travels through global memory, and a flag per chain block orders the
-// slices of the same chains (its predecessor is B >> S items earlier, so the wait is almost never taken; it cannot
-// deadlock: all S blocks are resident and each walks its items in increasing order).  Philox is keyed by (step, chain),
-// so the chains are bit-identical to the one-slice launch.
+// at the bench shape: 4.5 % of the launch).  Here S persistent blocks take the items (time slice j, block b), index
+// j B + b, from an atomic counter in increasing order: every persistent block gets the same amount of work to within one
+// item, the state of a slice's chains travels through global memory, and a flag per chain block orders the slices of the
+// same chains (the predecessor is B >> S items earlier, so the wait is almost never taken).  Philox is keyed by
+// (step, chain), so the chains are bit-identical to the one-slice launch.
 template <int DATA, int GL>
 __global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
 changepoint_sliced_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
@@ -645,16 +644,25 @@ changepoint_sliced_kernel(const __grid_constant__ CPParams P, const double* __re
         xs = smem;
     }
     rmn_trace_t tr{};
-    const int64_t items = (int64_t)nblk * nslice;
-    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-        const int j = (int)(it / nblk), b = (int)(it % nblk);
-        if (j > 0) {
-            if (threadIdx.x == 0) {
+    __shared__ int s_item;
+    const int items = nblk * nslice;
+    for (;;) {
+        // items are handed out in increasing order to blocks that are RUNNING: the predecessor of an item was taken
+        // earlier, so its owner is resident whatever else shares the device -- the wait below cannot deadlock
+        if (threadIdx.x == 0) {
+            const int it = atomicAdd(done + nblk, 1);
+            const int j = it / nblk, b = it % nblk;
+            if (it < items && j > 0) {
                 while (*reinterpret_cast<volatile int*>(done + b) < j) __nanosleep(64);
                 __threadfence();
             }
-            __syncthreads();
+            s_item = it;
         }
+        __syncthreads();
+        const int it = s_item;
+        __syncthreads();
+        if (it >= items) break;
+        const int j = it / nblk, b = it % nblk;
         const int64_t t0 = (int64_t)j * slice, t1 = (t0 + slice < T) ? t0 + slice : T;
         cp_block<false, DATA, GL>(P, xs, st, K, t0, t1, step0, seed, chain_offset, nullptr, tr, shared_mv, b);
         __threadfence();
@@ -865,10 +873,10 @@ struct ChangepointSampler : SamplerImpl {
         if ((int)nblk > done_cap) {
             if (d_done) cudaFree(d_done);
             d_done = nullptr; done_cap = 0;
-            if (cudaMalloc(&d_done, (size_t)nblk * sizeof(int)) != cudaSuccess) return false;
+            if (cudaMalloc(&d_done, ((size_t)nblk + 1) * sizeof(int)) != cudaSuccess) return false;     // flags + item counter
             done_cap = (int)nblk;
         }
-        if (cudaMemsetAsync(d_done, 0, (size_t)nblk * sizeof(int), stream) != cudaSuccess) return false;
+        if (cudaMemsetAsync(d_done, 0, ((size_t)nblk + 1) * sizeof(int), stream) != cudaSuccess) return false;
         changepoint_sliced_kernel<DATA, GL><<<slots, 128, smem, stream>>>(
             P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, sh, (int)nblk, slice, nslice, d_done);
         return true;
