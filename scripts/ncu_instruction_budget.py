@@ -28,8 +28,8 @@ ANCHORS = {
                        ("// log of four per-chain arguments with one call", "batched log (log4)"),
                        ("__device__ __forceinline__ double cp_assemble", "log-posterior assembly (cp_assemble)"),
                        ("// full evaluation (pointwise entry", "full evaluation helper"),
-                       ("changepoint_kernel(const __grid_constant__ CPParams P", "prologue (state load, caches, Philox prefetch)"),
-                       ("    for (int64_t t = 0; t < T; ++t) {", "per-step randoms and move selection"),
+                       ("__device__ __forceinline__ void cp_block(", "prologue (state load, caches, Philox prefetch)"),
+                       ("    for (int64_t t = t_begin; t < t_end; ++t) {", "per-step randoms and move selection"),
                        ("        // What the warp as a whole needs this step", "warp votes"),
                        ("        // normals of the block moves", "normals (Box-Muller calls, second Philox block)"),
                        ("        // ---- build the proposal by selection", "fixed-dimension proposal by selection"),
@@ -40,6 +40,7 @@ ANCHORS = {
                        ("        // sampler.py:83-84 with Python's min(0, nan) == 0", "accept, state update"),
                        ("        if ((step % RMN_CP_DIAG_EVERY) == 0) {", "thinned diagnostics"),
                        ("        if (live && tracing) {", "trace stores + epilogue"),
+                       ("changepoint_kernel(const __grid_constant__ CPParams P", "kernel wrappers (data staging, time slices)"),
                        ("// evaluate n states given in the canonical layout", "(other kernels)")],
 }
 
@@ -107,7 +108,7 @@ def main():
                 label = lab
                 break
         by_region[label] += n
-    print("# Instruction budget of `changepoint_kernel<0,2,4>` (from `%s`)\n" % rep.split("/")[-1])
+    print("# Instruction budget of the changepoint kernel (`cp_block<0,2,4>`; from `%s`)\n" % rep.split("/")[-1])
     print("%.3e executed warp-instructions = **%.0f per warp-step = %.0f per chain-step** (8 chains per warp).\n"
           % (total, total / base, total / base / 8))
     print("## By how often an instruction runs\n\n| runs on this fraction of warp-steps | static instructions | executed per warp-step | share |\n|---|---|---|---|")
