@@ -206,13 +206,13 @@ int rmn_sampler_create(rmn_sampler_t** out, rmn_model_t* m, rmn_proposal_t* p, i
                        size_t workspace_bytes);
 /* Precision modes.  RMN_PREC_F64 (default): fp64 state and arithmetic like the reference's numpy (DMMA / DFMA).
  * RMN_PREC_TF32X3: the path's dense contraction on the tcgen05 tensor cores, fp32-accurate (a TF32 MMA for the leading
- * term plus two correction MMAs per product: TF32 in the dense Gaussian GEMM, bf16 at twice the depth in the logistic sweep),
+ * term plus two correction MMAs per product: TF32 in the dense Gaussian GEMM, scaled fp16 at twice the depth in the logistic sweep),
  * everything that enters the accept test reduced in fp64.  ONE stated budget per mode (riemann_b200/budgets.py, asserted by
  * the tests together with an accept-decision gate) on the log-posterior DIFFERENCE proposal - state of sampler.py:83:
  *   dense Gaussian model (fp32 chain state, the K x d by d x d product of the INCREMENT):  5e-7 d   (5e-4 at d = 1000)
  *   logistic model, MALA / HMC / RW / pCN / mMALA (ONE fused kernel per likelihood sweep, logistic_fused.cu: logits into
- *   tensor memory, sigmoid / softplus out of it, R = y - p back into tensor memory as the bf16 operand of the gradient
- *   product -- the gradient only shapes the proposal):  2e-3 sqrt(N / 1e6)   (2e-3 at N = 1e6).  A state's log-posterior also carries a constant offset (<= 5e-8 N,
+ *   tensor memory, sigmoid / softplus out of it, R = y - p back into tensor memory as the fp16 operand of the gradient
+ *   product -- the gradient only shapes the proposal):  1e-3 sqrt(N / 1e6)   (1e-3 at N = 1e6, SURVEY 8d's gate).  A state's log-posterior also carries a constant offset (<= 5e-8 N,
  *   the fp32 softplus) that is the same for every state and cancels in every Metropolis-Hastings ratio.
  *   With simplified mMALA the Fisher metric of the proposal is one GEMM with bf16 operands (round to nearest, fp32
  *   accumulate; see RMN_PREC_TF32_METRIC for why any deterministic metric keeps the sampler exact). */

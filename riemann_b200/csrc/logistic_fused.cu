@@ -9,15 +9,15 @@
 //
 //   TMA thread    ONE ring of SA slots; a slot holds the 64-row tile three times over the same rows:
 //                   Xh   fp32 (x rounded to nearest TF32)        [64][dp32]   SWIZZLE_128B boxes of 32 columns
-//                   Xlb  bf16 (x - Xh)                           [64][dp32]   SWIZZLE_128B boxes of 64 columns
-//                   Xhb  bf16 (x)                                [64][dp32]   SWIZZLE_128B boxes of 64 columns
+//                   Xlb  fp16 ((x - Xh) 2^10)                    [64][dp32]   SWIZZLE_128B boxes of 64 columns
+//                   Xhb  fp16 (x 2^-10)                          [64][dp32]   SWIZZLE_128B boxes of 64 columns
 //                 8 bytes per element, all of it read by BOTH products: the slot is released by GEMM2.
-//   MMA warp      GEMM1  Z[128 x 64] = Theta_h Xh^T  (kind::tf32)  +  Theta_hb Xlb^T + Theta_lb Xhb^T  (kind::f16, bf16):
-//                        the two correction terms are 2^-11 of the product, so bf16 operands (2^-9 relative) leave
+//   MMA warp      GEMM1  Z[128 x 64] = Theta_h Xh^T  (kind::tf32)  +  Theta_hb Xlb^T + Theta_lb Xhb^T  (kind::f16, fp16):
+//                        the two correction terms are 2^-11 of the product, so fp16 operands (2^-12 relative) leave
 //                        z fp32-accurate at HALF the instruction count of a TF32 correction (K = 16 per MMA).
-//                        A = Theta from TENSOR MEMORY (written once per CTA; bf16 parts packed two per column)
+//                        A = Theta from TENSOR MEMORY (written once per CTA; fp16 parts packed two per column)
 //                 GEMM2  G[128 x dp32] += R[128 x 64] Xhb[64 x dp32]   (kind::f16: the gradient only shapes the
-//                        proposal); A = R as bf16 pairs from tensor memory, written in place over Z by the pointwise
+//                        proposal); A = R as fp16 pairs from tensor memory, written in place over Z by the pointwise
 //                        warps; B = the SAME Xhb boxes read MN-major -- a 16-bit operand may be MN-major in the plain
 //                        128-byte swizzle, so the tile TMA wrote K-major for GEMM1 is, read with the other descriptor,
 //                        the transposed operand of GEMM2.  (Round 2's first version kept the gradient in TF32, whose
@@ -27,7 +27,7 @@
 //   4 x 4 warps   pointwise stage, all four warpgroups on every tile (16 of its 64 rows each): tcgen05.ld the logits, fp32
 //                 sigmoid / softplus (one MUFU.EX2, one MUFU.RCP and a degree-9 polynomial for log1p per element, two
 //                 elements per instruction with the packed fp32 FMA of sm_100),
-//                 log-likelihood partial sums in fp64, R = y - p rounded to bf16 -> tcgen05.st back into the first 8 of
+//                 log-likelihood partial sums in fp64, R = y - p rounded to fp16 -> tcgen05.st back into the first 8 of
 //                 the warpgroup's 16 TMEM columns (and W = p(1-p) to HBM for the mMALA metric GEMM)
 //
 //   TMEM columns: Theta_h [0, dp32) | Theta_hb, Theta_lb (dp32 / 2 each) | G (dp32) | Z/R buffer 0, 1 (64 each)
@@ -40,14 +40,15 @@
 // per 1,024-chain sweep against 1.77 -- four commits and four barrier waits per tile cost the MMA thread more than the
 // exposed TMA latency it hid.
 //
-// Accuracy.  Xh / Theta_h are rounded to nearest TF32 and the remainders to bf16, so the pair carries ~19 bits and the
-// dropped terms are ~2^-20 of a product; the per-row terms are fp32 (|error| ~1e-7 each), summed in fp64.  Measured
-// budget: tests/test_gpu_logistic.py (riemann_b200/budgets.py).
+// Accuracy.  Xh / Theta_h are rounded to nearest TF32 and the remainders to (scaled) fp16, so the pair carries 22 bits and
+// the dropped terms are ~2^-24 of a product; the per-row terms are fp32 (|error| ~1e-7 each), summed in fp64.  R and x
+// enter the gradient product as fp16 (2^-12 relative).  Measured budget: tests/test_gpu_logistic.py (riemann_b200/budgets.py).
 // The result is a deterministic function of theta (fixed tile order, no atomics).
 #include <algorithm>
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "logistic_fused.cuh"
 #include <stdlib.h>
 
@@ -66,7 +67,7 @@ constexpr int TMEM_COLS_ALLOC = 512;
 
 template <int DP32> struct Cfg {
     static constexpr int NBOX = DP32 / 32;                         // fp32 boxes (32 columns) of the Xh part
-    static constexpr int NB16 = DP32 / 64;                         // bf16 boxes (64 columns) of the Xlb / Xhb parts
+    static constexpr int NB16 = DP32 / 64;                         // fp16 boxes (64 columns) of the Xlb / Xhb parts
     static constexpr int OFF_LB = NBOX * BOX_BYTES;                // slot: Xh | Xlb | Xhb
     static constexpr int OFF_HB = OFF_LB + NB16 * BOX_BYTES;
     static constexpr int A_BYTES = OFF_HB + NB16 * BOX_BYTES;      // 64 KB (dp32 = 128) / 32 KB (64): 8 bytes per element
@@ -131,9 +132,9 @@ __device__ __forceinline__ void umma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a,
         "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, pa;\n"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
 }
-// the same issue form for kind::f16 (bf16 operands, K = 16 per instruction): A is 16 packed pairs per lane = 8 TMEM columns
+// the same issue form for kind::f16 (16-bit operands, K = 16 per instruction): A is 16 packed pairs per lane = 8 TMEM columns
 template <bool ACC>
-__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc) {
+__device__ __forceinline__ void umma_f16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc) {
     asm volatile(
         "{\n"
         ".reg .pred pe, pa;\n"
@@ -179,7 +180,7 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
 // shared-memory matrix descriptor, MN-major, 16-bit elements, plain 128-byte swizzle (layout type 2): 64 elements of the
 // MN index are contiguous (one 128-byte row), MN blocks of 64 are `lbo` bytes apart; the K index walks the 128-byte rows,
 // groups of 8 rows (one swizzle pattern) are `sbo` bytes apart.  This is the box TMA writes for a [rows = K][64 columns =
-// MN] bf16 tile with CU_TENSOR_MAP_SWIZZLE_128B -- the very tile that is a K-major operand when rows are taken as MN.
+// MN] 16-bit tile with CU_TENSOR_MAP_SWIZZLE_128B -- the very tile that is a K-major operand when rows are taken as MN.
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_b16(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -193,11 +194,19 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_b16(uint32_t saddr, uint32
 __device__ __forceinline__ float rn_tf32(float x) {          // round to nearest TF32 (10 explicit mantissa bits)
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-// two bf16 values in one 32-bit word, `even` in the low half: consecutive along the contraction of a kind::f16 MMA,
+// two fp16 values in one 32-bit word, `even` in the low half: consecutive along the contraction of a kind::f16 MMA,
 // both in a shared-memory row (little endian) and in a tensor-memory column of an A operand
-__device__ __forceinline__ uint32_t pack_bf16(float even, float odd) {
-    const __nv_bfloat162 b2 = __floats2bfloat162_rn(even, odd);          // .x (low half) = even
-    return *reinterpret_cast<const uint32_t*>(&b2);
+__device__ __forceinline__ uint32_t pack_f16(float even, float odd) {
+    const __half2 h2 = __floats2half2_rn(even, odd);                     // .x (low half) = even
+    return *reinterpret_cast<const uint32_t*>(&h2);
+}
+// The 16-bit operands are fp16 with power-of-two scales that cancel in every product: the remainders x - Xh, theta - Th
+// (<= 2^-12 of the value) are stored times 2^10, the values they multiply times 2^-10.  Both factors then sit in fp16's
+// normal range for |x|, |theta| between ~0.06 and ~6e4 (smaller ones lose relative, not absolute, accuracy), and the
+// correction terms keep 11 bits: their error is 2^-24 of a product, what TF32 remainders gave (bf16 operands: 2^-21).
+constexpr float CS_UP = 1024.0f, CS_DN = 1.0f / 1024.0f;
+constexpr uint32_t umma_idesc_f16(int M, int N) {                        // kind::f16, fp16 A and B, fp32 accumulate
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -287,7 +296,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         // warp too put 300 more cycles per tile on the critical chain.  Different accumulators (Z / G), so the order
         // in which the tensor pipe takes the two streams does not change a bit; the one hazard -- GEMM1 of tile t + 2
         // overwrites the Z buffer GEMM2 of tile t reads R from -- is covered by z_free.
-        const uint32_t idesc2 = umma_idesc_bf16(CB, DP32) | (1u << 16);          // B is MN-major
+        const uint32_t idesc2 = umma_idesc_f16(CB, DP32) | (1u << 16);           // B is MN-major
         constexpr uint32_t t_g = C::COL_G;
         const uint64_t dm0 = umma_desc_mnmajor_b16(0, BOX_BYTES, 1024);
         const uint32_t dm_hi = (uint32_t)(dm0 >> 32), dm_lo0 = (uint32_t)dm0;
@@ -303,11 +312,11 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             // the warpgroup's 16 logit columns; one K = 16 MMA per warpgroup, 16 rows = 2,048 bytes of the Xhb boxes
             const uint32_t tr = C::COL_Z + (uint32_t)((t & 1) * NT);
             const uint32_t lo_b = dm_lo0 + (((smem0 + (uint32_t)(s * C::A_BYTES + C::OFF_HB)) & 0x3FFFF) >> 4);
-            if (t == 0) umma_bf16_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
-            else umma_bf16_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
+            if (t == 0) umma_f16_ts_w<false>(t_g, tr, lo_b, dm_hi, idesc2);
+            else umma_f16_ts_w<true>(t_g, tr, lo_b, dm_hi, idesc2);
 #pragma unroll
             for (int ks = 1; ks < NT / 16; ++ks)
-                umma_bf16_ts_w<true>(t_g, tr + ks * PCOLS, lo_b + ks * (2048 >> 4), dm_hi, idesc2);
+                umma_f16_ts_w<true>(t_g, tr + ks * PCOLS, lo_b + ks * (2048 >> 4), dm_hi, idesc2);
             umma_commit_elect(&emptyA[s]);           // the slot is free once GEMM2 has read it
             umma_commit_elect(&z_free[t & 1]);
             stamp(t, 3);
@@ -337,8 +346,8 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                         l[i] = (float)(v - (double)h[i]);
                         hi[e + i] = __float_as_uint(h[i]);
                     }
-                    hb[e >> 1] = pack_bf16(x[0], x[1]);
-                    lb[e >> 1] = pack_bf16(l[0], l[1]);
+                    hb[e >> 1] = pack_f16(x[0] * CS_DN, x[1] * CS_DN);
+                    lb[e >> 1] = pack_f16(l[0] * CS_UP, l[1] * CS_UP);
                 }
                 tmem_st_32x32(lane_base + C::COL_TH + j0, hi);
                 tmem_st_32x16(lane_base + C::COL_TB + (j0 >> 1), hb);
@@ -397,8 +406,8 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 const float2 ei = __ffma2_rn(ex, inv, f2(0.0f));
                 const float g0 = (s0 >= 0.0f) ? inv.x : ei.x;                   // sigmoid(s);  y - p = (2y - 1) sigmoid(s)
                 const float g1 = (s1 >= 0.0f) ? inv.y : ei.y;
-                rr[e >> 1] = pack_bf16(__uint_as_float(__float_as_uint(g0) | (~ym.x & 0x80000000u)),       // nearest bf16
-                                       __uint_as_float(__float_as_uint(g1) | (~ym.y & 0x80000000u)));
+                rr[e >> 1] = pack_f16(__uint_as_float(__float_as_uint(g0) | (~ym.x & 0x80000000u)),        // nearest fp16
+                                      __uint_as_float(__float_as_uint(g1) | (~ym.y & 0x80000000u)));
                 if (HASW) { const float2 w2 = __ffma2_rn(ei, inv, f2(0.0f)); wv[e] = w2.x; wv[e + 1] = w2.y; }
                 if ((e & 6) == 6) { ll += (double)(part.x + part.y); part = f2(0.0f); }
             }
@@ -449,10 +458,10 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 for (int j0 = 0; j0 < DP32; j0 += 32) {
                     float v[32];
                     tmem_ld_32x32(lane_base + C::COL_G + j0, v);
-                    if (okc) {
+                    if (okc) {                                        // GEMM2 contracted R with x 2^-10
 #pragma unroll
                         for (int e = 0; e < 32; e += 4)
-                            *reinterpret_cast<float4*>(gout + j0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                            *reinterpret_cast<float4*>(gout + j0 + e) = make_float4(v[e] * CS_UP, v[e + 1] * CS_UP, v[e + 2] * CS_UP, v[e + 3] * CS_UP);
                     }
                 }
             } else if (okc) {
@@ -472,7 +481,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         // ===== GEMM1 issuer (warp 1): the kernel's convergent tail, issuing lane elected once (see the role dispatch) =====
         // Every operand is thread-invariant (the CTA owns all 512 TMEM columns, so its TMEM base is 0 and the addresses are
         // literals; descriptors differ by an add on their low word) and lives in uniform registers.
-        const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_bf16(CB, NT);
+        const uint32_t idesc1 = umma_idesc_tf32(CB, NT), idesc1b = umma_idesc_f16(CB, NT);
         constexpr uint32_t t_th = C::COL_TH, t_tb = C::COL_TB, t_lb = C::COL_LB;
         const int d8 = (a.d + 7) / 8, d16 = (a.d + 15) / 16;                    // K steps of GEMM1 that hold data
         const uint64_t dk0 = umma_desc_kmajor<128>(0);                           // descriptor with a zero start address
@@ -499,7 +508,7 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             umma_ts_l<false, false>(leader, tz, t_th, lo_h, dk_hi, idesc1);
             for (int k = 1; k < d8; ++k)
                 umma_ts_l<true, false>(leader, tz, t_th + (uint32_t)(k * 8), lo_h + (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2), dk_hi, idesc1);
-            // Theta_hb Xlb^T + Theta_lb Xhb^T: bf16, K = 16 = 32 bytes of a row (8 packed TMEM columns) per MMA
+            // Theta_hb Xlb^T + Theta_lb Xhb^T: fp16, K = 16 = 32 bytes of a row (8 packed TMEM columns) per MMA
             for (int k = 0; k < d16; ++k) {
                 const uint32_t off = (uint32_t)((k >> 2) * (BOX_BYTES >> 4) + (k & 3) * 2);
                 umma_ts_l<true, true>(leader, tz, t_tb + (uint32_t)(k * 8), lo_lb + off, dk_hi, idesc1b);
@@ -513,11 +522,11 @@ lg_fused_sweep_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     cta_sync_all();
 }
 
-// X[N][d] (fp64) -> Xh [N][ldx] fp32 (x rounded to nearest TF32), Xlb = bf16(x - Xh), Xhb = bf16(x) [N][ldx] (row pitch
+// X[N][d] (fp64) -> Xh [N][ldx] fp32 (x rounded to nearest TF32), Xlb = fp16((x - Xh) 2^10), Xhb = fp16(x 2^-10) [N][ldx] (row pitch
 // ldx = d rounded up to 8), and the label sign masks
 __global__ void __launch_bounds__(256)
 lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, const double* __restrict__ X, const double* __restrict__ y,
-                float* __restrict__ Xh, __nv_bfloat16* __restrict__ Xlb, __nv_bfloat16* __restrict__ Xhb,
+                float* __restrict__ Xh, __half* __restrict__ Xlb, __half* __restrict__ Xhb,
                 uint32_t* __restrict__ ys) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx < N * ldx) {
@@ -526,8 +535,8 @@ lgf_prep_kernel(int64_t N, int d, int ldx, int64_t nys, const double* __restrict
         const double x = (k < d) ? X[i * d + k] : 0.0;
         const float hi = rn_tf32((float)x);
         Xh[idx] = hi;
-        Xlb[idx] = __float2bfloat16_rn((float)(x - (double)hi));
-        Xhb[idx] = __float2bfloat16_rn((float)x);
+        Xlb[idx] = __float2half_rn((float)(x - (double)hi) * CS_UP);
+        Xhb[idx] = __float2half_rn((float)x * CS_DN);
     }
     if (idx < nys) ys[idx] = (idx < N && y[idx] != 0.0) ? 0x80000000u : 0u;
 }
@@ -584,8 +593,8 @@ void make_geometry(Geometry* g, int64_t N, int d, int64_t K) {
 int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y, float* Xh, float* Xl, uint32_t* ys,
            cudaStream_t st) {
     const int64_t n = std::max<int64_t>(N * g.ldx, g.nys);
-    // the second buffer (N ldx fp32 words) holds the two bf16 copies one after the other
-    __nv_bfloat16* Xlb = reinterpret_cast<__nv_bfloat16*>(Xl);
+    // the second buffer (N ldx fp32 words) holds the two fp16 copies one after the other
+    __half* Xlb = reinterpret_cast<__half*>(Xl);
     lgf_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, d, g.ldx, g.nys, X, y, Xh, Xlb, Xlb + N * g.ldx, ys);
     RMN_KERNEL_CHECK();
     return RMN_OK;
@@ -593,7 +602,7 @@ int prep_x(int64_t N, int d, const Geometry& g, const double* X, const double* y
 
 int make_maps(Maps* m, const Geometry& g, int64_t N, const float* Xh, const float* Xl) {
     // the maps are ldx columns wide: the boxes of the last column block reach past it and are zero-filled there
-    const __nv_bfloat16* Xlb = reinterpret_cast<const __nv_bfloat16*>(Xl);
+    const __half* Xlb = reinterpret_cast<const __half*>(Xl);      // 2-byte elements: the bf16 map type only names the size
     if (int rc = make_tmap_2d(&m->xh, Xh, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
     if (int rc = make_tmap_2d_bf16(&m->xlb, Xlb, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT)) return rc;
     return make_tmap_2d_bf16(&m->xhb, Xlb + N * g.ldx, (uint64_t)N, (uint64_t)g.ldx, (uint64_t)g.ldx, NT);

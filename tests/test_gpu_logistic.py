@@ -433,7 +433,7 @@ def test_tf32x3_logistic_chain_targets_the_same_posterior():
 
 def test_tf32x3_logistic_config4_budget():
     """BASELINE config 4 shape (N = 1e6, d = 100), the stated budget (riemann_b200/budgets.py): one state's offset
-    < 5e-8 N, the log-posterior DIFFERENCE proposal - state within 2e-3 of fp64, accept decisions identical to an fp64
+    < 5e-8 N, the log-posterior DIFFERENCE proposal - state within 1e-3 of fp64 (SURVEY 8d's gate), accept decisions identical to an fp64
     re-evaluation outside that band; K = 2,100 chains (17 chain blocks of the fused kernel, the last one ragged)."""
     from oracle import riemann_port as port
     from riemann_b200 import Sampler, budgets
@@ -444,7 +444,7 @@ def test_tf32x3_logistic_config4_budget():
     rng = np.random.default_rng(8)
     th0 = ts[None] + 0.01 * rng.standard_normal((K, d))
     off, dif = budgets.logistic_tf32x3_offset(N), budgets.logistic_tf32x3_difference(N)
-    assert dif == 2e-3
+    assert dif == 1e-3
     s = Sampler(dm, MALA(0.02, dm.grad_log_posterior), th0, precision="tf32x3", seed=1)
     lp = np.asarray(s._chain_logpost[0])
     sel = np.r_[0:160, K - 40:K]
