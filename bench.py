@@ -192,17 +192,20 @@ def _cpu_worker(args):
     if workload == "changepoint":
         c = synthetic.changepoint_problem()
         xq = c["xmin"] + (c["xmax"] - c["xmin"]) * (np.arange(6) + 0.5) / 6.0
-    n, spent, funcs = 0, 0.0, []
     import contextlib
+    segments = []                                          # the chain CONTINUES from one segment into the next
     with np.errstate(all="ignore"), (quiet() if quiet else contextlib.nullcontext()):
-        while spent < budget_s:
-            t0 = time.perf_counter()
-            s.run(chunk)                                   # Sampler.run (sampler.py:44-54): chunk x Sampler.sample
-            spent += time.perf_counter() - t0
-            n += chunk
-            new = s._chain_thetas[1:]                      # run() keeps [last state] + the chunk
-            funcs.append(_cp_functionals(new, xq) if xq is not None else _vec_functionals(new))
-    return n, spent, np.concatenate(funcs, axis=0)
+        for seg_s in (budget_s if isinstance(budget_s, (list, tuple)) else [budget_s]):
+            n, spent, funcs = 0, 0.0, []
+            while spent < seg_s:
+                t0 = time.perf_counter()
+                s.run(chunk)                               # Sampler.run (sampler.py:44-54): chunk x Sampler.sample
+                spent += time.perf_counter() - t0
+                n += chunk
+                new = s._chain_thetas[1:]                  # run() keeps [last state] + the chunk
+                funcs.append(_cp_functionals(new, xq) if xq is not None else _vec_functionals(new))
+            segments.append((n, spent, np.concatenate(funcs, axis=0)))
+    return segments if isinstance(budget_s, (list, tuple)) else segments[0]
 
 
 def chain_ess(funcs_list, wall, names):
@@ -225,6 +228,10 @@ def chain_ess(funcs_list, wall, names):
            "moment_tau_steps": [float(t) for t in tau_m], "steps_per_chain": int(n), "chains": int(chains),
            "window_over_tau": n / tmax, "reliable": bool(n >= 50 * tmax),
            "min_ess": chains * n / tmax, "min_ess_per_sec": chains * n / tmax / wall}
+    if chains > 1 and np.all(np.isfinite(tau_m)):
+        # the GPU arm's `ess` estimator (tau = n B / W over the chains) on these few chains: B has chains - 1 degrees
+        # of freedom, so this is a noisy figure (relative error ~ sqrt(2 / (chains - 1)))
+        out["moment_min_ess_per_sec"] = chains * n / max(float(np.max(tau_m)), 1.0) / wall
     if not out["reliable"]:
         out["reason"] = "chain length is %.1f tau of the slowest functional (< 50 tau: emcee would refuse)" % (n / tmax)
     return out
@@ -251,13 +258,48 @@ def cpu_baseline(workload, budget_s=12.0, cores=None, with_ess=True):
            "sample": "%d independent chains (one per host core) of %s on the same synthetic %s problem, %.1f s each, "
                      "%d chain-steps total" % (cores, what, workload, budget_s, steps)}
     if with_ess:
-        names = FUNC_NAMES.get(workload, ["theta%d" % j for j in range(7)] + ["mean(theta)"])
-        e = chain_ess([r[2] for r in res], wall, names[:res[0][2].shape[1]])
-        out["ess"] = e
-        out["min_ess_per_sec"] = e.get("min_ess_per_sec") if e.get("reliable") else None
-        if out["min_ess_per_sec"] is None:
-            out["min_ess_per_sec_unreliable"] = e.get("min_ess_per_sec")
+        _attach_ess(out, workload, [r[2] for r in res], wall)
     return out
+
+
+def _attach_ess(out, workload, funcs_list, wall):
+    names = FUNC_NAMES.get(workload, ["theta%d" % j for j in range(7)] + ["mean(theta)"])
+    e = chain_ess(funcs_list, wall, names[:funcs_list[0].shape[1]])
+    out["ess"] = e
+    out["min_ess_per_sec"] = e.get("min_ess_per_sec") if e.get("reliable") else None
+    if out["min_ess_per_sec"] is None:
+        out["min_ess_per_sec_unreliable"] = e.get("min_ess_per_sec")
+
+
+def cpu_reference_segments(workload, warm, timed, per_s, cores=None):
+    """The reference arm's timed region: every host core runs ONE chain through `warm` untimed and `timed` timed
+    segments of `per_s` seconds, the chain continuing from segment to segment (the warm-up segments are its burn-in).
+    Returns (per-segment chain-steps/s, cpu_baseline dict): throughput per segment = chain-steps of all chains / the
+    slowest chain's time in it; tau / ESS from the concatenated timed segments of every chain."""
+    import multiprocessing as mp
+    cores = cores or len(os.sched_getaffinity(0))
+    if workload.startswith("logistic"):
+        cores = min(cores, 16)
+    kind = cpu_kind(workload)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(workload, 1000 + i, [per_s] * (warm + timed), kind) for i in range(cores)])
+    vals, walls, steps = [], [], 0
+    for g in range(warm, warm + timed):
+        n = sum(r[g][0] for r in res)
+        w = max(r[g][1] for r in res)
+        vals.append(n / w)
+        walls.append(w)
+        steps += n
+    wall = float(sum(walls))
+    what = ("the UNMODIFIED reference (riemann/samplers/sampler.py:44-90 via oracle/refshim.py)" if kind == "reference"
+            else "the numpy restatement of riemann's Sampler.sample (oracle/riemann_port.py; the reference has no such model)")
+    out = {"value": steps / wall, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "%d independent chains (one per host core) of %s on the same synthetic %s problem: %d timed "
+                     "segments of %.1f s after %d untimed ones, each chain continuing across segments; %d chain-steps "
+                     "in the timed segments" % (cores, what, workload, timed, per_s, warm, steps)}
+    _attach_ess(out, workload, [np.concatenate([r[g][2] for g in range(warm, warm + timed)], axis=0) for r in res], wall)
+    return vals, out
 
 
 # ----------------------------------------------------------------------------
@@ -924,13 +966,13 @@ def run_reference(args):
         return
     wl = args.workload or "changepoint"
     W, K = max(args.warmup, 1), max(args.steps, 1)
-    per = max(2.0, min(20.0, 60.0 / (W + K)))
-    cpu_baseline(wl, 1.0, with_ess=False)               # warm the pool / imports
-    vals = [cpu_baseline(wl, per) for _ in range(K)]
-    v = float(np.mean([c["value"] for c in vals]))
-    cb = dict(vals[-1], value=v)
-    # ESS over the concatenated steps would need the chains to continue; each step restarts its chains, so the ESS
-    # figure is the best (longest-window) single step's
+    # a step = `per` seconds of every core's chain; the chains continue from step to step, so the tau / ESS window is
+    # the whole timed region (args.cpu_seconds_reference of sampling per chain; the warm-up steps are the burn-in)
+    per = max(1.0, min(30.0, args.cpu_seconds_reference / K))
+    Wn = max(1, min(W, int(round(0.15 * args.cpu_seconds_reference / per))))
+    vals, cb = cpu_reference_segments(wl, Wn, K, per)
+    v = cb["value"]
+    cb["per_step_values"] = [float(x) for x in vals]
     Kg = args.chains or CHAINS_PER_GPU[wl]
     entries = []
     if args.workload is None and not args.no_configs:
@@ -939,9 +981,10 @@ def run_reference(args):
             entries.append({"key": w, "workload": w, "value": c["value"], "unit": UNIT, "dtype": "f64",
                             "min_ess_per_sec": c.get("min_ess_per_sec"), "cpu_baseline": c})
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": K, "warmup": W, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "steps": K, "warmup": Wn, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s (CPU reference arm: one chain per host core, %.1f s per step)" % (wl, per),
+            "config": {"workload": "%s (CPU reference arm: one chain per host core, %.1f s per step, chains continue "
+                                   "across steps)" % (wl, per),
                        "chains_per_gpu": Kg},
             "min_ess_per_sec": cb.get("min_ess_per_sec"),
             "cpu_baseline": cb,
@@ -964,6 +1007,8 @@ def main():
     ap.add_argument("--burn", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-seconds-config", type=float, default=3.0)
+    ap.add_argument("--cpu-seconds-reference", type=float, default=110.0,
+                    help="--impl reference: seconds of sampling per chain in the timed region (split over --steps)")
     ap.add_argument("--ess-half-launches", type=int, default=400,
                     help="changepoint ESS phase: launches (of --iters MH steps) per half-window")
     ap.add_argument("--no-cpu", action="store_true")
