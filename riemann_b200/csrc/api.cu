@@ -4,8 +4,15 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>      // header-only; a no-op unless a profiler injects itself (NVTX_INJECTION64_PATH)
 
 static thread_local char g_err[1024] = "";
+
+// NVTX range around the calls of the per-iteration path, so a timeline shows set_state / run / get_state per job
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 void rmn_set_error(const char* fmt, ...) {
     va_list ap;
@@ -410,25 +417,30 @@ extern "C" int rmn_sampler_destroy(rmn_sampler_t* s) {
 #define RMN_S(s) RMN_REQUIRE((s) && (s)->impl, "null sampler handle")
 
 extern "C" int rmn_sampler_set_state(rmn_sampler_t* s, const double* d_theta, void* stream) {
+    NvtxRange nvtx_("rmn_sampler_set_state");
     RMN_S(s); RMN_REQUIRE(d_theta, "rmn_sampler_set_state: null theta");
     return s->impl->set_state(d_theta, (cudaStream_t)stream);
 }
 extern "C" int rmn_sampler_get_state(rmn_sampler_t* s, double* d_theta, double* d_logpost, void* stream) {
+    NvtxRange nvtx_("rmn_sampler_get_state");
     RMN_S(s);
     return s->impl->get_state(d_theta, d_logpost, (cudaStream_t)stream);
 }
 extern "C" int rmn_sampler_cp_set_state(rmn_sampler_t* s, const int32_t* d_k, const double* d_cpx,
                                         const double* d_cpv, const double* d_sig, void* stream) {
+    NvtxRange nvtx_("rmn_sampler_cp_set_state");
     RMN_S(s); RMN_REQUIRE(d_k && d_cpx && d_cpv && d_sig, "rmn_sampler_cp_set_state: null argument");
     return s->impl->cp_set_state(d_k, d_cpx, d_cpv, d_sig, (cudaStream_t)stream);
 }
 extern "C" int rmn_sampler_cp_get_state(rmn_sampler_t* s, int32_t* d_k, double* d_cpx, double* d_cpv,
                                         double* d_sig, double* d_logpost, void* stream) {
+    NvtxRange nvtx_("rmn_sampler_cp_get_state");
     RMN_S(s);
     return s->impl->cp_get_state(d_k, d_cpx, d_cpv, d_sig, d_logpost, (cudaStream_t)stream);
 }
 extern "C" int rmn_sampler_run(rmn_sampler_t* s, int64_t T, const rmn_inject_t* inj,
                                const rmn_trace_t* trace, void* stream) {
+    NvtxRange nvtx_("rmn_sampler_run");
     RMN_S(s); RMN_REQUIRE(T >= 0, "rmn_sampler_run: T must be >= 0");
     if (trace) RMN_REQUIRE(trace->thin >= 1 && trace->first >= 0, "rmn_sampler_run: need thin >= 1, first >= 0");
     if (T == 0) return RMN_OK;
@@ -456,6 +468,7 @@ extern "C" int rmn_sampler_reset_diagnostics(rmn_sampler_t* s, void* stream) {
     return s->impl->reset_diag((cudaStream_t)stream);
 }
 extern "C" int rmn_sampler_reduce_diagnostics(rmn_sampler_t* s, double* d_block, void* stream) {
+    NvtxRange nvtx_("rmn_sampler_reduce_diagnostics");
     RMN_S(s); RMN_REQUIRE(d_block, "rmn_sampler_reduce_diagnostics: null block");
     return s->impl->reduce_diag(d_block, (cudaStream_t)stream);
 }
