@@ -297,7 +297,9 @@ __device__ __forceinline__ double cp_logpost_rows(const CPParams& P, const doubl
 //   cpx move    :48-50                      searches, residual sums, gap product; height-prior sum cached
 //   birth/death :57-71                      the general path
 // ---------------------------------------------------------------------------------------
-template <bool INJ, int DATA, int GL>
+// GUARD = false: the instantiation for per-chain move schedules in Philox mode -- the warp executes the union of the
+// moves every step, so the votes and the guards that a uniform warp would use are compiled out (same arithmetic, same bits).
+template <bool INJ, int DATA, int GL, bool GUARD>
 __device__ __forceinline__ void cp_block(const CPParams& P, const double* __restrict__ xs, CPState st,
                                          int64_t K, int64_t t_begin, int64_t t_end, int64_t step0, uint64_t seed,
                                          int64_t chain_offset, const double* __restrict__ tape, const rmn_trace_t& tr,
@@ -406,7 +408,7 @@ __device__ __forceinline__ void cp_block(const CPParams& P, const double* __rest
         // the guards are almost always taken and the warp executes the union, selecting per chain.
         const bool any0 = __any_sync(FULL, mv == 0), any1 = __any_sync(FULL, mv == 1);
         const bool any3 = __any_sync(FULL, mv == 3);
-        const bool skip = RMN_CP_FASTPATHS && (INJ || shared_mv);      // per-chain Philox mode keeps ONE instruction stream
+        const bool skip = RMN_CP_FASTPATHS && GUARD && (INJ || shared_mv);   // per-chain Philox mode keeps ONE instruction stream
         const bool need_xi = !skip || __any_sync(FULL, mv != 3);
 
         // normals of the block moves: rows 0,1 from this step's block, rows 2,3 (only when some chain of the
@@ -605,7 +607,7 @@ __device__ __forceinline__ void cp_block(const CPParams& P, const double* __rest
 
 // DATA: 0 = data tables read from global memory (too large for shared memory), 1 = staged in shared
 // memory, 2 = staged and 64 <= M < 128 (P2 = 64: fully unrolled 7-level search; the bench shape)
-template <bool INJ, int DATA, int GL>
+template <bool INJ, int DATA, int GL, bool GUARD = true>
 __global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
 changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
                    int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset,
@@ -618,7 +620,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
         __syncthreads();
         xs = smem;
     }
-    cp_block<INJ, DATA, GL>(P, xs, st, K, 0, T, step0, seed, chain_offset, tape, tr, shared_mv, blockIdx.x);
+    cp_block<INJ, DATA, GL, GUARD>(P, xs, st, K, 0, T, step0, seed, chain_offset, tape, tr, shared_mv, blockIdx.x);
 }
 
 // Time-sliced form of the same run (plain Philox runs without traces).  A launch of B blocks that do not fit the SMs'
@@ -628,7 +630,7 @@ changepoint_kernel(const __grid_constant__ CPParams P, const double* __restrict_
 // item, the state of a slice's chains travels through global memory, and a flag per chain block orders the slices of the
 // same chains (the predecessor is B >> S items earlier, so the wait is almost never taken).  Philox is keyed by
 // (step, chain), so the chains are bit-identical to the one-slice launch.
-template <int DATA, int GL>
+template <int DATA, int GL, bool GUARD = true>
 __global__ void __launch_bounds__(128, (GL == 16) ? 8 : RMN_CP_MINBLOCKS)
 changepoint_sliced_kernel(const __grid_constant__ CPParams P, const double* __restrict__ gdata, CPState st,
                           int64_t K, int64_t T, int64_t step0, uint64_t seed, int64_t chain_offset, int shared_mv,
@@ -662,7 +664,7 @@ changepoint_sliced_kernel(const __grid_constant__ CPParams P, const double* __re
         if (it >= items) break;
         const int j = it / nblk, b = it % nblk;
         const int64_t t0 = (int64_t)j * slice, t1 = (t0 + slice < T) ? t0 + slice : T;
-        cp_block<false, DATA, GL>(P, xs, st, K, t0, t1, step0, seed, chain_offset, nullptr, tr, shared_mv, b);
+        cp_block<false, DATA, GL, GUARD>(P, xs, st, K, t0, t1, step0, seed, chain_offset, nullptr, tr, shared_mv, b);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(done + b) = j + 1;
@@ -763,6 +765,7 @@ struct ChangepointSampler : SamplerImpl {
         }
         if (const char* e = getenv("RMN_CP_SCHEDULE")) shared_mv = (e[0] == 'c' || e[0] == '0') ? 0 : 1;
         if (const char* e = getenv("RMN_CP_SLICED")) sliced = (e[0] == '0') ? 0 : 1;
+        if (const char* e = getenv("RMN_CP_GUARD")) force_guard = (e[0] == '1') ? 1 : 0;
         smem_bytes = (size_t)(P.XP + 2 * P.M + 2) * 8;
         use_smem = smem_bytes <= 96 * 1024;
     }
@@ -796,6 +799,10 @@ struct ChangepointSampler : SamplerImpl {
         if (e != cudaSuccess) return e;
         e = rmn_raise_dyn_smem((const void*)changepoint_kernel<true, 1, GL>, smem_bytes);
         if (e != cudaSuccess || GL != 4) return e;
+        e = rmn_raise_dyn_smem((const void*)changepoint_kernel<false, 1, 4, false>, smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = rmn_raise_dyn_smem((const void*)changepoint_sliced_kernel<1, 4, false>, smem_bytes);
+        if (e != cudaSuccess) return e;
         return rmn_raise_dyn_smem((const void*)changepoint_sliced_kernel<1, 4>, smem_bytes);
     }
     unsigned grid(int gl = LANES) const { return (unsigned)((s->K * gl + 127) / 128); }
@@ -844,9 +851,10 @@ struct ChangepointSampler : SamplerImpl {
     int* d_done = nullptr;
     int done_cap = 0;
     int sliced = 1;                 // RMN_CP_SLICED=0 switches it off (A/B)
+    int force_guard = 0;            // RMN_CP_GUARD=1: per-chain schedules through the guarded instantiation (A/B)
     ~ChangepointSampler() override { if (d_done) cudaFree(d_done); }
     bool last_sliced = false;       // which kernel the last plain launch used (the timer label is corrected after the launch)
-    template <int DATA, int GL>
+    template <int DATA, int GL, bool GUARD>
     bool launch_sliced(int64_t T, unsigned nblk, int sh, size_t smem, cudaStream_t stream) {
         constexpr int SLICE_MIN = 100;          // iterations: the state round trip and the entry evaluation cost about one
         last_sliced = false;
@@ -854,7 +862,7 @@ struct ChangepointSampler : SamplerImpl {
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, changepoint_sliced_kernel<DATA, GL>, 128, smem) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, changepoint_sliced_kernel<DATA, GL, GUARD>, 128, smem) != cudaSuccess || per_sm < 1)
             return false;
         const unsigned slots = (unsigned)(per_sm * sms);
         if (nblk <= slots || nblk % slots == 0) return false;       // one wave, or whole waves: nothing to gain
@@ -877,30 +885,39 @@ struct ChangepointSampler : SamplerImpl {
             done_cap = (int)nblk;
         }
         if (cudaMemsetAsync(d_done, 0, ((size_t)nblk + 1) * sizeof(int), stream) != cudaSuccess) return false;
-        changepoint_sliced_kernel<DATA, GL><<<slots, 128, smem, stream>>>(
+        changepoint_sliced_kernel<DATA, GL, GUARD><<<slots, 128, smem, stream>>>(
             P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, sh, (int)nblk, slice, nslice, d_done);
         last_sliced = true;
         return true;
     }
     template <bool INJ, int GL>
     void launch_gl(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
+        if constexpr (!INJ && GL == 4) {
+            // per-chain move schedules: the instantiation without the warp-uniform guards (RMN_CP_GUARD=1 keeps them: A/B
+            // and the bit-identity test)
+            if (!shared_mv && !force_guard) { launch_gl_g<INJ, GL, false>(T, tape, t0, stream); return; }
+        }
+        launch_gl_g<INJ, GL, true>(T, tape, t0, stream);
+    }
+    template <bool INJ, int GL, bool GUARD>
+    void launch_gl_g(int64_t T, const double* tape, const rmn_trace_t& t0, cudaStream_t stream) {
         const int sh = INJ ? 0 : shared_mv;
         const unsigned g = run_grid(GL, sh);
         last_sliced = false;
         const bool traced = t0.d_k || t0.d_cpx || t0.d_cpv || t0.d_sig || t0.d_logpost || t0.d_prop_logpost || t0.d_accepted ||
                             t0.d_logqratio || t0.d_prop_k || t0.d_prop_sig || t0.d_prop_cpx || t0.d_prop_cpv;
         if constexpr (!INJ && GL == 4) {
-            if (!traced && use_smem && P.P2 == 64) { if (launch_sliced<2, GL>(T, g, sh, smem_bytes, stream)) return; }
-            else if (!traced && use_smem) { if (launch_sliced<1, GL>(T, g, sh, smem_bytes, stream)) return; }
+            if (!traced && use_smem && P.P2 == 64) { if (launch_sliced<2, GL, GUARD>(T, g, sh, smem_bytes, stream)) return; }
+            else if (!traced && use_smem) { if (launch_sliced<1, GL, GUARD>(T, g, sh, smem_bytes, stream)) return; }
         }
         if (use_smem && P.P2 == 64)
-            changepoint_kernel<INJ, 2, GL><<<g, 128, smem_bytes, stream>>>(
+            changepoint_kernel<INJ, 2, GL, GUARD><<<g, 128, smem_bytes, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);
         else if (use_smem)
-            changepoint_kernel<INJ, 1, GL><<<g, 128, smem_bytes, stream>>>(
+            changepoint_kernel<INJ, 1, GL, GUARD><<<g, 128, smem_bytes, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);
         else
-            changepoint_kernel<INJ, 0, GL><<<g, 128, 0, stream>>>(
+            changepoint_kernel<INJ, 0, GL, GUARD><<<g, 128, 0, stream>>>(
                 P, s->model->d_cpdata, st, s->K, T, step0, s->seed, s->chain_offset, tape, t0, sh);
     }
     int run(int64_t T, const rmn_inject_t* inj, const rmn_trace_t* tr, cudaStream_t stream) override {

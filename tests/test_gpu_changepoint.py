@@ -272,6 +272,29 @@ def test_time_sliced_launch_is_bit_identical(schedule, off, monkeypatch):
     assert np.allclose(a_m[0], b_m[0], rtol=1e-12, atol=0) and np.allclose(a_m[1], b_m[1], rtol=1e-9, atol=1e-18)
 
 
+def test_per_chain_schedule_without_guards_is_bit_identical(monkeypatch):
+    """Per-chain move schedules run through an instantiation of the kernel with the warp-uniform guards compiled out
+    (the warp executes the union of the moves anyway).  RMN_CP_GUARD=1 sends the same run through the guarded
+    instantiation: states, log-posteriors and accept counts must agree bit for bit, one-slice and time-sliced."""
+    from riemann_b200 import Sampler
+    from riemann_b200.models.changepoint import ChangepointParams
+    dm, dp, _, _ = _setup()
+    th0 = ChangepointParams([2.0], [1.0, 3.0], 0.1)
+    for K, T in ((203, 600), (23000, 240)):
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("RMN_CP_GUARD", mode)
+            s = Sampler(dm, dp, th0, K=K, seed=9, chain_offset=3, move_schedule="chain")
+            s.run(T, trace=False)
+            out[mode] = (s._download_state(), s.diagnostics(allreduce=False))
+        (a_st, a_lp), a_d = out["0"]
+        (b_st, b_lp), b_d = out["1"]
+        for x, y in zip(a_st, b_st):
+            assert np.array_equal(x, y)
+        assert np.array_equal(a_lp, b_lp)
+        assert a_d["accept_rate"] == b_d["accept_rate"] and a_d["overflows"] == b_d["overflows"]
+
+
 @pytest.mark.parametrize("schedule", ["group", "chain"])
 def test_move_schedules_are_shard_invariant(schedule):
     """Philox mode: chains [off, off + n) of a sharded run equal the same chains of the unsharded run bit for bit, for
