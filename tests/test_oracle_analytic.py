@@ -42,6 +42,29 @@ def test_logistic_gradient_finite_difference():
         assert abs(fd - g[j]) < 1e-5 * max(1.0, abs(g[j]))
 
 
+def test_logistic_against_scikit_learn():
+    """An independent third-party statement of the same model (the reference has none): scikit-learn's log_loss is
+    -log-likelihood, and its L2-penalised LogisticRegression without intercept minimises 0.5 w.w + C sum(log-loss),
+    i.e. its optimum is the posterior mode for prior_var = C -- where the oracle's gradient must vanish and its
+    log-posterior must not be improved by the oracle's own Newton step."""
+    import sklearn.linear_model
+    import sklearn.metrics
+    from scipy.special import expit
+    X, y, ts, _ = port.make_logistic_problem(400, 6, seed=7)
+    pv = 3.0
+    m = port.LogisticRegression(X, y, pv)
+    for th in (0.3 * ts, -1.2 * ts, np.zeros_like(ts)):
+        ll = -sklearn.metrics.log_loss(y, expit(X @ th), normalize=False, labels=[0, 1])
+        assert abs(m.log_likelihood(th) - ll) < 1e-9 * max(1.0, abs(ll))
+    fit = sklearn.linear_model.LogisticRegression(C=pv, fit_intercept=False, tol=1e-12, max_iter=2000).fit(X, y)
+    mode = fit.coef_.ravel()
+    g = m.grad_log_posterior(mode)
+    assert np.max(np.abs(g)) < 1e-5 * np.max(np.abs(m.grad_log_posterior(np.zeros_like(mode))))
+    newton = mode + np.linalg.solve(m.metric(mode), g)
+    assert np.max(np.abs(newton - mode)) < 1e-6
+    assert m.log_posterior(mode) >= max(m.log_posterior(mode + 1e-3 * e) for e in np.eye(len(mode)))
+
+
 def test_logistic_metric_spd_and_is_neg_hessian():
     m, ts = _logistic()
     th = ts * 0.3
