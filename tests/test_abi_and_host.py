@@ -297,7 +297,7 @@ def test_bench_line_contract():
 
 def test_bench_line_contract_round2():
     """The line the default `bench.py` invocation printed on a B200 in round 2 (tests/golden/bench_line_r2.json, gpurun
-    r2be): the headline keys of the contract, the `configs` array with every BASELINE config at its own sharding, the
+    r2by): the headline keys of the contract, the `configs` array with every BASELINE config at its own sharding, the
     ESS phase, and the consistency of each entry's numbers."""
     import importlib.util
     import json
