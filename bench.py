@@ -1007,7 +1007,7 @@ def main():
     ap.add_argument("--burn", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-seconds-config", type=float, default=3.0)
-    ap.add_argument("--cpu-seconds-reference", type=float, default=110.0,
+    ap.add_argument("--cpu-seconds-reference", type=float, default=80.0,
                     help="--impl reference: seconds of sampling per chain in the timed region (split over --steps)")
     ap.add_argument("--ess-half-launches", type=int, default=400,
                     help="changepoint ESS phase: launches (of --iters MH steps) per half-window")
