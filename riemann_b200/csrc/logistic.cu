@@ -47,6 +47,9 @@
 namespace tc {
 int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
 int launch_plain_bf16(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st);
+int splits_used(int Kdim, int ksplit, bool bf16);
+int launch_single_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
+                         int64_t split_stride, bool bf16, cudaStream_t st);
 }
 
 namespace {
@@ -122,8 +125,9 @@ struct LogisticState {
     // mMALA, RMN_PREC_TF32_METRIC (all null / 0 otherwise)
     float* W;        // [K][Npad]    p(1-p) of the pending proposal, written by lg_eval_kernel
     float* KR;       // [NP][Npad]   x_ia x_ib for a >= b, pair index a(a+1)/2 + b
-    float* Gp;       // [K][NP]      packed lower triangle of the metric (likelihood part)
+    float* Gp;       // [gsplit][K][NP]  packed lower triangle of the metric (likelihood part), split-K partials
     int64_t Npad; int NP;
+    int gsplit;      // partial products of the metric GEMM (1 unless the chain shard leaves most SMs without a tile)
     int kr_bf16;     // W and KR are bf16 arrays (tf32x3 mode: the metric GEMM runs as kind::f16)
 };
 
@@ -131,7 +135,10 @@ struct LogisticState {
 __device__ __forceinline__ double metric_entry(const LogisticState& st, int64_t r, int a, int b) {
     if (st.Gp) {
         const int hi = a > b ? a : b, lo = a > b ? b : a;
-        return (double)st.Gp[r * st.NP + hi * (hi + 1) / 2 + lo];
+        const float* g = st.Gp + r * st.NP + hi * (hi + 1) / 2 + lo;
+        double v = (double)g[0];
+        for (int q = 1; q < st.gsplit; ++q) v += (double)g[(int64_t)q * st.K * st.NP];      // fixed order: deterministic
+        return v;
     }
     return st.Gm[r * (int64_t)st.d * st.d + a * st.d + b];
 }
@@ -1065,6 +1072,20 @@ struct LogisticSampler : SamplerImpl {
         st.kr_bf16 = bf16m ? 1 : 0;
         if (tf32m || tcx3) st.Npad = bf16m ? (st.N + 63) / 64 * 64 : (st.N + 31) / 32 * 32;
         if (tf32m) st.NP = (st.d * (st.d + 1) / 2 + 3) / 4 * 4;
+        st.gsplit = 1;
+        if (tf32m) {
+            // a small chain shard (BASELINE's 4,096 chains over 8 GPUs = 512 each: 4 x 9 tiles of 128 x 256) leaves most
+            // SMs without a tile while the contraction is N rows deep: split it so that about one wave of tiles exists
+            int dev = 0, sms = 148;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) {
+                sms = 148;
+                cudaGetLastError();
+            }
+            const int64_t tiles = ((st.K + tc::TM - 1) / tc::TM) * ((st.NP + tc::TN - 1) / tc::TN);
+            int want = (int)std::min<int64_t>(8, sms / std::max<int64_t>(tiles, 1));
+            if (const char* e = getenv("RMN_MMALA_KSPLIT")) want = atoi(e);
+            if (want > 1) st.gsplit = tc::splits_used((int)st.Npad, want, bf16m);
+        }
         if (tcx3) {
             fused = lgf::supported(st.d);
             if (fused) lgf::make_geometry(&fg, st.N, st.d, st.K);
@@ -1080,7 +1101,7 @@ struct LogisticSampler : SamplerImpl {
     }
     size_t kr_bytes() const { return align256((size_t)st.NP * st.Npad * (bf16m ? 2 : 4)); }
     size_t w_bytes() const { return align256((size_t)st.K * st.Npad * (bf16m ? 2 : 4)); }
-    size_t gp_bytes() const { return align256((size_t)st.K * st.NP * 4); }
+    size_t gp_bytes() const { return align256((size_t)st.gsplit * st.K * st.NP * 4); }
     size_t rowb() const { return align256((size_t)st.K * st.dp * 8); }
     size_t eval_smem() const { return eval_smem_bytes(st.ldt); }
     size_t metric_smem() const { return ((size_t)4 * st.ldt + 2 * BI * st.ldt + 4 * BI) * 8; }
@@ -1217,13 +1238,21 @@ struct LogisticSampler : SamplerImpl {
         launches += 2;
         return RMN_OK;
     }
+    // Gp = W KR^T on tcgen05 (bf16 operands in tf32x3 mode, single-pass TF32 in tf32-metric mode), split-K partials
+    // when the shard's tile count is small (metric_entry sums them)
+    int metric_gemm(cudaStream_t stream) {
+        if (st.gsplit > 1)
+            return tc::launch_single_splitk(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, st.gsplit,
+                                            (int64_t)st.K * st.NP, bf16m, stream);
+        return bf16m ? tc::launch_plain_bf16(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)
+                     : tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream);
+    }
     int eval(int fixed_slot, cudaStream_t stream) {
         if (tcx3) {
             if (int rc = eval_fused(fixed_slot, stream)) return rc;
             if (tf32m) {
                 ktimer.begin(bf16m ? "tf32x3_gemm_kernel<1,bf16>" : "tf32x3_gemm_kernel<1>", stream);
-                if (int rc = bf16m ? tc::launch_plain_bf16(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)
-                                   : tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
+                if (int rc = metric_gemm(stream)) return rc;
                 ktimer.end(stream);
                 launches++;
             }
@@ -1236,7 +1265,7 @@ struct LogisticSampler : SamplerImpl {
         if (time_eval) ktimer.end(stream);
         RMN_KERNEL_CHECK(); launches++;
         if (tf32m) {
-            if (int rc = tc::launch_plain_tf32(maps, st.K, st.NP, (int)st.Npad, st.Gp, st.NP, stream)) return rc;
+            if (int rc = metric_gemm(stream)) return rc;
             launches++;
         } else if (mmala) {
             ktimer.begin("lg_metric_kernel", stream);

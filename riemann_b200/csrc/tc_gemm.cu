@@ -339,6 +339,21 @@ int launch_plain_tf32(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C
 int launch_plain_bf16(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, cudaStream_t st) {
     return launch_common(maps, M, N, Kdim, C, ldc, st, 1, 1, 0, 0, TN, false, true);
 }
+// Single-pass products (TF32, or bf16 when `bf16`) with the contraction split into `ksplit` ranges, partial s at
+// C + s * split_stride: for outputs with far fewer tiles than SMs and a long contraction (the Fisher-metric GEMM of a
+// small chain shard).  splits_used() tells the caller how many partials the launch writes.
+int splits_used(int Kdim, int ksplit, bool bf16) {
+    const int tk = bf16 ? 64 : TK;
+    const int kb = Kdim / tk;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > kb) ksplit = kb > 0 ? kb : 1;
+    const int kbp = (kb + ksplit - 1) / ksplit;
+    return kbp > 0 ? (kb + kbp - 1) / kbp : 1;
+}
+int launch_single_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,
+                         int64_t split_stride, bool bf16, cudaStream_t st) {
+    return launch_common(maps, M, N, Kdim, C, ldc, st, 1, ksplit, split_stride, 0, TN, false, bf16);
+}
 // 3-pass product with the contraction split into `ksplit` ranges; returns the number of splits actually
 // used through *used (<= ksplit); partial s is at C + s * split_stride
 int launch_plain_splitk(const GemmMaps& maps, int64_t M, int N, int Kdim, float* C, int ldc, int ksplit,

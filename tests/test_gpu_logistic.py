@@ -236,6 +236,40 @@ def test_tf32_metric_is_a_deterministic_function_of_theta():
     assert runs[0][2].any()                                   # the chain moves
 
 
+@pytest.mark.parametrize("prec", ["tf32-metric", "tf32x3"])
+def test_metric_gemm_split_k_matches_the_unsplit_product(prec, monkeypatch):
+    """A small chain shard leaves most SMs without a tile of the Fisher-metric GEMM, so its contraction over the data
+    rows is split into partial products that the Cholesky kernel sums (RMN_MMALA_KSPLIT forces a count; the default
+    picks about one wave of tiles).  Same states, same noise: proposals with 1, 3 and the default number of partials
+    differ only by the fp32 summation order (<< the metric's own rounding), and every setting is deterministic."""
+    from oracle import riemann_port as port
+    from riemann_b200 import Sampler
+    from riemann_b200.proposals.hamiltonian import SimplifiedMMALA
+    N, d = 6000, 24
+    X, y, ts, pv = port.make_logistic_problem(N, d, seed=12)
+    dm, _ = _models(X, y, pv)
+    K = 200
+    rng = np.random.default_rng(6)
+    th0 = ts[None] + 0.05 * rng.standard_normal((K, d))
+    xi, u = rng.standard_normal((2, K, d)), np.ones((2, K))              # u = 1: nothing is accepted
+    out = {}
+    for split in ("1", "3", None, "3"):
+        if split is None:
+            monkeypatch.delenv("RMN_MMALA_KSPLIT", raising=False)
+        else:
+            monkeypatch.setenv("RMN_MMALA_KSPLIT", split)
+        s = Sampler(dm, SimplifiedMMALA(0.8, dm), th0, precision=prec)
+        ex = s.run_injected(xi=xi, u=u)
+        if split in out:
+            assert np.array_equal(out[split][0], ex["prop_theta"]) and np.array_equal(out[split][1], ex["logqratio"])
+        out[split] = (ex["prop_theta"].copy(), ex["logqratio"].copy())
+    step = np.linalg.norm(out["1"][0][0] - th0, axis=1)
+    for split in ("3", None):
+        assert np.all(np.linalg.norm(out[split][0][0] - out["1"][0][0], axis=1) < 1e-4 * step)
+        assert np.max(np.abs(out[split][1] - out["1"][1])) < 1e-3
+    assert np.any(out["3"][0] != out["1"][0])                            # the partials really were summed differently
+
+
 def test_tf32_metric_proposals_track_the_fp64_metric():
     """Same states, same noise: the proposal built with the TF32 metric differs from the fp64 one by the
     metric's rounding only (<~ 1e-3 relative in G, so ~1e-3 of the step), and its log-posterior -- still
