@@ -135,12 +135,35 @@ struct LogisticState {
 __device__ __forceinline__ double metric_entry(const LogisticState& st, int64_t r, int a, int b) {
     if (st.Gp) {
         const int hi = a > b ? a : b, lo = a > b ? b : a;
-        const float* g = st.Gp + r * st.NP + hi * (hi + 1) / 2 + lo;
-        double v = (double)g[0];
-        for (int q = 1; q < st.gsplit; ++q) v += (double)g[(int64_t)q * st.K * st.NP];      // fixed order: deterministic
-        return v;
+        return (double)st.Gp[r * st.NP + hi * (hi + 1) / 2 + lo];
     }
     return st.Gm[r * (int64_t)st.d * st.d + a * st.d + b];
+}
+
+// Lw[a][b] = likelihood part of chain r's metric + the prior precision on the diagonal (one warp).  The split-K partials
+// of the metric GEMM are summed here, in a fixed order; the unsplit case keeps its own loop (its gathers stay
+// independent of each other, so the compiler overlaps them).
+__device__ __forceinline__ void fill_metric(const LogisticState& st, int64_t r, double* Lw, int d, int ldl, double pvinv, int lane) {
+    if (st.Gp && st.gsplit > 1) {
+        const int64_t stride = st.K * (int64_t)st.NP;
+        for (int q = lane; q < d * d; q += 32) {
+            const int a = q / d, b = q % d;
+            const int hi = a > b ? a : b, lo = a > b ? b : a;
+            const float* g = st.Gp + r * st.NP + hi * (hi + 1) / 2 + lo;
+            float part[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) part[k] = (k < st.gsplit) ? g[k * stride] : 0.0f;       // gsplit <= 8 (constructor)
+            double v = (double)part[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) v += (double)part[k];
+            Lw[a * ldl + b] = v + ((a == b) ? pvinv : 0.0);
+        }
+        return;
+    }
+    for (int q = lane; q < d * d; q += 32) {
+        const int a = q / d, b = q % d;
+        Lw[a * ldl + b] = metric_entry(st, r, a, b) + ((a == b) ? pvinv : 0.0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -688,10 +711,7 @@ lg_finish_propose_kernel(LogisticState st, LgStep sp) {
             else lqr = 0.0;                                               // randomwalk.py:26
         } else {
             // geometry of the proposal: L' = chol(G'), logdet', nat' = G'^-1 grad'
-            for (int q = lane; q < d * d; q += 32) {
-                const int a = q / d, b = q % d;
-                Lw[a * ldl + b] = metric_entry(st, r, a, b) + ((a == b) ? pvinv : 0.0);
-            }
+            fill_metric(st, r, Lw, d, ldl, pvinv, lane);
             __syncwarp();
             const double ld = warp_cholesky(Lw, d, ldl, lane);
             for (int j = lane; j < d; j += 32) v1[j] = grp[j];
@@ -903,7 +923,7 @@ lg_adopt_kernel(LogisticState st) {
         const int ldl = LDL(d);
         double* Lw = sm + (size_t)wib * (d * ldl + dp);
         double* v1 = Lw + d * ldl;
-        for (int q = lane; q < d * d; q += 32) Lw[(q / d) * ldl + q % d] = metric_entry(st, r, q / d, q % d) + ((q / d == q % d) ? pvinv : 0.0);
+        fill_metric(st, r, Lw, d, ldl, pvinv, lane);
         __syncwarp();
         const double ld = warp_cholesky(Lw, d, ldl, lane);
         for (int j = lane; j < d; j += 32) v1[j] = gr[j];
@@ -1083,7 +1103,7 @@ struct LogisticSampler : SamplerImpl {
             }
             const int64_t tiles = ((st.K + tc::TM - 1) / tc::TM) * ((st.NP + tc::TN - 1) / tc::TN);
             int want = (int)std::min<int64_t>(8, sms / std::max<int64_t>(tiles, 1));
-            if (const char* e = getenv("RMN_MMALA_KSPLIT")) want = atoi(e);
+            if (const char* e = getenv("RMN_MMALA_KSPLIT")) want = std::min(atoi(e), 8);       // fill_metric sums at most 8
             if (want > 1) st.gsplit = tc::splits_used((int)st.Npad, want, bf16m);
         }
         if (tcx3) {
