@@ -330,6 +330,25 @@ def test_bench_line_contract_round2():
     assert tot["logistic_mala_f64"] == 8192 and tot["logistic_mmala_tf32x3"] == 4096 and tot["gauss2d_rw_k1"] == 1
 
 
+def test_reference_arm_chains_continue_across_steps():
+    """bench.py --impl reference: every core's chain of the UNMODIFIED reference runs through warm-up and timed segments
+    without restarting, so the tau / ESS window is the whole timed region -- the window is the sum of the timed
+    segments' steps, and the per-step throughputs average to the line's value."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    b = importlib.import_module("bench")              # by its real name: the spawned workers unpickle bench._cpu_worker
+    vals, cb = b.cpu_reference_segments("gauss2d_rw", 1, 3, 0.4, cores=2)
+    assert cb["kind"] == "reference" and cb["cores"] == 2 and len(vals) == 3 and all(v > 0 for v in vals)
+    e = cb["ess"]
+    assert e["chains"] == 2 and e["steps_per_chain"] >= 3 * 2000          # three timed segments of whole 2,000-step chunks
+    assert min(vals) <= cb["value"] <= max(vals)
+    assert "3 timed segments" in cb["sample"] and "after 1 untimed" in cb["sample"]
+    assert ("min_ess_per_sec" in cb) and (cb["min_ess_per_sec"] is not None or "min_ess_per_sec_unreliable" in cb)
+
+
 def test_split_rhat_sees_a_common_drift():
     """summarize_split: chains that all drift the same way have R-hat ~ 1 over the whole window (every chain mean
     is the same) but split-R-hat > 1; stationary AR(1) chains give ~1 and the right tau either way."""
