@@ -231,6 +231,23 @@ def test_diagnostics_allreduce_two_ranks_gloo(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches `bench.py --impl reference --gpus N` like the engine arm (torchrun, one process per GPU):
+    rank 0 alone runs the CPU sampler and prints the line, the other ranks exit 0 without work and without output."""
+    import json
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1",
+                        "--cpu-seconds-reference", "1.5", "--workload", "gauss2d_rw"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
 def test_sokal_tau_matches_ar1_and_oracle():
     """riemann_b200.diagnostics (emcee-style integrated autocorrelation time) on AR(1) chains with the
     analytic tau = (1 + phi) / (1 - phi), against oracle/ess.py, and against the engine's moment-based
